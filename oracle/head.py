@@ -1,0 +1,141 @@
+"""fp32 CPU restatement of the tag-decoder head, confidence sort, threshold and focal loss.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  **Pinned**: every function
+here is checked against outputs of the reference's own classes (imported from
+``/root/reference`` through a stub ``diffusers`` module by
+``tests/golden/make_golden.py``) stored in ``tests/golden/head_golden.pt``.
+
+Functional style: each function takes the reference ``state_dict`` (keys per
+SURVEY.md Appendix B) so that one set of tensors drives oracle and CUDA path.
+
+Reference lines followed:
+  * SpatialAttention.forward ............... modules.py:36-47
+  * feature_compress ....................... modules.py:377-382 (used :437)
+  * MultiHeadSelfAttention.forward ......... modules.py:66-91
+  * classifier ............................. modules.py:401-418 (used :462)
+  * get_confidence ......................... modules.py:470-475
+  * ClassificationDecoder (--no_attention) . modules.py:303-356
+  * threshold loop ......................... infer_full.py:109-124
+  * FocalLoss.forward ...................... improved_losses.py:47-56
+All in eval mode (dropout identity, BatchNorm running statistics).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def spatial_attention(sd: dict, x: torch.Tensor, prefix="spatial_attention.") -> torch.Tensor:
+    w1 = sd[prefix + "channel_att.0.weight"]  # [C/8, C, 1, 1]
+    w2 = sd[prefix + "channel_att.2.weight"]  # [C, C/8, 1, 1]
+    w7 = sd[prefix + "spatial_att.0.weight"]  # [1, 2, 7, 7]
+
+    def mlp(v):
+        return F.conv2d(F.relu(F.conv2d(v, w1)), w2)
+
+    avg = x.mean(dim=(2, 3), keepdim=True)
+    mx = x.amax(dim=(2, 3), keepdim=True)
+    x = x * torch.sigmoid(mlp(avg) + mlp(mx))
+    m = torch.cat([x.mean(dim=1, keepdim=True), x.amax(dim=1, keepdim=True)], dim=1)
+    return x * torch.sigmoid(F.conv2d(m, w7, padding=3))
+
+
+def feature_compress(sd: dict, x: torch.Tensor, prefix="feature_compress.") -> torch.Tensor:
+    y = F.conv2d(x, sd[prefix + "0.weight"], sd[prefix + "0.bias"], padding=1)
+    y = F.batch_norm(
+        y,
+        sd[prefix + "1.running_mean"],
+        sd[prefix + "1.running_var"],
+        sd[prefix + "1.weight"],
+        sd[prefix + "1.bias"],
+        training=False,
+        eps=1e-5,
+    )
+    return F.adaptive_avg_pool2d(F.relu(y), (8, 8))
+
+
+def self_attention(sd: dict, x: torch.Tensor, heads: int = 8, prefix="self_attention_post.") -> torch.Tensor:
+    b, c, h, w = x.shape
+    n, hd = h * w, c // heads
+    xf = x.reshape(b, c, n).transpose(1, 2)
+    t = F.layer_norm(xf, (c,), sd[prefix + "norm.weight"], sd[prefix + "norm.bias"], eps=1e-5)
+
+    def proj(name):
+        y = F.linear(t, sd[prefix + name + ".weight"], sd[prefix + name + ".bias"])
+        return y.reshape(b, n, heads, hd).transpose(1, 2)
+
+    q, k, v = proj("q_proj"), proj("k_proj"), proj("v_proj")
+    p = torch.softmax(torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(hd), dim=-1)
+    o = torch.matmul(p, v).transpose(1, 2).reshape(b, n, c)
+    o = F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"]) + xf
+    return o.transpose(1, 2).reshape(b, c, h, w)
+
+
+def classifier(sd: dict, f: torch.Tensor, prefix="classifier.") -> torch.Tensor:
+    for lin, ln in ((0, 1), (4, 5), (8, 9)):
+        f = F.linear(f, sd[f"{prefix}{lin}.weight"], sd[f"{prefix}{lin}.bias"])
+        f = F.relu(F.layer_norm(f, (f.shape[-1],), sd[f"{prefix}{ln}.weight"], sd[f"{prefix}{ln}.bias"], eps=1e-5))
+    return F.linear(f, sd[prefix + "12.weight"], sd[prefix + "12.bias"])
+
+
+def attention_decoder_logits(sd: dict, latent: torch.Tensor, heads: int = 8,
+                             use_spatial_attention=True, use_self_attention=True) -> torch.Tensor:
+    """AttentionClassificationDecoder.forward (modules.py:424-468), cross-attention off."""
+    x = latent
+    if use_spatial_attention:
+        x = spatial_attention(sd, x)
+    x = feature_compress(sd, x)
+    if use_self_attention:
+        x = self_attention(sd, x, heads)
+    return classifier(sd, x.reshape(x.shape[0], -1))
+
+
+def plain_decoder_logits(sd: dict, latent: torch.Tensor) -> torch.Tensor:
+    """ClassificationDecoder.forward (modules.py:335-349), use_adaptive_pooling=True."""
+    f = F.adaptive_avg_pool2d(latent, (4, 4)).reshape(latent.shape[0], -1)
+    for lin, ln in ((0, 1), (4, 5)):
+        f = F.linear(f, sd[f"classifier.{lin}.weight"], sd[f"classifier.{lin}.bias"])
+        f = F.layer_norm(f, (f.shape[-1],), sd[f"classifier.{ln}.weight"], sd[f"classifier.{ln}.bias"], eps=1e-5)
+        f = F.leaky_relu(f, 0.2)
+    return F.linear(f, sd["classifier.8.weight"], sd["classifier.8.bias"])
+
+
+def get_confidence(logits: torch.Tensor):
+    """modules.py:470-475: sigmoid then descending sort along tags."""
+    conf = torch.sigmoid(logits)
+    return torch.sort(conf, descending=True)
+
+
+def threshold_tags(sorted_conf: torch.Tensor, indices: torch.Tensor, thr: float):
+    """infer_full.py:109-124 for one image (1-D inputs): tags with conf >= thr, in sorted
+    order, plus count / max / mean-of-top-5 with the reference's 4-decimal rounding."""
+    conf = [float(c) for c in sorted_conf.tolist()]
+    idx = [int(i) for i in indices.tolist()]
+    picked = [(i, float(f"{c:.4f}")) for c, i in zip(conf, idx) if c >= thr]
+    return {
+        "predicted": picked,
+        "total_tags_above_threshold": len(picked),
+        "max_confidence": float(f"{max(conf):.4f}"),
+        "avg_confidence_top5": float(f"{sum(conf[:5]) / 5:.4f}"),
+    }
+
+
+def focal_loss(logits: torch.Tensor, targets: torch.Tensor, alpha=1.0, gamma=2.0, reduction="mean"):
+    """improved_losses.py:47-56."""
+    bce = F.binary_cross_entropy_with_logits(logits, targets, reduction="none")
+    pt = torch.exp(-bce)
+    fl = alpha * (1.0 - pt) ** gamma * bce
+    if reduction == "mean":
+        return fl.mean()
+    if reduction == "sum":
+        return fl.sum()
+    return fl
+
+
+def focal_loss_grad(logits: torch.Tensor, targets: torch.Tensor, alpha=1.0, gamma=2.0):
+    """d mean(focal)/d logits via autograd on the restatement above (for the fused kernel)."""
+    x = logits.detach().clone().requires_grad_(True)
+    focal_loss(x, targets, alpha, gamma).backward()
+    return x.grad
