@@ -1,0 +1,174 @@
+/* vae_tagger_b200 -- C ABI of the B200-native encode+tag hot path.
+ *
+ * The reference (spawner1145/vae-tagger) has no FFI: its boundary for this path is the
+ * Python module surface.  This header is the C-ABI that surface is backed by
+ * in this repo; every entry point names the reference interface it replaces.  The Python
+ * side (vae_tagger_b200/_native.py) binds it with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; vt_last_error() then
+ *     returns a thread-local, NUL-terminated description.  No exceptions cross the ABI.
+ *   - plain pointers and sizes only.  "device pointer" = CUDA device memory of the
+ *     context's device, caller-owned.  Workspace is owned by the context.
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*; NULL =
+ *     legacy default stream); no hidden synchronisation except where stated (host variants).
+ *   - one context per device / per rank; a context is not thread-safe.
+ *   - tensors are fp32, PyTorch layouts (NCHW activations, OIHW conv weights, [out][in]
+ *     linear weights) at the boundary; the NHWC bf16 layout used internally never leaks.
+ */
+#ifndef VAE_TAGGER_B200_H
+#define VAE_TAGGER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VT_ABI_VERSION 1
+
+typedef struct vt_ctx vt_ctx;
+
+/* precision of the encoder contraction path */
+#define VT_PREC_BF16 0 /* tcgen05 implicit GEMM, bf16 operands, fp32 accumulate (TMEM) */
+#define VT_PREC_FP32 1 /* FFMA verification mode (north star "fp32 mode", rel L2 <= 1e-4) */
+
+/* image input formats of vt_encode */
+#define VT_IN_F32_NCHW 0 /* [B,3,H,W] fp32 already normalised to [-1,1] (modules.py:136-140) */
+#define VT_IN_U8_NHWC 1  /* [B,H,W,3] uint8; (u/255-0.5)/0.5 is fused into the conv_in gather */
+
+const char* vt_last_error(void);
+int vt_abi_version(void);
+
+int vt_ctx_create(int device, vt_ctx** out);
+int vt_ctx_destroy(vt_ctx* ctx);
+
+/* ---------------------------------------------------------------- encoder (FLUX AutoencoderKL)
+ * Replaces: diffusers AutoencoderKL(**config) constructed at diffusers_vae_loader.py:8-35 and
+ * its load_state_dict at :44. */
+typedef struct vt_encoder_config {
+    int in_channels;           /* 3 */
+    int num_blocks;            /* 4 */
+    int block_out_channels[8]; /* 128,256,512,512 */
+    int layers_per_block;      /* 2 */
+    int norm_num_groups;       /* 32 */
+    int latent_channels;       /* 16 */
+    int mid_block_add_attention; /* 1 */
+    int has_scaling_factor;    /* hasattr(config,'scaling_factor') diffusers_vae_loader.py:81 */
+    int has_shift_factor;      /* :83 */
+    float scaling_factor;      /* 0.3611 */
+    float shift_factor;        /* 0.1159 */
+} vt_encoder_config;
+
+int vt_encoder_configure(vt_ctx* ctx, const vt_encoder_config* cfg);
+/* name = diffusers state-dict key below "encoder." (SURVEY.md Appendix B), e.g.
+ * "down_blocks.0.resnets.0.conv1.weight"; data = fp32, host or device pointer, PyTorch layout */
+int vt_encoder_set_param(vt_ctx* ctx, const char* name, const float* data, const int64_t* shape, int ndim);
+/* checks that every parameter is present and repacks for the kernels.  Call again after
+ * changing parameters. */
+int vt_encoder_finalize(vt_ctx* ctx);
+
+typedef struct vt_encode_args {
+    const void* images; /* device pointer, format in_fmt */
+    int in_fmt;
+    int batch, height, width; /* height, width multiples of 8 (bf16 path: of 16 at every level is fastest) */
+    int precision;            /* VT_PREC_* */
+    int sample;               /* 0: latent_dist.mode() (diffusers_vae_loader.py:80); 1: .sample() (:74) */
+    int apply_scale_shift;    /* 1: DiffusersVAEWrapper.encode semantics (mode*scale+shift, :80-84) */
+    uint64_t seed;            /* sample noise stream when noise == NULL */
+    const float* noise;       /* optional device [B,LC,H/8,W/8] standard normal (exact-parity sampling) */
+    float* latent;            /* out, device [B,LC,H/8,W/8] fp32 NCHW; may be NULL */
+    float* mean;              /* out, optional: DiagonalGaussianDistribution.mean */
+    float* logvar;            /* out, optional: clamped logvar */
+    int micro_batch;          /* images per internal pass; 0 = library default */
+    void* stream;
+} vt_encode_args;
+
+/* Replaces: DiffusersVAEWrapper.encode (diffusers_vae_loader.py:78-86) and
+ * AutoencoderKL.encode(x).latent_dist.{mode,sample,mean,logvar} (:73-74, :79-80). */
+int vt_encode(vt_ctx* ctx, const vt_encode_args* args);
+
+/* ---------------------------------------------------------------- tag head
+ * Replaces: AttentionClassificationDecoder / ClassificationDecoder (modules.py:303-475). */
+#define VT_HEAD_ATTENTION 0 /* AttentionClassificationDecoder */
+#define VT_HEAD_PLAIN 1     /* ClassificationDecoder (--no_attention) */
+typedef struct vt_head_config {
+    int kind;
+    int latent_channels; /* 16 */
+    int num_classes;
+    int use_spatial_attention;
+    int use_self_attention;
+    int attention_heads; /* 8 */
+} vt_head_config;
+int vt_head_configure(vt_ctx* ctx, const vt_head_config* cfg);
+/* name = reference state-dict key, e.g. "classifier.12.weight" */
+int vt_head_set_param(vt_ctx* ctx, const char* name, const float* data, const int64_t* shape, int ndim);
+int vt_head_finalize(vt_ctx* ctx);
+
+typedef struct vt_tag_args {
+    const float* latent; /* device [B,LC,h,w] fp32 NCHW */
+    int batch, lat_h, lat_w;
+    float threshold;      /* infer_full.py:114 uses conf >= threshold */
+    float* logits;        /* out, optional device [B,T]: decoder(latent) (modules.py:424-468) */
+    float* probs;         /* out, optional device [B,T]: sigmoid(logits) in tag order */
+    float* conf_sorted;   /* out, optional device [B,T]: get_confidence()[0] (modules.py:470-475) */
+    int64_t* idx_sorted;  /* out, optional device [B,T]: get_confidence()[1] */
+    int32_t* count;       /* out, optional device [B]: number of tags with conf >= threshold */
+    void* stream;
+} vt_tag_args;
+int vt_tag(vt_ctx* ctx, const vt_tag_args* args);
+
+/* ---------------------------------------------------------------- end-to-end, host buffers
+ * Replaces the per-image loop of infer_full.py:95-124 for a whole batch: H2D of the images,
+ * encode (mode, scale/shift), tag, D2H of the sorted confidences / indices / counts.  Host
+ * pointers should be pinned; the call synchronises the stream before returning. */
+typedef struct vt_infer_host_args {
+    const void* images_host; /* format in_fmt */
+    int in_fmt;
+    int batch, height, width;
+    int precision;
+    float threshold;
+    float* conf_sorted_host;  /* [B,T] */
+    int64_t* idx_sorted_host; /* [B,T] */
+    int32_t* count_host;      /* [B] */
+    float* latent_host;       /* optional [B,LC,H/8,W/8] */
+    int micro_batch;
+    void* stream;
+} vt_infer_host_args;
+int vt_infer_host(vt_ctx* ctx, const vt_infer_host_args* args);
+
+/* ---------------------------------------------------------------- focal loss (training step)
+ * Replaces FocalLoss.forward (improved_losses.py:47-56) and its autograd backward:
+ * loss_sum += sum(alpha*(1-pt)^gamma*bce); grad = grad_scale * d(sum)/d(logits). */
+int vt_focal_loss(vt_ctx* ctx, const float* logits, const float* targets, int64_t n, float alpha, float gamma,
+                  float grad_scale, float* loss_sum /* device, 1 float, accumulated */,
+                  float* grad /* device [n], optional */, void* stream);
+
+/* ---------------------------------------------------------------- accounting
+ * Kernel classes: 0 implicit GEMM (tcgen05), 1 GroupNorm, 2 conv_in gather, 3 softmax,
+ * 4 latent, 5 head, 6 fp32-mode contraction, 7 misc. */
+#define VT_NUM_KERNEL_CLASSES 8
+int vt_profile_enable(vt_ctx* ctx, int timing);
+/* out[class][4] = {launches, milliseconds (timing mode only), flops, bytes}; synchronises the device */
+int vt_profile_read(vt_ctx* ctx, double* out, int reset);
+
+/* ---------------------------------------------------------------- single-op entry points
+ * Used by the parity tests to pin each kernel family against the oracle.  Activations and
+ * weights cross the boundary in fp32 PyTorch layouts and are repacked internally. */
+int vt_op_conv2d(vt_ctx* ctx, const float* x /*[N,Cin,H,W]*/, const float* w /*[Cout,Cin,k,k]*/,
+                 const float* bias /*[Cout] or NULL*/, const float* residual /*[N,Cout,Ho,Wo] or NULL*/,
+                 const float* sc_x /*[N,Cs,Ho,Wo] or NULL*/, const float* sc_w /*[Cout,Cs,1,1] or NULL*/, int N,
+                 int Cin, int H, int W, int Cout, int ksize, int stride, int Cs, int precision,
+                 float* out /*[N,Cout,Ho,Wo]*/, double* stats /*[N,32,2] (sum,sumsq) or NULL*/, void* stream);
+int vt_op_gemm_nt(vt_ctx* ctx, const float* A /*[batch,M,K]*/, const float* B /*[batch or 1,N,K]*/,
+                  const float* bias, int batch, int M, int N, int K, int b_batched, float alpha, int precision,
+                  float* out /*[batch,M,N]*/, void* stream);
+int vt_op_group_norm(vt_ctx* ctx, const float* x /*[N,C,H,W]*/, const float* gamma, const float* beta, int N, int C,
+                     int H, int W, int groups, float eps, int silu, int precision, float* out, void* stream);
+int vt_op_softmax_rows(vt_ctx* ctx, const float* s, int64_t rows, int cols, int precision, float* out,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAE_TAGGER_B200_H */

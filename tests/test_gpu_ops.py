@@ -1,0 +1,135 @@
+"""Single-kernel parity: each CUDA kernel family through the C-ABI op entry points against a
+plain PyTorch fp32 reference of the same op (floating-point kernels; tolerances stated per test).
+
+bf16 mode: operands are rounded to bf16, accumulation is fp32 in TMEM -> the reference is computed
+from bf16-rounded operands in fp32, leaving only accumulation-order error (<= 2e-3 relative to the
+output scale is a loose bound; observed ~1e-6).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from vae_tagger_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def r16(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("batch,M,Nn,K,b_batched", [
+    (1, 128, 128, 64, 0), (1, 256, 256, 512, 0), (2, 192, 1536, 512, 0), (3, 64, 32, 128, 1),
+    (2, 320, 448, 1024, 1), (1, 1024, 4096, 512, 1),
+])
+def test_gemm_bf16(ctx, batch, M, Nn, K, b_batched):
+    g = torch.Generator().manual_seed(M + Nn + K)
+    A = torch.randn(batch, M, K, generator=g)
+    B = torch.randn(batch if b_batched else 1, Nn, K, generator=g)
+    bias = torch.randn(Nn, generator=g)
+    out = ctx.op_gemm_nt(A, B if b_batched else B[0], bias, alpha=0.5, precision=N.PREC_BF16).cpu()
+    ref = 0.5 * torch.matmul(r16(A), r16(B).transpose(1, 2)) + bias
+    assert rel(out, ref) < 2e-5, (rel(out, ref), (out - ref).abs().max().item())
+
+
+@pytest.mark.parametrize("batch,M,Nn,K", [(1, 70, 50, 36), (2, 128, 64, 512)])
+def test_gemm_fp32(ctx, batch, M, Nn, K):
+    g = torch.Generator().manual_seed(7)
+    A = torch.randn(batch, M, K, generator=g)
+    B = torch.randn(batch, Nn, K, generator=g)
+    out = ctx.op_gemm_nt(A, B, None, alpha=1.0, precision=N.PREC_FP32).cpu()
+    ref = torch.matmul(A, B.transpose(1, 2))
+    assert rel(out, ref) < 2e-6
+
+
+CONV_CASES = [
+    # N, Cin, H, W, Cout, k, stride, residual, shortcut Cs
+    (1, 128, 16, 16, 128, 3, 1, False, 0),
+    (2, 128, 24, 40, 128, 3, 1, True, 0),
+    (1, 128, 32, 32, 256, 3, 1, False, 0),
+    (1, 256, 16, 16, 256, 3, 1, False, 128),
+    (2, 512, 8, 8, 512, 3, 1, True, 0),
+    (1, 256, 16, 24, 512, 3, 1, False, 256),
+    (1, 128, 32, 32, 128, 3, 2, False, 0),
+    (2, 256, 16, 48, 256, 3, 2, False, 0),
+    (1, 512, 16, 16, 32, 3, 1, False, 0),
+    (1, 64, 16, 16, 128, 1, 1, False, 0),
+    (1, 512, 72, 8, 512, 3, 1, True, 0),
+]
+
+
+def conv_ref(x, w, b, res, scx, scw, stride):
+    if stride == 2:
+        y = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)
+    else:
+        y = F.conv2d(x, w, b, padding=w.shape[-1] // 2)
+    if scx is not None:
+        y = y + F.conv2d(scx, scw)
+    if res is not None:
+        y = y + res
+    return y
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("prec", [N.PREC_BF16, N.PREC_FP32])
+def test_conv(ctx, case, prec):
+    n, cin, h, w_, cout, k, stride, use_res, cs = case
+    g = torch.Generator().manual_seed(sum(case[:7]))
+    x = torch.randn(n, cin, h, w_, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ho, wo = (h, w_) if stride == 1 else (h // 2, w_ // 2)
+    res = torch.randn(n, cout, ho, wo, generator=g) if use_res else None
+    scx = torch.randn(n, cs, ho, wo, generator=g) if cs else None
+    scw = torch.randn(cout, cs, 1, 1, generator=g) / cs ** 0.5 if cs else None
+    want_stats = cout in (128, 256, 512)
+    r = ctx.op_conv2d(x, w, b, res, scx, scw, stride=stride, precision=prec, want_stats=want_stats)
+    out, stats = (r if want_stats else (r, None))
+    out = out.cpu()
+    if prec == N.PREC_BF16:
+        ref = conv_ref(r16(x), r16(w), b, r16(res) if use_res else None, r16(scx) if cs else None,
+                       r16(scw) if cs else None, stride)
+        tol = 3e-5
+    else:
+        ref = conv_ref(x, w, b, res, scx, scw, stride)
+        tol = 3e-6
+    assert rel(out, ref) < tol, (rel(out, ref), (out - ref).abs().max().item())
+    if stats is not None:
+        # fused GroupNorm statistics: (sum, sumsq) over (pixels, channels of the group), 32 groups
+        grp = ref.double().reshape(n, 32, -1)
+        want = torch.stack([grp.sum(-1), (grp * grp).sum(-1)], dim=-1)
+        got = stats.cpu()
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-3 * grp.shape[-1] ** 0.5), (got - want).abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 16, 24), (1, 256, 8, 8), (3, 512, 12, 4)])
+@pytest.mark.parametrize("silu", [False, True])
+@pytest.mark.parametrize("prec", [N.PREC_BF16, N.PREC_FP32])
+def test_group_norm(ctx, shape, silu, prec):
+    g = torch.Generator().manual_seed(shape[1])
+    x = torch.randn(*shape, generator=g) * 2 + 0.7
+    gamma = torch.randn(shape[1], generator=g)
+    beta = torch.randn(shape[1], generator=g)
+    out = ctx.op_group_norm(x, gamma, beta, silu=silu, precision=prec).cpu()
+    xin = r16(x) if prec == N.PREC_BF16 else x
+    ref = F.group_norm(xin, 32, gamma, beta, eps=1e-6)
+    if silu:
+        ref = F.silu(ref)
+    # bf16 mode rounds the result to bf16: half an ulp = 2^-9 relative
+    tol = 4e-3 if prec == N.PREC_BF16 else 2e-6
+    assert rel(out, ref) < tol, rel(out, ref)
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 64), (3, 1000), (4, 4096), (2, 16384), (2, 20000)])
+@pytest.mark.parametrize("prec", [N.PREC_BF16, N.PREC_FP32])
+def test_softmax_rows(ctx, rows, cols, prec):
+    g = torch.Generator().manual_seed(cols)
+    s = torch.randn(rows, cols, generator=g) * 4
+    out = ctx.op_softmax_rows(s, precision=prec).cpu()
+    ref = torch.softmax(s, dim=-1)
+    tol = 4e-3 if prec == N.PREC_BF16 else 2e-6
+    assert rel(out, ref) < tol, rel(out, ref)

@@ -1,0 +1,395 @@
+"""ctypes binding of ``include/vae_tagger_b200.h`` (the C-ABI of the encode+tag path).
+
+There is NO fallback: if ``_lib/libvt_b200.so`` is missing or a call fails, a
+``NativeError`` is raised.  Tensors cross the boundary as raw device pointers
+(``tensor.data_ptr()``) plus sizes; the stream is torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import torch
+
+from . import _build
+
+PREC_BF16, PREC_FP32 = 0, 1
+IN_F32_NCHW, IN_U8_NHWC = 0, 1
+HEAD_ATTENTION, HEAD_PLAIN = 0, 1
+NUM_KERNEL_CLASSES = 8
+KERNEL_CLASS_NAMES = ["igemm_tcgen05", "group_norm", "conv_in_gather", "softmax", "latent", "head", "fp32_contract", "misc"]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class EncoderConfig(C.Structure):
+    _fields_ = [
+        ("in_channels", C.c_int), ("num_blocks", C.c_int), ("block_out_channels", C.c_int * 8),
+        ("layers_per_block", C.c_int), ("norm_num_groups", C.c_int), ("latent_channels", C.c_int),
+        ("mid_block_add_attention", C.c_int), ("has_scaling_factor", C.c_int), ("has_shift_factor", C.c_int),
+        ("scaling_factor", C.c_float), ("shift_factor", C.c_float),
+    ]
+
+
+class EncodeArgs(C.Structure):
+    _fields_ = [
+        ("images", C.c_void_p), ("in_fmt", C.c_int), ("batch", C.c_int), ("height", C.c_int), ("width", C.c_int),
+        ("precision", C.c_int), ("sample", C.c_int), ("apply_scale_shift", C.c_int), ("seed", C.c_uint64),
+        ("noise", C.c_void_p), ("latent", C.c_void_p), ("mean", C.c_void_p), ("logvar", C.c_void_p),
+        ("micro_batch", C.c_int), ("stream", C.c_void_p),
+    ]
+
+
+class HeadConfig(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("latent_channels", C.c_int), ("num_classes", C.c_int),
+        ("use_spatial_attention", C.c_int), ("use_self_attention", C.c_int), ("attention_heads", C.c_int),
+    ]
+
+
+class TagArgs(C.Structure):
+    _fields_ = [
+        ("latent", C.c_void_p), ("batch", C.c_int), ("lat_h", C.c_int), ("lat_w", C.c_int), ("threshold", C.c_float),
+        ("logits", C.c_void_p), ("probs", C.c_void_p), ("conf_sorted", C.c_void_p), ("idx_sorted", C.c_void_p),
+        ("count", C.c_void_p), ("stream", C.c_void_p),
+    ]
+
+
+class InferHostArgs(C.Structure):
+    _fields_ = [
+        ("images_host", C.c_void_p), ("in_fmt", C.c_int), ("batch", C.c_int), ("height", C.c_int), ("width", C.c_int),
+        ("precision", C.c_int), ("threshold", C.c_float), ("conf_sorted_host", C.c_void_p),
+        ("idx_sorted_host", C.c_void_p), ("count_host", C.c_void_p), ("latent_host", C.c_void_p),
+        ("micro_batch", C.c_int), ("stream", C.c_void_p),
+    ]
+
+
+# every symbol include/vae_tagger_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "vt_last_error": (C.c_char_p, []),
+    "vt_abi_version": (C.c_int, []),
+    "vt_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "vt_ctx_destroy": (C.c_int, [_P]),
+    "vt_encoder_configure": (C.c_int, [_P, C.POINTER(EncoderConfig)]),
+    "vt_encoder_set_param": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "vt_encoder_finalize": (C.c_int, [_P]),
+    "vt_encode": (C.c_int, [_P, C.POINTER(EncodeArgs)]),
+    "vt_head_configure": (C.c_int, [_P, C.POINTER(HeadConfig)]),
+    "vt_head_set_param": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "vt_head_finalize": (C.c_int, [_P]),
+    "vt_tag": (C.c_int, [_P, C.POINTER(TagArgs)]),
+    "vt_infer_host": (C.c_int, [_P, C.POINTER(InferHostArgs)]),
+    "vt_focal_loss": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, _P, _P, _P]),
+    "vt_profile_enable": (C.c_int, [_P, C.c_int]),
+    "vt_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
+    "vt_op_conv2d": (C.c_int, [_P, _P, _P, _P, _P, _P, _P] + [C.c_int] * 9 + [_P, _P, _P]),
+    "vt_op_gemm_nt": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, _P, _P]),
+    "vt_op_group_norm": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_int, _P, _P]),
+    "vt_op_softmax_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load_library() -> C.CDLL:
+    """Load the C-ABI library (no CUDA call is made).  Raises NativeError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise NativeError(
+            f"{path} is missing: the sm_100a extension is not built (run `python -m vae_tagger_b200._build`); "
+            "there is no CPU or PyTorch fallback for the encode+tag path")
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.vt_abi_version() != 1:
+        raise NativeError(f"ABI version mismatch: library {lib.vt_abi_version()}, binding 1")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = load_library().vt_last_error()
+        raise NativeError(f"vae_tagger_b200 native call failed ({rc}): {msg.decode(errors='replace') if msg else '?'}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32c(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class Context:
+    """One native context per CUDA device (per rank)."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise NativeError("vae_tagger_b200 needs a CUDA device (B200, sm_100a); torch.cuda.is_available() is False")
+        self.lib = load_library()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)  # make sure the primary context exists
+            h = C.c_void_p()
+            _check(self.lib.vt_ctx_create(self.device.index, C.byref(h)))
+        self.h = h
+        self.latent_channels = 16
+        self.num_blocks = 4
+        self.num_classes = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vt_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ encoder
+    def configure_encoder(self, cfg: dict):
+        ec = EncoderConfig()
+        chans = list(cfg.get("block_out_channels", [128, 256, 512, 512]))
+        ec.in_channels = int(cfg.get("in_channels", 3))
+        ec.num_blocks = len(chans)
+        for i, ch in enumerate(chans):
+            ec.block_out_channels[i] = int(ch)
+        ec.layers_per_block = int(cfg.get("layers_per_block", 2))
+        ec.norm_num_groups = int(cfg.get("norm_num_groups", 32))
+        ec.latent_channels = int(cfg.get("latent_channels", 16))
+        ec.mid_block_add_attention = int(bool(cfg.get("mid_block_add_attention", True)))
+        ec.has_scaling_factor = int(cfg.get("scaling_factor") is not None)
+        ec.has_shift_factor = int(cfg.get("shift_factor") is not None)
+        ec.scaling_factor = float(cfg.get("scaling_factor") or 1.0)
+        ec.shift_factor = float(cfg.get("shift_factor") or 0.0)
+        _check(self.lib.vt_encoder_configure(self.h, C.byref(ec)))
+        self.latent_channels = ec.latent_channels
+        self.num_blocks = ec.num_blocks
+
+    def _set_params(self, fn, sd: Dict[str, torch.Tensor]):
+        for name, t in sd.items():
+            if not torch.is_floating_point(t):
+                continue
+            t32 = t.detach().to(dtype=torch.float32).contiguous()
+            shape = (C.c_int64 * max(1, t32.dim()))(*t32.shape)
+            _check(fn(self.h, name.encode(), C.c_void_p(t32.data_ptr()), shape, t32.dim()))
+
+    def load_encoder(self, state_dict: Dict[str, torch.Tensor]):
+        """state_dict keys relative to ``encoder.`` (diffusers naming)."""
+        self._set_params(self.lib.vt_encoder_set_param, state_dict)
+        _check(self.lib.vt_encoder_finalize(self.h))
+
+    def encode(self, images: torch.Tensor, precision=PREC_BF16, sample=False, apply_scale_shift=True, seed=0,
+               noise: Optional[torch.Tensor] = None, want_moments=False, micro_batch=0):
+        """images: [B,3,H,W] float (any float dtype; normalised) or [B,H,W,3] uint8, on this device.
+        Returns latent [B,LC,H/8,W/8] fp32 (and mean, logvar when want_moments)."""
+        if images.dtype == torch.uint8:
+            fmt = IN_U8_NHWC
+            assert images.dim() == 4 and images.shape[-1] == 3, "uint8 images must be [B,H,W,3]"
+            x = images.to(self.device).contiguous()
+            B, H, W = x.shape[0], x.shape[1], x.shape[2]
+        else:
+            fmt = IN_F32_NCHW
+            assert images.dim() == 4 and images.shape[1] == 3, "float images must be [B,3,H,W]"
+            x = _f32c(images, self.device)
+            B, H, W = x.shape[0], x.shape[2], x.shape[3]
+        down = 1 << (self.num_blocks - 1)
+        lc = self.latent_channels
+        lat = torch.empty(B, lc, H // down, W // down, device=self.device, dtype=torch.float32)
+        mean = torch.empty_like(lat) if want_moments else None
+        logvar = torch.empty_like(lat) if want_moments else None
+        nz = _f32c(noise, self.device) if noise is not None else None
+        a = EncodeArgs()
+        a.images = x.data_ptr(); a.in_fmt = fmt; a.batch = B; a.height = H; a.width = W
+        a.precision = precision; a.sample = int(bool(sample)); a.apply_scale_shift = int(bool(apply_scale_shift))
+        a.seed = int(seed) & (2**64 - 1)
+        a.noise = nz.data_ptr() if nz is not None else None
+        a.latent = lat.data_ptr()
+        a.mean = mean.data_ptr() if mean is not None else None
+        a.logvar = logvar.data_ptr() if logvar is not None else None
+        a.micro_batch = int(micro_batch)
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_encode(self.h, C.byref(a)))
+        if want_moments:
+            return lat, mean, logvar
+        return lat
+
+    # ------------------------------------------------------------------ head
+    def configure_head(self, kind: int, latent_channels: int, num_classes: int, use_spatial_attention=True,
+                       use_self_attention=True, attention_heads=8):
+        hc = HeadConfig(kind, latent_channels, num_classes, int(use_spatial_attention), int(use_self_attention),
+                        attention_heads)
+        _check(self.lib.vt_head_configure(self.h, C.byref(hc)))
+        self.num_classes = num_classes
+
+    def load_head(self, state_dict: Dict[str, torch.Tensor]):
+        self._set_params(self.lib.vt_head_set_param, state_dict)
+        _check(self.lib.vt_head_finalize(self.h))
+
+    def tag(self, latent: torch.Tensor, threshold=0.5, want=("logits", "probs", "conf", "idx", "count")):
+        lat = _f32c(latent, self.device)
+        B, _, h, w = lat.shape
+        T = self.num_classes
+        out = {}
+        if "logits" in want:
+            out["logits"] = torch.empty(B, T, device=self.device, dtype=torch.float32)
+        if "probs" in want:
+            out["probs"] = torch.empty(B, T, device=self.device, dtype=torch.float32)
+        if "conf" in want:
+            out["conf"] = torch.empty(B, T, device=self.device, dtype=torch.float32)
+        if "idx" in want:
+            out["idx"] = torch.empty(B, T, device=self.device, dtype=torch.int64)
+        if "count" in want:
+            out["count"] = torch.empty(B, device=self.device, dtype=torch.int32)
+        a = TagArgs()
+        a.latent = lat.data_ptr(); a.batch = B; a.lat_h = h; a.lat_w = w; a.threshold = float(threshold)
+        a.logits = out["logits"].data_ptr() if "logits" in out else None
+        a.probs = out["probs"].data_ptr() if "probs" in out else None
+        a.conf_sorted = out["conf"].data_ptr() if "conf" in out else None
+        a.idx_sorted = out["idx"].data_ptr() if "idx" in out else None
+        a.count = out["count"].data_ptr() if "count" in out else None
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_tag(self.h, C.byref(a)))
+        return out
+
+    def infer_host(self, images_host: torch.Tensor, threshold=0.5, precision=PREC_BF16, want_latent=False,
+                   micro_batch=0, out=None):
+        """End-to-end on HOST tensors (pinned recommended): H2D + encode + tag + D2H, synchronous."""
+        x = images_host
+        assert x.device.type == "cpu" and x.is_contiguous()
+        if x.dtype == torch.uint8:
+            fmt, B, H, W = IN_U8_NHWC, x.shape[0], x.shape[1], x.shape[2]
+        else:
+            assert x.dtype == torch.float32
+            fmt, B, H, W = IN_F32_NCHW, x.shape[0], x.shape[2], x.shape[3]
+        T = self.num_classes
+        down = 1 << (self.num_blocks - 1)
+        if out is None:
+            out = {
+                "conf": torch.empty(B, T, dtype=torch.float32).pin_memory(),
+                "idx": torch.empty(B, T, dtype=torch.int64).pin_memory(),
+                "count": torch.empty(B, dtype=torch.int32).pin_memory(),
+            }
+            if want_latent:
+                out["latent"] = torch.empty(B, self.latent_channels, H // down, W // down).pin_memory()
+        a = InferHostArgs()
+        a.images_host = x.data_ptr(); a.in_fmt = fmt; a.batch = B; a.height = H; a.width = W
+        a.precision = precision; a.threshold = float(threshold)
+        a.conf_sorted_host = out["conf"].data_ptr(); a.idx_sorted_host = out["idx"].data_ptr()
+        a.count_host = out["count"].data_ptr()
+        a.latent_host = out["latent"].data_ptr() if "latent" in out else None
+        a.micro_batch = int(micro_batch)
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_infer_host(self.h, C.byref(a)))
+        return out
+
+    # ------------------------------------------------------------------ loss
+    def focal_loss(self, logits: torch.Tensor, targets: torch.Tensor, alpha=1.0, gamma=2.0, want_grad=True):
+        """Returns (sum of focal terms as a 1-element device tensor, d(mean)/d(logits) or None)."""
+        x = _f32c(logits, self.device)
+        y = _f32c(targets, self.device)
+        n = x.numel()
+        loss = torch.zeros(1, device=self.device, dtype=torch.float32)
+        grad = torch.empty_like(x) if want_grad else None
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_focal_loss(self.h, _ptr(x), _ptr(y), n, float(alpha), float(gamma), 1.0 / n, _ptr(loss),
+                                          _ptr(grad), _stream(self.device)))
+        return loss, grad
+
+    # ------------------------------------------------------------------ accounting
+    def profile_enable(self, timing: bool):
+        _check(self.lib.vt_profile_enable(self.h, int(timing)))
+
+    def profile_read(self, reset=True):
+        buf = (C.c_double * (NUM_KERNEL_CLASSES * 4))()
+        _check(self.lib.vt_profile_read(self.h, buf, int(reset)))
+        return {KERNEL_CLASS_NAMES[i]: {"launches": buf[4 * i], "ms": buf[4 * i + 1], "flops": buf[4 * i + 2],
+                                        "bytes": buf[4 * i + 3]} for i in range(NUM_KERNEL_CLASSES)}
+
+    # ------------------------------------------------------------------ single ops (tests)
+    def op_conv2d(self, x, w, bias=None, residual=None, sc_x=None, sc_w=None, stride=1, precision=PREC_BF16,
+                  want_stats=False):
+        x = _f32c(x, self.device); w = _f32c(w, self.device)
+        bias = _f32c(bias, self.device) if bias is not None else None
+        residual = _f32c(residual, self.device) if residual is not None else None
+        sc_x = _f32c(sc_x, self.device) if sc_x is not None else None
+        sc_w = _f32c(sc_w, self.device) if sc_w is not None else None
+        N, Cin, H, W = x.shape
+        Cout, _, k, _ = w.shape
+        Ho, Wo = (H, W) if stride == 1 else (H // 2, W // 2)
+        out = torch.empty(N, Cout, Ho, Wo, device=self.device, dtype=torch.float32)
+        stats = torch.zeros(N, 32, 2, device=self.device, dtype=torch.float64) if want_stats else None
+        Cs = sc_x.shape[1] if sc_x is not None else 0
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_op_conv2d(self.h, _ptr(x), _ptr(w), _ptr(bias), _ptr(residual), _ptr(sc_x), _ptr(sc_w),
+                                         N, Cin, H, W, Cout, k, stride, Cs, precision, _ptr(out), _ptr(stats),
+                                         _stream(self.device)))
+        return (out, stats) if want_stats else out
+
+    def op_gemm_nt(self, A, B, bias=None, alpha=1.0, precision=PREC_BF16):
+        A = _f32c(A, self.device); B = _f32c(B, self.device)
+        bias = _f32c(bias, self.device) if bias is not None else None
+        if A.dim() == 2:
+            A = A[None]
+        batch, M, K = A.shape
+        b_batched = int(B.dim() == 3)
+        N = B.shape[-2]
+        out = torch.empty(batch, M, N, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_op_gemm_nt(self.h, _ptr(A), _ptr(B), _ptr(bias), batch, M, N, K, b_batched, float(alpha),
+                                          precision, _ptr(out), _stream(self.device)))
+        return out
+
+    def op_group_norm(self, x, gamma, beta, groups=32, eps=1e-6, silu=False, precision=PREC_BF16):
+        x = _f32c(x, self.device); gamma = _f32c(gamma, self.device); beta = _f32c(beta, self.device)
+        N, Cc, H, W = x.shape
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_op_group_norm(self.h, _ptr(x), _ptr(gamma), _ptr(beta), N, Cc, H, W, groups, float(eps),
+                                             int(silu), precision, _ptr(out), _stream(self.device)))
+        return out
+
+    def op_softmax_rows(self, s, precision=PREC_BF16):
+        s = _f32c(s, self.device)
+        rows, cols = s.shape
+        out = torch.empty_like(s)
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_op_softmax_rows(self.h, _ptr(s), rows, cols, precision, _ptr(out), _stream(self.device)))
+        return out
+
+
+_contexts: Dict[int, Context] = {}
+
+
+def get_context(device=None) -> Context:
+    """Process-wide context of a device (created on first use)."""
+    if not torch.cuda.is_available():
+        raise NativeError("vae_tagger_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    if idx not in _contexts:
+        _contexts[idx] = Context(torch.device("cuda", idx))
+    return _contexts[idx]

@@ -1,0 +1,239 @@
+"""``AutoencoderKL`` -- the object the reference builds at ``diffusers_vae_loader.py:8-35`` --
+backed by the sm_100a encoder kernels.
+
+Only what the encode+tag hot path touches is implemented:
+``.config`` (attribute access, incl. ``scaling_factor`` / ``shift_factor``),
+``.encode(x).latent_dist`` with ``.mode() / .sample() / .kl() / .mean / .logvar / .std / .var``,
+``.load_state_dict(sd, strict=False)`` (diffusers key names, Appendix B; ``decoder.*`` keys of a
+full FLUX VAE checkpoint are tolerated), ``.parameters()``, ``.to()``, ``.eval()``.
+``.decode`` (the VAE decoder) is outside the path and raises.
+
+The module holds ordinary ``nn.Parameter``s under diffusers' names so checkpoints load with the
+stock ``nn.Module`` machinery; the parameters are mirrored into the native context (repacked to
+``[Cout][kh][kw][Cin]`` bf16) lazily and again whenever they change.  There is no PyTorch
+forward: every ``encode`` runs the CUDA path or raises.
+"""
+from __future__ import annotations
+
+import os
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _native
+
+_LEGACY_ATTN = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}
+
+
+class _Config(SimpleNamespace):
+    """Attribute + mapping access like diffusers' FrozenDict config."""
+
+    def get(self, k, default=None):
+        return getattr(self, k, default)
+
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+    def keys(self):
+        return vars(self).keys()
+
+
+def _resnet(cin, cout, groups):
+    m = nn.Module()
+    m.norm1 = nn.GroupNorm(groups, cin, eps=1e-6, affine=True)
+    m.conv1 = nn.Conv2d(cin, cout, 3, 1, 1)
+    m.norm2 = nn.GroupNorm(groups, cout, eps=1e-6, affine=True)
+    m.conv2 = nn.Conv2d(cout, cout, 3, 1, 1)
+    if cin != cout:
+        m.conv_shortcut = nn.Conv2d(cin, cout, 1, 1, 0)
+    return m
+
+
+def _encoder_params(cfg) -> nn.Module:
+    """Parameter containers with diffusers' ``Encoder`` state-dict layout (never called)."""
+    chans = list(cfg.block_out_channels)
+    g = cfg.norm_num_groups
+    enc = nn.Module()
+    enc.conv_in = nn.Conv2d(cfg.in_channels, chans[0], 3, 1, 1)
+    blocks, cin = [], chans[0]
+    for i, cout in enumerate(chans):
+        b = nn.Module()
+        b.resnets = nn.ModuleList([_resnet(cin if j == 0 else cout, cout, g) for j in range(cfg.layers_per_block)])
+        if i < len(chans) - 1:
+            d = nn.Module()
+            d.conv = nn.Conv2d(cout, cout, 3, 2, 0)
+            b.downsamplers = nn.ModuleList([d])
+        blocks.append(b)
+        cin = cout
+    enc.down_blocks = nn.ModuleList(blocks)
+    mid = nn.Module()
+    c = chans[-1]
+    if cfg.mid_block_add_attention:
+        a = nn.Module()
+        a.group_norm = nn.GroupNorm(g, c, eps=1e-6, affine=True)
+        a.to_q = nn.Linear(c, c)
+        a.to_k = nn.Linear(c, c)
+        a.to_v = nn.Linear(c, c)
+        a.to_out = nn.ModuleList([nn.Linear(c, c), nn.Dropout(0.0)])
+        mid.attentions = nn.ModuleList([a])
+    mid.resnets = nn.ModuleList([_resnet(c, c, g), _resnet(c, c, g)])
+    enc.mid_block = mid
+    enc.conv_norm_out = nn.GroupNorm(g, c, eps=1e-6, affine=True)
+    enc.conv_out = nn.Conv2d(c, 2 * cfg.latent_channels, 3, 1, 1)
+    return enc
+
+
+class DiagonalGaussianDistribution:
+    """Posterior returned by ``AutoencoderKL.encode(x).latent_dist``."""
+
+    def __init__(self, mean: torch.Tensor, logvar: torch.Tensor):
+        self.mean = mean
+        self.logvar = logvar  # already clamped to [-30, 20] by the kernel
+        self.deterministic = False
+
+    @property
+    def std(self):
+        return torch.exp(0.5 * self.logvar)
+
+    @property
+    def var(self):
+        return torch.exp(self.logvar)
+
+    def mode(self):
+        return self.mean
+
+    def sample(self, generator: Optional[torch.Generator] = None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+    def kl(self, other=None):
+        if other is not None:
+            raise NotImplementedError("kl() against another distribution is not on the encode+tag path")
+        return 0.5 * torch.sum(self.mean.pow(2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
+
+
+class AutoencoderKLOutput(SimpleNamespace):
+    pass
+
+
+class AutoencoderKL(nn.Module):
+    """B200-native stand-in for ``diffusers.models.AutoencoderKL`` on the encode path."""
+
+    def __init__(self, in_channels=3, out_channels=3, down_block_types=None, up_block_types=None,
+                 block_out_channels=(128, 256, 512, 512), layers_per_block=2, act_fn="silu", latent_channels=16,
+                 norm_num_groups=32, sample_size=1024, scaling_factor=0.3611, shift_factor=0.1159,
+                 use_quant_conv=False, use_post_quant_conv=False, force_upcast=True, mid_block_add_attention=True,
+                 latents_mean=None, latents_std=None, **unused):
+        super().__init__()
+        nblk = len(block_out_channels)
+        if act_fn != "silu":
+            raise ValueError("only act_fn='silu' is implemented (FLUX VAE)")
+        if use_quant_conv:
+            raise ValueError("use_quant_conv=True is not implemented (FLUX VAE has no quant convs)")
+        if down_block_types is not None and any(t != "DownEncoderBlock2D" for t in down_block_types):
+            raise ValueError("only DownEncoderBlock2D encoder blocks are implemented")
+        self.config = _Config(
+            in_channels=in_channels, out_channels=out_channels,
+            down_block_types=list(down_block_types or ["DownEncoderBlock2D"] * nblk),
+            up_block_types=list(up_block_types or ["UpDecoderBlock2D"] * nblk),
+            block_out_channels=list(block_out_channels), layers_per_block=layers_per_block, act_fn=act_fn,
+            latent_channels=latent_channels, norm_num_groups=norm_num_groups, sample_size=sample_size,
+            scaling_factor=scaling_factor, shift_factor=shift_factor, use_quant_conv=use_quant_conv,
+            use_post_quant_conv=use_post_quant_conv, force_upcast=force_upcast,
+            mid_block_add_attention=mid_block_add_attention, latents_mean=latents_mean, latents_std=latents_std)
+        self.encoder = _encoder_params(self.config)
+        # "bf16" (tcgen05 path) or "fp32" (verification mode); VT_B200_PRECISION overrides the default
+        self.precision = os.environ.get("VT_B200_PRECISION", "bf16")
+        self.micro_batch = 0
+        self._native_key = None
+
+    # ------------------------------------------------------------------ state dict
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        sd = {}
+        dropped = []
+        for k, v in state_dict.items():
+            if k.startswith(("decoder.", "quant_conv.", "post_quant_conv.")):
+                dropped.append(k)  # VAE decoder half: not on the encode path
+                continue
+            parts = k.split(".")
+            if "attentions" in parts and len(parts) >= 2 and parts[-2] in _LEGACY_ATTN:
+                parts[-2:-1] = _LEGACY_ATTN[parts[-2]].split(".")
+                k = ".".join(parts)
+                if v.dim() == 4:  # legacy 1x1-conv attention projections
+                    v = v.reshape(v.shape[0], v.shape[1])
+            sd[k] = v
+        result = super().load_state_dict(sd, strict=strict, assign=assign)
+        self._native_key = None
+        return result
+
+    # ------------------------------------------------------------------ native mirror
+    def _sync_native(self, device) -> "_native.Context":
+        ctx = _native.get_context(device)
+        params = list(self.encoder.named_parameters())
+        key = (id(ctx), tuple((p.data_ptr(), p._version) for _, p in params))
+        if key != self._native_key:
+            ctx.configure_encoder(vars(self.config))
+            ctx.load_encoder({n: p for n, p in params})
+            self._native_key = key
+        return ctx
+
+    def _precision(self) -> int:
+        if self.precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
+        return _native.PREC_FP32 if self.precision == "fp32" else _native.PREC_BF16
+
+    def _device_of(self, x: torch.Tensor):
+        if x.device.type != "cuda":
+            raise _native.NativeError(
+                "AutoencoderKL.encode needs CUDA tensors on a B200: the encode path has no CPU fallback")
+        return x.device
+
+    # ------------------------------------------------------------------ API
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, return_dict: bool = True):
+        """``vae.encode(x).latent_dist`` (diffusers_vae_loader.py:73, :79)."""
+        ctx = self._sync_native(self._device_of(x))
+        _, mean, logvar = ctx.encode(x, precision=self._precision(), sample=False, apply_scale_shift=False,
+                                     want_moments=True, micro_batch=self.micro_batch)
+        dist = DiagonalGaussianDistribution(mean, logvar)
+        if not return_dict:
+            return (dist,)
+        return AutoencoderKLOutput(latent_dist=dist)
+
+    @torch.no_grad()
+    def encode_latent(self, x: torch.Tensor, sample: bool = False, apply_scale_shift: bool = True, seed: int = 0,
+                      noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Fused ``latent_dist.mode()|sample() * scaling_factor + shift_factor`` (one kernel epilogue);
+        what ``DiffusersVAEWrapper.encode`` (diffusers_vae_loader.py:78-86) computes."""
+        ctx = self._sync_native(self._device_of(x))
+        return ctx.encode(x, precision=self._precision(), sample=sample, apply_scale_shift=apply_scale_shift,
+                          seed=seed, noise=noise, micro_batch=self.micro_batch)
+
+    def decode(self, z, return_dict: bool = True):
+        raise NotImplementedError(
+            "AutoencoderKL.decode (the VAE decoder) is outside the encode+tag hot path of vae_tagger_b200 "
+            "(SURVEY.md 8f item 3)")
+
+    def forward(self, x):
+        raise NotImplementedError("use .encode(); the reconstruction path needs the VAE decoder (out of scope)")
+
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, **kw):
+        """Local directory with ``config.json`` + ``diffusion_pytorch_model.safetensors`` (no network)."""
+        import json
+
+        root = os.path.join(path, subfolder) if subfolder else path
+        with open(os.path.join(root, "config.json"), "r", encoding="utf-8") as f:
+            cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        vae = cls(**cfg)
+        st = os.path.join(root, "diffusion_pytorch_model.safetensors")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+
+            vae.load_state_dict(load_file(st), strict=False)
+        else:
+            vae.load_state_dict(torch.load(os.path.join(root, "diffusion_pytorch_model.bin"), map_location="cpu"),
+                                strict=False)
+        return vae

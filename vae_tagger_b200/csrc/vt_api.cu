@@ -1,0 +1,966 @@
+// C-ABI of the encode+tag path (include/vae_tagger_b200.h): context, parameter store and
+// repacking, the encoder schedule (which kernel runs on which buffer, in what order), the
+// tag-head schedule, the host end-to-end call and the single-op test entry points.
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "../../include/vae_tagger_b200.h"
+#include "vt_internal.h"
+
+using namespace vt;
+
+namespace {
+
+struct Param {
+    std::vector<int64_t> shape;
+    float* dev = nullptr;
+    size_t numel = 0;
+};
+
+struct ConvW {      // packed conv / linear operand: [Cout][Ktot]
+    bf16* w16 = nullptr;
+    float* w32 = nullptr;
+    float* bias = nullptr;  // [Cout] (conv2 + shortcut biases folded)
+    int Cin = 0, Cout = 0, ksize = 1, Cs = 0, Ktot = 0;
+};
+struct NormW {
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+};
+struct ResnetW {
+    NormW norm1, norm2;
+    ConvW conv1, conv2;  // conv2 carries the 1x1 shortcut as an extra K slab when cin != cout
+    int cin = 0, cout = 0;
+};
+struct AttnW {
+    NormW gn;
+    ConvW qk;   // [2C][C]  rows 0..C-1 = to_q, C..2C-1 = to_k
+    ConvW v;    // [C][C]   used as the A operand of the V^T GEMM; bias applied after P.V
+    ConvW out;  // [C][C]
+    int C = 0;
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        VT_CUDA(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct vt_ctx {
+    int device = 0;
+    Profiler* prof = nullptr;
+
+    // ---- encoder
+    vt_encoder_config ecfg{};
+    bool ecfg_set = false, enc_ready = false;
+    std::map<std::string, Param> eparams;
+    std::vector<void*> epacked;  // allocations owned by the packed representation
+    ConvW conv_in, conv_out;
+    std::vector<std::vector<ResnetW>> down;  // [block][layer]
+    std::vector<ConvW> downsample;           // per block (Cout == 0: none)
+    ResnetW mid0, mid1;
+    AttnW attn;
+    NormW norm_out;
+    DevBuf arena;  // activation workspace
+    DevBuf stats;  // GroupNorm (sum, sumsq) slots
+    DevBuf mom;    // conv_out moments fp32 NHWC
+
+    // ---- head
+    vt_head_config hcfg{};
+    bool hcfg_set = false, head_ready = false;
+    std::map<std::string, Param> hparams;
+    DevBuf hws;  // head workspace
+    DevBuf e2e;  // device staging of vt_infer_host
+
+    DevBuf opws;  // single-op entry points
+};
+
+namespace {
+
+int set_device(vt_ctx* c) {
+    VT_CHECK(c != nullptr, "null context");
+    VT_CUDA(cudaSetDevice(c->device));
+    return 0;
+}
+
+int store_param(std::map<std::string, Param>& m, const char* name, const float* data, const int64_t* shape,
+                int ndim) {
+    VT_CHECK(name && data && (shape || ndim == 0) && ndim >= 0 && ndim <= 8, "bad parameter arguments");
+    Param& p = m[name];
+    size_t n = 1;
+    std::vector<int64_t> sh(shape, shape + ndim);
+    for (auto d : sh) {
+        VT_CHECK(d > 0, "parameter dimensions must be positive");
+        n *= static_cast<size_t>(d);
+    }
+    if (p.dev == nullptr || p.numel != n) {
+        if (p.dev) cudaFree(p.dev);
+        p.dev = nullptr;
+        VT_CUDA(cudaMalloc(&p.dev, n * sizeof(float)));
+    }
+    p.shape = sh;
+    p.numel = n;
+    VT_CUDA(cudaMemcpy(p.dev, data, n * sizeof(float), cudaMemcpyDefault));
+    return 0;
+}
+
+void free_params(std::map<std::string, Param>& m) {
+    for (auto& kv : m)
+        if (kv.second.dev) cudaFree(kv.second.dev);
+    m.clear();
+}
+
+// ---- weight packing kernels: OIHW fp32 -> [Cout][Ktot] with k = (kh*ks+kw)*Cin + ci, at column
+// offset k_off (the shortcut slab lands behind the taps).
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cout, int Cin, int ks,
+                                   int Ktot, int k_off) {
+    const long long total = 1LL * Cout * Cin * ks * ks;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        // i indexes src = ((co*Cin + ci)*ks + kh)*ks + kw
+        long long r = i;
+        const int kw = static_cast<int>(r % ks); r /= ks;
+        const int kh = static_cast<int>(r % ks); r /= ks;
+        const int ci = static_cast<int>(r % Cin);
+        const int co = static_cast<int>(r / Cin);
+        const long long d = 1LL * co * Ktot + k_off + (kh * ks + kw) * Cin + ci;
+        if constexpr (sizeof(T) == 2) dst[d] = __float2bfloat16(src[i]);
+        else dst[d] = src[i];
+    }
+}
+__global__ void add_vec_kernel(float* __restrict__ a, const float* __restrict__ b, int n) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) a[i] += b[i];
+}
+
+struct Packer {
+    vt_ctx* c;
+    int get(const std::string& name, std::initializer_list<int64_t> shape, const Param** out) {
+        auto it = c->eparams.find(name);
+        if (it == c->eparams.end()) {
+            set_error("encoder parameter missing: " + name);
+            return -4;
+        }
+        const Param& p = it->second;
+        std::vector<int64_t> want(shape);
+        if (p.shape != want) {
+            std::string m = "encoder parameter " + name + " has shape [";
+            for (auto d : p.shape) m += std::to_string(d) + ",";
+            m += "] expected [";
+            for (auto d : want) m += std::to_string(d) + ",";
+            set_error(m + "]");
+            return -4;
+        }
+        *out = &p;
+        return 0;
+    }
+    template <typename T>
+    int alloc(T** p, size_t n) {
+        void* q = nullptr;
+        VT_CUDA(cudaMalloc(&q, n * sizeof(T)));
+        VT_CUDA(cudaMemset(q, 0, n * sizeof(T)));
+        c->epacked.push_back(q);
+        *p = static_cast<T*>(q);
+        return 0;
+    }
+    // conv weight `prefix`.weight [Cout][Cin][ks][ks] (+ optional shortcut [Cout][Cs][1][1]); Kpad pads K
+    int conv(const std::string& prefix, int Cin, int Cout, int ks, const std::string& sc_prefix, int Cs, int Kpad,
+             ConvW* w) {
+        const Param *pw, *pb;
+        VT_TRY(get(prefix + ".weight", {Cout, Cin, ks, ks}, &pw));
+        VT_TRY(get(prefix + ".bias", {Cout}, &pb));
+        const int Ktot = std::max(Kpad, ks * ks * Cin + Cs);
+        w->Cin = Cin; w->Cout = Cout; w->ksize = ks; w->Cs = Cs; w->Ktot = Ktot;
+        VT_TRY(alloc(&w->w16, static_cast<size_t>(Cout) * Ktot));
+        VT_TRY(alloc(&w->w32, static_cast<size_t>(Cout) * Ktot));
+        VT_TRY(alloc(&w->bias, static_cast<size_t>(Cout)));
+        const int grid = 1024;
+        pack_weight_kernel<bf16><<<grid, 256>>>(pw->dev, w->w16, Cout, Cin, ks, Ktot, 0);
+        pack_weight_kernel<float><<<grid, 256>>>(pw->dev, w->w32, Cout, Cin, ks, Ktot, 0);
+        VT_CUDA(cudaMemcpy(w->bias, pb->dev, Cout * sizeof(float), cudaMemcpyDeviceToDevice));
+        if (Cs > 0) {
+            const Param *sw, *sb;
+            VT_TRY(get(sc_prefix + ".weight", {Cout, Cs, 1, 1}, &sw));
+            VT_TRY(get(sc_prefix + ".bias", {Cout}, &sb));
+            pack_weight_kernel<bf16><<<grid, 256>>>(sw->dev, w->w16, Cout, Cs, 1, Ktot, ks * ks * Cin);
+            pack_weight_kernel<float><<<grid, 256>>>(sw->dev, w->w32, Cout, Cs, 1, Ktot, ks * ks * Cin);
+            add_vec_kernel<<<(Cout + 255) / 256, 256>>>(w->bias, sb->dev, Cout);
+        }
+        VT_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // linear weights [out][in] stacked along the output dimension
+    int linear(std::initializer_list<std::string> prefixes, int In, int OutEach, bool with_bias, ConvW* w) {
+        const int n = static_cast<int>(prefixes.size());
+        w->Cin = In; w->Cout = n * OutEach; w->ksize = 1; w->Cs = 0; w->Ktot = In;
+        VT_TRY(alloc(&w->w16, static_cast<size_t>(w->Cout) * In));
+        VT_TRY(alloc(&w->w32, static_cast<size_t>(w->Cout) * In));
+        VT_TRY(alloc(&w->bias, static_cast<size_t>(w->Cout)));
+        int i = 0;
+        for (const auto& pre : prefixes) {
+            const Param *pw, *pb;
+            VT_TRY(get(pre + ".weight", {OutEach, In}, &pw));
+            VT_TRY(get(pre + ".bias", {OutEach}, &pb));
+            const size_t off = static_cast<size_t>(i) * OutEach * In;
+            VT_TRY(launch_cast_f32_bf16(pw->dev, w->w16 + off, 1LL * OutEach * In, nullptr));
+            VT_CUDA(cudaMemcpy(w->w32 + off, pw->dev, sizeof(float) * OutEach * In, cudaMemcpyDeviceToDevice));
+            if (with_bias)
+                VT_CUDA(cudaMemcpy(w->bias + static_cast<size_t>(i) * OutEach, pb->dev, sizeof(float) * OutEach,
+                                   cudaMemcpyDeviceToDevice));
+            ++i;
+        }
+        return 0;
+    }
+    int norm(const std::string& prefix, int C, NormW* n) {
+        const Param *g, *b;
+        VT_TRY(get(prefix + ".weight", {C}, &g));
+        VT_TRY(get(prefix + ".bias", {C}, &b));
+        n->gamma = g->dev;
+        n->beta = b->dev;
+        return 0;
+    }
+    int resnet(const std::string& prefix, int cin, int cout, ResnetW* r) {
+        r->cin = cin; r->cout = cout;
+        VT_TRY(norm(prefix + ".norm1", cin, &r->norm1));
+        VT_TRY(conv(prefix + ".conv1", cin, cout, 3, "", 0, 0, &r->conv1));
+        VT_TRY(norm(prefix + ".norm2", cout, &r->norm2));
+        VT_TRY(conv(prefix + ".conv2", cout, cout, 3, prefix + ".conv_shortcut", cin != cout ? cin : 0, 0, &r->conv2));
+        return 0;
+    }
+};
+
+void free_packed(vt_ctx* c) {
+    for (void* p : c->epacked) cudaFree(p);
+    c->epacked.clear();
+    c->down.clear();
+    c->downsample.clear();
+    c->enc_ready = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The encoder schedule.  Activations are NHWC (bf16, or fp32 in verification mode) in four
+// ping-pong buffers of the workspace arena; GroupNorm statistics come from the producing
+// contraction's epilogue (bf16) or a separate reduction (fp32 mode).
+struct EncRun {
+    vt_ctx* c;
+    cudaStream_t s;
+    int fp32;
+    int n;        // images in this micro-batch
+    size_t es;    // activation element size
+    double* stats_base;
+    int stats_used = 0;
+    int groups;
+
+    double* new_stats() {
+        double* p = stats_base + static_cast<size_t>(stats_used) * n * groups * 2;
+        ++stats_used;
+        return p;
+    }
+    const void* W(const ConvW& w) const { return fp32 ? static_cast<const void*>(w.w32) : static_cast<const void*>(w.w16); }
+
+    int conv(const void* in, int H, int Wd, const ConvW& w, int stride, const void* sc_in, const void* residual,
+             void* out, int out_fp32, double* st) {
+        ConvOp op;
+        op.in = in; op.N = n; op.Hin = H; op.Win = Wd; op.Cin = w.Cin; op.ksize = w.ksize; op.stride = stride;
+        op.w = W(w); op.Cout = w.Cout; op.sc_in = sc_in; op.Cs = w.Cs; op.bias = w.bias; op.residual = residual;
+        op.out = out; op.out_fp32 = out_fp32 || fp32;
+        if (fp32) {
+            VT_TRY(launch_conv_fp32(op, s, c->prof));
+            if (st) {
+                const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? Wd : Wd / 2;
+                VT_TRY(launch_gn_stats(out, 1, st, n, 1LL * Ho * Wo, w.Cout, groups, s, c->prof));
+            }
+            return 0;
+        }
+        op.stats = st;
+        return launch_conv(op, s, c->prof);
+    }
+    int gemm(GemmOp& op, long long rows_for_stats) {
+        if (fp32) {
+            double* st = op.stats;
+            op.stats = nullptr;
+            op.out_fp32 = 1;
+            VT_TRY(launch_gemm_fp32(op, s, c->prof));
+            if (st) VT_TRY(launch_gn_stats(op.out, 1, st, op.batch, rows_for_stats, op.N, groups, s, c->prof));
+            return 0;
+        }
+        return launch_gemm(op, s, c->prof);
+    }
+    int gn(const void* x, void* y, const double* st, const NormW& nw, long long HW, int C, int silu) {
+        return launch_gn_apply(x, y, fp32, st, nw.gamma, nw.beta, n, HW, C, groups, 1e-6f, silu, s, c->prof);
+    }
+    // ResnetBlock2D: out = x (+shortcut) + conv2(silu(norm2(conv1(silu(norm1(x))))))
+    int resnet(const ResnetW& r, const void* x, const double* st_x, int H, int Wd, void* T, void* Hb, void* out,
+               double* st_out) {
+        const long long HW = 1LL * H * Wd;
+        VT_TRY(gn(x, T, st_x, r.norm1, HW, r.cin, 1));
+        double* st_h = new_stats();
+        VT_TRY(conv(T, H, Wd, r.conv1, 1, nullptr, nullptr, Hb, 0, st_h));
+        VT_TRY(gn(Hb, T, st_h, r.norm2, HW, r.cout, 1));
+        if (r.cin != r.cout) return conv(T, H, Wd, r.conv2, 1, x, nullptr, out, 0, st_out);
+        return conv(T, H, Wd, r.conv2, 1, nullptr, x, out, 0, st_out);
+    }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int run_encoder_microbatch(vt_ctx* c, const vt_encode_args* a, int img0, int n, cudaStream_t s) {
+    const vt_encoder_config& cfg = c->ecfg;
+    const int H = a->height, Wd = a->width;
+    const int fp32 = a->precision == VT_PREC_FP32;
+    const size_t es = fp32 ? 4 : 2;
+    const int C0 = cfg.block_out_channels[0];
+    const int LC = cfg.latent_channels;
+    const int nb = cfg.num_blocks;
+    const int lh = H >> (nb - 1), lw = Wd >> (nb - 1);
+    const long long tokens = 1LL * lh * lw;
+    const int Cm = cfg.block_out_channels[nb - 1];
+
+    // ---- workspace layout
+    const size_t act = align_up(static_cast<size_t>(n) * H * Wd * C0 * es, 1024);
+    size_t attn_bytes = 0;
+    long long rows_per_chunk = 0;
+    int ipc = 1;
+    size_t qk_b = 0, vt_b = 0, s_b = 0, p_b = 0, o_b = 0;
+    if (cfg.mid_block_add_attention) {
+        const size_t s_budget = 64ull << 20;  // score tile kept L2 resident
+        const long long max_rows = static_cast<long long>(s_budget / (tokens * 4));
+        if (max_rows >= tokens) {
+            rows_per_chunk = tokens;
+            ipc = static_cast<int>(std::min<long long>(n, std::max<long long>(1, max_rows / tokens)));
+        } else {
+            rows_per_chunk = std::max<long long>(128, max_rows / 128 * 128);
+            ipc = 1;
+        }
+        qk_b = align_up(static_cast<size_t>(n) * tokens * 2 * Cm * es, 1024);
+        vt_b = align_up(static_cast<size_t>(n) * tokens * Cm * es, 1024);
+        s_b = align_up(static_cast<size_t>(ipc) * rows_per_chunk * tokens * 4, 1024);
+        p_b = align_up(static_cast<size_t>(ipc) * rows_per_chunk * tokens * es, 1024);
+        o_b = vt_b;
+        attn_bytes = qk_b + vt_b + s_b + p_b + o_b;
+    }
+    VT_TRY(c->arena.ensure(4 * act + attn_bytes));
+    char* base = static_cast<char*>(c->arena.p);
+    void* X = base;            // residual stream
+    void* T = base + act;      // normalised operand
+    void* Hb = base + 2 * act; // conv1 output / conv_in gather
+    void* Y = base + 3 * act;  // block output
+    char* ab = base + 4 * act;
+
+    const int groups = cfg.norm_num_groups;
+    const int max_slots = 64;
+    VT_TRY(c->stats.ensure(static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double)));
+    VT_CUDA(cudaMemsetAsync(c->stats.p, 0, static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double), s));
+    VT_TRY(c->mom.ensure(static_cast<size_t>(n) * tokens * 2 * LC * sizeof(float)));
+
+    EncRun R{c, s, fp32, n, es, static_cast<double*>(c->stats.p), 0, groups};
+
+    // ---- conv_in: gather the 3x3x3 patches (K = 27 padded to 64) then one K chunk of contraction
+    const char* img = static_cast<const char*>(a->images);
+    const size_t img_stride = a->in_fmt == VT_IN_U8_NHWC ? static_cast<size_t>(H) * Wd * 3
+                                                         : static_cast<size_t>(H) * Wd * 3 * sizeof(float);
+    VT_TRY(launch_im2col3x3(img + img_stride * img0, a->in_fmt, Hb, fp32, n, H, Wd, s, c->prof));
+    double* st_x = R.new_stats();
+    {
+        ConvW w = c->conv_in;  // viewed as a 1x1 conv over the 64-wide gathered patches
+        w.Cin = 64; w.ksize = 1; w.Cs = 0;
+        VT_TRY(R.conv(Hb, H, Wd, w, 1, nullptr, nullptr, X, 0, st_x));
+    }
+
+    int h = H, w_ = Wd;
+    for (int b = 0; b < nb; ++b) {
+        for (size_t l = 0; l < c->down[b].size(); ++l) {
+            double* st_o = R.new_stats();
+            VT_TRY(R.resnet(c->down[b][l], X, st_x, h, w_, T, Hb, Y, st_o));
+            std::swap(X, Y);
+            st_x = st_o;
+        }
+        if (c->downsample[b].Cout != 0) {
+            double* st_o = R.new_stats();
+            VT_TRY(R.conv(X, h, w_, c->downsample[b], 2, nullptr, nullptr, Y, 0, st_o));
+            std::swap(X, Y);
+            st_x = st_o;
+            h /= 2; w_ /= 2;
+        }
+    }
+    // ---- mid block
+    {
+        double* st_o = R.new_stats();
+        VT_TRY(R.resnet(c->mid0, X, st_x, h, w_, T, Hb, Y, st_o));
+        std::swap(X, Y);
+        st_x = st_o;
+    }
+    if (cfg.mid_block_add_attention) {
+        const AttnW& A = c->attn;
+        const int C = A.C;
+        char* QK = ab;
+        char* Vt = QK + qk_b;
+        char* S = Vt + vt_b;
+        char* P = S + s_b;
+        char* O = P + p_b;
+        VT_TRY(R.gn(X, T, st_x, A.gn, tokens, C, 0));
+        {   // [q | k] = t Wqk^T + b : [n][tokens][2C]
+            GemmOp g;
+            g.A = T; g.B = R.W(A.qk); g.batch = n; g.M = static_cast<int>(tokens); g.N = 2 * C; g.K = C;
+            g.a_batched = 1; g.b_batched = 0; g.bias = A.qk.bias; g.out = QK;
+            VT_TRY(R.gemm(g, tokens));
+        }
+        {   // V^T = Wv t^T : [n][C][tokens]  (bias b_v is added after P.V: softmax rows sum to one)
+            GemmOp g;
+            g.A = R.W(A.v); g.B = T; g.batch = n; g.M = C; g.N = static_cast<int>(tokens); g.K = C;
+            g.a_batched = 0; g.b_batched = 1; g.out = Vt;
+            VT_TRY(R.gemm(g, 0));
+        }
+        const float scale = 1.0f / sqrtf(static_cast<float>(C));
+        for (int i0 = 0; i0 < n; i0 += ipc) {
+            const int nb_img = std::min(ipc, n - i0);
+            for (long long r0 = 0; r0 < tokens; r0 += rows_per_chunk) {
+                const int rows = static_cast<int>(std::min<long long>(rows_per_chunk, tokens - r0));
+                {   // S = scale * Q K^T (fp32)
+                    GemmOp g;
+                    g.A = QK + (static_cast<size_t>(i0) * tokens + r0) * 2 * C * es;
+                    g.lda = 2 * C; g.a_bstride = tokens * 2 * C;
+                    g.B = QK + (static_cast<size_t>(i0) * tokens * 2 * C + C) * es;
+                    g.ldb = 2 * C; g.b_bstride = tokens * 2 * C;
+                    g.batch = nb_img; g.M = rows; g.N = static_cast<int>(tokens); g.K = C;
+                    g.alpha = scale; g.out = S; g.out_fp32 = 1;
+                    VT_TRY(R.gemm(g, 0));
+                }
+                VT_TRY(launch_softmax_rows(reinterpret_cast<const float*>(S), P, fp32, 1LL * nb_img * rows,
+                                           static_cast<int>(tokens), tokens, tokens, s, c->prof));
+                {   // O = P V + b_v
+                    GemmOp g;
+                    g.A = P; g.lda = tokens; g.a_bstride = 1LL * rows * tokens;
+                    g.B = Vt + static_cast<size_t>(i0) * C * tokens * es; g.ldb = tokens; g.b_bstride = 1LL * C * tokens;
+                    g.batch = nb_img; g.M = rows; g.N = C; g.K = static_cast<int>(tokens);
+                    g.bias = A.v.bias;
+                    g.out = O + (static_cast<size_t>(i0) * tokens + r0) * C * es;
+                    g.ld_out = C; g.out_bstride = tokens * C;
+                    VT_TRY(R.gemm(g, 0));
+                }
+            }
+        }
+        {   // out = O Wo^T + b_o + x
+            double* st_o = R.new_stats();
+            GemmOp g;
+            g.A = O; g.B = R.W(A.out); g.batch = n; g.M = static_cast<int>(tokens); g.N = C; g.K = C;
+            g.a_batched = 1; g.b_batched = 0; g.bias = A.out.bias; g.residual = X; g.out = Y; g.stats = st_o;
+            VT_TRY(R.gemm(g, tokens));
+            std::swap(X, Y);
+            st_x = st_o;
+        }
+    }
+    {
+        double* st_o = R.new_stats();
+        VT_TRY(R.resnet(c->mid1, X, st_x, h, w_, T, Hb, Y, st_o));
+        std::swap(X, Y);
+        st_x = st_o;
+    }
+    // ---- conv_norm_out + SiLU + conv_out -> moments (fp32 NHWC) -> DiagonalGaussian outputs
+    VT_TRY(R.gn(X, T, st_x, c->norm_out, tokens, Cm, 1));
+    VT_TRY(R.conv(T, h, w_, c->conv_out, 1, nullptr, nullptr, c->mom.p, 1, nullptr));
+    const size_t lat_stride = static_cast<size_t>(LC) * tokens;
+    VT_TRY(launch_moments_to_latent(static_cast<const float*>(c->mom.p),
+                                    a->latent ? a->latent + lat_stride * img0 : nullptr,
+                                    a->mean ? a->mean + lat_stride * img0 : nullptr,
+                                    a->logvar ? a->logvar + lat_stride * img0 : nullptr,
+                                    a->noise ? a->noise + lat_stride * img0 : nullptr, n, h, w_, LC, a->sample,
+                                    a->seed + 0x9E37ULL * static_cast<unsigned long long>(img0),
+                                    cfg.scaling_factor, cfg.shift_factor,
+                                    a->apply_scale_shift && cfg.has_scaling_factor,
+                                    a->apply_scale_shift && cfg.has_shift_factor, s, c->prof));
+    VT_CHECK(R.stats_used <= max_slots, "GroupNorm statistics slots exhausted");
+    return 0;
+}
+
+const float* hp(vt_ctx* c, const std::string& name) {
+    auto it = c->hparams.find(name);
+    return it == c->hparams.end() ? nullptr : it->second.dev;
+}
+int hcheck(vt_ctx* c, const std::string& name, std::initializer_list<int64_t> shape) {
+    auto it = c->hparams.find(name);
+    if (it == c->hparams.end()) {
+        set_error("head parameter missing: " + name);
+        return -4;
+    }
+    if (it->second.shape != std::vector<int64_t>(shape)) {
+        std::string m = "head parameter " + name + " has shape [";
+        for (auto d : it->second.shape) m += std::to_string(d) + ",";
+        m += "] expected [";
+        for (auto d : shape) m += std::to_string(d) + ",";
+        set_error(m + "]");
+        return -4;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* vt_last_error(void) { return vt::last_error(); }
+int vt_abi_version(void) { return VT_ABI_VERSION; }
+
+int vt_ctx_create(int device, vt_ctx** out) {
+    VT_CHECK(out != nullptr, "null output pointer");
+    int count = 0;
+    VT_CUDA(cudaGetDeviceCount(&count));
+    VT_CHECK(device >= 0 && device < count, "CUDA device index out of range");
+    VT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("vae_tagger_b200 needs an sm_100a (B200) device; found ") + prop.name + " (sm_" +
+                  std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+        return -5;
+    }
+    vt_ctx* c = new vt_ctx();
+    c->device = device;
+    c->prof = profiler_create();
+    *out = c;
+    return 0;
+}
+
+int vt_ctx_destroy(vt_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_packed(c);
+    free_params(c->eparams);
+    free_params(c->hparams);
+    c->arena.release(); c->stats.release(); c->mom.release(); c->hws.release(); c->e2e.release(); c->opws.release();
+    profiler_destroy(c->prof);
+    delete c;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- encoder
+int vt_encoder_configure(vt_ctx* c, const vt_encoder_config* cfg) {
+    VT_TRY(set_device(c));
+    VT_CHECK(cfg != nullptr, "null config");
+    VT_CHECK(cfg->in_channels == 3, "encoder in_channels must be 3");
+    VT_CHECK(cfg->num_blocks >= 1 && cfg->num_blocks <= 8, "num_blocks must be in 1..8");
+    VT_CHECK(cfg->norm_num_groups == 32, "norm_num_groups must be 32");
+    VT_CHECK(cfg->layers_per_block >= 1 && cfg->layers_per_block <= 8, "layers_per_block must be in 1..8");
+    for (int i = 0; i < cfg->num_blocks; ++i) {
+        const int ch = cfg->block_out_channels[i];
+        VT_CHECK(ch == 128 || ch == 256 || ch == 512,
+                 "block_out_channels entries must be 128, 256 or 512 (tile configs exist for those)");
+    }
+    VT_CHECK(cfg->latent_channels == 16, "latent_channels must be 16 (conv_out is a 32-column tile)");
+    free_packed(c);
+    c->ecfg = *cfg;
+    c->ecfg_set = true;
+    return 0;
+}
+
+int vt_encoder_set_param(vt_ctx* c, const char* name, const float* data, const int64_t* shape, int ndim) {
+    VT_TRY(set_device(c));
+    c->enc_ready = false;
+    return store_param(c->eparams, name, data, shape, ndim);
+}
+
+int vt_encoder_finalize(vt_ctx* c) {
+    VT_TRY(set_device(c));
+    VT_CHECK(c->ecfg_set, "vt_encoder_configure has not been called");
+    free_packed(c);
+    const vt_encoder_config& cfg = c->ecfg;
+    Packer P{c};
+    const int C0 = cfg.block_out_channels[0];
+    VT_TRY(P.conv("conv_in", 3, C0, 3, "", 0, 64, &c->conv_in));
+    c->down.resize(cfg.num_blocks);
+    c->downsample.resize(cfg.num_blocks);
+    int cin = C0;
+    for (int b = 0; b < cfg.num_blocks; ++b) {
+        const int cout = cfg.block_out_channels[b];
+        c->down[b].resize(cfg.layers_per_block);
+        for (int l = 0; l < cfg.layers_per_block; ++l) {
+            VT_TRY(P.resnet("down_blocks." + std::to_string(b) + ".resnets." + std::to_string(l), l == 0 ? cin : cout,
+                            cout, &c->down[b][l]));
+        }
+        if (b < cfg.num_blocks - 1)
+            VT_TRY(P.conv("down_blocks." + std::to_string(b) + ".downsamplers.0.conv", cout, cout, 3, "", 0, 0,
+                          &c->downsample[b]));
+        cin = cout;
+    }
+    const int Cm = cfg.block_out_channels[cfg.num_blocks - 1];
+    VT_TRY(P.resnet("mid_block.resnets.0", Cm, Cm, &c->mid0));
+    VT_TRY(P.resnet("mid_block.resnets.1", Cm, Cm, &c->mid1));
+    if (cfg.mid_block_add_attention) {
+        const std::string a = "mid_block.attentions.0";
+        c->attn.C = Cm;
+        VT_TRY(P.norm(a + ".group_norm", Cm, &c->attn.gn));
+        VT_TRY(P.linear({a + ".to_q", a + ".to_k"}, Cm, Cm, true, &c->attn.qk));
+        VT_TRY(P.linear({a + ".to_v"}, Cm, Cm, true, &c->attn.v));
+        VT_TRY(P.linear({a + ".to_out.0"}, Cm, Cm, true, &c->attn.out));
+    }
+    VT_TRY(P.norm("conv_norm_out", Cm, &c->norm_out));
+    VT_TRY(P.conv("conv_out", Cm, 2 * cfg.latent_channels, 3, "", 0, 0, &c->conv_out));
+    VT_CUDA(cudaDeviceSynchronize());
+    c->enc_ready = true;
+    return 0;
+}
+
+int vt_encode(vt_ctx* c, const vt_encode_args* a) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr, "null arguments");
+    VT_CHECK(c->enc_ready, "encoder parameters not finalised (vt_encoder_finalize)");
+    VT_CHECK(a->images != nullptr, "null image pointer");
+    VT_CHECK(a->batch > 0, "batch must be positive");
+    const int down = 1 << (c->ecfg.num_blocks - 1);
+    VT_CHECK(a->height > 0 && a->width > 0 && a->height % down == 0 && a->width % down == 0,
+             "image height and width must be positive multiples of 2^(num_blocks-1)");
+    VT_CHECK(a->in_fmt == VT_IN_F32_NCHW || a->in_fmt == VT_IN_U8_NHWC, "unknown image format");
+    VT_CHECK(a->precision == VT_PREC_BF16 || a->precision == VT_PREC_FP32, "unknown precision");
+    cudaStream_t s = static_cast<cudaStream_t>(a->stream);
+    int mb = a->micro_batch;
+    if (mb <= 0) {
+        // keep the top-level activation of one pass near 2 GB (bf16) so four ping-pong buffers stay small
+        const double per_img = 1.0 * a->height * a->width * c->ecfg.block_out_channels[0] * 2;
+        mb = static_cast<int>(std::max(1.0, std::min(32.0, (2.2e9) / per_img)));
+    }
+    for (int i0 = 0; i0 < a->batch; i0 += mb)
+        VT_TRY(run_encoder_microbatch(c, a, i0, std::min(mb, a->batch - i0), s));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- head
+int vt_head_configure(vt_ctx* c, const vt_head_config* cfg) {
+    VT_TRY(set_device(c));
+    VT_CHECK(cfg != nullptr, "null config");
+    VT_CHECK(cfg->kind == VT_HEAD_ATTENTION || cfg->kind == VT_HEAD_PLAIN, "unknown head kind");
+    VT_CHECK(cfg->latent_channels >= 8 && cfg->latent_channels <= 32 && cfg->latent_channels % 8 == 0,
+             "latent_channels must be 8, 16, 24 or 32");
+    VT_CHECK(cfg->num_classes >= 1 && cfg->num_classes <= 16384, "num_classes must be in 1..16384");
+    if (cfg->kind == VT_HEAD_ATTENTION && cfg->use_self_attention)
+        VT_CHECK(cfg->attention_heads >= 1 && (cfg->latent_channels / 2) % cfg->attention_heads == 0,
+                 "embed_dim must be divisible by num_heads (modules.py:56)");
+    c->hcfg = *cfg;
+    c->hcfg_set = true;
+    c->head_ready = false;
+    return 0;
+}
+
+int vt_head_set_param(vt_ctx* c, const char* name, const float* data, const int64_t* shape, int ndim) {
+    VT_TRY(set_device(c));
+    c->head_ready = false;
+    return store_param(c->hparams, name, data, shape, ndim);
+}
+
+int vt_head_finalize(vt_ctx* c) {
+    VT_TRY(set_device(c));
+    VT_CHECK(c->hcfg_set, "vt_head_configure has not been called");
+    const vt_head_config& h = c->hcfg;
+    const int C = h.latent_channels, E = C / 2, T = h.num_classes;
+    if (h.kind == VT_HEAD_ATTENTION) {
+        if (h.use_spatial_attention) {
+            VT_TRY(hcheck(c, "spatial_attention.channel_att.0.weight", {C / 8, C, 1, 1}));
+            VT_TRY(hcheck(c, "spatial_attention.channel_att.2.weight", {C, C / 8, 1, 1}));
+            VT_TRY(hcheck(c, "spatial_attention.spatial_att.0.weight", {1, 2, 7, 7}));
+        }
+        VT_TRY(hcheck(c, "feature_compress.0.weight", {E, C, 3, 3}));
+        VT_TRY(hcheck(c, "feature_compress.0.bias", {E}));
+        for (const char* k : {"weight", "bias", "running_mean", "running_var"})
+            VT_TRY(hcheck(c, std::string("feature_compress.1.") + k, {E}));
+        if (h.use_self_attention) {
+            for (const char* k : {"q_proj", "k_proj", "v_proj", "out_proj"}) {
+                VT_TRY(hcheck(c, std::string("self_attention_post.") + k + ".weight", {E, E}));
+                VT_TRY(hcheck(c, std::string("self_attention_post.") + k + ".bias", {E}));
+            }
+            VT_TRY(hcheck(c, "self_attention_post.norm.weight", {E}));
+            VT_TRY(hcheck(c, "self_attention_post.norm.bias", {E}));
+        }
+        const int dims[5] = {E * 64, 1024, 512, 256, T};
+        const int lin[4] = {0, 4, 8, 12}, ln[3] = {1, 5, 9};
+        for (int i = 0; i < 4; ++i) {
+            VT_TRY(hcheck(c, "classifier." + std::to_string(lin[i]) + ".weight", {dims[i + 1], dims[i]}));
+            VT_TRY(hcheck(c, "classifier." + std::to_string(lin[i]) + ".bias", {dims[i + 1]}));
+            if (i < 3) {
+                VT_TRY(hcheck(c, "classifier." + std::to_string(ln[i]) + ".weight", {dims[i + 1]}));
+                VT_TRY(hcheck(c, "classifier." + std::to_string(ln[i]) + ".bias", {dims[i + 1]}));
+            }
+        }
+    } else {
+        const int dims[4] = {C * 16, 512, 256, T};
+        const int lin[3] = {0, 4, 8}, ln[2] = {1, 5};
+        for (int i = 0; i < 3; ++i) {
+            VT_TRY(hcheck(c, "classifier." + std::to_string(lin[i]) + ".weight", {dims[i + 1], dims[i]}));
+            VT_TRY(hcheck(c, "classifier." + std::to_string(lin[i]) + ".bias", {dims[i + 1]}));
+            if (i < 2) {
+                VT_TRY(hcheck(c, "classifier." + std::to_string(ln[i]) + ".weight", {dims[i + 1]}));
+                VT_TRY(hcheck(c, "classifier." + std::to_string(ln[i]) + ".bias", {dims[i + 1]}));
+            }
+        }
+    }
+    c->head_ready = true;
+    return 0;
+}
+
+int vt_tag(vt_ctx* c, const vt_tag_args* a) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr, "null arguments");
+    VT_CHECK(c->head_ready, "head parameters not finalised (vt_head_finalize)");
+    VT_CHECK(a->latent != nullptr && a->batch > 0 && a->lat_h > 0 && a->lat_w > 0, "bad latent arguments");
+    const vt_head_config& h = c->hcfg;
+    const int B = a->batch, C = h.latent_channels, E = C / 2, T = h.num_classes;
+    const int H = a->lat_h, W = a->lat_w, HW = H * W;
+    cudaStream_t s = static_cast<cudaStream_t>(a->stream);
+    Profiler* pf = c->prof;
+    // workspace (floats)
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += (n + 63) / 64 * 64; return o; };
+    const size_t o_pool = take(static_cast<size_t>(B) * C * 2), o_cg = take(static_cast<size_t>(B) * C);
+    const size_t o_map = take(static_cast<size_t>(B) * 2 * HW), o_x2 = take(static_cast<size_t>(B) * C * HW);
+    const size_t o_pooled = take(static_cast<size_t>(B) * E * 64), o_feat = take(static_cast<size_t>(B) * 1024);
+    const size_t o_a = take(static_cast<size_t>(B) * 1024), o_b = take(static_cast<size_t>(B) * 1024);
+    const size_t o_logits = take(static_cast<size_t>(B) * T);
+    VT_TRY(c->hws.ensure(off * sizeof(float)));
+    float* ws = static_cast<float*>(c->hws.p);
+    float* logits = a->logits ? a->logits : ws + o_logits;
+
+    if (h.kind == VT_HEAD_ATTENTION) {
+        const float* x = a->latent;
+        if (h.use_spatial_attention) {
+            VT_TRY(launch_head_spatial_attention(a->latent, hp(c, "spatial_attention.channel_att.0.weight"),
+                                                 hp(c, "spatial_attention.channel_att.2.weight"),
+                                                 hp(c, "spatial_attention.spatial_att.0.weight"), ws + o_pool,
+                                                 ws + o_cg, ws + o_map, ws + o_x2, B, C, H, W, s, pf));
+            x = ws + o_x2;
+        }
+        VT_TRY(launch_head_compress(x, hp(c, "feature_compress.0.weight"), hp(c, "feature_compress.0.bias"),
+                                    hp(c, "feature_compress.1.weight"), hp(c, "feature_compress.1.bias"),
+                                    hp(c, "feature_compress.1.running_mean"), hp(c, "feature_compress.1.running_var"),
+                                    1e-5f, ws + o_pooled, B, C, H, W, s, pf));
+        const std::string sp = "self_attention_post.";
+        const float* mp[10] = {hp(c, sp + "norm.weight"), hp(c, sp + "norm.bias"),
+                               hp(c, sp + "q_proj.weight"), hp(c, sp + "q_proj.bias"),
+                               hp(c, sp + "k_proj.weight"), hp(c, sp + "k_proj.bias"),
+                               hp(c, sp + "v_proj.weight"), hp(c, sp + "v_proj.bias"),
+                               hp(c, sp + "out_proj.weight"), hp(c, sp + "out_proj.bias")};
+        VT_TRY(launch_head_mhsa(ws + o_pooled, mp, ws + o_feat, B, E, h.use_self_attention ? h.attention_heads : 1,
+                                h.use_self_attention, s, pf));
+        const int dims[5] = {E * 64, 1024, 512, 256, T};
+        const int lin[4] = {0, 4, 8, 12}, ln[3] = {1, 5, 9};
+        const float* cur = ws + o_feat;
+        float* bufs[2] = {ws + o_a, ws + o_b};
+        for (int i = 0; i < 4; ++i) {
+            float* out = i == 3 ? logits : bufs[i & 1];
+            VT_TRY(launch_head_linear(cur, hp(c, "classifier." + std::to_string(lin[i]) + ".weight"),
+                                      hp(c, "classifier." + std::to_string(lin[i]) + ".bias"), out, B, dims[i],
+                                      dims[i + 1], s, pf));
+            if (i < 3)
+                VT_TRY(launch_head_ln_act(out, hp(c, "classifier." + std::to_string(ln[i]) + ".weight"),
+                                          hp(c, "classifier." + std::to_string(ln[i]) + ".bias"), B, dims[i + 1], 1,
+                                          s, pf));
+            cur = out;
+        }
+    } else {
+        VT_TRY(launch_head_adaptive_pool(a->latent, ws + o_feat, B, C, H, W, 4, 4, s, pf));
+        const int dims[4] = {C * 16, 512, 256, T};
+        const int lin[3] = {0, 4, 8}, ln[2] = {1, 5};
+        const float* cur = ws + o_feat;
+        float* bufs[2] = {ws + o_a, ws + o_b};
+        for (int i = 0; i < 3; ++i) {
+            float* out = i == 2 ? logits : bufs[i & 1];
+            VT_TRY(launch_head_linear(cur, hp(c, "classifier." + std::to_string(lin[i]) + ".weight"),
+                                      hp(c, "classifier." + std::to_string(lin[i]) + ".bias"), out, B, dims[i],
+                                      dims[i + 1], s, pf));
+            if (i < 2)
+                VT_TRY(launch_head_ln_act(out, hp(c, "classifier." + std::to_string(ln[i]) + ".weight"),
+                                          hp(c, "classifier." + std::to_string(ln[i]) + ".bias"), B, dims[i + 1], 2,
+                                          s, pf));
+            cur = out;
+        }
+    }
+    if (a->conf_sorted || a->idx_sorted || a->count || a->probs)
+        VT_TRY(launch_head_confidence(logits, a->conf_sorted, reinterpret_cast<long long*>(a->idx_sorted), a->count,
+                                      a->probs, B, T, a->threshold, s, pf));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- e2e
+int vt_infer_host(vt_ctx* c, const vt_infer_host_args* a) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr && a->images_host != nullptr, "null arguments");
+    VT_CHECK(c->enc_ready && c->head_ready, "encoder and head must be finalised");
+    cudaStream_t s = static_cast<cudaStream_t>(a->stream);
+    const int B = a->batch, H = a->height, W = a->width;
+    const int LC = c->ecfg.latent_channels, T = c->hcfg.num_classes;
+    const int down = 1 << (c->ecfg.num_blocks - 1);
+    VT_CHECK(B > 0 && H > 0 && W > 0 && H % down == 0 && W % down == 0, "bad image shape");
+    const int lh = H / down, lw = W / down;
+    const size_t img_b = align_up(static_cast<size_t>(B) * H * W * 3 * (a->in_fmt == VT_IN_U8_NHWC ? 1 : 4), 256);
+    const size_t lat_b = align_up(static_cast<size_t>(B) * LC * lh * lw * 4, 256);
+    const size_t conf_b = align_up(static_cast<size_t>(B) * T * 4, 256), idx_b = align_up(static_cast<size_t>(B) * T * 8, 256);
+    const size_t cnt_b = align_up(static_cast<size_t>(B) * 4, 256);
+    VT_TRY(c->e2e.ensure(img_b + lat_b + conf_b + idx_b + cnt_b));
+    char* d = static_cast<char*>(c->e2e.p);
+    char* d_img = d; float* d_lat = reinterpret_cast<float*>(d + img_b);
+    float* d_conf = reinterpret_cast<float*>(d + img_b + lat_b);
+    int64_t* d_idx = reinterpret_cast<int64_t*>(d + img_b + lat_b + conf_b);
+    int32_t* d_cnt = reinterpret_cast<int32_t*>(d + img_b + lat_b + conf_b + idx_b);
+    VT_CUDA(cudaMemcpyAsync(d_img, a->images_host,
+                            static_cast<size_t>(B) * H * W * 3 * (a->in_fmt == VT_IN_U8_NHWC ? 1 : 4),
+                            cudaMemcpyHostToDevice, s));
+    vt_encode_args e{};
+    e.images = d_img; e.in_fmt = a->in_fmt; e.batch = B; e.height = H; e.width = W; e.precision = a->precision;
+    e.sample = 0; e.apply_scale_shift = 1; e.latent = d_lat; e.micro_batch = a->micro_batch; e.stream = a->stream;
+    VT_TRY(vt_encode(c, &e));
+    vt_tag_args t{};
+    t.latent = d_lat; t.batch = B; t.lat_h = lh; t.lat_w = lw; t.threshold = a->threshold;
+    t.conf_sorted = d_conf; t.idx_sorted = d_idx; t.count = d_cnt; t.stream = a->stream;
+    VT_TRY(vt_tag(c, &t));
+    if (a->conf_sorted_host)
+        VT_CUDA(cudaMemcpyAsync(a->conf_sorted_host, d_conf, static_cast<size_t>(B) * T * 4, cudaMemcpyDeviceToHost, s));
+    if (a->idx_sorted_host)
+        VT_CUDA(cudaMemcpyAsync(a->idx_sorted_host, d_idx, static_cast<size_t>(B) * T * 8, cudaMemcpyDeviceToHost, s));
+    if (a->count_host)
+        VT_CUDA(cudaMemcpyAsync(a->count_host, d_cnt, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));
+    if (a->latent_host)
+        VT_CUDA(cudaMemcpyAsync(a->latent_host, d_lat, static_cast<size_t>(B) * LC * lh * lw * 4,
+                                cudaMemcpyDeviceToHost, s));
+    VT_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int vt_focal_loss(vt_ctx* c, const float* logits, const float* targets, int64_t n, float alpha, float gamma,
+                  float grad_scale, float* loss_sum, float* grad, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(logits && targets && n > 0, "bad focal loss arguments");
+    return launch_focal_loss(logits, targets, loss_sum, grad, n, alpha, gamma, grad_scale,
+                             static_cast<cudaStream_t>(stream), c->prof);
+}
+
+// ------------------------------------------------------------------------------------- accounting
+int vt_profile_enable(vt_ctx* c, int timing) {
+    VT_TRY(set_device(c));
+    profiler_enable(c->prof, timing != 0);
+    return 0;
+}
+int vt_profile_read(vt_ctx* c, double* out, int reset) {
+    VT_TRY(set_device(c));
+    VT_CHECK(out != nullptr, "null output");
+    VT_CUDA(cudaDeviceSynchronize());
+    return profiler_read(c->prof, out, reset);
+}
+
+// ------------------------------------------------------------------------------------- single ops
+int vt_op_conv2d(vt_ctx* c, const float* x, const float* w, const float* bias, const float* residual,
+                 const float* sc_x, const float* sc_w, int N, int Cin, int H, int W, int Cout, int ksize, int stride,
+                 int Cs, int precision, float* out, double* stats, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(x && w && out, "null pointers");
+    VT_CHECK((sc_x == nullptr) == (sc_w == nullptr), "shortcut operand and weight go together");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int fp32 = precision == VT_PREC_FP32;
+    const size_t es = fp32 ? 4 : 2;
+    const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
+    if (!sc_x) Cs = 0;
+    const int Ktot = ksize * ksize * Cin + Cs;
+    const size_t b_x = align_up(static_cast<size_t>(N) * H * W * Cin * es, 256);
+    const size_t b_o = align_up(static_cast<size_t>(N) * Ho * Wo * Cout * 4, 256);
+    const size_t b_r = align_up(static_cast<size_t>(N) * Ho * Wo * Cout * es, 256);
+    const size_t b_s = align_up(static_cast<size_t>(N) * Ho * Wo * std::max(Cs, 1) * es, 256);
+    const size_t b_w = align_up(static_cast<size_t>(Cout) * Ktot * es, 256);
+    VT_TRY(c->opws.ensure(b_x + b_o + b_r + b_s + b_w));
+    char* p = static_cast<char*>(c->opws.p);
+    void* dx = p; void* dout = p + b_x; void* dres = p + b_x + b_o; void* dsc = p + b_x + b_o + b_r;
+    void* dw = p + b_x + b_o + b_r + b_s;
+    VT_TRY(launch_nchw_to_nhwc(x, dx, fp32, N, Cin, 1LL * H * W, s));
+    if (residual) VT_TRY(launch_nchw_to_nhwc(residual, dres, fp32, N, Cout, 1LL * Ho * Wo, s));
+    if (sc_x) VT_TRY(launch_nchw_to_nhwc(sc_x, dsc, fp32, N, Cs, 1LL * Ho * Wo, s));
+    VT_CUDA(cudaMemsetAsync(dw, 0, b_w, s));
+    if (fp32) {
+        pack_weight_kernel<float><<<256, 256, 0, s>>>(w, static_cast<float*>(dw), Cout, Cin, ksize, Ktot, 0);
+        if (sc_w) pack_weight_kernel<float><<<256, 256, 0, s>>>(sc_w, static_cast<float*>(dw), Cout, Cs, 1, Ktot, ksize * ksize * Cin);
+    } else {
+        pack_weight_kernel<bf16><<<256, 256, 0, s>>>(w, static_cast<bf16*>(dw), Cout, Cin, ksize, Ktot, 0);
+        if (sc_w) pack_weight_kernel<bf16><<<256, 256, 0, s>>>(sc_w, static_cast<bf16*>(dw), Cout, Cs, 1, Ktot, ksize * ksize * Cin);
+    }
+    VT_CUDA(cudaGetLastError());
+    ConvOp op;
+    op.in = dx; op.N = N; op.Hin = H; op.Win = W; op.Cin = Cin; op.ksize = ksize; op.stride = stride; op.w = dw;
+    op.Cout = Cout; op.sc_in = sc_x ? dsc : nullptr; op.Cs = Cs; op.bias = bias; op.residual = residual ? dres : nullptr;
+    op.out = dout; op.out_fp32 = 1;
+    if (stats) VT_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * N * 64, s));
+    if (fp32) {
+        VT_TRY(launch_conv_fp32(op, s, c->prof));
+        if (stats) VT_TRY(launch_gn_stats(dout, 1, stats, N, 1LL * Ho * Wo, Cout, 32, s, c->prof));
+    } else {
+        op.stats = stats;
+        VT_TRY(launch_conv(op, s, c->prof));
+    }
+    return launch_nhwc_to_nchw(dout, 1, out, N, Cout, 1LL * Ho * Wo, s);
+}
+
+int vt_op_gemm_nt(vt_ctx* c, const float* A, const float* B, const float* bias, int batch, int M, int N, int K,
+                  int b_batched, float alpha, int precision, float* out, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(A && B && out, "null pointers");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    GemmOp g;
+    g.batch = batch; g.M = M; g.N = N; g.K = K; g.a_batched = 1; g.b_batched = b_batched; g.bias = bias;
+    g.alpha = alpha; g.out = out; g.out_fp32 = 1;
+    if (precision == VT_PREC_FP32) {
+        g.A = A; g.B = B;
+        return launch_gemm_fp32(g, s, c->prof);
+    }
+    const size_t na = static_cast<size_t>(batch) * M * K, nbb = static_cast<size_t>(b_batched ? batch : 1) * N * K;
+    VT_TRY(c->opws.ensure(align_up(na * 2, 256) + nbb * 2));
+    bf16* da = static_cast<bf16*>(c->opws.p);
+    bf16* db = reinterpret_cast<bf16*>(static_cast<char*>(c->opws.p) + align_up(na * 2, 256));
+    VT_TRY(launch_cast_f32_bf16(A, da, static_cast<long long>(na), s));
+    VT_TRY(launch_cast_f32_bf16(B, db, static_cast<long long>(nbb), s));
+    g.A = da; g.B = db;
+    return launch_gemm(g, s, c->prof);
+}
+
+int vt_op_group_norm(vt_ctx* c, const float* x, const float* gamma, const float* beta, int N, int C, int H, int W,
+                     int groups, float eps, int silu, int precision, float* out, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(x && gamma && beta && out, "null pointers");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int fp32 = precision == VT_PREC_FP32;
+    const size_t es = fp32 ? 4 : 2;
+    const long long HW = 1LL * H * W;
+    const size_t b_x = align_up(static_cast<size_t>(N) * HW * C * es, 256);
+    const size_t b_s = align_up(static_cast<size_t>(N) * groups * 2 * sizeof(double), 256);
+    VT_TRY(c->opws.ensure(2 * b_x + b_s));
+    char* p = static_cast<char*>(c->opws.p);
+    void* dx = p; void* dy = p + b_x; double* st = reinterpret_cast<double*>(p + 2 * b_x);
+    VT_TRY(launch_nchw_to_nhwc(x, dx, fp32, N, C, HW, s));
+    VT_CUDA(cudaMemsetAsync(st, 0, b_s, s));
+    VT_TRY(launch_gn_stats(dx, fp32, st, N, HW, C, groups, s, c->prof));
+    VT_TRY(launch_gn_apply(dx, dy, fp32, st, gamma, beta, N, HW, C, groups, eps, silu, s, c->prof));
+    return launch_nhwc_to_nchw(dy, fp32, out, N, C, HW, s);
+}
+
+int vt_op_softmax_rows(vt_ctx* c, const float* sc, int64_t rows, int cols, int precision, float* out, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(sc && out, "null pointers");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (precision == VT_PREC_FP32) return launch_softmax_rows(sc, out, 1, rows, cols, cols, cols, s, c->prof);
+    VT_TRY(c->opws.ensure(static_cast<size_t>(rows) * cols * 2));
+    VT_TRY(launch_softmax_rows(sc, c->opws.p, 0, rows, cols, cols, cols, s, c->prof));
+    // widen bf16 -> fp32 through the layout kernel with C = cols, HW = 1 per row
+    return launch_nhwc_to_nchw(c->opws.p, 0, out, static_cast<int>(rows), cols, 1, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,509 @@
+// HBM-bound kernels of the encoder path: conv_in patch gather, GroupNorm statistics /
+// apply (+SiLU), attention row softmax, moments -> latent, layout conversions.
+// All are vectorised (16-byte accesses), channel-innermost (NHWC) and warp-shuffle based.
+#include "vt_internal.h"
+#include "vt_ptx.cuh"
+
+namespace vt {
+
+static inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// conv_in patch gather.  in: fp32 NCHW [N,3,H,W] in [-1,1]  (fmt 0)  or uint8 NHWC [N,H,W,3]
+// (fmt 1; normalised (u/255 - 0.5)/0.5 exactly like ToTensor+Normalize, modules.py:136-140).
+// out: [N,H,W,64] (bf16 or fp32) with k = (kh*3+kw)*3 + c for k < 27 and zeros above: the K=27
+// contraction of conv_in becomes one 64-wide K chunk of the implicit-GEMM kernel.
+// 8 threads per pixel, each writes 8 consecutive k.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out,
+                                                        int N, int H, int W) {
+    const long long total = 1LL * N * H * W * 8;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int j = static_cast<int>(i & 7);
+        long long p = i >> 3;
+        const int x = static_cast<int>(p % W);
+        p /= W;
+        const int y = static_cast<int>(p % H);
+        const int n = static_cast<int>(p / H);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = j * 8 + e;
+            float val = 0.f;
+            if (k < 27) {
+                const int tap = k / 3, c = k - tap * 3;
+                const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                    if (fmt == 0) {
+                        val = __ldg(static_cast<const float*>(in) + ((1LL * n * 3 + c) * H + yy) * W + xx);
+                    } else {
+                        const float u = static_cast<float>(
+                            __ldg(static_cast<const unsigned char*>(in) + ((1LL * n * H + yy) * W + xx) * 3 + c));
+                        val = (u / 255.0f - 0.5f) / 0.5f;
+                    }
+                }
+            }
+            v[e] = val;
+        }
+        if constexpr (sizeof(T) == 2) {
+            uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                 pack_bf16x2(v[6], v[7]));
+            reinterpret_cast<uint4*>(out)[i] = o;
+        } else {
+            float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+}
+
+int launch_im2col3x3(const void* in, int fmt, void* out, int out_fp32, int N, int H, int W, cudaStream_t s,
+                     Profiler* prof) {
+    const long long total = 1LL * N * H * W * 8;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 1LL * sm_count() * 16));
+    const double bytes = 1.0 * N * H * W * ((fmt ? 3.0 : 12.0) + 64.0 * (out_fp32 ? 4 : 2));
+    profiler_begin(prof, KC_IM2COL, s, 0, bytes);
+    if (out_fp32) im2col3x3_kernel<float><<<grid, 256, 0, s>>>(in, fmt, static_cast<float*>(out), N, H, W);
+    else im2col3x3_kernel<bf16><<<grid, 256, 0, s>>>(in, fmt, static_cast<bf16*>(out), N, H, W);
+    profiler_end(prof, KC_IM2COL, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm statistics (used by the fp32 verification path and by tests; the bf16 path gets
+// its statistics from the producing conv's epilogue).  x: [N][HW][C] ; stats: [N][G][2] double,
+// ACCUMULATED into (caller zeroes).  grid = (chunks, N); each block reduces a pixel range.
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ stats,
+                                                       long long HW, int C, int G) {
+    __shared__ double sh[2 * 32];
+    const int n = blockIdx.y;
+    const int cpg = C / G;
+    for (int i = threadIdx.x; i < 2 * G; i += 256) sh[i] = 0.0;
+    __syncthreads();
+    // thread -> fixed channel quad (4 channels); C/4 divides 256 for C in {128,256,512}; general C
+    // handled by looping the quad index.
+    const int quads = C / 4;
+    const long long chunk = (HW + gridDim.x - 1) / gridDim.x;
+    const long long p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+    for (int qd = threadIdx.x % min(quads, 256); qd < quads; qd += 256) {
+        const int ppb = max(1, 256 / quads);  // pixels per block step
+        const int psub = threadIdx.x / quads;
+        double s = 0.0, ss = 0.0;
+        if (psub < ppb) {
+            float fs = 0.f, fss = 0.f;
+            int cnt = 0;
+            for (long long p = p0 + psub; p < p1; p += ppb) {
+                const T* px = x + (1LL * n * HW + p) * C + qd * 4;
+                float a, b, c, d;
+                if constexpr (sizeof(T) == 2) {
+                    const uint2 u = *reinterpret_cast<const uint2*>(px);
+                    a = bf16_lo(u.x); b = bf16_hi(u.x); c = bf16_lo(u.y); d = bf16_hi(u.y);
+                } else {
+                    const float4 f = *reinterpret_cast<const float4*>(px);
+                    a = f.x; b = f.y; c = f.z; d = f.w;
+                }
+                fs += (a + b) + (c + d);
+                fss += (a * a + b * b) + (c * c + d * d);
+                if (++cnt == 64) { s += fs; ss += fss; fs = fss = 0.f; cnt = 0; }
+            }
+            s += fs; ss += fss;
+        }
+        const int g = (qd * 4) / cpg;  // cpg is a multiple of 4
+        atomicAdd(&sh[2 * g], s);
+        atomicAdd(&sh[2 * g + 1], ss);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += 256) atomicAdd(&stats[1LL * n * 2 * G + i], sh[i]);
+}
+
+int launch_gn_stats(const void* x, int is_fp32, double* stats, int N, long long HW, int C, int G, cudaStream_t s,
+                    Profiler* prof) {
+    VT_CHECK(G == 32 && C % (4 * G) == 0, "GroupNorm statistics need 32 groups of a multiple of 4 channels");
+    const int chunks = static_cast<int>(std::min<long long>((HW + 63) / 64, std::max(1, sm_count() * 8 / N)));
+    dim3 grid(chunks, N);
+    profiler_begin(prof, KC_GN_APPLY, s, 0, 1.0 * N * HW * C * (is_fp32 ? 4 : 2));
+    if (is_fp32) gn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), stats, HW, C, G);
+    else gn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), stats, HW, C, G);
+    profiler_end(prof, KC_GN_APPLY, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm apply (+ optional SiLU): y = act((x - mean) * rstd * gamma + beta), statistics from
+// (sum, sumsq) doubles.  One thread owns 8 consecutive channels of a fixed channel block and
+// walks pixels, so scale/shift live in registers; every access is a 16-byte (bf16) or 2x16-byte
+// (fp32) vector and a warp touches 512 contiguous bytes.
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                       const double* __restrict__ stats,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, long long HW, int C, int G,
+                                                       float eps, int silu) {
+    const int n = blockIdx.y;
+    const int cb = C / 8;              // 8-channel blocks per pixel
+    const int tpb = min(cb, 256);      // threads spanning the channel dimension
+    const int ppb = 256 / tpb;         // pixels per block step
+    const int psub = threadIdx.x / tpb;
+    const int cpg = C / G;
+    const double cnt = static_cast<double>(HW) * cpg;
+    const long long chunk = (HW + gridDim.x - 1) / gridDim.x;
+    const long long p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+    for (int c8 = threadIdx.x % tpb; c8 < cb; c8 += tpb) {
+        float sc[8], sh[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = c8 * 8 + e;
+            const int g = c / cpg;
+            const double su = stats[(1LL * n * G + g) * 2], sq = stats[(1LL * n * G + g) * 2 + 1];
+            const double mean = su / cnt;
+            double var = sq / cnt - mean * mean;
+            var = var > 0.0 ? var : 0.0;
+            const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+            const float ga = gamma[c], be = beta[c];
+            sc[e] = rstd * ga;
+            sh[e] = be - static_cast<float>(mean) * rstd * ga;
+        }
+        for (long long p = p0 + psub; p < p1; p += ppb) {
+            const long long off = (1LL * n * HW + p) * C + c8 * 8;
+            float v[8];
+            if constexpr (sizeof(T) == 2) {
+                const uint4 u = *reinterpret_cast<const uint4*>(x + off);
+                v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+                v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+            } else {
+                const float4 a = *reinterpret_cast<const float4*>(x + off);
+                const float4 b = *reinterpret_cast<const float4*>(x + off + 4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float t = fmaf(v[e], sc[e], sh[e]);
+                if (silu) {
+                    if constexpr (FAST) t = __fdividef(t, 1.0f + __expf(-t));
+                    else t = t / (1.0f + expf(-t));
+                }
+                v[e] = t;
+            }
+            if constexpr (sizeof(T) == 2) {
+                *reinterpret_cast<uint4*>(y + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                                pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            } else {
+                *reinterpret_cast<float4*>(y + off) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(y + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+    }
+}
+
+int launch_gn_apply(const void* x, void* y, int is_fp32, const double* stats, const float* gamma,
+                    const float* beta, int N, long long HW, int C, int G, float eps, int silu, cudaStream_t s,
+                    Profiler* prof) {
+    VT_CHECK(C % 8 == 0 && C % G == 0, "GroupNorm apply needs C % 8 == 0 and C % groups == 0");
+    const int tpb = std::min(C / 8, 256), ppb = 256 / tpb;
+    // ~16 pixel steps per block at least, and enough blocks to fill the machine a few times
+    long long want = (HW + 1LL * ppb * 16 - 1) / (1LL * ppb * 16);
+    const long long cap = std::max(1, sm_count() * 16 / N);
+    const int chunks = static_cast<int>(std::max<long long>(1, std::min(want, cap)));
+    dim3 grid(chunks, N);
+    profiler_begin(prof, KC_GN_APPLY, s, 0, 2.0 * N * HW * C * (is_fp32 ? 4 : 2));
+    if (is_fp32)
+        gn_apply_kernel<float, false><<<grid, 256, 0, s>>>(static_cast<const float*>(x), static_cast<float*>(y),
+                                                           stats, gamma, beta, HW, C, G, eps, silu);
+    else
+        gn_apply_kernel<bf16, true><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), stats,
+                                                         gamma, beta, HW, C, G, eps, silu);
+    profiler_end(prof, KC_GN_APPLY, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Attention row softmax: p = softmax(s) along the last dimension (scores already scaled by
+// the GEMM epilogue).  One 256-thread CTA per row; the row (<= 16384 values) lives in
+// registers, so it is read once and written once.  Wider rows take the three-pass loop.
+template <typename TO>
+__device__ __forceinline__ void store_prob(TO* p, float v) {
+    if constexpr (sizeof(TO) == 2) *p = __float2bfloat16(v);
+    else *p = v;
+}
+
+template <typename TO, int PER>  // PER values per thread, cols <= 256*PER
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, TO* __restrict__ p,
+                                                           int cols, long long ld_s, long long ld_p) {
+    __shared__ float red[8];
+    __shared__ float bcast;
+    const long long row = blockIdx.x;
+    const float* sr = s + row * ld_s;
+    TO* pr = p + row * ld_p;
+    float v[PER];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = i * 256 + threadIdx.x;
+        v[i] = c < cols ? sr[c] : -INFINITY;
+        m = fmaxf(m, v[i]);
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < 8 ? red[threadIdx.x] : -INFINITY;
+        t = warp_max(t);
+        if (threadIdx.x == 0) bcast = t;
+    }
+    __syncthreads();
+    m = bcast;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        v[i] = expf(v[i] - m);  // exp(-inf) = 0 for the padding
+        sum += v[i];
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) bcast = t;
+    }
+    __syncthreads();
+    const float inv = 1.0f / bcast;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = i * 256 + threadIdx.x;
+        if (c < cols) store_prob(pr + c, v[i] * inv);
+    }
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256) softmax_rows_wide_kernel(const float* __restrict__ s, TO* __restrict__ p,
+                                                                int cols, long long ld_s, long long ld_p) {
+    __shared__ float red[8];
+    __shared__ float bcast;
+    const long long row = blockIdx.x;
+    const float* sr = s + row * ld_s;
+    TO* pr = p + row * ld_p;
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, sr[c]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = red[0];
+        for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+        bcast = t;
+    }
+    __syncthreads();
+    m = bcast;
+    float sum = 0.f;
+    for (int c = threadIdx.x; c < cols; c += 256) sum += expf(sr[c] - m);
+    sum = warp_sum(sum);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        bcast = t;
+    }
+    __syncthreads();
+    const float inv = 1.0f / bcast;
+    for (int c = threadIdx.x; c < cols; c += 256) store_prob(pr + c, expf(sr[c] - m) * inv);
+}
+
+template <typename TO>
+static void softmax_dispatch(const float* s, TO* p, long long rows, int cols, long long ld_s, long long ld_p,
+                             cudaStream_t st) {
+    const unsigned grid = static_cast<unsigned>(rows);
+    if (cols <= 256 * 4) softmax_rows_kernel<TO, 4><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p);
+    else if (cols <= 256 * 16) softmax_rows_kernel<TO, 16><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p);
+    else if (cols <= 256 * 64) softmax_rows_kernel<TO, 64><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p);
+    else softmax_rows_wide_kernel<TO><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p);
+}
+
+int launch_softmax_rows(const float* s, void* p, int p_fp32, long long rows, int cols, long long ld_s,
+                        long long ld_p, cudaStream_t st, Profiler* prof) {
+    VT_CHECK(rows > 0 && rows < (1LL << 31) && cols > 0, "softmax shape");
+    profiler_begin(prof, KC_SOFTMAX, st, 0, 1.0 * rows * cols * (4 + (p_fp32 ? 4 : 2)));
+    if (p_fp32) softmax_dispatch<float>(s, static_cast<float*>(p), rows, cols, ld_s, ld_p, st);
+    else softmax_dispatch<bf16>(s, static_cast<bf16*>(p), rows, cols, ld_s, ld_p, st);
+    profiler_end(prof, KC_SOFTMAX, st);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// moments (conv_out, fp32 NHWC [N,h,w,32]) -> DiagonalGaussian outputs, NCHW fp32:
+//   mean, logvar = clamp(., -30, 20), latent = (mode|sample) * scale + shift
+// sample = mean + exp(0.5 logvar) * eps with eps from a caller tensor (exact parity with a
+// host-supplied noise) or from a counter-based generator (splitmix64 + Box-Muller).
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float counter_normal(unsigned long long seed, unsigned long long idx) {
+    const unsigned long long r = splitmix64(seed ^ splitmix64(idx));
+    const float u1 = (static_cast<float>(r >> 40) + 1.0f) * (1.0f / 16777216.0f);        // (0,1]
+    const float u2 = static_cast<float>((r >> 16) & 0xFFFFFF) * (1.0f / 16777216.0f);    // [0,1)
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+__global__ void __launch_bounds__(256) moments_to_latent_kernel(const float* __restrict__ mom,
+                                                                float* __restrict__ latent,
+                                                                float* __restrict__ mean_out,
+                                                                float* __restrict__ logvar_out,
+                                                                const float* __restrict__ noise, int N, int HW,
+                                                                int LC, int sample, unsigned long long seed,
+                                                                float scale, float shift, int apply_scale,
+                                                                int apply_shift) {
+    // one thread per (n, c, pixel) of the NCHW output: writes coalesced along pixels; the NHWC
+    // reads of a warp hit 32 different pixels of one channel (128-byte stride) -- the tensor is
+    // tiny (128 KB .. 2 MB per image) and L2 resident.
+    const long long total = 1LL * N * LC * HW;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int p = static_cast<int>(i % HW);
+        const int c = static_cast<int>((i / HW) % LC);
+        const int n = static_cast<int>(i / (1LL * HW * LC));
+        const float* m = mom + (1LL * n * HW + p) * (2 * LC);
+        const float mean = m[c];
+        const float lv = fminf(fmaxf(m[LC + c], -30.0f), 20.0f);
+        float z = mean;
+        if (sample) {
+            const float e = noise ? noise[i] : counter_normal(seed, static_cast<unsigned long long>(i));
+            z = mean + expf(0.5f * lv) * e;
+        }
+        if (apply_scale) z = z * scale;
+        if (apply_shift) z = z + shift;
+        if (latent) latent[i] = z;
+        if (mean_out) mean_out[i] = mean;
+        if (logvar_out) logvar_out[i] = lv;
+    }
+}
+
+int launch_moments_to_latent(const float* moments_nhwc, float* latent, float* mean_out, float* logvar_out,
+                             const float* noise, int N, int H, int W, int LC, int sample, unsigned long long seed,
+                             float scale, float shift, int apply_scale, int apply_shift, cudaStream_t s,
+                             Profiler* prof) {
+    const long long total = 1LL * N * LC * H * W;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 1LL * sm_count() * 8));
+    profiler_begin(prof, KC_LATENT, s, 0, total * 12.0);
+    moments_to_latent_kernel<<<grid, 256, 0, s>>>(moments_nhwc, latent, mean_out, logvar_out, noise, N, H * W, LC,
+                                                  sample, seed, scale, shift, apply_scale, apply_shift);
+    profiler_end(prof, KC_LATENT, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Layout conversions (tests, op-level entry points, fp32 path I/O): tiled transpose through
+// shared memory so both sides are coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out,
+                                                           int C, long long HW) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long long p0 = blockIdx.x * 32LL;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r;
+        const long long p = p0 + tx;
+        tile[r][tx] = (c < C && p < HW) ? in[(1LL * n * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const long long p = p0 + r;
+        const int c = c0 + tx;
+        if (c < C && p < HW) {
+            if constexpr (sizeof(T) == 2) out[(1LL * n * HW + p) * C + c] = __float2bfloat16(tile[tx][r]);
+            else out[(1LL * n * HW + p) * C + c] = tile[tx][r];
+        }
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out,
+                                                           int C, long long HW) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long long p0 = blockIdx.x * 32LL;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const long long p = p0 + r;
+        const int c = c0 + tx;
+        float v = 0.f;
+        if (c < C && p < HW) {
+            if constexpr (sizeof(T) == 2) v = __bfloat162float(in[(1LL * n * HW + p) * C + c]);
+            else v = in[(1LL * n * HW + p) * C + c];
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r;
+        const long long p = p0 + tx;
+        if (c < C && p < HW) out[(1LL * n * C + c) * HW + p] = tile[tx][r];
+    }
+}
+
+int launch_nchw_to_nhwc(const float* in, void* out, int out_fp32, int N, int C, long long HW, cudaStream_t s) {
+    dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N);
+    if (out_fp32) nchw_to_nhwc_kernel<float><<<grid, 256, 0, s>>>(in, static_cast<float*>(out), C, HW);
+    else nchw_to_nhwc_kernel<bf16><<<grid, 256, 0, s>>>(in, static_cast<bf16*>(out), C, HW);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_nhwc_to_nchw(const void* in, int in_fp32, float* out, int N, int C, long long HW, cudaStream_t s) {
+    dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N);
+    if (in_fp32) nhwc_to_nchw_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(in), out, C, HW);
+    else nhwc_to_nchw_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(in), out, C, HW);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// fp32 -> bf16 (weights packing) with an arbitrary gather done on the host side; plain cast here.
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
+                                                            long long n) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x)
+        out[i] = __float2bfloat16(in[i]);
+}
+int launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
+    const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 1LL * sm_count() * 8));
+    cast_f32_bf16_kernel<<<grid, 256, 0, s>>>(in, out, n);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace vt

@@ -1,0 +1,236 @@
+// Host side of the tcgen05 implicit-GEMM kernel: builds the TMA tensor maps and the slab
+// table for each conv / GEMM and launches igemm_kernel<BLOCK_N>.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "vt_igemm.cuh"
+#include "vt_internal.h"
+
+namespace vt {
+
+// cuTensorMapEncodeTiled is a driver entry point; fetch it through the runtime so the
+// library has no link-time dependency on libcuda.
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+// bf16 tensor map, 128-byte swizzle, zero fill out of bounds.
+static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+    auto fn = get_encode_fn();
+    VT_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    uint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        std::string m = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) + " rank " +
+                        std::to_string(rank) + " dims";
+        for (int i = 0; i < rank; ++i) m += " " + std::to_string(dims[i]);
+        m += " box";
+        for (int i = 0; i < rank; ++i) m += " " + std::to_string(box[i]);
+        set_error(m);
+        return -3;
+    }
+    return 0;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BLOCK_N>
+static int launch_variant(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const IgemmParams& P,
+                          cudaStream_t stream) {
+    using Cfg = IgemmCfg<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VT_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y * P.n_blocks;
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    igemm_kernel<BLOCK_N><<<grid, IGEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, P);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int pick_block_n(int n_total) {
+    if (n_total >= 256) return 256;
+    if (n_total >= 128) return 128;
+    return 32;
+}
+
+static int dispatch(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                    const IgemmParams& P, cudaStream_t stream) {
+    switch (block_n) {
+        case 256: return launch_variant<256>(a0, a1, b, P, stream);
+        case 128: return launch_variant<128>(a0, a1, b, P, stream);
+        case 32: return launch_variant<32>(a0, a1, b, P, stream);
+    }
+    set_error("unsupported BLOCK_N");
+    return -2;
+}
+
+// 5-D activation map (c, x, p, y, img).  stride 1: dims {C, W, 1, H, N}.
+// stride 2: the input [N][Hin][Win][C] is viewed as {2C, Win/2, 2, Hin/2, N}: channel
+// coordinate pw*C + c, x = column pair, p = row parity, y = row pair -- so a stride-2 tap
+// (kh, kw) is a plain box at (c0 + (kw&1)*C, ox + (kw>>1), kh&1, oy + (kh>>1)) and the
+// bottom/right zero padding of Downsample2D is TMA out-of-bounds fill.
+static int make_act_map(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int stride, int tw, int th) {
+    uint64_t dims[5], str[4];
+    uint32_t box[5] = {64, static_cast<uint32_t>(tw), 1, static_cast<uint32_t>(th), 1};
+    if (stride == 1) {
+        dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
+        str[0] = 2ull * C;
+        str[1] = 2ull * C * W;  // size-1 dimension: any legal stride
+        str[2] = 2ull * C * W;
+        str[3] = 2ull * C * W * H;
+    } else {
+        VT_CHECK(H % 2 == 0 && W % 2 == 0, "stride-2 conv needs even input size");
+        dims[0] = 2ull * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
+        str[0] = 2ull * 2 * C;
+        str[1] = 2ull * C * W;
+        str[2] = 2ull * C * W * 2;
+        str[3] = 2ull * C * W * H;
+    }
+    return make_tmap(tm, base, 5, dims, str, box);
+}
+
+int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
+    VT_CHECK(op.ksize == 1 || op.ksize == 3, "conv kernel size must be 1 or 3");
+    VT_CHECK(op.stride == 1 || (op.stride == 2 && op.ksize == 3), "stride must be 1, or 2 with a 3x3 kernel");
+    VT_CHECK(op.Cin % 64 == 0 && op.Cin > 0, "Cin must be a multiple of 64");
+    VT_CHECK(op.Cout % 32 == 0 && op.Cout > 0, "Cout must be a multiple of 32");
+    VT_CHECK(op.Cs % 64 == 0, "shortcut channels must be a multiple of 64");
+    VT_CHECK(op.sc_in == nullptr || op.stride == 1, "shortcut slab needs a stride-1 conv");
+    const int Hout = op.stride == 1 ? op.Hin : op.Hin / 2;
+    const int Wout = op.stride == 1 ? op.Win : op.Win / 2;
+    const int taps = op.ksize * op.ksize;
+    const int Ktot = taps * op.Cin + (op.sc_in ? op.Cs : 0);
+    const int block_n = pick_block_n(op.Cout);
+
+    IgemmParams P{};
+    P.W = Wout; P.H = Hout; P.NB = op.N;
+    P.tw = 16; P.th = 8;
+    P.tiles_x = (Wout + P.tw - 1) / P.tw;
+    P.tiles_y = (Hout + P.th - 1) / P.th;
+    P.n_total = op.Cout;
+    P.n_blocks = (op.Cout + block_n - 1) / block_n;
+    P.a_batched = 1; P.b_batched = 0;
+    P.out_fp32 = op.out_fp32;
+    P.group_size = op.stats ? op.Cout / 32 : 0;
+    VT_CHECK(op.stats == nullptr || (op.Cout % 32 == 0 && (P.group_size == 4 || P.group_size == 8 || P.group_size == 16)),
+             "fused GroupNorm statistics need 4, 8 or 16 channels per group");
+    P.alpha = op.alpha;
+    P.bias = op.bias; P.residual = static_cast<const bf16*>(op.residual); P.out = op.out; P.ld_out = op.Cout;
+    P.out_bstride = 1LL * Hout * Wout * op.Cout; P.stats = op.stats;
+
+    int ns = 0;
+    for (int kh = 0; kh < op.ksize; ++kh)
+        for (int kw = 0; kw < op.ksize; ++kw) {
+            IgemmSlab& s = P.slabs[ns];
+            s.map = 0;
+            if (op.ksize == 1) { s.c_base = 0; s.dx = 0; s.p = 0; s.dy = 0; }
+            else if (op.stride == 1) { s.c_base = 0; s.dx = kw - 1; s.p = 0; s.dy = kh - 1; }
+            else { s.c_base = (kw & 1) * op.Cin; s.dx = kw >> 1; s.p = kh & 1; s.dy = kh >> 1; }
+            s.kb_base = ns * op.Cin;
+            s.nchunks = op.Cin / 64;
+            ++ns;
+        }
+    if (op.sc_in) {
+        IgemmSlab& s = P.slabs[ns];
+        s.map = 1; s.c_base = 0; s.dx = 0; s.p = 0; s.dy = 0;
+        s.kb_base = taps * op.Cin; s.nchunks = op.Cs / 64;
+        ++ns;
+    }
+    P.num_slabs = ns;
+
+    CUtensorMap a0, a1, b;
+    VT_TRY(make_act_map(&a0, op.in, op.N, op.Hin, op.Win, op.Cin, op.stride, P.tw, P.th));
+    if (op.sc_in) VT_TRY(make_act_map(&a1, op.sc_in, op.N, Hout, Wout, op.Cs, 1, P.tw, P.th));
+    else a1 = a0;
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(op.Cout), 1};
+        uint64_t str[2] = {2ull * Ktot, 2ull * Ktot * op.Cout};
+        uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
+        VT_TRY(make_tmap(&b, op.w, 3, dims, str, box));
+    }
+    const double flops = 2.0 * op.N * Hout * Wout * static_cast<double>(op.Cout) * Ktot;
+    const double bytes = 2.0 * op.N * (1.0 * op.Hin * op.Win * op.Cin + 1.0 * Hout * Wout * op.Cout);
+    profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
+    int rc = dispatch(block_n, a0, a1, b, P, stream);
+    profiler_end(prof, KC_IGEMM, stream);
+    return rc;
+}
+
+int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
+    VT_CHECK(op.K % 64 == 0 && op.K > 0, "GEMM K must be a multiple of 64");
+    VT_CHECK(op.N % 32 == 0 && op.N > 0, "GEMM N must be a multiple of 32");
+    const long long lda = op.lda ? op.lda : op.K, ldb = op.ldb ? op.ldb : op.K;
+    const long long ldo = op.ld_out ? op.ld_out : op.N;
+    const int block_n = pick_block_n(op.N);
+
+    IgemmParams P{};
+    P.W = op.M; P.H = 1; P.NB = op.batch;
+    P.tw = 128; P.th = 1;
+    P.tiles_x = (op.M + 127) / 128;
+    P.tiles_y = 1;
+    P.n_total = op.N;
+    P.n_blocks = (op.N + block_n - 1) / block_n;
+    P.a_batched = op.a_batched; P.b_batched = op.b_batched;
+    P.out_fp32 = op.out_fp32;
+    P.group_size = op.stats ? op.N / 32 : 0;
+    VT_CHECK(op.stats == nullptr || (P.group_size == 4 || P.group_size == 8 || P.group_size == 16),
+             "fused GroupNorm statistics need 4, 8 or 16 channels per group");
+    P.alpha = op.alpha;
+    P.bias = op.bias; P.residual = static_cast<const bf16*>(op.residual); P.out = op.out; P.ld_out = ldo;
+    P.out_bstride = op.out_bstride ? op.out_bstride : 1LL * op.M * ldo; P.stats = op.stats;
+    P.num_slabs = 1;
+    P.slabs[0] = IgemmSlab{0, 0, 0, 0, 0, 0, op.K / 64, 0};
+
+    CUtensorMap a, b;
+    {
+        uint64_t dims[5] = {static_cast<uint64_t>(op.K), static_cast<uint64_t>(op.M), 1, 1,
+                            static_cast<uint64_t>(op.a_batched ? op.batch : 1)};
+        const uint64_t abs_ = 2ull * (op.a_bstride ? op.a_bstride : lda * op.M);
+        uint64_t str[4] = {2ull * lda, abs_, abs_, abs_};
+        uint32_t box[5] = {64, 128, 1, 1, 1};
+        VT_TRY(make_tmap(&a, op.A, 5, dims, str, box));
+    }
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(op.K), static_cast<uint64_t>(op.N),
+                            static_cast<uint64_t>(op.b_batched ? op.batch : 1)};
+        uint64_t str[2] = {2ull * ldb, 2ull * (op.b_bstride ? op.b_bstride : ldb * op.N)};
+        uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
+        VT_TRY(make_tmap(&b, op.B, 3, dims, str, box));
+    }
+    // the epilogue addresses out as ((img*H + y)*W + x)*ld_out: batch stride is M*ld_out
+    const double flops = 2.0 * op.batch * static_cast<double>(op.M) * op.N * op.K;
+    const double bytes = 2.0 * op.batch * (1.0 * op.M * op.K + 1.0 * op.N * op.K) +
+                         (op.out_fp32 ? 4.0 : 2.0) * op.batch * op.M * op.N;
+    profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
+    int rc = dispatch(block_n, a, a, b, P, stream);
+    profiler_end(prof, KC_IGEMM, stream);
+    return rc;
+}
+
+}  // namespace vt

@@ -1,0 +1,143 @@
+// Internal (non-ABI) declarations shared by the vae-tagger B200 translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <algorithm>
+#include <string>
+
+namespace vt {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing: int return codes + thread-local message, no exceptions across the ABI
+void set_error(const std::string& msg);
+const char* last_error();
+#define VT_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            ::vt::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                            std::to_string(__LINE__) + ")");                                            \
+            return -1;                                                                                  \
+        }                                                                                               \
+    } while (0)
+#define VT_CHECK(cond, msg)                                                           \
+    do {                                                                              \
+        if (!(cond)) {                                                                \
+            ::vt::set_error(std::string(msg) + " [" #cond "] (" __FILE__ ":" +        \
+                            std::to_string(__LINE__) + ")");                          \
+            return -2;                                                                \
+        }                                                                             \
+    } while (0)
+#define VT_TRY(expr)              \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != 0) return _r;   \
+    } while (0)
+
+// ---- kernel-class accounting (launch counts + optional CUDA-event timing per class)
+enum KernelClass {
+    KC_IGEMM = 0,      // tcgen05 implicit-GEMM (convs, projections, QK^T, PV)
+    KC_GN_APPLY = 1,   // GroupNorm apply (+SiLU)
+    KC_IM2COL = 2,     // conv_in patch gather
+    KC_SOFTMAX = 3,    // attention row softmax
+    KC_LATENT = 4,     // moments -> latent (mode/sample, scale/shift)
+    KC_HEAD = 5,       // tag head kernels
+    KC_FP32 = 6,       // fp32 verification-mode kernels
+    KC_MISC = 7,
+    KC_COUNT = 8
+};
+struct Profiler;
+Profiler* profiler_create();
+void profiler_destroy(Profiler*);
+void profiler_enable(Profiler*, bool timing);
+void profiler_begin(Profiler*, KernelClass, cudaStream_t, double flops, double bytes);
+void profiler_end(Profiler*, KernelClass, cudaStream_t);
+// out: [KC_COUNT][4] = launches, milliseconds, flops, bytes ; resets when reset != 0
+int profiler_read(Profiler*, double* out, int reset);
+
+// ---- tcgen05 implicit GEMM (vt_igemm.cu)
+struct ConvOp {
+    // input activation, NHWC bf16
+    const void* in = nullptr;  // bf16 (tcgen05 path) or fp32 (launch_conv_fp32)
+    int N = 0, Hin = 0, Win = 0, Cin = 0;
+    int ksize = 3;   // 1 or 3
+    int stride = 1;  // 1 (pad 1 for 3x3) or 2 (pad right/bottom by 1, diffusers Downsample2D)
+    // packed weights [Cout][ksize*ksize*Cin (+ Cs)] bf16, K contiguous, tap-major then channel
+    const void* w = nullptr;
+    int Cout = 0;
+    // optional 1x1 shortcut operand folded in as an extra K-slab: [N][Hout][Wout][Cs]
+    const void* sc_in = nullptr;
+    int Cs = 0;
+    const float* bias = nullptr;     // [Cout]
+    const void* residual = nullptr;  // [N][Hout][Wout][Cout]
+    void* out = nullptr;             // [N][Hout][Wout][Cout] bf16 or fp32
+    int out_fp32 = 0;
+    double* stats = nullptr;  // [N][32][2] GroupNorm (sum, sumsq) of the output (group = Cout/32 channels)
+    float alpha = 1.f;
+};
+int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof);
+
+struct GemmOp {
+    // D[b][m][n] = alpha * sum_k A[b?][m][k] * B[b?][n][k] (+ bias[n]) (+ residual[b][m][n])
+    // element type of A / B / residual: bf16 (tcgen05 path) or fp32 (launch_gemm_fp32)
+    const void* A = nullptr;
+    const void* B = nullptr;
+    int batch = 1, M = 0, N = 0, K = 0;
+    int a_batched = 1, b_batched = 1;
+    long long lda = 0, ldb = 0;              // row strides in elements (default K)
+    long long a_bstride = 0, b_bstride = 0;  // batch strides in elements (default rows * ld)
+    const float* bias = nullptr;
+    const void* residual = nullptr;
+    void* out = nullptr;
+    int out_fp32 = 0;
+    long long ld_out = 0;       // default N
+    long long out_bstride = 0;  // default M * ld_out (also used for residual)
+    double* stats = nullptr;    // [batch][32][2] over (m, group of N/32 columns)
+    float alpha = 1.f;
+};
+int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof);
+
+// ---- HBM-bound kernels (vt_elementwise.cu)
+int launch_im2col3x3(const void* in, int fmt, void* out, int out_fp32, int N, int H, int W, cudaStream_t,
+                     Profiler*);
+int launch_gn_stats(const void* x, int is_fp32, double* stats, int N, long long HW, int C, int G, cudaStream_t,
+                    Profiler*);
+int launch_gn_apply(const void* x, void* y, int is_fp32, const double* stats, const float* gamma,
+                    const float* beta, int N, long long HW, int C, int G, float eps, int silu, cudaStream_t,
+                    Profiler*);
+int launch_softmax_rows(const float* s, void* p, int p_fp32, long long rows, int cols, long long ld_s,
+                        long long ld_p, cudaStream_t, Profiler*);
+int launch_moments_to_latent(const float* moments_nhwc, float* latent, float* mean_out, float* logvar_out,
+                             const float* noise, int N, int H, int W, int LC, int sample, unsigned long long seed,
+                             float scale, float shift, int apply_scale, int apply_shift, cudaStream_t, Profiler*);
+int launch_nchw_to_nhwc(const float* in, void* out, int out_fp32, int N, int C, long long HW, cudaStream_t);
+int launch_nhwc_to_nchw(const void* in, int in_fp32, float* out, int N, int C, long long HW, cudaStream_t);
+int launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t);
+
+// ---- fp32 verification mode (vt_fp32.cu): FFMA implicit GEMM, NHWC fp32, same operand packing
+int launch_conv_fp32(const ConvOp& op, cudaStream_t, Profiler*);
+int launch_gemm_fp32(const GemmOp& op, cudaStream_t, Profiler*);
+
+// ---- tag head (vt_head.cu), fp32, NCHW latent
+int launch_head_spatial_attention(const float* latent, const float* w1, const float* w2, const float* w7,
+                                  float* pool, float* cgate, float* map2, float* out, int N, int C, int H, int W,
+                                  cudaStream_t, Profiler*);
+int launch_head_compress(const float* x, const float* cw, const float* cb, const float* bn_w, const float* bn_b,
+                         const float* bn_rm, const float* bn_rv, float bn_eps, float* pooled, int N, int C, int H,
+                         int W, cudaStream_t, Profiler*);
+int launch_head_mhsa(const float* pooled, const float* const* params10, float* feat, int N, int E, int heads,
+                     int enabled, cudaStream_t, Profiler*);
+int launch_head_adaptive_pool(const float* x, float* out, int N, int C, int H, int W, int OH, int OW, cudaStream_t,
+                              Profiler*);
+int launch_head_linear(const float* x, const float* w, const float* b, float* y, int B, int I, int O, cudaStream_t,
+                       Profiler*);
+int launch_head_ln_act(float* x, const float* w, const float* b, int B, int D, int act, cudaStream_t, Profiler*);
+int launch_head_confidence(const float* logits, float* conf_sorted, long long* idx_sorted, int* count, float* probs,
+                           int B, int T, float thr, cudaStream_t, Profiler*);
+int launch_focal_loss(const float* logits, const float* targets, float* loss_sum, float* grad, long long n,
+                      float alpha, float gamma, float grad_scale, cudaStream_t, Profiler*);
+
+}  // namespace vt
