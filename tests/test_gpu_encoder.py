@@ -54,18 +54,51 @@ def test_encoder_bf16_mode(pair, B, H, W):
     assert rel(got, ref) <= BF16_TOL, rel(got, ref)
 
 
-def test_micro_batching_is_invisible(pair):
-    _, wrap = pair
-    x = synthetic_images(5, 64, 128).cuda()
+def test_micro_batching(pair):
+    """Splitting a batch into micro-batches changes only the order of the fp64 statistics atomics.  In
+    fp32 mode that is invisible (<= 1e-6).  In bf16 mode a last-bit change flips bf16 roundings, and
+    every flip re-draws the rounding noise downstream (tools/emulate_bf16.py: a 1e-7 input perturbation
+    moves the bf16 result by ~9e-3), so two bf16 runs agree only to the bf16 noise level -- both must
+    still meet the bar against the oracle."""
+    oracle, wrap = pair
+    xc = synthetic_images(5, 64, 128)
+    with torch.no_grad():
+        ref = oracle_wrapper_encode(oracle, xc)
+    x = xc.cuda()
+    for prec, tol_pair, tol_ref in (("fp32", 1e-6, FP32_TOL), ("bf16", 2 * BF16_TOL, BF16_TOL)):
+        wrap.vae.precision = prec
+        wrap.vae.micro_batch = 5
+        a = wrap.encode(x)
+        wrap.vae.micro_batch = 2
+        b = wrap.encode(x)
+        wrap.vae.micro_batch = 0
+        assert rel(b, a) <= tol_pair, (prec, rel(b, a))
+        assert rel(a.cpu(), ref) <= tol_ref and rel(b.cpu(), ref) <= tol_ref
     wrap.vae.precision = "bf16"
-    wrap.vae.micro_batch = 5
-    a = wrap.encode(x)
-    wrap.vae.micro_batch = 2
-    b = wrap.encode(x)
-    wrap.vae.micro_batch = 0
-    # fp64 atomics of the GroupNorm statistics make the last bits order dependent; bf16 rounding can
-    # then flip an ulp here and there
-    assert rel(b, a) < 2e-3
+
+
+def test_bf16_tag_agreement(pair, golden):
+    """North star, bf16 mode: max |delta sigmoid| <= 1e-2 and identical tag sets at threshold 0.5 on
+    >= 99.5 % of images, with the reference's 11-tag example vocabulary."""
+    from oracle import head as OH
+    from vae_tagger_b200 import modules as M
+
+    oracle, wrap = pair
+    sd = dict(golden["attention_head_base"])
+    sd.update(golden["attention_head"]["att_T11_64x64"]["state_dict"])
+    x = synthetic_images(32, 64, 64)
+    with torch.no_grad():
+        ref_lat = oracle_wrapper_encode(oracle, x)
+        ref_p = torch.sigmoid(OH.attention_decoder_logits(sd, ref_lat))
+    dec = M.create_attention_decoder(16, 8, 8, 11, attention_config={})
+    dec.load_state_dict(sd)
+    dec = dec.cuda().eval()
+    wrap.vae.precision = "bf16"
+    lat = wrap.encode(x.cuda())
+    p = torch.sigmoid(dec(lat)).cpu()
+    assert (p - ref_p).abs().max().item() <= 1e-2, (p - ref_p).abs().max().item()
+    same = ((p >= 0.5) == (ref_p >= 0.5)).all(dim=1).float().mean().item()
+    assert same >= 0.995, same
 
 
 def test_posterior_api(pair):

@@ -1,0 +1,117 @@
+"""CPU: host-side logic of the drop-in surface (no GPU, no compute through the native library)."""
+import json
+
+import pytest
+import torch
+
+from oracle import encoder as OE
+from vae_tagger_b200 import _native
+from vae_tagger_b200 import diffusers_vae_loader as L
+from vae_tagger_b200 import modules as M
+
+
+def test_bucketing_matches_reference(golden):
+    arb = M.AspectRatioBucketing()
+    assert [tuple(b) for b in golden["buckets"]] == arb.buckets
+    assert len(arb.buckets) == 81 and arb.buckets[0] == (512, 512) and arb.buckets[-1] == (1024, 1024)
+    reach = {}
+    for w, h in arb.buckets:
+        reach.setdefault(w / h, (w, h))
+    assert sorted(reach.values()) == [tuple(b) for b in golden["reachable_buckets"]]
+    assert len(reach) == 67
+    # first-in-sorted-order wins ties: a square image lands in (512, 512), never (1024, 1024)
+    assert arb.bucket_for_size(1024, 1024) == (512, 512)
+    assert arb.bucket_for_size(2000, 1000) == (1024, 512)
+
+
+def test_latent_info_and_config(golden):
+    assert M.get_vae_latent_info(1024) == golden["latent_info_1024"]
+    assert M.get_vae_latent_info(1024)["total_dim"] == 262144
+    assert L.get_diffusers_vae_config() == golden["vae_config"]
+
+
+def test_head_state_dict_keys_match_reference(golden):
+    dec = M.create_attention_decoder(16, 128, 128, 1000, attention_config={})
+    assert list(dec.state_dict().keys()) == golden["att_keys"]
+    assert sum(p.numel() for p in dec.parameters()) == golden["att_T1000_param_count"]
+    plain = M.create_attention_decoder(16, 64, 64, 11, attention_config=None)
+    assert list(plain.state_dict().keys()) == list(golden["plain_head"]["state_dict"].keys())
+    assert isinstance(plain, M.ClassificationDecoder)
+
+
+def test_vae_state_dict_keys_match_oracle_and_load():
+    vae = L.load_diffusers_vae_from_config(L.get_diffusers_vae_config())
+    oracle = OE.make_oracle_vae(0)
+    assert sorted(vae.state_dict().keys()) == sorted(oracle.state_dict().keys())
+    assert sum(p.numel() for p in vae.parameters()) == 34_274_208
+    sd = dict(oracle.state_dict())
+    # a full FLUX checkpoint also carries decoder.* keys; legacy checkpoints name the attention
+    # projections query/key/value/proj_attn
+    sd["decoder.conv_in.weight"] = torch.zeros(1)
+    for old, new in (("query", "to_q"), ("key", "to_k"), ("value", "to_v"), ("proj_attn", "to_out.0")):
+        for leaf in ("weight", "bias"):
+            sd[f"encoder.mid_block.attentions.0.{old}.{leaf}"] = sd.pop(f"encoder.mid_block.attentions.0.{new}.{leaf}")
+    missing, unexpected = vae.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    assert torch.equal(vae.state_dict()["encoder.mid_block.attentions.0.to_q.weight"],
+                       oracle.state_dict()["encoder.mid_block.attentions.0.to_q.weight"])
+    assert vae.config.scaling_factor == 0.3611 and vae.config.shift_factor == 0.1159
+    assert hasattr(vae.config, "scaling_factor")
+
+
+def test_loader_file_roundtrip(tmp_path):
+    cfg = tmp_path / "vae.json"
+    cfg.write_text(json.dumps(L.get_diffusers_vae_config()))
+    oracle = OE.make_oracle_vae(0)
+    ck = tmp_path / "vae.pt"
+    torch.save(oracle.state_dict(), ck)
+    wrap = L.create_vae_from_config_file(str(cfg), str(ck))
+    assert isinstance(wrap, L.DiffusersVAEWrapper)
+    assert torch.equal(wrap.vae.state_dict()["encoder.conv_in.weight"], oracle.state_dict()["encoder.conv_in.weight"])
+    # a missing checkpoint path silently keeps the random init (reference :37)
+    wrap2 = L.create_vae_from_config_file(str(cfg), str(tmp_path / "missing.safetensors"))
+    assert isinstance(wrap2.vae, torch.nn.Module)
+    assert L.load_diffusers_vae_from_pretrained(str(tmp_path / "nope")) is None
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without the CUDA path (never route to a CPU implementation)."""
+    wrap = L.DiffusersVAEWrapper(L.load_diffusers_vae_from_config(L.get_diffusers_vae_config())).eval()
+    with pytest.raises(_native.NativeError):
+        wrap.encode(torch.zeros(1, 3, 64, 64))
+    dec = M.create_attention_decoder(16, 8, 8, 11, attention_config={}).eval()
+    with pytest.raises(_native.NativeError):
+        dec(torch.zeros(1, 16, 8, 8))
+    with pytest.raises(_native.NativeError):
+        dec.get_confidence(torch.zeros(1, 16, 8, 8))
+    with pytest.raises(NotImplementedError):
+        wrap.vae.decode(torch.zeros(1, 16, 8, 8))
+
+
+def test_train_mode_head_is_differentiable_and_matches_oracle(golden):
+    """train_decoder.py keeps a PyTorch graph in train() mode; with dropout off and BN in eval it must
+    agree with the reference outputs."""
+    c = golden["attention_head"]["att_T11_64x64"]
+    sd = dict(golden["attention_head_base"]); sd.update(c["state_dict"])
+    dec = M.create_attention_decoder(16, 64, 64, 11, attention_config={})
+    dec.load_state_dict(sd)
+    dec.train()
+    for m in dec.modules():
+        if isinstance(m, (torch.nn.Dropout, torch.nn.BatchNorm2d)):
+            m.eval()
+    out = dec(c["latent"])
+    assert torch.allclose(out, c["logits"], atol=1e-5)
+    out.sum().backward()
+    assert all(p.grad is not None for p in dec.parameters())
+
+
+def test_package_does_not_import_oracle():
+    import os
+    import re
+
+    root = os.path.dirname(os.path.abspath(M.__file__))
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

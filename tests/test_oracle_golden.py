@@ -1,0 +1,95 @@
+"""CPU: pin the oracle.  The head / loss / wrapper restatements are checked against golden vectors
+produced by the reference's OWN code (tests/golden/make_golden.py, run in the build container where
+/root/reference exists).  The encoder restatement is "parity unpinned" by the reference (diffusers is
+not installable here) and is pinned by known answers only."""
+import math
+
+import pytest
+import torch
+
+from oracle import encoder as OE
+from oracle import head as OH
+
+
+def full_sd(golden, case):
+    sd = dict(golden["attention_head_base"])
+    sd.update(golden["attention_head"][case]["state_dict"])
+    return sd
+
+
+@pytest.mark.parametrize("case", ["att_T11_64x64", "att_T37_40x24", "att_T1000_16x16"])
+def test_head_oracle_matches_reference_outputs(golden, case):
+    c = golden["attention_head"][case]
+    sd = full_sd(golden, case)
+    sa = OH.spatial_attention(sd, c["latent"])
+    assert torch.allclose(sa, c["spatial"], atol=1e-6)
+    fc = OH.feature_compress(sd, sa)
+    assert torch.allclose(fc, c["compressed"], atol=1e-6)
+    at = OH.self_attention(sd, fc)
+    assert torch.allclose(at, c["attended"], atol=1e-6)
+    logits = OH.attention_decoder_logits(sd, c["latent"])
+    assert torch.allclose(logits, c["logits"], atol=1e-5)
+    conf, idx = OH.get_confidence(logits)
+    assert torch.allclose(conf, c["conf"], atol=1e-6)
+    assert (idx == c["idx"]).float().mean() > 0.99
+
+
+def test_plain_head_oracle(golden):
+    c = golden["plain_head"]
+    assert torch.allclose(OH.plain_decoder_logits(c["state_dict"], c["latent"]), c["logits"], atol=1e-5)
+
+
+def test_focal_oracle(golden):
+    f = golden["focal"]
+    for (a, g), want in f["cases"].items():
+        assert torch.allclose(OH.focal_loss(f["logits"], f["targets"], a, g), want["loss"], atol=1e-7)
+        assert torch.allclose(OH.focal_loss_grad(f["logits"], f["targets"], a, g), want["grad"], atol=1e-7)
+    # known answer: FocalLoss(1,2) at logit 0 = 0.25*ln2
+    assert abs(f["at_zero"].item() - 0.25 * math.log(2)) < 1e-7
+    assert abs(OH.focal_loss(torch.zeros(4, 7), torch.ones(4, 7)).item() - 0.173286795) < 1e-7
+
+
+def test_wrapper_scale_shift(golden):
+    w = golden["wrapper"]
+    assert torch.allclose(w["mean"] * 0.3611 + 0.1159, w["latent"], atol=1e-7)
+
+
+def test_head_param_count_and_keys(golden):
+    assert golden["att_T1000_param_count"] == 1_443_666 == 1_186_666 + 257 * 1000
+
+
+def test_encoder_known_answers():
+    vae = OE.make_oracle_vae(seed=0)
+    sd = vae.state_dict()
+    assert sum(p.numel() for p in vae.parameters()) == 34_274_208
+    assert len(sd) == 106
+    assert sd["encoder.conv_in.weight"].shape == (128, 3, 3, 3)
+    assert sd["encoder.conv_out.weight"].shape == (32, 512, 3, 3)
+    assert sd["encoder.down_blocks.1.resnets.0.conv_shortcut.weight"].shape == (256, 128, 1, 1)
+    assert "encoder.down_blocks.3.downsamplers.0.conv.weight" not in sd
+    x = OE.synthetic_images(1, 64, 64)
+    with torch.no_grad():
+        moments = vae.encoder(x)
+        lat = OE.oracle_wrapper_encode(vae, x)
+    assert moments.shape == (1, 32, 8, 8) and lat.shape == (1, 16, 8, 8)
+    d = OE.OracleDiagonalGaussian(moments)
+    assert torch.equal(d.mode(), moments[:, :16])
+    assert torch.allclose(lat, moments[:, :16] * 0.3611 + 0.1159)
+    noise = torch.randn(1, 16, 8, 8, generator=torch.Generator().manual_seed(0))
+    assert torch.allclose(d.sample(noise=noise), d.mean + torch.exp(0.5 * d.logvar) * noise)
+    assert d.kl().shape == (1,)
+    # determinism of the generators
+    assert torch.equal(OE.synthetic_images(2, 8, 8)[1], OE.synthetic_images(3, 8, 8)[1])
+    assert torch.equal(OE.make_oracle_vae(0).state_dict()["encoder.conv_in.bias"], sd["encoder.conv_in.bias"])
+
+
+def test_downsample_pads_right_and_bottom_only():
+    d = OE.OracleDownsample2D(4)
+    with torch.no_grad():
+        d.conv.weight.zero_(); d.conv.bias.zero_()
+        d.conv.weight[:, :, 2, 2] = 1.0  # only the bottom-right tap
+        x = torch.ones(1, 4, 4, 4)
+        y = d(x)
+    # last output row/column read the zero padding
+    assert y.shape == (1, 4, 2, 2)
+    assert y[0, 0, 0, 0] == 4 and y[0, 0, 1, 1] == 0 and y[0, 0, 0, 1] == 0

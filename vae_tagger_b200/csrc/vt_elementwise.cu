@@ -161,8 +161,8 @@ int launch_gn_stats(const void* x, int is_fp32, double* stats, int N, long long 
 // (sum, sumsq) doubles.  One thread owns 8 consecutive channels of a fixed channel block and
 // walks pixels, so scale/shift live in registers; every access is a 16-byte (bf16) or 2x16-byte
 // (fp32) vector and a warp touches 512 contiguous bytes.
-template <typename T, bool FAST>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y,
+template <typename TI, typename TO, bool FAST>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y,
                                                        const double* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, long long HW, int C, int G,
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
         for (long long p = p0 + psub; p < p1; p += ppb) {
             const long long off = (1LL * n * HW + p) * C + c8 * 8;
             float v[8];
-            if constexpr (sizeof(T) == 2) {
+            if constexpr (sizeof(TI) == 2) {
                 const uint4 u = *reinterpret_cast<const uint4*>(x + off);
                 v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
                 v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
                 }
                 v[e] = t;
             }
-            if constexpr (sizeof(T) == 2) {
+            if constexpr (sizeof(TO) == 2) {
                 *reinterpret_cast<uint4*>(y + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                                 pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
             } else {
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
     }
 }
 
-int launch_gn_apply(const void* x, void* y, int is_fp32, const double* stats, const float* gamma,
+int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fp32, const double* stats, const float* gamma,
                     const float* beta, int N, long long HW, int C, int G, float eps, int silu, cudaStream_t s,
                     Profiler* prof) {
     VT_CHECK(C % 8 == 0 && C % G == 0, "GroupNorm apply needs C % 8 == 0 and C % groups == 0");
@@ -233,13 +233,20 @@ int launch_gn_apply(const void* x, void* y, int is_fp32, const double* stats, co
     const long long cap = std::max(1, sm_count() * 16 / N);
     const int chunks = static_cast<int>(std::max<long long>(1, std::min(want, cap)));
     dim3 grid(chunks, N);
-    profiler_begin(prof, KC_GN_APPLY, s, 0, 2.0 * N * HW * C * (is_fp32 ? 4 : 2));
-    if (is_fp32)
-        gn_apply_kernel<float, false><<<grid, 256, 0, s>>>(static_cast<const float*>(x), static_cast<float*>(y),
-                                                           stats, gamma, beta, HW, C, G, eps, silu);
-    else
-        gn_apply_kernel<bf16, true><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), stats,
-                                                         gamma, beta, HW, C, G, eps, silu);
+    profiler_begin(prof, KC_GN_APPLY, s, 0, 1.0 * N * HW * C * ((x_fp32 ? 4 : 2) + (y_fp32 ? 4 : 2)));
+    if (x_fp32 && y_fp32)
+        gn_apply_kernel<float, float, false><<<grid, 256, 0, s>>>(static_cast<const float*>(x), static_cast<float*>(y),
+                                                                  stats, gamma, beta, HW, C, G, eps, silu);
+    else if (x_fp32)
+        gn_apply_kernel<float, bf16, true><<<grid, 256, 0, s>>>(static_cast<const float*>(x), static_cast<bf16*>(y),
+                                                                stats, gamma, beta, HW, C, G, eps, silu);
+    else if (!y_fp32)
+        gn_apply_kernel<bf16, bf16, true><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y),
+                                                               stats, gamma, beta, HW, C, G, eps, silu);
+    else {
+        set_error("GroupNorm apply bf16 -> fp32 is not instantiated");
+        return -2;
+    }
     profiler_end(prof, KC_GN_APPLY, s);
     VT_CUDA(cudaGetLastError());
     return 0;

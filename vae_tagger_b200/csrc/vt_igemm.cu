@@ -141,7 +141,7 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     VT_CHECK(op.stats == nullptr || (op.Cout % 32 == 0 && (P.group_size == 4 || P.group_size == 8 || P.group_size == 16)),
              "fused GroupNorm statistics need 4, 8 or 16 channels per group");
     P.alpha = op.alpha;
-    P.bias = op.bias; P.residual = static_cast<const bf16*>(op.residual); P.out = op.out; P.ld_out = op.Cout;
+    P.bias = op.bias; P.residual = op.residual; P.res_fp32 = op.residual_fp32; P.out = op.out; P.ld_out = op.Cout;
     P.out_bstride = 1LL * Hout * Wout * op.Cout; P.stats = op.stats;
 
     int ns = 0;
@@ -202,7 +202,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     VT_CHECK(op.stats == nullptr || (P.group_size == 4 || P.group_size == 8 || P.group_size == 16),
              "fused GroupNorm statistics need 4, 8 or 16 channels per group");
     P.alpha = op.alpha;
-    P.bias = op.bias; P.residual = static_cast<const bf16*>(op.residual); P.out = op.out; P.ld_out = ldo;
+    P.bias = op.bias; P.residual = op.residual; P.res_fp32 = op.residual_fp32; P.out = op.out; P.ld_out = ldo;
     P.out_bstride = op.out_bstride ? op.out_bstride : 1LL * op.M * ldo; P.stats = op.stats;
     P.num_slabs = 1;
     P.slabs[0] = IgemmSlab{0, 0, 0, 0, 0, 0, op.K / 64, 0};

@@ -49,10 +49,11 @@ struct IgemmParams {
     int a_batched;         // A coordinate 4 = image index (0: shared operand)
     int b_batched;         // B coordinate 2 = image index (0: shared operand)
     int out_fp32;          // output element type: 0 bf16, 1 fp32
+    int res_fp32;          // residual element type: 0 bf16, 1 fp32
     int group_size;        // channels per GroupNorm group for the fused statistics; 0 = off
     float alpha;
     const float* bias;              // [n_total] or nullptr
-    const __nv_bfloat16* residual;  // same geometry as out, or nullptr
+    const void* residual;  // same geometry as out (bf16 or fp32), or nullptr
     void* out;
     long long ld_out;      // elements between consecutive pixels of out / residual
     long long out_bstride;  // elements between consecutive images of out / residual
@@ -286,14 +287,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                     }
                 }
                 if (P.residual != nullptr && valid) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(P.residual + off + j * 32);
+                    if (P.res_fp32) {
+                        const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(P.residual) + off + j * 32);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint4 u = __ldg(rp + i);
-                        v[8 * i] += bf16_lo(u.x); v[8 * i + 1] += bf16_hi(u.x);
-                        v[8 * i + 2] += bf16_lo(u.y); v[8 * i + 3] += bf16_hi(u.y);
-                        v[8 * i + 4] += bf16_lo(u.z); v[8 * i + 5] += bf16_hi(u.z);
-                        v[8 * i + 6] += bf16_lo(u.w); v[8 * i + 7] += bf16_hi(u.w);
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 u = __ldg(rp + i);
+                            v[4 * i] += u.x; v[4 * i + 1] += u.y; v[4 * i + 2] += u.z; v[4 * i + 3] += u.w;
+                        }
+                    } else {
+                        const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.residual) + off + j * 32);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 u = __ldg(rp + i);
+                            v[8 * i] += bf16_lo(u.x); v[8 * i + 1] += bf16_hi(u.x);
+                            v[8 * i + 2] += bf16_lo(u.y); v[8 * i + 3] += bf16_hi(u.y);
+                            v[8 * i + 4] += bf16_lo(u.z); v[8 * i + 5] += bf16_hi(u.z);
+                            v[8 * i + 6] += bf16_lo(u.w); v[8 * i + 7] += bf16_hi(u.w);
+                        }
                     }
                 }
                 if (P.group_size != 0) {

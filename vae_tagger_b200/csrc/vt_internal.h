@@ -73,6 +73,7 @@ struct ConvOp {
     int Cs = 0;
     const float* bias = nullptr;     // [Cout]
     const void* residual = nullptr;  // [N][Hout][Wout][Cout]
+    int residual_fp32 = 0;           // residual element type (tcgen05 path; the fp32 path is all fp32)
     void* out = nullptr;             // [N][Hout][Wout][Cout] bf16 or fp32
     int out_fp32 = 0;
     double* stats = nullptr;  // [N][32][2] GroupNorm (sum, sumsq) of the output (group = Cout/32 channels)
@@ -91,6 +92,7 @@ struct GemmOp {
     long long a_bstride = 0, b_bstride = 0;  // batch strides in elements (default rows * ld)
     const float* bias = nullptr;
     const void* residual = nullptr;
+    int residual_fp32 = 0;
     void* out = nullptr;
     int out_fp32 = 0;
     long long ld_out = 0;       // default N
@@ -105,7 +107,7 @@ int launch_im2col3x3(const void* in, int fmt, void* out, int out_fp32, int N, in
                      Profiler*);
 int launch_gn_stats(const void* x, int is_fp32, double* stats, int N, long long HW, int C, int G, cudaStream_t,
                     Profiler*);
-int launch_gn_apply(const void* x, void* y, int is_fp32, const double* stats, const float* gamma,
+int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fp32, const double* stats, const float* gamma,
                     const float* beta, int N, long long HW, int C, int G, float eps, int silu, cudaStream_t,
                     Profiler*);
 int launch_softmax_rows(const float* s, void* p, int p_fp32, long long rows, int cols, long long ld_s,
