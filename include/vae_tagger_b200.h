@@ -10,8 +10,10 @@
  *     returns a thread-local, NUL-terminated description.  No exceptions cross the ABI.
  *   - plain pointers and sizes only.  "device pointer" = CUDA device memory of the
  *     context's device, caller-owned.  Workspace is owned by the context.
- *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*; NULL =
- *     legacy default stream); no hidden synchronisation except where stated (host variants).
+ *   - all work is ordered on the caller's stream (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream): it starts after everything already enqueued there and later work on that
+ *     stream waits for it.  vt_encode may fan micro-batches out to two internal streams (joined
+ *     back with events).  No host synchronisation except where stated (host variants).
  *   - one context per device / per rank; a context is not thread-safe.
  *   - tensors are fp32, PyTorch layouts (NCHW activations, OIHW conv weights, [out][in]
  *     linear weights) at the boundary; the NHWC bf16 layout used internally never leaks.
@@ -81,6 +83,7 @@ typedef struct vt_encode_args {
     float* mean;              /* out, optional: DiagonalGaussianDistribution.mean */
     float* logvar;            /* out, optional: clamped logvar */
     int micro_batch;          /* images per internal pass; 0 = library default */
+    int single_lane;          /* 1: run micro-batches back to back on the caller's stream (no overlap) */
     void* stream;
 } vt_encode_args;
 

@@ -39,7 +39,7 @@ class EncodeArgs(C.Structure):
         ("images", C.c_void_p), ("in_fmt", C.c_int), ("batch", C.c_int), ("height", C.c_int), ("width", C.c_int),
         ("precision", C.c_int), ("sample", C.c_int), ("apply_scale_shift", C.c_int), ("seed", C.c_uint64),
         ("noise", C.c_void_p), ("latent", C.c_void_p), ("mean", C.c_void_p), ("logvar", C.c_void_p),
-        ("micro_batch", C.c_int), ("stream", C.c_void_p),
+        ("micro_batch", C.c_int), ("single_lane", C.c_int), ("stream", C.c_void_p),
     ]
 
 
@@ -201,7 +201,7 @@ class Context:
         _check(self.lib.vt_encoder_finalize(self.h))
 
     def encode(self, images: torch.Tensor, precision=PREC_BF16, sample=False, apply_scale_shift=True, seed=0,
-               noise: Optional[torch.Tensor] = None, want_moments=False, micro_batch=0):
+               noise: Optional[torch.Tensor] = None, want_moments=False, micro_batch=0, single_lane=False):
         """images: [B,3,H,W] float (any float dtype; normalised) or [B,H,W,3] uint8, on this device.
         Returns latent [B,LC,H/8,W/8] fp32 (and mean, logvar when want_moments)."""
         if images.dtype == torch.uint8:
@@ -229,6 +229,7 @@ class Context:
         a.mean = mean.data_ptr() if mean is not None else None
         a.logvar = logvar.data_ptr() if logvar is not None else None
         a.micro_batch = int(micro_batch)
+        a.single_lane = int(bool(single_lane))
         a.stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             _check(self.lib.vt_encode(self.h, C.byref(a)))

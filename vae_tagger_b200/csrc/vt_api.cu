@@ -77,9 +77,17 @@ struct vt_ctx {
     ResnetW mid0, mid1;
     AttnW attn;
     NormW norm_out;
-    DevBuf arena;  // activation workspace
-    DevBuf stats;  // GroupNorm (sum, sumsq) slots
-    DevBuf mom;    // conv_out moments fp32 NHWC
+    // Two execution lanes: consecutive micro-batches of one vt_encode call alternate between two
+    // internal streams with private workspaces, so the HBM-bound passes (GroupNorm apply, softmax) of
+    // one micro-batch run under the tensor-bound contractions of the other and kernel tails overlap.
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        DevBuf arena;  // activation workspace
+        DevBuf stats;  // GroupNorm (sum, sumsq) slots
+        DevBuf mom;    // conv_out moments fp32 NHWC
+    } lanes[2];
+    cudaEvent_t ev_start = nullptr;
 
     // ---- head
     vt_head_config hcfg{};
@@ -340,7 +348,7 @@ struct EncRun {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int run_encoder_microbatch(vt_ctx* c, const vt_encode_args* a, int img0, int n, cudaStream_t s) {
+int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, int img0, int n, cudaStream_t s) {
     const vt_encoder_config& cfg = c->ecfg;
     const int H = a->height, Wd = a->width;
     const int fp32 = a->precision == VT_PREC_FP32;
@@ -367,7 +375,8 @@ int run_encoder_microbatch(vt_ctx* c, const vt_encode_args* a, int img0, int n, 
     size_t attn_bytes = 0;
     long long rows_per_chunk = 0;
     int ipc = 1;
-    size_t qk_b = 0, vt_b = 0, s_b = 0, p_b = 0, o_b = 0;
+    size_t qk_b = 0, vt_b = 0, s_b = 0, p_b = 0, o_b = 0, part_b = 0;
+    int pv_splits = 1;
     if (cfg.mid_block_add_attention) {
         const size_t s_budget = 64ull << 20;  // score tile kept L2 resident
         const long long max_rows = static_cast<long long>(s_budget / (tokens * 4));
@@ -383,10 +392,20 @@ int run_encoder_microbatch(vt_ctx* c, const vt_encode_args* a, int img0, int n, 
         s_b = align_up(static_cast<size_t>(ipc) * rows_per_chunk * tokens * 4, 1024);
         p_b = align_up(static_cast<size_t>(ipc) * rows_per_chunk * tokens * es, 1024);
         o_b = vt_b;
-        attn_bytes = qk_b + vt_b + s_b + p_b + o_b;
+        // P.V of a row chunk has only ceil(rows/128) * C/256 output tiles: split K (= tokens) across
+        // CTAs when that leaves most of the machine idle, combine the fp32 partials afterwards
+        if (!fp32 && ipc == 1) {
+            const long long tiles = (rows_per_chunk + 127) / 128 * ((Cm + 255) / 256);
+            const long long kchunks = tokens / 64;
+            int want = static_cast<int>(std::min<long long>(16, 148 / std::max<long long>(1, tiles)));
+            while (want > 1 && kchunks % want != 0) --want;
+            pv_splits = std::max(1, want);
+            if (pv_splits > 1) part_b = align_up(static_cast<size_t>(pv_splits) * rows_per_chunk * Cm * 4, 1024);
+        }
+        attn_bytes = qk_b + vt_b + s_b + p_b + o_b + part_b;
     }
-    VT_TRY(c->arena.ensure(4 * act + attn_bytes));
-    char* base = static_cast<char*>(c->arena.p);
+    VT_TRY(L.arena.ensure(4 * act + attn_bytes));
+    char* base = static_cast<char*>(L.arena.p);
     void* Xp = base;           // residual stream
     void* T = base + act;      // normalised operand
     void* Hb = base + 2 * act; // conv1 output / conv_in gather
@@ -395,11 +414,11 @@ int run_encoder_microbatch(vt_ctx* c, const vt_encode_args* a, int img0, int n, 
 
     const int groups = cfg.norm_num_groups;
     const int max_slots = 64;
-    VT_TRY(c->stats.ensure(static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double)));
-    VT_CUDA(cudaMemsetAsync(c->stats.p, 0, static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double), s));
-    VT_TRY(c->mom.ensure(static_cast<size_t>(n) * tokens * 2 * LC * sizeof(float)));
+    VT_TRY(L.stats.ensure(static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double)));
+    VT_CUDA(cudaMemsetAsync(L.stats.p, 0, static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double), s));
+    VT_TRY(L.mom.ensure(static_cast<size_t>(n) * tokens * 2 * LC * sizeof(float)));
 
-    EncRun R{c, s, fp32, n, static_cast<double*>(c->stats.p), 0, groups};
+    EncRun R{c, s, fp32, n, static_cast<double*>(L.stats.p), 0, groups};
 
     // ---- conv_in: gather the 3x3x3 patches (K = 27 padded to 64) then one K chunk of contraction
     const char* img = static_cast<const char*>(a->images);
@@ -458,6 +477,7 @@ int run_encoder_microbatch(vt_ctx* c, const vt_encode_args* a, int img0, int n, 
         char* S = Vt + vt_b;
         char* P = S + s_b;
         char* O = P + p_b;
+        char* PART = O + o_b;
         VT_TRY(R.gn(X, T, st_x, A.gn, tokens, C, 0));
         {   // [q | k] = t Wqk^T + b : [n][tokens][2C]
             GemmOp g;
@@ -488,7 +508,19 @@ int run_encoder_microbatch(vt_ctx* c, const vt_encode_args* a, int img0, int n, 
                 }
                 VT_TRY(launch_softmax_rows(reinterpret_cast<const float*>(S), P, fp32, 1LL * nb_img * rows,
                                            static_cast<int>(tokens), tokens, tokens, s, c->prof));
-                {   // O = P V + b_v
+                if (pv_splits > 1) {
+                    // O = P V + b_v with K split: batch index = K slice, fp32 partials, then combine
+                    const long long ks = tokens / pv_splits;
+                    GemmOp g;
+                    g.A = P; g.lda = tokens; g.a_bstride = ks;
+                    g.B = Vt + static_cast<size_t>(i0) * C * tokens * es; g.ldb = tokens; g.b_bstride = ks;
+                    g.batch = pv_splits; g.M = rows; g.N = C; g.K = static_cast<int>(ks);
+                    g.out = PART; g.out_fp32 = 1; g.ld_out = C; g.out_bstride = 1LL * rows * C;
+                    VT_TRY(R.gemm(g, 0));
+                    VT_TRY(launch_splitk_reduce(reinterpret_cast<const float*>(PART), pv_splits, 1LL * rows * C, A.v.bias,
+                                                reinterpret_cast<bf16*>(O + (static_cast<size_t>(i0) * tokens + r0) * C * es),
+                                                rows, C, C, s, c->prof));
+                } else {   // O = P V + b_v
                     GemmOp g;
                     g.A = P; g.lda = tokens; g.a_bstride = 1LL * rows * tokens;
                     g.B = Vt + static_cast<size_t>(i0) * C * tokens * es; g.ldb = tokens; g.b_bstride = 1LL * C * tokens;
@@ -521,9 +553,9 @@ int run_encoder_microbatch(vt_ctx* c, const vt_encode_args* a, int img0, int n, 
     }
     // ---- conv_norm_out + SiLU + conv_out -> moments (fp32 NHWC) -> DiagonalGaussian outputs
     VT_TRY(R.gn(X, T, st_x, c->norm_out, tokens, Cm, 1));
-    VT_TRY(R.conv(T, h, w_, c->conv_out, 1, nullptr, nullptr, Act{c->mom.p, 1}, nullptr));
+    VT_TRY(R.conv(T, h, w_, c->conv_out, 1, nullptr, nullptr, Act{L.mom.p, 1}, nullptr));
     const size_t lat_stride = static_cast<size_t>(LC) * tokens;
-    VT_TRY(launch_moments_to_latent(static_cast<const float*>(c->mom.p),
+    VT_TRY(launch_moments_to_latent(static_cast<const float*>(L.mom.p),
                                     a->latent ? a->latent + lat_stride * img0 : nullptr,
                                     a->mean ? a->mean + lat_stride * img0 : nullptr,
                                     a->logvar ? a->logvar + lat_stride * img0 : nullptr,
@@ -581,6 +613,11 @@ int vt_ctx_create(int device, vt_ctx** out) {
     vt_ctx* c = new vt_ctx();
     c->device = device;
     c->prof = profiler_create();
+    for (auto& L : c->lanes) {
+        VT_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        VT_CUDA(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    }
+    VT_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
     *out = c;
     return 0;
 }
@@ -592,7 +629,13 @@ int vt_ctx_destroy(vt_ctx* c) {
     free_packed(c);
     free_params(c->eparams);
     free_params(c->hparams);
-    c->arena.release(); c->stats.release(); c->mom.release(); c->hws.release(); c->e2e.release(); c->opws.release();
+    for (auto& L : c->lanes) {
+        L.arena.release(); L.stats.release(); L.mom.release();
+        if (L.stream) cudaStreamDestroy(L.stream);
+        if (L.done) cudaEventDestroy(L.done);
+    }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    c->hws.release(); c->e2e.release(); c->opws.release();
     profiler_destroy(c->prof);
     delete c;
     return 0;
@@ -679,12 +722,27 @@ int vt_encode(vt_ctx* c, const vt_encode_args* a) {
     cudaStream_t s = static_cast<cudaStream_t>(a->stream);
     int mb = a->micro_batch;
     if (mb <= 0) {
-        // keep the top-level activation of one pass near 2 GB (bf16) so four ping-pong buffers stay small
+        // keep the top-level activation of one pass near 1 GB (bf16): 2 lanes x 4 ping-pong buffers
         const double per_img = 1.0 * a->height * a->width * c->ecfg.block_out_channels[0] * 2;
-        mb = static_cast<int>(std::max(1.0, std::min(32.0, (2.2e9) / per_img)));
+        mb = static_cast<int>(std::max(1.0, std::min(32.0, (1.1e9) / per_img)));
     }
-    for (int i0 = 0; i0 < a->batch; i0 += mb)
-        VT_TRY(run_encoder_microbatch(c, a, i0, std::min(mb, a->batch - i0), s));
+    if (mb >= a->batch || a->single_lane) {
+        for (int i0 = 0; i0 < a->batch; i0 += mb)
+            VT_TRY(run_encoder_microbatch(c, c->lanes[0], a, i0, std::min(mb, a->batch - i0), s));
+        return 0;
+    }
+    // several micro-batches: alternate between the two lanes
+    VT_CUDA(cudaEventRecord(c->ev_start, s));
+    for (auto& L : c->lanes) VT_CUDA(cudaStreamWaitEvent(L.stream, c->ev_start, 0));
+    int k = 0;
+    for (int i0 = 0; i0 < a->batch; i0 += mb, ++k) {
+        vt_ctx::Lane& L = c->lanes[k & 1];
+        VT_TRY(run_encoder_microbatch(c, L, a, i0, std::min(mb, a->batch - i0), L.stream));
+    }
+    for (auto& L : c->lanes) {
+        VT_CUDA(cudaEventRecord(L.done, L.stream));
+        VT_CUDA(cudaStreamWaitEvent(s, L.done, 0));
+    }
     return 0;
 }
 

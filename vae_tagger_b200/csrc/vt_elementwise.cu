@@ -500,6 +500,35 @@ int launch_nhwc_to_nchw(const void* in, int in_fp32, float* out, int N, int C, l
     return 0;
 }
 
+// Split-K combine: out[r][c] = bias[c] + sum_s part[s][r][c]  (part fp32, out bf16; 4 columns / thread)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits,
+                                                            long long split_stride, const float* __restrict__ bias,
+                                                            bf16* __restrict__ out, long long rows, int cols,
+                                                            long long ld_out) {
+    const long long total = rows * (cols / 4);
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const long long r = i / (cols / 4);
+        const int c = static_cast<int>(i % (cols / 4)) * 4;
+        float4 a = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < splits; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(part + s * split_stride + r * cols + c);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        *reinterpret_cast<uint2*>(out + r * ld_out + c) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+    }
+}
+int launch_splitk_reduce(const float* part, int splits, long long split_stride, const float* bias, bf16* out,
+                         long long rows, int cols, long long ld_out, cudaStream_t s, Profiler* prof) {
+    VT_CHECK(cols % 4 == 0, "split-K combine needs a column count divisible by 4");
+    const long long total = rows * (cols / 4);
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 1LL * sm_count() * 8));
+    profiler_begin(prof, KC_MISC, s, 0, 4.0 * splits * rows * cols + 2.0 * rows * cols);
+    splitk_reduce_kernel<<<grid, 256, 0, s>>>(part, splits, split_stride, bias, out, rows, cols, ld_out);
+    profiler_end(prof, KC_MISC, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // fp32 -> bf16 (weights packing) with an arbitrary gather done on the host side; plain cast here.
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
                                                             long long n) {

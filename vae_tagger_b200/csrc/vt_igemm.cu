@@ -68,7 +68,7 @@ static int launch_variant(const CUtensorMap& a0, const CUtensorMap& a1, const CU
     }
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y * P.n_blocks;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    igemm_kernel<BLOCK_N><<<grid, IGEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, P);
+    igemm_kernel<BLOCK_N><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, P);
     VT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -130,7 +130,7 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
 
     IgemmParams P{};
     P.W = Wout; P.H = Hout; P.NB = op.N;
-    P.tw = 16; P.th = 8;
+    P.tw = 16; P.th = 8; P.tw_log2 = 4;
     P.tiles_x = (Wout + P.tw - 1) / P.tw;
     P.tiles_y = (Hout + P.th - 1) / P.th;
     P.n_total = op.Cout;
@@ -191,7 +191,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
 
     IgemmParams P{};
     P.W = op.M; P.H = 1; P.NB = op.batch;
-    P.tw = 128; P.th = 1;
+    P.tw = 128; P.th = 1; P.tw_log2 = 7;
     P.tiles_x = (op.M + 127) / 128;
     P.tiles_y = 1;
     P.n_total = op.N;

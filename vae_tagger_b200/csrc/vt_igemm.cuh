@@ -13,9 +13,8 @@
 //   D: fp32 accumulator in TMEM (tcgen05.mma cta_group::1, M=128, N=BLOCK_N, K=16),
 //      double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias/residual/GroupNorm partial sums ->
-// bf16|fp32 global stores).  Persistent CTAs, static round-robin tile order with the
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2.. = epilogue
+// (TMEM -> smem staging -> bias/residual/GroupNorm partial sums -> coalesced bf16|fp32 stores).  Persistent CTAs, static round-robin tile order with the
 // n-blocks of one pixel tile adjacent (they share the A tile through L2).
 #pragma once
 #include "vt_ptx.cuh"
@@ -26,7 +25,6 @@ constexpr int IGEMM_BLOCK_M = 128;
 constexpr int IGEMM_BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int IGEMM_A_BYTES = IGEMM_BLOCK_M * IGEMM_BLOCK_K * 2;
 constexpr int IGEMM_MAX_SLABS = 10;
-constexpr int IGEMM_THREADS = 192;
 
 struct IgemmSlab {
     int map;      // 0 / 1: which A tensor map
@@ -41,7 +39,8 @@ struct IgemmSlab {
 
 struct IgemmParams {
     int W, H, NB;          // output pixels per row / rows / images (plain GEMM: W=M, H=1, NB=batch)
-    int tw, th;            // M-tile patch, tw*th == 128
+    int tw, th;            // M-tile patch, tw*th == 128, tw a power of two
+    int tw_log2;
     int tiles_x, tiles_y;  // patches per image
     int n_total;           // valid output channels (multiple of 32)
     int n_blocks;          // ceil(n_total / BLOCK_N)
@@ -62,82 +61,54 @@ struct IgemmParams {
     IgemmSlab slabs[IGEMM_MAX_SLABS];
 };
 
-// Reduce V (power of two <= 32) per-thread values across the warp with V-1 + (5-log2 V)
-// shuffles instead of 5*V: after the call lane l holds the total of value (l >> (5 - log2 V)).
-template <int V>
-__device__ __forceinline__ float warp_multi_reduce(float (&a)[V], int lane) {
-    int n = V;
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        if (n > 1) {
-            const int half = n / 2;
-            const bool upper = (lane & o) != 0;
-#pragma unroll
-            for (int i = 0; i < V / 2; ++i) {
-                if (i < half) {
-                    const float send = upper ? a[i] : a[i + half];
-                    const float keep = upper ? a[i + half] : a[i];
-                    a[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, o);
-                }
-            }
-            n = half;
-        } else {
-            a[0] += __shfl_xor_sync(0xFFFFFFFFu, a[0], o);
-        }
-    }
-    return a[0];
-}
-
-template <int G>  // G = channels per group (4, 8, 16): accumulate one 32-column chunk
-__device__ __forceinline__ void stats_chunk(const float (&v)[32], bool valid, int lane, float* s_acc) {
-    constexpr int NG = 32 / G;
-    constexpr int V = 2 * NG;
-    float a[V];
-#pragma unroll
-    for (int k = 0; k < NG; ++k) {
-        float s = 0.f, ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < G; ++i) {
-            const float x = v[k * G + i];
-            s += x;
-            ss = fmaf(x, x, ss);
-        }
-        a[2 * k] = valid ? s : 0.f;
-        a[2 * k + 1] = valid ? ss : 0.f;
-    }
-    const float tot = warp_multi_reduce<V>(a, lane);
-    constexpr int SH = (V == 16) ? 1 : (V == 8) ? 2 : 3;
-    if ((lane & ((1 << SH) - 1)) == 0) atomicAdd(&s_acc[lane >> SH], tot);
-}
-
 template <int BLOCK_N>
 struct IgemmCfg {
     static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;
     static constexpr int STAGE_BYTES = IGEMM_A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    // epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, splitting the columns)
+    static constexpr int EPI_WARPS = (BLOCK_N == 128) ? 8 : 4;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int COLS_PER_WARP = BLOCK_N / (EPI_WARPS / 4);
+    static constexpr int PASSES = COLS_PER_WARP / 32;
+    static constexpr int STAGE_ROW_FLOATS = 36;  // 32 columns + 4 pad: conflict-free 16-byte rows
+    static constexpr int EPI_STAGING_BYTES = EPI_WARPS * 32 * STAGE_ROW_FLOATS * 4;
+    static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 5 : 8);
     static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                      : (2 * BLOCK_N <= 256) ? 256 : 512;
     static constexpr int BAR_BYTES = 1024;  // barriers, tmem pointer, stats scratch
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
+// Epilogue (v2).  Each epilogue warp owns one TMEM lane quadrant (32 accumulator rows = 32 output
+// pixels) and a column range, processed in passes of 32 columns:
+//   phase A  tcgen05.ld: thread t = row t, 32 fp32 columns -> per-warp smem staging tile [32][32(+4)]
+//   phase B  lanes re-map to (row = 4*it + lane/8, 4 columns = lane%8): staging -> registers, * alpha,
+//            + bias, + residual (coalesced global loads issued before phase A), GroupNorm partial sums
+//            accumulated per lane over its 8 rows, bf16/fp32 pack, coalesced global stores (8 lanes
+//            cover 32 consecutive channels of one pixel, a warp instruction covers 4 pixels).
+// Statistics: the 4 columns of a lane lie in one group (group sizes are multiples of 4); after the 8
+// rows, two shuffles fold the 4 row-slots and 8 lanes add into the CTA's smem accumulators.
 template <int BLOCK_N>
-__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+__global__ void __launch_bounds__(IgemmCfg<BLOCK_N>::THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ IgemmParams P) {
     using Cfg = IgemmCfg<BLOCK_N>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int EPI_WARPS = Cfg::EPI_WARPS;
+    constexpr int RF = Cfg::STAGE_ROW_FLOATS;
     static_assert(2 * BLOCK_N <= 512, "two accumulators must fit TMEM");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* ctrl = smem + STAGES * Cfg::STAGE_BYTES;
+    float* staging_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* ctrl = smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGING_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);      // [STAGES]
     uint64_t* empty_bar = full_bar + STAGES;                     // [STAGES]
     uint64_t* tfull_bar = empty_bar + STAGES;                    // [2]
     uint64_t* tempty_bar = tfull_bar + 2;                        // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* s_stats = reinterpret_cast<float*>(ctrl + 256);       // [2][128]
+    float* s_stats = reinterpret_cast<float*>(ctrl + 256);       // [2][128]: (sum, sumsq) per group of the n-block
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -155,7 +126,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], EPI_WARPS);
         }
         fence_mbar_init();
     }
@@ -164,7 +135,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         tmem_relinquish();
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < 256; i += 128) s_stats[i] = 0.f;
+        for (int i = threadIdx.x - 64; i < 256; i += 32 * EPI_WARPS) s_stats[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -236,10 +207,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
-        const int q = warp & 3;           // TMEM lane quadrant this warp may access
-        const int row = q * 32 + lane;    // accumulator row = pixel within the patch
-        const int et = threadIdx.x - 64;  // 0..127
+        // ------------------------------------------------------------ epilogue warps
+        const int ew = warp - 2;            // 0 .. EPI_WARPS-1
+        const int q = warp & 3;             // TMEM lane quadrant this warp may access
+        const int cg = ew >> 2;             // column range of this warp
+        const int col_base = cg * Cfg::COLS_PER_WARP;
+        float* stg = staging_all + ew * 32 * RF;
+        const int et = threadIdx.x - 64;
+        const int rsub = lane >> 3;         // phase B: row slot 0..3
+        const int c4 = (lane & 7) * 4;      // phase B: 4-column offset inside the 32-column pass
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int nb = static_cast<int>(tile % P.n_blocks);
@@ -249,88 +225,104 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             const int ty = static_cast<int>(m % P.tiles_y);
             const int img = static_cast<int>(m / P.tiles_y);
             const int n0 = nb * BLOCK_N;
-            const int x = tx * P.tw + row % P.tw;
-            const int y = ty * P.th + row / P.tw;
-            const bool valid = (x < P.W) && (y < P.H);
-            const long long off = static_cast<long long>(img) * P.out_bstride +
-                                  (static_cast<long long>(y) * P.W + x) * P.ld_out + n0;
+            const long long img_off = static_cast<long long>(img) * P.out_bstride;
+
+            // phase-B geometry of this lane's 8 rows: element offset of the pixel, or -1 when outside
+            long long poff[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = q * 32 + i * 4 + rsub;
+                const int x = tx * P.tw + (row & (P.tw - 1));
+                const int y = ty * P.th + (row >> P.tw_log2);
+                poff[i] = (x < P.W && y < P.H) ? img_off + (static_cast<long long>(y) * P.W + x) * P.ld_out : -1;
+            }
 
             const uint32_t acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             float* s_acc = s_stats + acc * 128;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + col_base + (static_cast<uint32_t>(q * 32) << 16);
 
 #pragma unroll 1
-            for (int j = 0; j < BLOCK_N / 32; ++j) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + j * 32, r);
-                tmem_ld_wait();
-                if (j == BLOCK_N / 32 - 1) {
-                    // accumulator fully read: hand the TMEM buffer back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                }
-                const int nc = n0 + j * 32;
-                if (nc >= P.n_total) continue;  // ragged N: whole chunk out of range
-                float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * P.alpha;
-                if (P.bias != nullptr) {
-                    const float4* bp = reinterpret_cast<const float4*>(P.bias + nc);
+            for (int ps = 0; ps < Cfg::PASSES; ++ps) {
+                const int nc = n0 + col_base + ps * 32;          // first global column of this pass
+                const bool pass_valid = nc < P.n_total;          // ragged N: whole pass out of range
+                // residual prefetch (coalesced: 8 lanes x 4 channels = 32 consecutive channels of a pixel)
+                float4 res[8];
+                if (P.residual != nullptr && pass_valid) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 b = __ldg(bp + i);
-                        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-                    }
-                }
-                if (P.residual != nullptr && valid) {
-                    if (P.res_fp32) {
-                        const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(P.residual) + off + j * 32);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 u = __ldg(rp + i);
-                            v[4 * i] += u.x; v[4 * i + 1] += u.y; v[4 * i + 2] += u.z; v[4 * i + 3] += u.w;
-                        }
-                    } else {
-                        const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.residual) + off + j * 32);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint4 u = __ldg(rp + i);
-                            v[8 * i] += bf16_lo(u.x); v[8 * i + 1] += bf16_hi(u.x);
-                            v[8 * i + 2] += bf16_lo(u.y); v[8 * i + 3] += bf16_hi(u.y);
-                            v[8 * i + 4] += bf16_lo(u.z); v[8 * i + 5] += bf16_hi(u.z);
-                            v[8 * i + 6] += bf16_lo(u.w); v[8 * i + 7] += bf16_hi(u.w);
+                        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (poff[i] >= 0) {
+                            if (P.res_fp32) {
+                                res[i] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(P.residual) +
+                                                                               poff[i] + nc + c4));
+                            } else {
+                                const uint2 u = __ldg(reinterpret_cast<const uint2*>(
+                                    static_cast<const __nv_bfloat16*>(P.residual) + poff[i] + nc + c4));
+                                res[i] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+                            }
                         }
                     }
                 }
-                if (P.group_size != 0) {
-                    // channel groups never straddle a 32-column chunk (group_size | 32)
-                    if (P.group_size == 4) stats_chunk<4>(v, valid, lane, s_acc + j * 16);
-                    else if (P.group_size == 8) stats_chunk<8>(v, valid, lane, s_acc + j * 8);
-                    else stats_chunk<16>(v, valid, lane, s_acc + j * 4);
+                // ---- phase A: TMEM -> staging
+                {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + ps * 32, r);
+                    tmem_ld_wait();
+                    if (ps == Cfg::PASSES - 1) {
+                        // this warp's part of the accumulator is read: hand the TMEM buffer back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    float4* dst = reinterpret_cast<float4*>(stg + lane * RF);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                             __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
                 }
-                if (valid) {
-                    if (P.out_fp32) {
-                        float4* op = reinterpret_cast<float4*>(static_cast<float*>(P.out) + off + j * 32);
+                __syncwarp();
+                // ---- phase B: staging -> global
+                if (pass_valid) {
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (P.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(P.bias + nc + c4));
+                    float ssum = 0.f, ssq = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    } else {
-                        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(P.out) + off + j * 32);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                               pack_bf16x2(v[8 * i + 4], v[8 * i + 5]),
-                                               pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+                    for (int i = 0; i < 8; ++i) {
+                        float4 v = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * RF + c4);
+                        v.x = fmaf(v.x, P.alpha, b4.x); v.y = fmaf(v.y, P.alpha, b4.y);
+                        v.z = fmaf(v.z, P.alpha, b4.z); v.w = fmaf(v.w, P.alpha, b4.w);
+                        if (P.residual != nullptr) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+                        if (poff[i] >= 0) {
+                            ssum += (v.x + v.y) + (v.z + v.w);
+                            ssq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ssq))));
+                            if (P.out_fp32) {
+                                *reinterpret_cast<float4*>(static_cast<float*>(P.out) + poff[i] + nc + c4) = v;
+                            } else {
+                                *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(P.out) + poff[i] + nc + c4) =
+                                    make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                            }
+                        }
+                    }
+                    if (P.group_size != 0) {
+                        ssum += __shfl_xor_sync(0xFFFFFFFFu, ssum, 8);
+                        ssq += __shfl_xor_sync(0xFFFFFFFFu, ssq, 8);
+                        ssum += __shfl_xor_sync(0xFFFFFFFFu, ssum, 16);
+                        ssq += __shfl_xor_sync(0xFFFFFFFFu, ssq, 16);
+                        if (lane < 8) {
+                            const int g = (col_base + ps * 32 + c4) / P.group_size;  // group within the n-block
+                            atomicAdd(&s_acc[2 * g], ssum);
+                            atomicAdd(&s_acc[2 * g + 1], ssq);
+                        }
                     }
                 }
+                __syncwarp();  // staging is reused by the next pass
             }
             if (P.group_size != 0) {
-                // all four epilogue warps finished adding into s_acc -> flush to global
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // all epilogue warps finished adding into s_acc -> flush to global (fp64 atomics)
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
                 const int nvals = 2 * BLOCK_N / P.group_size;  // (sum, sumsq) per group of this n-block
                 if (et < nvals) {
                     const int g_total = P.n_total / P.group_size;
@@ -338,7 +330,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                     s_acc[et] = 0.f;
                     const int grp = n0 / P.group_size + (et >> 1);
                     if (grp < g_total)
-                        atomicAdd(P.stats + (static_cast<long long>(img) * g_total + grp) * 2 + (et & 1), static_cast<double>(val));
+                        atomicAdd(P.stats + (static_cast<long long>(img) * g_total + grp) * 2 + (et & 1),
+                                  static_cast<double>(val));
                 }
             }
         }

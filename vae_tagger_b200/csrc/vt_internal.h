@@ -118,6 +118,8 @@ int launch_moments_to_latent(const float* moments_nhwc, float* latent, float* me
 int launch_nchw_to_nhwc(const float* in, void* out, int out_fp32, int N, int C, long long HW, cudaStream_t);
 int launch_nhwc_to_nchw(const void* in, int in_fp32, float* out, int N, int C, long long HW, cudaStream_t);
 int launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t);
+int launch_splitk_reduce(const float* part, int splits, long long split_stride, const float* bias, bf16* out,
+                         long long rows, int cols, long long ld_out, cudaStream_t, Profiler*);
 
 // ---- fp32 verification mode (vt_fp32.cu): FFMA implicit GEMM, NHWC fp32, same operand packing
 int launch_conv_fp32(const ConvOp& op, cudaStream_t, Profiler*);
