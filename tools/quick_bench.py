@@ -28,9 +28,23 @@ def main():
         dt = time.time() - t0
         print(f"iter {it}: {dt * 1e3:.1f} ms  -> {B / dt:.2f} img/s  latent mean {lat.mean().item():.4f} std {lat.std().item():.4f}",
               flush=True)
+    # lanes on/off comparison straight through the native context
+    vae = wrap.vae
+    nctx = vae._sync_native(x.device)
+    for label, kw in (("two lanes mb=default", dict()), ("single lane mb=default", dict(single_lane=True)),
+                      ("single lane mb=8", dict(single_lane=True, micro_batch=8)), ("two lanes mb=2", dict(micro_batch=2))):
+        for _ in range(2):
+            nctx.encode(x, **kw)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(3):
+            nctx.encode(x, **kw)
+        torch.cuda.synchronize()
+        dt = (time.time() - t0) / 3
+        print(f"encode only, {label:24s}: {dt * 1e3:7.2f} ms -> {B / dt:7.2f} img/s", flush=True)
     ctx.profile_enable(True)
     ctx.profile_read(reset=True)
-    lat = wrap.encode(x)
+    lat = nctx.encode(x, single_lane=True)
     out = dec.tag(lat)
     prof = ctx.profile_read(reset=True)
     ctx.profile_enable(False)

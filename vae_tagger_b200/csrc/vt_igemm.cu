@@ -56,19 +56,19 @@ static int num_sms() {
     return n;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MT>
 static int launch_variant(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const IgemmParams& P,
                           cudaStream_t stream) {
-    using Cfg = IgemmCfg<BLOCK_N>;
+    using Cfg = IgemmCfg<BLOCK_N, MT>;
     static bool attr_set = false;
     if (!attr_set) {
-        VT_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VT_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y * P.n_blocks;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    igemm_kernel<BLOCK_N><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, P);
+    igemm_kernel<BLOCK_N, MT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, P);
     VT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -79,12 +79,16 @@ static int pick_block_n(int n_total) {
     return 32;
 }
 
+// CTA tile configurations: 128 rows x 256 columns, 2x128 rows x 128 columns (two pixel tiles share
+// every weight chunk: same bytes per flop as the 128x256 tile), 128 x 32 for conv_out.
+static int pick_mt(int block_n) { return block_n == 128 ? 2 : 1; }
+
 static int dispatch(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                     const IgemmParams& P, cudaStream_t stream) {
     switch (block_n) {
-        case 256: return launch_variant<256>(a0, a1, b, P, stream);
-        case 128: return launch_variant<128>(a0, a1, b, P, stream);
-        case 32: return launch_variant<32>(a0, a1, b, P, stream);
+        case 256: return launch_variant<256, 1>(a0, a1, b, P, stream);
+        case 128: return launch_variant<128, 2>(a0, a1, b, P, stream);
+        case 32: return launch_variant<32, 1>(a0, a1, b, P, stream);
     }
     set_error("unsupported BLOCK_N");
     return -2;
@@ -130,9 +134,11 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
 
     IgemmParams P{};
     P.W = Wout; P.H = Hout; P.NB = op.N;
+    const int mt = pick_mt(block_n);
     P.tw = 16; P.th = 8; P.tw_log2 = 4;
+    P.sub_dx = 0; P.sub_dy = 1;  // sub-tiles stacked vertically: one TMA box of th*mt rows
     P.tiles_x = (Wout + P.tw - 1) / P.tw;
-    P.tiles_y = (Hout + P.th - 1) / P.th;
+    P.tiles_y = (Hout + P.th * mt - 1) / (P.th * mt);
     P.n_total = op.Cout;
     P.n_blocks = (op.Cout + block_n - 1) / block_n;
     P.a_batched = 1; P.b_batched = 0;
@@ -165,8 +171,8 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     P.num_slabs = ns;
 
     CUtensorMap a0, a1, b;
-    VT_TRY(make_act_map(&a0, op.in, op.N, op.Hin, op.Win, op.Cin, op.stride, P.tw, P.th));
-    if (op.sc_in) VT_TRY(make_act_map(&a1, op.sc_in, op.N, Hout, Wout, op.Cs, 1, P.tw, P.th));
+    VT_TRY(make_act_map(&a0, op.in, op.N, op.Hin, op.Win, op.Cin, op.stride, P.tw, P.th * mt));
+    if (op.sc_in) VT_TRY(make_act_map(&a1, op.sc_in, op.N, Hout, Wout, op.Cs, 1, P.tw, P.th * mt));
     else a1 = a0;
     {
         uint64_t dims[3] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(op.Cout), 1};
@@ -191,8 +197,10 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
 
     IgemmParams P{};
     P.W = op.M; P.H = 1; P.NB = op.batch;
+    const int mt = pick_mt(block_n);
     P.tw = 128; P.th = 1; P.tw_log2 = 7;
-    P.tiles_x = (op.M + 127) / 128;
+    P.sub_dx = 1; P.sub_dy = 0;  // sub-tiles are consecutive 128-row blocks
+    P.tiles_x = (op.M + 128 * mt - 1) / (128 * mt);
     P.tiles_y = 1;
     P.n_total = op.N;
     P.n_blocks = (op.N + block_n - 1) / block_n;
@@ -213,7 +221,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
                             static_cast<uint64_t>(op.a_batched ? op.batch : 1)};
         const uint64_t abs_ = 2ull * (op.a_bstride ? op.a_bstride : lda * op.M);
         uint64_t str[4] = {2ull * lda, abs_, abs_, abs_};
-        uint32_t box[5] = {64, 128, 1, 1, 1};
+        uint32_t box[5] = {64, static_cast<uint32_t>(128 * mt), 1, 1, 1};
         VT_TRY(make_tmap(&a, op.A, 5, dims, str, box));
     }
     {
