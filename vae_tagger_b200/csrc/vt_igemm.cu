@@ -137,6 +137,8 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     const int mt = pick_mt(block_n);
     P.tw = 16; P.th = 8; P.tw_log2 = 4;
     P.sub_dx = 0; P.sub_dy = 1;  // sub-tiles stacked vertically: one TMA box of th*mt rows
+    P.row_jump = Wout * op.Cout;   // accumulator row r+16 is the pixel one image row below (tw = 16)
+    VT_CHECK(1LL * Hout * Wout * op.Cout < (1LL << 31), "conv output of one image exceeds 2^31 elements");
     P.tiles_x = (Wout + P.tw - 1) / P.tw;
     P.tiles_y = (Hout + P.th * mt - 1) / (P.th * mt);
     P.n_total = op.Cout;
@@ -200,6 +202,8 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     const int mt = pick_mt(block_n);
     P.tw = 128; P.th = 1; P.tw_log2 = 7;
     P.sub_dx = 1; P.sub_dy = 0;  // sub-tiles are consecutive 128-row blocks
+    P.row_jump = static_cast<int>(16 * ldo);  // accumulator row r+16 is output row +16 (tw = 128)
+    VT_CHECK(1LL * (op.M + 256) * ldo < (1LL << 31), "GEMM output of one batch exceeds 2^31 elements");
     P.tiles_x = (op.M + 128 * mt - 1) / (128 * mt);
     P.tiles_y = 1;
     P.n_total = op.N;

@@ -17,6 +17,8 @@
 // (TMEM -> smem staging -> bias/residual/GroupNorm partial sums -> coalesced bf16|fp32 stores).  Persistent CTAs, static round-robin tile order with the
 // n-blocks of one pixel tile adjacent (they share the A tile through L2).
 #pragma once
+#include <type_traits>
+
 #include "vt_ptx.cuh"
 
 namespace vt {
@@ -51,6 +53,7 @@ struct IgemmParams {
     int out_fp32;          // output element type: 0 bf16, 1 fp32
     int res_fp32;          // residual element type: 0 bf16, 1 fp32
     int group_size;        // channels per GroupNorm group for the fused statistics; 0 = off
+    int row_jump;          // element offset between accumulator rows r and r+16 of a sub-tile (see epilogue)
     float alpha;
     const float* bias;              // [n_total] or nullptr
     const void* residual;  // same geometry as out (bf16 or fp32), or nullptr
@@ -79,21 +82,274 @@ struct IgemmCfg {
     static constexpr int ACC_COLS = MT * BLOCK_N;  // TMEM columns of one accumulator set
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
                                      : (2 * ACC_COLS <= 256) ? 256 : 512;
-    static constexpr int BAR_BYTES = 2560;  // barriers, tmem pointer, fp32 + fp64 stats scratch
+    static constexpr int PART_FLOATS = 2 * EPI_WARPS * (COLS_PER_WARP / 4) * 2;  // [acc][warp][4-col slot][sum,sq]
+    static constexpr int BAR_BYTES = 256 + 1024 + PART_FLOATS * 4;  // barriers + tmem pointer | fp64 running sums | partials
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(2 * ACC_COLS <= 512, "two accumulator sets must fit TMEM");
 };
 
-// Epilogue (v2).  Each epilogue warp owns one TMEM lane quadrant (32 accumulator rows = 32 output
-// pixels) and a column range, processed in passes of 32 columns:
+// ---------------------------------------------------------------------------------------------
+// Epilogue.  Each epilogue warp owns one TMEM lane quadrant (32 accumulator rows = 32 output pixels)
+// and a column range, processed in passes of 32 columns:
 //   phase A  tcgen05.ld: thread t = row t, 32 fp32 columns -> per-warp smem staging tile [32][32(+4)]
-//   phase B  lanes re-map to (row = 4*it + lane/8, 4 columns = lane%8): staging -> registers, * alpha,
-//            + bias, + residual (coalesced global loads issued before phase A), GroupNorm partial sums
-//            accumulated per lane over its 8 rows, bf16/fp32 pack, coalesced global stores (8 lanes
-//            cover 32 consecutive channels of one pixel, a warp instruction covers 4 pixels).
-// Statistics: the 4 columns of a lane lie in one group (group sizes are multiples of 4); after the 8
-// rows, two shuffles fold the 4 row-slots and 8 lanes add into the CTA's smem accumulators.
+//   phase B  lanes re-map to (row = 8*i + lane/4, 8 columns = lane%4): staging -> registers, * alpha,
+//            + bias, + residual (prefetched one pass ahead; the first pass of a tile is in flight
+//            while the tile's MMAs still run), GroupNorm partial sums, bf16/fp32 pack, stores in which
+//            4 lanes cover 32 consecutive channels of a pixel (64 / 128 contiguous bytes).
+// Everything that varies per launch but not per element (output type, residual type, statistics)
+// is a template parameter, addresses are one 64-bit base per tile plus 32-bit offsets, and the shared
+// GroupNorm accumulators are per-warp slots (no shared-memory atomics): the first two versions of this
+// epilogue spent ~1000 issue slots per 32x32 chunk on branches, 64-bit address arithmetic and
+// compare-and-swap loops and were the limiter of every layer with few K chunks per tile.
+template <int BLOCK_N, int MT, bool OUT_F32, int RES, bool STATS>
+__device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* staging_all, uint8_t* ctrl,
+                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
+                                               uint32_t total_tiles, int warp, int lane) {
+    using Cfg = IgemmCfg<BLOCK_N, MT>;
+    constexpr int EPI_WARPS = Cfg::EPI_WARPS;
+    constexpr int RF = Cfg::STAGE_ROW_FLOATS;
+    constexpr int SLOTS = Cfg::COLS_PER_WARP / 4;  // 4-column statistic slots per warp
+    typedef typename std::conditional<OUT_F32, float, __nv_bfloat16>::type OutT;
+
+    const int ew = warp - 2;            // 0 .. EPI_WARPS-1
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int cg = ew >> 2;             // column range of this warp
+    const int col_base = cg * Cfg::COLS_PER_WARP;
+    const uint32_t stg = smem_u32(staging_all + ew * 32 * RF);  // shared-space byte address
+    const int et = threadIdx.x - 64;
+    const int rlane = lane >> 2;        // phase B: row slot 0..7
+    const int j8 = (lane & 3) * 8;      // phase B: 8-column offset inside the 32-column pass
+
+    double* s_run = reinterpret_cast<double*>(ctrl + 256);                 // [128] fp64 running sums, slot et
+    float* s_part = reinterpret_cast<float*>(ctrl + 256 + 1024);          // [2][EPI_WARPS][SLOTS][2]
+    if (STATS) {
+        if (et < 128) s_run[et] = 0.0;
+        for (int i = et; i < Cfg::PART_FLOATS; i += 32 * EPI_WARPS) s_part[i] = 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    }
+    int run_img = -1, run_nb = -1;
+    auto flush_stats = [&]() {
+        const int nvals = 2 * BLOCK_N / P.group_size;
+        if (run_img >= 0 && et < nvals) {
+            const int g_total = P.n_total / P.group_size;
+            const int grp = run_nb * (BLOCK_N / P.group_size) + (et >> 1);
+            if (grp < g_total)
+                atomicAdd(P.stats + (static_cast<long long>(run_img) * g_total + grp) * 2 + (et & 1), s_run[et]);
+            s_run[et] = 0.0;
+        }
+    };
+
+    // per-tile geometry: image, n-block, and for each sub-tile the element offset of this lane's first
+    // row (i = 0) inside the image plus a 4-bit validity mask of its rows i = 0..3
+    struct Geo {
+        int nb, img;
+        int off0[MT];
+        unsigned vmask[MT];
+    };
+    auto geometry = [&](uint32_t tile, Geo& g) {
+        g.nb = static_cast<int>(tile % static_cast<uint32_t>(P.n_blocks));
+        uint32_t m = tile / static_cast<uint32_t>(P.n_blocks);
+        const int tx = static_cast<int>(m % static_cast<uint32_t>(P.tiles_x));
+        m /= static_cast<uint32_t>(P.tiles_x);
+        const int ty = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
+        g.img = static_cast<int>(m / static_cast<uint32_t>(P.tiles_y));
+        const int r0 = q * 32 + rlane;
+#pragma unroll
+        for (int t = 0; t < MT; ++t) {
+            const int xs = (tx * (P.sub_dx ? MT : 1) + t * P.sub_dx) * P.tw;
+            const int ys = (ty * (P.sub_dy ? MT : 1) + t * P.sub_dy) * P.th;
+            const int px0 = xs + (r0 & (P.tw - 1)), py0 = ys + (r0 >> P.tw_log2);
+            g.off0[t] = (py0 * P.W + px0) * static_cast<int>(P.ld_out);
+            unsigned vm = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int px = px0 + 8 * (i & 1) + (P.tw > 16 ? 16 * (i >> 1) : 0);
+                const int py = py0 + (P.tw > 16 ? 0 : (i >> 1));
+                if (px < P.W && py < P.H) vm |= 1u << i;
+            }
+            g.vmask[t] = vm;
+        }
+    };
+    const int step1 = 8 * static_cast<int>(P.ld_out);  // row r -> r + 8
+    const int step2 = P.row_jump;                      // row r -> r + 16
+
+    // residual registers of one pass: 8 channels x 4 rows per lane
+    struct ResRegs {
+        uint4 lo[4];
+        uint4 hi[4];  // only used for fp32 residuals
+    };
+    auto load_res = [&](ResRegs& rr, const Geo& g, int t, int nc) {
+        if (RES == 0) return;
+        const long long base = static_cast<long long>(g.img) * P.out_bstride + nc + j8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int off = g.off0[t] + (i & 1) * step1 + (i >> 1) * step2;
+            const bool ok = ((g.vmask[t] >> i) & 1u) && nc < P.n_total;
+            rr.lo[i] = make_uint4(0u, 0u, 0u, 0u);
+            rr.hi[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (RES == 1) {
+                if (ok) rr.lo[i] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.residual) + base + off));
+            } else {
+                const float* rp = static_cast<const float*>(P.residual) + base + off;
+                if (ok) {
+                    rr.lo[i] = __ldg(reinterpret_cast<const uint4*>(rp));
+                    rr.hi[i] = __ldg(reinterpret_cast<const uint4*>(rp + 4));
+                }
+            }
+        }
+    };
+
+    uint32_t it = 0;
+    uint32_t tile = blockIdx.x;
+    Geo geo, ngeo;
+    ResRegs rnext;
+    if (tile < total_tiles) {
+        geometry(tile, geo);
+        load_res(rnext, geo, 0, geo.nb * BLOCK_N + col_base);   // in flight while the MMAs run
+    }
+    for (; tile < total_tiles; ++it) {
+        const int n0 = geo.nb * BLOCK_N;
+        const uint32_t acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        float* part = s_part + (acc * EPI_WARPS + ew) * SLOTS * 2;
+        if (STATS && (geo.img != run_img || geo.nb != run_nb)) {
+            flush_stats();
+            run_img = geo.img; run_nb = geo.nb;
+        }
+        const uint32_t next_tile = tile + gridDim.x;
+        if (next_tile < total_tiles) geometry(next_tile, ngeo);
+        OutT* out_img = static_cast<OutT*>(P.out) + static_cast<long long>(geo.img) * P.out_bstride;
+
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + col_base + (static_cast<uint32_t>(q * 32) << 16);
+
+#pragma unroll
+        for (int sub = 0; sub < MT; ++sub) {                  // 128-row sub-tile (unrolled: static register indexing)
+#pragma unroll 1
+            for (int pc = 0; pc < Cfg::PASSES_PER_SUB; ++pc) {  // 32-column chunk inside this warp's range
+                const bool last_pass = (sub == MT - 1) && (pc == Cfg::PASSES_PER_SUB - 1);
+                const int nc = n0 + col_base + pc * 32;         // first global column of this pass
+                const bool pass_valid = nc < P.n_total;         // ragged N: whole pass out of range
+                // ---- phase A: TMEM -> staging
+                {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + sub * BLOCK_N + pc * 32, r);
+                    tmem_ld_wait();
+                    if (last_pass) {
+                        // this warp's part of the accumulator set is read: hand the TMEM buffer back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    const uint32_t dst = stg + lane * RF * 4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        sts128(dst + i * 16, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                }
+                __syncwarp();
+                // ---- phase B: staging -> global
+                ResRegs rcur = rnext;
+                if (RES != 0) {   // prefetch the residual of the next pass / next sub-tile / next tile
+                    if (pc + 1 < Cfg::PASSES_PER_SUB) load_res(rnext, geo, sub, nc + 32);
+                    else if (sub + 1 < MT) load_res(rnext, geo, sub + 1 < MT ? sub + 1 : 0, n0 + col_base);
+                    else if (next_tile < total_tiles) load_res(rnext, ngeo, 0, ngeo.nb * BLOCK_N + col_base);
+                }
+                if (pass_valid) {
+                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                    if (P.bias != nullptr) {
+                        b0 = __ldg(reinterpret_cast<const float4*>(P.bias + nc + j8));
+                        b1 = __ldg(reinterpret_cast<const float4*>(P.bias + nc + j8 + 4));
+                    }
+                    float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+                    OutT* optr = out_img + nc + j8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t sp = stg + ((8 * i + rlane) * RF + j8) * 4;
+                        float4 v0 = lds128(sp);
+                        float4 v1 = lds128(sp + 16);
+                        v0.x = fmaf(v0.x, P.alpha, b0.x); v0.y = fmaf(v0.y, P.alpha, b0.y);
+                        v0.z = fmaf(v0.z, P.alpha, b0.z); v0.w = fmaf(v0.w, P.alpha, b0.w);
+                        v1.x = fmaf(v1.x, P.alpha, b1.x); v1.y = fmaf(v1.y, P.alpha, b1.y);
+                        v1.z = fmaf(v1.z, P.alpha, b1.z); v1.w = fmaf(v1.w, P.alpha, b1.w);
+                        if (RES == 1) {
+                            const uint4 u = rcur.lo[i];
+                            v0.x += bf16_lo(u.x); v0.y += bf16_hi(u.x); v0.z += bf16_lo(u.y); v0.w += bf16_hi(u.y);
+                            v1.x += bf16_lo(u.z); v1.y += bf16_hi(u.z); v1.z += bf16_lo(u.w); v1.w += bf16_hi(u.w);
+                        } else if (RES == 2) {
+                            const uint4 a = rcur.lo[i], b = rcur.hi[i];
+                            v0.x += __uint_as_float(a.x); v0.y += __uint_as_float(a.y);
+                            v0.z += __uint_as_float(a.z); v0.w += __uint_as_float(a.w);
+                            v1.x += __uint_as_float(b.x); v1.y += __uint_as_float(b.y);
+                            v1.z += __uint_as_float(b.z); v1.w += __uint_as_float(b.w);
+                        }
+                        const bool ok = (geo.vmask[sub] >> i) & 1u;
+                        if (STATS && ok) {
+                            s_lo += (v0.x + v0.y) + (v0.z + v0.w);
+                            q_lo = fmaf(v0.x, v0.x, fmaf(v0.y, v0.y, fmaf(v0.z, v0.z, fmaf(v0.w, v0.w, q_lo))));
+                            s_hi += (v1.x + v1.y) + (v1.z + v1.w);
+                            q_hi = fmaf(v1.x, v1.x, fmaf(v1.y, v1.y, fmaf(v1.z, v1.z, fmaf(v1.w, v1.w, q_hi))));
+                        }
+                        OutT* o = optr + (geo.off0[sub] + (i & 1) * step1 + (i >> 1) * step2);
+                        if (OUT_F32) {
+                            if (ok) {
+                                reinterpret_cast<float4*>(o)[0] = v0;
+                                reinterpret_cast<float4*>(o)[1] = v1;
+                            }
+                        } else {
+                            const uint4 pk = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w),
+                                                        pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+                            if (ok) *reinterpret_cast<uint4*>(o) = pk;
+                        }
+                    }
+                    if (STATS) {
+                        // fold the 8 row slots (lanes with equal lane%4), then lanes 0..3 own two 4-column slots each
+#pragma unroll
+                        for (int o = 4; o <= 16; o <<= 1) {
+                            s_lo += __shfl_xor_sync(0xFFFFFFFFu, s_lo, o);
+                            q_lo += __shfl_xor_sync(0xFFFFFFFFu, q_lo, o);
+                            s_hi += __shfl_xor_sync(0xFFFFFFFFu, s_hi, o);
+                            q_hi += __shfl_xor_sync(0xFFFFFFFFu, q_hi, o);
+                        }
+                        if (lane < 4) {
+                            float4* pp = reinterpret_cast<float4*>(part + (pc * 8 + lane * 2) * 2);
+                            float4 cur = *pp;
+                            cur.x += s_lo; cur.y += q_lo; cur.z += s_hi; cur.w += q_hi;
+                            *pp = cur;
+                        }
+                    }
+                }
+                __syncwarp();  // staging is reused by the next pass
+            }
+        }
+        if (STATS) {
+            // all epilogue warps have written their slots -> fold into the CTA's running fp64 sums
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            const int nvals = 2 * BLOCK_N / P.group_size;  // (sum, sumsq) per group of this n-block
+            if (et < nvals) {
+                const int g = et >> 1, which = et & 1;
+                const int slots_per_group = P.group_size / 4;
+                float tot = 0.f;
+                for (int sidx = g * slots_per_group; sidx < (g + 1) * slots_per_group; ++sidx) {
+                    const int cgi = sidx / SLOTS, ls = sidx - cgi * SLOTS;
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        float* pv = s_part + ((acc * EPI_WARPS + cgi * 4 + qq) * SLOTS + ls) * 2 + which;
+                        tot += *pv;
+                        *pv = 0.f;
+                    }
+                }
+                s_run[et] += static_cast<double>(tot);
+            }
+        }
+        tile = next_tile;
+        geo = ngeo;
+    }
+    if (STATS) flush_stats();
+}
+
 template <int BLOCK_N, int MT>
 __global__ void __launch_bounds__(IgemmCfg<BLOCK_N, MT>::THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -101,7 +357,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     using Cfg = IgemmCfg<BLOCK_N, MT>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int EPI_WARPS = Cfg::EPI_WARPS;
-    constexpr int RF = Cfg::STAGE_ROW_FLOATS;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -112,13 +367,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     uint64_t* tfull_bar = empty_bar + STAGES;                    // [2]
     uint64_t* tempty_bar = tfull_bar + 2;                        // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* s_stats = reinterpret_cast<float*>(ctrl + 256);       // [2][128]: (sum, sumsq) per group of the n-block
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int tiles_per_img = P.tiles_x * P.tiles_y;
-    const long long total_tiles = 1LL * P.NB * tiles_per_img * P.n_blocks;
+    const uint32_t tiles_per_img = static_cast<uint32_t>(P.tiles_x * P.tiles_y);
+    const uint32_t total_tiles = static_cast<uint32_t>(P.NB) * tiles_per_img * static_cast<uint32_t>(P.n_blocks);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0);
@@ -138,9 +392,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < 256; i += 32 * EPI_WARPS) s_stats[i] = 0.f;
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -151,13 +402,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nb = static_cast<int>(tile % P.n_blocks);
-                long long m = tile / P.n_blocks;
-                const int tx = static_cast<int>(m % P.tiles_x);
-                m /= P.tiles_x;
-                const int ty = static_cast<int>(m % P.tiles_y);
-                const int img = static_cast<int>(m / P.tiles_y);
+            for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nb = static_cast<int>(tile % static_cast<uint32_t>(P.n_blocks));
+                uint32_t m = tile / static_cast<uint32_t>(P.n_blocks);
+                const int tx = static_cast<int>(m % static_cast<uint32_t>(P.tiles_x));
+                m /= static_cast<uint32_t>(P.tiles_x);
+                const int ty = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
+                const int img = static_cast<int>(m / static_cast<uint32_t>(P.tiles_y));
                 const int x0 = tx * P.tw * (P.sub_dx ? MT : 1), y0 = ty * P.th * (P.sub_dy ? MT : 1), n0 = nb * BLOCK_N;
                 for (int s = 0; s < P.num_slabs; ++s) {
                     const IgemmSlab sl = P.slabs[s];
@@ -186,7 +437,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             int kblocks = 0;
             for (int s = 0; s < P.num_slabs; ++s) kblocks += P.slabs[s].nchunks;
             uint32_t it = 0;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -215,187 +466,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue warps
-        const int ew = warp - 2;            // 0 .. EPI_WARPS-1
-        const int q = warp & 3;             // TMEM lane quadrant this warp may access
-        const int cg = ew >> 2;             // column range of this warp
-        const int col_base = cg * Cfg::COLS_PER_WARP;
-        float* stg = staging_all + ew * 32 * RF;
-        const int et = threadIdx.x - 64;
-        const int rsub = lane >> 3;         // phase B: row slot 0..3
-        const int c4 = (lane & 7) * 4;      // phase B: 4-column offset inside the 32-column pass
-        const bool has_res = P.residual != nullptr;
-
-        // residual fetch of one pass (coalesced: 8 lanes x 4 channels = 32 consecutive channels of a pixel)
-        auto load_res = [&](float4 (&res)[8], const long long* poff, int nc) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (poff[i] >= 0 && nc < P.n_total) {
-                    if (P.res_fp32) {
-                        res[i] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(P.residual) + poff[i] +
-                                                                       nc + c4));
-                    } else {
-                        const uint2 u = __ldg(reinterpret_cast<const uint2*>(
-                            static_cast<const __nv_bfloat16*>(P.residual) + poff[i] + nc + c4));
-                        res[i] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-                    }
-                }
-            }
-        };
-        auto tile_geometry = [&](long long tile, int& nb, int& img, long long (&poff)[8 * MT]) {
-            nb = static_cast<int>(tile % P.n_blocks);
-            long long m = tile / P.n_blocks;
-            const int tx = static_cast<int>(m % P.tiles_x);
-            m /= P.tiles_x;
-            const int ty = static_cast<int>(m % P.tiles_y);
-            img = static_cast<int>(m / P.tiles_y);
-            const long long img_off = static_cast<long long>(img) * P.out_bstride;
-#pragma unroll
-            for (int t = 0; t < MT; ++t) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = q * 32 + i * 4 + rsub;
-                    const int x = (tx * (P.sub_dx ? MT : 1) + t * P.sub_dx) * P.tw + (row & (P.tw - 1));
-                    const int y = (ty * (P.sub_dy ? MT : 1) + t * P.sub_dy) * P.th + (row >> P.tw_log2);
-                    poff[t * 8 + i] =
-                        (x < P.W && y < P.H) ? img_off + (static_cast<long long>(y) * P.W + x) * P.ld_out : -1;
-                }
-            }
-        };
-
-        // running (sum, sumsq) of this CTA for the current (image, n-block): fp64 in shared memory,
-        // flushed to global with fp64 atomics only when the (image, n-block) changes -- a persistent CTA
-        // walks ~55 consecutive tiles of one image, so this removes ~98 % of the same-address atomics
-        double* s_run = reinterpret_cast<double*>(ctrl + 256 + 1024);  // [128], slot et owned by thread et
-        if (et < 128) s_run[et] = 0.0;
-        int run_img = -1, run_nb = -1;
-        auto flush_stats = [&]() {
-            const int nvals = 2 * BLOCK_N / P.group_size;
-            if (run_img >= 0 && et < nvals) {
-                const int g_total = P.n_total / P.group_size;
-                const int grp = run_nb * (BLOCK_N / P.group_size) + (et >> 1);
-                if (grp < g_total)
-                    atomicAdd(P.stats + (static_cast<long long>(run_img) * g_total + grp) * 2 + (et & 1), s_run[et]);
-                s_run[et] = 0.0;
-            }
-        };
-
-        uint32_t it = 0;
-        long long tile = blockIdx.x;
-        int nb = 0, img = 0;
-        long long poff[8 * MT];
-        float4 res0[8];
-        if (tile < total_tiles) {
-            tile_geometry(tile, nb, img, poff);
-            if (has_res) load_res(res0, poff, nb * BLOCK_N + col_base);   // in flight while the MMAs run
+        const int res = P.residual == nullptr ? 0 : (P.res_fp32 ? 2 : 1);
+        const int mode = (P.out_fp32 ? 1 : 0) | (res << 1) | (P.group_size != 0 ? 8 : 0);
+#define VT_EPI_CASE(O, R, S)                                                                                  \
+    case ((O) | ((R) << 1) | ((S) << 3)):                                                                     \
+        igemm_epilogue<BLOCK_N, MT, (O) != 0, (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar,     \
+                                                              tmem_base, total_tiles, warp, lane);            \
+        break;
+        switch (mode) {
+            VT_EPI_CASE(0, 0, 0) VT_EPI_CASE(1, 0, 0) VT_EPI_CASE(0, 1, 0) VT_EPI_CASE(1, 1, 0)
+            VT_EPI_CASE(0, 2, 0) VT_EPI_CASE(1, 2, 0) VT_EPI_CASE(0, 0, 1) VT_EPI_CASE(1, 0, 1)
+            VT_EPI_CASE(0, 1, 1) VT_EPI_CASE(1, 1, 1) VT_EPI_CASE(0, 2, 1) VT_EPI_CASE(1, 2, 1)
+            default: break;
         }
-        for (; tile < total_tiles; ++it) {
-            const int n0 = nb * BLOCK_N;
-            const uint32_t acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            float* s_acc = s_stats + acc * 128;
-            if (P.group_size != 0 && (img != run_img || nb != run_nb)) {
-                flush_stats();
-                run_img = img; run_nb = nb;
-            }
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + col_base + (static_cast<uint32_t>(q * 32) << 16);
-
-            // geometry of the next tile (needed to prefetch its first residual pass at the end of this one)
-            const long long next_tile = tile + gridDim.x;
-            int nnb = 0, nimg = 0;
-            long long npoff[8 * MT];
-            if (next_tile < total_tiles) tile_geometry(next_tile, nnb, nimg, npoff);
-
-#pragma unroll
-            for (int sub = 0; sub < MT; ++sub) {                 // 128-row sub-tile (unrolled: static register indexing)
-            const long long* pf = poff + sub * 8;
-#pragma unroll 1
-            for (int pc = 0; pc < Cfg::PASSES_PER_SUB; ++pc) {   // 32-column chunk inside this warp's range
-                const bool last_pass = (sub == MT - 1) && (pc == Cfg::PASSES_PER_SUB - 1);
-                const int nc = n0 + col_base + pc * 32;          // first global column of this pass
-                const bool pass_valid = nc < P.n_total;          // ragged N: whole pass out of range
-                // ---- phase A: TMEM -> staging
-                {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + sub * BLOCK_N + pc * 32, r);
-                    tmem_ld_wait();
-                    if (last_pass) {
-                        // this warp's part of the accumulator is read: hand the TMEM buffer back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                    }
-                    float4* dst = reinterpret_cast<float4*>(stg + lane * RF);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                             __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                }
-                __syncwarp();
-                // ---- phase B: staging -> global
-                float4 res[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) res[i] = res0[i];
-                // prefetch the residual of the next pass (or of the next tile's first pass)
-                if (has_res) {
-                    if (pc + 1 < Cfg::PASSES_PER_SUB) load_res(res0, pf, nc + 32);
-                    else if (sub + 1 < MT) load_res(res0, poff + (sub + 1 < MT ? sub + 1 : 0) * 8, n0 + col_base);
-                    else if (next_tile < total_tiles) load_res(res0, npoff, nnb * BLOCK_N + col_base);
-                }
-                if (pass_valid) {
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (P.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(P.bias + nc + c4));
-                    float ssum = 0.f, ssq = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float4 v = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * RF + c4);
-                        v.x = fmaf(v.x, P.alpha, b4.x); v.y = fmaf(v.y, P.alpha, b4.y);
-                        v.z = fmaf(v.z, P.alpha, b4.z); v.w = fmaf(v.w, P.alpha, b4.w);
-                        if (has_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
-                        if (pf[i] >= 0) {
-                            ssum += (v.x + v.y) + (v.z + v.w);
-                            ssq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ssq))));
-                            if (P.out_fp32) {
-                                *reinterpret_cast<float4*>(static_cast<float*>(P.out) + pf[i] + nc + c4) = v;
-                            } else {
-                                *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(P.out) + pf[i] + nc + c4) =
-                                    make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-                            }
-                        }
-                    }
-                    if (P.group_size != 0) {
-                        ssum += __shfl_xor_sync(0xFFFFFFFFu, ssum, 8);
-                        ssq += __shfl_xor_sync(0xFFFFFFFFu, ssq, 8);
-                        ssum += __shfl_xor_sync(0xFFFFFFFFu, ssum, 16);
-                        ssq += __shfl_xor_sync(0xFFFFFFFFu, ssq, 16);
-                        if (lane < 8) {
-                            const int g = (col_base + pc * 32 + c4) / P.group_size;  // group within the n-block
-                            atomicAdd(&s_acc[2 * g], ssum);
-                            atomicAdd(&s_acc[2 * g + 1], ssq);
-                        }
-                    }
-                }
-                __syncwarp();  // staging is reused by the next pass
-            }
-            }
-            if (P.group_size != 0) {
-                // all epilogue warps finished adding into s_acc -> fold into the CTA's running fp64 sums
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-                const int nvals = 2 * BLOCK_N / P.group_size;  // (sum, sumsq) per group of this n-block
-                if (et < nvals) {
-                    s_run[et] += static_cast<double>(s_acc[et]);
-                    s_acc[et] = 0.f;
-                }
-            }
-            // advance to the next tile
-            tile = next_tile;
-            nb = nnb; img = nimg;
-#pragma unroll
-            for (int i = 0; i < 8 * MT; ++i) poff[i] = npoff[i];
-        }
-        if (P.group_size != 0) flush_stats();
+#undef VT_EPI_CASE
     }
 
     tc_fence_before();
