@@ -1,0 +1,92 @@
+"""CPU, world size 2, gloo: the N>1 host logic -- batch sharding of the inference stream and the
+decoder-gradient exchange of the training step (one flat all-reduce, BN buffers from rank 0)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+from vae_tagger_b200 import modules as M
+from vae_tagger_b200.sharding import shard_range
+from vae_tagger_b200.train_decoder import DecoderTrainer, cosine_schedule_with_warmup
+
+
+def test_shard_ranges_cover_the_stream_without_overlap():
+    for n in (0, 1, 7, 100_000):
+        for g in (1, 2, 4, 8):
+            spans = [shard_range(n, r, g) for r in range(g)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_cosine_schedule_matches_definition():
+    opt = torch.optim.SGD([nn.Parameter(torch.zeros(1))], lr=1.0)
+    sched = cosine_schedule_with_warmup(opt, 2, 10)
+    lrs = []
+    for _ in range(10):
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step(); sched.step()
+    assert lrs[0] == 0.0 and abs(lrs[1] - 0.5) < 1e-9 and abs(lrs[2] - 1.0) < 1e-9
+    assert abs(lrs[6] - 0.5) < 1e-9 and lrs[9] < 0.05
+
+
+class _IdentityVAE(nn.Module):
+    def encode(self, x):
+        return x
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                 # deliberately different initial weights per rank
+    dec = M.create_attention_decoder(16, 16, 16, 5, attention_config={})
+    for m in dec.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0
+    opt = torch.optim.SGD(dec.parameters(), lr=0.1)
+    tr = DecoderTrainer(_IdentityVAE(), dec, nn.BCEWithLogitsLoss(), opt, None, max_grad_norm=0.0)
+    start = {k: v.clone() for k, v in dec.state_dict().items()}
+    g = torch.Generator().manual_seed(7 + rank)   # each rank has its own shard of the batch
+    x = torch.randn(4, 16, 16, 16, generator=g)
+    y = (torch.rand(4, 5, generator=g) < 0.3).float()
+    tr.step(x, y)
+    local_grad = tr.flat_grad.clone()             # before the exchange completes on this rank's view
+    tr._pending.wait()
+    summed = tr.flat_grad.clone()
+    tr._pending = dist.all_reduce(torch.zeros(1), async_op=True)  # dummy handle so finish_update proceeds
+    tr.flat_grad.copy_(summed)
+    tr.finish_update()
+    torch.save({"start": start, "end": dec.state_dict(), "summed": summed, "local": local_grad},
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_exchange(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(tmp_path / "r0.pt")
+    r1 = torch.load(tmp_path / "r1.pt")
+    # initial broadcast: both ranks start from rank 0's weights
+    for k in r0["start"]:
+        assert torch.equal(r0["start"][k], r1["start"][k]), k
+    # the all-reduce sums the per-rank gradients identically on both ranks
+    assert torch.allclose(r0["summed"], r1["summed"])
+    # parameters stay in lock-step after the optimizer step; BatchNorm running stats are per rank
+    for k in r0["end"]:
+        if "running_" in k or "num_batches" in k:
+            continue
+        assert torch.allclose(r0["end"][k], r1["end"][k], atol=1e-7), k
+    assert not torch.equal(r0["end"]["feature_compress.1.running_mean"], r1["end"]["feature_compress.1.running_mean"])

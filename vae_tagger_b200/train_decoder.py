@@ -1,0 +1,305 @@
+"""Drop-in for the reference's ``train_decoder.py``: train the tag decoder on a frozen FLUX VAE
+encoder (reference step: train_decoder.py:178-206).
+
+Differences in *how* (not what):
+  * the frozen encoder forward -- >99.9 % of the step's FLOPs -- runs as sm_100a kernels;
+  * ``accelerate`` is replaced by plain ``torch.distributed`` (one process per GPU, NCCL): decoder
+    gradients live in ONE flat fp32 buffer that is all-reduced once per optimizer step; the
+    all-reduce is asynchronous and is waited for only after the *next* batch's encoder forward, so
+    it is hidden behind it.  BatchNorm statistics stay per rank and the BatchNorm buffers are
+    broadcast from rank 0 like DDP's ``broadcast_buffers``;
+  * the focal loss forward+backward is one fused kernel.
+The decoder's own forward/backward in train() mode is a PyTorch autograd graph.
+
+Launch:  torchrun --nproc-per-node N -m vae_tagger_b200.train_decoder --vae_checkpoint ... (same flags as
+the reference; ``--mixed_precision`` is accepted and ignored: the encoder runs bf16 tensor-core
+kernels with fp32 accumulation, the head in fp32).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .diffusers_vae_loader import (DiffusersVAEWrapper, create_vae_from_config_file, get_diffusers_vae_config,
+                                   load_diffusers_vae_from_config)
+from .modules import (ClassificationDecoder, TaggedImageDataset, create_attention_decoder, get_image_transform,
+                      get_vae_latent_info)
+
+
+def cosine_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps):
+    """``get_scheduler("cosine")`` of diffusers: linear warm-up then half a cosine to zero."""
+
+    def lr_lambda(step):
+        if step < num_warmup_steps:
+            return step / max(1, num_warmup_steps)
+        progress = (step - num_warmup_steps) / max(1, num_training_steps - num_warmup_steps)
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * min(1.0, progress))))
+
+    return torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda)
+
+
+def get_scheduler(name, optimizer, num_warmup_steps, num_training_steps):
+    if name == "cosine":
+        return cosine_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps)
+    if name == "constant":
+        return torch.optim.lr_scheduler.LambdaLR(optimizer, lambda s: 1.0)
+    if name == "linear":
+        return torch.optim.lr_scheduler.LambdaLR(
+            optimizer, lambda s: s / max(1, num_warmup_steps) if s < num_warmup_steps else max(
+                0.0, (num_training_steps - s) / max(1, num_training_steps - num_warmup_steps)))
+    raise ValueError(f"unknown lr_scheduler_type {name!r}")
+
+
+class DecoderTrainer:
+    """One training step of the decoder head on a frozen encoder, data-parallel over ``world`` ranks."""
+
+    def __init__(self, vae_model, decoder, loss_fn, optimizer, scheduler=None, max_grad_norm=1.0,
+                 gradient_accumulation_steps=1, process_group=None):
+        self.vae, self.decoder, self.loss_fn = vae_model, decoder, loss_fn
+        self.opt, self.sched = optimizer, scheduler
+        self.max_grad_norm = max_grad_norm
+        self.accum = max(1, gradient_accumulation_steps)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.params = [p for p in decoder.parameters() if p.requires_grad]
+        # one flat gradient bucket; every p.grad is a view into it
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.buffers = [b for b in decoder.buffers() if b.is_floating_point()]
+        self._pending = None
+        self._micro = 0
+        if self.world > 1:  # initial parameter broadcast (DDP does the same at wrap time)
+            for t in list(decoder.parameters()) + list(decoder.buffers()):
+                dist.broadcast(t.data, src=0, group=self.pg)
+
+    # -- gradient exchange ------------------------------------------------------------------
+    def _launch_allreduce(self):
+        if self.world > 1:
+            self._pending = dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        else:
+            self._pending = True
+
+    def finish_update(self):
+        """Wait for the in-flight all-reduce (if any), average, clip, step the optimizer."""
+        if self._pending is None:
+            return
+        if self.world > 1:
+            self._pending.wait()
+            self.flat_grad.div_(self.world)
+        self._pending = None
+        if self.max_grad_norm and self.max_grad_norm > 0:
+            nn.utils.clip_grad_norm_(self.params, self.max_grad_norm)
+        self.opt.step()
+        if self.sched is not None:
+            self.sched.step()
+        self.flat_grad.zero_()
+
+    # -- one micro-step ----------------------------------------------------------------------
+    def step(self, pixel_values, labels):
+        with torch.no_grad():
+            latent = self.vae.encode(pixel_values)       # frozen encoder; overlaps the pending all-reduce
+        self.finish_update()                             # parameters of step k-1 are now final
+        if self.world > 1:                               # DDP broadcast_buffers semantics
+            for b in self.buffers:
+                dist.broadcast(b, src=0, group=self.pg)
+        self.decoder.train()
+        logits = self.decoder(latent)
+        loss = self.loss_fn(logits, labels) / self.accum
+        loss.backward()                                  # accumulates into the flat bucket views
+        self._micro += 1
+        if self._micro % self.accum == 0:
+            self._launch_allreduce()
+        return loss.detach()
+
+    def flush(self):
+        self.finish_update()
+
+
+def _ddp_env():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def train_decoder(args):
+    import pandas as pd
+    from torch.utils.data import DataLoader
+    from torch.utils.data.distributed import DistributedSampler
+
+    from .improved_losses import ClassBalancedLoss, FocalLoss, compute_class_distribution
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("vae_tagger_b200 needs CUDA devices (B200)")
+    world, rank, local = _ddp_env()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=device)
+    os.makedirs(args.output_dir, exist_ok=True)
+    if args.seed is not None:
+        torch.manual_seed(args.seed)
+
+    if args.vae_config_path and os.path.exists(args.vae_config_path):
+        vae_model = create_vae_from_config_file(args.vae_config_path, args.vae_checkpoint)
+    elif args.vae_checkpoint and os.path.exists(args.vae_checkpoint):
+        vae_model = DiffusersVAEWrapper(load_diffusers_vae_from_config(get_diffusers_vae_config(), args.vae_checkpoint))
+    else:
+        raise RuntimeError("a VAE checkpoint or a VAE config file must be provided")
+    vae_model.to(device).eval()
+    for p in vae_model.parameters():
+        p.requires_grad = False
+
+    info = get_vae_latent_info(args.resolution)
+    tags_df = pd.read_csv(args.tags_csv_path)
+    num_classes = len(tags_df["name"])
+    if args.use_attention:
+        decoder = create_attention_decoder(
+            info["latent_channels"], info["latent_height"], info["latent_width"], num_classes,
+            attention_config={"use_spatial_attention": args.use_spatial_attention,
+                              "use_self_attention": args.use_self_attention,
+                              "use_cross_attention": args.use_cross_attention,
+                              "attention_heads": args.attention_heads,
+                              "attention_dropout": args.attention_dropout})
+    else:
+        decoder = ClassificationDecoder(info["latent_channels"], info["latent_height"], info["latent_width"],
+                                        num_classes, use_adaptive_pooling=True)
+    if args.decoder_checkpoint and os.path.exists(args.decoder_checkpoint):
+        try:
+            decoder.load_state_dict(torch.load(args.decoder_checkpoint, map_location="cpu"), strict=False)
+        except Exception as e:  # noqa: BLE001 - the reference falls back to training from scratch (:87-92)
+            print(f"decoder checkpoint could not be loaded, training from scratch: {e}")
+    decoder.to(device)
+
+    transform = None if args.use_bucketing else get_image_transform(args.resolution)
+    dataset = TaggedImageDataset(args.json_path, args.tags_csv_path, transform=transform,
+                                 use_bucketing=args.use_bucketing, base_resolution=args.base_resolution,
+                                 max_resolution=args.max_resolution, bucket_step=args.bucket_step)
+    class_distribution = compute_class_distribution(dataset)
+    val_size = max(1, int(len(dataset) * 0.1))
+    train_ds, val_ds = torch.utils.data.random_split(dataset, [len(dataset) - val_size, val_size],
+                                                     generator=torch.Generator().manual_seed(args.seed or 0))
+    sampler = DistributedSampler(train_ds, world, rank, shuffle=True) if world > 1 else None
+    train_dl = DataLoader(train_ds, batch_size=args.train_batch_size, shuffle=sampler is None, sampler=sampler,
+                          pin_memory=True, num_workers=args.num_workers,
+                          prefetch_factor=args.prefetch_factor if args.num_workers > 0 else None,
+                          persistent_workers=args.num_workers > 0)
+    val_dl = DataLoader(val_ds, batch_size=args.train_batch_size, shuffle=False, pin_memory=True, num_workers=0)
+
+    loss_fn = FocalLoss(alpha=args.focal_alpha, gamma=args.focal_gamma) if args.use_focal_loss else nn.BCEWithLogitsLoss()
+    cb = ClassBalancedLoss() if args.use_class_balanced else None
+    if cb is not None:
+        base_fn = lambda logits, labels: cb(logits, labels, class_distribution)  # noqa: E731
+    else:
+        base_fn = loss_fn
+    optimizer = torch.optim.AdamW(decoder.parameters(), lr=args.learning_rate, weight_decay=args.weight_decay)
+    scheduler = get_scheduler(args.lr_scheduler_type, optimizer, args.lr_warmup_steps, args.num_epochs * len(train_dl))
+    trainer = DecoderTrainer(vae_model, decoder, base_fn, optimizer, scheduler, args.max_grad_norm,
+                             args.gradient_accumulation_steps)
+
+    best, history = float("inf"), {"train_loss": [], "val_loss": [], "learning_rates": []}
+    for epoch in range(args.num_epochs):
+        if sampler is not None:
+            sampler.set_epoch(epoch)
+        total, steps = torch.zeros((), device=device), 0
+        for step, batch in enumerate(train_dl):
+            loss = trainer.step(batch["pixel_values"].to(device, non_blocking=True),
+                                batch["labels"].to(device, non_blocking=True))
+            total += loss
+            steps += 1
+            if rank == 0 and step % args.logging_steps == 0:  # the only host sync of the loop
+                print(f"Epoch: {epoch}, Step: {step}, Loss: {loss.item():.4f}, "
+                      f"Avg Loss: {(total / steps).item():.4f}, LR: {optimizer.param_groups[0]['lr']:.2e}")
+        trainer.flush()
+        decoder.eval()
+        vtotal, vsteps = torch.zeros((), device=device), 0
+        with torch.no_grad():
+            for batch in val_dl:
+                logits = decoder(vae_model.encode(batch["pixel_values"].to(device)))
+                vtotal += base_fn(logits, batch["labels"].to(device))
+                vsteps += 1
+        tl, vl = (total / max(1, steps)).item(), (vtotal / max(1, vsteps)).item()
+        history["train_loss"].append(tl); history["val_loss"].append(vl)
+        history["learning_rates"].append(optimizer.param_groups[0]["lr"])
+        if rank == 0:
+            print(f"Epoch {epoch} completed - Train Loss: {tl:.4f}, Val Loss: {vl:.4f}")
+            if vl < best:
+                best = vl
+                torch.save(decoder.state_dict(), os.path.join(args.output_dir, "best_pytorch_model.bin"))
+            if (epoch + 1) % args.save_steps == 0:
+                torch.save(decoder.state_dict(), os.path.join(args.output_dir, "pytorch_model.bin"))
+    if rank == 0:
+        with open(os.path.join(args.output_dir, "training_history.json"), "w") as f:
+            json.dump(history, f, indent=2)
+    if world > 1:
+        dist.barrier()
+    return history
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--vae_checkpoint", type=str, required=True)
+    p.add_argument("--vae_config_path", type=str, default=None)
+    p.add_argument("--decoder_checkpoint", type=str, default=None)
+    p.add_argument("--json_path", type=str, required=True)
+    p.add_argument("--tags_csv_path", type=str, required=True)
+    p.add_argument("--output_dir", type=str, default="decoder_output")
+    p.add_argument("--resolution", type=int, default=1024)
+    p.add_argument("--train_batch_size", type=int, default=1)
+    p.add_argument("--num_epochs", type=int, default=10)
+    p.add_argument("--learning_rate", type=float, default=1e-3)
+    p.add_argument("--weight_decay", type=float, default=1e-6)
+    p.add_argument("--mixed_precision", type=str, default="fp16")
+    p.add_argument("--use_attention", action="store_true", default=True)
+    p.add_argument("--no_attention", action="store_true")
+    p.add_argument("--use_spatial_attention", action="store_true", default=True)
+    p.add_argument("--use_self_attention", action="store_true", default=True)
+    p.add_argument("--use_cross_attention", action="store_true")
+    p.add_argument("--attention_heads", type=int, default=8)
+    p.add_argument("--attention_dropout", type=float, default=0.1)
+    p.add_argument("--use_simplified_decoder_loss", action="store_true", default=True)
+    p.add_argument("--use_focal_loss", action="store_true")
+    p.add_argument("--use_class_balanced", action="store_true")
+    p.add_argument("--focal_alpha", type=float, default=1.0)
+    p.add_argument("--focal_gamma", type=float, default=2.0)
+    p.add_argument("--lr_scheduler_type", type=str, default="cosine")
+    p.add_argument("--lr_warmup_steps", type=int, default=500)
+    p.add_argument("--max_grad_norm", type=float, default=1.0)
+    p.add_argument("--logging_steps", type=int, default=100)
+    p.add_argument("--save_steps", type=int, default=5)
+    p.add_argument("--use_quant_conv", action="store_true")
+    p.add_argument("--use_post_quant_conv", action="store_true")
+    p.add_argument("--use_safetensors", action="store_true")
+    p.add_argument("--use_bucketing", action="store_true")
+    p.add_argument("--base_resolution", type=int, default=512)
+    p.add_argument("--max_resolution", type=int, default=1024)
+    p.add_argument("--bucket_step", type=int, default=64)
+    p.add_argument("--num_workers", type=int, default=4)
+    p.add_argument("--prefetch_factor", type=int, default=2)
+    p.add_argument("--gradient_accumulation_steps", type=int, default=1)
+    p.add_argument("--seed", type=int, default=42)
+    p.add_argument("--cudnn_benchmark", action="store_true")
+    p.add_argument("--cudnn_deterministic", action="store_true")
+    return p
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if args.no_attention:
+        args.use_attention = False
+    return train_decoder(args)
+
+
+if __name__ == "__main__":
+    main()
