@@ -32,8 +32,9 @@ extern "C" {
 typedef struct vt_ctx vt_ctx;
 
 /* precision of the encoder contraction path */
-#define VT_PREC_BF16 0 /* tcgen05 implicit GEMM, bf16 operands, fp32 accumulate (TMEM) */
+#define VT_PREC_BF16 0 /* tcgen05 implicit GEMM, 16-bit operands (bf16 raw / fp16 bounded), fp32 accumulate (TMEM) */
 #define VT_PREC_FP32 1 /* FFMA verification mode (north star "fp32 mode", rel L2 <= 1e-4) */
+#define VT_PREC_F16 2  /* vt_op_* only: fp16 operands (what the encoder schedule uses for bounded operands) */
 
 /* image input formats of vt_encode */
 #define VT_IN_F32_NCHW 0 /* [B,3,H,W] fp32 already normalised to [-1,1] (modules.py:136-140) */

@@ -22,17 +22,28 @@ def r16(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def rh(t):
+    return t.to(torch.float16).to(torch.float32)
+
+
+def opd_round(prec):
+    """rounding applied to the main operands by each precision mode of the single-op entry points"""
+    return {N.PREC_BF16: r16, N.PREC_F16: rh, N.PREC_FP32: (lambda t: t)}[prec]
+
+
 @pytest.mark.parametrize("batch,M,Nn,K,b_batched", [
     (1, 128, 128, 64, 0), (1, 256, 256, 512, 0), (2, 192, 1536, 512, 0), (3, 64, 32, 128, 1),
     (2, 320, 448, 1024, 1), (1, 1024, 4096, 512, 1),
 ])
-def test_gemm_bf16(ctx, batch, M, Nn, K, b_batched):
+@pytest.mark.parametrize("prec", [N.PREC_BF16, N.PREC_F16])
+def test_gemm_16bit(ctx, batch, M, Nn, K, b_batched, prec):
     g = torch.Generator().manual_seed(M + Nn + K)
     A = torch.randn(batch, M, K, generator=g)
     B = torch.randn(batch if b_batched else 1, Nn, K, generator=g)
     bias = torch.randn(Nn, generator=g)
-    out = ctx.op_gemm_nt(A, B if b_batched else B[0], bias, alpha=0.5, precision=N.PREC_BF16).cpu()
-    ref = 0.5 * torch.matmul(r16(A), r16(B).transpose(1, 2)) + bias
+    out = ctx.op_gemm_nt(A, B if b_batched else B[0], bias, alpha=0.5, precision=prec).cpu()
+    rr = opd_round(prec)
+    ref = 0.5 * torch.matmul(rr(A), rr(B).transpose(1, 2)) + bias
     assert rel(out, ref) < 2e-5, (rel(out, ref), (out - ref).abs().max().item())
 
 
@@ -75,7 +86,7 @@ def conv_ref(x, w, b, res, scx, scw, stride):
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("prec", [N.PREC_BF16, N.PREC_FP32])
+@pytest.mark.parametrize("prec", [N.PREC_BF16, N.PREC_F16, N.PREC_FP32])
 def test_conv(ctx, case, prec):
     n, cin, h, w_, cout, k, stride, use_res, cs = case
     g = torch.Generator().manual_seed(sum(case[:7]))
@@ -90,8 +101,10 @@ def test_conv(ctx, case, prec):
     r = ctx.op_conv2d(x, w, b, res, scx, scw, stride=stride, precision=prec, want_stats=want_stats)
     out, stats = (r if want_stats else (r, None))
     out = out.cpu()
-    if prec == N.PREC_BF16:
-        ref = conv_ref(r16(x), r16(w), b, r16(res) if use_res else None, r16(scx) if cs else None,
+    if prec != N.PREC_FP32:
+        # main operand + weights in the mode's format; residual / shortcut operands are raw bf16 tensors
+        rr = opd_round(prec)
+        ref = conv_ref(rr(x), rr(w), b, r16(res) if use_res else None, r16(scx) if cs else None,
                        r16(scw) if cs else None, stride)
         tol = 3e-5
     else:
@@ -108,28 +121,28 @@ def test_conv(ctx, case, prec):
 
 @pytest.mark.parametrize("shape", [(2, 128, 16, 24), (1, 256, 8, 8), (3, 512, 12, 4)])
 @pytest.mark.parametrize("silu", [False, True])
-@pytest.mark.parametrize("prec", [N.PREC_BF16, N.PREC_FP32])
+@pytest.mark.parametrize("prec", [N.PREC_BF16, N.PREC_F16, N.PREC_FP32])
 def test_group_norm(ctx, shape, silu, prec):
     g = torch.Generator().manual_seed(shape[1])
     x = torch.randn(*shape, generator=g) * 2 + 0.7
     gamma = torch.randn(shape[1], generator=g)
     beta = torch.randn(shape[1], generator=g)
     out = ctx.op_group_norm(x, gamma, beta, silu=silu, precision=prec).cpu()
-    xin = r16(x) if prec == N.PREC_BF16 else x
+    xin = x if prec == N.PREC_FP32 else r16(x)   # raw activations are stored bf16 in both 16-bit modes
     ref = F.group_norm(xin, 32, gamma, beta, eps=1e-6)
     if silu:
         ref = F.silu(ref)
-    # bf16 mode rounds the result to bf16: half an ulp = 2^-9 relative
-    tol = 4e-3 if prec == N.PREC_BF16 else 2e-6
+    # the result is rounded to bf16 (half an ulp = 2^-9 relative) or fp16 (2^-12)
+    tol = {N.PREC_BF16: 4e-3, N.PREC_F16: 5e-4, N.PREC_FP32: 2e-6}[prec]
     assert rel(out, ref) < tol, rel(out, ref)
 
 
 @pytest.mark.parametrize("rows,cols", [(5, 64), (3, 1000), (4, 4096), (2, 16384), (2, 20000)])
-@pytest.mark.parametrize("prec", [N.PREC_BF16, N.PREC_FP32])
+@pytest.mark.parametrize("prec", [N.PREC_BF16, N.PREC_F16, N.PREC_FP32])
 def test_softmax_rows(ctx, rows, cols, prec):
     g = torch.Generator().manual_seed(cols)
     s = torch.randn(rows, cols, generator=g) * 4
     out = ctx.op_softmax_rows(s, precision=prec).cpu()
     ref = torch.softmax(s, dim=-1)
-    tol = 4e-3 if prec == N.PREC_BF16 else 2e-6
+    tol = {N.PREC_BF16: 4e-3, N.PREC_F16: 5e-4, N.PREC_FP32: 2e-6}[prec]
     assert rel(out, ref) < tol, rel(out, ref)

@@ -14,7 +14,7 @@ import torch
 
 from . import _build
 
-PREC_BF16, PREC_FP32 = 0, 1
+PREC_BF16, PREC_FP32, PREC_F16 = 0, 1, 2
 IN_F32_NCHW, IN_U8_NHWC = 0, 1
 HEAD_ATTENTION, HEAD_PLAIN = 0, 1
 NUM_KERNEL_CLASSES = 8

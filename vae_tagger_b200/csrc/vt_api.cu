@@ -7,6 +7,7 @@
 
 #include "../../include/vae_tagger_b200.h"
 #include "vt_internal.h"
+#include "vt_ptx.cuh"
 
 using namespace vt;
 
@@ -19,10 +20,11 @@ struct Param {
 };
 
 struct ConvW {      // packed conv / linear operand: [Cout][Ktot]
-    bf16* w16 = nullptr;
+    bf16* w16 = nullptr;   // 16-bit copy (fp16 or bf16 bits, see f16)
     float* w32 = nullptr;
     float* bias = nullptr;  // [Cout] (conv2 + shortcut biases folded)
     int Cin = 0, Cout = 0, ksize = 1, Cs = 0, Ktot = 0;
+    bool f16 = true;  // 16-bit copy: main columns fp16 (else bf16); shortcut columns are always bf16
 };
 struct NormW {
     const float* gamma = nullptr;
@@ -136,8 +138,8 @@ void free_params(std::map<std::string, Param>& m) {
 
 // ---- weight packing kernels: OIHW fp32 -> [Cout][Ktot] with k = (kh*ks+kw)*Cin + ci, at column
 // offset k_off (the shortcut slab lands behind the taps).
-template <typename T>
-__global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cout, int Cin, int ks,
+template <int OFMT>  // FMT_BF16 / FMT_F32 / FMT_F16
+__global__ void pack_weight_kernel(const float* __restrict__ src, void* __restrict__ dstv, int Cout, int Cin, int ks,
                                    int Ktot, int k_off) {
     const long long total = 1LL * Cout * Cin * ks * ks;
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
@@ -148,8 +150,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
         const int ci = static_cast<int>(r % Cin);
         const int co = static_cast<int>(r / Cin);
         const long long d = 1LL * co * Ktot + k_off + (kh * ks + kw) * Cin + ci;
-        if constexpr (sizeof(T) == 2) dst[d] = __float2bfloat16(src[i]);
-        else dst[d] = src[i];
+        if constexpr (OFMT == FMT_BF16) static_cast<bf16*>(dstv)[d] = __float2bfloat16(src[i]);
+        else if constexpr (OFMT == FMT_F16)
+            static_cast<__half*>(dstv)[d] = __float2half_rn(fminf(fmaxf(src[i], -65504.f), 65504.f));
+        else static_cast<float*>(dstv)[d] = src[i];
     }
 }
 __global__ void add_vec_kernel(float* __restrict__ a, const float* __restrict__ b, int n) {
@@ -187,9 +191,11 @@ struct Packer {
         *p = static_cast<T*>(q);
         return 0;
     }
-    // conv weight `prefix`.weight [Cout][Cin][ks][ks] (+ optional shortcut [Cout][Cs][1][1]); Kpad pads K
+    // conv weight `prefix`.weight [Cout][Cin][ks][ks] (+ optional shortcut [Cout][Cs][1][1]); Kpad pads K.
+    // f16: the main operand of this conv is a normalised (bounded) tensor -> fp16 weight columns; the
+    // shortcut columns always multiply a raw bf16 activation and stay bf16.
     int conv(const std::string& prefix, int Cin, int Cout, int ks, const std::string& sc_prefix, int Cs, int Kpad,
-             ConvW* w) {
+             ConvW* w, bool f16 = true) {
         const Param *pw, *pb;
         VT_TRY(get(prefix + ".weight", {Cout, Cin, ks, ks}, &pw));
         VT_TRY(get(prefix + ".bias", {Cout}, &pb));
@@ -199,15 +205,17 @@ struct Packer {
         VT_TRY(alloc(&w->w32, static_cast<size_t>(Cout) * Ktot));
         VT_TRY(alloc(&w->bias, static_cast<size_t>(Cout)));
         const int grid = 1024;
-        pack_weight_kernel<bf16><<<grid, 256>>>(pw->dev, w->w16, Cout, Cin, ks, Ktot, 0);
-        pack_weight_kernel<float><<<grid, 256>>>(pw->dev, w->w32, Cout, Cin, ks, Ktot, 0);
+        w->f16 = f16;
+        if (f16) pack_weight_kernel<FMT_F16><<<grid, 256>>>(pw->dev, w->w16, Cout, Cin, ks, Ktot, 0);
+        else pack_weight_kernel<FMT_BF16><<<grid, 256>>>(pw->dev, w->w16, Cout, Cin, ks, Ktot, 0);
+        pack_weight_kernel<FMT_F32><<<grid, 256>>>(pw->dev, w->w32, Cout, Cin, ks, Ktot, 0);
         VT_CUDA(cudaMemcpy(w->bias, pb->dev, Cout * sizeof(float), cudaMemcpyDeviceToDevice));
         if (Cs > 0) {
             const Param *sw, *sb;
             VT_TRY(get(sc_prefix + ".weight", {Cout, Cs, 1, 1}, &sw));
             VT_TRY(get(sc_prefix + ".bias", {Cout}, &sb));
-            pack_weight_kernel<bf16><<<grid, 256>>>(sw->dev, w->w16, Cout, Cs, 1, Ktot, ks * ks * Cin);
-            pack_weight_kernel<float><<<grid, 256>>>(sw->dev, w->w32, Cout, Cs, 1, Ktot, ks * ks * Cin);
+            pack_weight_kernel<FMT_BF16><<<grid, 256>>>(sw->dev, w->w16, Cout, Cs, 1, Ktot, ks * ks * Cin);
+            pack_weight_kernel<FMT_F32><<<grid, 256>>>(sw->dev, w->w32, Cout, Cs, 1, Ktot, ks * ks * Cin);
             add_vec_kernel<<<(Cout + 255) / 256, 256>>>(w->bias, sb->dev, Cout);
         }
         VT_CUDA(cudaGetLastError());
@@ -216,7 +224,7 @@ struct Packer {
     // linear weights [out][in] stacked along the output dimension
     int linear(std::initializer_list<std::string> prefixes, int In, int OutEach, bool with_bias, ConvW* w) {
         const int n = static_cast<int>(prefixes.size());
-        w->Cin = In; w->Cout = n * OutEach; w->ksize = 1; w->Cs = 0; w->Ktot = In;
+        w->Cin = In; w->Cout = n * OutEach; w->ksize = 1; w->Cs = 0; w->Ktot = In; w->f16 = true;
         VT_TRY(alloc(&w->w16, static_cast<size_t>(w->Cout) * In));
         VT_TRY(alloc(&w->w32, static_cast<size_t>(w->Cout) * In));
         VT_TRY(alloc(&w->bias, static_cast<size_t>(w->Cout)));
@@ -226,7 +234,7 @@ struct Packer {
             VT_TRY(get(pre + ".weight", {OutEach, In}, &pw));
             VT_TRY(get(pre + ".bias", {OutEach}, &pb));
             const size_t off = static_cast<size_t>(i) * OutEach * In;
-            VT_TRY(launch_cast_f32_bf16(pw->dev, w->w16 + off, 1LL * OutEach * In, nullptr));
+            VT_TRY(launch_cast_f32_16(pw->dev, w->w16 + off, FMT_F16, 1LL * OutEach * In, nullptr));
             VT_CUDA(cudaMemcpy(w->w32 + off, pw->dev, sizeof(float) * OutEach * In, cudaMemcpyDeviceToDevice));
             if (with_bias)
                 VT_CUDA(cudaMemcpy(w->bias + static_cast<size_t>(i) * OutEach, pb->dev, sizeof(float) * OutEach,
@@ -266,16 +274,19 @@ void free_packed(vt_ctx* c) {
 // GroupNorm statistics come from the producing contraction's epilogue (bf16 mode) or a separate
 // reduction (fp32 mode).
 //
-// Storage precision policy of bf16 mode (operands of every contraction are bf16, accumulation is
-// fp32 in TMEM): tensors that are only read by a GroupNorm pass or as an epilogue residual are
-// kept in fp32 where that is cheap -- the residual stream from the second resolution level down,
-// conv1 outputs from the third level down -- because storage rounding of the stream is what
-// pushes the bf16 pipeline over the 1e-2 latent bar (tools/emulate_bf16.py: 1.06e-2 all-bf16
-// storage, 9.1e-3 with this policy).  Tensors a TMA operand reads (downsample inputs, shortcut
-// operands) stay bf16.  The full-resolution level, which carries ~60 % of the HBM traffic, is bf16.
+// Formats of bf16 mode ("16-bit tensor-core mode"; accumulation is always fp32 in TMEM):
+//   * raw activations (residual stream, conv1 outputs) are stored bf16: unbounded range, 8-bit mantissa;
+//   * every *bounded* MMA operand -- GroupNorm+SiLU outputs, the normalised image patches, q/k/v, softmax
+//     probabilities, the attention output, and all weights that multiply them -- is fp16 (11-bit
+//     mantissa): the operand rounding that dominates the pipeline's error shrinks 8x.  Measured with
+//     tools/emulate_bf16.py against the fp32 oracle: all-bf16 operands 1.06e-2 latent rel-L2 (over the
+//     1e-2 bar), fp16 bounded operands + bf16 storage 0.80e-2.  The reference itself infers under
+//     fp16 autocast (infer_full.py:100);
+//   * operands that ARE raw activations (downsample conv input, 1x1 shortcut input) stay bf16, with
+//     bf16 weight columns.
 struct Act {
     void* p = nullptr;
-    int fp32 = 0;
+    int fmt = 0;  // FMT_BF16 / FMT_F32 / FMT_F16
 };
 
 struct EncRun {
@@ -293,16 +304,17 @@ struct EncRun {
         return p;
     }
     const void* W(const ConvW& w) const { return fp32 ? static_cast<const void*>(w.w32) : static_cast<const void*>(w.w16); }
-    bool stream_fp32(int level, bool feeds_tma) const { return fp32 || (level >= 1 && !feeds_tma); }
-    bool h_fp32(int level) const { return fp32 || level >= 2; }
+    int raw_fmt() const { return fp32 ? FMT_F32 : FMT_BF16; }   // residual stream / conv1 outputs
+    int opd_fmt() const { return fp32 ? FMT_F32 : FMT_F16; }    // bounded MMA operands
 
     int conv(const void* in, int H, int Wd, const ConvW& w, int stride, const void* sc_in, const Act* residual,
              Act out, double* st) {
         ConvOp op;
         op.in = in; op.N = n; op.Hin = H; op.Win = Wd; op.Cin = w.Cin; op.ksize = w.ksize; op.stride = stride;
+        op.in_f16 = w.f16;
         op.w = W(w); op.Cout = w.Cout; op.sc_in = sc_in; op.Cs = w.Cs; op.bias = w.bias;
-        if (residual) { op.residual = residual->p; op.residual_fp32 = residual->fp32; }
-        op.out = out.p; op.out_fp32 = out.fp32;
+        if (residual) { op.residual = residual->p; op.residual_fp32 = residual->fmt == FMT_F32; }
+        op.out = out.p; op.out_fmt = out.fmt;
         if (fp32) {
             VT_TRY(launch_conv_fp32(op, s, c->prof));
             if (st) {
@@ -318,16 +330,17 @@ struct EncRun {
         if (fp32) {
             double* st = op.stats;
             op.stats = nullptr;
-            op.out_fp32 = 1;
+            op.out_fmt = FMT_F32;
             VT_TRY(launch_gemm_fp32(op, s, c->prof));
             if (st) VT_TRY(launch_gn_stats(op.out, 1, st, op.batch, rows_for_stats, op.N, groups, s, c->prof));
             return 0;
         }
         return launch_gemm(op, s, c->prof);
     }
-    // normalised operand: always bf16 in bf16 mode (it feeds TMA), fp32 in verification mode
+    // normalised operand: fp16 in 16-bit mode (it feeds TMA), fp32 in verification mode
     int gn(Act x, void* y, const double* st, const NormW& nw, long long HW, int C, int silu) {
-        return launch_gn_apply(x.p, x.fp32, y, fp32, st, nw.gamma, nw.beta, n, HW, C, groups, 1e-6f, silu, s, c->prof);
+        return launch_gn_apply(x.p, x.fmt == FMT_F32, y, opd_fmt(), st, nw.gamma, nw.beta, n, HW, C, groups, 1e-6f, silu,
+                               s, c->prof);
     }
     // ResnetBlock2D: out = x (+shortcut) + conv2(silu(norm2(conv1(silu(norm1(x))))))
     int resnet(const ResnetW& r, Act x, const double* st_x, int H, int Wd, int level, void* T, void* Hb, Act out,
@@ -335,11 +348,11 @@ struct EncRun {
         const long long HW = 1LL * H * Wd;
         VT_TRY(gn(x, T, st_x, r.norm1, HW, r.cin, 1));
         double* st_h = new_stats();
-        Act h{Hb, h_fp32(level)};
+        Act h{Hb, raw_fmt()};
         VT_TRY(conv(T, H, Wd, r.conv1, 1, nullptr, nullptr, h, st_h));
         VT_TRY(gn(h, T, st_h, r.norm2, HW, r.cout, 1));
         if (r.cin != r.cout) {
-            VT_CHECK(fp32 || !x.fp32, "shortcut operand must be bf16");
+            VT_CHECK(fp32 || x.fmt == FMT_BF16, "shortcut operand must be bf16");
             return conv(T, H, Wd, r.conv2, 1, x.p, nullptr, out, st_out);
         }
         return conv(T, H, Wd, r.conv2, 1, nullptr, &x, out, st_out);
@@ -360,17 +373,8 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
     const long long tokens = 1LL * lh * lw;
     const int Cm = cfg.block_out_channels[nb - 1];
 
-    // ---- workspace layout.  One activation buffer holds the largest tensor of any level in its
-    // storage type: level 0 is C0 channels at es bytes; deeper levels have at most 2x the channels at
-    // 1/4 of the pixels, so even stored as fp32 they fit.
+    // ---- workspace layout.  One activation buffer holds the largest tensor of any level (level 0).
     size_t act = static_cast<size_t>(n) * H * Wd * C0 * es;
-    {
-        int hh = H, ww = Wd;
-        for (int b = 0; b < nb; ++b) {
-            act = std::max(act, static_cast<size_t>(n) * hh * ww * cfg.block_out_channels[b] * 4 * (b >= 1 || fp32 ? 1 : 0));
-            if (b < nb - 1) { hh /= 2; ww /= 2; }
-        }
-    }
     act = align_up(act, 1024);
     size_t attn_bytes = 0;
     long long rows_per_chunk = 0;
@@ -424,9 +428,9 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
     const char* img = static_cast<const char*>(a->images);
     const size_t img_stride = a->in_fmt == VT_IN_U8_NHWC ? static_cast<size_t>(H) * Wd * 3
                                                          : static_cast<size_t>(H) * Wd * 3 * sizeof(float);
-    VT_TRY(launch_im2col3x3(img + img_stride * img0, a->in_fmt, Hb, fp32, n, H, Wd, s, c->prof));
+    VT_TRY(launch_im2col3x3(img + img_stride * img0, a->in_fmt, Hb, R.opd_fmt(), n, H, Wd, s, c->prof));
     double* st_x = R.new_stats();
-    Act X{Xp, R.stream_fp32(0, false)};
+    Act X{Xp, R.raw_fmt()};
     {
         ConvW w = c->conv_in;  // viewed as a 1x1 conv over the 64-wide gathered patches
         w.Cin = 64; w.ksize = 1; w.Cs = 0;
@@ -440,20 +444,16 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
         const int nl = static_cast<int>(c->down[b].size());
         const bool has_down = c->downsample[b].Cout != 0;
         for (int l = 0; l < nl; ++l) {
-            // who reads this block's output through TMA?  the downsample conv (last layer of a level)
-            const bool feeds_tma = (l == nl - 1) && has_down;
             double* st_o = R.new_stats();
-            Act out{spare, R.stream_fp32(b, feeds_tma)};
+            Act out{spare, R.raw_fmt()};
             VT_TRY(R.resnet(c->down[b][l], X, st_x, h, w_, b, T, Hb, out, st_o));
             advance(out);
             st_x = st_o;
         }
         if (has_down) {
-            // the next level's first resnet reads its input as a shortcut operand when channels change
-            const bool feeds_tma = cfg.block_out_channels[b + 1] != cfg.block_out_channels[b];
             double* st_o = R.new_stats();
-            Act out{spare, R.stream_fp32(b + 1, feeds_tma)};
-            VT_CHECK(fp32 || !X.fp32, "downsample operand must be bf16");
+            Act out{spare, R.raw_fmt()};
+            VT_CHECK(fp32 || X.fmt == FMT_BF16, "downsample operand must be bf16");
             VT_TRY(R.conv(X.p, h, w_, c->downsample[b], 2, nullptr, nullptr, out, st_o));
             advance(out);
             st_x = st_o;
@@ -464,7 +464,7 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
     // ---- mid block
     {
         double* st_o = R.new_stats();
-        Act out{spare, R.stream_fp32(lvl, false)};
+        Act out{spare, R.raw_fmt()};
         VT_TRY(R.resnet(c->mid0, X, st_x, h, w_, lvl, T, Hb, out, st_o));
         advance(out);
         st_x = st_o;
@@ -482,13 +482,13 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
         {   // [q | k] = t Wqk^T + b : [n][tokens][2C]
             GemmOp g;
             g.A = T; g.B = R.W(A.qk); g.batch = n; g.M = static_cast<int>(tokens); g.N = 2 * C; g.K = C;
-            g.a_batched = 1; g.b_batched = 0; g.bias = A.qk.bias; g.out = QK;
+            g.a_batched = 1; g.b_batched = 0; g.bias = A.qk.bias; g.out = QK; g.ab_f16 = 1; g.out_fmt = R.opd_fmt();
             VT_TRY(R.gemm(g, tokens));
         }
         {   // V^T = Wv t^T : [n][C][tokens]  (bias b_v is added after P.V: softmax rows sum to one)
             GemmOp g;
             g.A = R.W(A.v); g.B = T; g.batch = n; g.M = C; g.N = static_cast<int>(tokens); g.K = C;
-            g.a_batched = 0; g.b_batched = 1; g.out = Vt;
+            g.a_batched = 0; g.b_batched = 1; g.out = Vt; g.ab_f16 = 1; g.out_fmt = R.opd_fmt();
             VT_TRY(R.gemm(g, 0));
         }
         const float scale = 1.0f / sqrtf(static_cast<float>(C));
@@ -503,10 +503,10 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
                     g.B = QK + (static_cast<size_t>(i0) * tokens * 2 * C + C) * es;
                     g.ldb = 2 * C; g.b_bstride = tokens * 2 * C;
                     g.batch = nb_img; g.M = rows; g.N = static_cast<int>(tokens); g.K = C;
-                    g.alpha = scale; g.out = S; g.out_fp32 = 1;
+                    g.alpha = scale; g.out = S; g.out_fmt = FMT_F32; g.ab_f16 = 1;
                     VT_TRY(R.gemm(g, 0));
                 }
-                VT_TRY(launch_softmax_rows(reinterpret_cast<const float*>(S), P, fp32, 1LL * nb_img * rows,
+                VT_TRY(launch_softmax_rows(reinterpret_cast<const float*>(S), P, R.opd_fmt(), 1LL * nb_img * rows,
                                            static_cast<int>(tokens), tokens, tokens, s, c->prof));
                 if (pv_splits > 1) {
                     // O = P V + b_v with K split: batch index = K slice, fp32 partials, then combine
@@ -515,17 +515,17 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
                     g.A = P; g.lda = tokens; g.a_bstride = ks;
                     g.B = Vt + static_cast<size_t>(i0) * C * tokens * es; g.ldb = tokens; g.b_bstride = ks;
                     g.batch = pv_splits; g.M = rows; g.N = C; g.K = static_cast<int>(ks);
-                    g.out = PART; g.out_fp32 = 1; g.ld_out = C; g.out_bstride = 1LL * rows * C;
+                    g.out = PART; g.out_fmt = FMT_F32; g.ab_f16 = 1; g.ld_out = C; g.out_bstride = 1LL * rows * C;
                     VT_TRY(R.gemm(g, 0));
                     VT_TRY(launch_splitk_reduce(reinterpret_cast<const float*>(PART), pv_splits, 1LL * rows * C, A.v.bias,
-                                                reinterpret_cast<bf16*>(O + (static_cast<size_t>(i0) * tokens + r0) * C * es),
-                                                rows, C, C, s, c->prof));
+                                                O + (static_cast<size_t>(i0) * tokens + r0) * C * es, FMT_F16, rows, C, C,
+                                                s, c->prof));
                 } else {   // O = P V + b_v
                     GemmOp g;
                     g.A = P; g.lda = tokens; g.a_bstride = 1LL * rows * tokens;
                     g.B = Vt + static_cast<size_t>(i0) * C * tokens * es; g.ldb = tokens; g.b_bstride = 1LL * C * tokens;
                     g.batch = nb_img; g.M = rows; g.N = C; g.K = static_cast<int>(tokens);
-                    g.bias = A.v.bias;
+                    g.bias = A.v.bias; g.ab_f16 = 1; g.out_fmt = R.opd_fmt();
                     g.out = O + (static_cast<size_t>(i0) * tokens + r0) * C * es;
                     g.ld_out = C; g.out_bstride = tokens * C;
                     VT_TRY(R.gemm(g, 0));
@@ -534,11 +534,11 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
         }
         {   // out = O Wo^T + b_o + x
             double* st_o = R.new_stats();
-            Act out{spare, R.stream_fp32(lvl, false)};
+            Act out{spare, R.raw_fmt()};
             GemmOp g;
             g.A = O; g.B = R.W(A.out); g.batch = n; g.M = static_cast<int>(tokens); g.N = C; g.K = C;
-            g.a_batched = 1; g.b_batched = 0; g.bias = A.out.bias; g.residual = X.p; g.residual_fp32 = X.fp32;
-            g.out = out.p; g.out_fp32 = out.fp32; g.stats = st_o;
+            g.a_batched = 1; g.b_batched = 0; g.bias = A.out.bias; g.residual = X.p; g.residual_fp32 = X.fmt == FMT_F32;
+            g.out = out.p; g.out_fmt = out.fmt; g.ab_f16 = 1; g.stats = st_o;
             VT_TRY(R.gemm(g, tokens));
             advance(out);
             st_x = st_o;
@@ -546,14 +546,14 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
     }
     {
         double* st_o = R.new_stats();
-        Act out{spare, R.stream_fp32(lvl, false)};
+        Act out{spare, R.raw_fmt()};
         VT_TRY(R.resnet(c->mid1, X, st_x, h, w_, lvl, T, Hb, out, st_o));
         advance(out);
         st_x = st_o;
     }
     // ---- conv_norm_out + SiLU + conv_out -> moments (fp32 NHWC) -> DiagonalGaussian outputs
     VT_TRY(R.gn(X, T, st_x, c->norm_out, tokens, Cm, 1));
-    VT_TRY(R.conv(T, h, w_, c->conv_out, 1, nullptr, nullptr, Act{L.mom.p, 1}, nullptr));
+    VT_TRY(R.conv(T, h, w_, c->conv_out, 1, nullptr, nullptr, Act{L.mom.p, FMT_F32}, nullptr));
     const size_t lat_stride = static_cast<size_t>(LC) * tokens;
     VT_TRY(launch_moments_to_latent(static_cast<const float*>(L.mom.p),
                                     a->latent ? a->latent + lat_stride * img0 : nullptr,
@@ -687,7 +687,7 @@ int vt_encoder_finalize(vt_ctx* c) {
         }
         if (b < cfg.num_blocks - 1)
             VT_TRY(P.conv("down_blocks." + std::to_string(b) + ".downsamplers.0.conv", cout, cout, 3, "", 0, 0,
-                          &c->downsample[b]));
+                          &c->downsample[b], /*f16=*/false));
         cin = cout;
     }
     const int Cm = cfg.block_out_channels[cfg.num_blocks - 1];
@@ -967,6 +967,10 @@ int vt_profile_read(vt_ctx* c, double* out, int reset) {
 }
 
 // ------------------------------------------------------------------------------------- single ops
+// precision: VT_PREC_BF16 (bf16 operands), VT_PREC_FP32 (FFMA path), VT_PREC_F16 (fp16 operands, the
+// format the encoder schedule uses for bounded operands; raw shortcut operands stay bf16)
+static int op_fmt(int precision) { return precision == VT_PREC_FP32 ? FMT_F32 : (precision == VT_PREC_F16 ? FMT_F16 : FMT_BF16); }
+
 int vt_op_conv2d(vt_ctx* c, const float* x, const float* w, const float* bias, const float* residual,
                  const float* sc_x, const float* sc_w, int N, int Cin, int H, int W, int Cout, int ksize, int stride,
                  int Cs, int precision, float* out, double* stats, void* stream) {
@@ -975,6 +979,8 @@ int vt_op_conv2d(vt_ctx* c, const float* x, const float* w, const float* bias, c
     VT_CHECK((sc_x == nullptr) == (sc_w == nullptr), "shortcut operand and weight go together");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int fp32 = precision == VT_PREC_FP32;
+    const int fmt = op_fmt(precision);
+    const int raw = fp32 ? FMT_F32 : FMT_BF16;
     const size_t es = fp32 ? 4 : 2;
     const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
     if (!sc_x) Cs = 0;
@@ -988,22 +994,24 @@ int vt_op_conv2d(vt_ctx* c, const float* x, const float* w, const float* bias, c
     char* p = static_cast<char*>(c->opws.p);
     void* dx = p; void* dout = p + b_x; void* dres = p + b_x + b_o; void* dsc = p + b_x + b_o + b_r;
     void* dw = p + b_x + b_o + b_r + b_s;
-    VT_TRY(launch_nchw_to_nhwc(x, dx, fp32, N, Cin, 1LL * H * W, s));
-    if (residual) VT_TRY(launch_nchw_to_nhwc(residual, dres, fp32, N, Cout, 1LL * Ho * Wo, s));
-    if (sc_x) VT_TRY(launch_nchw_to_nhwc(sc_x, dsc, fp32, N, Cs, 1LL * Ho * Wo, s));
+    VT_TRY(launch_nchw_to_nhwc(x, dx, fmt, N, Cin, 1LL * H * W, s));
+    if (residual) VT_TRY(launch_nchw_to_nhwc(residual, dres, raw, N, Cout, 1LL * Ho * Wo, s));
+    if (sc_x) VT_TRY(launch_nchw_to_nhwc(sc_x, dsc, raw, N, Cs, 1LL * Ho * Wo, s));
     VT_CUDA(cudaMemsetAsync(dw, 0, b_w, s));
-    if (fp32) {
-        pack_weight_kernel<float><<<256, 256, 0, s>>>(w, static_cast<float*>(dw), Cout, Cin, ksize, Ktot, 0);
-        if (sc_w) pack_weight_kernel<float><<<256, 256, 0, s>>>(sc_w, static_cast<float*>(dw), Cout, Cs, 1, Ktot, ksize * ksize * Cin);
+    if (fmt == FMT_F32) {
+        pack_weight_kernel<FMT_F32><<<256, 256, 0, s>>>(w, dw, Cout, Cin, ksize, Ktot, 0);
+        if (sc_w) pack_weight_kernel<FMT_F32><<<256, 256, 0, s>>>(sc_w, dw, Cout, Cs, 1, Ktot, ksize * ksize * Cin);
     } else {
-        pack_weight_kernel<bf16><<<256, 256, 0, s>>>(w, static_cast<bf16*>(dw), Cout, Cin, ksize, Ktot, 0);
-        if (sc_w) pack_weight_kernel<bf16><<<256, 256, 0, s>>>(sc_w, static_cast<bf16*>(dw), Cout, Cs, 1, Ktot, ksize * ksize * Cin);
+        if (fmt == FMT_F16) pack_weight_kernel<FMT_F16><<<256, 256, 0, s>>>(w, dw, Cout, Cin, ksize, Ktot, 0);
+        else pack_weight_kernel<FMT_BF16><<<256, 256, 0, s>>>(w, dw, Cout, Cin, ksize, Ktot, 0);
+        if (sc_w) pack_weight_kernel<FMT_BF16><<<256, 256, 0, s>>>(sc_w, dw, Cout, Cs, 1, Ktot, ksize * ksize * Cin);
     }
     VT_CUDA(cudaGetLastError());
     ConvOp op;
-    op.in = dx; op.N = N; op.Hin = H; op.Win = W; op.Cin = Cin; op.ksize = ksize; op.stride = stride; op.w = dw;
+    op.in = dx; op.in_f16 = fmt == FMT_F16; op.N = N; op.Hin = H; op.Win = W; op.Cin = Cin; op.ksize = ksize;
+    op.stride = stride; op.w = dw;
     op.Cout = Cout; op.sc_in = sc_x ? dsc : nullptr; op.Cs = Cs; op.bias = bias; op.residual = residual ? dres : nullptr;
-    op.out = dout; op.out_fp32 = 1;
+    op.out = dout; op.out_fmt = FMT_F32;
     if (stats) VT_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * N * 64, s));
     if (fp32) {
         VT_TRY(launch_conv_fp32(op, s, c->prof));
@@ -1012,7 +1020,7 @@ int vt_op_conv2d(vt_ctx* c, const float* x, const float* w, const float* bias, c
         op.stats = stats;
         VT_TRY(launch_conv(op, s, c->prof));
     }
-    return launch_nhwc_to_nchw(dout, 1, out, N, Cout, 1LL * Ho * Wo, s);
+    return launch_nhwc_to_nchw(dout, FMT_F32, out, N, Cout, 1LL * Ho * Wo, s);
 }
 
 int vt_op_gemm_nt(vt_ctx* c, const float* A, const float* B, const float* bias, int batch, int M, int N, int K,
@@ -1022,18 +1030,19 @@ int vt_op_gemm_nt(vt_ctx* c, const float* A, const float* B, const float* bias, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     GemmOp g;
     g.batch = batch; g.M = M; g.N = N; g.K = K; g.a_batched = 1; g.b_batched = b_batched; g.bias = bias;
-    g.alpha = alpha; g.out = out; g.out_fp32 = 1;
+    g.alpha = alpha; g.out = out; g.out_fmt = FMT_F32;
     if (precision == VT_PREC_FP32) {
         g.A = A; g.B = B;
         return launch_gemm_fp32(g, s, c->prof);
     }
+    const int fmt = op_fmt(precision);
     const size_t na = static_cast<size_t>(batch) * M * K, nbb = static_cast<size_t>(b_batched ? batch : 1) * N * K;
     VT_TRY(c->opws.ensure(align_up(na * 2, 256) + nbb * 2));
-    bf16* da = static_cast<bf16*>(c->opws.p);
-    bf16* db = reinterpret_cast<bf16*>(static_cast<char*>(c->opws.p) + align_up(na * 2, 256));
-    VT_TRY(launch_cast_f32_bf16(A, da, static_cast<long long>(na), s));
-    VT_TRY(launch_cast_f32_bf16(B, db, static_cast<long long>(nbb), s));
-    g.A = da; g.B = db;
+    void* da = c->opws.p;
+    void* db = static_cast<char*>(c->opws.p) + align_up(na * 2, 256);
+    VT_TRY(launch_cast_f32_16(A, da, fmt, static_cast<long long>(na), s));
+    VT_TRY(launch_cast_f32_16(B, db, fmt, static_cast<long long>(nbb), s));
+    g.A = da; g.B = db; g.ab_f16 = fmt == FMT_F16;
     return launch_gemm(g, s, c->prof);
 }
 
@@ -1043,6 +1052,8 @@ int vt_op_group_norm(vt_ctx* c, const float* x, const float* gamma, const float*
     VT_CHECK(x && gamma && beta && out, "null pointers");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int fp32 = precision == VT_PREC_FP32;
+    const int ofmt = op_fmt(precision);          // output: bf16 / fp32 / fp16
+    const int ifmt = fp32 ? FMT_F32 : FMT_BF16;  // raw input storage
     const size_t es = fp32 ? 4 : 2;
     const long long HW = 1LL * H * W;
     const size_t b_x = align_up(static_cast<size_t>(N) * HW * C * es, 256);
@@ -1050,22 +1061,23 @@ int vt_op_group_norm(vt_ctx* c, const float* x, const float* gamma, const float*
     VT_TRY(c->opws.ensure(2 * b_x + b_s));
     char* p = static_cast<char*>(c->opws.p);
     void* dx = p; void* dy = p + b_x; double* st = reinterpret_cast<double*>(p + 2 * b_x);
-    VT_TRY(launch_nchw_to_nhwc(x, dx, fp32, N, C, HW, s));
+    VT_TRY(launch_nchw_to_nhwc(x, dx, ifmt, N, C, HW, s));
     VT_CUDA(cudaMemsetAsync(st, 0, b_s, s));
     VT_TRY(launch_gn_stats(dx, fp32, st, N, HW, C, groups, s, c->prof));
-    VT_TRY(launch_gn_apply(dx, fp32, dy, fp32, st, gamma, beta, N, HW, C, groups, eps, silu, s, c->prof));
-    return launch_nhwc_to_nchw(dy, fp32, out, N, C, HW, s);
+    VT_TRY(launch_gn_apply(dx, fp32, dy, ofmt, st, gamma, beta, N, HW, C, groups, eps, silu, s, c->prof));
+    return launch_nhwc_to_nchw(dy, ofmt, out, N, C, HW, s);
 }
 
 int vt_op_softmax_rows(vt_ctx* c, const float* sc, int64_t rows, int cols, int precision, float* out, void* stream) {
     VT_TRY(set_device(c));
     VT_CHECK(sc && out, "null pointers");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (precision == VT_PREC_FP32) return launch_softmax_rows(sc, out, 1, rows, cols, cols, cols, s, c->prof);
+    if (precision == VT_PREC_FP32) return launch_softmax_rows(sc, out, FMT_F32, rows, cols, cols, cols, s, c->prof);
+    const int fmt = op_fmt(precision);
     VT_TRY(c->opws.ensure(static_cast<size_t>(rows) * cols * 2));
-    VT_TRY(launch_softmax_rows(sc, c->opws.p, 0, rows, cols, cols, cols, s, c->prof));
-    // widen bf16 -> fp32 through the layout kernel with C = cols, HW = 1 per row
-    return launch_nhwc_to_nchw(c->opws.p, 0, out, static_cast<int>(rows), cols, 1, s);
+    VT_TRY(launch_softmax_rows(sc, c->opws.p, fmt, rows, cols, cols, cols, s, c->prof));
+    // widen to fp32 through the layout kernel with C = cols, HW = 1 per row
+    return launch_nhwc_to_nchw(c->opws.p, fmt, out, static_cast<int>(rows), cols, 1, s);
 }
 
 }  // extern "C"

@@ -1,6 +1,8 @@
 // HBM-bound kernels of the encoder path: conv_in patch gather, GroupNorm statistics /
 // apply (+SiLU), attention row softmax, moments -> latent, layout conversions.
 // All are vectorised (16-byte accesses), channel-innermost (NHWC) and warp-shuffle based.
+#include <type_traits>
+
 #include "vt_internal.h"
 #include "vt_ptx.cuh"
 
@@ -39,8 +41,8 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // out: [N,H,W,64] (bf16 or fp32) with k = (kh*3+kw)*3 + c for k < 27 and zeros above: the K=27
 // contraction of conv_in becomes one 64-wide K chunk of the implicit-GEMM kernel.
 // 8 threads per pixel, each writes 8 consecutive k.
-template <typename T>
-__global__ void __launch_bounds__(256) im2col3x3_kernel(const void* __restrict__ in, int fmt, T* __restrict__ out,
+template <int OFMT>
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const void* __restrict__ in, int fmt, void* __restrict__ out,
                                                         int N, int H, int W) {
     const long long total = 1LL * N * H * W * 8;
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
@@ -70,9 +72,9 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const void* __restrict__
             }
             v[e] = val;
         }
-        if constexpr (sizeof(T) == 2) {
-            uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                 pack_bf16x2(v[6], v[7]));
+        if constexpr (OFMT != FMT_F32) {
+            uint4 o = make_uint4(pack16x2<OFMT>(v[0], v[1]), pack16x2<OFMT>(v[2], v[3]), pack16x2<OFMT>(v[4], v[5]),
+                                 pack16x2<OFMT>(v[6], v[7]));
             reinterpret_cast<uint4*>(out)[i] = o;
         } else {
             float4* o = reinterpret_cast<float4*>(out) + 2 * i;
@@ -82,14 +84,15 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const void* __restrict__
     }
 }
 
-int launch_im2col3x3(const void* in, int fmt, void* out, int out_fp32, int N, int H, int W, cudaStream_t s,
+int launch_im2col3x3(const void* in, int fmt, void* out, int out_fmt, int N, int H, int W, cudaStream_t s,
                      Profiler* prof) {
     const long long total = 1LL * N * H * W * 8;
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 1LL * sm_count() * 16));
-    const double bytes = 1.0 * N * H * W * ((fmt ? 3.0 : 12.0) + 64.0 * (out_fp32 ? 4 : 2));
+    const double bytes = 1.0 * N * H * W * ((fmt ? 3.0 : 12.0) + 64.0 * (out_fmt == FMT_F32 ? 4 : 2));
     profiler_begin(prof, KC_IM2COL, s, 0, bytes);
-    if (out_fp32) im2col3x3_kernel<float><<<grid, 256, 0, s>>>(in, fmt, static_cast<float*>(out), N, H, W);
-    else im2col3x3_kernel<bf16><<<grid, 256, 0, s>>>(in, fmt, static_cast<bf16*>(out), N, H, W);
+    if (out_fmt == FMT_F32) im2col3x3_kernel<FMT_F32><<<grid, 256, 0, s>>>(in, fmt, out, N, H, W);
+    else if (out_fmt == FMT_F16) im2col3x3_kernel<FMT_F16><<<grid, 256, 0, s>>>(in, fmt, out, N, H, W);
+    else im2col3x3_kernel<FMT_BF16><<<grid, 256, 0, s>>>(in, fmt, out, N, H, W);
     profiler_end(prof, KC_IM2COL, s);
     VT_CUDA(cudaGetLastError());
     return 0;
@@ -161,8 +164,8 @@ int launch_gn_stats(const void* x, int is_fp32, double* stats, int N, long long 
 // (sum, sumsq) doubles.  One thread owns 8 consecutive channels of a fixed channel block and
 // walks pixels, so scale/shift live in registers; every access is a 16-byte (bf16) or 2x16-byte
 // (fp32) vector and a warp touches 512 contiguous bytes.
-template <typename TI, typename TO, bool FAST>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y,
+template <typename TI, int OFMT, bool FAST>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const TI* __restrict__ x, void* __restrict__ yv,
                                                        const double* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, long long HW, int C, int G,
@@ -212,10 +215,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const TI* __restrict__ x,
                 }
                 v[e] = t;
             }
-            if constexpr (sizeof(TO) == 2) {
-                *reinterpret_cast<uint4*>(y + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                                pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            if constexpr (OFMT != FMT_F32) {
+                *reinterpret_cast<uint4*>(static_cast<bf16*>(yv) + off) =
+                    make_uint4(pack16x2<OFMT>(v[0], v[1]), pack16x2<OFMT>(v[2], v[3]), pack16x2<OFMT>(v[4], v[5]),
+                               pack16x2<OFMT>(v[6], v[7]));
             } else {
+                float* y = static_cast<float*>(yv);
                 *reinterpret_cast<float4*>(y + off) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4*>(y + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
             }
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const TI* __restrict__ x,
     }
 }
 
-int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fp32, const double* stats, const float* gamma,
+int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fmt, const double* stats, const float* gamma,
                     const float* beta, int N, long long HW, int C, int G, float eps, int silu, cudaStream_t s,
                     Profiler* prof) {
     VT_CHECK(C % 8 == 0 && C % G == 0, "GroupNorm apply needs C % 8 == 0 and C % groups == 0");
@@ -233,20 +238,19 @@ int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fp32, const double
     const long long cap = std::max(1, sm_count() * 16 / N);
     const int chunks = static_cast<int>(std::max<long long>(1, std::min(want, cap)));
     dim3 grid(chunks, N);
-    profiler_begin(prof, KC_GN_APPLY, s, 0, 1.0 * N * HW * C * ((x_fp32 ? 4 : 2) + (y_fp32 ? 4 : 2)));
-    if (x_fp32 && y_fp32)
-        gn_apply_kernel<float, float, false><<<grid, 256, 0, s>>>(static_cast<const float*>(x), static_cast<float*>(y),
-                                                                  stats, gamma, beta, HW, C, G, eps, silu);
-    else if (x_fp32)
-        gn_apply_kernel<float, bf16, true><<<grid, 256, 0, s>>>(static_cast<const float*>(x), static_cast<bf16*>(y),
-                                                                stats, gamma, beta, HW, C, G, eps, silu);
-    else if (!y_fp32)
-        gn_apply_kernel<bf16, bf16, true><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y),
-                                                               stats, gamma, beta, HW, C, G, eps, silu);
+    profiler_begin(prof, KC_GN_APPLY, s, 0, 1.0 * N * HW * C * ((x_fp32 ? 4 : 2) + (y_fmt == FMT_F32 ? 4 : 2)));
+#define VT_GN(TI, OF, FAST) \
+    gn_apply_kernel<TI, OF, FAST><<<grid, 256, 0, s>>>(static_cast<const TI*>(x), y, stats, gamma, beta, HW, C, G, eps, silu)
+    if (x_fp32 && y_fmt == FMT_F32) VT_GN(float, FMT_F32, false);
+    else if (x_fp32 && y_fmt == FMT_F16) VT_GN(float, FMT_F16, true);
+    else if (x_fp32 && y_fmt == FMT_BF16) VT_GN(float, FMT_BF16, true);
+    else if (!x_fp32 && y_fmt == FMT_F16) VT_GN(bf16, FMT_F16, true);
+    else if (!x_fp32 && y_fmt == FMT_BF16) VT_GN(bf16, FMT_BF16, true);
     else {
         set_error("GroupNorm apply bf16 -> fp32 is not instantiated");
         return -2;
     }
+#undef VT_GN
     profiler_end(prof, KC_GN_APPLY, s);
     VT_CUDA(cudaGetLastError());
     return 0;
@@ -256,9 +260,11 @@ int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fp32, const double
 // Attention row softmax: p = softmax(s) along the last dimension (scores already scaled by
 // the GEMM epilogue).  One 256-thread CTA per row; the row (<= 16384 values) lives in
 // registers, so it is read once and written once.  Wider rows take the three-pass loop.
+struct half_out { __half v; };  // distinct 2-byte element types for the probability output
 template <typename TO>
 __device__ __forceinline__ void store_prob(TO* p, float v) {
-    if constexpr (sizeof(TO) == 2) *p = __float2bfloat16(v);
+    if constexpr (std::is_same<TO, half_out>::value) p->v = __float2half_rn(v);
+    else if constexpr (sizeof(TO) == 2) *p = __float2bfloat16(v);
     else *p = v;
 }
 
@@ -358,11 +364,12 @@ static void softmax_dispatch(const float* s, TO* p, long long rows, int cols, lo
     else softmax_rows_wide_kernel<TO><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p);
 }
 
-int launch_softmax_rows(const float* s, void* p, int p_fp32, long long rows, int cols, long long ld_s,
+int launch_softmax_rows(const float* s, void* p, int p_fmt, long long rows, int cols, long long ld_s,
                         long long ld_p, cudaStream_t st, Profiler* prof) {
     VT_CHECK(rows > 0 && rows < (1LL << 31) && cols > 0, "softmax shape");
-    profiler_begin(prof, KC_SOFTMAX, st, 0, 1.0 * rows * cols * (4 + (p_fp32 ? 4 : 2)));
-    if (p_fp32) softmax_dispatch<float>(s, static_cast<float*>(p), rows, cols, ld_s, ld_p, st);
+    profiler_begin(prof, KC_SOFTMAX, st, 0, 1.0 * rows * cols * (4 + (p_fmt == FMT_F32 ? 4 : 2)));
+    if (p_fmt == FMT_F32) softmax_dispatch<float>(s, static_cast<float*>(p), rows, cols, ld_s, ld_p, st);
+    else if (p_fmt == FMT_F16) softmax_dispatch<half_out>(s, static_cast<half_out*>(p), rows, cols, ld_s, ld_p, st);
     else softmax_dispatch<bf16>(s, static_cast<bf16*>(p), rows, cols, ld_s, ld_p, st);
     profiler_end(prof, KC_SOFTMAX, st);
     VT_CUDA(cudaGetLastError());
@@ -436,8 +443,8 @@ int launch_moments_to_latent(const float* moments_nhwc, float* latent, float* me
 // ------------------------------------------------------------------------------------------
 // Layout conversions (tests, op-level entry points, fp32 path I/O): tiled transpose through
 // shared memory so both sides are coalesced.
-template <typename T>
-__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out,
+template <int OFMT>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, void* __restrict__ outv,
                                                            int C, long long HW) {
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
@@ -454,13 +461,15 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
         const long long p = p0 + r;
         const int c = c0 + tx;
         if (c < C && p < HW) {
-            if constexpr (sizeof(T) == 2) out[(1LL * n * HW + p) * C + c] = __float2bfloat16(tile[tx][r]);
-            else out[(1LL * n * HW + p) * C + c] = tile[tx][r];
+            const long long o = (1LL * n * HW + p) * C + c;
+            if constexpr (OFMT == FMT_BF16) static_cast<bf16*>(outv)[o] = __float2bfloat16(tile[tx][r]);
+            else if constexpr (OFMT == FMT_F16) static_cast<__half*>(outv)[o] = __float2half_rn(tile[tx][r]);
+            else static_cast<float*>(outv)[o] = tile[tx][r];
         }
     }
 }
-template <typename T>
-__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out,
+template <int IFMT>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const void* __restrict__ inv, float* __restrict__ out,
                                                            int C, long long HW) {
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
@@ -472,8 +481,10 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__
         const int c = c0 + tx;
         float v = 0.f;
         if (c < C && p < HW) {
-            if constexpr (sizeof(T) == 2) v = __bfloat162float(in[(1LL * n * HW + p) * C + c]);
-            else v = in[(1LL * n * HW + p) * C + c];
+            const long long o = (1LL * n * HW + p) * C + c;
+            if constexpr (IFMT == FMT_BF16) v = __bfloat162float(static_cast<const bf16*>(inv)[o]);
+            else if constexpr (IFMT == FMT_F16) v = __half2float(static_cast<const __half*>(inv)[o]);
+            else v = static_cast<const float*>(inv)[o];
         }
         tile[r][tx] = v;
     }
@@ -485,22 +496,25 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__
     }
 }
 
-int launch_nchw_to_nhwc(const float* in, void* out, int out_fp32, int N, int C, long long HW, cudaStream_t s) {
+int launch_nchw_to_nhwc(const float* in, void* out, int out_fmt, int N, int C, long long HW, cudaStream_t s) {
     dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N);
-    if (out_fp32) nchw_to_nhwc_kernel<float><<<grid, 256, 0, s>>>(in, static_cast<float*>(out), C, HW);
-    else nchw_to_nhwc_kernel<bf16><<<grid, 256, 0, s>>>(in, static_cast<bf16*>(out), C, HW);
+    if (out_fmt == FMT_F32) nchw_to_nhwc_kernel<FMT_F32><<<grid, 256, 0, s>>>(in, out, C, HW);
+    else if (out_fmt == FMT_F16) nchw_to_nhwc_kernel<FMT_F16><<<grid, 256, 0, s>>>(in, out, C, HW);
+    else nchw_to_nhwc_kernel<FMT_BF16><<<grid, 256, 0, s>>>(in, out, C, HW);
     VT_CUDA(cudaGetLastError());
     return 0;
 }
-int launch_nhwc_to_nchw(const void* in, int in_fp32, float* out, int N, int C, long long HW, cudaStream_t s) {
+int launch_nhwc_to_nchw(const void* in, int in_fmt, float* out, int N, int C, long long HW, cudaStream_t s) {
     dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N);
-    if (in_fp32) nhwc_to_nchw_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(in), out, C, HW);
-    else nhwc_to_nchw_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(in), out, C, HW);
+    if (in_fmt == FMT_F32) nhwc_to_nchw_kernel<FMT_F32><<<grid, 256, 0, s>>>(in, out, C, HW);
+    else if (in_fmt == FMT_F16) nhwc_to_nchw_kernel<FMT_F16><<<grid, 256, 0, s>>>(in, out, C, HW);
+    else nhwc_to_nchw_kernel<FMT_BF16><<<grid, 256, 0, s>>>(in, out, C, HW);
     VT_CUDA(cudaGetLastError());
     return 0;
 }
 
-// Split-K combine: out[r][c] = bias[c] + sum_s part[s][r][c]  (part fp32, out bf16; 4 columns / thread)
+// Split-K combine: out[r][c] = bias[c] + sum_s part[s][r][c]  (part fp32, out 16-bit; 4 columns / thread)
+template <int OFMT>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits,
                                                             long long split_stride, const float* __restrict__ bias,
                                                             bf16* __restrict__ out, long long rows, int cols,
@@ -514,30 +528,37 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
             const float4 v = *reinterpret_cast<const float4*>(part + s * split_stride + r * cols + c);
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
-        *reinterpret_cast<uint2*>(out + r * ld_out + c) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+        *reinterpret_cast<uint2*>(out + r * ld_out + c) = make_uint2(pack16x2<OFMT>(a.x, a.y), pack16x2<OFMT>(a.z, a.w));
     }
 }
-int launch_splitk_reduce(const float* part, int splits, long long split_stride, const float* bias, bf16* out,
-                         long long rows, int cols, long long ld_out, cudaStream_t s, Profiler* prof) {
-    VT_CHECK(cols % 4 == 0, "split-K combine needs a column count divisible by 4");
+int launch_splitk_reduce(const float* part, int splits, long long split_stride, const float* bias, void* out,
+                         int out_fmt, long long rows, int cols, long long ld_out, cudaStream_t s, Profiler* prof) {
+    VT_CHECK(cols % 4 == 0 && out_fmt != FMT_F32, "split-K combine needs a column count divisible by 4 and a 16-bit output");
     const long long total = rows * (cols / 4);
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 1LL * sm_count() * 8));
     profiler_begin(prof, KC_MISC, s, 0, 4.0 * splits * rows * cols + 2.0 * rows * cols);
-    splitk_reduce_kernel<<<grid, 256, 0, s>>>(part, splits, split_stride, bias, out, rows, cols, ld_out);
+    if (out_fmt == FMT_F16)
+        splitk_reduce_kernel<FMT_F16><<<grid, 256, 0, s>>>(part, splits, split_stride, bias, static_cast<bf16*>(out), rows, cols, ld_out);
+    else
+        splitk_reduce_kernel<FMT_BF16><<<grid, 256, 0, s>>>(part, splits, split_stride, bias, static_cast<bf16*>(out), rows, cols, ld_out);
     profiler_end(prof, KC_MISC, s);
     VT_CUDA(cudaGetLastError());
     return 0;
 }
 
-// fp32 -> bf16 (weights packing) with an arbitrary gather done on the host side; plain cast here.
-__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
-                                                            long long n) {
-    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x)
-        out[i] = __float2bfloat16(in[i]);
+// fp32 -> 16-bit cast (weights / test operands)
+template <int OFMT>
+__global__ void __launch_bounds__(256) cast_f32_16_kernel(const float* __restrict__ in, void* __restrict__ out,
+                                                          long long n) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+        if constexpr (OFMT == FMT_F16) static_cast<__half*>(out)[i] = __float2half_rn(fminf(fmaxf(in[i], -65504.f), 65504.f));
+        else static_cast<bf16*>(out)[i] = __float2bfloat16(in[i]);
+    }
 }
-int launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
+int launch_cast_f32_16(const float* in, void* out, int out_fmt, long long n, cudaStream_t s) {
     const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 1LL * sm_count() * 8));
-    cast_f32_bf16_kernel<<<grid, 256, 0, s>>>(in, out, n);
+    if (out_fmt == FMT_F16) cast_f32_16_kernel<FMT_F16><<<grid, 256, 0, s>>>(in, out, n);
+    else cast_f32_16_kernel<FMT_BF16><<<grid, 256, 0, s>>>(in, out, n);
     VT_CUDA(cudaGetLastError());
     return 0;
 }

@@ -144,8 +144,9 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     P.n_total = op.Cout;
     P.n_blocks = (op.Cout + block_n - 1) / block_n;
     P.a_batched = 1; P.b_batched = 0;
-    P.out_fp32 = op.out_fp32;
+    P.out_fmt = op.out_fmt;
     P.group_size = op.stats ? op.Cout / 32 : 0;
+    VT_CHECK(op.out_fmt != 2 || (op.residual == nullptr && op.stats == nullptr), "fp16 output has no residual / statistics epilogue");
     VT_CHECK(op.stats == nullptr || (op.Cout % 32 == 0 && (P.group_size == 4 || P.group_size == 8 || P.group_size == 16)),
              "fused GroupNorm statistics need 4, 8 or 16 channels per group");
     P.alpha = op.alpha;
@@ -162,12 +163,14 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
             else { s.c_base = (kw & 1) * op.Cin; s.dx = kw >> 1; s.p = kh & 1; s.dy = kh >> 1; }
             s.kb_base = ns * op.Cin;
             s.nchunks = op.Cin / 64;
+            s.f16 = op.in_f16;
             ++ns;
         }
     if (op.sc_in) {
         IgemmSlab& s = P.slabs[ns];
         s.map = 1; s.c_base = 0; s.dx = 0; s.p = 0; s.dy = 0;
         s.kb_base = taps * op.Cin; s.nchunks = op.Cs / 64;
+        s.f16 = 0;  // the shortcut operand is a raw activation: bf16, and so are its weight columns
         ++ns;
     }
     P.num_slabs = ns;
@@ -209,15 +212,16 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     P.n_total = op.N;
     P.n_blocks = (op.N + block_n - 1) / block_n;
     P.a_batched = op.a_batched; P.b_batched = op.b_batched;
-    P.out_fp32 = op.out_fp32;
+    P.out_fmt = op.out_fmt;
     P.group_size = op.stats ? op.N / 32 : 0;
+    VT_CHECK(op.out_fmt != 2 || (op.residual == nullptr && op.stats == nullptr), "fp16 output has no residual / statistics epilogue");
     VT_CHECK(op.stats == nullptr || (P.group_size == 4 || P.group_size == 8 || P.group_size == 16),
              "fused GroupNorm statistics need 4, 8 or 16 channels per group");
     P.alpha = op.alpha;
     P.bias = op.bias; P.residual = op.residual; P.res_fp32 = op.residual_fp32; P.out = op.out; P.ld_out = ldo;
     P.out_bstride = op.out_bstride ? op.out_bstride : 1LL * op.M * ldo; P.stats = op.stats;
     P.num_slabs = 1;
-    P.slabs[0] = IgemmSlab{0, 0, 0, 0, 0, 0, op.K / 64, 0};
+    P.slabs[0] = IgemmSlab{0, 0, 0, 0, 0, 0, op.K / 64, op.ab_f16};
 
     CUtensorMap a, b;
     {
@@ -238,7 +242,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     // the epilogue addresses out as ((img*H + y)*W + x)*ld_out: batch stride is M*ld_out
     const double flops = 2.0 * op.batch * static_cast<double>(op.M) * op.N * op.K;
     const double bytes = 2.0 * op.batch * (1.0 * op.M * op.K + 1.0 * op.N * op.K) +
-                         (op.out_fp32 ? 4.0 : 2.0) * op.batch * op.M * op.N;
+                         (op.out_fmt == 1 ? 4.0 : 2.0) * op.batch * op.M * op.N;
     profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
     int rc = dispatch(block_n, a, a, b, P, stream);
     profiler_end(prof, KC_IGEMM, stream);

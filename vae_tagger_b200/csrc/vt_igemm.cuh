@@ -36,7 +36,7 @@ struct IgemmSlab {
     int dy;       // added to the tile's y origin (A coordinate 3)
     int kb_base;  // B coordinate 0 of the slab's first chunk
     int nchunks;  // number of 64-wide K chunks in this slab
-    int pad_;
+    int f16;      // operand format of this slab (A and B): 1 = fp16, 0 = bf16
 };
 
 struct IgemmParams {
@@ -50,7 +50,7 @@ struct IgemmParams {
     int num_slabs;
     int a_batched;         // A coordinate 4 = image index (0: shared operand)
     int b_batched;         // B coordinate 2 = image index (0: shared operand)
-    int out_fp32;          // output element type: 0 bf16, 1 fp32
+    int out_fmt;           // output element type: FMT_BF16 / FMT_F32 / FMT_F16
     int res_fp32;          // residual element type: 0 bf16, 1 fp32
     int group_size;        // channels per GroupNorm group for the fused statistics; 0 = off
     int row_jump;          // element offset between accumulator rows r and r+16 of a sub-tile (see epilogue)
@@ -102,7 +102,7 @@ struct IgemmCfg {
 // GroupNorm accumulators are per-warp slots (no shared-memory atomics): the first two versions of this
 // epilogue spent ~1000 issue slots per 32x32 chunk on branches, 64-bit address arithmetic and
 // compare-and-swap loops and were the limiter of every layer with few K chunks per tile.
-template <int BLOCK_N, int MT, bool OUT_F32, int RES, bool STATS>
+template <int BLOCK_N, int MT, int OUT, int RES, bool STATS>
 __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* staging_all, uint8_t* ctrl,
                                                uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
                                                uint32_t total_tiles, int warp, int lane) {
@@ -110,7 +110,8 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
     constexpr int EPI_WARPS = Cfg::EPI_WARPS;
     constexpr int RF = Cfg::STAGE_ROW_FLOATS;
     constexpr int SLOTS = Cfg::COLS_PER_WARP / 4;  // 4-column statistic slots per warp
-    typedef typename std::conditional<OUT_F32, float, __nv_bfloat16>::type OutT;
+    constexpr bool OUT_F32 = (OUT == FMT_F32);
+    typedef typename std::conditional<OUT_F32, float, __nv_bfloat16>::type OutT;  // 2-byte outputs share the pointer type
 
     const int ew = warp - 2;            // 0 .. EPI_WARPS-1
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
@@ -299,8 +300,8 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
                                 reinterpret_cast<float4*>(o)[1] = v1;
                             }
                         } else {
-                            const uint4 pk = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w),
-                                                        pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+                            const uint4 pk = make_uint4(pack16x2<OUT>(v0.x, v0.y), pack16x2<OUT>(v0.z, v0.w),
+                                                        pack16x2<OUT>(v1.x, v1.y), pack16x2<OUT>(v1.z, v1.w));
                             if (ok) *reinterpret_cast<uint4*>(o) = pk;
                         }
                     }
@@ -431,11 +432,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(IGEMM_BLOCK_M, BLOCK_N);
+            constexpr uint32_t idesc_bf16 = umma_idesc_16(IGEMM_BLOCK_M, BLOCK_N, false);
+            constexpr uint32_t idesc_f16 = umma_idesc_16(IGEMM_BLOCK_M, BLOCK_N, true);
             int stage = 0;
             uint32_t phase = 0;
-            int kblocks = 0;
-            for (int s = 0; s < P.num_slabs; ++s) kblocks += P.slabs[s].nchunks;
             uint32_t it = 0;
             for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1;
@@ -443,22 +443,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint64_t db = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+                uint32_t first = 0;  // 0 until the first MMA of the tile has been issued
+                for (int sl = 0; sl < P.num_slabs; ++sl) {
+                    const uint32_t idesc = P.slabs[sl].f16 ? idesc_f16 : idesc_bf16;
+                    const int nch = P.slabs[sl].nchunks;
+                    for (int kb = 0; kb < nch; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                        const uint64_t db = umma_desc_k_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < IGEMM_BLOCK_K / 16; ++k) {
+                        for (int k = 0; k < IGEMM_BLOCK_K / 16; ++k) {
 #pragma unroll
-                        for (int t = 0; t < MT; ++t) {
-                            // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
-                            const uint64_t da = umma_desc_k_sw128(sa + t * IGEMM_A_BYTES);
-                            umma_bf16_ss(tmem_d + t * BLOCK_N, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            for (int t = 0; t < MT; ++t) {
+                                // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
+                                const uint64_t da = umma_desc_k_sw128(sa + t * IGEMM_A_BYTES);
+                                umma_bf16_ss(tmem_d + t * BLOCK_N, da + 2 * k, db + 2 * k, idesc, first | k);
+                            }
                         }
+                        first = 1;
+                        umma_commit(&empty_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);
             }
@@ -467,14 +473,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     } else {
         // ------------------------------------------------------------ epilogue warps
         const int res = P.residual == nullptr ? 0 : (P.res_fp32 ? 2 : 1);
-        const int mode = (P.out_fp32 ? 1 : 0) | (res << 1) | (P.group_size != 0 ? 8 : 0);
+        const int mode = P.out_fmt | (res << 2) | (P.group_size != 0 ? 16 : 0);
 #define VT_EPI_CASE(O, R, S)                                                                                  \
-    case ((O) | ((R) << 1) | ((S) << 3)):                                                                     \
-        igemm_epilogue<BLOCK_N, MT, (O) != 0, (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar,     \
-                                                              tmem_base, total_tiles, warp, lane);            \
+    case ((O) | ((R) << 2) | ((S) << 4)):                                                                     \
+        igemm_epilogue<BLOCK_N, MT, (O), (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base, \
+                                                         total_tiles, warp, lane);                            \
         break;
         switch (mode) {
-            VT_EPI_CASE(0, 0, 0) VT_EPI_CASE(1, 0, 0) VT_EPI_CASE(0, 1, 0) VT_EPI_CASE(1, 1, 0)
+            VT_EPI_CASE(0, 0, 0) VT_EPI_CASE(1, 0, 0) VT_EPI_CASE(2, 0, 0) VT_EPI_CASE(0, 1, 0) VT_EPI_CASE(1, 1, 0)
             VT_EPI_CASE(0, 2, 0) VT_EPI_CASE(1, 2, 0) VT_EPI_CASE(0, 0, 1) VT_EPI_CASE(1, 0, 1)
             VT_EPI_CASE(0, 1, 1) VT_EPI_CASE(1, 1, 1) VT_EPI_CASE(0, 2, 1) VT_EPI_CASE(1, 2, 1)
             default: break;

@@ -61,7 +61,8 @@ int profiler_read(Profiler*, double* out, int reset);
 // ---- tcgen05 implicit GEMM (vt_igemm.cu)
 struct ConvOp {
     // input activation, NHWC bf16
-    const void* in = nullptr;  // bf16 (tcgen05 path) or fp32 (launch_conv_fp32)
+    const void* in = nullptr;  // 16-bit (tcgen05 path) or fp32 (launch_conv_fp32)
+    int in_f16 = 0;            // tcgen05 path: main operand + its weight columns are fp16 (else bf16)
     int N = 0, Hin = 0, Win = 0, Cin = 0;
     int ksize = 3;   // 1 or 3
     int stride = 1;  // 1 (pad 1 for 3x3) or 2 (pad right/bottom by 1, diffusers Downsample2D)
@@ -74,8 +75,8 @@ struct ConvOp {
     const float* bias = nullptr;     // [Cout]
     const void* residual = nullptr;  // [N][Hout][Wout][Cout]
     int residual_fp32 = 0;           // residual element type (tcgen05 path; the fp32 path is all fp32)
-    void* out = nullptr;             // [N][Hout][Wout][Cout] bf16 or fp32
-    int out_fp32 = 0;
+    void* out = nullptr;             // [N][Hout][Wout][Cout]
+    int out_fmt = 0;                 // 0 bf16, 1 fp32, 2 fp16
     double* stats = nullptr;  // [N][32][2] GroupNorm (sum, sumsq) of the output (group = Cout/32 channels)
     float alpha = 1.f;
 };
@@ -94,7 +95,8 @@ struct GemmOp {
     const void* residual = nullptr;
     int residual_fp32 = 0;
     void* out = nullptr;
-    int out_fp32 = 0;
+    int out_fmt = 0;            // 0 bf16, 1 fp32, 2 fp16
+    int ab_f16 = 0;             // tcgen05 path: A and B are fp16 (else bf16)
     long long ld_out = 0;       // default N
     long long out_bstride = 0;  // default M * ld_out (also used for residual)
     double* stats = nullptr;    // [batch][32][2] over (m, group of N/32 columns)
@@ -103,23 +105,23 @@ struct GemmOp {
 int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof);
 
 // ---- HBM-bound kernels (vt_elementwise.cu)
-int launch_im2col3x3(const void* in, int fmt, void* out, int out_fp32, int N, int H, int W, cudaStream_t,
+int launch_im2col3x3(const void* in, int fmt, void* out, int out_fmt, int N, int H, int W, cudaStream_t,
                      Profiler*);
 int launch_gn_stats(const void* x, int is_fp32, double* stats, int N, long long HW, int C, int G, cudaStream_t,
                     Profiler*);
-int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fp32, const double* stats, const float* gamma,
+int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fmt, const double* stats, const float* gamma,
                     const float* beta, int N, long long HW, int C, int G, float eps, int silu, cudaStream_t,
                     Profiler*);
-int launch_softmax_rows(const float* s, void* p, int p_fp32, long long rows, int cols, long long ld_s,
+int launch_softmax_rows(const float* s, void* p, int p_fmt, long long rows, int cols, long long ld_s,
                         long long ld_p, cudaStream_t, Profiler*);
 int launch_moments_to_latent(const float* moments_nhwc, float* latent, float* mean_out, float* logvar_out,
                              const float* noise, int N, int H, int W, int LC, int sample, unsigned long long seed,
                              float scale, float shift, int apply_scale, int apply_shift, cudaStream_t, Profiler*);
-int launch_nchw_to_nhwc(const float* in, void* out, int out_fp32, int N, int C, long long HW, cudaStream_t);
-int launch_nhwc_to_nchw(const void* in, int in_fp32, float* out, int N, int C, long long HW, cudaStream_t);
-int launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t);
-int launch_splitk_reduce(const float* part, int splits, long long split_stride, const float* bias, bf16* out,
-                         long long rows, int cols, long long ld_out, cudaStream_t, Profiler*);
+int launch_nchw_to_nhwc(const float* in, void* out, int out_fmt, int N, int C, long long HW, cudaStream_t);
+int launch_nhwc_to_nchw(const void* in, int in_fmt, float* out, int N, int C, long long HW, cudaStream_t);
+int launch_cast_f32_16(const float* in, void* out, int out_fmt, long long n, cudaStream_t);
+int launch_splitk_reduce(const float* part, int splits, long long split_stride, const float* bias, void* out,
+                         int out_fmt, long long rows, int cols, long long ld_out, cudaStream_t, Profiler*);
 
 // ---- fp32 verification mode (vt_fp32.cu): FFMA implicit GEMM, NHWC fp32, same operand packing
 int launch_conv_fp32(const ConvOp& op, cudaStream_t, Profiler*);

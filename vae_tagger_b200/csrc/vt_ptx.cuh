@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -120,14 +121,16 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr, uint32
     return d;
 }
 
-// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4)                              // D format  = F32
-           | (1u << 7)                            // A format  = BF16
-           | (1u << 10)                           // B format  = BF16
+// Instruction descriptor, kind::f16: 16-bit x 16-bit -> fp32, both operands K-major.
+// Operand format field: 0 = F16, 1 = BF16 (A at bits [7,10), B at bits [10,13)).
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, bool f16) {
+    return (1u << 4)                                // D format  = F32
+           | ((f16 ? 0u : 1u) << 7)                 // A format
+           | ((f16 ? 0u : 1u) << 10)                // B format
            | (static_cast<uint32_t>(N >> 3) << 17)  // N >> 3
            | (static_cast<uint32_t>(M >> 4) << 24); // M >> 4
 }
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) { return umma_idesc_16(M, N, false); }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -178,6 +181,26 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+// fp16 pack with saturation to the finite range (normalised operands are bounded; this is a guard)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// 16-bit storage formats used by the kernels: 0 = bf16 (raw activations), 2 = fp16 (bounded MMA operands)
+enum { FMT_BF16 = 0, FMT_F32 = 1, FMT_F16 = 2 };
+template <int FMT>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+    if constexpr (FMT == FMT_F16) return pack_f16x2(lo, hi);
+    else return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float f16_lo(uint32_t v) {
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFFu)));
+}
+__device__ __forceinline__ float f16_hi(uint32_t v) {
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16)));
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
