@@ -164,6 +164,12 @@ int vt_op_conv2d(vt_ctx* ctx, const float* x /*[N,Cin,H,W]*/, const float* w /*[
                  const float* sc_x /*[N,Cs,Ho,Wo] or NULL*/, const float* sc_w /*[Cout,Cs,1,1] or NULL*/, int N,
                  int Cin, int H, int W, int Cout, int ksize, int stride, int Cs, int precision,
                  float* out /*[N,Cout,Ho,Wo]*/, double* stats /*[N,32,2] (sum,sumsq) or NULL*/, void* stream);
+/* conv3x3(silu(group_norm_32(x))) + bias (+ residual) with the normalisation fused into the operand path;
+ * x and residual are rounded to bf16 (raw storage format), weights and the normalised operand to fp16 */
+int vt_op_conv3_fused(vt_ctx* ctx, const float* x /*[N,Cin,H,W]*/, const float* gamma, const float* beta,
+                      const float* w /*[Cout,Cin,3,3]*/, const float* bias, const float* residual /*or NULL*/, int N,
+                      int Cin, int H, int W, int Cout, float eps, int silu, float* out /*[N,Cout,H,W]*/,
+                      double* stats /*[N,32,2] of out, or NULL*/, void* stream);
 int vt_op_gemm_nt(vt_ctx* ctx, const float* A /*[batch,M,K]*/, const float* B /*[batch or 1,N,K]*/,
                   const float* bias, int batch, int M, int N, int K, int b_batched, float alpha, int precision,
                   float* out /*[batch,M,N]*/, void* stream);

@@ -146,3 +146,42 @@ def test_softmax_rows(ctx, rows, cols, prec):
     ref = torch.softmax(s, dim=-1)
     tol = {N.PREC_BF16: 4e-3, N.PREC_F16: 5e-4, N.PREC_FP32: 2e-6}[prec]
     assert rel(out, ref) < tol, rel(out, ref)
+
+
+FUSED_CASES = [
+    # N, Cin, H, W, Cout, residual
+    (1, 128, 16, 16, 128, False),
+    (2, 128, 40, 24, 128, True),
+    (1, 128, 64, 64, 128, True),
+    (1, 256, 16, 32, 256, False),
+    (2, 512, 8, 8, 512, True),
+    (1, 128, 32, 16, 256, False),
+    (1, 512, 72, 24, 512, True),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_conv3_fused_groupnorm_silu(ctx, case):
+    """conv3x3(silu(GroupNorm32(x))) with the normalisation fused into the operand path (halo tile, nine
+    shifted descriptor views).  Reference: x rounded to bf16 (raw storage), GroupNorm+SiLU in fp32, result
+    rounded to fp16 (operand), fp16 weights, fp32 accumulation, bf16 residual."""
+    n, cin, h, w_, cout, use_res = case
+    g = torch.Generator().manual_seed(sum(case[:5]))
+    x = torch.randn(n, cin, h, w_, generator=g) * 1.7 + 0.4
+    gamma = torch.randn(cin, generator=g) * 0.5 + 1.0
+    beta = torch.randn(cin, generator=g) * 0.3
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(n, cout, h, w_, generator=g) if use_res else None
+    out, stats = ctx.op_conv3_fused(x, gamma, beta, w, b, res, want_stats=True)
+    out = out.cpu()
+    t = F.silu(F.group_norm(r16(x), 32, gamma, beta, eps=1e-6))
+    ref = F.conv2d(rh(t), rh(w), b, padding=1)
+    if use_res:
+        ref = ref + r16(res)
+    # the kernel's sigmoid uses ex2.approx / rcp.approx: operand values can differ by one fp16 ulp
+    assert rel(out, ref) < 3e-4, (rel(out, ref), (out - ref).abs().max().item())
+    grp = ref.double().reshape(n, 32, -1)
+    want = torch.stack([grp.sum(-1), (grp * grp).sum(-1)], dim=-1)
+    got = stats.cpu()
+    assert torch.allclose(got, want, rtol=2e-3, atol=2e-3 * grp.shape[-1] ** 0.5), (got - want).abs().max().item()

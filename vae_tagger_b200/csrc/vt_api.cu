@@ -297,6 +297,7 @@ struct EncRun {
     double* stats_base;
     int stats_used = 0;
     int groups;
+    int use_fused = 1;  // GroupNorm+SiLU fused into the 3x3 convs (VT_B200_NO_FUSED_GN=1 disables)
 
     double* new_stats() {
         double* p = stats_base + static_cast<size_t>(stats_used) * n * groups * 2;
@@ -342,13 +343,32 @@ struct EncRun {
         return launch_gn_apply(x.p, x.fmt == FMT_F32, y, opd_fmt(), st, nw.gamma, nw.beta, n, HW, C, groups, 1e-6f, silu,
                                s, c->prof);
     }
+    int conv_fused(Act x, const double* st_x, const NormW& nw, int H, int Wd, const ConvW& w, const Act* residual,
+                   Act out, double* st) {
+        Conv3FusedOp op;
+        op.in = x.p; op.N = n; op.H = H; op.W = Wd; op.Cin = w.Cin; op.Cout = w.Cout; op.gn_stats = st_x;
+        op.gamma = nw.gamma; op.beta = nw.beta; op.w = w.w16; op.bias = w.bias;
+        if (residual) { op.residual = residual->p; op.residual_fp32 = residual->fmt == FMT_F32; }
+        op.out = out.p; op.out_fmt = out.fmt; op.stats = st;
+        return launch_conv3_fused(op, s, c->prof);
+    }
     // ResnetBlock2D: out = x (+shortcut) + conv2(silu(norm2(conv1(silu(norm1(x))))))
+    // 16-bit mode: both GroupNorm+SiLU steps are fused into the operand path of the following 3x3 conv
+    // (vt_conv3.cuh); only the conv2 of a channel-changing block keeps the separate GroupNorm pass because
+    // its 1x1 shortcut is an extra K slab of the generic implicit-GEMM kernel.
     int resnet(const ResnetW& r, Act x, const double* st_x, int H, int Wd, int level, void* T, void* Hb, Act out,
                double* st_out) {
+        (void)level;
         const long long HW = 1LL * H * Wd;
-        VT_TRY(gn(x, T, st_x, r.norm1, HW, r.cin, 1));
         double* st_h = new_stats();
         Act h{Hb, raw_fmt()};
+        if (!fp32 && use_fused) {
+            VT_TRY(conv_fused(x, st_x, r.norm1, H, Wd, r.conv1, nullptr, h, st_h));
+            if (r.cin == r.cout) return conv_fused(h, st_h, r.norm2, H, Wd, r.conv2, &x, out, st_out);
+            VT_TRY(gn(h, T, st_h, r.norm2, HW, r.cout, 1));
+            return conv(T, H, Wd, r.conv2, 1, x.p, nullptr, out, st_out);
+        }
+        VT_TRY(gn(x, T, st_x, r.norm1, HW, r.cin, 1));
         VT_TRY(conv(T, H, Wd, r.conv1, 1, nullptr, nullptr, h, st_h));
         VT_TRY(gn(h, T, st_h, r.norm2, HW, r.cout, 1));
         if (r.cin != r.cout) {
@@ -423,6 +443,10 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
     VT_TRY(L.mom.ensure(static_cast<size_t>(n) * tokens * 2 * LC * sizeof(float)));
 
     EncRun R{c, s, fp32, n, static_cast<double*>(L.stats.p), 0, groups};
+    {
+        const char* e = getenv("VT_B200_NO_FUSED_GN");
+        R.use_fused = !(e && e[0] == '1');
+    }
 
     // ---- conv_in: gather the 3x3x3 patches (K = 27 padded to 64) then one K chunk of contraction
     const char* img = static_cast<const char*>(a->images);
@@ -1021,6 +1045,37 @@ int vt_op_conv2d(vt_ctx* c, const float* x, const float* w, const float* bias, c
         VT_TRY(launch_conv(op, s, c->prof));
     }
     return launch_nhwc_to_nchw(dout, FMT_F32, out, N, Cout, 1LL * Ho * Wo, s);
+}
+
+int vt_op_conv3_fused(vt_ctx* c, const float* x, const float* gamma, const float* beta, const float* w,
+                      const float* bias, const float* residual, int N, int Cin, int H, int W, int Cout, float eps,
+                      int silu, float* out, double* stats, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(x && gamma && beta && w && out, "null pointers");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long HW = 1LL * H * W;
+    const size_t b_x = align_up(static_cast<size_t>(N) * HW * Cin * 2, 1024);
+    const size_t b_o = align_up(static_cast<size_t>(N) * HW * Cout * 4, 1024);
+    const size_t b_r = align_up(static_cast<size_t>(N) * HW * Cout * 2, 1024);
+    const size_t b_w = align_up(static_cast<size_t>(Cout) * 9 * Cin * 2, 1024);
+    const size_t b_s = 1024 + static_cast<size_t>(N) * 64 * sizeof(double);
+    VT_TRY(c->opws.ensure(b_x + b_o + b_r + b_w + b_s));
+    char* p = static_cast<char*>(c->opws.p);
+    void* dx = p; void* dout = p + b_x; void* dres = p + b_x + b_o; void* dw = p + b_x + b_o + b_r;
+    double* st_in = reinterpret_cast<double*>(p + b_x + b_o + b_r + b_w);
+    VT_TRY(launch_nchw_to_nhwc(x, dx, FMT_BF16, N, Cin, HW, s));
+    if (residual) VT_TRY(launch_nchw_to_nhwc(residual, dres, FMT_BF16, N, Cout, HW, s));
+    pack_weight_kernel<FMT_F16><<<256, 256, 0, s>>>(w, dw, Cout, Cin, 3, 9 * Cin, 0);
+    VT_CUDA(cudaGetLastError());
+    VT_CUDA(cudaMemsetAsync(st_in, 0, static_cast<size_t>(N) * 64 * sizeof(double), s));
+    VT_TRY(launch_gn_stats(dx, 0, st_in, N, HW, Cin, 32, s, c->prof));
+    if (stats) VT_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * N * 64, s));
+    Conv3FusedOp op;
+    op.in = dx; op.N = N; op.H = H; op.W = W; op.Cin = Cin; op.Cout = Cout; op.gn_stats = st_in; op.gamma = gamma;
+    op.beta = beta; op.eps = eps; op.silu = silu; op.w = dw; op.bias = bias; op.residual = residual ? dres : nullptr;
+    op.out = dout; op.out_fmt = FMT_F32; op.stats = stats;
+    VT_TRY(launch_conv3_fused(op, s, c->prof));
+    return launch_nhwc_to_nchw(dout, FMT_F32, out, N, Cout, HW, s);
 }
 
 int vt_op_gemm_nt(vt_ctx* c, const float* A, const float* B, const float* bias, int batch, int M, int N, int K,

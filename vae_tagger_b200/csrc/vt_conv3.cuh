@@ -1,0 +1,295 @@
+// 3x3 stride-1 convolution with GroupNorm(32)+SiLU fused into the operand path ("halo" kernel).
+//
+//   out = conv3x3( silu( gn(x) ) ) + bias (+ residual),   GroupNorm statistics of `out` in the epilogue
+//
+// What differs from igemm_kernel:
+//   * the A operand of a CTA tile is loaded ONCE per 64-channel chunk as a halo tile
+//     ((8*MT+2) x 18 pixels x 64 channels, one 5-D TMA box, out-of-bounds = zero) and the nine taps
+//     are nine tcgen05 descriptors that point into that tile at a row offset (dy*HWID + dx): with the
+//     128-byte swizzle being a function of the shared-memory address only (checked on hardware with
+//     tools/umma_probe.cu) a K-major operand may start at any 128-byte row and use any 8-row-group
+//     pitch (here HWID*128 bytes).  L2->SM traffic for A drops 9x -> 1.27x.
+//   * four "transform" warps rewrite each halo tile in place before the MMAs read it:
+//     raw bf16 x -> fp32 -> *scale_c + shift_c -> SiLU -> fp16 (scale/shift from the producer's
+//     (sum, sumsq) statistics, per image), and pixels outside the image are forced to zero (the
+//     reference pads AFTER GroupNorm+SiLU).  The separate GroupNorm pass over HBM disappears.
+// Accumulators, epilogue, tile scheduler and weight (B) pipeline are those of igemm_kernel.
+#pragma once
+#include "vt_igemm.cuh"
+
+namespace vt {
+
+template <int BLOCK_N, int MT>
+struct Conv3Cfg {
+    static constexpr int kBlockN = BLOCK_N, kMT = MT;
+    static constexpr int HWID = 8 * MT + 2;           // halo width in pixels
+    static constexpr int HHGT = 18;                   // halo height (16 + 2)
+    static constexpr int HROWS = HWID * HHGT;         // 128-byte rows per halo chunk
+    static constexpr int HALO_BYTES = (HROWS * 128 + 1023) / 1024 * 1024;
+    static constexpr int NHALO = 3;
+    static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;
+    static constexpr int BSTAGES = 4;
+    static constexpr int EPI_WARPS = 4;
+    static constexpr int XF_WARPS = 4;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
+    static constexpr int COLS_PER_WARP = BLOCK_N;
+    static constexpr int PASSES_PER_SUB = COLS_PER_WARP / 32;
+    static constexpr int PASSES = MT * PASSES_PER_SUB;
+    static constexpr int STAGE_ROW_FLOATS = 36;
+    static constexpr int EPI_STAGING_BYTES = EPI_WARPS * 32 * STAGE_ROW_FLOATS * 4;
+    static constexpr int ACC_COLS = MT * BLOCK_N;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int PART_FLOATS = 2 * EPI_WARPS * (COLS_PER_WARP / 4) * 2;
+    static constexpr int SCSH_BYTES = 2 * 512 * 4;     // scale / shift tables, up to 512 input channels
+    static constexpr int BAR_BYTES = 256 + 1024 + PART_FLOATS * 4;
+    static constexpr int SMEM_BYTES =
+        NHALO * HALO_BYTES + BSTAGES * B_BYTES + EPI_STAGING_BYTES + SCSH_BYTES + BAR_BYTES + 1024;
+    static_assert(2 * ACC_COLS <= 512, "two accumulator sets must fit TMEM");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int BLOCK_N, int MT>
+__global__ void __launch_bounds__(Conv3Cfg<BLOCK_N, MT>::THREADS, 1)
+conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ IgemmParams P) {
+    using Cfg = Conv3Cfg<BLOCK_N, MT>;
+    constexpr int NHALO = Cfg::NHALO, BST = Cfg::BSTAGES, HWID = Cfg::HWID, HROWS = Cfg::HROWS;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_halo = smem;                                   // [NHALO][HALO_BYTES]
+    uint8_t* s_b = smem + NHALO * Cfg::HALO_BYTES;            // [BST][B_BYTES]
+    float* staging_all = reinterpret_cast<float*>(s_b + BST * Cfg::B_BYTES);
+    float* s_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(staging_all) + Cfg::EPI_STAGING_BYTES);
+    float* s_sh = s_sc + 512;
+    uint8_t* ctrl = reinterpret_cast<uint8_t*>(s_sc) + Cfg::SCSH_BYTES;
+    uint64_t* halo_full = reinterpret_cast<uint64_t*>(ctrl);  // [NHALO] TMA landed (raw)
+    uint64_t* halo_ready = halo_full + NHALO;                 // [NHALO] transformed, MMA may read
+    uint64_t* halo_free = halo_ready + NHALO;                 // [NHALO] MMAs done, TMA may overwrite
+    uint64_t* b_full = halo_free + NHALO;                     // [BST]
+    uint64_t* b_empty = b_full + BST;                         // [BST]
+    uint64_t* tfull_bar = b_empty + BST;                      // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                     // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t tiles_per_img = static_cast<uint32_t>(P.tiles_x * P.tiles_y);
+    const uint32_t total_tiles = static_cast<uint32_t>(P.NB) * tiles_per_img * static_cast<uint32_t>(P.n_blocks);
+    const int nchunks = P.cin_chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < NHALO; ++i) {
+            mbar_init(&halo_full[i], 1);
+            mbar_init(&halo_ready[i], Cfg::XF_WARPS);
+            mbar_init(&halo_free[i], 1);
+        }
+        for (int i = 0; i < BST; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], Cfg::EPI_WARPS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto decode = [&](uint32_t tile, int& nb, int& x0, int& y0, int& img) {
+        nb = static_cast<int>(tile % static_cast<uint32_t>(P.n_blocks));
+        uint32_t m = tile / static_cast<uint32_t>(P.n_blocks);
+        const int tx = static_cast<int>(m % static_cast<uint32_t>(P.tiles_x));
+        m /= static_cast<uint32_t>(P.tiles_x);
+        const int ty = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
+        img = static_cast<int>(m / static_cast<uint32_t>(P.tiles_y));
+        x0 = tx * 8 * MT;
+        y0 = ty * 16;
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int hb = 0, bs = 0;
+            uint32_t hphase = 0, bphase = 0;
+            // the halo of item i+1 is requested before the nine weight tiles of item i
+            uint32_t h_tile = blockIdx.x;
+            int h_chunk = 0;
+            auto issue_halo = [&]() {
+                if (h_tile >= total_tiles) return;
+                int nb, x0, y0, img;
+                decode(h_tile, nb, x0, y0, img);
+                mbar_wait(&halo_free[hb], hphase ^ 1);
+                mbar_arrive_expect_tx(&halo_full[hb], HROWS * 128);
+                tma_load_5d(s_halo + hb * Cfg::HALO_BYTES, &tmA, &halo_full[hb], h_chunk * IGEMM_BLOCK_K, x0 - 1, 0, y0 - 1,
+                            img);
+                if (++hb == NHALO) { hb = 0; hphase ^= 1; }
+                if (++h_chunk == nchunks) { h_chunk = 0; h_tile += gridDim.x; }
+            };
+            issue_halo();
+            for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int nb, x0, y0, img;
+                decode(tile, nb, x0, y0, img);
+                const int n0 = nb * BLOCK_N;
+                for (int c = 0; c < nchunks; ++c) {
+                    issue_halo();
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&b_empty[bs], bphase ^ 1);
+                        mbar_arrive_expect_tx(&b_full[bs], Cfg::B_BYTES);
+                        tma_load_3d(s_b + bs * Cfg::B_BYTES, &tmB, &b_full[bs], tap * P.gn_C + c * IGEMM_BLOCK_K, n0, 0);
+                        if (++bs == BST) { bs = 0; bphase ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_16(IGEMM_BLOCK_M, BLOCK_N, true);  // fp16 x fp16
+            int hb = 0, bs = 0;
+            uint32_t hphase = 0, bphase = 0, it = 0;
+            for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
+                uint32_t first = 0;
+                for (int c = 0; c < nchunks; ++c) {
+                    mbar_wait(&halo_ready[hb], hphase);
+                    tc_fence_after();
+                    const uint32_t hbase = smem_u32(s_halo + hb * Cfg::HALO_BYTES);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3, dx = tap - dy * 3;
+                        mbar_wait(&b_full[bs], bphase);
+                        tc_fence_after();
+                        const uint64_t db = umma_desc_k_sw128(smem_u32(s_b + bs * Cfg::B_BYTES));
+#pragma unroll
+                        for (int k = 0; k < IGEMM_BLOCK_K / 16; ++k) {
+#pragma unroll
+                            for (int t = 0; t < MT; ++t) {
+                                // tap (dy, dx), sub-tile t: rows start at halo pixel (dy, dx + 8t); one 8-row
+                                // group per output row, HWID halo pixels apart
+                                const uint64_t da = umma_desc_k_sw128(hbase + (dy * HWID + dx + 8 * t) * 128, HWID * 128);
+                                umma_bf16_ss(tmem_d + t * BLOCK_N, da + 2 * k, db + 2 * k, idesc, first | k);
+                            }
+                        }
+                        first = 1;
+                        umma_commit(&b_empty[bs]);
+                        if (++bs == BST) { bs = 0; bphase ^= 1; }
+                    }
+                    umma_commit(&halo_free[hb]);
+                    if (++hb == NHALO) { hb = 0; hphase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < 2 + Cfg::EPI_WARPS) {
+        // ------------------------------------------------------------ epilogue warps (2..5)
+        const int res = P.residual == nullptr ? 0 : (P.res_fp32 ? 2 : 1);
+        const int mode = P.out_fmt | (res << 2) | (P.group_size != 0 ? 16 : 0);
+#define VT_EPI_CASE(O, R, S)                                                                                  \
+    case ((O) | ((R) << 2) | ((S) << 4)):                                                                     \
+        igemm_epilogue<Cfg, (O), (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base,         \
+                                                 total_tiles, warp, lane);                                    \
+        break;
+        switch (mode) {
+            VT_EPI_CASE(0, 0, 0) VT_EPI_CASE(1, 0, 0) VT_EPI_CASE(0, 1, 0) VT_EPI_CASE(0, 0, 1) VT_EPI_CASE(1, 0, 1)
+            VT_EPI_CASE(0, 1, 1) VT_EPI_CASE(0, 2, 1) VT_EPI_CASE(1, 2, 1)
+            default: break;
+        }
+#undef VT_EPI_CASE
+    } else {
+        // ------------------------------------------------------------ transform warps (6..9)
+        const int xt = threadIdx.x - (64 + 32 * Cfg::EPI_WARPS);  // 0..127
+        const int lc = xt & 7;        // logical 8-channel group of this thread (fixed)
+        const int rbase = xt >> 3;    // first halo row of this thread; then +16 per step
+        int hb = 0;
+        uint32_t hphase = 0;
+        int cur_img = -1;
+        const double cnt = static_cast<double>(P.H) * P.W * P.gn_gs;
+        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int nb, x0, y0, img;
+            decode(tile, nb, x0, y0, img);
+            if (img != cur_img) {
+                // per-channel scale / shift of this image from the producer's (sum, sumsq)
+                asm volatile("bar.sync 2, %0;" ::"n"(32 * Cfg::XF_WARPS) : "memory");
+                for (int ch = xt; ch < P.gn_C; ch += 32 * Cfg::XF_WARPS) {
+                    const int g = ch / P.gn_gs;
+                    const double su = P.gn_stats[(static_cast<long long>(img) * 32 + g) * 2];
+                    const double sq = P.gn_stats[(static_cast<long long>(img) * 32 + g) * 2 + 1];
+                    const double mean = su / cnt;
+                    double var = sq / cnt - mean * mean;
+                    var = var > 0.0 ? var : 0.0;
+                    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(P.gn_eps)));
+                    const float ga = P.gn_gamma[ch], be = P.gn_beta[ch];
+                    s_sc[ch] = rstd * ga;
+                    s_sh[ch] = be - static_cast<float>(mean) * rstd * ga;
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(32 * Cfg::XF_WARPS) : "memory");
+                cur_img = img;
+            }
+            for (int c = 0; c < nchunks; ++c) {
+                float sc[8], sh[8];
+                {
+                    const float4 a0 = *reinterpret_cast<const float4*>(s_sc + c * 64 + lc * 8);
+                    const float4 a1 = *reinterpret_cast<const float4*>(s_sc + c * 64 + lc * 8 + 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(s_sh + c * 64 + lc * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(s_sh + c * 64 + lc * 8 + 4);
+                    sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+                    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+                }
+                mbar_wait(&halo_full[hb], hphase);
+                const uint32_t base = smem_u32(s_halo + hb * Cfg::HALO_BYTES);
+#pragma unroll 2
+                for (int row = rbase; row < HROWS; row += 16) {
+                    const int hy = row / HWID, hx = row - hy * HWID;
+                    const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+                    // physical 16-byte chunk of this thread's channel group in this row (128B swizzle)
+                    const uint32_t addr = base + row * 128 + ((lc ^ (row & 7)) << 4);
+                    uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+                    if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) {
+                        uint32_t u0, u1, u2, u3;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(addr) : "memory");
+                        float v[8] = {bf16_lo(u0), bf16_hi(u0), bf16_lo(u1), bf16_hi(u1),
+                                      bf16_lo(u2), bf16_hi(u2), bf16_lo(u3), bf16_hi(u3)};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float t = fmaf(v[e], sc[e], sh[e]);
+                            if (P.gn_silu) t = __fdividef(t, 1.0f + __expf(-t));
+                            v[e] = t;
+                        }
+                        o0 = pack_f16x2(v[0], v[1]); o1 = pack_f16x2(v[2], v[3]);
+                        o2 = pack_f16x2(v[4], v[5]); o3 = pack_f16x2(v[6], v[7]);
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+                }
+                // generic-proxy writes -> visible to the tensor core's async proxy, then signal the MMA warp
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&halo_ready[hb]);
+                if (++hb == NHALO) { hb = 0; hphase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace vt

@@ -4,6 +4,7 @@
 
 #include <mutex>
 
+#include "vt_conv3.cuh"
 #include "vt_igemm.cuh"
 #include "vt_internal.h"
 
@@ -137,7 +138,7 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     const int mt = pick_mt(block_n);
     P.tw = 16; P.th = 8; P.tw_log2 = 4;
     P.sub_dx = 0; P.sub_dy = 1;  // sub-tiles stacked vertically: one TMA box of th*mt rows
-    P.row_jump = Wout * op.Cout;   // accumulator row r+16 is the pixel one image row below (tw = 16)
+    P.ax1 = 8; P.ay1 = 0; P.ax2 = 0; P.ay2 = 1;  // 16x8 patch: row r+8 = 8 pixels right, r+16 = next image row
     VT_CHECK(1LL * Hout * Wout * op.Cout < (1LL << 31), "conv output of one image exceeds 2^31 elements");
     P.tiles_x = (Wout + P.tw - 1) / P.tw;
     P.tiles_y = (Hout + P.th * mt - 1) / (P.th * mt);
@@ -193,6 +194,72 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     return rc;
 }
 
+template <int BLOCK_N, int MT>
+static int launch_conv3_variant(const CUtensorMap& a, const CUtensorMap& b, const IgemmParams& P, cudaStream_t stream) {
+    using Cfg = Conv3Cfg<BLOCK_N, MT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VT_CUDA(cudaFuncSetAttribute(conv3_fused_kernel<BLOCK_N, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y * P.n_blocks;
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    conv3_fused_kernel<BLOCK_N, MT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, b, P);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// out = conv3x3(silu(gn(in))) + bias (+ residual); in: raw bf16 NHWC; weights fp16 [Cout][9*Cin].
+int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* prof) {
+    VT_CHECK(op.Cin % 64 == 0 && op.Cin > 0 && op.Cin <= 512, "fused conv: Cin must be a multiple of 64, at most 512");
+    VT_CHECK(op.Cout == 128 || (op.Cout >= 256 && op.Cout % 32 == 0), "fused conv: Cout must be 128 or >= 256");
+    VT_CHECK(op.Cin % 32 == 0 && (op.Cin / 32) % 4 == 0, "fused conv: GroupNorm(32) groups must hold a multiple of 4 channels");
+    VT_CHECK(op.gn_stats && op.gamma && op.beta, "fused conv needs the input statistics and affine parameters");
+    VT_CHECK(op.out_fmt != 2 || (op.residual == nullptr && op.stats == nullptr), "fp16 output has no residual / statistics epilogue");
+    const int block_n = op.Cout == 128 ? 128 : 256;
+    const int mt = block_n == 128 ? 2 : 1;
+    const int H = op.H, W = op.W;
+    IgemmParams P{};
+    P.W = W; P.H = H; P.NB = op.N;
+    P.tw = 8; P.th = 16; P.tw_log2 = 3;
+    P.sub_dx = 1; P.sub_dy = 0;
+    P.ax1 = 0; P.ay1 = 1; P.ax2 = 0; P.ay2 = 2;  // 8x16 patch: accumulator row r+8 is the next image row
+    P.tiles_x = (W + 8 * mt - 1) / (8 * mt);
+    P.tiles_y = (H + 15) / 16;
+    P.n_total = op.Cout;
+    P.n_blocks = (op.Cout + block_n - 1) / block_n;
+    P.num_slabs = 0;
+    P.a_batched = 1; P.b_batched = 0;
+    P.out_fmt = op.out_fmt;
+    P.res_fp32 = op.residual_fp32;
+    P.group_size = op.stats ? op.Cout / 32 : 0;
+    VT_CHECK(op.stats == nullptr || P.group_size == 4 || P.group_size == 8 || P.group_size == 16,
+             "fused GroupNorm statistics need 4, 8 or 16 channels per group");
+    P.alpha = 1.f;
+    P.bias = op.bias; P.residual = op.residual; P.out = op.out; P.ld_out = op.Cout;
+    P.out_bstride = 1LL * H * W * op.Cout; P.stats = op.stats;
+    VT_CHECK(1LL * H * W * op.Cout < (1LL << 31), "conv output of one image exceeds 2^31 elements");
+    P.gn_stats = op.gn_stats; P.gn_gamma = op.gamma; P.gn_beta = op.beta;
+    P.gn_C = op.Cin; P.gn_gs = op.Cin / 32; P.gn_eps = op.eps; P.gn_silu = op.silu; P.cin_chunks = op.Cin / 64;
+
+    CUtensorMap a, b;
+    VT_TRY(make_act_map(&a, op.in, op.N, H, W, op.Cin, 1, 8 * mt + 2, 18));
+    {
+        const int Ktot = 9 * op.Cin;
+        uint64_t dims[3] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(op.Cout), 1};
+        uint64_t str[2] = {2ull * Ktot, 2ull * Ktot * op.Cout};
+        uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
+        VT_TRY(make_tmap(&b, op.w, 3, dims, str, box));
+    }
+    const double flops = 2.0 * op.N * H * W * static_cast<double>(op.Cout) * 9 * op.Cin;
+    const double bytes = 2.0 * op.N * H * W * (1.0 * op.Cin + op.Cout);
+    profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
+    int rc = block_n == 128 ? launch_conv3_variant<128, 2>(a, b, P, stream) : launch_conv3_variant<256, 1>(a, b, P, stream);
+    profiler_end(prof, KC_IGEMM, stream);
+    return rc;
+}
+
 int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     VT_CHECK(op.K % 64 == 0 && op.K > 0, "GEMM K must be a multiple of 64");
     VT_CHECK(op.N % 32 == 0 && op.N > 0, "GEMM N must be a multiple of 32");
@@ -205,7 +272,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     const int mt = pick_mt(block_n);
     P.tw = 128; P.th = 1; P.tw_log2 = 7;
     P.sub_dx = 1; P.sub_dy = 0;  // sub-tiles are consecutive 128-row blocks
-    P.row_jump = static_cast<int>(16 * ldo);  // accumulator row r+16 is output row +16 (tw = 128)
+    P.ax1 = 8; P.ay1 = 0; P.ax2 = 16; P.ay2 = 0;  // 128x1 patch: rows are consecutive output rows
     VT_CHECK(1LL * (op.M + 256) * ldo < (1LL << 31), "GEMM output of one batch exceeds 2^31 elements");
     P.tiles_x = (op.M + 128 * mt - 1) / (128 * mt);
     P.tiles_y = 1;

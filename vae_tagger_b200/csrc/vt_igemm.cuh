@@ -53,7 +53,7 @@ struct IgemmParams {
     int out_fmt;           // output element type: FMT_BF16 / FMT_F32 / FMT_F16
     int res_fp32;          // residual element type: 0 bf16, 1 fp32
     int group_size;        // channels per GroupNorm group for the fused statistics; 0 = off
-    int row_jump;          // element offset between accumulator rows r and r+16 of a sub-tile (see epilogue)
+    int ax1, ay1, ax2, ay2;  // pixel offset of accumulator row r+8 / r+16 relative to row r (patch shape dependent)
     float alpha;
     const float* bias;              // [n_total] or nullptr
     const void* residual;  // same geometry as out (bf16 or fp32), or nullptr
@@ -63,10 +63,19 @@ struct IgemmParams {
     double* stats;     // [NB][n_total/group_size][2] running (sum, sum of squares): fp32 per-tile partials,
                        // fp64 atomics across tiles (keeps E[x^2]-E[x]^2 well conditioned)
     IgemmSlab slabs[IGEMM_MAX_SLABS];
+    // ---- fused GroupNorm+SiLU 3x3 convolution only (vt_conv3.cuh)
+    const double* gn_stats;  // [NB][32][2] (sum, sumsq) of the INPUT tensor
+    const float* gn_gamma;   // [Cin]
+    const float* gn_beta;    // [Cin]
+    int gn_C, gn_gs;         // input channels, channels per group
+    float gn_eps;
+    int gn_silu;
+    int cin_chunks;          // Cin / 64
 };
 
 template <int BLOCK_N, int MT>  // MT = 128-row sub-tiles per CTA tile (2: two pixel tiles share every weight chunk)
 struct IgemmCfg {
+    static constexpr int kBlockN = BLOCK_N, kMT = MT;
     static constexpr int A_BYTES = MT * IGEMM_A_BYTES;
     static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -102,11 +111,11 @@ struct IgemmCfg {
 // GroupNorm accumulators are per-warp slots (no shared-memory atomics): the first two versions of this
 // epilogue spent ~1000 issue slots per 32x32 chunk on branches, 64-bit address arithmetic and
 // compare-and-swap loops and were the limiter of every layer with few K chunks per tile.
-template <int BLOCK_N, int MT, int OUT, int RES, bool STATS>
+template <typename Cfg, int OUT, int RES, bool STATS>
 __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* staging_all, uint8_t* ctrl,
                                                uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
                                                uint32_t total_tiles, int warp, int lane) {
-    using Cfg = IgemmCfg<BLOCK_N, MT>;
+    constexpr int BLOCK_N = Cfg::kBlockN, MT = Cfg::kMT;
     constexpr int EPI_WARPS = Cfg::EPI_WARPS;
     constexpr int RF = Cfg::STAGE_ROW_FLOATS;
     constexpr int SLOTS = Cfg::COLS_PER_WARP / 4;  // 4-column statistic slots per warp
@@ -165,15 +174,15 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
             unsigned vm = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int px = px0 + 8 * (i & 1) + (P.tw > 16 ? 16 * (i >> 1) : 0);
-                const int py = py0 + (P.tw > 16 ? 0 : (i >> 1));
+                const int px = px0 + (i & 1) * P.ax1 + (i >> 1) * P.ax2;
+                const int py = py0 + (i & 1) * P.ay1 + (i >> 1) * P.ay2;
                 if (px < P.W && py < P.H) vm |= 1u << i;
             }
             g.vmask[t] = vm;
         }
     };
-    const int step1 = 8 * static_cast<int>(P.ld_out);  // row r -> r + 8
-    const int step2 = P.row_jump;                      // row r -> r + 16
+    const int step1 = (P.ay1 * P.W + P.ax1) * static_cast<int>(P.ld_out);  // accumulator row r -> r + 8
+    const int step2 = (P.ay2 * P.W + P.ax2) * static_cast<int>(P.ld_out);  // accumulator row r -> r + 16
 
     // residual registers of one pass: 8 channels x 4 rows per lane
     struct ResRegs {
@@ -476,7 +485,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         const int mode = P.out_fmt | (res << 2) | (P.group_size != 0 ? 16 : 0);
 #define VT_EPI_CASE(O, R, S)                                                                                  \
     case ((O) | ((R) << 2) | ((S) << 4)):                                                                     \
-        igemm_epilogue<BLOCK_N, MT, (O), (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base, \
+        igemm_epilogue<Cfg, (O), (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base,         \
                                                          total_tiles, warp, lane);                            \
         break;
         switch (mode) {

@@ -104,6 +104,25 @@ struct GemmOp {
 };
 int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof);
 
+// 3x3 stride-1 conv with GroupNorm(32)+SiLU of the INPUT fused into the operand path (vt_conv3.cuh)
+struct Conv3FusedOp {
+    const void* in = nullptr;   // raw activation, bf16 NHWC [N][H][W][Cin]
+    int N = 0, H = 0, W = 0, Cin = 0, Cout = 0;
+    const double* gn_stats = nullptr;  // [N][32][2] (sum, sumsq) of `in`
+    const float* gamma = nullptr;      // [Cin]
+    const float* beta = nullptr;       // [Cin]
+    float eps = 1e-6f;
+    int silu = 1;
+    const void* w = nullptr;           // fp16 [Cout][9*Cin], tap-major then channel
+    const float* bias = nullptr;
+    const void* residual = nullptr;    // [N][H][W][Cout]
+    int residual_fp32 = 0;
+    void* out = nullptr;
+    int out_fmt = 0;
+    double* stats = nullptr;           // (sum, sumsq) of the output
+};
+int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* prof);
+
 // ---- HBM-bound kernels (vt_elementwise.cu)
 int launch_im2col3x3(const void* in, int fmt, void* out, int out_fmt, int N, int H, int W, cudaStream_t,
                      Profiler*);

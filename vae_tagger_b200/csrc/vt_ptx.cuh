@@ -184,10 +184,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 // fp16 pack with saturation to the finite range (normalised operands are bounded; this is a guard)
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t r;  // one F2FP.SATFINITE.F16.F32.PACK_AB
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 // 16-bit storage formats used by the kernels: 0 = bf16 (raw activations), 2 = fp16 (bounded MMA operands)
 enum { FMT_BF16 = 0, FMT_F32 = 1, FMT_F16 = 2 };
