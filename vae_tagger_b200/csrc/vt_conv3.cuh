@@ -205,9 +205,9 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                                  total_tiles, warp, lane);                                    \
         break;
         switch (mode) {
-            VT_EPI_CASE(0, 0, 0) VT_EPI_CASE(1, 0, 0) VT_EPI_CASE(0, 1, 0) VT_EPI_CASE(0, 0, 1) VT_EPI_CASE(1, 0, 1)
-            VT_EPI_CASE(0, 1, 1) VT_EPI_CASE(0, 2, 1) VT_EPI_CASE(1, 2, 1)
-            default: break;
+            VT_EPI_CASE(0, 0, 0) VT_EPI_CASE(1, 0, 0) VT_EPI_CASE(0, 1, 0) VT_EPI_CASE(1, 1, 0)
+            VT_EPI_CASE(0, 0, 1) VT_EPI_CASE(1, 0, 1) VT_EPI_CASE(0, 1, 1) VT_EPI_CASE(1, 1, 1)
+            default: __trap();  // the host launcher rejects every other combination
         }
 #undef VT_EPI_CASE
     } else {

@@ -216,7 +216,7 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
     VT_CHECK(op.Cout == 128 || (op.Cout >= 256 && op.Cout % 32 == 0), "fused conv: Cout must be 128 or >= 256");
     VT_CHECK(op.Cin % 32 == 0 && (op.Cin / 32) % 4 == 0, "fused conv: GroupNorm(32) groups must hold a multiple of 4 channels");
     VT_CHECK(op.gn_stats && op.gamma && op.beta, "fused conv needs the input statistics and affine parameters");
-    VT_CHECK(op.out_fmt != 2 || (op.residual == nullptr && op.stats == nullptr), "fp16 output has no residual / statistics epilogue");
+    VT_CHECK(op.out_fmt != 2 && !op.residual_fp32, "fused conv: output must be bf16 or fp32 and the residual bf16");
     const int block_n = op.Cout == 128 ? 128 : 256;
     const int mt = block_n == 128 ? 2 : 1;
     const int H = op.H, W = op.W;

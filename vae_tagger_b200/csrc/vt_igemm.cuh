@@ -492,7 +492,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             VT_EPI_CASE(0, 0, 0) VT_EPI_CASE(1, 0, 0) VT_EPI_CASE(2, 0, 0) VT_EPI_CASE(0, 1, 0) VT_EPI_CASE(1, 1, 0)
             VT_EPI_CASE(0, 2, 0) VT_EPI_CASE(1, 2, 0) VT_EPI_CASE(0, 0, 1) VT_EPI_CASE(1, 0, 1)
             VT_EPI_CASE(0, 1, 1) VT_EPI_CASE(1, 1, 1) VT_EPI_CASE(0, 2, 1) VT_EPI_CASE(1, 2, 1)
-            default: break;
+            default: __trap();  // the host launcher rejects every other combination
         }
 #undef VT_EPI_CASE
     }
