@@ -19,40 +19,238 @@
 
 namespace vt {
 
-template <int BLOCK_N, int MT>
+// TR = false: accumulator rows = pixels (MT sub-tiles of 8x16), columns = BLOCK_N output channels.
+// TR = true ("transposed", for 128-channel layers): accumulator rows = 128 output channels (weights are
+//   the A operand), columns = 256 pixels (an 8x32 patch, the halo view is the B operand).  A 128x128
+//   MMA reads 8 KB of operands per 64 cycles -- the full shared-memory read bandwidth -- and measured
+//   ~45 % tensor-pipe utilisation next to the TMA writes; 128x256 reads 12 KB per 128 cycles.
+template <int BLOCK_N, int MT, bool TR>
 struct Conv3Cfg {
     static constexpr int kBlockN = BLOCK_N, kMT = MT;
-    static constexpr int HWID = 8 * MT + 2;           // halo width in pixels
-    static constexpr int HHGT = 18;                   // halo height (16 + 2)
+    static constexpr bool kTR = TR;
+    static constexpr int PX_W = 8 * MT;               // CTA tile in pixels
+    static constexpr int PX_H = TR ? 32 : 16;
+    static constexpr int HWID = PX_W + 2;             // halo width in pixels
+    static constexpr int HHGT = PX_H + 2;             // halo height
     static constexpr int HROWS = HWID * HHGT;         // 128-byte rows per halo chunk
     static constexpr int HALO_BYTES = (HROWS * 128 + 1023) / 1024 * 1024;
     static constexpr int NHALO = 3;
-    static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;   // weight tile of one (tap, 64-channel chunk)
     static constexpr int BSTAGES = 4;
     static constexpr int EPI_WARPS = 4;
     static constexpr int XF_WARPS = 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
-    static constexpr int COLS_PER_WARP = BLOCK_N;
+    static constexpr int COLS_PER_WARP = TR ? 256 : BLOCK_N;      // TMEM columns each epilogue warp walks
     static constexpr int PASSES_PER_SUB = COLS_PER_WARP / 32;
     static constexpr int PASSES = MT * PASSES_PER_SUB;
     static constexpr int STAGE_ROW_FLOATS = 36;
     static constexpr int EPI_STAGING_BYTES = EPI_WARPS * 32 * STAGE_ROW_FLOATS * 4;
-    static constexpr int ACC_COLS = MT * BLOCK_N;
+    static constexpr int ACC_COLS = TR ? 256 : MT * BLOCK_N;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int PART_FLOATS = 2 * EPI_WARPS * (COLS_PER_WARP / 4) * 2;
+    static constexpr int PART_FLOATS = TR ? (2 * EPI_WARPS * 8 * 2) : (2 * EPI_WARPS * (COLS_PER_WARP / 4) * 2);
     static constexpr int SCSH_BYTES = 2 * 512 * 4;     // scale / shift tables, up to 512 input channels
     static constexpr int BAR_BYTES = 256 + 1024 + PART_FLOATS * 4;
     static constexpr int SMEM_BYTES =
         NHALO * HALO_BYTES + BSTAGES * B_BYTES + EPI_STAGING_BYTES + SCSH_BYTES + BAR_BYTES + 1024;
     static_assert(2 * ACC_COLS <= 512, "two accumulator sets must fit TMEM");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(!TR || (BLOCK_N == 128 && MT == 1), "transposed variant: 128 channels x (8x32) pixels");
 };
 
-template <int BLOCK_N, int MT>
-__global__ void __launch_bounds__(Conv3Cfg<BLOCK_N, MT>::THREADS, 1)
+// Epilogue of the transposed variant: TMEM lane = output channel, column = pixel.  Each epilogue warp
+// owns 32 channels; per pass of 32 pixels (4 image rows x 8) the chunk goes through a column-swizzled
+// staging tile so that 4 lanes hold 32 consecutive channels of one pixel (64 contiguous bytes) and a
+// warp store covers 8 pixels.  The lane's 8 channels are fixed for the whole kernel: bias lives in
+// registers and the GroupNorm partial sums are folded once per tile.
+template <typename Cfg, int OUT, int RES, bool STATS>
+__device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* staging_all, uint8_t* ctrl,
+                                                uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
+                                                uint32_t total_tiles, int warp, int lane) {
+    constexpr int EPI_WARPS = Cfg::EPI_WARPS;
+    constexpr int RF = Cfg::STAGE_ROW_FLOATS;
+    constexpr bool OUT_F32 = (OUT == FMT_F32);
+    typedef typename std::conditional<OUT_F32, float, __nv_bfloat16>::type OutT;
+    const int ew = warp - 2;
+    const int q = warp & 3;                   // TMEM lane quadrant = channels 32q .. 32q+31 of the n-block
+    const uint32_t stg = smem_u32(staging_all + ew * 32 * RF);
+    const int et = threadIdx.x - 64;
+    const int psub = lane >> 2;               // phase B: pixel x inside the 8-pixel row
+    const int cgrp = lane & 3;                // phase B: 8-channel group inside the warp's 32 channels
+    const int swz_a = 8 * ((lane >> 3) & 3);  // phase A: column swizzle of this thread's staging row
+
+    double* s_run = reinterpret_cast<double*>(ctrl + 256);
+    float* s_part = reinterpret_cast<float*>(ctrl + 256 + 1024);  // [2][EPI_WARPS][8 slots][2]
+    if (STATS) {
+        if (et < 128) s_run[et] = 0.0;
+        for (int i = et; i < Cfg::PART_FLOATS; i += 32 * EPI_WARPS) s_part[i] = 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    }
+    int run_img = -1, run_nb = -1;
+    auto flush_stats = [&]() {
+        const int nvals = 2 * 128 / P.group_size;
+        if (run_img >= 0 && et < nvals) {
+            const int g_total = P.n_total / P.group_size;
+            const int grp = run_nb * (128 / P.group_size) + (et >> 1);
+            if (grp < g_total)
+                atomicAdd(P.stats + (static_cast<long long>(run_img) * g_total + grp) * 2 + (et & 1), s_run[et]);
+            s_run[et] = 0.0;
+        }
+    };
+    auto decode = [&](uint32_t tile, int& nb, int& x0, int& y0, int& img) {
+        nb = static_cast<int>(tile % static_cast<uint32_t>(P.n_blocks));
+        uint32_t m = tile / static_cast<uint32_t>(P.n_blocks);
+        const int tx = static_cast<int>(m % static_cast<uint32_t>(P.tiles_x));
+        m /= static_cast<uint32_t>(P.tiles_x);
+        const int ty = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
+        img = static_cast<int>(m / static_cast<uint32_t>(P.tiles_y));
+        x0 = tx * Cfg::PX_W;
+        y0 = ty * Cfg::PX_H;
+    };
+    const int ld = static_cast<int>(P.ld_out);
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        int nb, x0, y0, img;
+        decode(tile, nb, x0, y0, img);
+        const int ch0 = nb * 128 + q * 32 + cgrp * 8;    // this lane's first output channel
+        const bool ch_ok = ch0 < P.n_total;
+        const uint32_t acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        if (STATS && (img != run_img || nb != run_nb)) {
+            flush_stats();
+            run_img = img; run_nb = nb;
+        }
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (P.bias != nullptr && ch_ok) {
+            b0 = __ldg(reinterpret_cast<const float4*>(P.bias + ch0));
+            b1 = __ldg(reinterpret_cast<const float4*>(P.bias + ch0 + 4));
+        }
+        const long long img_off = static_cast<long long>(img) * P.out_bstride + ch0;
+        OutT* out_img = static_cast<OutT*>(P.out) + img_off;
+        const int px = x0 + psub;
+        const bool x_ok = px < P.W && ch_ok;
+        float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int pc = 0; pc < 8; ++pc) {             // 32 pixels = image rows y0+4pc .. +3
+            // residual prefetch for the 4 pixels of this lane in this pass
+            uint4 rlo[4], rhi[4];
+            if (RES != 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int py = y0 + 4 * pc + i;
+                    rlo[i] = make_uint4(0u, 0u, 0u, 0u);
+                    rhi[i] = rlo[i];
+                    if (x_ok && py < P.H) {
+                        const int off = (py * P.W + px) * ld;
+                        if (RES == 1) {
+                            rlo[i] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.residual) + img_off + off));
+                        } else {
+                            const float* rp = static_cast<const float*>(P.residual) + img_off + off;
+                            rlo[i] = __ldg(reinterpret_cast<const uint4*>(rp));
+                            rhi[i] = __ldg(reinterpret_cast<const uint4*>(rp + 4));
+                        }
+                    }
+                }
+            }
+            // ---- phase A: TMEM (row = channel, 32 pixel columns) -> column-swizzled staging
+            {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + pc * 32, r);
+                tmem_ld_wait();
+                if (pc == 7) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                }
+                const uint32_t dst = stg + lane * RF * 4;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    sts128(dst + (((4 * k) ^ swz_a) << 2), __uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
+                           __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+            }
+            __syncwarp();
+            // ---- phase B: (pixel, 8 channels) per lane
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int py = y0 + 4 * pc + i;
+                const int col = (8 * i + psub) ^ (8 * cgrp);
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float t;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(stg + ((cgrp * 8 + e) * RF + col) * 4) : "memory");
+                    v[e] = t;
+                }
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                if (RES == 1) {
+                    const uint4 u = rlo[i];
+                    v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
+                    v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
+                } else if (RES == 2) {
+                    const uint4 a = rlo[i], b = rhi[i];
+                    v[0] += __uint_as_float(a.x); v[1] += __uint_as_float(a.y); v[2] += __uint_as_float(a.z); v[3] += __uint_as_float(a.w);
+                    v[4] += __uint_as_float(b.x); v[5] += __uint_as_float(b.y); v[6] += __uint_as_float(b.z); v[7] += __uint_as_float(b.w);
+                }
+                const bool ok = x_ok && py < P.H;
+                if (STATS && ok) {
+                    s_lo += (v[0] + v[1]) + (v[2] + v[3]);
+                    q_lo = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], q_lo))));
+                    s_hi += (v[4] + v[5]) + (v[6] + v[7]);
+                    q_hi = fmaf(v[4], v[4], fmaf(v[5], v[5], fmaf(v[6], v[6], fmaf(v[7], v[7], q_hi))));
+                }
+                OutT* o = out_img + (py * P.W + px) * ld;
+                if (OUT_F32) {
+                    if (ok) {
+                        reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    }
+                } else {
+                    const uint4 pk = make_uint4(pack16x2<OUT>(v[0], v[1]), pack16x2<OUT>(v[2], v[3]),
+                                                pack16x2<OUT>(v[4], v[5]), pack16x2<OUT>(v[6], v[7]));
+                    if (ok) *reinterpret_cast<uint4*>(o) = pk;
+                }
+            }
+            __syncwarp();  // staging is reused by the next pass
+        }
+        if (STATS) {
+            // fold the 8 pixel lanes that share a channel group, then lanes 0..3 own two 4-channel slots each
+#pragma unroll
+            for (int o = 4; o <= 16; o <<= 1) {
+                s_lo += __shfl_xor_sync(0xFFFFFFFFu, s_lo, o);
+                q_lo += __shfl_xor_sync(0xFFFFFFFFu, q_lo, o);
+                s_hi += __shfl_xor_sync(0xFFFFFFFFu, s_hi, o);
+                q_hi += __shfl_xor_sync(0xFFFFFFFFu, q_hi, o);
+            }
+            float* part = s_part + (acc * EPI_WARPS + ew) * 16;
+            if (lane < 4) *reinterpret_cast<float4*>(part + lane * 4) = make_float4(s_lo, q_lo, s_hi, q_hi);
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            const int nvals = 2 * 128 / P.group_size;
+            if (et < nvals) {
+                // value et = (group g, sum|sumsq): 4-channel slots g*gs/4 .. ; slot s lives in warp q' = s/8
+                const int g = et >> 1, which = et & 1;
+                const int spg = P.group_size / 4;
+                float tot = 0.f;
+                for (int sidx = g * spg; sidx < (g + 1) * spg; ++sidx) {
+                    // epilogue warp index for quadrant qq is (qq + 2) & 3 (warps 2,3,4,5 own quadrants 2,3,0,1)
+                    const int qq = sidx >> 3, wsel = (qq + 2) & 3;
+                    tot += s_part[(acc * EPI_WARPS + wsel) * 16 + (sidx & 7) * 2 + which];
+                }
+                s_run[et] += static_cast<double>(tot);
+            }
+        }
+    }
+    if (STATS) flush_stats();
+}
+
+template <int BLOCK_N, int MT, bool TR>
+__global__ void __launch_bounds__(Conv3Cfg<BLOCK_N, MT, TR>::THREADS, 1)
 conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ IgemmParams P) {
-    using Cfg = Conv3Cfg<BLOCK_N, MT>;
+    using Cfg = Conv3Cfg<BLOCK_N, MT, TR>;
     constexpr int NHALO = Cfg::NHALO, BST = Cfg::BSTAGES, HWID = Cfg::HWID, HROWS = Cfg::HROWS;
 
     extern __shared__ uint8_t smem_raw[];
@@ -112,8 +310,8 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         m /= static_cast<uint32_t>(P.tiles_x);
         const int ty = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
         img = static_cast<int>(m / static_cast<uint32_t>(P.tiles_y));
-        x0 = tx * 8 * MT;
-        y0 = ty * 16;
+        x0 = tx * Cfg::PX_W;
+        y0 = ty * Cfg::PX_H;
     };
 
     if (warp == 0) {
@@ -155,7 +353,8 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_16(IGEMM_BLOCK_M, BLOCK_N, true);  // fp16 x fp16
+            // fp16 x fp16; transposed: M = 128 channels, N = 256 pixels
+            constexpr uint32_t idesc = umma_idesc_16(IGEMM_BLOCK_M, TR ? 256 : BLOCK_N, true);
             int hb = 0, bs = 0;
             uint32_t hphase = 0, bphase = 0, it = 0;
             for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -173,15 +372,21 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const int dy = tap / 3, dx = tap - dy * 3;
                         mbar_wait(&b_full[bs], bphase);
                         tc_fence_after();
-                        const uint64_t db = umma_desc_k_sw128(smem_u32(s_b + bs * Cfg::B_BYTES));
+                        const uint64_t dw = umma_desc_k_sw128(smem_u32(s_b + bs * Cfg::B_BYTES));
 #pragma unroll
                         for (int k = 0; k < IGEMM_BLOCK_K / 16; ++k) {
+                            if constexpr (TR) {
+                                // A = weights (128 channels), B = halo view: 32 image rows of 8 pixels, one
+                                // 8-row group per image row, HWID halo pixels apart
+                                const uint64_t dp = umma_desc_k_sw128(hbase + (dy * HWID + dx) * 128, HWID * 128);
+                                umma_bf16_ss(tmem_d, dw + 2 * k, dp + 2 * k, idesc, first | k);
+                            } else {
 #pragma unroll
-                            for (int t = 0; t < MT; ++t) {
-                                // tap (dy, dx), sub-tile t: rows start at halo pixel (dy, dx + 8t); one 8-row
-                                // group per output row, HWID halo pixels apart
-                                const uint64_t da = umma_desc_k_sw128(hbase + (dy * HWID + dx + 8 * t) * 128, HWID * 128);
-                                umma_bf16_ss(tmem_d + t * BLOCK_N, da + 2 * k, db + 2 * k, idesc, first | k);
+                                for (int t = 0; t < MT; ++t) {
+                                    // tap (dy, dx), sub-tile t: rows start at halo pixel (dy, dx + 8t)
+                                    const uint64_t da = umma_desc_k_sw128(hbase + (dy * HWID + dx + 8 * t) * 128, HWID * 128);
+                                    umma_bf16_ss(tmem_d + t * BLOCK_N, da + 2 * k, dw + 2 * k, idesc, first | k);
+                                }
                             }
                         }
                         first = 1;
@@ -201,8 +406,12 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int mode = P.out_fmt | (res << 2) | (P.group_size != 0 ? 16 : 0);
 #define VT_EPI_CASE(O, R, S)                                                                                  \
     case ((O) | ((R) << 2) | ((S) << 4)):                                                                     \
-        igemm_epilogue<Cfg, (O), (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base,         \
-                                                 total_tiles, warp, lane);                                    \
+        if constexpr (TR)                                                                                     \
+            conv3t_epilogue<Cfg, (O), (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base,    \
+                                                      total_tiles, warp, lane);                               \
+        else                                                                                                  \
+            igemm_epilogue<Cfg, (O), (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base,     \
+                                                     total_tiles, warp, lane);                                \
         break;
         switch (mode) {
             VT_EPI_CASE(0, 0, 0) VT_EPI_CASE(1, 0, 0) VT_EPI_CASE(0, 1, 0) VT_EPI_CASE(1, 1, 0)

@@ -194,18 +194,18 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     return rc;
 }
 
-template <int BLOCK_N, int MT>
+template <int BLOCK_N, int MT, bool TR>
 static int launch_conv3_variant(const CUtensorMap& a, const CUtensorMap& b, const IgemmParams& P, cudaStream_t stream) {
-    using Cfg = Conv3Cfg<BLOCK_N, MT>;
+    using Cfg = Conv3Cfg<BLOCK_N, MT, TR>;
     static bool attr_set = false;
     if (!attr_set) {
-        VT_CUDA(cudaFuncSetAttribute(conv3_fused_kernel<BLOCK_N, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VT_CUDA(cudaFuncSetAttribute(conv3_fused_kernel<BLOCK_N, MT, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y * P.n_blocks;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    conv3_fused_kernel<BLOCK_N, MT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, b, P);
+    conv3_fused_kernel<BLOCK_N, MT, TR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, b, P);
     VT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -217,16 +217,19 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
     VT_CHECK(op.Cin % 32 == 0 && (op.Cin / 32) % 4 == 0, "fused conv: GroupNorm(32) groups must hold a multiple of 4 channels");
     VT_CHECK(op.gn_stats && op.gamma && op.beta, "fused conv needs the input statistics and affine parameters");
     VT_CHECK(op.out_fmt != 2 && !op.residual_fp32, "fused conv: output must be bf16 or fp32 and the residual bf16");
-    const int block_n = op.Cout == 128 ? 128 : 256;
-    const int mt = block_n == 128 ? 2 : 1;
+    // 128-channel layers: transposed variant (channels on the accumulator rows, an 8x32 pixel patch on the
+    // columns); wider layers: 8x16 pixel patch x 256 channels
+    const bool tr = op.Cout == 128;
+    const int block_n = tr ? 128 : 256;
+    const int pxw = 8, pxh = tr ? 32 : 16;
     const int H = op.H, W = op.W;
     IgemmParams P{};
     P.W = W; P.H = H; P.NB = op.N;
     P.tw = 8; P.th = 16; P.tw_log2 = 3;
     P.sub_dx = 1; P.sub_dy = 0;
     P.ax1 = 0; P.ay1 = 1; P.ax2 = 0; P.ay2 = 2;  // 8x16 patch: accumulator row r+8 is the next image row
-    P.tiles_x = (W + 8 * mt - 1) / (8 * mt);
-    P.tiles_y = (H + 15) / 16;
+    P.tiles_x = (W + pxw - 1) / pxw;
+    P.tiles_y = (H + pxh - 1) / pxh;
     P.n_total = op.Cout;
     P.n_blocks = (op.Cout + block_n - 1) / block_n;
     P.num_slabs = 0;
@@ -244,7 +247,7 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
     P.gn_C = op.Cin; P.gn_gs = op.Cin / 32; P.gn_eps = op.eps; P.gn_silu = op.silu; P.cin_chunks = op.Cin / 64;
 
     CUtensorMap a, b;
-    VT_TRY(make_act_map(&a, op.in, op.N, H, W, op.Cin, 1, 8 * mt + 2, 18));
+    VT_TRY(make_act_map(&a, op.in, op.N, H, W, op.Cin, 1, pxw + 2, pxh + 2));
     {
         const int Ktot = 9 * op.Cin;
         uint64_t dims[3] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(op.Cout), 1};
@@ -255,7 +258,7 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
     const double flops = 2.0 * op.N * H * W * static_cast<double>(op.Cout) * 9 * op.Cin;
     const double bytes = 2.0 * op.N * H * W * (1.0 * op.Cin + op.Cout);
     profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
-    int rc = block_n == 128 ? launch_conv3_variant<128, 2>(a, b, P, stream) : launch_conv3_variant<256, 1>(a, b, P, stream);
+    int rc = tr ? launch_conv3_variant<128, 1, true>(a, b, P, stream) : launch_conv3_variant<256, 1, false>(a, b, P, stream);
     profiler_end(prof, KC_IGEMM, stream);
     return rc;
 }
