@@ -36,18 +36,18 @@ struct Conv3Cfg {
     static constexpr int HALO_BYTES = (HROWS * 128 + 1023) / 1024 * 1024;
     static constexpr int NHALO = 3;
     static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;   // weight tile of one (tap, 64-channel chunk)
-    static constexpr int BSTAGES = 4;
-    static constexpr int EPI_WARPS = 4;
+    static constexpr int BSTAGES = 3;
+    static constexpr int EPI_WARPS = 8;   // two per TMEM lane quadrant: the epilogue is latency bound
     static constexpr int XF_WARPS = 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
-    static constexpr int COLS_PER_WARP = TR ? 256 : BLOCK_N;      // TMEM columns each epilogue warp walks
+    static constexpr int COLS_PER_WARP = (TR ? 256 : BLOCK_N) / (EPI_WARPS / 4);  // TMEM columns each epilogue warp walks
     static constexpr int PASSES_PER_SUB = COLS_PER_WARP / 32;
     static constexpr int PASSES = MT * PASSES_PER_SUB;
     static constexpr int STAGE_ROW_FLOATS = 36;
     static constexpr int EPI_STAGING_BYTES = EPI_WARPS * 32 * STAGE_ROW_FLOATS * 4;
     static constexpr int ACC_COLS = TR ? 256 : MT * BLOCK_N;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int PART_FLOATS = TR ? (2 * EPI_WARPS * 8 * 2) : (2 * EPI_WARPS * (COLS_PER_WARP / 4) * 2);
+    static constexpr int PART_FLOATS = TR ? (2 * EPI_WARPS * 16) : (2 * EPI_WARPS * (COLS_PER_WARP / 4) * 2);
     static constexpr int SCSH_BYTES = 2 * 512 * 4;     // scale / shift tables, up to 512 input channels
     static constexpr int BAR_BYTES = 256 + 1024 + PART_FLOATS * 4;
     static constexpr int SMEM_BYTES =
@@ -77,6 +77,8 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
     const int psub = lane >> 2;               // phase B: pixel x inside the 8-pixel row
     const int cgrp = lane & 3;                // phase B: 8-channel group inside the warp's 32 channels
     const int swz_a = 8 * ((lane >> 3) & 3);  // phase A: column swizzle of this thread's staging row
+    constexpr int NPASS = Cfg::PASSES_PER_SUB;             // 32-pixel passes per warp
+    const int pc0 = (ew >> 2) * NPASS;                     // first pass of this warp (two warps per quadrant)
 
     double* s_run = reinterpret_cast<double*>(ctrl + 256);
     float* s_part = reinterpret_cast<float*>(ctrl + 256 + 1024);  // [2][EPI_WARPS][8 slots][2]
@@ -134,7 +136,7 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-        for (int pc = 0; pc < 8; ++pc) {             // 32 pixels = image rows y0+4pc .. +3
+        for (int pc = pc0; pc < pc0 + NPASS; ++pc) {   // 32 pixels = image rows y0+4pc .. +3
             // residual prefetch for the 4 pixels of this lane in this pass
             uint4 rlo[4], rhi[4];
             if (RES != 0) {
@@ -160,7 +162,7 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + pc * 32, r);
                 tmem_ld_wait();
-                if (pc == 7) {
+                if (pc == pc0 + NPASS - 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -235,9 +237,11 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
                 const int spg = P.group_size / 4;
                 float tot = 0.f;
                 for (int sidx = g * spg; sidx < (g + 1) * spg; ++sidx) {
-                    // epilogue warp index for quadrant qq is (qq + 2) & 3 (warps 2,3,4,5 own quadrants 2,3,0,1)
+                    // epilogue warps of quadrant qq: ew = (qq + 2) & 3 and that + 4 (warps 2..5 / 6..9 own quadrants 2,3,0,1)
                     const int qq = sidx >> 3, wsel = (qq + 2) & 3;
-                    tot += s_part[(acc * EPI_WARPS + wsel) * 16 + (sidx & 7) * 2 + which];
+#pragma unroll
+                    for (int h = 0; h < EPI_WARPS / 4; ++h)
+                        tot += s_part[(acc * EPI_WARPS + wsel + 4 * h) * 16 + (sidx & 7) * 2 + which];
                 }
                 s_run[et] += static_cast<double>(tot);
             }
