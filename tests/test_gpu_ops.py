@@ -179,8 +179,9 @@ def test_conv3_fused_groupnorm_silu(ctx, case):
     ref = F.conv2d(rh(t), rh(w), b, padding=1)
     if use_res:
         ref = ref + r16(res)
-    # the kernel's sigmoid uses ex2.approx / rcp.approx: operand values can differ by one fp16 ulp
-    assert rel(out, ref) < 3e-4, (rel(out, ref), (out - ref).abs().max().item())
+    # the kernel evaluates SiLU as h + h*tanh.approx(h) on half2 (h = t/2 in fp16): operand values differ from
+    # the fp32 reference rounded to fp16 by up to ~2 fp16 ulps (2^-10 relative)
+    assert rel(out, ref) < 1e-3, (rel(out, ref), (out - ref).abs().max().item())
     grp = ref.double().reshape(n, 32, -1)
     want = torch.stack([grp.sum(-1), (grp * grp).sum(-1)], dim=-1)
     got = stats.cpu()

@@ -36,8 +36,10 @@ struct Conv3Cfg {
     static constexpr int HALO_BYTES = (HROWS * 128 + 1023) / 1024 * 1024;
     static constexpr int NHALO = 3;
     static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;   // weight tile of one (tap, 64-channel chunk)
-    static constexpr int BSTAGES = 3;
-    static constexpr int EPI_WARPS = 8;   // two per TMEM lane quadrant: the epilogue is latency bound
+    // transposed (level 0, 2 channel chunks per tile): the epilogue is on the critical path -> two warps per
+    // TMEM lane quadrant, paid for with one weight stage; deep-K layers keep four stages and four warps
+    static constexpr int BSTAGES = TR ? 3 : 4;
+    static constexpr int EPI_WARPS = TR ? 8 : 4;
     static constexpr int XF_WARPS = 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
     static constexpr int COLS_PER_WARP = (TR ? 256 : BLOCK_N) / (EPI_WARPS / 4);  // TMEM columns each epilogue warp walks
@@ -454,39 +456,47 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 cur_img = img;
             }
             for (int c = 0; c < nchunks; ++c) {
+                // SiLU(t) = t*sigmoid(t) = h + h*tanh(h) with h = t/2: the halving is folded into the per-channel
+                // scale/shift, h is rounded to fp16 and tanh / fma run on half2 (one MUFU per two elements);
+                // tools/emulate_bf16.py: no measurable change of the latent error vs the exp/rcp form
                 float sc[8], sh[8];
                 {
+                    const float half_if_silu = P.gn_silu ? 0.5f : 1.0f;
                     const float4 a0 = *reinterpret_cast<const float4*>(s_sc + c * 64 + lc * 8);
                     const float4 a1 = *reinterpret_cast<const float4*>(s_sc + c * 64 + lc * 8 + 4);
                     const float4 b0 = *reinterpret_cast<const float4*>(s_sh + c * 64 + lc * 8);
                     const float4 b1 = *reinterpret_cast<const float4*>(s_sh + c * 64 + lc * 8 + 4);
                     sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
                     sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { sc[e] *= half_if_silu; sh[e] *= half_if_silu; }
                 }
                 mbar_wait(&halo_full[hb], hphase);
                 const uint32_t base = smem_u32(s_halo + hb * Cfg::HALO_BYTES);
-#pragma unroll 2
+                const bool silu = P.gn_silu != 0;
+#pragma unroll 4
                 for (int row = rbase; row < HROWS; row += 16) {
                     const int hy = row / HWID, hx = row - hy * HWID;
                     const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
                     // physical 16-byte chunk of this thread's channel group in this row (128B swizzle)
                     const uint32_t addr = base + row * 128 + ((lc ^ (row & 7)) << 4);
-                    uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
-                    if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) {
-                        uint32_t u0, u1, u2, u3;
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(addr) : "memory");
-                        float v[8] = {bf16_lo(u0), bf16_hi(u0), bf16_lo(u1), bf16_hi(u1),
-                                      bf16_lo(u2), bf16_hi(u2), bf16_lo(u3), bf16_hi(u3)};
+                    uint32_t u[4];
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(addr) : "memory");
+                    const bool inside = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+                    uint32_t o[4];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float t = fmaf(v[e], sc[e], sh[e]);
-                            if (P.gn_silu) t = __fdividef(t, 1.0f + __expf(-t));
-                            v[e] = t;
+                    for (int j = 0; j < 4; ++j) {
+                        const float lo = fmaf(bf16_lo(u[j]), sc[2 * j], sh[2 * j]);
+                        const float hi = fmaf(bf16_hi(u[j]), sc[2 * j + 1], sh[2 * j + 1]);
+                        uint32_t h2 = pack_f16x2(lo, hi);
+                        if (silu) {
+                            uint32_t th;
+                            asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(h2));
+                            asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(h2) : "r"(h2), "r"(th));
                         }
-                        o0 = pack_f16x2(v[0], v[1]); o1 = pack_f16x2(v[2], v[3]);
-                        o2 = pack_f16x2(v[4], v[5]); o3 = pack_f16x2(v[6], v[7]);
+                        o[j] = inside ? h2 : 0u;   // the reference zero-pads AFTER GroupNorm+SiLU
                     }
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
                 }
                 // generic-proxy writes -> visible to the tensor core's async proxy, then signal the MMA warp
                 fence_proxy_async_smem();

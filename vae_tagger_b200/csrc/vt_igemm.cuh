@@ -80,7 +80,9 @@ struct IgemmCfg {
     static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, splitting the columns)
-    static constexpr int EPI_WARPS = (BLOCK_N >= 128) ? 8 : 4;
+    // 128-column tiles have few K chunks per tile (level 0, conv_in): their epilogue is on the critical
+    // path and latency bound, so two warps per scheduler; 256-column tiles keep a fourth operand stage
+    static constexpr int EPI_WARPS = (BLOCK_N == 128) ? 8 : 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int COLS_PER_WARP = BLOCK_N / (EPI_WARPS / 4);
     static constexpr int PASSES_PER_SUB = COLS_PER_WARP / 32;
@@ -89,7 +91,7 @@ struct IgemmCfg {
     static constexpr int EPI_STAGING_BYTES = EPI_WARPS * 32 * STAGE_ROW_FLOATS * 4;
     // the epilogue is latency bound (one dependent chain per warp): two warps per scheduler are worth more
     // than a fourth operand stage, which is what their staging tiles cost
-    static constexpr int STAGES = (STAGE_BYTES >= 48 * 1024) ? 3 : (STAGE_BYTES >= 32 * 1024 ? 5 : 8);
+    static constexpr int STAGES = (STAGE_BYTES >= 48 * 1024) ? (EPI_WARPS == 8 ? 3 : 4) : (STAGE_BYTES >= 32 * 1024 ? 5 : 8);
     static constexpr int ACC_COLS = MT * BLOCK_N;  // TMEM columns of one accumulator set
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
                                      : (2 * ACC_COLS <= 256) ? 256 : 512;
