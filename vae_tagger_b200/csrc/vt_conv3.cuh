@@ -358,9 +358,13 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // The whole warp walks the loops (warp-uniform control flow keeps the descriptors in uniform
+        // registers); one elected lane issues the MMAs and commits.
+        {
             // fp16 x fp16; transposed: M = 128 channels, N = 256 pixels
             constexpr uint32_t idesc = umma_idesc_16(IGEMM_BLOCK_M, TR ? 256 : BLOCK_N, true);
+            const uint64_t dw_base = umma_desc_k_sw128(smem_u32(s_b));                       // weight tile, stage 0
+            const uint64_t dh_base = umma_desc_k_sw128(smem_u32(s_halo), HWID * 128);        // halo tile, buffer 0
             int hb = 0, bs = 0;
             uint32_t hphase = 0, bphase = 0, it = 0;
             for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -373,39 +377,41 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 for (int c = 0; c < nchunks; ++c) {
                     mbar_wait(&halo_ready[hb], hphase);
                     tc_fence_after();
-                    const uint32_t hbase = smem_u32(s_halo + hb * Cfg::HALO_BYTES);
+                    const uint64_t dh = dh_base + static_cast<uint64_t>(hb * (Cfg::HALO_BYTES >> 4));
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const int dy = tap / 3, dx = tap - dy * 3;
+                        constexpr int kDummy = 0; (void)kDummy;
+                        const int dy = tap / 3, dx = tap % 3;
                         mbar_wait(&b_full[bs], bphase);
                         tc_fence_after();
-                        const uint64_t dw = umma_desc_k_sw128(smem_u32(s_b + bs * Cfg::B_BYTES));
+                        const uint64_t dw = dw_base + static_cast<uint64_t>(bs * (Cfg::B_BYTES >> 4));
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < IGEMM_BLOCK_K / 16; ++k) {
-                            if constexpr (TR) {
-                                // A = weights (128 channels), B = halo view: 32 image rows of 8 pixels, one
-                                // 8-row group per image row, HWID halo pixels apart
-                                const uint64_t dp = umma_desc_k_sw128(hbase + (dy * HWID + dx) * 128, HWID * 128);
-                                umma_bf16_ss(tmem_d, dw + 2 * k, dp + 2 * k, idesc, first | k);
-                            } else {
+                            for (int k = 0; k < IGEMM_BLOCK_K / 16; ++k) {
+                                if constexpr (TR) {
+                                    // A = weights (128 channels), B = halo view: 32 image rows of 8 pixels, one
+                                    // 8-row group per image row, HWID halo pixels apart
+                                    umma_bf16_ss(tmem_d, dw + 2 * k, dh + ((dy * HWID + dx) * 8 + 2 * k), idesc, first | k);
+                                } else {
 #pragma unroll
-                                for (int t = 0; t < MT; ++t) {
-                                    // tap (dy, dx), sub-tile t: rows start at halo pixel (dy, dx + 8t)
-                                    const uint64_t da = umma_desc_k_sw128(hbase + (dy * HWID + dx + 8 * t) * 128, HWID * 128);
-                                    umma_bf16_ss(tmem_d + t * BLOCK_N, da + 2 * k, dw + 2 * k, idesc, first | k);
+                                    for (int t = 0; t < MT; ++t)
+                                        umma_bf16_ss(tmem_d + t * BLOCK_N, dh + ((dy * HWID + dx + 8 * t) * 8 + 2 * k),
+                                                     dw + 2 * k, idesc, first | k);
                                 }
                             }
+                            umma_commit(&b_empty[bs]);
+                            if (tap == 8) umma_commit(&halo_free[hb]);
                         }
+                        __syncwarp();
                         first = 1;
-                        umma_commit(&b_empty[bs]);
                         if (++bs == BST) { bs = 0; bphase ^= 1; }
                     }
-                    umma_commit(&halo_free[hb]);
                     if (++hb == NHALO) { hb = 0; hphase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);
+                if (elect_one()) umma_commit(&tfull_bar[acc]);
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else if (warp < 2 + Cfg::EPI_WARPS) {
         // ------------------------------------------------------------ epilogue warps (2..5)
         const int res = P.residual == nullptr ? 0 : (P.res_fp32 ? 2 : 1);

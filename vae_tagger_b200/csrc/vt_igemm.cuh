@@ -444,9 +444,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // The whole warp walks the loops (warp-uniform control flow keeps the descriptors in uniform
+        // registers); one elected lane issues the MMAs and commits.
+        {
             constexpr uint32_t idesc_bf16 = umma_idesc_16(IGEMM_BLOCK_M, BLOCK_N, false);
             constexpr uint32_t idesc_f16 = umma_idesc_16(IGEMM_BLOCK_M, BLOCK_N, true);
+            const uint64_t da_base = umma_desc_k_sw128(smem_u32(smem));                  // stage 0, sub-tile 0
+            const uint64_t db_base = umma_desc_k_sw128(smem_u32(smem) + Cfg::A_BYTES);   // stage 0
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
@@ -463,26 +467,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                     for (int kb = 0; kb < nch; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                        const uint64_t db = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+                        const uint64_t so = static_cast<uint64_t>(stage * (Cfg::STAGE_BYTES >> 4));
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < IGEMM_BLOCK_K / 16; ++k) {
+                            for (int k = 0; k < IGEMM_BLOCK_K / 16; ++k) {
 #pragma unroll
-                            for (int t = 0; t < MT; ++t) {
-                                // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
-                                const uint64_t da = umma_desc_k_sw128(sa + t * IGEMM_A_BYTES);
-                                umma_bf16_ss(tmem_d + t * BLOCK_N, da + 2 * k, db + 2 * k, idesc, first | k);
+                                for (int t = 0; t < MT; ++t) {
+                                    // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
+                                    umma_bf16_ss(tmem_d + t * BLOCK_N, da_base + so + (t * (IGEMM_A_BYTES >> 4) + 2 * k),
+                                                 db_base + so + 2 * k, idesc, first | k);
+                                }
                             }
+                            umma_commit(&empty_bar[stage]);
                         }
+                        __syncwarp();
                         first = 1;
-                        umma_commit(&empty_bar[stage]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
-                umma_commit(&tfull_bar[acc]);
+                if (elect_one()) umma_commit(&tfull_bar[acc]);
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue warps
         const int res = P.residual == nullptr ? 0 : (P.res_fp32 ? 2 : 1);
