@@ -176,18 +176,24 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
                            __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
             }
             __syncwarp();
-            // ---- phase B: (pixel, 8 channels) per lane
+            // ---- phase B: (pixel, 8 channels) per lane; all staging reads of the pass are issued first
+            float vv[4][8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int py = y0 + 4 * pc + i;
                 const int col = (8 * i + psub) ^ (8 * cgrp);
-                float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     float t;
                     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(stg + ((cgrp * 8 + e) * RF + col) * 4) : "memory");
-                    v[e] = t;
+                    vv[i][e] = t;
                 }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int py = y0 + 4 * pc + i;
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = vv[i][e];
                 v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
                 v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
                 if (RES == 1) {
@@ -480,29 +486,47 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 mbar_wait(&halo_full[hb], hphase);
                 const uint32_t base = smem_u32(s_halo + hb * Cfg::HALO_BYTES);
                 const bool silu = P.gn_silu != 0;
-#pragma unroll 4
-                for (int row = rbase; row < HROWS; row += 16) {
-                    const int hy = row / HWID, hx = row - hy * HWID;
-                    const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
-                    // physical 16-byte chunk of this thread's channel group in this row (128B swizzle)
-                    const uint32_t addr = base + row * 128 + ((lc ^ (row & 7)) << 4);
-                    uint32_t u[4];
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(addr) : "memory");
-                    const bool inside = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
-                    uint32_t o[4];
+                // four halo rows per step: all loads first, then the math, then the stores (the shared-memory
+                // accesses are volatile asm and keep their program order, so interleaving them per row would
+                // serialise four dependent chains)
+#pragma unroll 1
+                for (int row0 = rbase; row0 < HROWS; row0 += 64) {
+                    uint32_t u[4][4];
+                    uint32_t addr[4];
+                    bool inside[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float lo = fmaf(bf16_lo(u[j]), sc[2 * j], sh[2 * j]);
-                        const float hi = fmaf(bf16_hi(u[j]), sc[2 * j + 1], sh[2 * j + 1]);
-                        uint32_t h2 = pack_f16x2(lo, hi);
-                        if (silu) {
-                            uint32_t th;
-                            asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(h2));
-                            asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(h2) : "r"(h2), "r"(th));
-                        }
-                        o[j] = inside ? h2 : 0u;   // the reference zero-pads AFTER GroupNorm+SiLU
+                    for (int r = 0; r < 4; ++r) {
+                        const int row = row0 + 16 * r;
+                        const int hy = row / HWID, hx = row - hy * HWID;
+                        const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+                        inside[r] = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+                        // physical 16-byte chunk of this thread's channel group in this row (128B swizzle)
+                        addr[r] = base + row * 128 + ((lc ^ (row & 7)) << 4);
+                        if (row < HROWS)
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(u[r][0]), "=r"(u[r][1]), "=r"(u[r][2]), "=r"(u[r][3]) : "r"(addr[r]) : "memory");
                     }
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float lo = fmaf(bf16_lo(u[r][j]), sc[2 * j], sh[2 * j]);
+                            const float hi = fmaf(bf16_hi(u[r][j]), sc[2 * j + 1], sh[2 * j + 1]);
+                            uint32_t h2 = pack_f16x2(lo, hi);
+                            if (silu) {
+                                uint32_t th;
+                                asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(h2));
+                                asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(h2) : "r"(h2), "r"(th));
+                            }
+                            u[r][j] = inside[r] ? h2 : 0u;   // the reference zero-pads AFTER GroupNorm+SiLU
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (row0 + 16 * r < HROWS)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[r]), "r"(u[r][0]), "r"(u[r][1]),
+                                         "r"(u[r][2]), "r"(u[r][3]) : "memory");
+                    }
                 }
                 // generic-proxy writes -> visible to the tensor core's async proxy, then signal the MMA warp
                 fence_proxy_async_smem();

@@ -279,11 +279,18 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
                     }
                     float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
                     OutT* optr = out_img + nc + j8;
+                    // all staging reads of the pass first (volatile accesses keep program order)
+                    float4 sv0[4], sv1[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t sp = stg + ((8 * i + rlane) * RF + j8) * 4;
-                        float4 v0 = lds128(sp);
-                        float4 v1 = lds128(sp + 16);
+                        sv0[i] = lds128(sp);
+                        sv1[i] = lds128(sp + 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 v0 = sv0[i];
+                        float4 v1 = sv1[i];
                         v0.x = fmaf(v0.x, P.alpha, b0.x); v0.y = fmaf(v0.y, P.alpha, b0.y);
                         v0.z = fmaf(v0.z, P.alpha, b0.z); v0.w = fmaf(v0.w, P.alpha, b0.w);
                         v1.x = fmaf(v1.x, P.alpha, b1.x); v1.y = fmaf(v1.y, P.alpha, b1.y);
