@@ -97,7 +97,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # VT_B200_LIB: development override (A/B builds of the same ABI)
+    return os.environ.get("VT_B200_LIB") or _build.LIB_PATH
 
 
 def load_library() -> C.CDLL:

@@ -17,6 +17,11 @@
 #pragma once
 #include "vt_igemm.cuh"
 
+#ifndef VT_TR_CFG
+#define VT_TR_CFG 0  // transposed-variant resource split: 0 = 3 halo / 3 weight stages / 8 epilogue warps,
+                     // 1 = 2 halo / 6 stages / 8 warps, 2 = 3 halo / 4 stages / 4 warps
+#endif
+
 namespace vt {
 
 // TR = false: accumulator rows = pixels (MT sub-tiles of 8x16), columns = BLOCK_N output channels.
@@ -34,12 +39,12 @@ struct Conv3Cfg {
     static constexpr int HHGT = PX_H + 2;             // halo height
     static constexpr int HROWS = HWID * HHGT;         // 128-byte rows per halo chunk
     static constexpr int HALO_BYTES = (HROWS * 128 + 1023) / 1024 * 1024;
-    static constexpr int NHALO = 3;
+    static constexpr int NHALO = (TR && VT_TR_CFG == 1) ? 2 : 3;
     static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;   // weight tile of one (tap, 64-channel chunk)
     // transposed (level 0, 2 channel chunks per tile): the epilogue is on the critical path -> two warps per
     // TMEM lane quadrant, paid for with one weight stage; deep-K layers keep four stages and four warps
-    static constexpr int BSTAGES = TR ? 3 : 4;
-    static constexpr int EPI_WARPS = TR ? 8 : 4;
+    static constexpr int BSTAGES = TR ? (VT_TR_CFG == 1 ? 6 : (VT_TR_CFG == 2 ? 4 : 3)) : 4;
+    static constexpr int EPI_WARPS = TR ? (VT_TR_CFG == 2 ? 4 : 8) : 4;
     static constexpr int XF_WARPS = 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
     static constexpr int COLS_PER_WARP = (TR ? 256 : BLOCK_N) / (EPI_WARPS / 4);  // TMEM columns each epilogue warp walks
