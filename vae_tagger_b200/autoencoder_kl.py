@@ -147,6 +147,7 @@ class AutoencoderKL(nn.Module):
         # "bf16" (tcgen05 path) or "fp32" (verification mode); VT_B200_PRECISION overrides the default
         self.precision = os.environ.get("VT_B200_PRECISION", "bf16")
         self.micro_batch = 0
+        self.single_lane = False  # True: micro-batches back to back on one stream (per-kernel timing runs)
         self._native_key = None
 
     # ------------------------------------------------------------------ state dict
@@ -196,7 +197,7 @@ class AutoencoderKL(nn.Module):
         """``vae.encode(x).latent_dist`` (diffusers_vae_loader.py:73, :79)."""
         ctx = self._sync_native(self._device_of(x))
         _, mean, logvar = ctx.encode(x, precision=self._precision(), sample=False, apply_scale_shift=False,
-                                     want_moments=True, micro_batch=self.micro_batch)
+                                     want_moments=True, micro_batch=self.micro_batch, single_lane=self.single_lane)
         dist = DiagonalGaussianDistribution(mean, logvar)
         if not return_dict:
             return (dist,)
@@ -209,7 +210,7 @@ class AutoencoderKL(nn.Module):
         what ``DiffusersVAEWrapper.encode`` (diffusers_vae_loader.py:78-86) computes."""
         ctx = self._sync_native(self._device_of(x))
         return ctx.encode(x, precision=self._precision(), sample=sample, apply_scale_shift=apply_scale_shift,
-                          seed=seed, noise=noise, micro_batch=self.micro_batch)
+                          seed=seed, noise=noise, micro_batch=self.micro_batch, single_lane=self.single_lane)
 
     def decode(self, z, return_dict: bool = True):
         raise NotImplementedError(
