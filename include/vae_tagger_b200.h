@@ -170,6 +170,10 @@ int vt_op_conv3_fused(vt_ctx* ctx, const float* x /*[N,Cin,H,W]*/, const float* 
                       const float* w /*[Cout,Cin,3,3]*/, const float* bias, const float* residual /*or NULL*/, int N,
                       int Cin, int H, int W, int Cout, float eps, int silu, float* out /*[N,Cout,H,W]*/,
                       double* stats /*[N,32,2] of out, or NULL*/, void* stream);
+/* fused attention, head_dim 512: out[n,tokens,512] = softmax(scale * q k^T) v + bias_v with
+ * qk = [n,tokens,1024] (q | k) and vt = [n,512,tokens] (v transposed); operands rounded to fp16 */
+int vt_op_flash_attention(vt_ctx* ctx, const float* qk, const float* vt, const float* bias_v, int n, int tokens,
+                          float scale, float* out, void* stream);
 int vt_op_gemm_nt(vt_ctx* ctx, const float* A /*[batch,M,K]*/, const float* B /*[batch or 1,N,K]*/,
                   const float* bias, int batch, int M, int N, int K, int b_batched, float alpha, int precision,
                   float* out /*[batch,M,N]*/, void* stream);

@@ -187,3 +187,20 @@ def test_conv3_fused_groupnorm_silu(ctx, case):
     want = torch.stack([grp.sum(-1), (grp * grp).sum(-1)], dim=-1)
     got = stats.cpu()
     assert torch.allclose(got, want, rtol=1e-4, atol=1e-3 * grp.shape[-1] ** 0.5), (got - want).abs().max().item()
+
+
+@pytest.mark.parametrize("n,tokens", [(1, 64), (2, 128), (1, 320), (2, 1024), (1, 4160)])
+def test_flash_attention_d512(ctx, n, tokens):
+    """Fused attention (head_dim 512) against softmax(q k^T / sqrt(512)) v + b_v in fp32 on fp16-rounded
+    operands.  Tolerance: P and O are rounded to fp16 inside the kernel (2^-11 relative each)."""
+    g = torch.Generator().manual_seed(tokens)
+    q = torch.randn(n, tokens, 512, generator=g) * 1.5
+    k = torch.randn(n, tokens, 512, generator=g) * 1.5
+    v = torch.randn(n, tokens, 512, generator=g)
+    bv = torch.randn(512, generator=g)
+    # make some rows sharply peaked so the running-maximum rescale path is exercised
+    k[:, tokens // 2] = q[:, 0] * 3.0
+    out = ctx.op_flash_attention(q, k, v, bv).cpu()
+    s_ = torch.matmul(rh(q), rh(k).transpose(1, 2)) / 512 ** 0.5
+    ref = torch.matmul(torch.softmax(s_, dim=-1), rh(v)) + bv
+    assert rel(out, ref) < 2e-3, (rel(out, ref), (out - ref).abs().max().item())

@@ -88,6 +88,7 @@ SYMBOLS = {
     "vt_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "vt_op_conv2d": (C.c_int, [_P, _P, _P, _P, _P, _P, _P] + [C.c_int] * 9 + [_P, _P, _P]),
     "vt_op_conv3_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, _P, _P, _P]),
+    "vt_op_flash_attention": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "vt_op_gemm_nt": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, _P, _P]),
     "vt_op_group_norm": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_int, _P, _P]),
     "vt_op_softmax_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
@@ -367,6 +368,20 @@ class Context:
                                               _ptr(residual), N, Cin, H, W, Cout, float(eps), int(silu), _ptr(out),
                                               _ptr(stats), _stream(self.device)))
         return (out, stats) if want_stats else out
+
+    def op_flash_attention(self, q, k, v, bias_v=None, scale=None):
+        """q, k, v: [n, tokens, 512] fp32 -> softmax(scale q k^T) v + bias_v, [n, tokens, 512] fp32."""
+        q = _f32c(q, self.device); k = _f32c(k, self.device); v = _f32c(v, self.device)
+        n, tokens, d = q.shape
+        qk = torch.cat([q, k], dim=2).contiguous()
+        vt = v.transpose(1, 2).contiguous()
+        bias_v = _f32c(bias_v, self.device) if bias_v is not None else None
+        out = torch.empty(n, tokens, d, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_op_flash_attention(self.h, _ptr(qk), _ptr(vt), _ptr(bias_v), n, tokens,
+                                                  float(scale if scale is not None else d ** -0.5), _ptr(out),
+                                                  _stream(self.device)))
+        return out
 
     def op_gemm_nt(self, A, B, bias=None, alpha=1.0, precision=PREC_BF16):
         A = _f32c(A, self.device); B = _f32c(B, self.device)

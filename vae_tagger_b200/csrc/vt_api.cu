@@ -298,6 +298,7 @@ struct EncRun {
     int stats_used = 0;
     int groups;
     int use_fused = 1;  // GroupNorm+SiLU fused into the 3x3 convs (VT_B200_NO_FUSED_GN=1 disables)
+    int use_flash = 1;  // fused attention kernel (VT_B200_NO_FLASH=1: score-matrix path)
 
     double* new_stats() {
         double* p = stats_base + static_cast<size_t>(stats_used) * n * groups * 2;
@@ -446,6 +447,8 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
     {
         const char* e = getenv("VT_B200_NO_FUSED_GN");
         R.use_fused = !(e && e[0] == '1');
+        const char* f = getenv("VT_B200_NO_FLASH");
+        R.use_flash = !(f && f[0] == '1');
     }
 
     // ---- conv_in: gather the 3x3x3 patches (K = 27 padded to 64) then one K chunk of contraction
@@ -516,6 +519,13 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
             VT_TRY(R.gemm(g, 0));
         }
         const float scale = 1.0f / sqrtf(static_cast<float>(C));
+        if (!fp32 && C == 512 && R.use_flash) {
+            // fused attention (vt_flash.cu): scores and probabilities never leave the SM
+            FlashOp f;
+            f.qk = QK; f.vt = Vt; f.bias_v = A.v.bias; f.out = O; f.n = n; f.tokens = static_cast<int>(tokens);
+            f.C = C; f.scale = scale;
+            VT_TRY(launch_flash_attention(f, s, c->prof));
+        } else
         for (int i0 = 0; i0 < n; i0 += ipc) {
             const int nb_img = std::min(ipc, n - i0);
             for (long long r0 = 0; r0 < tokens; r0 += rows_per_chunk) {
@@ -1076,6 +1086,25 @@ int vt_op_conv3_fused(vt_ctx* c, const float* x, const float* gamma, const float
     op.out = dout; op.out_fmt = FMT_F32; op.stats = stats;
     VT_TRY(launch_conv3_fused(op, s, c->prof));
     return launch_nhwc_to_nchw(dout, FMT_F32, out, N, Cout, HW, s);
+}
+
+int vt_op_flash_attention(vt_ctx* c, const float* qk, const float* vt, const float* bias_v, int n, int tokens,
+                          float scale, float* out, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(qk && vt && out, "null pointers");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t nqk = static_cast<size_t>(n) * tokens * 1024, nv = static_cast<size_t>(n) * 512 * tokens;
+    const size_t b_qk = align_up(nqk * 2, 1024), b_v = align_up(nv * 2, 1024), b_o = align_up(nv * 2, 1024);
+    VT_TRY(c->opws.ensure(b_qk + b_v + b_o));
+    char* p = static_cast<char*>(c->opws.p);
+    VT_TRY(launch_cast_f32_16(qk, p, FMT_F16, static_cast<long long>(nqk), s));
+    VT_TRY(launch_cast_f32_16(vt, p + b_qk, FMT_F16, static_cast<long long>(nv), s));
+    FlashOp f;
+    f.qk = p; f.vt = p + b_qk; f.bias_v = bias_v; f.out = p + b_qk + b_v; f.n = n; f.tokens = tokens; f.C = 512; f.scale = scale;
+    VT_TRY(launch_flash_attention(f, s, c->prof));
+    // widen fp16 [n*tokens][512] -> fp32 (layout kernel with one "pixel" per row)
+    VT_CHECK(static_cast<long long>(n) * tokens < 65536, "op entry point: n * tokens must be below 65536");
+    return launch_nhwc_to_nchw(p + b_qk + b_v, FMT_F16, out, n * tokens, 512, 1, s);
 }
 
 int vt_op_gemm_nt(vt_ctx* c, const float* A, const float* B, const float* bias, int batch, int M, int N, int K,

@@ -104,6 +104,22 @@ struct GemmOp {
 };
 int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof);
 
+// 16-bit tensor map, 128-byte swizzle, zero fill out of bounds (vt_igemm.cu)
+int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box);
+
+// Fused attention for head_dim 512 (vt_flash.cu): O = softmax(scale * Q K^T) V + bias_v, fp16 operands.
+//   qk: [n][tokens][2C] (q | k), vt: [n][C][tokens] (V transposed), out: [n][tokens][C] fp16
+struct FlashOp {
+    const void* qk = nullptr;
+    const void* vt = nullptr;
+    const float* bias_v = nullptr;
+    void* out = nullptr;
+    int n = 0, tokens = 0, C = 512;
+    float scale = 1.f;
+};
+int launch_flash_attention(const FlashOp& op, cudaStream_t stream, Profiler* prof);
+
 // 3x3 stride-1 conv with GroupNorm(32)+SiLU of the INPUT fused into the operand path (vt_conv3.cuh)
 struct Conv3FusedOp {
     const void* in = nullptr;   // raw activation, bf16 NHWC [N][H][W][Cin]
