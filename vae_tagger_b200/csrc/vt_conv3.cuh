@@ -17,11 +17,6 @@
 #pragma once
 #include "vt_igemm.cuh"
 
-#ifndef VT_TR_CFG
-#define VT_TR_CFG 0  // transposed-variant resource split: 0 = 3 halo / 3 weight stages / 8 epilogue warps,
-                     // 1 = 2 halo / 6 stages / 8 warps, 2 = 3 halo / 4 stages / 4 warps
-#endif
-
 namespace vt {
 
 // TR = false: accumulator rows = pixels (MT sub-tiles of 8x16), columns = BLOCK_N output channels.
@@ -39,13 +34,15 @@ struct Conv3Cfg {
     static constexpr int HHGT = PX_H + 2;             // halo height
     static constexpr int HROWS = HWID * HHGT;         // 128-byte rows per halo chunk
     static constexpr int HALO_BYTES = (HROWS * 128 + 1023) / 1024 * 1024;
-    static constexpr int NHALO = (TR && VT_TR_CFG == 1) ? 2 : 3;
+    static constexpr int NHALO = 3;
     static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;   // weight tile of one (tap, 64-channel chunk)
     // transposed (level 0, 2 channel chunks per tile): the epilogue is on the critical path -> two warps per
     // TMEM lane quadrant, paid for with one weight stage; deep-K layers keep four stages and four warps
-    static constexpr int BSTAGES = TR ? (VT_TR_CFG == 1 ? 6 : (VT_TR_CFG == 2 ? 4 : 3)) : 4;
-    static constexpr int EPI_WARPS = TR ? (VT_TR_CFG == 2 ? 4 : 8) : 4;
-    static constexpr int XF_WARPS = 4;
+    // (measured alternatives, 128->128 @1024^2 x2, no residual / residual: 3 halo + 3 stages + 8 epilogue + 4
+    // transform warps 535/605 us; 2 halo + 6 stages 554/607; 4 epilogue warps + 4 stages 507/720; this one 518/608)
+    static constexpr int BSTAGES = TR ? 3 : 4;
+    static constexpr int EPI_WARPS = TR ? 8 : 4;
+    static constexpr int XF_WARPS = TR ? 8 : 4;   // level 0 has 2 channel chunks per tile: the transform is on the critical path
     static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
     static constexpr int COLS_PER_WARP = (TR ? 256 : BLOCK_N) / (EPI_WARPS / 4);  // TMEM columns each epilogue warp walks
     static constexpr int PASSES_PER_SUB = COLS_PER_WARP / 32;
@@ -446,7 +443,8 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ------------------------------------------------------------ transform warps (6..9)
         const int xt = threadIdx.x - (64 + 32 * Cfg::EPI_WARPS);  // 0..127
         const int lc = xt & 7;        // logical 8-channel group of this thread (fixed)
-        const int rbase = xt >> 3;    // first halo row of this thread; then +16 per step
+        constexpr int RSTEP = 4 * Cfg::XF_WARPS;  // halo rows covered by the transform warps per step
+        const int rbase = xt >> 3;    // first halo row of this thread; then +RSTEP per step
         int hb = 0;
         uint32_t hphase = 0;
         int cur_img = -1;
@@ -495,13 +493,13 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 // accesses are volatile asm and keep their program order, so interleaving them per row would
                 // serialise four dependent chains)
 #pragma unroll 1
-                for (int row0 = rbase; row0 < HROWS; row0 += 64) {
+                for (int row0 = rbase; row0 < HROWS; row0 += 4 * RSTEP) {
                     uint32_t u[4][4];
                     uint32_t addr[4];
                     bool inside[4];
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const int row = row0 + 16 * r;
+                        const int row = row0 + RSTEP * r;
                         const int hy = row / HWID, hx = row - hy * HWID;
                         const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
                         inside[r] = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
@@ -528,7 +526,7 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        if (row0 + 16 * r < HROWS)
+                        if (row0 + RSTEP * r < HROWS)
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[r]), "r"(u[r][0]), "r"(u[r][1]),
                                          "r"(u[r][2]), "r"(u[r][3]) : "memory");
                     }
