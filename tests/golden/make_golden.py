@@ -158,3 +158,20 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def dump_cli_flags():
+    """CLI flag names of the reference entry points -> tests/golden/cli_flags.json"""
+    import json
+    import re
+
+    out = {}
+    for f in ("infer_full.py", "train_decoder.py", "infer_vae.py"):
+        src = open(os.path.join(REF, f)).read()
+        out[f] = sorted(set(re.findall(r'add_argument\(\s*"(--[a-z_0-9]+)"', src)))
+    with open(os.path.join(HERE, "cli_flags.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
+if __name__ == "__main__":
+    dump_cli_flags()

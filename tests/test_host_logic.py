@@ -115,3 +115,24 @@ def test_package_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_cli_flags_cover_the_reference_entry_points():
+    """Every flag of the reference's infer_full.py / train_decoder.py / infer_vae.py exists here (golden list
+    parsed from the reference sources by tests/golden/make_golden.py)."""
+    import os
+
+    from vae_tagger_b200 import infer_full, infer_vae, train_decoder
+
+    flags = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cli_flags.json")))
+    for name, mod in (("infer_full.py", infer_full), ("train_decoder.py", train_decoder), ("infer_vae.py", infer_vae)):
+        have = {a for act in mod.build_parser()._actions for a in act.option_strings}
+        missing = [f for f in flags[name] if f not in have]
+        assert not missing, (name, missing)
+    # defaults that define behaviour
+    a = infer_full.build_parser().parse_args(["--vae_checkpoint", "v", "--decoder_checkpoint", "d", "--image_path",
+                                              "i", "--tags_csv_path", "t"])
+    assert a.resolution == 1024 and a.confidence_threshold == 0.5 and a.use_attention and a.attention_heads == 8
+    t = train_decoder.build_parser().parse_args(["--vae_checkpoint", "v", "--json_path", "j", "--tags_csv_path", "t"])
+    assert t.learning_rate == 1e-3 and t.weight_decay == 1e-6 and t.lr_warmup_steps == 500 and t.max_grad_norm == 1.0
+    assert t.focal_alpha == 1.0 and t.focal_gamma == 2.0 and t.gradient_accumulation_steps == 1 and t.seed == 42
