@@ -167,8 +167,9 @@ int vt_op_conv2d(vt_ctx* ctx, const float* x /*[N,Cin,H,W]*/, const float* w /*[
 /* conv3x3(silu(group_norm_32(x))) + bias (+ residual) with the normalisation fused into the operand path;
  * x and residual are rounded to bf16 (raw storage format), weights and the normalised operand to fp16 */
 int vt_op_conv3_fused(vt_ctx* ctx, const float* x /*[N,Cin,H,W]*/, const float* gamma, const float* beta,
-                      const float* w /*[Cout,Cin,3,3]*/, const float* bias, const float* residual /*or NULL*/, int N,
-                      int Cin, int H, int W, int Cout, float eps, int silu, float* out /*[N,Cout,H,W]*/,
+                      const float* w /*[Cout,Cin,3,3]*/, const float* bias, const float* residual /*or NULL*/,
+                      const float* sc_x /*[N,Cs,H,W] or NULL*/, const float* sc_w /*[Cout,Cs,1,1] or NULL*/, int N,
+                      int Cin, int H, int W, int Cout, int Cs, float eps, int silu, float* out /*[N,Cout,H,W]*/,
                       double* stats /*[N,32,2] of out, or NULL*/, void* stream);
 /* fused attention, head_dim 512: out[n,tokens,512] = softmax(scale * q k^T) v + bias_v with
  * qk = [n,tokens,1024] (q | k) and vt = [n,512,tokens] (v transposed); operands rounded to fp16 */

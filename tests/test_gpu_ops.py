@@ -148,6 +148,23 @@ def test_softmax_rows(ctx, rows, cols, prec):
     assert rel(out, ref) < tol, rel(out, ref)
 
 
+def test_conv3_fused_with_shortcut_slab(ctx):
+    """conv2 of a channel-changing ResnetBlock2D: conv3x3(silu(gn(h))) + W_s x, the 1x1 shortcut as extra K slab."""
+    for n, cin, cs, h, w_, cout in ((1, 256, 128, 32, 24, 256), (2, 512, 256, 16, 16, 512)):
+        g = torch.Generator().manual_seed(cin + cs)
+        x = torch.randn(n, cin, h, w_, generator=g) * 1.3 - 0.2
+        gamma = torch.randn(cin, generator=g) * 0.5 + 1.0
+        beta = torch.randn(cin, generator=g) * 0.3
+        w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+        b = torch.randn(cout, generator=g)
+        scx = torch.randn(n, cs, h, w_, generator=g)
+        scw = torch.randn(cout, cs, 1, 1, generator=g) / cs ** 0.5
+        out = ctx.op_conv3_fused(x, gamma, beta, w, b, None, sc_x=scx, sc_w=scw).cpu()
+        t = F.silu(F.group_norm(r16(x), 32, gamma, beta, eps=1e-6))
+        ref = F.conv2d(rh(t), rh(w), b, padding=1) + F.conv2d(r16(scx), r16(scw))
+        assert rel(out, ref) < 1e-3, (cin, rel(out, ref))
+
+
 FUSED_CASES = [
     # N, Cin, H, W, Cout, residual
     (1, 128, 16, 16, 128, False),

@@ -87,7 +87,7 @@ SYMBOLS = {
     "vt_profile_enable": (C.c_int, [_P, C.c_int]),
     "vt_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "vt_op_conv2d": (C.c_int, [_P, _P, _P, _P, _P, _P, _P] + [C.c_int] * 9 + [_P, _P, _P]),
-    "vt_op_conv3_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, _P, _P, _P]),
+    "vt_op_conv3_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P] + [C.c_int] * 6 + [C.c_float, C.c_int, _P, _P, _P]),
     "vt_op_flash_attention": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "vt_op_gemm_nt": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, _P, _P]),
     "vt_op_group_norm": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_int, _P, _P]),
@@ -354,19 +354,23 @@ class Context:
                                          _stream(self.device)))
         return (out, stats) if want_stats else out
 
-    def op_conv3_fused(self, x, gamma, beta, w, bias=None, residual=None, eps=1e-6, silu=True, want_stats=False):
+    def op_conv3_fused(self, x, gamma, beta, w, bias=None, residual=None, eps=1e-6, silu=True, want_stats=False,
+                       sc_x=None, sc_w=None):
         x = _f32c(x, self.device); w = _f32c(w, self.device)
         gamma = _f32c(gamma, self.device); beta = _f32c(beta, self.device)
         bias = _f32c(bias, self.device) if bias is not None else None
         residual = _f32c(residual, self.device) if residual is not None else None
+        sc_x = _f32c(sc_x, self.device) if sc_x is not None else None
+        sc_w = _f32c(sc_w, self.device) if sc_w is not None else None
         N, Cin, H, W = x.shape
         Cout = w.shape[0]
+        Cs = sc_x.shape[1] if sc_x is not None else 0
         out = torch.empty(N, Cout, H, W, device=self.device, dtype=torch.float32)
         stats = torch.zeros(N, 32, 2, device=self.device, dtype=torch.float64) if want_stats else None
         with torch.cuda.device(self.device):
             _check(self.lib.vt_op_conv3_fused(self.h, _ptr(x), _ptr(gamma), _ptr(beta), _ptr(w), _ptr(bias),
-                                              _ptr(residual), N, Cin, H, W, Cout, float(eps), int(silu), _ptr(out),
-                                              _ptr(stats), _stream(self.device)))
+                                              _ptr(residual), _ptr(sc_x), _ptr(sc_w), N, Cin, H, W, Cout, Cs,
+                                              float(eps), int(silu), _ptr(out), _ptr(stats), _stream(self.device)))
         return (out, stats) if want_stats else out
 
     def op_flash_attention(self, q, k, v, bias_v=None, scale=None):

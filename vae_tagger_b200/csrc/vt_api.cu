@@ -345,8 +345,9 @@ struct EncRun {
                                s, c->prof);
     }
     int conv_fused(Act x, const double* st_x, const NormW& nw, int H, int Wd, const ConvW& w, const Act* residual,
-                   Act out, double* st) {
+                   Act out, double* st, const void* sc_in = nullptr) {
         Conv3FusedOp op;
+        op.sc_in = sc_in; op.Cs = sc_in ? w.Cs : 0;
         op.in = x.p; op.N = n; op.H = H; op.W = Wd; op.Cin = w.Cin; op.Cout = w.Cout; op.gn_stats = st_x;
         op.gamma = nw.gamma; op.beta = nw.beta; op.w = w.w16; op.bias = w.bias;
         if (residual) { op.residual = residual->p; op.residual_fp32 = residual->fmt == FMT_F32; }
@@ -355,8 +356,7 @@ struct EncRun {
     }
     // ResnetBlock2D: out = x (+shortcut) + conv2(silu(norm2(conv1(silu(norm1(x))))))
     // 16-bit mode: both GroupNorm+SiLU steps are fused into the operand path of the following 3x3 conv
-    // (vt_conv3.cuh); only the conv2 of a channel-changing block keeps the separate GroupNorm pass because
-    // its 1x1 shortcut is an extra K slab of the generic implicit-GEMM kernel.
+    // (vt_conv3.cuh), including the 1x1 shortcut slab of the channel-changing blocks.
     int resnet(const ResnetW& r, Act x, const double* st_x, int H, int Wd, int level, void* T, void* Hb, Act out,
                double* st_out) {
         (void)level;
@@ -366,6 +366,11 @@ struct EncRun {
         if (!fp32 && use_fused) {
             VT_TRY(conv_fused(x, st_x, r.norm1, H, Wd, r.conv1, nullptr, h, st_h));
             if (r.cin == r.cout) return conv_fused(h, st_h, r.norm2, H, Wd, r.conv2, &x, out, st_out);
+            if (r.cout >= 256) {
+                // channel-changing block: the 1x1 shortcut of the block input is an extra K slab of conv2
+                VT_CHECK(x.fmt == FMT_BF16, "shortcut operand must be bf16");
+                return conv_fused(h, st_h, r.norm2, H, Wd, r.conv2, nullptr, out, st_out, x.p);
+            }
             VT_TRY(gn(h, T, st_h, r.norm2, HW, r.cout, 1));
             return conv(T, H, Wd, r.conv2, 1, x.p, nullptr, out, st_out);
         }
@@ -1058,8 +1063,8 @@ int vt_op_conv2d(vt_ctx* c, const float* x, const float* w, const float* bias, c
 }
 
 int vt_op_conv3_fused(vt_ctx* c, const float* x, const float* gamma, const float* beta, const float* w,
-                      const float* bias, const float* residual, int N, int Cin, int H, int W, int Cout, float eps,
-                      int silu, float* out, double* stats, void* stream) {
+                      const float* bias, const float* residual, const float* sc_x, const float* sc_w, int N, int Cin,
+                      int H, int W, int Cout, int Cs, float eps, int silu, float* out, double* stats, void* stream) {
     VT_TRY(set_device(c));
     VT_CHECK(x && gamma && beta && w && out, "null pointers");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1067,15 +1072,22 @@ int vt_op_conv3_fused(vt_ctx* c, const float* x, const float* gamma, const float
     const size_t b_x = align_up(static_cast<size_t>(N) * HW * Cin * 2, 1024);
     const size_t b_o = align_up(static_cast<size_t>(N) * HW * Cout * 4, 1024);
     const size_t b_r = align_up(static_cast<size_t>(N) * HW * Cout * 2, 1024);
-    const size_t b_w = align_up(static_cast<size_t>(Cout) * 9 * Cin * 2, 1024);
+    VT_CHECK((sc_x == nullptr) == (sc_w == nullptr), "shortcut operand and weight go together");
+    if (!sc_x) Cs = 0;
+    const int Ktot = 9 * Cin + Cs;
+    const size_t b_w = align_up(static_cast<size_t>(Cout) * Ktot * 2, 1024);
     const size_t b_s = 1024 + static_cast<size_t>(N) * 64 * sizeof(double);
-    VT_TRY(c->opws.ensure(b_x + b_o + b_r + b_w + b_s));
+    const size_t b_c = align_up(static_cast<size_t>(N) * HW * std::max(Cs, 1) * 2, 1024);
+    VT_TRY(c->opws.ensure(b_x + b_o + b_r + b_w + b_s + b_c));
     char* p = static_cast<char*>(c->opws.p);
     void* dx = p; void* dout = p + b_x; void* dres = p + b_x + b_o; void* dw = p + b_x + b_o + b_r;
     double* st_in = reinterpret_cast<double*>(p + b_x + b_o + b_r + b_w);
+    void* dsc = p + b_x + b_o + b_r + b_w + b_s;
     VT_TRY(launch_nchw_to_nhwc(x, dx, FMT_BF16, N, Cin, HW, s));
     if (residual) VT_TRY(launch_nchw_to_nhwc(residual, dres, FMT_BF16, N, Cout, HW, s));
-    pack_weight_kernel<FMT_F16><<<256, 256, 0, s>>>(w, dw, Cout, Cin, 3, 9 * Cin, 0);
+    if (sc_x) VT_TRY(launch_nchw_to_nhwc(sc_x, dsc, FMT_BF16, N, Cs, HW, s));
+    pack_weight_kernel<FMT_F16><<<256, 256, 0, s>>>(w, dw, Cout, Cin, 3, Ktot, 0);
+    if (sc_w) pack_weight_kernel<FMT_BF16><<<256, 256, 0, s>>>(sc_w, dw, Cout, Cs, 1, Ktot, 9 * Cin);
     VT_CUDA(cudaGetLastError());
     VT_CUDA(cudaMemsetAsync(st_in, 0, static_cast<size_t>(N) * 64 * sizeof(double), s));
     VT_TRY(launch_gn_stats(dx, 0, st_in, N, HW, Cin, 32, s, c->prof));
@@ -1083,7 +1095,7 @@ int vt_op_conv3_fused(vt_ctx* c, const float* x, const float* gamma, const float
     Conv3FusedOp op;
     op.in = dx; op.N = N; op.H = H; op.W = W; op.Cin = Cin; op.Cout = Cout; op.gn_stats = st_in; op.gamma = gamma;
     op.beta = beta; op.eps = eps; op.silu = silu; op.w = dw; op.bias = bias; op.residual = residual ? dres : nullptr;
-    op.out = dout; op.out_fmt = FMT_F32; op.stats = stats;
+    op.out = dout; op.out_fmt = FMT_F32; op.stats = stats; op.sc_in = sc_x ? dsc : nullptr; op.Cs = Cs;
     VT_TRY(launch_conv3_fused(op, s, c->prof));
     return launch_nhwc_to_nchw(dout, FMT_F32, out, N, Cout, HW, s);
 }

@@ -263,7 +263,7 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
 template <int BLOCK_N, int MT, bool TR>
 __global__ void __launch_bounds__(Conv3Cfg<BLOCK_N, MT, TR>::THREADS, 1)
 conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ IgemmParams P) {
+                   const __grid_constant__ CUtensorMap tmS, const __grid_constant__ IgemmParams P) {
     using Cfg = Conv3Cfg<BLOCK_N, MT, TR>;
     constexpr int NHALO = Cfg::NHALO, BST = Cfg::BSTAGES, HWID = Cfg::HWID, HROWS = Cfg::HROWS;
 
@@ -289,10 +289,15 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t tiles_per_img = static_cast<uint32_t>(P.tiles_x * P.tiles_y);
     const uint32_t total_tiles = static_cast<uint32_t>(P.NB) * tiles_per_img * static_cast<uint32_t>(P.n_blocks);
     const int nchunks = P.cin_chunks;
+    // 1x1 shortcut of a channel-changing block: extra items whose A tile is the raw (bf16, untransformed)
+    // block input and whose weight columns follow the nine taps (non-transposed variant only)
+    const int sc_chunks = TR ? 0 : P.sc_chunks;
+    const int items = nchunks + sc_chunks;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmS);
         for (int i = 0; i < NHALO; ++i) {
             mbar_init(&halo_full[i], 1);
             mbar_init(&halo_ready[i], Cfg::XF_WARPS);
@@ -341,23 +346,32 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 int nb, x0, y0, img;
                 decode(h_tile, nb, x0, y0, img);
                 mbar_wait(&halo_free[hb], hphase ^ 1);
-                mbar_arrive_expect_tx(&halo_full[hb], HROWS * 128);
-                tma_load_5d(s_halo + hb * Cfg::HALO_BYTES, &tmA, &halo_full[hb], h_chunk * IGEMM_BLOCK_K, x0 - 1, 0, y0 - 1,
-                            img);
+                if (h_chunk < nchunks) {
+                    mbar_arrive_expect_tx(&halo_full[hb], HROWS * 128);
+                    tma_load_5d(s_halo + hb * Cfg::HALO_BYTES, &tmA, &halo_full[hb], h_chunk * IGEMM_BLOCK_K, x0 - 1, 0,
+                                y0 - 1, img);
+                } else {   // shortcut operand: the plain 8x16 pixel tile, 128 rows of 128 bytes
+                    mbar_arrive_expect_tx(&halo_full[hb], 128 * 128);
+                    tma_load_5d(s_halo + hb * Cfg::HALO_BYTES, &tmS, &halo_full[hb], (h_chunk - nchunks) * IGEMM_BLOCK_K,
+                                x0, 0, y0, img);
+                }
                 if (++hb == NHALO) { hb = 0; hphase ^= 1; }
-                if (++h_chunk == nchunks) { h_chunk = 0; h_tile += gridDim.x; }
+                if (++h_chunk == items) { h_chunk = 0; h_tile += gridDim.x; }
             };
             issue_halo();
             for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int nb, x0, y0, img;
                 decode(tile, nb, x0, y0, img);
                 const int n0 = nb * BLOCK_N;
-                for (int c = 0; c < nchunks; ++c) {
+                for (int c = 0; c < items; ++c) {
                     issue_halo();
-                    for (int tap = 0; tap < 9; ++tap) {
+                    const int ntaps = c < nchunks ? 9 : 1;
+                    for (int tap = 0; tap < ntaps; ++tap) {
                         mbar_wait(&b_empty[bs], bphase ^ 1);
                         mbar_arrive_expect_tx(&b_full[bs], Cfg::B_BYTES);
-                        tma_load_3d(s_b + bs * Cfg::B_BYTES, &tmB, &b_full[bs], tap * P.gn_C + c * IGEMM_BLOCK_K, n0, 0);
+                        const int kb = c < nchunks ? tap * P.gn_C + c * IGEMM_BLOCK_K
+                                                   : 9 * P.gn_C + (c - nchunks) * IGEMM_BLOCK_K;
+                        tma_load_3d(s_b + bs * Cfg::B_BYTES, &tmB, &b_full[bs], kb, n0, 0);
                         if (++bs == BST) { bs = 0; bphase ^= 1; }
                     }
                 }
@@ -415,6 +429,27 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         if (++bs == BST) { bs = 0; bphase ^= 1; }
                     }
                     if (++hb == NHALO) { hb = 0; hphase ^= 1; }
+                }
+                if constexpr (!TR) {
+                    constexpr uint32_t idesc_sc = umma_idesc_16(IGEMM_BLOCK_M, BLOCK_N, false);   // bf16 x bf16
+                    const uint64_t dx_base = umma_desc_k_sw128(smem_u32(s_halo));                 // plain tile: 1024 B groups
+                    for (int c = 0; c < sc_chunks; ++c) {
+                        mbar_wait(&halo_ready[hb], hphase);
+                        mbar_wait(&b_full[bs], bphase);
+                        tc_fence_after();
+                        const uint64_t dx = dx_base + static_cast<uint64_t>(hb * (Cfg::HALO_BYTES >> 4));
+                        const uint64_t dw = dw_base + static_cast<uint64_t>(bs * (Cfg::B_BYTES >> 4));
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < IGEMM_BLOCK_K / 16; ++k)
+                                umma_bf16_ss(tmem_d, dx + 2 * k, dw + 2 * k, idesc_sc, 1u);
+                            umma_commit(&b_empty[bs]);
+                            umma_commit(&halo_free[hb]);
+                        }
+                        __syncwarp();
+                        if (++bs == BST) { bs = 0; bphase ^= 1; }
+                        if (++hb == NHALO) { hb = 0; hphase ^= 1; }
+                    }
                 }
                 if (elect_one()) umma_commit(&tfull_bar[acc]);
                 __syncwarp();
@@ -533,6 +568,13 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
                 // generic-proxy writes -> visible to the tensor core's async proxy, then signal the MMA warp
                 fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&halo_ready[hb]);
+                if (++hb == NHALO) { hb = 0; hphase ^= 1; }
+            }
+            for (int c = 0; c < sc_chunks; ++c) {
+                // shortcut operand: raw bf16 tile, nothing to rewrite -- hand it straight to the MMA warp
+                mbar_wait(&halo_full[hb], hphase);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&halo_ready[hb]);
                 if (++hb == NHALO) { hb = 0; hphase ^= 1; }

@@ -195,7 +195,8 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
 }
 
 template <int BLOCK_N, int MT, bool TR>
-static int launch_conv3_variant(const CUtensorMap& a, const CUtensorMap& b, const IgemmParams& P, cudaStream_t stream) {
+static int launch_conv3_variant(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sc, const IgemmParams& P,
+                                cudaStream_t stream) {
     using Cfg = Conv3Cfg<BLOCK_N, MT, TR>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -205,7 +206,7 @@ static int launch_conv3_variant(const CUtensorMap& a, const CUtensorMap& b, cons
     }
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y * P.n_blocks;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    conv3_fused_kernel<BLOCK_N, MT, TR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, b, P);
+    conv3_fused_kernel<BLOCK_N, MT, TR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, b, sc, P);
     VT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -245,20 +246,24 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
     VT_CHECK(1LL * H * W * op.Cout < (1LL << 31), "conv output of one image exceeds 2^31 elements");
     P.gn_stats = op.gn_stats; P.gn_gamma = op.gamma; P.gn_beta = op.beta;
     P.gn_C = op.Cin; P.gn_gs = op.Cin / 32; P.gn_eps = op.eps; P.gn_silu = op.silu; P.cin_chunks = op.Cin / 64;
+    VT_CHECK(op.sc_in == nullptr || (!tr && op.Cs % 64 == 0 && op.Cs > 0), "fused conv: shortcut slab needs Cout >= 256 and Cs % 64 == 0");
+    P.sc_chunks = op.sc_in ? op.Cs / 64 : 0;
 
-    CUtensorMap a, b;
+    CUtensorMap a, b, sc;
     VT_TRY(make_act_map(&a, op.in, op.N, H, W, op.Cin, 1, pxw + 2, pxh + 2));
+    if (op.sc_in) VT_TRY(make_act_map(&sc, op.sc_in, op.N, H, W, op.Cs, 1, pxw, pxh));
+    else sc = a;
     {
-        const int Ktot = 9 * op.Cin;
+        const int Ktot = 9 * op.Cin + (op.sc_in ? op.Cs : 0);
         uint64_t dims[3] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(op.Cout), 1};
         uint64_t str[2] = {2ull * Ktot, 2ull * Ktot * op.Cout};
         uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
         VT_TRY(make_tmap(&b, op.w, 3, dims, str, box));
     }
-    const double flops = 2.0 * op.N * H * W * static_cast<double>(op.Cout) * 9 * op.Cin;
+    const double flops = 2.0 * op.N * H * W * static_cast<double>(op.Cout) * (9 * op.Cin + (op.sc_in ? op.Cs : 0));
     const double bytes = 2.0 * op.N * H * W * (1.0 * op.Cin + op.Cout);
     profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
-    int rc = tr ? launch_conv3_variant<128, 1, true>(a, b, P, stream) : launch_conv3_variant<256, 1, false>(a, b, P, stream);
+    int rc = tr ? launch_conv3_variant<128, 1, true>(a, b, sc, P, stream) : launch_conv3_variant<256, 1, false>(a, b, sc, P, stream);
     profiler_end(prof, KC_IGEMM, stream);
     return rc;
 }

@@ -71,6 +71,7 @@ struct IgemmParams {
     float gn_eps;
     int gn_silu;
     int cin_chunks;          // Cin / 64
+    int sc_chunks;           // Cs / 64: 1x1 shortcut slab (0 = none)
 };
 
 template <int BLOCK_N, int MT>  // MT = 128-row sub-tiles per CTA tile (2: two pixel tiles share every weight chunk)

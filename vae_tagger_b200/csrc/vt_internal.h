@@ -129,7 +129,9 @@ struct Conv3FusedOp {
     const float* beta = nullptr;       // [Cin]
     float eps = 1e-6f;
     int silu = 1;
-    const void* w = nullptr;           // fp16 [Cout][9*Cin], tap-major then channel
+    const void* w = nullptr;           // fp16 [Cout][9*Cin (+Cs bf16 shortcut columns)], tap-major then channel
+    const void* sc_in = nullptr;       // optional 1x1 shortcut operand, raw bf16 [N][H][W][Cs] (Cout >= 256 only)
+    int Cs = 0;
     const float* bias = nullptr;
     const void* residual = nullptr;    // [N][H][W][Cout]
     int residual_fp32 = 0;
