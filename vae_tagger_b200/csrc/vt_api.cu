@@ -460,10 +460,18 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
     const char* img = static_cast<const char*>(a->images);
     const size_t img_stride = a->in_fmt == VT_IN_U8_NHWC ? static_cast<size_t>(H) * Wd * 3
                                                          : static_cast<size_t>(H) * Wd * 3 * sizeof(float);
-    VT_TRY(launch_im2col3x3(img + img_stride * img0, a->in_fmt, Hb, R.opd_fmt(), n, H, Wd, s, c->prof));
     double* st_x = R.new_stats();
     Act X{Xp, R.raw_fmt()};
-    {
+    const bool convin_direct = !fp32 && cfg.block_out_channels[0] == 128 && X.fmt == FMT_BF16 && c->conv_in.f16 &&
+                               !(getenv("VT_B200_NO_CONVIN") && getenv("VT_B200_NO_CONVIN")[0] == '1');
+    if (convin_direct) {
+        // operand rows built in shared memory from the image itself (vt_convin.cuh)
+        ConvInOp op;
+        op.img = img + img_stride * img0; op.in_fmt = a->in_fmt; op.N = n; op.H = H; op.W = Wd;
+        op.w = c->conv_in.w16; op.bias = c->conv_in.bias; op.out = X.p; op.stats = st_x;
+        VT_TRY(launch_conv_in(op, s, c->prof));
+    } else {
+        VT_TRY(launch_im2col3x3(img + img_stride * img0, a->in_fmt, Hb, R.opd_fmt(), n, H, Wd, s, c->prof));
         ConvW w = c->conv_in;  // viewed as a 1x1 conv over the 64-wide gathered patches
         w.Cin = 64; w.ksize = 1; w.Cs = 0;
         VT_TRY(R.conv(Hb, H, Wd, w, 1, nullptr, nullptr, X, st_x));

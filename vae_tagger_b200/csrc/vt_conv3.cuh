@@ -78,7 +78,6 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
     const int q = warp & 3;                   // TMEM lane quadrant = channels 32q .. 32q+31 of the n-block
     const uint32_t stg = smem_u32(staging_all + ew * 32 * RF);
     const int et = threadIdx.x - 64;
-    const int psub = lane >> 2;               // phase B: pixel x inside the 8-pixel row
     const int cgrp = lane & 3;                // phase B: 8-channel group inside the warp's 32 channels
     const int swz_a = 8 * ((lane >> 3) & 3);  // phase A: column swizzle of this thread's staging row
     constexpr int NPASS = Cfg::PASSES_PER_SUB;             // 32-pixel passes per warp
@@ -132,31 +131,49 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
         }
         const long long img_off = static_cast<long long>(img) * P.out_bstride + ch0;
         OutT* out_img = static_cast<OutT*>(P.out) + img_off;
-        const int px = x0 + psub;
-        const bool x_ok = px < P.W && ch_ok;
+        // phase B lane mapping: four consecutive pixel columns (one 16-byte staging read per channel) of one
+        // image row: column 4*pq + j = 8*row + x  ->  row = pq >> 1, x = 4 * (pq & 1) + j
+        const int pq = lane >> 2;
+        const int pxb = x0 + 4 * (pq & 1);
         float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
 
+        if (RES == 1 && tile + gridDim.x < total_tiles) {
+            // pull the residual rows of this CTA's NEXT tile into L2 now (one pixel = 256 B per thread): the
+            // register loads below then hit L2 instead of paying the HBM round trip inside a pass
+            int nb2, x2, y2, img2;
+            decode(tile + gridDim.x, nb2, x2, y2, img2);
+            const int ppx = x2 + (et & 7), ppy = y2 + (et >> 3);
+            if (ppx < P.W && ppy < P.H) {
+                const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(P.residual) +
+                                          static_cast<long long>(img2) * P.out_bstride + nb2 * 128 +
+                                          (ppy * P.W + ppx) * ld;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 64));
+            }
+        }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
         for (int pc = pc0; pc < pc0 + NPASS; ++pc) {   // 32 pixels = image rows y0+4pc .. +3
+            const int py = y0 + 4 * pc + (pq >> 1);
+            const bool y_ok = py < P.H && ch_ok;
+            const int row_off = (py * P.W + pxb) * ld;
             // residual prefetch for the 4 pixels of this lane in this pass
             uint4 rlo[4], rhi[4];
             if (RES != 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int py = y0 + 4 * pc + i;
-                    rlo[i] = make_uint4(0u, 0u, 0u, 0u);
-                    rhi[i] = rlo[i];
-                    if (x_ok && py < P.H) {
-                        const int off = (py * P.W + px) * ld;
+                for (int j = 0; j < 4; ++j) {
+                    rlo[j] = make_uint4(0u, 0u, 0u, 0u);
+                    rhi[j] = rlo[j];
+                    if (y_ok && pxb + j < P.W) {
+                        const int off = row_off + j * ld;
                         if (RES == 1) {
-                            rlo[i] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.residual) + img_off + off));
+                            rlo[j] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.residual) + img_off + off));
                         } else {
                             const float* rp = static_cast<const float*>(P.residual) + img_off + off;
-                            rlo[i] = __ldg(reinterpret_cast<const uint4*>(rp));
-                            rhi[i] = __ldg(reinterpret_cast<const uint4*>(rp + 4));
+                            rlo[j] = __ldg(reinterpret_cast<const uint4*>(rp));
+                            rhi[j] = __ldg(reinterpret_cast<const uint4*>(rp + 4));
                         }
                     }
                 }
@@ -178,21 +195,19 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
                            __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
             }
             __syncwarp();
-            // ---- phase B: (pixel, 8 channels) per lane; all staging reads of the pass are issued first
+            // ---- phase B: 4 pixels x 8 channels per lane; one 16-byte staging read per channel (the column
+            // swizzle of phase A makes the eight lanes of a quarter-warp hit eight different bank groups)
             float vv[4][8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int col = (8 * i + psub) ^ (8 * cgrp);
+            {
+                const uint32_t src = stg + ((cgrp * 8) * RF + ((4 * pq) ^ (8 * cgrp))) * 4;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    float t;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(stg + ((cgrp * 8 + e) * RF + col) * 4) : "memory");
-                    vv[i][e] = t;
+                    const float4 t = lds128(src + e * RF * 4);
+                    vv[0][e] = t.x; vv[1][e] = t.y; vv[2][e] = t.z; vv[3][e] = t.w;
                 }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int py = y0 + 4 * pc + i;
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = vv[i][e];
@@ -207,14 +222,14 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
                     v[0] += __uint_as_float(a.x); v[1] += __uint_as_float(a.y); v[2] += __uint_as_float(a.z); v[3] += __uint_as_float(a.w);
                     v[4] += __uint_as_float(b.x); v[5] += __uint_as_float(b.y); v[6] += __uint_as_float(b.z); v[7] += __uint_as_float(b.w);
                 }
-                const bool ok = x_ok && py < P.H;
+                const bool ok = y_ok && pxb + i < P.W;
                 if (STATS && ok) {
                     s_lo += (v[0] + v[1]) + (v[2] + v[3]);
                     q_lo = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], q_lo))));
                     s_hi += (v[4] + v[5]) + (v[6] + v[7]);
                     q_hi = fmaf(v[4], v[4], fmaf(v[5], v[5], fmaf(v[6], v[6], fmaf(v[7], v[7], q_hi))));
                 }
-                OutT* o = out_img + (py * P.W + px) * ld;
+                OutT* o = out_img + row_off + i * ld;
                 if (OUT_F32) {
                     if (ok) {
                         reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);

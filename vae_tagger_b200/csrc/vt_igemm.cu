@@ -5,6 +5,7 @@
 #include <mutex>
 
 #include "vt_conv3.cuh"
+#include "vt_convin.cuh"
 #include "vt_igemm.cuh"
 #include "vt_internal.h"
 
@@ -192,6 +193,46 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     int rc = dispatch(block_n, a0, a1, b, P, stream);
     profiler_end(prof, KC_IGEMM, stream);
     return rc;
+}
+
+int launch_conv_in(const ConvInOp& op, cudaStream_t stream, Profiler* prof) {
+    VT_CHECK(op.img && op.w && op.out, "conv_in: null operand");
+    VT_CHECK(1LL * op.H * op.W * 128 < (1LL << 31), "conv_in output of one image exceeds 2^31 elements");
+    IgemmParams P{};
+    P.W = op.W; P.H = op.H; P.NB = op.N;
+    P.tw = 128; P.th = 1; P.tw_log2 = 7;          // tile = 2 x 128 consecutive pixels of one image row
+    P.sub_dx = 1; P.sub_dy = 0;
+    P.ax1 = 8; P.ay1 = 0; P.ax2 = 16; P.ay2 = 0;
+    P.tiles_x = (op.W + 255) / 256;
+    P.tiles_y = op.H;
+    P.n_total = 128; P.n_blocks = 1;
+    P.out_fmt = FMT_BF16;
+    P.group_size = op.stats ? 4 : 0;
+    P.alpha = 1.f;
+    P.bias = op.bias; P.out = op.out; P.ld_out = 128;
+    P.out_bstride = 1LL * op.H * op.W * 128; P.stats = op.stats;
+    CUtensorMap b;
+    {
+        uint64_t dims[3] = {64, 128, 1};
+        uint64_t str[2] = {128, 128 * 128};
+        uint32_t box[3] = {64, 128, 1};
+        VT_TRY(make_tmap(&b, op.w, 3, dims, str, box));
+    }
+    ConvInParams Q{op.img, op.in_fmt};
+    static bool attr_set = false;
+    if (!attr_set) {
+        VT_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvInCfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y;
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    const double flops = 2.0 * op.N * op.H * op.W * 128.0 * 27.0;
+    const double bytes = 1.0 * op.N * op.H * op.W * ((op.in_fmt ? 3.0 : 12.0) + 256.0);
+    profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
+    conv_in_kernel<<<grid, ConvInCfg::THREADS, ConvInCfg::SMEM_BYTES, stream>>>(b, P, Q);
+    profiler_end(prof, KC_IGEMM, stream);
+    VT_CUDA(cudaGetLastError());
+    return 0;
 }
 
 template <int BLOCK_N, int MT, bool TR>

@@ -233,7 +233,25 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
             run_img = geo.img; run_nb = geo.nb;
         }
         const uint32_t next_tile = tile + gridDim.x;
-        if (next_tile < total_tiles) geometry(next_tile, ngeo);
+        if (next_tile < total_tiles) {
+            geometry(next_tile, ngeo);
+            if (RES == 1) {
+                // pull the residual rows of the next tile into L2 (the four lanes that share an accumulator row
+                // split that row's 128-byte lines): the per-pass register loads then never wait on HBM
+                constexpr int LINES = Cfg::COLS_PER_WARP / 64;
+                const int nc0 = ngeo.nb * BLOCK_N + col_base + (lane & 3) * 64;
+                if ((lane & 3) < LINES && nc0 < P.n_total) {
+                    const __nv_bfloat16* rb = static_cast<const __nv_bfloat16*>(P.residual) +
+                                              static_cast<long long>(ngeo.img) * P.out_bstride + nc0;
+#pragma unroll
+                    for (int t = 0; t < MT; ++t)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if ((ngeo.vmask[t] >> i) & 1u)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(rb + ngeo.off0[t] + (i & 1) * step1 + (i >> 1) * step2));
+                }
+            }
+        }
         OutT* out_img = static_cast<OutT*>(P.out) + static_cast<long long>(geo.img) * P.out_bstride;
 
         mbar_wait(&tfull_bar[acc], acc_phase);

@@ -82,6 +82,19 @@ struct ConvOp {
 };
 int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof);
 
+// conv_in (3 -> 128, 3x3, pad 1) straight from the image batch: the operand rows are built in shared
+// memory by gather warps (vt_convin.cuh), no patch matrix in HBM
+struct ConvInOp {
+    const void* img = nullptr;  // [N][3][H][W] fp32 or [N][H][W][3] u8
+    int in_fmt = 0;             // VT_IN_F32_NCHW / VT_IN_U8_NHWC
+    int N = 0, H = 0, W = 0;
+    const void* w = nullptr;    // [128][64] fp16, k = (kh*3+kw)*3+c, k >= 27 zero
+    const float* bias = nullptr;
+    void* out = nullptr;        // [N][H][W][128] bf16
+    double* stats = nullptr;    // [N][32][2] or null
+};
+int launch_conv_in(const ConvInOp& op, cudaStream_t stream, Profiler* prof);
+
 struct GemmOp {
     // D[b][m][n] = alpha * sum_k A[b?][m][k] * B[b?][n][k] (+ bias[n]) (+ residual[b][m][n])
     // element type of A / B / residual: bf16 (tcgen05 path) or fp32 (launch_gemm_fp32)
