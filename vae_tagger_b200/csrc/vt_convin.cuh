@@ -137,28 +137,58 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             const int x0 = tx * 256;
             __half* strip = strips + (it & 1) * (Cfg::STRIP_ALLOC / 4);
             // ---- image rows y-1 .. y+1, columns x0-1 .. x0+256, three channels -> fp16 strip [kh*3+c][x]
+            // (all loads of a tile are issued before the first is used: one L2 round trip per tile, not one per element)
             if (Q.in_fmt == 0) {
                 const float* src = static_cast<const float*>(Q.img) + 3LL * img * plane;
-                for (int e = gt; e < 9 * 258; e += NG) {
-                    const int rowid = e / 258, xx = e - rowid * 258;
+                float v[27];
+#pragma unroll
+                for (int rowid = 0; rowid < 9; ++rowid) {
                     const int kh = rowid / 3, c = rowid - kh * 3;
-                    const int gy = y + kh - 1, gx = x0 + xx - 1;
-                    float v = 0.f;
-                    if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) v = __ldg(src + c * plane + static_cast<long long>(gy) * P.W + gx);
-                    strip[rowid * SW + xx] = __float2half_rn(v);
+                    const int gy = y + kh - 1;
+                    const bool y_ok = gy >= 0 && gy < P.H;
+                    const float* rowp = src + c * plane + static_cast<long long>(gy) * P.W + (x0 - 1);
+#pragma unroll
+                    for (int part = 0; part < 3; ++part) {
+                        const int xx = gt + NG * part, gx = x0 + xx - 1;
+                        float t = 0.f;
+                        if (y_ok && xx < 258 && gx >= 0 && gx < P.W) t = __ldg(rowp + xx);
+                        v[rowid * 3 + part] = t;
+                    }
                 }
+#pragma unroll
+                for (int rowid = 0; rowid < 9; ++rowid)
+#pragma unroll
+                    for (int part = 0; part < 3; ++part) {
+                        const int xx = gt + NG * part;
+                        if (xx < 258) strip[rowid * SW + xx] = __float2half_rn(v[rowid * 3 + part]);
+                    }
             } else {
                 const unsigned char* src = static_cast<const unsigned char*>(Q.img) + 3LL * img * plane;
-                for (int e = gt; e < 3 * 774; e += NG) {
-                    const int kh = e / 774, b = e - kh * 774;
-                    const int xx = b / 3, c = b - xx * 3;
-                    const int gy = y + kh - 1, gx = x0 + xx - 1;
-                    float v = 0.f;
-                    if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) {
-                        const float u = static_cast<float>(__ldg(src + (static_cast<long long>(gy) * P.W + gx) * 3 + c));
-                        v = (u / 255.0f - 0.5f) / 0.5f;
+                unsigned char u[21];
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int gy = y + kh - 1;
+                    const bool y_ok = gy >= 0 && gy < P.H;
+                    const unsigned char* rowp = src + (static_cast<long long>(gy) * P.W + (x0 - 1)) * 3;
+#pragma unroll
+                    for (int part = 0; part < 7; ++part) {
+                        const int b = gt + NG * part, xx = b / 3, gx = x0 + xx - 1;
+                        unsigned char t = 0;
+                        if (y_ok && b < 774 && gx >= 0 && gx < P.W) t = __ldg(rowp + b);
+                        u[kh * 7 + part] = t;
                     }
-                    strip[(kh * 3 + c) * SW + xx] = __float2half_rn(v);
+                }
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int gy = y + kh - 1;
+                    const bool y_ok = gy >= 0 && gy < P.H;
+#pragma unroll
+                    for (int part = 0; part < 7; ++part) {
+                        const int b = gt + NG * part, xx = b / 3, c = b - xx * 3, gx = x0 + xx - 1;
+                        const bool ok = y_ok && gx >= 0 && gx < P.W;
+                        const float val = ok ? (static_cast<float>(u[kh * 7 + part]) / 255.0f - 0.5f) / 0.5f : 0.f;
+                        if (b < 774) strip[(kh * 3 + c) * SW + xx] = __float2half_rn(val);
+                    }
                 }
             }
             asm volatile("bar.sync 3, %0;" ::"n"(NG) : "memory");

@@ -3,11 +3,18 @@
 //   O = softmax(scale * Q K^T) V + b_v          (fp16 operands, fp32 accumulation in TMEM)
 //
 // One CTA = 128 queries x one half (256 columns) of d_v, looping over 128-key tiles:
-//   S(j)   = Q K_j^T            tcgen05.mma M=128 N=128, K = 512 streamed as 8 chunks of (Q_c, K_c)
-//   P(j)   = exp2(c*S - m)      4 softmax warps, one query row per thread (no shuffles), fp16 -> smem
-//   O     += P(j) V_j           tcgen05.mma M=128 N=256, K = 128
-// TMEM: two S buffers (2 x 128 columns) + O (256 columns) = 512 columns: that is why d_v is split over
+//   S(j)   = Q K_j^T            tcgen05.mma M=128 N=128, K = 512: Q resident in shared memory (8 chunks),
+//                               K_j streamed as 8 chunks of 128 keys x 64 dims
+//   P(j)   = exp2(c*S - m)      8 softmax warps: a query row is owned by two threads (64 keys each, the row
+//                               maximum is exchanged through shared memory); fp16 P is written back into
+//                               TENSOR MEMORY over its own S buffer (two values per column)
+//   O     += P(j) V_j           tcgen05.mma with the A operand in tensor memory, M=128 N=128 per d_v quarter,
+//                               V_j streamed as 4 chunks of 128 d_v rows x 64 keys
+// TMEM: two S/P buffers (2 x 128 columns) + O (256 columns) = 512 columns: that is why d_v is split over
 // two CTAs (an O tile of 128 x 512 fp32 alone would fill TMEM) -- QK^T is computed twice, PV once.
+// Shared memory: Q 128 KB + one ring of six 16 KB chunks carrying K and V in consumption order.  The first
+// version re-streamed Q with every key tile and staged P through shared memory: 320 KB of L2->SM traffic
+// and ~700 KB of shared-memory traffic per key tile, which (not the tensor pipe) set its speed.
 // The running maximum is only raised when a row's new maximum exceeds it by more than 2^8 (lazy
 // rescale: P stays within fp16 range, O is rescaled in TMEM only then).  Scores never touch HBM.
 #include "vt_internal.h"
@@ -21,13 +28,14 @@ constexpr int FQ = 128;                 // queries per CTA
 constexpr int FK = 128;                 // keys per tile
 constexpr int FD = 512;                 // head dim
 constexpr int FDV = 256;                // d_v columns per CTA
-constexpr int QK_STAGE = 2 * 16384;     // Q chunk + K chunk (128 rows x 128 B each)
-constexpr int QK_STAGES = 3;
-constexpr int V_STAGE = FDV * 128;      // 256 d_v rows x 64 keys x 2 B
-constexpr int V_STAGES = 2;
-constexpr int P_BYTES = 2 * 16384;      // two 64-key chunks of 128 rows x 128 B
-constexpr int FLASH_SMEM = QK_STAGES * QK_STAGE + V_STAGES * V_STAGE + P_BYTES + 1024 + 1024;
-constexpr int FLASH_THREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 softmax / epilogue
+constexpr int CHUNK = 16384;            // 128 rows x 128 B (64 fp16, 128B-swizzled K-major)
+constexpr int Q_BYTES = (FD / 64) * CHUNK;
+constexpr int RING = 6;                 // K chunks (8 per tile) and V chunks (4 per tile) in consumption order
+constexpr int XCHG_BYTES = 2 * 2 * FQ * 4;   // [tile parity][column half][row] row maxima / row sums
+constexpr int FLASH_SMEM = Q_BYTES + RING * CHUNK + 256 + XCHG_BYTES;   // no alignment slack: see the kernel
+static_assert(FLASH_SMEM <= 227 * 1024, "shared memory budget");
+constexpr int SM_WARPS = 8;              // softmax warps: two per TMEM lane quadrant, each owns 64 of a tile's 128 keys
+constexpr int FLASH_THREADS = 64 + 32 * SM_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / epilogue
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -47,25 +55,37 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// D[tmem] (+)= A[tmem] * B[smem]: A is 128 rows (lanes) x 16 fp16 = 8 columns, two values per column
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 __global__ void __launch_bounds__(FLASH_THREADS, 1)
 flash_d512_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                   __half* __restrict__ out, const float* __restrict__ bias_v, int tokens, int q_tiles,
                   float scale_log2) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* s_qk = smem;                                   // [QK_STAGES][Q 16 KB | K 16 KB]
-    uint8_t* s_v = smem + QK_STAGES * QK_STAGE;             // [V_STAGES][32 KB]
-    uint8_t* s_p = s_v + V_STAGES * V_STAGE;                // [2 chunks][16 KB]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + P_BYTES);
-    uint64_t* qk_full = bars;            // [3]
-    uint64_t* qk_empty = bars + 3;       // [3]
-    uint64_t* v_full = bars + 6;         // [2]
-    uint64_t* v_empty = bars + 8;        // [2]
-    uint64_t* s_full = bars + 10;        // [2]  S(j) accumulated
-    uint64_t* s_empty = bars + 12;       // [2]  S buffer read by the softmax warps
-    uint64_t* p_full = bars + 14;        // [1]  P(j) written to shared memory
-    uint64_t* p_empty = bars + 15;       // [1]  P(j) V_j done: P may be overwritten, O may be rescaled
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+    // Q + ring fill the 227 KB to within 1 KB, so there is no room for an alignment pad: the dynamic window is
+    // declared 1024-byte aligned (what the 128B-swizzled tiles need) and the kernel refuses to run otherwise
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    uint8_t* s_q = smem;                                    // [8 chunks][128 queries x 64 dims]
+    uint8_t* s_ring = smem + Q_BYTES;                       // [RING][16 KB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + RING * CHUNK);
+    uint64_t* q_full = bars;                 // [1]
+    uint64_t* ring_full = bars + 1;          // [RING]
+    uint64_t* ring_empty = ring_full + RING; // [RING]
+    uint64_t* s_full = ring_empty + RING;    // [2]  S(j) accumulated
+    uint64_t* p_full = s_full + 2;           // [2]  P(j) written to tensor memory
+    uint64_t* o_done = p_full + 2;           // [1]  P(j) V_j accumulated: O may be rescaled / read
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
+    float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][2][FQ]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // blockIdx.x = (img * q_tiles + q_tile) * 2 + half
@@ -78,11 +98,10 @@ flash_d512_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQK);
         tma_prefetch_desc(&tmV);
-        for (int i = 0; i < QK_STAGES; ++i) { mbar_init(&qk_full[i], 1); mbar_init(&qk_empty[i], 1); }
-        for (int i = 0; i < V_STAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
-        mbar_init(p_full, 4);
-        mbar_init(p_empty, 1);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < RING; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], SM_WARPS); }
+        mbar_init(o_done, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -93,181 +112,181 @@ flash_d512_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tmem_s = tmem_base;          // columns 0..255: S double buffer
+    const uint32_t tmem_s = tmem_base;          // columns 0..255: S double buffer (P aliases the first 64 columns of each)
     const uint32_t tmem_o = tmem_base + 256;    // columns 256..511: O
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            int qs = 0, vs = 0;
-            uint32_t qph = 0, vph = 0;
-            auto load_s_tile = [&](int j) {      // 8 (Q_c, K_c) chunk pairs of key tile j
-                for (int c = 0; c < FD / 64; ++c) {
-                    mbar_wait(&qk_empty[qs], qph ^ 1);
-                    uint8_t* st = s_qk + qs * QK_STAGE;
-                    mbar_arrive_expect_tx(&qk_full[qs], QK_STAGE);
-                    tma_load_3d(st, &tmQK, &qk_full[qs], c * 64, q0, img);                    // Q chunk
-                    tma_load_3d(st + 16384, &tmQK, &qk_full[qs], FD + c * 64, j * FK, img);  // K chunk
-                    if (++qs == QK_STAGES) { qs = 0; qph ^= 1; }
-                }
+            mbar_arrive_expect_tx(q_full, Q_BYTES);
+            for (int c = 0; c < FD / 64; ++c) tma_load_3d(s_q + c * CHUNK, &tmQK, q_full, c * 64, q0, img);
+            int rs = 0;
+            uint32_t rph = 0;
+            auto put = [&](const CUtensorMap* map, int c0, int c1) {
+                mbar_wait(&ring_empty[rs], rph ^ 1);
+                mbar_arrive_expect_tx(&ring_full[rs], CHUNK);
+                tma_load_3d(s_ring + rs * CHUNK, map, &ring_full[rs], c0, c1, img);
+                if (++rs == RING) { rs = 0; rph ^= 1; }
             };
-            load_s_tile(0);
+            auto load_k = [&](int j) {           // K chunks of key tile j: [128 keys][64 dims]
+                for (int c = 0; c < FD / 64; ++c) put(&tmQK, FD + c * 64, j * FK);
+            };
+            load_k(0);
             for (int j = 0; j < key_tiles; ++j) {
-                if (j + 1 < key_tiles) load_s_tile(j + 1);
-                for (int kc = 0; kc < FK / 64; ++kc) {   // V^T chunks of key tile j: [256 d_v rows][64 keys]
-                    mbar_wait(&v_empty[vs], vph ^ 1);
-                    mbar_arrive_expect_tx(&v_full[vs], V_STAGE);
-                    tma_load_3d(s_v + vs * V_STAGE, &tmV, &v_full[vs], j * FK + kc * 64, half * FDV, img);
-                    if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
-                }
+                if (j + 1 < key_tiles) load_k(j + 1);
+                for (int kc = 0; kc < FK / 64; ++kc)     // V^T chunks of key tile j: [128 d_v rows][64 keys]
+                    for (int h = 0; h < FDV / 128; ++h) put(&tmV, j * FK + kc * 64, half * FDV + h * 128);
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (warp-uniform loops)
-        constexpr uint32_t idesc_s = umma_idesc_16(128, FK, true);     // S: M=128 queries, N=128 keys
-        constexpr uint32_t idesc_o = umma_idesc_16(128, FDV, true);    // O: M=128 queries, N=256 d_v
-        const uint64_t dq_base = umma_desc_k_sw128(smem_u32(s_qk));
-        const uint64_t dk_base = umma_desc_k_sw128(smem_u32(s_qk) + 16384);
-        const uint64_t dv_base = umma_desc_k_sw128(smem_u32(s_v));
-        const uint64_t dp_base = umma_desc_k_sw128(smem_u32(s_p));
-        int qs = 0, vs = 0;
-        uint32_t qph = 0, vph = 0;
+        constexpr uint32_t idesc = umma_idesc_16(128, 128, true);   // S: 128 queries x 128 keys; O: 128 queries x 128 d_v
+        const uint64_t dq_base = umma_desc_k_sw128(smem_u32(s_q));
+        const uint64_t dr_base = umma_desc_k_sw128(smem_u32(s_ring));
+        int rs = 0;
+        uint32_t rph = 0;
+        mbar_wait(q_full, 0);
         auto issue_s = [&](int j) {
+            // S(j) overwrites the buffer that held P(j-2): P(j-2) V was issued earlier and the tensor pipe
+            // executes in issue order, so no barrier is needed for that hazard
             const uint32_t sb = j & 1;
-            mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
-            tc_fence_after();
             for (int c = 0; c < FD / 64; ++c) {
-                mbar_wait(&qk_full[qs], qph);
+                mbar_wait(&ring_full[rs], rph);
                 tc_fence_after();
-                const uint64_t so = static_cast<uint64_t>(qs * (QK_STAGE >> 4));
+                const uint64_t ro = static_cast<uint64_t>(rs * (CHUNK >> 4));
+                const uint64_t qo = static_cast<uint64_t>(c * (CHUNK >> 4));
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(tmem_s + sb * FK, dq_base + so + 2 * k, dk_base + so + 2 * k, idesc_s, (c | k) != 0);
-                    umma_commit(&qk_empty[qs]);
+                        umma_bf16_ss(tmem_s + sb * FK, dq_base + qo + 2 * k, dr_base + ro + 2 * k, idesc, (c | k) != 0);
+                    umma_commit(&ring_empty[rs]);
                     if (c == FD / 64 - 1) umma_commit(&s_full[sb]);
                 }
                 __syncwarp();
-                if (++qs == QK_STAGES) { qs = 0; qph ^= 1; }
+                if (++rs == RING) { rs = 0; rph ^= 1; }
             }
         };
         issue_s(0);
         for (int j = 0; j < key_tiles; ++j) {
             if (j + 1 < key_tiles) issue_s(j + 1);            // overlaps the softmax of tile j
-            mbar_wait(p_full, j & 1);
+            const uint32_t sb = j & 1;
+            mbar_wait(&p_full[sb], (j >> 1) & 1);
             tc_fence_after();
-            for (int kc = 0; kc < FK / 64; ++kc) {
-                mbar_wait(&v_full[vs], vph);
-                tc_fence_after();
-                const uint64_t vo = static_cast<uint64_t>(vs * (V_STAGE >> 4));
-                if (elect_one()) {
+            for (int kc = 0; kc < FK / 64; ++kc)
+                for (int h = 0; h < FDV / 128; ++h) {
+                    mbar_wait(&ring_full[rs], rph);
+                    tc_fence_after();
+                    const uint64_t ro = static_cast<uint64_t>(rs * (CHUNK >> 4));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(tmem_o, dp_base + (kc * (16384 >> 4) + 2 * k), dv_base + vo + 2 * k, idesc_o,
-                                     (j | kc | k) != 0);
-                    umma_commit(&v_empty[vs]);
-                    if (kc == FK / 64 - 1) umma_commit(p_empty);
+                        for (int k = 0; k < 4; ++k)   // A = P(j) keys [kc*64 + 16k, +16): 8 tensor-memory columns
+                            umma_f16_ts(tmem_o + h * 128, tmem_s + sb * FK + kc * 32 + k * 8, dr_base + ro + 2 * k, idesc,
+                                        (j | kc | k) != 0);
+                        umma_commit(&ring_empty[rs]);
+                        if (kc == FK / 64 - 1 && h == FDV / 128 - 1) umma_commit(o_done);
+                    }
+                    __syncwarp();
+                    if (++rs == RING) { rs = 0; rph ^= 1; }
                 }
-                __syncwarp();
-                if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
-            }
         }
     } else {
-        // ------------------------------------------------------------ softmax warps (one query row per thread)
-        const int q = warp & 3;                           // TMEM lane quadrant
+        // ------------------------------------------------------------ softmax warps
+        // thread = (query row, column half hs): 64 keys of every tile, 128 of the 256 O columns
+        const int q = warp & 3;                           // TMEM lane quadrant (hardware: warp id % 4)
+        const int hs = (warp - 2) >> 2;                   // 0: warps 2..5, 1: warps 6..9
         const int row = q * 32 + lane;                    // query row inside the tile
         const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t p_row = smem_u32(s_p) + row * 128;
+        const int pair_bar = 1 + q;                       // named barrier of the two warps that share a quadrant
         float m_used = -INFINITY;                         // maximum the exponentials are taken against (log2 units)
-        float l = 0.f;
+        float l = 0.f;                                    // this thread's part of the row sum
         for (int j = 0; j < key_tiles; ++j) {
             const uint32_t sb = j & 1;
             mbar_wait(&s_full[sb], (j >> 1) & 1);
             tc_fence_after();
-            uint32_t r[4][32];
+            uint32_t r[2][32];
 #pragma unroll
-            for (int cchunk = 0; cchunk < 4; ++cchunk) tmem_ld_32x32(tmem_s + sb * FK + cchunk * 32 + lane_sel, r[cchunk]);
+            for (int cchunk = 0; cchunk < 2; ++cchunk)
+                tmem_ld_32x32(tmem_s + sb * FK + hs * 64 + cchunk * 32 + lane_sel, r[cchunk]);
             tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[sb]);     // S(j+2) may overwrite this buffer
-            // scale to log2 units, mask keys beyond the sequence, row maximum
-            const int key0 = j * FK;
-            float mx = -INFINITY;
+            // scale to log2 units, mask keys beyond the sequence, row maximum (four independent chains)
+            const int key0 = j * FK + hs * 64;
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int cchunk = 0; cchunk < 4; ++cchunk)
+            for (int cchunk = 0; cchunk < 2; ++cchunk)
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     float v = __uint_as_float(r[cchunk][i]) * scale_log2;
                     if (key0 + cchunk * 32 + i >= tokens) v = -INFINITY;
                     r[cchunk][i] = __float_as_uint(v);
-                    mx = fmaxf(mx, v);
+                    mx4[i & 3] = fmaxf(mx4[i & 3], v);
                 }
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            // the other half of the row lives in the partner warp: exchange the maxima
+            float* xs = xchg + (j & 1) * (2 * FQ);
+            xs[hs * FQ + row] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            mx = fmaxf(mx, xs[(hs ^ 1) * FQ + row]);
             // lazy rescale: raise the reference maximum only when it is exceeded by more than 2^8
             const bool raise = mx > m_used + 8.0f;
             const float m_new = raise ? mx : m_used;
             const float alpha = (raise && j > 0) ? exp2f(m_used - m_new) : 1.0f;
             const bool any_raise = __any_sync(0xFFFFFFFFu, raise && j > 0);
-            if (j > 0) {
-                mbar_wait(p_empty, (j - 1) & 1);          // P(j-1) V done: O is stable, P may be overwritten
-                tc_fence_after();
-            }
             if (any_raise) {
-                // rescale this warp's 32 rows of O in TMEM (rows that keep their maximum use alpha = 1)
+                // O must be stable: P(j-1) V accumulated (P(j-2) V certainly is -- S(j) was issued after it)
+                mbar_wait(o_done, (j - 1) & 1);
+                tc_fence_after();
+                // rescale this thread's 128 O columns of its row (rows that keep their maximum use alpha = 1)
 #pragma unroll 1
-                for (int cchunk = 0; cchunk < FDV / 32; ++cchunk) {
+                for (int cchunk = 0; cchunk < 4; ++cchunk) {
                     uint32_t o[32];
-                    tmem_ld_32x32(tmem_o + cchunk * 32 + lane_sel, o);
+                    tmem_ld_32x32(tmem_o + hs * 128 + cchunk * 32 + lane_sel, o);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st_32x32(tmem_o + cchunk * 32 + lane_sel, o);
+                    tmem_st_32x32(tmem_o + hs * 128 + cchunk * 32 + lane_sel, o);
                 }
-                tmem_st_wait();
                 l *= alpha;
             }
             m_used = m_new;
-            // P = exp2(s - m), fp16, into the K-major 128B-swizzled A-operand layout
-            float lsum = 0.f;
+            // P = exp2(s - m) as fp16 pairs, written over this row's S values: keys 2w, 2w+1 -> column w
+            float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t pk[32];
 #pragma unroll
-            for (int cchunk = 0; cchunk < 4; ++cchunk) {
-                uint32_t pk[16];
+            for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float a = fast_exp2(__uint_as_float(r[cchunk][2 * i]) - m_used);
-                    const float b = fast_exp2(__uint_as_float(r[cchunk][2 * i + 1]) - m_used);
-                    lsum += a + b;
-                    pk[i] = pack_f16x2(a, b);
+                    const float a = fast_exp2(__uint_as_float(r[cc][2 * i]) - m_used);
+                    const float b = fast_exp2(__uint_as_float(r[cc][2 * i + 1]) - m_used);
+                    ls4[i & 3] += a + b;
+                    pk[cc * 16 + i] = pack_f16x2(a, b);
                 }
-                // 32 keys = 64 bytes = four 16-byte chunks of this row: keys [cchunk*32, +32)
-#pragma unroll
-                for (int w4 = 0; w4 < 4; ++w4) {
-                    const int chunk16 = cchunk * 4 + w4;                 // 0..15 across the 128 keys
-                    const int kc = chunk16 >> 3, pos = (chunk16 & 7) ^ (row & 7);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + kc * 16384 + pos * 16),
-                                 "r"(pk[4 * w4]), "r"(pk[4 * w4 + 1]), "r"(pk[4 * w4 + 2]), "r"(pk[4 * w4 + 3]) : "memory");
-                }
-            }
-            l += lsum;
-            fence_proxy_async_smem();
+            tmem_st_32x32(tmem_s + sb * FK + hs * 32 + lane_sel, pk);
+            l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
+            if (lane == 0) mbar_arrive(&p_full[sb]);
         }
-        // ---- epilogue: O / l + b_v -> fp16 global
-        mbar_wait(p_empty, (key_tiles - 1) & 1);
+        // ---- epilogue: O / l + b_v -> fp16 global; the row sum is the two threads' parts added up
+        {
+            float* xs = xchg + (key_tiles & 1) * (2 * FQ);
+            xs[hs * FQ + row] = l;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            l += xs[(hs ^ 1) * FQ + row];
+        }
+        mbar_wait(o_done, (key_tiles - 1) & 1);
         tc_fence_after();
         const float inv = 1.0f / l;
         const int qrow = q0 + row;
-        __half* orow = out + (static_cast<long long>(img) * tokens + qrow) * FD + half * FDV;
+        __half* orow = out + (static_cast<long long>(img) * tokens + qrow) * FD + half * FDV + hs * 128;
 #pragma unroll 1
-        for (int cchunk = 0; cchunk < FDV / 32; ++cchunk) {
+        for (int cchunk = 0; cchunk < 4; ++cchunk) {
             uint32_t o[32];
-            tmem_ld_32x32(tmem_o + cchunk * 32 + lane_sel, o);
+            tmem_ld_32x32(tmem_o + hs * 128 + cchunk * 32 + lane_sel, o);
             tmem_ld_wait();
             if (qrow < tokens) {
-                const float* bv = bias_v + half * FDV + cchunk * 32;
+                const float* bv = bias_v + half * FDV + hs * 128 + cchunk * 32;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint32_t w[4];
@@ -306,7 +325,7 @@ int launch_flash_attention(const FlashOp& op, cudaStream_t stream, Profiler* pro
     {
         uint64_t dims[3] = {static_cast<uint64_t>(op.tokens), static_cast<uint64_t>(FD), static_cast<uint64_t>(op.n)};
         uint64_t str[2] = {2ull * op.tokens, 2ull * op.tokens * FD};
-        uint32_t box[3] = {64, static_cast<uint32_t>(FDV), 1};
+        uint32_t box[3] = {64, 128, 1};
         VT_TRY(make_tmap(&tv, op.vt, 3, dims, str, box));
     }
     static bool attr_set = false;
@@ -317,7 +336,8 @@ int launch_flash_attention(const FlashOp& op, cudaStream_t stream, Profiler* pro
     const int q_tiles = (op.tokens + FQ - 1) / FQ;
     const int grid = op.n * q_tiles * 2;
     const double key_t = (op.tokens + FK - 1) / FK * FK;
-    const double flops = 2.0 * op.n * q_tiles * FQ * key_t * FD * 3.0;  // QK^T twice (two d_v halves) + PV
+    // algorithmic work: QK^T and PV once each (the second QK^T of the d_v split is overhead, not counted)
+    const double flops = 2.0 * op.n * q_tiles * FQ * key_t * FD * 2.0;
     profiler_begin(prof, KC_IGEMM, stream, flops, 2.0 * op.n * op.tokens * FD * 4.0);
     flash_d512_kernel<<<grid, FLASH_THREADS, FLASH_SMEM, stream>>>(tq, tv, static_cast<__half*>(op.out), op.bias_v,
                                                                    op.tokens, q_tiles,
