@@ -12,9 +12,13 @@
 //                               V_j streamed as 4 chunks of 128 d_v rows x 64 keys
 // TMEM: two S/P buffers (2 x 128 columns) + O (256 columns) = 512 columns: that is why d_v is split over
 // two CTAs (an O tile of 128 x 512 fp32 alone would fill TMEM) -- QK^T is computed twice, PV once.
-// Shared memory: Q 128 KB + one ring of six 16 KB chunks carrying K and V in consumption order.  The first
-// version re-streamed Q with every key tile and staged P through shared memory: 320 KB of L2->SM traffic
-// and ~700 KB of shared-memory traffic per key tile, which (not the tensor pipe) set its speed.
+// CTA PAIRS: two CTAs with neighbouring query tiles (same d_v half) form a cluster and run every MMA as
+// one tcgen05.mma.cta_group::2 (M = 256: 128 query rows per CTA): the B operand -- K_j for S, V_j for O --
+// is split across the pair, so each CTA streams and reads only HALF of every K / V chunk.
+// Shared memory per CTA: Q 128 KB + one ring of twelve 8 KB half-chunks carrying K and V in consumption
+// order.  The first version re-streamed Q with every key tile, staged P through shared memory and ran
+// single-CTA MMAs: 320 KB of L2->SM traffic and ~700 KB of shared-memory traffic per key tile, which (not
+// the tensor pipe) set its speed; now 96 KB and ~320 KB.
 // The running maximum is only raised when a row's new maximum exceeds it by more than 2^8 (lazy
 // rescale: P stays within fp16 range, O is rescaled in TMEM only then).  Scores never touch HBM.
 #include "vt_internal.h"
@@ -30,9 +34,10 @@ constexpr int FD = 512;                 // head dim
 constexpr int FDV = 256;                // d_v columns per CTA
 constexpr int CHUNK = 16384;            // 128 rows x 128 B (64 fp16, 128B-swizzled K-major)
 constexpr int Q_BYTES = (FD / 64) * CHUNK;
-constexpr int RING = 6;                 // K chunks (8 per tile) and V chunks (4 per tile) in consumption order
+constexpr int HCHUNK = CHUNK / 2;       // this CTA's half of a K / V chunk: 64 rows x 128 B
+constexpr int RING = 12;                // K half-chunks (8 per tile) and V half-chunks (4 per tile) in consumption order
 constexpr int XCHG_BYTES = 2 * 2 * FQ * 4;   // [tile parity][column half][row] row maxima / row sums
-constexpr int FLASH_SMEM = Q_BYTES + RING * CHUNK + 256 + XCHG_BYTES;   // no alignment slack: see the kernel
+constexpr int FLASH_SMEM = Q_BYTES + RING * HCHUNK + 256 + XCHG_BYTES;   // no alignment slack: see the kernel
 static_assert(FLASH_SMEM <= 227 * 1024, "shared memory budget");
 constexpr int SM_WARPS = 8;              // softmax warps: two per TMEM lane quadrant, each owns 64 of a tile's 128 keys
 constexpr int FLASH_THREADS = 64 + 32 * SM_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / epilogue
@@ -55,140 +60,134 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// D[tmem] (+)= A[tmem] * B[smem]: A is 128 rows (lanes) x 16 fp16 = 8 columns, two values per column
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__global__ void __launch_bounds__(FLASH_THREADS, 1)
-flash_d512_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
-                  __half* __restrict__ out, const float* __restrict__ bias_v, int tokens, int q_tiles,
-                  float scale_log2) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FLASH_THREADS, 1)
+flash_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out,
+                  const float* __restrict__ bias_v, int tokens, int q_pairs, float scale_log2) {
     // Q + ring fill the 227 KB to within 1 KB, so there is no room for an alignment pad: the dynamic window is
     // declared 1024-byte aligned (what the 128B-swizzled tiles need) and the kernel refuses to run otherwise
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* s_q = smem;                                    // [8 chunks][128 queries x 64 dims]
-    uint8_t* s_ring = smem + Q_BYTES;                       // [RING][16 KB]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + RING * CHUNK);
-    uint64_t* q_full = bars;                 // [1]
-    uint64_t* ring_full = bars + 1;          // [RING]
-    uint64_t* ring_empty = ring_full + RING; // [RING]
-    uint64_t* s_full = ring_empty + RING;    // [2]  S(j) accumulated
-    uint64_t* p_full = s_full + 2;           // [2]  P(j) written to tensor memory
-    uint64_t* o_done = p_full + 2;           // [1]  P(j) V_j accumulated: O may be rescaled / read
+    uint8_t* s_ring = smem + Q_BYTES;                       // [RING][8 KB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + RING * HCHUNK);
+    uint64_t* q_full = bars;                 // [1]     (leader's is waited on)
+    uint64_t* ring_full = bars + 1;          // [RING]  (leader's is waited on: both CTAs' TMA bytes land there)
+    uint64_t* ring_empty = ring_full + RING; // [RING]  tcgen05.commit multicast to both CTAs
+    uint64_t* s_full = ring_empty + RING;    // [2]  S(j) accumulated (multicast)
+    uint64_t* p_full = s_full + 2;           // [2]  P(j) written to tensor memory in BOTH CTAs (leader's)
+    uint64_t* o_done = p_full + 2;           // [1]  P(j) V_j accumulated: O may be rescaled / read (multicast)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
     float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][2][FQ]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // blockIdx.x = (img * q_tiles + q_tile) * 2 + half
-    const int half = blockIdx.x & 1;
-    const int qt = (blockIdx.x >> 1) % q_tiles;
-    const int img = (blockIdx.x >> 1) / q_tiles;
-    const int q0 = qt * FQ;
+    // blockIdx.x = (((img * q_pairs + q_pair) * 2 + half) * 2 + rank): the cluster is the two query tiles of a pair
+    const uint32_t rank = cluster_ctarank();
+    const int half = (blockIdx.x >> 1) & 1;
+    const int qp = (blockIdx.x >> 2) % q_pairs;
+    const int img = (blockIdx.x >> 2) / q_pairs;
+    const int q0 = (qp * 2 + static_cast<int>(rank)) * FQ;   // may lie beyond the sequence (odd tile count): TMA zero-fills, stores are masked
     const int key_tiles = (tokens + FK - 1) / FK;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQK);
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
         mbar_init(q_full, 1);
         for (int i = 0; i < RING; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], SM_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 2 * SM_WARPS); }
         mbar_init(o_done, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, 512);
-        tmem_relinquish();
+        tmem_alloc_pair(tmem_ptr, 512);
+        tmem_relinquish_pair();
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();      // the peer's barriers are initialised before any remote arrive / TMA signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_s = tmem_base;          // columns 0..255: S double buffer (P aliases the first 64 columns of each)
     const uint32_t tmem_o = tmem_base + 256;    // columns 256..511: O
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------ TMA producer (both CTAs, own halves)
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, Q_BYTES);
-            for (int c = 0; c < FD / 64; ++c) tma_load_3d(s_q + c * CHUNK, &tmQK, q_full, c * 64, q0, img);
+            if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * Q_BYTES);
+            for (int c = 0; c < FD / 64; ++c) tma_load_3d_pair(s_q + c * CHUNK, &tmQ, q_full, c * 64, q0, img);
             int rs = 0;
             uint32_t rph = 0;
             auto put = [&](const CUtensorMap* map, int c0, int c1) {
                 mbar_wait(&ring_empty[rs], rph ^ 1);
-                mbar_arrive_expect_tx(&ring_full[rs], CHUNK);
-                tma_load_3d(s_ring + rs * CHUNK, map, &ring_full[rs], c0, c1, img);
+                if (rank == 0) mbar_arrive_expect_tx(&ring_full[rs], 2 * HCHUNK);
+                tma_load_3d_pair(s_ring + rs * HCHUNK, map, &ring_full[rs], c0, c1 + static_cast<int>(rank) * 64, img);
                 if (++rs == RING) { rs = 0; rph ^= 1; }
             };
-            auto load_k = [&](int j) {           // K chunks of key tile j: [128 keys][64 dims]
-                for (int c = 0; c < FD / 64; ++c) put(&tmQK, FD + c * 64, j * FK);
+            auto load_k = [&](int j) {           // this CTA's 64 keys of key tile j, 8 chunks of 64 dims
+                for (int c = 0; c < FD / 64; ++c) put(&tmK, FD + c * 64, j * FK);
             };
             load_k(0);
             for (int j = 0; j < key_tiles; ++j) {
                 if (j + 1 < key_tiles) load_k(j + 1);
-                for (int kc = 0; kc < FK / 64; ++kc)     // V^T chunks of key tile j: [128 d_v rows][64 keys]
+                for (int kc = 0; kc < FK / 64; ++kc)     // V^T: this CTA's 64 of the 128 d_v rows x 64 keys
                     for (int h = 0; h < FDV / 128; ++h) put(&tmV, j * FK + kc * 64, half * FDV + h * 128);
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (warp-uniform loops)
-        constexpr uint32_t idesc = umma_idesc_16(128, 128, true);   // S: 128 queries x 128 keys; O: 128 queries x 128 d_v
-        const uint64_t dq_base = umma_desc_k_sw128(smem_u32(s_q));
-        const uint64_t dr_base = umma_desc_k_sw128(smem_u32(s_ring));
-        int rs = 0;
-        uint32_t rph = 0;
-        mbar_wait(q_full, 0);
-        auto issue_s = [&](int j) {
-            // S(j) overwrites the buffer that held P(j-2): P(j-2) V was issued earlier and the tensor pipe
-            // executes in issue order, so no barrier is needed for that hazard
-            const uint32_t sb = j & 1;
-            for (int c = 0; c < FD / 64; ++c) {
-                mbar_wait(&ring_full[rs], rph);
-                tc_fence_after();
-                const uint64_t ro = static_cast<uint64_t>(rs * (CHUNK >> 4));
-                const uint64_t qo = static_cast<uint64_t>(c * (CHUNK >> 4));
-                if (elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(tmem_s + sb * FK, dq_base + qo + 2 * k, dr_base + ro + 2 * k, idesc, (c | k) != 0);
-                    umma_commit(&ring_empty[rs]);
-                    if (c == FD / 64 - 1) umma_commit(&s_full[sb]);
-                }
-                __syncwarp();
-                if (++rs == RING) { rs = 0; rph ^= 1; }
-            }
-        };
-        issue_s(0);
-        for (int j = 0; j < key_tiles; ++j) {
-            if (j + 1 < key_tiles) issue_s(j + 1);            // overlaps the softmax of tile j
-            const uint32_t sb = j & 1;
-            mbar_wait(&p_full[sb], (j >> 1) & 1);
-            tc_fence_after();
-            for (int kc = 0; kc < FK / 64; ++kc)
-                for (int h = 0; h < FDV / 128; ++h) {
+        // ------------------------------------------------------------ MMA issuer: leader CTA only
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_16(256, 128, true);   // pair MMA: 2 x 128 queries; 128 keys / 128 d_v
+            const uint64_t dq_base = umma_desc_k_sw128(smem_u32(s_q));
+            const uint64_t dr_base = umma_desc_k_sw128(smem_u32(s_ring));
+            int rs = 0;
+            uint32_t rph = 0;
+            mbar_wait(q_full, 0);
+            auto issue_s = [&](int j) {
+                // S(j) overwrites the buffer that held P(j-2): P(j-2) V was issued earlier and the tensor pipe
+                // executes in issue order, so no barrier is needed for that hazard
+                const uint32_t sb = j & 1;
+                for (int c = 0; c < FD / 64; ++c) {
                     mbar_wait(&ring_full[rs], rph);
                     tc_fence_after();
-                    const uint64_t ro = static_cast<uint64_t>(rs * (CHUNK >> 4));
+                    const uint64_t ro = static_cast<uint64_t>(rs * (HCHUNK >> 4));
+                    const uint64_t qo = static_cast<uint64_t>(c * (CHUNK >> 4));
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)   // A = P(j) keys [kc*64 + 16k, +16): 8 tensor-memory columns
-                            umma_f16_ts(tmem_o + h * 128, tmem_s + sb * FK + kc * 32 + k * 8, dr_base + ro + 2 * k, idesc,
-                                        (j | kc | k) != 0);
-                        umma_commit(&ring_empty[rs]);
-                        if (kc == FK / 64 - 1 && h == FDV / 128 - 1) umma_commit(o_done);
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_ss_pair(tmem_s + sb * FK, dq_base + qo + 2 * k, dr_base + ro + 2 * k, idesc, (c | k) != 0);
+                        umma_commit_pair(&ring_empty[rs]);
+                        if (c == FD / 64 - 1) umma_commit_pair(&s_full[sb]);
                     }
                     __syncwarp();
                     if (++rs == RING) { rs = 0; rph ^= 1; }
                 }
+            };
+            issue_s(0);
+            for (int j = 0; j < key_tiles; ++j) {
+                if (j + 1 < key_tiles) issue_s(j + 1);            // overlaps the softmax of tile j
+                const uint32_t sb = j & 1;
+                mbar_wait(&p_full[sb], (j >> 1) & 1);
+                tc_fence_after();
+                for (int kc = 0; kc < FK / 64; ++kc)
+                    for (int h = 0; h < FDV / 128; ++h) {
+                        mbar_wait(&ring_full[rs], rph);
+                        tc_fence_after();
+                        const uint64_t ro = static_cast<uint64_t>(rs * (HCHUNK >> 4));
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)   // A = P(j) keys [kc*64 + 16k, +16): 8 tensor-memory columns
+                                umma_f16_ts_pair(tmem_o + h * 128, tmem_s + sb * FK + kc * 32 + k * 8, dr_base + ro + 2 * k,
+                                                 idesc, (j | kc | k) != 0);
+                            umma_commit_pair(&ring_empty[rs]);
+                            if (kc == FK / 64 - 1 && h == FDV / 128 - 1) umma_commit_pair(o_done);
+                        }
+                        __syncwarp();
+                        if (++rs == RING) { rs = 0; rph ^= 1; }
+                    }
+            }
         }
     } else {
         // ------------------------------------------------------------ softmax warps
@@ -266,7 +265,7 @@ flash_d512_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[sb]);
+            if (lane == 0) mbar_arrive_cluster(&p_full[sb], 0);   // the leader issues P V for both CTAs
         }
         // ---- epilogue: O / l + b_v -> fp16 global; the row sum is the two threads' parts added up
         {
@@ -304,9 +303,10 @@ flash_d512_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();      // neither CTA leaves (or frees tensor memory) while the pair still works
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc_pair(tmem_base, 512);
     }
 }
 
@@ -315,17 +315,19 @@ flash_d512_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
 int launch_flash_attention(const FlashOp& op, cudaStream_t stream, Profiler* prof) {
     VT_CHECK(op.C == FD, "fused attention is specialised for head_dim 512");
     VT_CHECK(op.tokens > 0 && op.tokens % 8 == 0 && op.n > 0, "fused attention: token count must be a positive multiple of 8");
-    CUtensorMap tq, tv;
+    CUtensorMap tq, tk, tv;
     {
         uint64_t dims[3] = {static_cast<uint64_t>(2 * FD), static_cast<uint64_t>(op.tokens), static_cast<uint64_t>(op.n)};
         uint64_t str[2] = {2ull * 2 * FD, 2ull * 2 * FD * op.tokens};
         uint32_t box[3] = {64, 128, 1};
         VT_TRY(make_tmap(&tq, op.qk, 3, dims, str, box));
+        uint32_t boxk[3] = {64, 64, 1};     // one CTA's half of a 128-key chunk
+        VT_TRY(make_tmap(&tk, op.qk, 3, dims, str, boxk));
     }
     {
         uint64_t dims[3] = {static_cast<uint64_t>(op.tokens), static_cast<uint64_t>(FD), static_cast<uint64_t>(op.n)};
         uint64_t str[2] = {2ull * op.tokens, 2ull * op.tokens * FD};
-        uint32_t box[3] = {64, 128, 1};
+        uint32_t box[3] = {64, 64, 1};      // 64 keys x one CTA's 64 of the 128 d_v rows
         VT_TRY(make_tmap(&tv, op.vt, 3, dims, str, box));
     }
     static bool attr_set = false;
@@ -334,13 +336,14 @@ int launch_flash_attention(const FlashOp& op, cudaStream_t stream, Profiler* pro
         attr_set = true;
     }
     const int q_tiles = (op.tokens + FQ - 1) / FQ;
-    const int grid = op.n * q_tiles * 2;
+    const int q_pairs = (q_tiles + 1) / 2;
+    const int grid = op.n * q_pairs * 4;   // pair x d_v half
     const double key_t = (op.tokens + FK - 1) / FK * FK;
     // algorithmic work: QK^T and PV once each (the second QK^T of the d_v split is overhead, not counted)
     const double flops = 2.0 * op.n * q_tiles * FQ * key_t * FD * 2.0;
     profiler_begin(prof, KC_IGEMM, stream, flops, 2.0 * op.n * op.tokens * FD * 4.0);
-    flash_d512_kernel<<<grid, FLASH_THREADS, FLASH_SMEM, stream>>>(tq, tv, static_cast<__half*>(op.out), op.bias_v,
-                                                                   op.tokens, q_tiles,
+    flash_d512_kernel<<<grid, FLASH_THREADS, FLASH_SMEM, stream>>>(tq, tk, tv, static_cast<__half*>(op.out), op.bias_v,
+                                                                   op.tokens, q_pairs,
                                                                    op.scale * 1.4426950408889634f);
     profiler_end(prof, KC_IGEMM, stream);
     VT_CUDA(cudaGetLastError());
