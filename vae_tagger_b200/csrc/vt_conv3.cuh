@@ -24,7 +24,7 @@ namespace vt {
 //   the A operand), columns = 256 pixels (an 8x32 patch, the halo view is the B operand).  A 128x128
 //   MMA reads 8 KB of operands per 64 cycles -- the full shared-memory read bandwidth -- and measured
 //   ~45 % tensor-pipe utilisation next to the TMA writes; 128x256 reads 12 KB per 128 cycles.
-template <int BLOCK_N, int MT, bool TR>
+template <int BLOCK_N, int MT, bool TR, bool PAIR = false>
 struct Conv3Cfg {
     static constexpr int kBlockN = BLOCK_N, kMT = MT;
     static constexpr bool kTR = TR;
@@ -35,12 +35,17 @@ struct Conv3Cfg {
     static constexpr int HROWS = HWID * HHGT;         // 128-byte rows per halo chunk
     static constexpr int HALO_BYTES = (HROWS * 128 + 1023) / 1024 * 1024;
     static constexpr int NHALO = 3;
-    static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;   // weight tile of one (tap, 64-channel chunk)
+    // PAIR: two CTAs (neighbouring pixel tiles, same output channels) run every MMA as one
+    // tcgen05.mma.cta_group::2 (M = 256); the weight tile -- the B operand -- is split across the pair, so each
+    // CTA streams and reads only half of it (shared-memory data pipe: tensor-core operand reads 12 -> 8 KB per MMA)
+    static constexpr bool kPair = PAIR;
+    static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;   // weight rows this CTA holds
+    static constexpr int B_BYTES = B_ROWS * IGEMM_BLOCK_K * 2;    // weight tile of one (tap, 64-channel chunk)
     // transposed (level 0, 2 channel chunks per tile): the epilogue is on the critical path -> two warps per
     // TMEM lane quadrant, paid for with one weight stage; deep-K layers keep four stages and four warps
     // (measured alternatives, 128->128 @1024^2 x2, no residual / residual: 3 halo + 3 stages + 8 epilogue + 4
     // transform warps 535/605 us; 2 halo + 6 stages 554/607; 4 epilogue warps + 4 stages 507/720; this one 518/608)
-    static constexpr int BSTAGES = TR ? 3 : 4;
+    static constexpr int BSTAGES = TR ? 3 : (PAIR ? 8 : 4);
     static constexpr int EPI_WARPS = TR ? 8 : 4;
     static constexpr int XF_WARPS = TR ? 8 : 4;   // level 0 has 2 channel chunks per tile: the transform is on the critical path
     static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
@@ -59,6 +64,7 @@ struct Conv3Cfg {
     static_assert(2 * ACC_COLS <= 512, "two accumulator sets must fit TMEM");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(!TR || (BLOCK_N == 128 && MT == 1), "transposed variant: 128 channels x (8x32) pixels");
+    static_assert(!PAIR || (!TR && MT == 1), "pair variant: non-transposed, one sub-tile per CTA");
 };
 
 // Epilogue of the transposed variant: TMEM lane = output channel, column = pixel.  Each epilogue warp
@@ -275,11 +281,11 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
     if (STATS) flush_stats();
 }
 
-template <int BLOCK_N, int MT, bool TR>
-__global__ void __launch_bounds__(Conv3Cfg<BLOCK_N, MT, TR>::THREADS, 1)
+template <int BLOCK_N, int MT, bool TR, bool PAIR>
+__global__ void __launch_bounds__(Conv3Cfg<BLOCK_N, MT, TR, PAIR>::THREADS, 1)
 conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmS, const __grid_constant__ IgemmParams P) {
-    using Cfg = Conv3Cfg<BLOCK_N, MT, TR>;
+    using Cfg = Conv3Cfg<BLOCK_N, MT, TR, PAIR>;
     constexpr int NHALO = Cfg::NHALO, BST = Cfg::BSTAGES, HWID = Cfg::HWID, HROWS = Cfg::HROWS;
 
     extern __shared__ uint8_t smem_raw[];
@@ -301,6 +307,7 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // pair kernels: rank 0 (leader) issues every MMA
     const uint32_t tiles_per_img = static_cast<uint32_t>(P.tiles_x * P.tiles_y);
     const uint32_t total_tiles = static_cast<uint32_t>(P.NB) * tiles_per_img * static_cast<uint32_t>(P.n_blocks);
     const int nchunks = P.cin_chunks;
@@ -315,7 +322,7 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tma_prefetch_desc(&tmS);
         for (int i = 0; i < NHALO; ++i) {
             mbar_init(&halo_full[i], 1);
-            mbar_init(&halo_ready[i], Cfg::XF_WARPS);
+            mbar_init(&halo_ready[i], (PAIR ? 2 : 1) * Cfg::XF_WARPS);   // pair: both CTAs' transform warps, on the leader
             mbar_init(&halo_free[i], 1);
         }
         for (int i = 0; i < BST; ++i) {
@@ -324,22 +331,27 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], Cfg::EPI_WARPS);
+            mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * Cfg::EPI_WARPS);
         }
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (PAIR) { tmem_alloc_pair(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // the peer's barriers exist before any remote arrive / TMA signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    // pair kernels number the tiles ((pixel-pair * n_blocks + n-block) * 2 + rank): blockIdx.x + k * gridDim.x
+    // (gridDim.x even) keeps the rank, and the two CTAs of a cluster walk the same (pixel-pair, n-block) sequence
     auto decode = [&](uint32_t tile, int& nb, int& x0, int& y0, int& img) {
-        nb = static_cast<int>(tile % static_cast<uint32_t>(P.n_blocks));
-        uint32_t m = tile / static_cast<uint32_t>(P.n_blocks);
+        const uint32_t tq = PAIR ? (tile >> 1) : tile;
+        nb = static_cast<int>(tq % static_cast<uint32_t>(P.n_blocks));
+        uint32_t m = tq / static_cast<uint32_t>(P.n_blocks);
+        if (PAIR) m = 2u * m + (tile & 1u);
         const int tx = static_cast<int>(m % static_cast<uint32_t>(P.tiles_x));
         m /= static_cast<uint32_t>(P.tiles_x);
         const int ty = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
@@ -383,10 +395,17 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const int ntaps = c < nchunks ? 9 : 1;
                     for (int tap = 0; tap < ntaps; ++tap) {
                         mbar_wait(&b_empty[bs], bphase ^ 1);
-                        mbar_arrive_expect_tx(&b_full[bs], Cfg::B_BYTES);
                         const int kb = c < nchunks ? tap * P.gn_C + c * IGEMM_BLOCK_K
                                                    : 9 * P.gn_C + (c - nchunks) * IGEMM_BLOCK_K;
-                        tma_load_3d(s_b + bs * Cfg::B_BYTES, &tmB, &b_full[bs], kb, n0, 0);
+                        if constexpr (PAIR) {
+                            // this CTA's half of the weight rows; both halves are counted on the leader's barrier
+                            if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2 * Cfg::B_BYTES);
+                            tma_load_3d_pair(s_b + bs * Cfg::B_BYTES, &tmB, &b_full[bs], kb,
+                                             n0 + static_cast<int>(rank) * Cfg::B_ROWS, 0);
+                        } else {
+                            mbar_arrive_expect_tx(&b_full[bs], Cfg::B_BYTES);
+                            tma_load_3d(s_b + bs * Cfg::B_BYTES, &tmB, &b_full[bs], kb, n0, 0);
+                        }
                         if (++bs == BST) { bs = 0; bphase ^= 1; }
                     }
                 }
@@ -397,9 +416,17 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ------------------------------------------------------------ MMA issuer
         // The whole warp walks the loops (warp-uniform control flow keeps the descriptors in uniform
         // registers); one elected lane issues the MMAs and commits.
-        {
-            // fp16 x fp16; transposed: M = 128 channels, N = 256 pixels
-            constexpr uint32_t idesc = umma_idesc_16(IGEMM_BLOCK_M, TR ? 256 : BLOCK_N, true);
+        if (rank == 0) {
+            // fp16 x fp16; transposed: M = 128 channels, N = 256 pixels; pair: M = 2 x 128 pixels
+            constexpr uint32_t idesc = umma_idesc_16(PAIR ? 256 : IGEMM_BLOCK_M, TR ? 256 : BLOCK_N, true);
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accum) {
+                if constexpr (PAIR) umma_f16_ss_pair(d, a, b, id, accum);
+                else umma_bf16_ss(d, a, b, id, accum);
+            };
+            auto commit = [&](uint64_t* bar) {
+                if constexpr (PAIR) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
             const uint64_t dw_base = umma_desc_k_sw128(smem_u32(s_b));                       // weight tile, stage 0
             const uint64_t dh_base = umma_desc_k_sw128(smem_u32(s_halo), HWID * 128);        // halo tile, buffer 0
             int hb = 0, bs = 0;
@@ -428,16 +455,16 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                 if constexpr (TR) {
                                     // A = weights (128 channels), B = halo view: 32 image rows of 8 pixels, one
                                     // 8-row group per image row, HWID halo pixels apart
-                                    umma_bf16_ss(tmem_d, dw + 2 * k, dh + ((dy * HWID + dx) * 8 + 2 * k), idesc, first | k);
+                                    mma(tmem_d, dw + 2 * k, dh + ((dy * HWID + dx) * 8 + 2 * k), idesc, first | k);
                                 } else {
 #pragma unroll
                                     for (int t = 0; t < MT; ++t)
-                                        umma_bf16_ss(tmem_d + t * BLOCK_N, dh + ((dy * HWID + dx + 8 * t) * 8 + 2 * k),
-                                                     dw + 2 * k, idesc, first | k);
+                                        mma(tmem_d + t * BLOCK_N, dh + ((dy * HWID + dx + 8 * t) * 8 + 2 * k), dw + 2 * k, idesc,
+                                            first | k);
                                 }
                             }
-                            umma_commit(&b_empty[bs]);
-                            if (tap == 8) umma_commit(&halo_free[hb]);
+                            commit(&b_empty[bs]);
+                            if (tap == 8) commit(&halo_free[hb]);
                         }
                         __syncwarp();
                         first = 1;
@@ -446,7 +473,7 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (++hb == NHALO) { hb = 0; hphase ^= 1; }
                 }
                 if constexpr (!TR) {
-                    constexpr uint32_t idesc_sc = umma_idesc_16(IGEMM_BLOCK_M, BLOCK_N, false);   // bf16 x bf16
+                    constexpr uint32_t idesc_sc = umma_idesc_16(PAIR ? 256 : IGEMM_BLOCK_M, BLOCK_N, false);   // bf16 x bf16
                     const uint64_t dx_base = umma_desc_k_sw128(smem_u32(s_halo));                 // plain tile: 1024 B groups
                     for (int c = 0; c < sc_chunks; ++c) {
                         mbar_wait(&halo_ready[hb], hphase);
@@ -457,16 +484,16 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < IGEMM_BLOCK_K / 16; ++k)
-                                umma_bf16_ss(tmem_d, dx + 2 * k, dw + 2 * k, idesc_sc, 1u);
-                            umma_commit(&b_empty[bs]);
-                            umma_commit(&halo_free[hb]);
+                                mma(tmem_d, dx + 2 * k, dw + 2 * k, idesc_sc, 1u);
+                            commit(&b_empty[bs]);
+                            commit(&halo_free[hb]);
                         }
                         __syncwarp();
                         if (++bs == BST) { bs = 0; bphase ^= 1; }
                         if (++hb == NHALO) { hb = 0; hphase ^= 1; }
                     }
                 }
-                if (elect_one()) umma_commit(&tfull_bar[acc]);
+                if (elect_one()) commit(&tfull_bar[acc]);
                 __syncwarp();
             }
         }
@@ -584,14 +611,20 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 // generic-proxy writes -> visible to the tensor core's async proxy, then signal the MMA warp
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&halo_ready[hb]);
+                if (lane == 0) {
+                    if constexpr (PAIR) mbar_arrive_cluster_cta(&halo_ready[hb], 0);
+                    else mbar_arrive(&halo_ready[hb]);
+                }
                 if (++hb == NHALO) { hb = 0; hphase ^= 1; }
             }
             for (int c = 0; c < sc_chunks; ++c) {
                 // shortcut operand: raw bf16 tile, nothing to rewrite -- hand it straight to the MMA warp
                 mbar_wait(&halo_full[hb], hphase);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&halo_ready[hb]);
+                if (lane == 0) {
+                    if constexpr (PAIR) mbar_arrive_cluster_cta(&halo_ready[hb], 0);
+                    else mbar_arrive(&halo_ready[hb]);
+                }
                 if (++hb == NHALO) { hb = 0; hphase ^= 1; }
             }
         }
@@ -599,9 +632,11 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // neither CTA leaves while the pair still signals / computes
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 

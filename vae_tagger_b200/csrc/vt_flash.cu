@@ -265,7 +265,7 @@ flash_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&p_full[sb], 0);   // the leader issues P V for both CTAs
+            if (lane == 0) mbar_arrive_cluster_relaxed(&p_full[sb], 0);   // the leader issues P V for both CTAs
         }
         // ---- epilogue: O / l + b_v -> fp16 global; the row sum is the two threads' parts added up
         {

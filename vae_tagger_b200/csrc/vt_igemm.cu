@@ -235,19 +235,34 @@ int launch_conv_in(const ConvInOp& op, cudaStream_t stream, Profiler* prof) {
     return 0;
 }
 
-template <int BLOCK_N, int MT, bool TR>
+template <int BLOCK_N, int MT, bool TR, bool PAIR>
 static int launch_conv3_variant(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sc, const IgemmParams& P,
                                 cudaStream_t stream) {
-    using Cfg = Conv3Cfg<BLOCK_N, MT, TR>;
+    using Cfg = Conv3Cfg<BLOCK_N, MT, TR, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
-        VT_CUDA(cudaFuncSetAttribute(conv3_fused_kernel<BLOCK_N, MT, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VT_CUDA(cudaFuncSetAttribute(conv3_fused_kernel<BLOCK_N, MT, TR, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y * P.n_blocks;
-    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    conv3_fused_kernel<BLOCK_N, MT, TR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, b, sc, P);
+    int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    if (!PAIR) {
+        conv3_fused_kernel<BLOCK_N, MT, TR, PAIR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, b, sc, P);
+    } else {
+        grid &= ~1;   // whole clusters of two CTAs (tiles is even: the launcher checked)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(Cfg::THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        VT_CUDA(cudaLaunchKernelEx(&cfg, conv3_fused_kernel<BLOCK_N, MT, TR, PAIR>, a, b, sc, P));
+    }
     VT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -290,6 +305,11 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
     VT_CHECK(op.sc_in == nullptr || (!tr && op.Cs % 64 == 0 && op.Cs > 0), "fused conv: shortcut slab needs Cout >= 256 and Cs % 64 == 0");
     P.sc_chunks = op.sc_in ? op.Cs / 64 : 0;
 
+    // CTA pairs for the 256-wide variant when the pixel tiles pair up (VT_B200_NO_PAIR=1: single-CTA kernel)
+    static const bool no_pair = [] { const char* e = getenv("VT_B200_NO_PAIR"); return e && e[0] == '1'; }();
+    const bool pair = !tr && !no_pair && ((1LL * op.N * P.tiles_x * P.tiles_y) % 2 == 0) && num_sms() >= 2;
+    P.pair = pair ? 1 : 0;
+
     CUtensorMap a, b, sc;
     VT_TRY(make_act_map(&a, op.in, op.N, H, W, op.Cin, 1, pxw + 2, pxh + 2));
     if (op.sc_in) VT_TRY(make_act_map(&sc, op.sc_in, op.N, H, W, op.Cs, 1, pxw, pxh));
@@ -298,13 +318,15 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
         const int Ktot = 9 * op.Cin + (op.sc_in ? op.Cs : 0);
         uint64_t dims[3] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(op.Cout), 1};
         uint64_t str[2] = {2ull * Ktot, 2ull * Ktot * op.Cout};
-        uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
+        uint32_t box[3] = {64, static_cast<uint32_t>(pair ? block_n / 2 : block_n), 1};
         VT_TRY(make_tmap(&b, op.w, 3, dims, str, box));
     }
     const double flops = 2.0 * op.N * H * W * static_cast<double>(op.Cout) * (9 * op.Cin + (op.sc_in ? op.Cs : 0));
     const double bytes = 2.0 * op.N * H * W * (1.0 * op.Cin + op.Cout);
     profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
-    int rc = tr ? launch_conv3_variant<128, 1, true>(a, b, sc, P, stream) : launch_conv3_variant<256, 1, false>(a, b, sc, P, stream);
+    int rc = tr ? launch_conv3_variant<128, 1, true, false>(a, b, sc, P, stream)
+                : pair ? launch_conv3_variant<256, 1, false, true>(a, b, sc, P, stream)
+                       : launch_conv3_variant<256, 1, false, false>(a, b, sc, P, stream);
     profiler_end(prof, KC_IGEMM, stream);
     return rc;
 }

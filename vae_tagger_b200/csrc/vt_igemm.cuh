@@ -72,6 +72,7 @@ struct IgemmParams {
     int gn_silu;
     int cin_chunks;          // Cin / 64
     int sc_chunks;           // Cs / 64: 1x1 shortcut slab (0 = none)
+    int pair;                // CTA-pair kernel: tile index = ((pixel-pair * n_blocks + n-block) * 2 + cluster rank)
 };
 
 template <int BLOCK_N, int MT>  // MT = 128-row sub-tiles per CTA tile (2: two pixel tiles share every weight chunk)
@@ -163,8 +164,11 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
         unsigned vmask[MT];
     };
     auto geometry = [&](uint32_t tile, Geo& g) {
-        g.nb = static_cast<int>(tile % static_cast<uint32_t>(P.n_blocks));
-        uint32_t m = tile / static_cast<uint32_t>(P.n_blocks);
+        const uint32_t rk = P.pair ? (tile & 1u) : 0u;
+        const uint32_t tq = P.pair ? (tile >> 1) : tile;
+        g.nb = static_cast<int>(tq % static_cast<uint32_t>(P.n_blocks));
+        uint32_t m = tq / static_cast<uint32_t>(P.n_blocks);
+        if (P.pair) m = 2u * m + rk;
         const int tx = static_cast<int>(m % static_cast<uint32_t>(P.tiles_x));
         m /= static_cast<uint32_t>(P.tiles_x);
         const int ty = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
@@ -274,7 +278,11 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
                         // this warp's part of the accumulator set is read: hand the TMEM buffer back
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        if (lane == 0) {
+                            // pair kernels: the leader CTA issues the MMAs into both CTAs' accumulators
+                            if (P.pair) mbar_arrive_cluster_relaxed(&tempty_bar[acc], 0);
+                            else mbar_arrive(&tempty_bar[acc]);
+                        }
                     }
                     const uint32_t dst = stg + lane * RF * 4;
 #pragma unroll

@@ -101,12 +101,35 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.
+// release.cluster orders this thread's earlier (generic-proxy) memory writes before the arrive -- it
+// compiles to MEMBAR.ALL.GPU + ERRBAR, hundreds of cycles
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+// default semantics (release at CTA scope): the signalling thread's own earlier writes -- e.g. operand rows it
+// rewrote in ITS shared memory and published to the async proxy with fence.proxy.async -- are ordered before
+// the arrive; nothing has to become visible to the remote CTA's threads, only to the local tensor core
+__device__ __forceinline__ void mbar_arrive_cluster_cta(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+// the same without memory ordering: for hand-offs whose payload is in TENSOR memory (made visible by
+// tcgen05.wait::st + tcgen05.fence::before_thread_sync), where there is nothing in the generic proxy to publish
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
         "r"(cta)
         : "memory");
 }
