@@ -208,19 +208,23 @@ flash_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             for (int cchunk = 0; cchunk < 2; ++cchunk)
                 tmem_ld_32x32(tmem_s + sb * FK + hs * 64 + cchunk * 32 + lane_sel, r[cchunk]);
             tmem_ld_wait();
-            // scale to log2 units, mask keys beyond the sequence, row maximum (four independent chains)
+            // row maximum of the raw scores (four independent chains); the softmax scale is positive, so it is
+            // applied to the maximum here and folded into one FFMA per element below.  Keys beyond the sequence
+            // exist only in a ragged last tile: masked to -inf there, no per-element test anywhere else.
             const int key0 = j * FK + hs * 64;
+            if (key0 + 64 > tokens) {
+#pragma unroll
+                for (int cchunk = 0; cchunk < 2; ++cchunk)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (key0 + cchunk * 32 + i >= tokens) r[cchunk][i] = __float_as_uint(-INFINITY);
+            }
             float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
             for (int cchunk = 0; cchunk < 2; ++cchunk)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float v = __uint_as_float(r[cchunk][i]) * scale_log2;
-                    if (key0 + cchunk * 32 + i >= tokens) v = -INFINITY;
-                    r[cchunk][i] = __float_as_uint(v);
-                    mx4[i & 3] = fmaxf(mx4[i & 3], v);
-                }
-            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+                for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[cchunk][i]));
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_log2;
             // the other half of the row lives in the partner warp: exchange the maxima
             float* xs = xchg + (j & 1) * (2 * FQ);
             xs[hs * FQ + row] = mx;
@@ -255,8 +259,8 @@ flash_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float a = fast_exp2(__uint_as_float(r[cc][2 * i]) - m_used);
-                    const float b = fast_exp2(__uint_as_float(r[cc][2 * i + 1]) - m_used);
+                    const float a = fast_exp2(fmaf(__uint_as_float(r[cc][2 * i]), scale_log2, -m_used));
+                    const float b = fast_exp2(fmaf(__uint_as_float(r[cc][2 * i + 1]), scale_log2, -m_used));
                     ls4[i & 3] += a + b;
                     pk[cc * 16 + i] = pack_f16x2(a, b);
                 }
