@@ -298,7 +298,8 @@ def run_ours(args):
         "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"],
         "frac_of_burst_peak": achieved / peaks["burst"], "peak_source": peaks["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
         "launches_per_step": ig["launches"] / 2, "avg_launch_ms": ig["ms"] / max(1.0, ig["launches"]),
-        "kernel_ms_per_step": ig["ms"] / 2, "algorithmic_flop_per_step": flops_per_image(R) * B, "traffic": None,
+        "kernel_ms_per_step": ig["ms"] / 2, "algorithmic_flop_per_step": flops_per_image(R) * B,
+        "traffic": traffic_per_launch(R, B, ig["launches"] / 2),
         "per_class_ms_per_step": {k: v["ms"] / 2 for k, v in prof_t.items() if v["launches"]},
         "whole_step_frac_of_burst": (value / world) * flops_per_image(R) / 1e12 / peaks["burst"],
     }
@@ -321,6 +322,18 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def traffic_per_launch(R, B, launches_per_step):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per tensor-kernel launch, from the committed
+    ``ncu --set full`` capture of one 1024^2 image (profiles/r01_dram_traffic_v20.json) scaled to this step's
+    images per launch; None for other resolutions or when the capture is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_dram_traffic_v20.json")
+    if R != 1024 or not os.path.exists(path) or not launches_per_step:
+        return None
+    with open(path, "r", encoding="utf-8") as f:
+        t = json.load(f)["per_image_all_tensor_kernels"]
+    return (t["dram_read_MB"] + t["dram_write_MB"]) * 1e6 * B / launches_per_step
 
 
 def main():
