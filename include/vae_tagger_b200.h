@@ -148,6 +148,56 @@ int vt_focal_loss(vt_ctx* ctx, const float* logits, const float* targets, int64_
                   float grad_scale, float* loss_sum /* device, 1 float, accumulated */,
                   float* grad /* device [n], optional */, void* stream);
 
+/* ---------------------------------------------------------------- head training step
+ * Replaces, for one batch, the autograd graph of the reference training step
+ * (train_decoder.py:186-195): decoder.train(); logits = decoder(latent);
+ * loss = loss_fn(logits, labels); loss.backward() -- for the head configured with
+ * vt_head_configure (AttentionClassificationDecoder without cross-attention, modules.py:358-468, or
+ * ClassificationDecoder, modules.py:303-349).  The latent is the frozen encoder's output and gets
+ * no gradient.  Parameters are read from, and gradients ACCUMULATED (+=) into, caller-owned flat
+ * fp32 device buffers laid out like the reference module's parameters() -- vt_head_param_layout
+ * gives the offsets; the same flat gradient buffer is what the data-parallel step all-reduces
+ * (train_decoder.py:39 accelerate/DDP).  BatchNorm2d runs on batch statistics and updates the
+ * running buffers in place.  nn.BCEWithLogitsLoss is focal_alpha = 1, focal_gamma = 0. */
+int vt_head_param_count(vt_ctx* ctx, int32_t* n_tensors, int64_t* n_floats);
+/* index in [0, n_tensors): state-dict key (copied into name, NUL-terminated), offset and size in floats */
+int vt_head_param_layout(vt_ctx* ctx, int32_t index, char* name, int32_t name_cap, int64_t* offset,
+                         int64_t* numel);
+
+typedef struct vt_head_train_args {
+    const float* latent;  /* device [B,LC,h,w] fp32 NCHW (DiffusersVAEWrapper.encode output) */
+    const float* targets; /* device [B,T] multi-hot labels */
+    int batch, lat_h, lat_w;
+    const float* params; /* device, flat, vt_head_param_layout order */
+    float* grads;        /* device, flat, same layout, accumulated; NULL = forward + loss only */
+    float* bn_running_mean;          /* device [LC/2], updated in place (feature_compress.1); may be NULL */
+    float* bn_running_var;           /* device [LC/2] */
+    int64_t* bn_num_batches_tracked; /* device scalar, += 1; may be NULL */
+    float bn_momentum;               /* 0.1 */
+    float focal_alpha, focal_gamma;  /* FocalLoss (improved_losses.py:47-56), reduction = mean */
+    float loss_scale;                /* 1 / gradient_accumulation_steps: scales loss and gradients */
+    int dropout;                     /* 1: Dropout layers active (module.train()); 0: identity */
+    float attention_dropout;         /* p of MultiHeadSelfAttention.dropout (modules.py:64) */
+    uint64_t seed;                   /* dropout mask stream of this step */
+    float* loss;   /* device scalar, += loss_scale * mean loss; may be NULL */
+    float* logits; /* optional out, device [B,T] */
+    void* stream;
+} vt_head_train_args;
+int vt_head_train_step(vt_ctx* ctx, const vt_head_train_args* args);
+
+/* The dropout keep-masks (0/1 floats) vt_head_train_step uses for (seed, batch): attn [B,heads,64,64],
+ * cls[i] [B, width of classifier block i].  For parity tests: the oracle applies the same masks. */
+int vt_head_dropout_masks(vt_ctx* ctx, int batch, float attention_dropout, uint64_t seed, float* attn,
+                          float* cls0, float* cls1, float* cls2, void* stream);
+
+/* Replaces clip_grad_norm_(max_grad_norm) + torch.optim.AdamW.step() + zero_grad
+ * (train_decoder.py:197-203) on flat device buffers: g *= grad_scale (1/world after the all-reduce),
+ * clipped to max_norm (<= 0: no clipping), decoupled weight decay, bias correction for `step` (1-based).
+ * norm_out (device scalar, optional) receives the gradient norm before clipping. */
+int vt_adamw_step(vt_ctx* ctx, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                  float max_norm, int zero_grad, float* norm_out, void* stream);
+
 /* ---------------------------------------------------------------- accounting
  * Kernel classes: 0 implicit GEMM (tcgen05), 1 GroupNorm, 2 conv_in gather, 3 softmax,
  * 4 latent, 5 head, 6 fp32-mode contraction, 7 misc. */

@@ -17,7 +17,11 @@ Reference lines followed:
   * ClassificationDecoder (--no_attention) . modules.py:303-356
   * threshold loop ......................... infer_full.py:109-124
   * FocalLoss.forward ...................... improved_losses.py:47-56
-All in eval mode (dropout identity, BatchNorm running statistics).
+Eval mode (dropout identity, BatchNorm running statistics) unless a function says otherwise; the
+``*_train`` functions restate module.train() semantics (batch-statistics BatchNorm with running-buffer
+update, Dropout with EXPLICIT keep-masks so that a checker can apply the masks of the path under test)
+and are pinned by ``tests/golden/head_train_golden.pt`` (reference modules in train mode, gradients by
+the reference's own autograd graph; ``tests/golden/make_train_golden.py``).
 """
 from __future__ import annotations
 
@@ -139,3 +143,110 @@ def focal_loss_grad(logits: torch.Tensor, targets: torch.Tensor, alpha=1.0, gamm
     x = logits.detach().clone().requires_grad_(True)
     focal_loss(x, targets, alpha, gamma).backward()
     return x.grad
+
+
+# ----------------------------------------------------------------------------- train mode
+CLASSIFIER_DROPOUT = (0.3, 0.2, 0.1)          # modules.py:405,410,415
+PLAIN_CLASSIFIER_DROPOUT = (0.3, 0.2)         # modules.py:321,326
+
+
+def _drop(x: torch.Tensor, mask, p: float) -> torch.Tensor:
+    """nn.Dropout(p) in train mode with an explicit keep-mask (None = identity)."""
+    return x if mask is None else x * mask / (1.0 - p)
+
+
+def feature_compress_train(sd: dict, x: torch.Tensor, momentum=0.1, prefix="feature_compress."):
+    """modules.py:377-382 in train mode.  Returns (pooled, new running_mean, new running_var)."""
+    y = F.conv2d(x, sd[prefix + "0.weight"], sd[prefix + "0.bias"], padding=1)
+    rm, rv = sd[prefix + "1.running_mean"].clone(), sd[prefix + "1.running_var"].clone()
+    y = F.batch_norm(y, rm, rv, sd[prefix + "1.weight"], sd[prefix + "1.bias"], training=True, momentum=momentum,
+                     eps=1e-5)
+    return F.adaptive_avg_pool2d(F.relu(y), (8, 8)), rm, rv
+
+
+def self_attention_train(sd: dict, x: torch.Tensor, heads: int = 8, attn_mask=None, p=0.1,
+                         prefix="self_attention_post.") -> torch.Tensor:
+    """modules.py:66-91 with the dropout of :81 applied through ``attn_mask`` [B,heads,N,N]."""
+    b, c, h, w = x.shape
+    n, hd = h * w, c // heads
+    xf = x.reshape(b, c, n).transpose(1, 2)
+    t = F.layer_norm(xf, (c,), sd[prefix + "norm.weight"], sd[prefix + "norm.bias"], eps=1e-5)
+
+    def proj(name):
+        y = F.linear(t, sd[prefix + name + ".weight"], sd[prefix + name + ".bias"])
+        return y.reshape(b, n, heads, hd).transpose(1, 2)
+
+    q, k, v = proj("q_proj"), proj("k_proj"), proj("v_proj")
+    pw = _drop(torch.softmax(torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(hd), dim=-1), attn_mask, p)
+    o = torch.matmul(pw, v).transpose(1, 2).reshape(b, n, c)
+    o = F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"]) + xf
+    return o.transpose(1, 2).reshape(b, c, h, w)
+
+
+def attention_decoder_train(sd: dict, latent: torch.Tensor, heads: int = 8, use_spatial_attention=True,
+                            use_self_attention=True, attn_mask=None, attention_dropout=0.1, cls_masks=None,
+                            momentum=0.1):
+    """AttentionClassificationDecoder.forward (modules.py:424-468) under module.train().
+    Returns (logits, new running_mean, new running_var)."""
+    x = latent
+    if use_spatial_attention:
+        x = spatial_attention(sd, x)
+    x, rm, rv = feature_compress_train(sd, x, momentum)
+    if use_self_attention:
+        x = self_attention_train(sd, x, heads, attn_mask, attention_dropout)
+    f = x.reshape(x.shape[0], -1)
+    for i, (lin, ln) in enumerate(((0, 1), (4, 5), (8, 9))):
+        f = F.linear(f, sd[f"classifier.{lin}.weight"], sd[f"classifier.{lin}.bias"])
+        f = F.relu(F.layer_norm(f, (f.shape[-1],), sd[f"classifier.{ln}.weight"], sd[f"classifier.{ln}.bias"],
+                                eps=1e-5))
+        f = _drop(f, None if cls_masks is None else cls_masks[i], CLASSIFIER_DROPOUT[i])
+    return F.linear(f, sd["classifier.12.weight"], sd["classifier.12.bias"]), rm, rv
+
+
+def plain_decoder_train(sd: dict, latent: torch.Tensor, cls_masks=None) -> torch.Tensor:
+    """ClassificationDecoder.forward (modules.py:335-349) under module.train()."""
+    f = F.adaptive_avg_pool2d(latent, (4, 4)).reshape(latent.shape[0], -1)
+    for i, (lin, ln) in enumerate(((0, 1), (4, 5))):
+        f = F.linear(f, sd[f"classifier.{lin}.weight"], sd[f"classifier.{lin}.bias"])
+        f = F.layer_norm(f, (f.shape[-1],), sd[f"classifier.{ln}.weight"], sd[f"classifier.{ln}.bias"], eps=1e-5)
+        f = _drop(F.leaky_relu(f, 0.2), None if cls_masks is None else cls_masks[i], PLAIN_CLASSIFIER_DROPOUT[i])
+    return F.linear(f, sd["classifier.8.weight"], sd["classifier.8.bias"])
+
+
+NON_TRAINABLE = ("running_mean", "running_var", "num_batches_tracked")
+
+
+def head_train_step(sd: dict, latent, targets, alpha=1.0, gamma=2.0, kind="attention", dtype=torch.float32, **kw):
+    """One reference training step on the head (train_decoder.py:186-195 without the optimizer):
+    train-mode forward, FocalLoss(alpha, gamma) mean, autograd backward.
+    Returns dict(loss, logits, grads{key: tensor}, running_mean, running_var).
+    ``dtype=torch.float64`` evaluates the same graph in double precision (a tighter ground truth for
+    gradients that are long cancelling sums); results are returned in that dtype."""
+    def cast(v):
+        return v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v
+
+    latent, targets = cast(latent), cast(targets)
+    kw = {k: ([cast(m) for m in v] if isinstance(v, (list, tuple)) else cast(v)) for k, v in kw.items()}
+    leaf = {k: (cast(v.detach().clone()).requires_grad_(True) if not k.endswith(NON_TRAINABLE)
+                else cast(v.detach().clone())) for k, v in sd.items()}
+    if kind == "attention":
+        logits, rm, rv = attention_decoder_train(leaf, latent, **kw)
+    else:
+        logits, rm, rv = plain_decoder_train(leaf, latent, **kw), None, None
+    loss = focal_loss(logits, targets, alpha, gamma)
+    loss.backward()
+    grads = {k: v.grad for k, v in leaf.items() if v.requires_grad and v.grad is not None}
+    return {"loss": loss.detach(), "logits": logits.detach(), "grads": grads, "running_mean": rm, "running_var": rv}
+
+
+def adamw_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, wd=1e-2, step=1, max_norm=0.0):
+    """clip_grad_norm_(max_norm) then torch.optim.AdamW's update on flat tensors (train_decoder.py:197-203).
+    Returns (p, m, v, grad norm before clipping)."""
+    norm = g.double().norm().float()
+    if max_norm > 0:
+        g = g * torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+    p = p * (1.0 - lr * wd)
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    denom = v.sqrt() / math.sqrt(1 - beta2 ** step) + eps
+    return p - (lr / (1 - beta1 ** step)) * m / denom, m, v, norm

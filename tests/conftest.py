@@ -27,3 +27,11 @@ def golden():
     import torch
 
     return torch.load(os.path.join(ROOT, "tests", "golden", "head_golden.pt"), map_location="cpu", weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def train_golden():
+    import torch
+
+    return torch.load(os.path.join(ROOT, "tests", "golden", "head_train_golden.pt"), map_location="cpu",
+                      weights_only=False)

@@ -93,3 +93,48 @@ def test_downsample_pads_right_and_bottom_only():
     # last output row/column read the zero padding
     assert y.shape == (1, 4, 2, 2)
     assert y[0, 0, 0, 0] == 4 and y[0, 0, 1, 1] == 0 and y[0, 0, 0, 1] == 0
+
+
+# ----------------------------------------------------------------------------- training step
+def check_digest(got: torch.Tensor, want: dict, atol, rtol=1e-4):
+    if "full" in want:
+        torch.testing.assert_close(got, want["full"], atol=atol, rtol=rtol)
+    else:
+        torch.testing.assert_close(got[:8], want["rows"], atol=atol, rtol=rtol)
+        torch.testing.assert_close(got.sum(1), want["rowsum"], atol=atol * 30, rtol=rtol)
+        torch.testing.assert_close(got.sum(0), want["colsum"], atol=atol * 30, rtol=rtol)
+
+
+@pytest.mark.parametrize("case", ["nodrop_3x20x36", "drop_4x32x32", "bce_2x16x24"])
+def test_head_train_oracle_matches_reference_autograd(golden, train_golden, case):
+    c = train_golden["attention"][case]
+    sd = full_sd(golden, "att_T11_64x64")
+    masks = c["masks"]
+    r = OH.head_train_step(sd, c["latent"], c["targets"], c["alpha"], c["gamma"],
+                           attn_mask=None if masks is None else masks[0],
+                           cls_masks=None if masks is None else masks[1:])
+    torch.testing.assert_close(r["logits"], c["logits"], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(r["loss"], c["loss"], atol=1e-7, rtol=1e-5)
+    torch.testing.assert_close(r["running_mean"], c["running_mean"], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(r["running_var"], c["running_var"], atol=1e-6, rtol=1e-5)
+    assert list(r["grads"]) == c["param_order"]
+    for k, want in c["grads"].items():
+        check_digest(r["grads"][k], want, atol=1e-7)
+
+
+def test_plain_head_train_oracle(train_golden, golden):
+    c = train_golden["plain"]
+    r = OH.head_train_step(golden["plain_head"]["state_dict"], c["latent"], c["targets"], kind="plain")
+    torch.testing.assert_close(r["logits"], c["logits"], atol=1e-5, rtol=1e-5)
+    assert list(r["grads"]) == c["param_order"]
+    for k, want in c["grads"].items():
+        check_digest(r["grads"][k], want, atol=1e-7)
+
+
+def test_adamw_oracle(train_golden):
+    a = train_golden["adamw"]
+    p, m, v = a["p0"], torch.zeros(1000), torch.zeros(1000)
+    for i, g in enumerate(a["grads"]):
+        p, m, v, norm = OH.adamw_step(p, g, m, v, a["lr"], wd=a["wd"], step=i + 1, max_norm=a["max_norm"])
+        torch.testing.assert_close(norm, a["norms"][i], atol=1e-6, rtol=1e-6)
+        torch.testing.assert_close(p, a["params"][i], atol=1e-7, rtol=1e-6)

@@ -67,6 +67,17 @@ class InferHostArgs(C.Structure):
     ]
 
 
+class HeadTrainArgs(C.Structure):
+    _fields_ = [
+        ("latent", C.c_void_p), ("targets", C.c_void_p), ("batch", C.c_int), ("lat_h", C.c_int), ("lat_w", C.c_int),
+        ("params", C.c_void_p), ("grads", C.c_void_p), ("bn_running_mean", C.c_void_p),
+        ("bn_running_var", C.c_void_p), ("bn_num_batches_tracked", C.c_void_p), ("bn_momentum", C.c_float),
+        ("focal_alpha", C.c_float), ("focal_gamma", C.c_float), ("loss_scale", C.c_float), ("dropout", C.c_int),
+        ("attention_dropout", C.c_float), ("seed", C.c_uint64), ("loss", C.c_void_p), ("logits", C.c_void_p),
+        ("stream", C.c_void_p),
+    ]
+
+
 # every symbol include/vae_tagger_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -84,6 +95,13 @@ SYMBOLS = {
     "vt_tag": (C.c_int, [_P, C.POINTER(TagArgs)]),
     "vt_infer_host": (C.c_int, [_P, C.POINTER(InferHostArgs)]),
     "vt_focal_loss": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, _P, _P, _P]),
+    "vt_head_param_count": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "vt_head_param_layout": (C.c_int, [_P, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64)]),
+    "vt_head_train_step": (C.c_int, [_P, C.POINTER(HeadTrainArgs)]),
+    "vt_head_dropout_masks": (C.c_int, [_P, C.c_int, C.c_float, C.c_uint64, _P, _P, _P, _P, _P]),
+    "vt_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64] + [C.c_float] * 5 + [C.c_int64, C.c_float, C.c_float,
+                                                                                  C.c_int, _P, _P]),
     "vt_profile_enable": (C.c_int, [_P, C.c_int]),
     "vt_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "vt_op_conv2d": (C.c_int, [_P, _P, _P, _P, _P, _P, _P] + [C.c_int] * 9 + [_P, _P, _P]),
@@ -323,6 +341,73 @@ class Context:
             _check(self.lib.vt_focal_loss(self.h, _ptr(x), _ptr(y), n, float(alpha), float(gamma), 1.0 / n, _ptr(loss),
                                           _ptr(grad), _stream(self.device)))
         return loss, grad
+
+    # ------------------------------------------------------------------ head training step
+    def head_param_layout(self):
+        """[(state-dict key, offset, numel)] of the flat parameter / gradient buffers, in the order of the
+        reference module's ``parameters()``; needs ``configure_head`` first."""
+        n, total = C.c_int32(), C.c_int64()
+        _check(self.lib.vt_head_param_count(self.h, C.byref(n), C.byref(total)))
+        out = []
+        buf = C.create_string_buffer(128)
+        for i in range(n.value):
+            off, numel = C.c_int64(), C.c_int64()
+            _check(self.lib.vt_head_param_layout(self.h, i, buf, 128, C.byref(off), C.byref(numel)))
+            out.append((buf.value.decode(), off.value, numel.value))
+        assert not out or out[-1][1] + out[-1][2] == total.value
+        return out
+
+    def head_train_step(self, latent, targets, flat_params, flat_grads=None, bn_running_mean=None,
+                        bn_running_var=None, bn_num_batches_tracked=None, bn_momentum=0.1, focal_alpha=1.0,
+                        focal_gamma=2.0, loss_scale=1.0, dropout=True, attention_dropout=0.1, seed=0, loss=None,
+                        want_logits=False):
+        """Train-mode forward + focal/BCE loss + backward of the configured head (``vt_head_train_step``).
+        Gradients are accumulated into ``flat_grads``; returns (loss accumulator tensor, logits or None)."""
+        lat = _f32c(latent, self.device)
+        tgt = _f32c(targets, self.device)
+        B, _, h, w = lat.shape
+        for t in (flat_params, flat_grads, bn_running_mean, bn_running_var):
+            assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+        assert bn_num_batches_tracked is None or bn_num_batches_tracked.dtype == torch.int64
+        if loss is None:
+            loss = torch.zeros(1, device=self.device, dtype=torch.float32)
+        logits = torch.empty(B, self.num_classes, device=self.device, dtype=torch.float32) if want_logits else None
+        a = HeadTrainArgs()
+        a.latent = lat.data_ptr(); a.targets = tgt.data_ptr(); a.batch = B; a.lat_h = h; a.lat_w = w
+        a.params = flat_params.data_ptr()
+        a.grads = flat_grads.data_ptr() if flat_grads is not None else None
+        a.bn_running_mean = bn_running_mean.data_ptr() if bn_running_mean is not None else None
+        a.bn_running_var = bn_running_var.data_ptr() if bn_running_var is not None else None
+        a.bn_num_batches_tracked = bn_num_batches_tracked.data_ptr() if bn_num_batches_tracked is not None else None
+        a.bn_momentum = float(bn_momentum); a.focal_alpha = float(focal_alpha); a.focal_gamma = float(focal_gamma)
+        a.loss_scale = float(loss_scale); a.dropout = int(bool(dropout))
+        a.attention_dropout = float(attention_dropout); a.seed = int(seed) & (2 ** 64 - 1)
+        a.loss = loss.data_ptr(); a.logits = logits.data_ptr() if logits is not None else None
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_head_train_step(self.h, C.byref(a)))
+        return loss, logits
+
+    def head_dropout_masks(self, batch, attention_dropout, seed, heads=8, widths=(1024, 512, 256)):
+        """The keep-masks (0/1) ``head_train_step`` uses for ``seed``: (attn [B,heads,64,64], [cls_i [B,width_i]])."""
+        attn = torch.empty(batch, heads, 64, 64, device=self.device, dtype=torch.float32)
+        cls = [torch.empty(batch, w, device=self.device, dtype=torch.float32) for w in widths]
+        ptrs = [_ptr(c) for c in cls] + [None] * (3 - len(cls))
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_head_dropout_masks(self.h, batch, float(attention_dropout), int(seed) & (2 ** 64 - 1),
+                                                  _ptr(attn), ptrs[0], ptrs[1], ptrs[2], _stream(self.device)))
+        return attn, cls
+
+    def adamw_step(self, params, grads, exp_avg, exp_avg_sq, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                   step=1, grad_scale=1.0, max_norm=0.0, zero_grad=True, norm_out=None):
+        """clip_grad_norm_ + AdamW + zero_grad on flat fp32 device buffers (``vt_adamw_step``)."""
+        for t in (params, grads, exp_avg, exp_avg_sq):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == params.numel()
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_adamw_step(self.h, _ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq),
+                                          params.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                          float(weight_decay), int(step), float(grad_scale), float(max_norm),
+                                          int(bool(zero_grad)), _ptr(norm_out), _stream(self.device)))
 
     # ------------------------------------------------------------------ accounting
     def profile_enable(self, timing: bool):

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../include/vae_tagger_b200.h"
+#include "vt_head_train.h"
 #include "vt_internal.h"
 #include "vt_ptx.cuh"
 
@@ -99,6 +100,7 @@ struct vt_ctx {
     DevBuf e2e;  // device staging of vt_infer_host
 
     DevBuf opws;  // single-op entry points
+    DevBuf optws; // optimizer scratch
 };
 
 namespace {
@@ -682,7 +684,7 @@ int vt_ctx_destroy(vt_ctx* c) {
         if (L.done) cudaEventDestroy(L.done);
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
-    c->hws.release(); c->e2e.release(); c->opws.release();
+    c->hws.release(); c->e2e.release(); c->opws.release(); c->optws.release();
     profiler_destroy(c->prof);
     delete c;
     return 0;
@@ -893,7 +895,7 @@ int vt_tag(vt_ctx* c, const vt_tag_args* a) {
             VT_TRY(launch_head_spatial_attention(a->latent, hp(c, "spatial_attention.channel_att.0.weight"),
                                                  hp(c, "spatial_attention.channel_att.2.weight"),
                                                  hp(c, "spatial_attention.spatial_att.0.weight"), ws + o_pool,
-                                                 ws + o_cg, ws + o_map, ws + o_x2, B, C, H, W, s, pf));
+                                                 ws + o_cg, ws + o_map, ws + o_x2, nullptr, B, C, H, W, s, pf));
             x = ws + o_x2;
         }
         VT_TRY(launch_head_compress(x, hp(c, "feature_compress.0.weight"), hp(c, "feature_compress.0.bias"),
@@ -945,6 +947,63 @@ int vt_tag(vt_ctx* c, const vt_tag_args* a) {
         VT_TRY(launch_head_confidence(logits, a->conf_sorted, reinterpret_cast<long long*>(a->idx_sorted), a->count,
                                       a->probs, B, T, a->threshold, s, pf));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------- head training
+int vt_head_param_count(vt_ctx* c, int32_t* n_tensors, int64_t* n_floats) {
+    VT_CHECK(c != nullptr && c->hcfg_set, "vt_head_configure has not been called");
+    const auto L = head_param_layout(c->hcfg);
+    if (n_tensors) *n_tensors = static_cast<int32_t>(L.size());
+    if (n_floats) *n_floats = L.empty() ? 0 : L.back().offset + L.back().numel;
+    return 0;
+}
+
+int vt_head_param_layout(vt_ctx* c, int32_t index, char* name, int32_t name_cap, int64_t* offset, int64_t* numel) {
+    VT_CHECK(c != nullptr && c->hcfg_set, "vt_head_configure has not been called");
+    const auto L = head_param_layout(c->hcfg);
+    VT_CHECK(index >= 0 && index < static_cast<int32_t>(L.size()), "parameter index out of range");
+    const auto& e = L[index];
+    if (name) {
+        VT_CHECK(name_cap > static_cast<int32_t>(e.name.size()), "name buffer too small");
+        std::copy(e.name.begin(), e.name.end(), name);
+        name[e.name.size()] = 0;
+    }
+    if (offset) *offset = e.offset;
+    if (numel) *numel = e.numel;
+    return 0;
+}
+
+int vt_head_train_step(vt_ctx* c, const vt_head_train_args* a) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr, "null arguments");
+    VT_CHECK(c->hcfg_set, "vt_head_configure has not been called");
+    VT_CHECK(a->latent && a->targets && a->params, "latent, targets and params are required");
+    VT_CHECK(a->batch > 0 && a->lat_h > 0 && a->lat_w > 0, "bad latent arguments");
+    VT_CHECK(a->attention_dropout >= 0.f && a->attention_dropout < 1.f, "attention_dropout must be in [0,1)");
+    if (c->hcfg.kind == VT_HEAD_ATTENTION)
+        VT_CHECK(1LL * a->batch * a->lat_h * a->lat_w > 1, "BatchNorm in train mode needs more than one value per channel");
+    VT_TRY(c->hws.ensure(head_train_workspace_floats(c->hcfg, a->batch, a->lat_h, a->lat_w) * sizeof(float)));
+    return head_train_step(c->hcfg, *a, static_cast<float*>(c->hws.p), c->prof);
+}
+
+int vt_head_dropout_masks(vt_ctx* c, int batch, float attention_dropout, uint64_t seed, float* attn, float* cls0,
+                          float* cls1, float* cls2, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(c->hcfg_set && batch > 0, "vt_head_configure has not been called");
+    float* cls[3] = {cls0, cls1, cls2};
+    return head_dropout_masks(c->hcfg, batch, attention_dropout, seed, attn, cls, static_cast<cudaStream_t>(stream));
+}
+
+int vt_adamw_step(vt_ctx* c, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                  float max_norm, int zero_grad, float* norm_out, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "bad optimizer arguments");
+    VT_TRY(c->optws.ensure(1184 * sizeof(double) + 64));
+    double* scratch = static_cast<double*>(c->optws.p);
+    float* norm = norm_out ? norm_out : reinterpret_cast<float*>(scratch + 1184);
+    return launch_adamw(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                        max_norm, scratch, norm, zero_grad, static_cast<cudaStream_t>(stream), c->prof);
 }
 
 // ------------------------------------------------------------------------------------- e2e

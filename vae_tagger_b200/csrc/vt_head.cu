@@ -4,43 +4,10 @@
 // batch on chip (everything is L2 resident), not tensor-core kernels.
 #include <math_constants.h>
 
+#include "vt_head_common.cuh"
 #include "vt_internal.h"
 
 namespace vt {
-
-__device__ __forceinline__ float h_warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
-}
-__device__ __forceinline__ float h_warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
-    return v;
-}
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-// block-wide sum / max of one value per thread (256 threads); result valid in all threads
-__device__ __forceinline__ float block_sum256(float v, float* red) {
-    v = h_warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i];
-    return t;
-}
-__device__ __forceinline__ float block_max256(float v, float* red) {
-    v = h_warp_max(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float t = red[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
-    return t;
-}
 
 // ---- SpatialAttention step 1 (modules.py:38-39): global average and max per (image, channel)
 // latent NCHW fp32; grid = N*C blocks; pool[n][c][0]=avg, [1]=max
@@ -110,7 +77,9 @@ __global__ void __launch_bounds__(256) head_spatial_gate_kernel(const float* __r
                                                                 const float* __restrict__ cgate,
                                                                 const float* __restrict__ map2,
                                                                 const float* __restrict__ w7,  // [1][2][7][7]
-                                                                float* __restrict__ y, int C, int H, int W) {
+                                                                float* __restrict__ y,
+                                                                float* __restrict__ sgate,  // [N][HW] or nullptr
+                                                                int C, int H, int W) {
     __shared__ float ws[98];
     __shared__ float g[64];
     const int n = blockIdx.y;
@@ -134,6 +103,7 @@ __global__ void __launch_bounds__(256) head_spatial_gate_kernel(const float* __r
             }
         }
         const float sg = sigmoidf_(a);
+        if (sgate) sgate[1LL * n * HW + p] = sg;
         for (int c = 0; c < C; ++c) {
             const long long o = (1LL * n * C + c) * HW + p;
             y[o] = x[o] * g[c] * sg;
@@ -426,8 +396,8 @@ __global__ void __launch_bounds__(256) focal_loss_kernel(const float* __restrict
 
 // =========================================================================================
 int launch_head_spatial_attention(const float* latent, const float* w1, const float* w2, const float* w7,
-                                  float* pool, float* cgate, float* map2, float* out, int N, int C, int H, int W,
-                                  cudaStream_t s, Profiler* prof) {
+                                  float* pool, float* cgate, float* map2, float* out, float* sgate, int N, int C,
+                                  int H, int W, cudaStream_t s, Profiler* prof) {
     VT_CHECK(C <= 64 && C % 8 == 0 && C / 8 <= 16, "SpatialAttention supports up to 64 channels");
     const int HW = H * W;
     profiler_begin(prof, KC_HEAD, s, 0, 4.0 * N * C * HW);
@@ -438,7 +408,7 @@ int launch_head_spatial_attention(const float* latent, const float* w1, const fl
     head_channel_gate_kernel<<<dim3(chunks, N), 256, 0, s>>>(latent, pool, w1, w2, cgate, map2, C, C / 8, HW);
     profiler_end(prof, KC_HEAD, s);
     profiler_begin(prof, KC_HEAD, s, 0, 4.0 * N * (2 * C + 2) * HW);
-    head_spatial_gate_kernel<<<dim3(chunks, N), 256, 0, s>>>(latent, cgate, map2, w7, out, C, H, W);
+    head_spatial_gate_kernel<<<dim3(chunks, N), 256, 0, s>>>(latent, cgate, map2, w7, out, sgate, C, H, W);
     profiler_end(prof, KC_HEAD, s);
     VT_CUDA(cudaGetLastError());
     return 0;

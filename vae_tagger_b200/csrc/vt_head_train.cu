@@ -1,0 +1,1242 @@
+// Training step of the tag-decoder head: train-mode forward + loss + analytic backward, fp32.
+//
+// Replaces, for one batch, the autograd graph of the reference step (train_decoder.py:186-195):
+//     decoder.train(); logits = decoder(latent); loss = loss_fn(logits, labels); loss.backward()
+// for AttentionClassificationDecoder (modules.py:358-468, cross-attention off) and
+// ClassificationDecoder (modules.py:303-349).  The latent comes from the frozen encoder and needs no
+// gradient, so the backward stops at the SpatialAttention weights.
+//
+// Train-mode semantics that differ from the inference kernels in vt_head.cu:
+//   * BatchNorm2d uses the batch statistics over (N,H,W) (biased variance) and updates
+//     running_mean / running_var (momentum, unbiased variance) and num_batches_tracked;
+//   * Dropout: attention weights (p = attention_dropout, modules.py:81) and classifier (.3/.2/.1,
+//     modules.py:405-415) masks come from a counter-based generator (seed, mask stream, element), so
+//     the backward regenerates them instead of storing them.
+// Gradients are ACCUMULATED into one flat fp32 buffer laid out like decoder.parameters()
+// (head_param_layout) -- the buffer the data-parallel step all-reduces with NCCL.  Every reduction
+// over the batch is two-stage (per-CTA partials, then one sum in a fixed order): results are
+// bit-reproducible run to run.
+//
+// The work is ~1 MB of latent per image and a 1.4 M-parameter MLP: everything is L2 resident and
+// latency/HBM bound, so these are plain CUDA-core kernels.
+#include <vector>
+
+#include "../../include/vae_tagger_b200.h"
+#include "vt_head_common.cuh"
+#include "vt_head_train.h"
+#include "vt_internal.h"
+
+namespace vt {
+
+namespace {
+
+__device__ __forceinline__ double h_warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+__device__ __forceinline__ double block_sum256_d(double v, double* red) {
+    v = h_warp_sum_d(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+}
+
+// ------------------------------------------------------------------------------ feature_compress
+// conv3x3 C->Co (+bias) -> z[N][Co][HW], and per-CTA partial (sum, sumsq) of z per channel for the
+// batch statistics.  grid (ceil(HW/256), N); part[(n*gridDim.x+blockIdx.x)][Co][2] doubles.
+__global__ void __launch_bounds__(256) head_conv_train_kernel(const float* __restrict__ x,   // [N][C][H][W]
+                                                              const float* __restrict__ cw,  // [Co][C][3][3]
+                                                              const float* __restrict__ cb, float* __restrict__ z,
+                                                              double* __restrict__ part, int C, int Co, int H,
+                                                              int W) {
+    extern __shared__ float sw[];  // Co*C*9 weights, then 8 floats scratch
+    float* red = sw + Co * C * 9;
+    const int n = blockIdx.y, HW = H * W;
+    for (int i = threadIdx.x; i < Co * C * 9; i += 256) sw[i] = cw[i];
+    __syncthreads();
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    const bool live = p < HW;
+    float v[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) v[o] = (o < Co) ? cb[o] : 0.f;
+    if (live) {
+        const int py = p / W, px = p - py * W;
+        for (int c = 0; c < C; ++c) {
+            const float* xp = x + (1LL * n * C + c) * HW;
+            for (int ky = 0; ky < 3; ++ky) {
+                const int yy = py + ky - 1;
+                if (yy < 0 || yy >= H) continue;
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = px + kx - 1;
+                    if (xx < 0 || xx >= W) continue;
+                    const float xv = xp[yy * W + xx];
+#pragma unroll
+                    for (int o = 0; o < 16; ++o)
+                        if (o < Co) v[o] = fmaf(sw[((o * C + c) * 3 + ky) * 3 + kx], xv, v[o]);
+                }
+            }
+        }
+    }
+    double* dst = part + (1LL * n * gridDim.x + blockIdx.x) * Co * 2;
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        if (o < Co) {
+            const float t = live ? v[o] : 0.f;
+            if (live) z[(1LL * n * Co + o) * HW + p] = t;
+            const float s1 = block_sum256(t, red);
+            const float s2 = block_sum256(t * t, red);
+            if (threadIdx.x == 0) {
+                dst[2 * o] = static_cast<double>(s1);
+                dst[2 * o + 1] = static_cast<double>(s2);
+            }
+        }
+    }
+}
+
+// batch statistics from the partials (one CTA): stat[0..Co) = mean, stat[Co..2Co) = 1/sqrt(var+eps);
+// running buffers updated like nn.BatchNorm2d in train mode (momentum, unbiased variance).
+__global__ void __launch_bounds__(256) head_bn_finalize_kernel(const double* __restrict__ part, int nparts, int Co,
+                                                               double count, float eps, float momentum,
+                                                               float* __restrict__ stat, float* __restrict__ rmean,
+                                                               float* __restrict__ rvar,
+                                                               long long* __restrict__ tracked) {
+    __shared__ double red[8];
+    for (int o = 0; o < Co; ++o) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = threadIdx.x; i < nparts; i += 256) {
+            s1 += part[(1LL * i * Co + o) * 2];
+            s2 += part[(1LL * i * Co + o) * 2 + 1];
+        }
+        s1 = block_sum256_d(s1, red);
+        s2 = block_sum256_d(s2, red);
+        if (threadIdx.x == 0) {
+            const double mean = s1 / count;
+            double var = s2 / count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            stat[o] = static_cast<float>(mean);
+            stat[Co + o] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+            if (rmean) rmean[o] = (1.0f - momentum) * rmean[o] + momentum * static_cast<float>(mean);
+            if (rvar) {
+                const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+                rvar[o] = (1.0f - momentum) * rvar[o] + momentum * static_cast<float>(unbiased);
+            }
+        }
+    }
+    if (threadIdx.x == 0 && tracked) *tracked += 1;
+}
+
+// BatchNorm (batch statistics) -> ReLU -> AdaptiveAvgPool(8,8).  grid (64 cells, N).
+__global__ void __launch_bounds__(256) head_bn_relu_pool_kernel(const float* __restrict__ z,
+                                                                const float* __restrict__ stat,
+                                                                const float* __restrict__ bn_w,
+                                                                const float* __restrict__ bn_b,
+                                                                float* __restrict__ pooled, int Co, int H, int W) {
+    __shared__ float red[8];
+    const int n = blockIdx.y, cell = blockIdx.x, HW = H * W;
+    const int cy = cell / 8, cx = cell % 8;
+    const int y0 = (cy * H) / 8, y1 = ((cy + 1) * H + 7) / 8;
+    const int x0 = (cx * W) / 8, x1 = ((cx + 1) * W + 7) / 8;
+    const int wh = y1 - y0, ww = x1 - x0;
+    for (int o = 0; o < Co; ++o) {
+        const float mean = stat[o], a = stat[Co + o] * bn_w[o], b = bn_b[o];
+        const float* zp = z + (1LL * n * Co + o) * HW;
+        float acc = 0.f;
+        for (int i = threadIdx.x; i < wh * ww; i += 256) {
+            const float t = (zp[(y0 + i / ww) * W + x0 + i % ww] - mean) * a + b;
+            acc += fmaxf(t, 0.f);
+        }
+        const float t = block_sum256(acc, red);
+        if (threadIdx.x == 0) pooled[(1LL * n * Co + o) * 64 + cell] = t / static_cast<float>(wh * ww);
+    }
+}
+
+// backward of AdaptiveAvgPool + ReLU into dt (written to dz), and the two per-channel sums the
+// BatchNorm backward needs: part[blk][Co][2] = (sum dt, sum dt*xhat).  grid (ceil(HW/256), N).
+__global__ void __launch_bounds__(256) head_bn_bwd_stats_kernel(const float* __restrict__ z,
+                                                                const float* __restrict__ stat,
+                                                                const float* __restrict__ bn_w,
+                                                                const float* __restrict__ bn_b,
+                                                                const float* __restrict__ dpooled,  // [N][Co][64]
+                                                                float* __restrict__ dz, double* __restrict__ part,
+                                                                int Co, int H, int W) {
+    __shared__ float red[8];
+    const int n = blockIdx.y, HW = H * W;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    const bool live = p < HW;
+    // the (up to four) pooling windows that contain this pixel
+    int cells[4];
+    float inv_area[4];
+    int ncell = 0;
+    if (live) {
+        const int py = p / W, px = p - py * W;
+        for (int cy = 0; cy < 8; ++cy) {
+            const int y0 = (cy * H) / 8, y1 = ((cy + 1) * H + 7) / 8;
+            if (py < y0 || py >= y1) continue;
+            for (int cx = 0; cx < 8; ++cx) {
+                const int x0 = (cx * W) / 8, x1 = ((cx + 1) * W + 7) / 8;
+                if (px < x0 || px >= x1) continue;
+                if (ncell < 4) {
+                    cells[ncell] = cy * 8 + cx;
+                    inv_area[ncell] = 1.0f / static_cast<float>((y1 - y0) * (x1 - x0));
+                    ++ncell;
+                }
+            }
+        }
+    }
+    double* dst = part + (1LL * n * gridDim.x + blockIdx.x) * Co * 2;
+    for (int o = 0; o < Co; ++o) {
+        float dt = 0.f, xhat = 0.f;
+        if (live) {
+            const long long idx = (1LL * n * Co + o) * HW + p;
+            xhat = (z[idx] - stat[o]) * stat[Co + o];
+            const float t = xhat * bn_w[o] + bn_b[o];
+            float dr = 0.f;
+            for (int i = 0; i < ncell; ++i) dr += dpooled[(1LL * n * Co + o) * 64 + cells[i]] * inv_area[i];
+            dt = t > 0.f ? dr : 0.f;
+            dz[idx] = dt;
+        }
+        const float s1 = block_sum256(dt, red);
+        const float s2 = block_sum256(dt * xhat, red);
+        if (threadIdx.x == 0) {
+            dst[2 * o] = static_cast<double>(s1);
+            dst[2 * o + 1] = static_cast<double>(s2);
+        }
+    }
+}
+
+// sums the partials (one CTA): sums[0..Co) = sum dt, sums[Co..2Co) = sum dt*xhat; BatchNorm affine grads
+__global__ void __launch_bounds__(256) head_bn_bwd_finalize_kernel(const double* __restrict__ part, int nparts,
+                                                                   int Co, float* __restrict__ sums,
+                                                                   float* __restrict__ g_bn_w,
+                                                                   float* __restrict__ g_bn_b) {
+    __shared__ double red[8];
+    for (int o = 0; o < Co; ++o) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = threadIdx.x; i < nparts; i += 256) {
+            s1 += part[(1LL * i * Co + o) * 2];
+            s2 += part[(1LL * i * Co + o) * 2 + 1];
+        }
+        s1 = block_sum256_d(s1, red);
+        s2 = block_sum256_d(s2, red);
+        if (threadIdx.x == 0) {
+            sums[o] = static_cast<float>(s1);
+            sums[Co + o] = static_cast<float>(s2);
+            g_bn_b[o] += static_cast<float>(s1);
+            g_bn_w[o] += static_cast<float>(s2);
+        }
+    }
+}
+
+// dz = w*invstd*(dt - mean(dt) - xhat*mean(dt*xhat)), in place over dz (which holds dt)
+__global__ void __launch_bounds__(256) head_bn_bwd_apply_kernel(const float* __restrict__ z,
+                                                                const float* __restrict__ stat,
+                                                                const float* __restrict__ sums,
+                                                                const float* __restrict__ bn_w,
+                                                                float* __restrict__ dz, int Co, int HW,
+                                                                long long total, float inv_count) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int o = static_cast<int>((i / HW) % Co);
+        const float xhat = (z[i] - stat[o]) * stat[Co + o];
+        dz[i] = bn_w[o] * stat[Co + o] * (dz[i] - sums[o] * inv_count - xhat * sums[Co + o] * inv_count);
+    }
+}
+
+// conv3x3 weight gradient: dW[o][c][k] = sum_{n,p} dz[n][o][p] * x[n][c][p+k].  grid (C, bands, N):
+// one input channel and one band of rows per CTA, CO*9 accumulators per thread, block reduction,
+// partial[(n*bands+band)][o][c][k]; the c == 0 CTAs also reduce the bias gradient sum dz.
+template <int CO>
+__global__ void __launch_bounds__(256) head_conv_bwd_w_kernel(const float* __restrict__ x,   // [N][C][H][W]
+                                                              const float* __restrict__ dz,  // [N][CO][H][W]
+                                                              float* __restrict__ part_w, float* __restrict__ part_b,
+                                                              int C, int H, int W) {
+    __shared__ float red[8];
+    const int c = blockIdx.x, band = blockIdx.y, bands = gridDim.y, n = blockIdx.z;
+    const int HW = H * W;
+    const int r0 = (band * H) / bands, r1 = ((band + 1) * H) / bands;
+    const float* xp = x + (1LL * n * C + c) * HW;
+    const float* dzp = dz + 1LL * n * CO * HW;
+    float acc[CO * 9];
+    float bacc[CO];
+#pragma unroll
+    for (int i = 0; i < CO * 9; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int o = 0; o < CO; ++o) bacc[o] = 0.f;
+    for (int i = threadIdx.x; i < (r1 - r0) * W; i += 256) {
+        const int py = r0 + i / W, px = i % W;
+        float d[CO];
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+            d[o] = dzp[1LL * o * HW + py * W + px];
+            bacc[o] += d[o];
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = py + ky - 1;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = px + kx - 1;
+                const float xv = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? xp[yy * W + xx] : 0.f;
+#pragma unroll
+                for (int o = 0; o < CO; ++o) acc[o * 9 + ky * 3 + kx] = fmaf(d[o], xv, acc[o * 9 + ky * 3 + kx]);
+            }
+        }
+    }
+    const long long pidx = 1LL * n * bands + band;
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float t = block_sum256(acc[o * 9 + k], red);
+            if (threadIdx.x == 0) part_w[(pidx * CO + o) * C * 9 + c * 9 + k] = t;
+        }
+    }
+    if (c == 0) {
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+            const float t = block_sum256(bacc[o], red);
+            if (threadIdx.x == 0) part_b[pidx * CO + o] = t;
+        }
+    }
+}
+
+// conv3x3 input gradient: dx[n][c][p] = sum_{o,k} dz[n][o][p-k] * W[o][c][k].  grid (ceil(HW/256), N)
+template <int CO>
+__global__ void __launch_bounds__(256) head_conv_bwd_x_kernel(const float* __restrict__ dz,
+                                                              const float* __restrict__ cw,  // [CO][2CO][3][3]
+                                                              float* __restrict__ dx, int H, int W) {
+    constexpr int C = 2 * CO;
+    __shared__ float sw[CO * C * 9];
+    for (int i = threadIdx.x; i < CO * C * 9; i += 256) sw[i] = cw[i];
+    __syncthreads();
+    const int n = blockIdx.y, HW = H * W;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= HW) return;
+    const int py = p / W, px = p - py * W;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    for (int o = 0; o < CO; ++o) {
+        const float* dp = dz + (1LL * n * CO + o) * HW;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = py - (ky - 1);
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = px - (kx - 1);
+                if (xx < 0 || xx >= W) continue;
+                const float d = dp[yy * W + xx];
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = fmaf(d, sw[((o * C + c) * 3 + ky) * 3 + kx], acc[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) dx[(1LL * n * C + c) * HW + p] = acc[c];
+}
+
+// dst[i] += sum over parts of part[p][i]  (fixed order: deterministic)
+__global__ void __launch_bounds__(256) head_partial_reduce_kernel(const float* __restrict__ part, int nparts, int P,
+                                                                  float* __restrict__ dst) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part[1LL * p * P + i];
+    dst[i] += s;
+}
+
+// ------------------------------------------------------------------------------ SpatialAttention bwd
+// y = x*g[c]*s[p] (modules.py:36-47).  Step A: dpre[n][p] = s(1-s) * sum_c dy[c][p]*x[c][p]*g[c]
+__global__ void __launch_bounds__(256) head_sa_bwd_pre_kernel(const float* __restrict__ x,
+                                                              const float* __restrict__ cgate,
+                                                              const float* __restrict__ sgate,
+                                                              const float* __restrict__ dy,
+                                                              float* __restrict__ dpre, int C, int HW) {
+    __shared__ float g[64];
+    const int n = blockIdx.y;
+    if (threadIdx.x < C) g[threadIdx.x] = cgate[1LL * n * C + threadIdx.x];
+    __syncthreads();
+    for (int p = blockIdx.x * 256 + threadIdx.x; p < HW; p += 256 * gridDim.x) {
+        float ds = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const long long o = (1LL * n * C + c) * HW + p;
+            ds = fmaf(dy[o] * x[o], g[c], ds);
+        }
+        const float s = sgate[1LL * n * HW + p];
+        dpre[1LL * n * HW + p] = ds * s * (1.0f - s);
+    }
+}
+
+// Step B: gradient of the channel gate.  dm = convT7x7(dpre); dxg[c] = dy[c]*s + dm0/C + dm1*[c==argmax];
+// dg[n][c] = sum_p dxg[c]*x[c].  grid (bands, N); part_g[(n*bands+band)][C]
+__global__ void __launch_bounds__(256) head_sa_bwd_gate_sum_kernel(const float* __restrict__ x,
+                                                                   const float* __restrict__ cgate,
+                                                                   const float* __restrict__ sgate,
+                                                                   const float* __restrict__ dy,
+                                                                   const float* __restrict__ dpre,
+                                                                   const float* __restrict__ w7,
+                                                                   float* __restrict__ part_g, int C, int H, int W) {
+    __shared__ float ws[98];
+    __shared__ float g[64];
+    __shared__ float red[8];
+    const int n = blockIdx.y, HW = H * W;
+    if (threadIdx.x < 98) ws[threadIdx.x] = w7[threadIdx.x];
+    if (threadIdx.x < C) g[threadIdx.x] = cgate[1LL * n * C + threadIdx.x];
+    __syncthreads();
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    const float* dp = dpre + 1LL * n * HW;
+    const float inv_c = 1.0f / static_cast<float>(C);
+    for (int p = blockIdx.x * 256 + threadIdx.x; p < HW; p += 256 * gridDim.x) {
+        const int py = p / W, px = p - py * W;
+        float dm0 = 0.f, dm1 = 0.f;
+        for (int ky = 0; ky < 7; ++ky) {
+            const int yy = py - (ky - 3);
+            if (yy < 0 || yy >= H) continue;
+            for (int kx = 0; kx < 7; ++kx) {
+                const int xx = px - (kx - 3);
+                if (xx < 0 || xx >= W) continue;
+                const float d = dp[yy * W + xx];
+                dm0 = fmaf(d, ws[ky * 7 + kx], dm0);
+                dm1 = fmaf(d, ws[49 + ky * 7 + kx], dm1);
+            }
+        }
+        // channel of the maximum of x*g (first one wins, like torch.max)
+        int amax = 0;
+        float best = -CUDART_INF_F;
+        for (int c = 0; c < C; ++c) {
+            const float v = x[(1LL * n * C + c) * HW + p] * g[c];
+            if (v > best) {
+                best = v;
+                amax = c;
+            }
+        }
+        const float s = sgate[1LL * n * HW + p];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            if (c < C) {
+                const long long o = (1LL * n * C + c) * HW + p;
+                const float dxg = dy[o] * s + dm0 * inv_c + (c == amax ? dm1 : 0.f);
+                acc[c] = fmaf(dxg, x[o], acc[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        if (c < C) {
+            const float t = block_sum256(acc[c], red);
+            if (threadIdx.x == 0) part_g[(1LL * n * gridDim.x + blockIdx.x) * C + c] = t;
+        }
+    }
+}
+
+// Step C: 7x7 weight gradient dW7[ci][k] = sum_{n,p} dpre[p]*map2[ci][p+k].  grid (bands, N, 2):
+// one map channel per CTA, 49 accumulators per thread; part_w7[(n*bands+band)][98]
+__global__ void __launch_bounds__(256) head_sa_bwd_w7_kernel(const float* __restrict__ map2,
+                                                             const float* __restrict__ dpre,
+                                                             float* __restrict__ part_w7, int H, int W) {
+    __shared__ float red[8];
+    const int n = blockIdx.y, ci = blockIdx.z, HW = H * W;
+    const float* mp = map2 + (1LL * n * 2 + ci) * HW;
+    const float* dp = dpre + 1LL * n * HW;
+    float acc[49];
+#pragma unroll
+    for (int i = 0; i < 49; ++i) acc[i] = 0.f;
+    for (int p = blockIdx.x * 256 + threadIdx.x; p < HW; p += 256 * gridDim.x) {
+        const int py = p / W, px = p - py * W;
+        const float d = dp[p];
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+            const int yy = py + ky - 3;
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) {
+                const int xx = px + kx - 3;
+                const float m = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? mp[yy * W + xx] : 0.f;
+                acc[ky * 7 + kx] = fmaf(d, m, acc[ky * 7 + kx]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 49; ++i) {
+        const float t = block_sum256(acc[i], red);
+        if (threadIdx.x == 0) part_w7[(1LL * n * gridDim.x + blockIdx.x) * 98 + ci * 49 + i] = t;
+    }
+}
+
+// Step D (one CTA): channel-gate MLP backward, summed over the batch in image order.
+//   gate = sigmoid(W2 relu(W1 avg) + W2 relu(W1 max)); only the weights get a gradient.
+__global__ void __launch_bounds__(256) head_sa_bwd_mlp_kernel(const float* __restrict__ pool,   // [N][C][2]
+                                                              const float* __restrict__ cgate,  // [N][C]
+                                                              const float* __restrict__ part_g, int bands,
+                                                              const float* __restrict__ w1,  // [Ch][C]
+                                                              const float* __restrict__ w2,  // [C][Ch]
+                                                              float* __restrict__ g_w1, float* __restrict__ g_w2,
+                                                              int N, int C, int Ch) {
+    __shared__ float dpg[64];
+    __shared__ float hid[2][16];
+    __shared__ float dh[2][16];
+    const int t = threadIdx.x;
+    float acc1 = 0.f, acc2 = 0.f;  // this thread's element of dW1 ([j][c]) and dW2 ([c][j])
+    for (int n = 0; n < N; ++n) {
+        if (t < C) {
+            float dg = 0.f;
+            for (int b = 0; b < bands; ++b) dg += part_g[(1LL * n * bands + b) * C + t];
+            const float g = cgate[1LL * n * C + t];
+            dpg[t] = dg * g * (1.0f - g);
+        }
+        if (t >= 64 && t < 64 + 2 * Ch) {
+            const int which = (t - 64) / Ch, j = (t - 64) % Ch;
+            float a = 0.f;
+            for (int c = 0; c < C; ++c) a = fmaf(w1[j * C + c], pool[(1LL * n * C + c) * 2 + which], a);
+            hid[which][j] = a;
+        }
+        __syncthreads();
+        if (t < C * Ch) {  // dW2[c][j]
+            const int c = t / Ch, j = t % Ch;
+            acc2 += dpg[c] * (fmaxf(hid[0][j], 0.f) + fmaxf(hid[1][j], 0.f));
+        }
+        if (t >= 64 && t < 64 + 2 * Ch) {
+            const int which = (t - 64) / Ch, j = (t - 64) % Ch;
+            float a = 0.f;
+            for (int c = 0; c < C; ++c) a = fmaf(w2[c * Ch + j], dpg[c], a);
+            dh[which][j] = hid[which][j] > 0.f ? a : 0.f;
+        }
+        __syncthreads();
+        if (t < Ch * C) {  // dW1[j][c]
+            const int j = t / C, c = t % C;
+            acc1 += dh[0][j] * pool[(1LL * n * C + c) * 2] + dh[1][j] * pool[(1LL * n * C + c) * 2 + 1];
+        }
+        __syncthreads();
+    }
+    if (t < C * Ch) {
+        g_w1[t] += acc1;
+        g_w2[t] += acc2;
+    }
+}
+
+// ------------------------------------------------------------------------------ self-attention
+// MultiHeadSelfAttention in train mode (modules.py:66-91).  One CTA per image, one thread per token.
+// prm = q.w q.b k.w k.b v.w v.b out.w out.b norm.w norm.b, contiguous (the flat parameter order).
+// BWD = false: feat[n][e*64+t].  BWD = true: recomputes the forward, then dpooled[n][e][t] and the
+// per-image parameter gradients partial[n][4(E*E+E)+2E] in the same order as prm.
+template <class F>
+__device__ __forceinline__ void token_reduce(float (*sm)[65], int t, int count, float* dst, F contrib) {
+    for (int base = 0; base < count; base += 64) {
+        __syncthreads();
+        for (int i = 0; i < 64 && base + i < count; ++i) sm[t][i] = contrib(base + i);
+        __syncthreads();
+        if (base + t < count) {
+            float s = 0.f;
+            for (int r = 0; r < 64; ++r) s += sm[r][t];
+            dst[base + t] = s;
+        }
+    }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(64) head_mhsa_train_kernel(const float* __restrict__ pooled,  // [N][E][64]
+                                                             const float* __restrict__ prm,
+                                                             float* __restrict__ feat,
+                                                             const float* __restrict__ dfeat,  // [N][E*64]
+                                                             float* __restrict__ dpooled,
+                                                             float* __restrict__ partial, int E, int heads,
+                                                             float drop_p, unsigned long long seed) {
+    __shared__ float sk[64][17];
+    __shared__ float sv[64][17];
+    __shared__ float sq[64][17];
+    __shared__ float sd[64][17];
+    __shared__ float sm[64][65];
+    const int n = blockIdx.x, t = threadIdx.x;
+    const int EE = E * E;
+    const float *wq = prm, *bq = wq + EE, *wk = bq + E, *bk = wk + EE, *wv = bk + E, *bv = wv + EE, *wo = bv + E,
+                *bo = wo + EE, *ln_w = bo + E, *ln_b = ln_w + E;
+    float xin[16], xhat[16], xn[16], q[16];
+    for (int e = 0; e < E; ++e) xin[e] = pooled[(1LL * n * E + e) * 64 + t];
+    float mean = 0.f;
+    for (int e = 0; e < E; ++e) mean += xin[e];
+    mean /= static_cast<float>(E);
+    float var = 0.f;
+    for (int e = 0; e < E; ++e) var += (xin[e] - mean) * (xin[e] - mean);
+    var /= static_cast<float>(E);
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    for (int e = 0; e < E; ++e) {
+        xhat[e] = (xin[e] - mean) * rstd;
+        xn[e] = xhat[e] * ln_w[e] + ln_b[e];
+    }
+    for (int o = 0; o < E; ++o) {
+        float a = bq[o], b = bk[o], c = bv[o];
+        for (int e = 0; e < E; ++e) {
+            a = fmaf(wq[o * E + e], xn[e], a);
+            b = fmaf(wk[o * E + e], xn[e], b);
+            c = fmaf(wv[o * E + e], xn[e], c);
+        }
+        q[o] = a;
+        sk[t][o] = b;
+        sv[t][o] = c;
+        sq[t][o] = a;
+    }
+    float dout[16], dao[16], dq[16], dkk[16], dvv[16];
+    if (BWD) {
+        for (int o = 0; o < E; ++o) dout[o] = dfeat[1LL * n * E * 64 + o * 64 + t];
+        for (int e = 0; e < E; ++e) {
+            float a = 0.f;
+            for (int o = 0; o < E; ++o) a = fmaf(dout[o], wo[o * E + e], a);
+            dao[e] = a;
+            sd[t][e] = a;
+        }
+    }
+    __syncthreads();
+    const int hd = E / heads;
+    const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+    const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    float ao[16];
+    for (int h = 0; h < heads; ++h) {
+        float P[64];
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            float s = 0.f;
+            for (int d = 0; d < hd; ++d) s = fmaf(q[h * hd + d], sk[j][h * hd + d], s);
+            s *= scale;
+            P[j] = s;
+            m = fmaxf(m, s);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            P[j] = expf(P[j] - m);
+            sum += P[j];
+        }
+        const float inv = 1.0f / sum;
+        unsigned long long keep = ~0ULL;
+        if (drop_p > 0.f) {
+            keep = 0ULL;
+            const unsigned long long base = ((1ULL * n * heads + h) * 64 + t) * 64;
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+                if (h_dropout_keep(seed, 0u, base + j, drop_p)) keep |= 1ULL << j;
+        }
+#pragma unroll
+        for (int j = 0; j < 64; ++j) P[j] *= inv;
+        for (int d = 0; d < hd; ++d) {
+            float o = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+                if ((keep >> j) & 1ULL) o = fmaf(P[j] * inv_keep, sv[j][h * hd + d], o);
+            ao[h * hd + d] = o;
+        }
+        if (BWD) {
+            // dP_j = keep_j * inv_keep * sum_d dao[d]*v[j][d];  dS_j = P_j (dP_j - sum_j' dP_j' P_j') * scale
+            float rowdot = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                if ((keep >> j) & 1ULL) {
+                    float dp = 0.f;
+                    for (int d = 0; d < hd; ++d) dp = fmaf(dao[h * hd + d], sv[j][h * hd + d], dp);
+                    rowdot = fmaf(dp * inv_keep, P[j], rowdot);
+                }
+            }
+            for (int d = 0; d < hd; ++d) dq[h * hd + d] = 0.f;
+            __syncthreads();  // previous head's column sums are done with sm
+#pragma unroll
+            for (int j = 0; j < 64; ++j) sm[t][j] = ((keep >> j) & 1ULL) ? P[j] * inv_keep : 0.f;
+            __syncthreads();
+            for (int d = 0; d < hd; ++d) {  // dv of token t as a key: column t of the dropped weights
+                float a = 0.f;
+                for (int r = 0; r < 64; ++r) a = fmaf(sm[r][t], sd[r][h * hd + d], a);
+                dvv[h * hd + d] = a;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                float dp = 0.f;
+                if ((keep >> j) & 1ULL) {
+                    for (int d = 0; d < hd; ++d) dp = fmaf(dao[h * hd + d], sv[j][h * hd + d], dp);
+                    dp *= inv_keep;
+                }
+                const float ds = P[j] * (dp - rowdot) * scale;
+                sm[t][j] = ds;
+                for (int d = 0; d < hd; ++d) dq[h * hd + d] = fmaf(ds, sk[j][h * hd + d], dq[h * hd + d]);
+            }
+            __syncthreads();
+            for (int d = 0; d < hd; ++d) {  // dk of token t as a key
+                float a = 0.f;
+                for (int r = 0; r < 64; ++r) a = fmaf(sm[r][t], sq[r][h * hd + d], a);
+                dkk[h * hd + d] = a;
+            }
+        }
+    }
+    if (!BWD) {
+        for (int o = 0; o < E; ++o) {
+            float a = bo[o];
+            for (int e = 0; e < E; ++e) a = fmaf(wo[o * E + e], ao[e], a);
+            feat[1LL * n * E * 64 + o * 64 + t] = a + xin[o];
+        }
+        return;
+    }
+    // gradient of the LayerNorm output: dxn = Wq^T dq + Wk^T dk + Wv^T dv
+    float dxn[16];
+    for (int e = 0; e < E; ++e) {
+        float a = 0.f;
+        for (int o = 0; o < E; ++o) {
+            a = fmaf(dq[o], wq[o * E + e], a);
+            a = fmaf(dkk[o], wk[o * E + e], a);
+            a = fmaf(dvv[o], wv[o * E + e], a);
+        }
+        dxn[e] = a;
+    }
+    float m1 = 0.f, m2 = 0.f;
+    for (int e = 0; e < E; ++e) {
+        const float g = dxn[e] * ln_w[e];
+        m1 += g;
+        m2 += g * xhat[e];
+    }
+    m1 /= static_cast<float>(E);
+    m2 /= static_cast<float>(E);
+    for (int e = 0; e < E; ++e)
+        dpooled[(1LL * n * E + e) * 64 + t] = rstd * (dxn[e] * ln_w[e] - m1 - xhat[e] * m2) + dout[e];
+    // parameter gradients of this image: sums over the 64 tokens
+    float* dst = partial + 1LL * n * (4 * (EE + E) + 2 * E);
+    token_reduce(sm, t, EE, dst, [&](int i) { return dq[i / E] * xn[i % E]; });
+    token_reduce(sm, t, E, dst + EE, [&](int i) { return dq[i]; });
+    token_reduce(sm, t, EE, dst + EE + E, [&](int i) { return dkk[i / E] * xn[i % E]; });
+    token_reduce(sm, t, E, dst + 2 * EE + E, [&](int i) { return dkk[i]; });
+    token_reduce(sm, t, EE, dst + 2 * EE + 2 * E, [&](int i) { return dvv[i / E] * xn[i % E]; });
+    token_reduce(sm, t, E, dst + 3 * EE + 2 * E, [&](int i) { return dvv[i]; });
+    token_reduce(sm, t, EE, dst + 3 * EE + 3 * E, [&](int i) { return dout[i / E] * ao[i % E]; });
+    token_reduce(sm, t, E, dst + 4 * EE + 3 * E, [&](int i) { return dout[i]; });
+    token_reduce(sm, t, E, dst + 4 * EE + 4 * E, [&](int i) { return dxn[i] * xhat[i]; });
+    token_reduce(sm, t, E, dst + 4 * EE + 5 * E, [&](int i) { return dxn[i]; });
+}
+
+// ------------------------------------------------------------------------------ classifier
+// LayerNorm (eps 1e-5) -> ReLU / LeakyReLU(0.2) -> Dropout(p), out of place; stat[b] = (mean, rstd).
+__global__ void __launch_bounds__(256) head_ln_act_drop_kernel(const float* __restrict__ a, float* __restrict__ h,
+                                                               float* __restrict__ stat,
+                                                               const float* __restrict__ w,
+                                                               const float* __restrict__ b, int D, int act, float p,
+                                                               unsigned long long seed, unsigned stream_id) {
+    __shared__ float red[8];
+    const float* r = a + 1LL * blockIdx.x * D;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < D; i += 256) s += r[i];
+    const float mean = block_sum256(s, red) / static_cast<float>(D);
+    float v = 0.f;
+    for (int i = threadIdx.x; i < D; i += 256) v += (r[i] - mean) * (r[i] - mean);
+    const float var = block_sum256(v, red) / static_cast<float>(D);
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    if (threadIdx.x == 0) {
+        stat[2 * blockIdx.x] = mean;
+        stat[2 * blockIdx.x + 1] = rstd;
+    }
+    const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+    for (int i = threadIdx.x; i < D; i += 256) {
+        float t = (r[i] - mean) * rstd * w[i] + b[i];
+        if (act == 1) t = fmaxf(t, 0.f);
+        else if (act == 2) t = t > 0.f ? t : 0.2f * t;
+        if (p > 0.f) t = h_dropout_keep(seed, stream_id, 1ULL * blockIdx.x * D + i, p) ? t * inv_keep : 0.f;
+        h[1LL * blockIdx.x * D + i] = t;
+    }
+}
+
+// backward of the above.  dh (gradient w.r.t. the dropout output) is replaced by the gradient w.r.t.
+// the LayerNorm input; dt (gradient w.r.t. the LayerNorm output) is kept for the affine gradients.
+__global__ void __launch_bounds__(256) head_ln_act_drop_bwd_kernel(float* __restrict__ dh,
+                                                                   const float* __restrict__ a,
+                                                                   const float* __restrict__ stat,
+                                                                   const float* __restrict__ w,
+                                                                   const float* __restrict__ b,
+                                                                   float* __restrict__ dt_out, int D, int act,
+                                                                   float p, unsigned long long seed,
+                                                                   unsigned stream_id) {
+    __shared__ float red[8];
+    const long long row = 1LL * blockIdx.x * D;
+    const float mean = stat[2 * blockIdx.x], rstd = stat[2 * blockIdx.x + 1];
+    const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < D; i += 256) {
+        const float xhat = (a[row + i] - mean) * rstd;
+        const float t = xhat * w[i] + b[i];
+        float g = dh[row + i];
+        if (p > 0.f) g = h_dropout_keep(seed, stream_id, row + i, p) ? g * inv_keep : 0.f;
+        const float slope = t > 0.f ? 1.0f : (act == 2 ? 0.2f : 0.f);
+        const float dt = g * slope;
+        dt_out[row + i] = dt;
+        const float gw = dt * w[i];
+        s1 += gw;
+        s2 += gw * xhat;
+    }
+    const float m1 = block_sum256(s1, red) / static_cast<float>(D);
+    const float m2 = block_sum256(s2, red) / static_cast<float>(D);
+    for (int i = threadIdx.x; i < D; i += 256) {
+        const float xhat = (a[row + i] - mean) * rstd;
+        dh[row + i] = rstd * (dt_out[row + i] * w[i] - m1 - xhat * m2);
+    }
+}
+
+// LayerNorm affine gradients: dgamma[d] += sum_b dt[b][d]*xhat[b][d]; dbeta[d] += sum_b dt[b][d]
+__global__ void __launch_bounds__(256) head_ln_param_bwd_kernel(const float* __restrict__ dt,
+                                                                const float* __restrict__ a,
+                                                                const float* __restrict__ stat,
+                                                                float* __restrict__ g_w, float* __restrict__ g_b,
+                                                                int B, int D) {
+    const int d = blockIdx.x * 256 + threadIdx.x;
+    if (d >= D) return;
+    float sw = 0.f, sb = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float v = dt[1LL * b * D + d];
+        sw = fmaf(v, (a[1LL * b * D + d] - stat[2 * b]) * stat[2 * b + 1], sw);
+        sb += v;
+    }
+    g_w[d] += sw;
+    g_b[d] += sb;
+}
+
+// Linear backward, weights: dW[o][i] += sum_b dy[b][o]*x[b][i]; db[o] += sum_b dy[b][o]
+__global__ void __launch_bounds__(256) head_linear_bwd_w_kernel(const float* __restrict__ dy,
+                                                                const float* __restrict__ x,
+                                                                float* __restrict__ g_w, float* __restrict__ g_b,
+                                                                int B, int I, int O) {
+    const long long idx = blockIdx.x * 256LL + threadIdx.x;
+    if (idx >= 1LL * O * I) return;
+    const int o = static_cast<int>(idx / I), i = static_cast<int>(idx - 1LL * o * I);
+    float acc = 0.f, bacc = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float d = dy[1LL * b * O + o];
+        acc = fmaf(d, x[1LL * b * I + i], acc);
+        bacc += d;
+    }
+    g_w[idx] += acc;
+    if (i == 0) g_b[o] += bacc;
+}
+
+// Linear backward, input: dx[b][i] = sum_o dy[b][o]*W[o][i].  grid (ceil(I/256), ceil(B/8))
+__global__ void __launch_bounds__(256) head_linear_bwd_x_kernel(const float* __restrict__ dy,
+                                                                const float* __restrict__ w,
+                                                                float* __restrict__ dx, int B, int I, int O) {
+    __shared__ float sdy[8][256];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int b0 = blockIdx.y * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int o0 = 0; o0 < O; o0 += 256) {
+        __syncthreads();
+#pragma unroll
+        for (int bb = 0; bb < 8; ++bb)
+            sdy[bb][threadIdx.x] =
+                (b0 + bb < B && o0 + threadIdx.x < O) ? dy[1LL * (b0 + bb) * O + o0 + threadIdx.x] : 0.f;
+        __syncthreads();
+        if (i < I) {
+            const int cnt = min(256, O - o0);
+            for (int oo = 0; oo < cnt; ++oo) {
+                const float wv = w[1LL * (o0 + oo) * I + i];
+#pragma unroll
+                for (int bb = 0; bb < 8; ++bb) acc[bb] = fmaf(sdy[bb][oo], wv, acc[bb]);
+            }
+        }
+    }
+    if (i < I) {
+#pragma unroll
+        for (int bb = 0; bb < 8; ++bb)
+            if (b0 + bb < B) dx[1LL * (b0 + bb) * I + i] = acc[bb];
+    }
+}
+
+__global__ void head_scale_add_kernel(const float* __restrict__ src, float scale, float* __restrict__ dst) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *dst += *src * scale;
+}
+
+// dropout keep-masks as 0/1 floats (parity tests only: lets the oracle apply the same masks)
+__global__ void __launch_bounds__(256) head_dropout_mask_kernel(float* __restrict__ out, long long n, float p,
+                                                                unsigned long long seed, unsigned stream_id) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x)
+        out[i] = (p > 0.f && !h_dropout_keep(seed, stream_id, static_cast<unsigned long long>(i), p)) ? 0.f : 1.f;
+}
+
+// ------------------------------------------------------------------------------ optimizer
+// sum of squares of a flat buffer, two-stage: part[blockIdx.x] then one CTA
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n,
+                                                            double* __restrict__ part) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+        const double v = static_cast<double>(g[i]);
+        s += v * v;
+    }
+    s = block_sum256_d(s, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const double* __restrict__ part, int nparts,
+                                                          float grad_scale, float* __restrict__ norm_out) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 256) s += part[i];
+    s = block_sum256_d(s, red);
+    if (threadIdx.x == 0) *norm_out = static_cast<float>(sqrt(s)) * fabsf(grad_scale);
+}
+// clip_grad_norm_(max_norm) + torch.optim.AdamW (decoupled weight decay) on flat buffers; grads zeroed
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, long long n,
+                                                    float lr, float beta1, float beta2, float eps, float wd,
+                                                    float bias1, float bias2_sqrt, float grad_scale, float max_norm,
+                                                    const float* __restrict__ norm, int zero_grad) {
+    float clip = 1.0f;
+    if (max_norm > 0.f) clip = fminf(1.0f, max_norm / (*norm + 1e-6f));
+    const float gs = grad_scale * clip;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+        const float gi = g[i] * gs;
+        float pi = p[i] * (1.0f - lr * wd);
+        const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bias2_sqrt + eps;
+        pi -= (lr / bias1) * (mi / denom);
+        p[i] = pi;
+        if (zero_grad) g[i] = 0.f;
+    }
+}
+
+struct Mlp {
+    int n;           // number of Linear layers
+    int dims[6];     // n+1 widths
+    int act;         // 1 ReLU, 2 LeakyReLU(0.2)
+    float drop[5];   // dropout after each hidden layer
+};
+
+Mlp mlp_of(const vt_head_config& h) {
+    Mlp m{};
+    if (h.kind == VT_HEAD_ATTENTION) {
+        m.n = 4;
+        const int d[5] = {(h.latent_channels / 2) * 64, 1024, 512, 256, h.num_classes};
+        for (int i = 0; i < 5; ++i) m.dims[i] = d[i];
+        m.act = 1;
+        m.drop[0] = 0.3f; m.drop[1] = 0.2f; m.drop[2] = 0.1f;
+    } else {
+        m.n = 3;
+        const int d[4] = {h.latent_channels * 16, 512, 256, h.num_classes};
+        for (int i = 0; i < 4; ++i) m.dims[i] = d[i];
+        m.act = 2;
+        m.drop[0] = 0.3f; m.drop[1] = 0.2f;
+    }
+    return m;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ parameter layout
+std::vector<HeadParamEntry> head_param_layout(const vt_head_config& h) {
+    std::vector<HeadParamEntry> L;
+    int64_t off = 0;
+    auto add = [&](const std::string& name, std::vector<int64_t> shape) {
+        int64_t n = 1;
+        for (auto d : shape) n *= d;
+        L.push_back({name, off, n, shape});
+        off += n;
+    };
+    const int C = h.latent_channels, E = C / 2, T = h.num_classes;
+    if (h.kind == VT_HEAD_ATTENTION) {
+        if (h.use_spatial_attention) {
+            add("spatial_attention.channel_att.0.weight", {C / 8, C, 1, 1});
+            add("spatial_attention.channel_att.2.weight", {C, C / 8, 1, 1});
+            add("spatial_attention.spatial_att.0.weight", {1, 2, 7, 7});
+        }
+        add("feature_compress.0.weight", {E, C, 3, 3});
+        add("feature_compress.0.bias", {E});
+        add("feature_compress.1.weight", {E});
+        add("feature_compress.1.bias", {E});
+        if (h.use_self_attention) {
+            for (const char* k : {"q_proj", "k_proj", "v_proj", "out_proj"}) {
+                add(std::string("self_attention_post.") + k + ".weight", {E, E});
+                add(std::string("self_attention_post.") + k + ".bias", {E});
+            }
+            add("self_attention_post.norm.weight", {E});
+            add("self_attention_post.norm.bias", {E});
+        }
+    }
+    const Mlp m = mlp_of(h);
+    for (int i = 0; i < m.n; ++i) {
+        const std::string lin = "classifier." + std::to_string(4 * i);
+        add(lin + ".weight", {m.dims[i + 1], m.dims[i]});
+        add(lin + ".bias", {m.dims[i + 1]});
+        if (i + 1 < m.n) {
+            const std::string ln = "classifier." + std::to_string(4 * i + 1);
+            add(ln + ".weight", {m.dims[i + 1]});
+            add(ln + ".bias", {m.dims[i + 1]});
+        }
+    }
+    (void)T;
+    return L;
+}
+
+namespace {
+struct Arena {
+    size_t off = 0;
+    size_t take(size_t n) {
+        const size_t o = off;
+        off += (n + 63) / 64 * 64;
+        return o;
+    }
+};
+struct TrainWs {
+    size_t pool, cgate, map2, x2, sgate, z, dz, dy, dpre, bnstat, bnsums, pooled, dpooled, feat, dfeat;
+    size_t a[4], hbuf[4], stat[4], dtbuf, g0, g1, logits, dlogits, loss;
+    size_t part_bn, part_mhsa, part_cw, part_cb, part_g, part_w7, part_norm;
+    size_t total;
+};
+constexpr int kBands = 8;
+
+TrainWs plan(const vt_head_config& h, int B, int H, int W) {
+    TrainWs w{};
+    Arena A;
+    const size_t C = h.latent_channels, E = C / 2, HW = static_cast<size_t>(H) * W, T = h.num_classes;
+    const Mlp m = mlp_of(h);
+    const size_t nblk = (HW + 255) / 256;
+    if (h.kind == VT_HEAD_ATTENTION) {
+        w.pool = A.take(B * C * 2); w.cgate = A.take(B * C); w.map2 = A.take(B * 2 * HW);
+        w.x2 = A.take(B * C * HW); w.sgate = A.take(B * HW); w.z = A.take(B * E * HW); w.dz = A.take(B * E * HW);
+        w.dy = A.take(B * C * HW); w.dpre = A.take(B * HW); w.bnstat = A.take(2 * E); w.bnsums = A.take(2 * E);
+        w.pooled = A.take(B * E * 64); w.dpooled = A.take(B * E * 64);
+        w.part_bn = A.take(2 * (B * nblk * E * 2));  // doubles
+        w.part_mhsa = A.take(B * (4 * (E * E + E) + 2 * E));
+        w.part_cw = A.take(static_cast<size_t>(B) * kBands * E * C * 9);
+        w.part_cb = A.take(static_cast<size_t>(B) * kBands * E);
+        w.part_g = A.take(static_cast<size_t>(B) * kBands * C);
+        w.part_w7 = A.take(static_cast<size_t>(B) * kBands * 98);
+    }
+    size_t maxd = 0;
+    for (int i = 0; i <= m.n; ++i) maxd = std::max<size_t>(maxd, m.dims[i]);
+    w.feat = A.take(B * static_cast<size_t>(m.dims[0])); w.dfeat = A.take(B * static_cast<size_t>(m.dims[0]));
+    for (int i = 0; i + 1 < m.n; ++i) {
+        w.a[i] = A.take(B * static_cast<size_t>(m.dims[i + 1]));
+        w.hbuf[i] = A.take(B * static_cast<size_t>(m.dims[i + 1]));
+        w.stat[i] = A.take(2 * static_cast<size_t>(B));
+    }
+    w.dtbuf = A.take(B * maxd); w.g0 = A.take(B * maxd); w.g1 = A.take(B * maxd);
+    w.logits = A.take(B * T); w.dlogits = A.take(B * T); w.loss = A.take(1);
+    w.total = A.off;
+    return w;
+}
+}  // namespace
+
+size_t head_train_workspace_floats(const vt_head_config& h, int B, int H, int W) { return plan(h, B, H, W).total; }
+
+template <int CO>
+static void launch_conv_bwd(const float* x, const float* dz, const float* cw, float* part_w, float* part_b,
+                            float* dy, int N, int H, int W, cudaStream_t s) {
+    head_conv_bwd_w_kernel<CO><<<dim3(2 * CO, kBands, N), 256, 0, s>>>(x, dz, part_w, part_b, 2 * CO, H, W);
+    if (dy) head_conv_bwd_x_kernel<CO><<<dim3((H * W + 255) / 256, N), 256, 0, s>>>(dz, cw, dy, H, W);
+}
+
+#define VT_KC(...)                            \
+    do {                                      \
+        profiler_begin(pf, KC_HEAD, s, 0, 0); \
+        __VA_ARGS__;                          \
+        profiler_end(pf, KC_HEAD, s);         \
+    } while (0)
+
+int head_train_step(const vt_head_config& h, const vt_head_train_args& a, float* ws, Profiler* pf) {
+    cudaStream_t s = static_cast<cudaStream_t>(a.stream);
+    const int B = a.batch, C = h.latent_channels, E = C / 2, T = h.num_classes, H = a.lat_h, W = a.lat_w;
+    const int HW = H * W;
+    const TrainWs w = plan(h, B, H, W);
+    const Mlp m = mlp_of(h);
+    const auto layout = head_param_layout(h);
+    auto find = [&](const std::string& name) -> int64_t {
+        for (const auto& e : layout)
+            if (e.name == name) return e.offset;
+        return -1;
+    };
+    auto P = [&](const std::string& name) { return a.params + find(name); };
+    auto G = [&](const std::string& name) { return a.grads + find(name); };
+    const bool drop = a.dropout != 0;
+    const bool att = h.kind == VT_HEAD_ATTENTION;
+    const int nblk = (HW + 255) / 256;
+    const int chunks = std::max(1, std::min(nblk, kBands));
+    double* part_bn = reinterpret_cast<double*>(ws + w.part_bn);
+
+    // ------------------------------------------------------------------ forward (train mode)
+    const float* y = a.latent;  // input of feature_compress
+    if (att) {
+        VT_CHECK(E == 4 || E == 8 || E == 12 || E == 16, "head training needs latent_channels 8, 16, 24 or 32");
+        if (h.use_spatial_attention) {
+            VT_TRY(launch_head_spatial_attention(a.latent, P("spatial_attention.channel_att.0.weight"),
+                                                 P("spatial_attention.channel_att.2.weight"),
+                                                 P("spatial_attention.spatial_att.0.weight"), ws + w.pool,
+                                                 ws + w.cgate, ws + w.map2, ws + w.x2, ws + w.sgate, B, C, H, W, s,
+                                                 pf));
+            y = ws + w.x2;
+        }
+        const size_t smem = (static_cast<size_t>(E) * C * 9 + 8) * sizeof(float);
+        VT_KC(head_conv_train_kernel<<<dim3(nblk, B), 256, smem, s>>>(
+            y, P("feature_compress.0.weight"), P("feature_compress.0.bias"), ws + w.z, part_bn, C, E, H, W));
+        VT_KC(head_bn_finalize_kernel<<<1, 256, 0, s>>>(part_bn, B * nblk, E, static_cast<double>(B) * HW, 1e-5f,
+                                                         a.bn_momentum, ws + w.bnstat, a.bn_running_mean,
+                                                         a.bn_running_var,
+                                                         reinterpret_cast<long long*>(a.bn_num_batches_tracked)));
+        VT_KC(head_bn_relu_pool_kernel<<<dim3(64, B), 256, 0, s>>>(ws + w.z, ws + w.bnstat,
+                                                                     P("feature_compress.1.weight"),
+                                                                     P("feature_compress.1.bias"), ws + w.pooled, E,
+                                                                     H, W));
+        if (h.use_self_attention) {
+            VT_CHECK(h.attention_heads >= 1 && E % h.attention_heads == 0, "embed_dim not divisible by heads");
+            VT_KC(head_mhsa_train_kernel<false><<<B, 64, 0, s>>>(
+                ws + w.pooled, P("self_attention_post.q_proj.weight"), ws + w.feat, nullptr, nullptr, nullptr, E,
+                h.attention_heads, drop ? a.attention_dropout : 0.f, a.seed));
+        }
+    } else {
+        VT_TRY(launch_head_adaptive_pool(a.latent, ws + w.feat, B, C, H, W, 4, 4, s, pf));
+    }
+    const float* feat = (att && !h.use_self_attention) ? ws + w.pooled : ws + w.feat;
+    float* logits = a.logits ? a.logits : ws + w.logits;
+    {
+        const float* cur = feat;
+        for (int i = 0; i < m.n; ++i) {
+            const std::string lin = "classifier." + std::to_string(4 * i);
+            float* out = (i + 1 == m.n) ? logits : ws + w.a[i];
+            VT_TRY(launch_head_linear(cur, P(lin + ".weight"), P(lin + ".bias"), out, B, m.dims[i], m.dims[i + 1], s,
+                                      pf));
+            if (i + 1 < m.n) {
+                const std::string ln = "classifier." + std::to_string(4 * i + 1);
+                VT_KC(head_ln_act_drop_kernel<<<B, 256, 0, s>>>(out, ws + w.hbuf[i], ws + w.stat[i],
+                                                                 P(ln + ".weight"), P(ln + ".bias"), m.dims[i + 1],
+                                                                 m.act, drop ? m.drop[i] : 0.f, a.seed, 1u + i));
+                cur = ws + w.hbuf[i];
+            }
+        }
+    }
+    // ------------------------------------------------------------------ loss (mean over B*T) + dlogits
+    const long long nl = 1LL * B * T;
+    VT_CUDA(cudaMemsetAsync(ws + w.loss, 0, sizeof(float), s));
+    VT_TRY(launch_focal_loss(logits, a.targets, ws + w.loss, ws + w.dlogits, nl, a.focal_alpha, a.focal_gamma,
+                             a.loss_scale / static_cast<float>(nl), s, pf));
+    if (a.loss)
+        head_scale_add_kernel<<<1, 32, 0, s>>>(ws + w.loss, a.loss_scale / static_cast<float>(nl), a.loss);
+    if (!a.grads) {
+        VT_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // ------------------------------------------------------------------ backward: classifier
+    float* gcur = ws + w.dlogits;  // gradient w.r.t. the current layer's output
+    float* gbuf[2] = {ws + w.g0, ws + w.g1};
+    for (int i = m.n - 1; i >= 0; --i) {
+        const std::string lin = "classifier." + std::to_string(4 * i);
+        const float* xin = i == 0 ? feat : ws + w.hbuf[i - 1];
+        const int I = m.dims[i], O = m.dims[i + 1];
+        VT_KC(head_linear_bwd_w_kernel<<<static_cast<int>((1LL * O * I + 255) / 256), 256, 0, s>>>(
+            gcur, xin, G(lin + ".weight"), G(lin + ".bias"), B, I, O));
+        if (i == 0 && !att) break;  // the pooled latent needs no gradient
+        float* gx = i == 0 ? ws + w.dfeat : gbuf[i & 1];
+        VT_KC(head_linear_bwd_x_kernel<<<dim3((I + 255) / 256, (B + 7) / 8), 256, 0, s>>>(gcur, P(lin + ".weight"),
+                                                                                           gx, B, I, O));
+        gcur = gx;
+        if (i > 0) {
+            const std::string ln = "classifier." + std::to_string(4 * (i - 1) + 1);
+            VT_KC(head_ln_act_drop_bwd_kernel<<<B, 256, 0, s>>>(gcur, ws + w.a[i - 1], ws + w.stat[i - 1],
+                                                                 P(ln + ".weight"), P(ln + ".bias"), ws + w.dtbuf, I,
+                                                                 m.act, drop ? m.drop[i - 1] : 0.f, a.seed,
+                                                                 1u + (i - 1)));
+            VT_KC(head_ln_param_bwd_kernel<<<(I + 255) / 256, 256, 0, s>>>(ws + w.dtbuf, ws + w.a[i - 1],
+                                                                            ws + w.stat[i - 1], G(ln + ".weight"),
+                                                                            G(ln + ".bias"), B, I));
+        }
+    }
+    if (att) {
+        // -------------------------------------------------------------- self-attention
+        const float* dpooled = ws + w.dfeat;
+        if (h.use_self_attention) {
+            const int PM = 4 * (E * E + E) + 2 * E;
+            VT_KC(head_mhsa_train_kernel<true><<<B, 64, 0, s>>>(
+                ws + w.pooled, P("self_attention_post.q_proj.weight"), nullptr, ws + w.dfeat, ws + w.dpooled,
+                ws + w.part_mhsa, E, h.attention_heads, drop ? a.attention_dropout : 0.f, a.seed));
+            VT_KC(head_partial_reduce_kernel<<<(PM + 255) / 256, 256, 0, s>>>(
+                ws + w.part_mhsa, B, PM, G("self_attention_post.q_proj.weight")));
+            dpooled = ws + w.dpooled;
+        }
+        // -------------------------------------------------------------- pool / ReLU / BatchNorm / conv
+        VT_KC(head_bn_bwd_stats_kernel<<<dim3(nblk, B), 256, 0, s>>>(ws + w.z, ws + w.bnstat,
+                                                                      P("feature_compress.1.weight"),
+                                                                      P("feature_compress.1.bias"), dpooled,
+                                                                      ws + w.dz, part_bn, E, H, W));
+        VT_KC(head_bn_bwd_finalize_kernel<<<1, 256, 0, s>>>(part_bn, B * nblk, E, ws + w.bnsums,
+                                                             G("feature_compress.1.weight"),
+                                                             G("feature_compress.1.bias")));
+        const long long total = 1LL * B * E * HW;
+        VT_KC(head_bn_bwd_apply_kernel<<<static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16)), 256,
+                                          0, s>>>(ws + w.z, ws + w.bnstat, ws + w.bnsums,
+                                                  P("feature_compress.1.weight"), ws + w.dz, E, HW, total,
+                                                  1.0f / (static_cast<float>(B) * HW)));
+        float* dy = h.use_spatial_attention ? ws + w.dy : nullptr;
+        profiler_begin(pf, KC_HEAD, s, 0, 0);
+        switch (E) {
+            case 4: launch_conv_bwd<4>(y, ws + w.dz, P("feature_compress.0.weight"), ws + w.part_cw, ws + w.part_cb, dy, B, H, W, s); break;
+            case 8: launch_conv_bwd<8>(y, ws + w.dz, P("feature_compress.0.weight"), ws + w.part_cw, ws + w.part_cb, dy, B, H, W, s); break;
+            case 12: launch_conv_bwd<12>(y, ws + w.dz, P("feature_compress.0.weight"), ws + w.part_cw, ws + w.part_cb, dy, B, H, W, s); break;
+            default: launch_conv_bwd<16>(y, ws + w.dz, P("feature_compress.0.weight"), ws + w.part_cw, ws + w.part_cb, dy, B, H, W, s); break;
+        }
+        profiler_end(pf, KC_HEAD, s);
+        VT_KC(head_partial_reduce_kernel<<<(E * C * 9 + 255) / 256, 256, 0, s>>>(
+            ws + w.part_cw, B * kBands, E * C * 9, G("feature_compress.0.weight")));
+        VT_KC(head_partial_reduce_kernel<<<1, 256, 0, s>>>(ws + w.part_cb, B * kBands, E,
+                                                            G("feature_compress.0.bias")));
+        // -------------------------------------------------------------- spatial attention
+        if (h.use_spatial_attention) {
+            VT_KC(head_sa_bwd_pre_kernel<<<dim3(chunks, B), 256, 0, s>>>(a.latent, ws + w.cgate, ws + w.sgate,
+                                                                          ws + w.dy, ws + w.dpre, C, HW));
+            VT_KC(head_sa_bwd_gate_sum_kernel<<<dim3(chunks, B), 256, 0, s>>>(
+                a.latent, ws + w.cgate, ws + w.sgate, ws + w.dy, ws + w.dpre,
+                P("spatial_attention.spatial_att.0.weight"), ws + w.part_g, C, H, W));
+            VT_KC(head_sa_bwd_w7_kernel<<<dim3(chunks, B, 2), 256, 0, s>>>(ws + w.map2, ws + w.dpre,
+                                                                           ws + w.part_w7, H, W));
+            VT_KC(head_partial_reduce_kernel<<<1, 256, 0, s>>>(ws + w.part_w7, B * chunks, 98,
+                                                                G("spatial_attention.spatial_att.0.weight")));
+            VT_KC(head_sa_bwd_mlp_kernel<<<1, 256, 0, s>>>(ws + w.pool, ws + w.cgate, ws + w.part_g, chunks,
+                                                            P("spatial_attention.channel_att.0.weight"),
+                                                            P("spatial_attention.channel_att.2.weight"),
+                                                            G("spatial_attention.channel_att.0.weight"),
+                                                            G("spatial_attention.channel_att.2.weight"), B, C,
+                                                            C / 8));
+        }
+    }
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int head_dropout_masks(const vt_head_config& h, int B, float attention_dropout, unsigned long long seed,
+                       float* attn, float* const* cls, cudaStream_t s) {
+    const Mlp m = mlp_of(h);
+    if (attn && h.kind == VT_HEAD_ATTENTION && h.use_self_attention) {
+        const long long n = 1LL * B * h.attention_heads * 64 * 64;
+        head_dropout_mask_kernel<<<static_cast<int>(std::min<long long>((n + 255) / 256, 1184)), 256, 0, s>>>(
+            attn, n, attention_dropout, seed, 0u);
+    }
+    for (int i = 0; i + 1 < m.n; ++i) {
+        if (!cls || !cls[i]) continue;
+        const long long n = 1LL * B * m.dims[i + 1];
+        head_dropout_mask_kernel<<<static_cast<int>(std::min<long long>((n + 255) / 256, 1184)), 256, 0, s>>>(
+            cls[i], n, m.drop[i], seed, 1u + i);
+    }
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_adamw(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                 float wd, long long step, float grad_scale, float max_norm, double* scratch /*>=1184 doubles*/,
+                 float* norm_out, int zero_grad, cudaStream_t s, Profiler* pf) {
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, 1184)));
+    VT_KC(sumsq_partial_kernel<<<grid, 256, 0, s>>>(g, n, scratch));
+    VT_KC(sumsq_final_kernel<<<1, 256, 0, s>>>(scratch, grid, grad_scale, norm_out));
+    const float bias1 = 1.0f - static_cast<float>(pow(static_cast<double>(beta1), static_cast<double>(step)));
+    const float bias2 = 1.0f - static_cast<float>(pow(static_cast<double>(beta2), static_cast<double>(step)));
+    VT_KC(adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bias1, sqrtf(bias2),
+                                              grad_scale, max_norm, norm_out, zero_grad));
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace vt

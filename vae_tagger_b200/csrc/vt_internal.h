@@ -179,8 +179,8 @@ int launch_gemm_fp32(const GemmOp& op, cudaStream_t, Profiler*);
 
 // ---- tag head (vt_head.cu), fp32, NCHW latent
 int launch_head_spatial_attention(const float* latent, const float* w1, const float* w2, const float* w7,
-                                  float* pool, float* cgate, float* map2, float* out, int N, int C, int H, int W,
-                                  cudaStream_t, Profiler*);
+                                  float* pool, float* cgate, float* map2, float* out, float* sgate /*[N][HW] or null*/,
+                                  int N, int C, int H, int W, cudaStream_t, Profiler*);
 int launch_head_compress(const float* x, const float* cw, const float* cb, const float* bn_w, const float* bn_b,
                          const float* bn_rm, const float* bn_rv, float bn_eps, float* pooled, int N, int C, int H,
                          int W, cudaStream_t, Profiler*);

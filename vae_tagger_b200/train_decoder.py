@@ -8,8 +8,11 @@ Differences in *how* (not what):
     all-reduce is asynchronous and is waited for only after the *next* batch's encoder forward, so
     it is hidden behind it.  BatchNorm statistics stay per rank and the BatchNorm buffers are
     broadcast from rank 0 like DDP's ``broadcast_buffers`` (SURVEY.md 2.3);
-  * the focal loss forward+backward is one fused kernel.
-The decoder's own forward/backward in train() mode is a PyTorch autograd graph.
+  * the decoder's train-mode forward, the focal / BCE loss, the backward, gradient clipping and AdamW run
+    as native kernels on flat parameter / gradient buffers (``vt_head_train_step``, ``vt_adamw_step``);
+    the module's parameters are views into the flat buffer, so checkpoints and ``state_dict`` are
+    unchanged.  Configurations without a kernel (``--use_cross_attention``, ``--use_class_balanced``, a
+    non-AdamW optimizer) keep the PyTorch autograd graph for the head only.
 
 Launch:  torchrun --nproc-per-node N -m vae_tagger_b200.train_decoder --vae_checkpoint ... (same flags as
 the reference; ``--mixed_precision`` is accepted and ignored: the encoder runs bf16 tensor-core
@@ -26,9 +29,10 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
+from . import _native
 from .diffusers_vae_loader import (DiffusersVAEWrapper, create_vae_from_config_file, get_diffusers_vae_config,
                                    load_diffusers_vae_from_config)
-from .modules import (ClassificationDecoder, TaggedImageDataset, create_attention_decoder, get_image_transform,
+from .modules import (AttentionClassificationDecoder, ClassificationDecoder, TaggedImageDataset, create_attention_decoder, get_image_transform,
                       get_vae_latent_info)
 
 
@@ -57,10 +61,13 @@ def get_scheduler(name, optimizer, num_warmup_steps, num_training_steps):
 
 
 class DecoderTrainer:
-    """One training step of the decoder head on a frozen encoder, data-parallel over ``world`` ranks."""
+    """One training step of the decoder head on a frozen encoder, data-parallel over ``world`` ranks.
+
+    ``native_step``: None = use the native kernels when the configuration has them, True = require them
+    (``NativeError`` otherwise), False = PyTorch autograd for the head."""
 
     def __init__(self, vae_model, decoder, loss_fn, optimizer, scheduler=None, max_grad_norm=1.0,
-                 gradient_accumulation_steps=1, process_group=None):
+                 gradient_accumulation_steps=1, process_group=None, native_step=None):
         self.vae, self.decoder, self.loss_fn = vae_model, decoder, loss_fn
         self.opt, self.sched = optimizer, scheduler
         self.max_grad_norm = max_grad_norm
@@ -82,6 +89,94 @@ class DecoderTrainer:
         if self.world > 1:  # initial parameter broadcast (DDP does the same at wrap time)
             for t in list(decoder.parameters()) + list(decoder.buffers()):
                 dist.broadcast(t.data, src=0, group=self.pg)
+        self.native = False
+        why = self._native_plan()
+        if native_step is True and why is not None:
+            raise _native.NativeError(f"native head training step not available: {why}")
+        if native_step is not False and why is None:
+            self._go_native()
+
+    # -- native training step -----------------------------------------------------------------
+    def _native_plan(self):
+        """None when the step can run as native kernels, else the reason it cannot."""
+        from .improved_losses import FocalLoss
+
+        dec, dev = self.decoder, self.params[0].device
+        if dev.type != "cuda":
+            return "decoder is not on a CUDA device"
+        if len(self.params) != len(list(dec.parameters())):
+            return "some decoder parameters are frozen"
+        if isinstance(dec, AttentionClassificationDecoder):
+            if dec.use_cross_attention:
+                return "the cross-attention branch has no kernel"
+            want_p = (0.3, 0.2, 0.1)
+            attn_p = dec.self_attention_post.dropout.p if dec.use_self_attention else 0.0
+        elif isinstance(dec, ClassificationDecoder):
+            if not dec.use_adaptive_pooling:
+                return "ClassificationDecoder without adaptive pooling has no kernel"
+            want_p, attn_p = (0.3, 0.2), 0.0
+        else:
+            return f"{type(dec).__name__} has no kernel"
+        ps = tuple(m.p for m in dec.classifier if isinstance(m, nn.Dropout))
+        if all(p == 0 for p in ps) and attn_p == 0:
+            self._dropout = False
+        elif ps == want_p:
+            self._dropout = True
+        else:
+            return f"classifier dropout rates {ps} differ from the reference's {want_p}"
+        self._attn_p = float(attn_p)
+        if isinstance(self.loss_fn, FocalLoss) and self.loss_fn.reduction == "mean":
+            self._alpha, self._gamma = float(self.loss_fn.alpha), float(self.loss_fn.gamma)
+        elif (isinstance(self.loss_fn, nn.BCEWithLogitsLoss) and self.loss_fn.reduction == "mean"
+              and self.loss_fn.weight is None and self.loss_fn.pos_weight is None):
+            self._alpha, self._gamma = 1.0, 0.0
+        else:
+            return "loss is neither FocalLoss(mean) nor BCEWithLogitsLoss(mean)"
+        o = self.opt
+        if type(o) is not torch.optim.AdamW or len(o.param_groups) != 1:
+            return "optimizer is not a single-group torch.optim.AdamW"
+        g = o.param_groups[0]
+        if g.get("amsgrad") or g.get("maximize") or len(g["params"]) != len(self.params) or o.state:
+            return "AdamW options (amsgrad / maximize / partial parameter list / existing state) have no kernel"
+        return None
+
+    def _go_native(self):
+        dec, dev = self.decoder, self.params[0].device
+        self.ctx = _native.get_context(dev)
+        self._head_cfg = dec._head_config()
+        self.ctx.configure_head(self._head_cfg[0], **self._head_cfg[1])
+        self.ctx._head_owner = None
+        layout = self.ctx.head_param_layout()
+        named = list(dec.named_parameters())
+        if [(n, p.numel()) for n, p in named] != [(n, k) for n, _, k in layout]:
+            raise _native.NativeError("decoder.parameters() order differs from vt_head_param_layout")
+        total = layout[-1][1] + layout[-1][2]
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        for (_, p), (_, off, n) in zip(named, layout):     # parameters become views of the flat buffer
+            self.flat_param[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + n].view_as(p)
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        self._t = 0
+        bn = dec.feature_compress[1] if isinstance(dec, AttentionClassificationDecoder) else None
+        self._bn = bn
+        self._seed_base = (torch.initial_seed() * 1000003) & (2 ** 63 - 1)
+        self.rank = dist.get_rank(self.pg) if self.world > 1 else 0
+        self.native = True
+
+    def _native_forward_backward(self, latent, labels):
+        self.ctx.configure_head(self._head_cfg[0], **self._head_cfg[1])
+        self.ctx._head_owner = None                          # the inference mirror must be re-uploaded
+        self.decoder._native_key = None
+        bn = self._bn
+        loss, _ = self.ctx.head_train_step(
+            latent, labels.to(torch.float32), self.flat_param, self.flat_grad,
+            bn.running_mean if bn is not None else None, bn.running_var if bn is not None else None,
+            bn.num_batches_tracked if bn is not None else None,
+            bn_momentum=bn.momentum if bn is not None else 0.1, focal_alpha=self._alpha, focal_gamma=self._gamma,
+            loss_scale=1.0 / self.accum, dropout=self._dropout, attention_dropout=self._attn_p,
+            seed=self._seed_base + self._micro * self.world + self.rank)
+        return loss[0]
 
     # -- gradient exchange ------------------------------------------------------------------
     def _launch_allreduce(self):
@@ -96,8 +191,20 @@ class DecoderTrainer:
             return
         if self.world > 1:
             self._pending.wait()
-            self.flat_grad.div_(self.world)
+            if not self.native:
+                self.flat_grad.div_(self.world)
         self._pending = None
+        if self.native:    # clip + AdamW + zero_grad in one pass over the flat buffers (averaging folded in)
+            g = self.opt.param_groups[0]
+            self._t += 1
+            self.ctx.adamw_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr=g["lr"],
+                                betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], step=self._t,
+                                grad_scale=1.0 / self.world, max_norm=float(self.max_grad_norm or 0.0), zero_grad=True)
+            self.decoder._native_key = None
+            self.opt._opt_called = True                      # the scheduler only checks that a step happened
+            if self.sched is not None:
+                self.sched.step()
+            return
         if self.max_grad_norm and self.max_grad_norm > 0:
             nn.utils.clip_grad_norm_(self.params, self.max_grad_norm)
         self.opt.step()
@@ -114,9 +221,12 @@ class DecoderTrainer:
             for b in self.buffers:
                 dist.broadcast(b, src=0, group=self.pg)
         self.decoder.train()
-        logits = self.decoder(latent)
-        loss = self.loss_fn(logits, labels) / self.accum
-        loss.backward()                                  # accumulates into the flat bucket views
+        if self.native:
+            loss = self._native_forward_backward(latent, labels)
+        else:
+            logits = self.decoder(latent)
+            loss = self.loss_fn(logits, labels) / self.accum
+            loss.backward()                              # accumulates into the flat bucket views
         self._micro += 1
         if self._micro % self.accum == 0:
             self._launch_allreduce()
