@@ -198,6 +198,34 @@ int vt_adamw_step(vt_ctx* ctx, float* params, float* grads, float* exp_avg, floa
                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                   float max_norm, int zero_grad, float* norm_out, void* stream);
 
+/* ---------------------------------------------------------------- image preprocessing
+ * Replaces, on uint8 HWC images already on the device, what the reference does on the host through
+ * Pillow before ToTensor/Normalize: SmartResize.__call__ (modules.py:142-178: crop to the bucket's aspect
+ * ratio, then img.resize((W,H), Image.LANCZOS)) and transforms.Resize((res,res)) (modules.py:135, PIL
+ * BILINEAR).  Bit-exact with Pillow's 8-bit ImagingResample (fixed-point taps, uint8 intermediate,
+ * horizontal then vertical).  The output feeds vt_encode as VT_IN_U8_NHWC, which fuses
+ * ToTensor + Normalize(0.5, 0.5) into conv_in. */
+#define VT_FILTER_LANCZOS 1 /* PIL.Image.LANCZOS */
+#define VT_FILTER_BILINEAR 2 /* PIL.Image.BILINEAR */
+typedef struct vt_resize_args {
+    const void* src;    /* device, uint8 [src_h][src_w][3], rows src_stride bytes apart */
+    int src_w, src_h;
+    int64_t src_stride;
+    int crop_l, crop_t, crop_r, crop_b; /* img.crop((l,t,r,b)) applied first; (0,0,src_w,src_h) = none */
+    void* dst;          /* device, uint8 [dst_h][dst_w][3], rows dst_stride bytes apart */
+    int dst_w, dst_h;
+    int64_t dst_stride;
+    int filter;         /* VT_FILTER_* */
+    void* stream;
+} vt_resize_args;
+int vt_resize_u8(vt_ctx* ctx, const vt_resize_args* args);
+/* SmartResize's centre crop box for a src_w x src_h image and a dst_w x dst_h bucket (modules.py:149-172);
+ * host-only helper, box4 = (left, top, right, bottom) */
+int vt_smart_crop_box(int src_w, int src_h, int dst_w, int dst_h, int32_t* box4);
+/* the fixed-point filter taps of one axis (host-only; for tests): returns ksize, fills bounds[out_size][2]
+ * = (first input index, tap count) and kk[out_size][ksize] when the pointers are non-NULL */
+int vt_resize_coefficients(int in_size, int out_size, int filter, int32_t* ksize, int32_t* bounds, int32_t* kk);
+
 /* ---------------------------------------------------------------- accounting
  * Kernel classes: 0 implicit GEMM (tcgen05), 1 GroupNorm, 2 conv_in gather, 3 softmax,
  * 4 latent, 5 head, 6 fp32-mode contraction, 7 misc. */

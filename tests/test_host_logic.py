@@ -136,3 +136,32 @@ def test_cli_flags_cover_the_reference_entry_points():
     t = train_decoder.build_parser().parse_args(["--vae_checkpoint", "v", "--json_path", "j", "--tags_csv_path", "t"])
     assert t.learning_rate == 1e-3 and t.weight_decay == 1e-6 and t.lr_warmup_steps == 500 and t.max_grad_norm == 1.0
     assert t.focal_alpha == 1.0 and t.focal_gamma == 2.0 and t.gradient_accumulation_steps == 1 and t.seed == 42
+
+
+def test_resize_coefficients_and_crop_box_match_the_oracle():
+    """Host side of vt_resize_u8 (no GPU): the fixed-point filter taps and SmartResize's crop box computed
+    by the library equal the oracle's restatement of Pillow / modules.py:149-172 bit for bit."""
+    import numpy as np
+
+    from oracle import resample as R
+    from vae_tagger_b200 import _native
+
+    rng = np.random.default_rng(5)
+    pairs = [(4000, 1024), (97, 64), (64, 128), (513, 576), (1024, 1024), (1500, 512), (3, 7), (1, 1), (7, 3)]
+    pairs += [(int(a), int(b)) for a, b in zip(rng.integers(1, 5000, 40), rng.integers(1, 1100, 40))]
+    for a, b in pairs:
+        for f in (R.LANCZOS, R.BILINEAR):
+            ks, bd, kk = _native.resize_coefficients(a, b, f)
+            ks2, bd2, kk2 = R.precompute_coeffs(a, b, f)
+            assert ks == ks2 and np.array_equal(bd, bd2) and np.array_equal(kk, kk2), (a, b, f)
+            assert (kk.sum(1) - (1 << 22)).__abs__().max() <= ks      # taps sum to one in fixed point
+    from vae_tagger_b200.modules import AspectRatioBucketing
+
+    arb = AspectRatioBucketing()
+    for _ in range(200):
+        ow, oh = int(rng.integers(64, 6000)), int(rng.integers(64, 6000))
+        tw, th = arb.bucket_for_size(ow, oh)
+        box = _native.smart_crop_box(ow, oh, tw, th)
+        assert box == R.smart_crop_box(ow, oh, tw, th)
+        l, t, r, b = box
+        assert 0 <= l < r <= ow and 0 <= t < b <= oh

@@ -138,3 +138,31 @@ def test_adamw_oracle(train_golden):
         p, m, v, norm = OH.adamw_step(p, g, m, v, a["lr"], wd=a["wd"], step=i + 1, max_norm=a["max_norm"])
         torch.testing.assert_close(norm, a["norms"][i], atol=1e-6, rtol=1e-6)
         torch.testing.assert_close(p, a["params"][i], atol=1e-7, rtol=1e-6)
+
+
+# ----------------------------------------------------------------------------- preprocessing
+def test_resample_matches_pillow():
+    """oracle/resample.py restates Pillow's 8-bit ImagingResample (the arithmetic behind SmartResize's
+    ``img.resize(..., LANCZOS)``, modules.py:173, and ``transforms.Resize`` BILINEAR, modules.py:135):
+    bit-exact against Pillow itself on seeded images -- down- and up-scaling, one-axis-only, crops."""
+    import numpy as np
+    from PIL import Image
+
+    from oracle import resample as R
+
+    rng = np.random.default_rng(0)
+    cases = [((97, 131), (64, 64)), ((300, 200), (128, 192)), ((64, 48), (128, 96)), ((200, 100), (200, 64)),
+             ((100, 200), (64, 200)), ((513, 767), (576, 832)), ((33, 47), (33, 47))]
+    for (w, h), (tw, th) in cases:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for kind, pil in ((R.LANCZOS, Image.LANCZOS), (R.BILINEAR, Image.BILINEAR)):
+            want = np.asarray(Image.fromarray(img).resize((tw, th), pil))
+            assert np.array_equal(R.resize_u8(img, tw, th, kind), want), ((w, h), (tw, th), kind)
+    # SmartResize: crop to the bucket ratio, then LANCZOS (modules.py:142-178)
+    from vae_tagger_b200.modules import SmartResize
+
+    for (w, h), (tw, th) in [((640, 360), (576, 832)), ((300, 500), (768, 512)), ((512, 512), (512, 512)),
+                             ((401, 399), (1024, 1024))]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = np.asarray(SmartResize(tw, th)(Image.fromarray(img)))
+        assert np.array_equal(R.smart_resize_u8(img, tw, th), want), ((w, h), (tw, th))

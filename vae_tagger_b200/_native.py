@@ -17,6 +17,7 @@ from . import _build
 PREC_BF16, PREC_FP32, PREC_F16 = 0, 1, 2
 IN_F32_NCHW, IN_U8_NHWC = 0, 1
 HEAD_ATTENTION, HEAD_PLAIN = 0, 1
+FILTER_LANCZOS, FILTER_BILINEAR = 1, 2   # PIL.Image.LANCZOS / BILINEAR
 NUM_KERNEL_CLASSES = 8
 KERNEL_CLASS_NAMES = ["igemm_tcgen05", "group_norm", "conv_in_gather", "softmax", "latent", "head", "fp32_contract", "misc"]
 
@@ -78,6 +79,15 @@ class HeadTrainArgs(C.Structure):
     ]
 
 
+class ResizeArgs(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("src_w", C.c_int), ("src_h", C.c_int), ("src_stride", C.c_int64),
+        ("crop_l", C.c_int), ("crop_t", C.c_int), ("crop_r", C.c_int), ("crop_b", C.c_int),
+        ("dst", C.c_void_p), ("dst_w", C.c_int), ("dst_h", C.c_int), ("dst_stride", C.c_int64),
+        ("filter", C.c_int), ("stream", C.c_void_p),
+    ]
+
+
 # every symbol include/vae_tagger_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -102,6 +112,10 @@ SYMBOLS = {
     "vt_head_dropout_masks": (C.c_int, [_P, C.c_int, C.c_float, C.c_uint64, _P, _P, _P, _P, _P]),
     "vt_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64] + [C.c_float] * 5 + [C.c_int64, C.c_float, C.c_float,
                                                                                   C.c_int, _P, _P]),
+    "vt_resize_u8": (C.c_int, [_P, C.POINTER(ResizeArgs)]),
+    "vt_smart_crop_box": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
+    "vt_resize_coefficients": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32)]),
     "vt_profile_enable": (C.c_int, [_P, C.c_int]),
     "vt_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "vt_op_conv2d": (C.c_int, [_P, _P, _P, _P, _P, _P, _P] + [C.c_int] * 9 + [_P, _P, _P]),
@@ -157,6 +171,28 @@ def _stream(device) -> C.c_void_p:
 
 def _f32c(t: torch.Tensor, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def smart_crop_box(src_w: int, src_h: int, dst_w: int, dst_h: int):
+    """SmartResize's centre crop box (left, top, right, bottom) -- host-only, no GPU needed."""
+    box = (C.c_int32 * 4)()
+    _check(load_library().vt_smart_crop_box(src_w, src_h, dst_w, dst_h, box))
+    return tuple(box)
+
+
+def resize_coefficients(in_size: int, out_size: int, filter: int = FILTER_LANCZOS):
+    """(ksize, bounds [out,2], kk [out,ksize]) int32 numpy arrays of one resize axis -- host-only."""
+    import numpy as np
+
+    lib = load_library()
+    ks = C.c_int32()
+    _check(lib.vt_resize_coefficients(in_size, out_size, filter, C.byref(ks), None, None))
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ks.value), np.int32)
+    _check(lib.vt_resize_coefficients(in_size, out_size, filter, C.byref(ks),
+                                      bounds.ctypes.data_as(C.POINTER(C.c_int32)),
+                                      kk.ctypes.data_as(C.POINTER(C.c_int32))))
+    return ks.value, bounds, kk
 
 
 class Context:
@@ -341,6 +377,29 @@ class Context:
             _check(self.lib.vt_focal_loss(self.h, _ptr(x), _ptr(y), n, float(alpha), float(gamma), 1.0 / n, _ptr(loss),
                                           _ptr(grad), _stream(self.device)))
         return loss, grad
+
+    # ------------------------------------------------------------------ preprocessing
+    def resize_u8(self, src: torch.Tensor, size, box=None, filter=FILTER_LANCZOS, out: torch.Tensor = None):
+        """``PIL.Image.fromarray(src).crop(box).resize(size, filter)`` on the device, bit-exact.
+        src: uint8 [h,w,3] CUDA tensor (row stride may exceed w*3); size = (W, H); box = (l,t,r,b) or None;
+        out: optional uint8 [H,W,3] view to write into (e.g. one image of a batch buffer)."""
+        assert src.dtype == torch.uint8 and src.is_cuda and src.dim() == 3 and src.shape[2] == 3
+        assert src.stride(2) == 1 and src.stride(1) == 3, "pixels must be packed RGB"
+        W, H = int(size[0]), int(size[1])
+        if out is None:
+            out = torch.empty(H, W, 3, dtype=torch.uint8, device=self.device)
+        assert out.dtype == torch.uint8 and tuple(out.shape) == (H, W, 3) and out.stride(2) == 1 and out.stride(1) == 3
+        h, w = src.shape[0], src.shape[1]
+        l, t, r, b = box if box is not None else (0, 0, w, h)
+        a = ResizeArgs()
+        a.src = src.data_ptr(); a.src_w = w; a.src_h = h; a.src_stride = src.stride(0)
+        a.crop_l, a.crop_t, a.crop_r, a.crop_b = int(l), int(t), int(r), int(b)
+        a.dst = out.data_ptr(); a.dst_w = W; a.dst_h = H; a.dst_stride = out.stride(0)
+        a.filter = int(filter)
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_resize_u8(self.h, C.byref(a)))
+        return out
 
     # ------------------------------------------------------------------ head training step
     def head_param_layout(self):

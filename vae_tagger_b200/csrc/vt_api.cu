@@ -8,6 +8,7 @@
 #include "../../include/vae_tagger_b200.h"
 #include "vt_head_train.h"
 #include "vt_internal.h"
+#include "vt_resize.h"
 #include "vt_ptx.cuh"
 
 using namespace vt;
@@ -101,6 +102,7 @@ struct vt_ctx {
 
     DevBuf opws;  // single-op entry points
     DevBuf optws; // optimizer scratch
+    ResizeCache* resize = nullptr;  // preprocessing coefficient tables
 };
 
 namespace {
@@ -685,6 +687,7 @@ int vt_ctx_destroy(vt_ctx* c) {
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     c->hws.release(); c->e2e.release(); c->opws.release(); c->optws.release();
+    resize_cache_destroy(c->resize);
     profiler_destroy(c->prof);
     delete c;
     return 0;
@@ -1004,6 +1007,40 @@ int vt_adamw_step(vt_ctx* c, float* params, float* grads, float* exp_avg, float*
     float* norm = norm_out ? norm_out : reinterpret_cast<float*>(scratch + 1184);
     return launch_adamw(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
                         max_norm, scratch, norm, zero_grad, static_cast<cudaStream_t>(stream), c->prof);
+}
+
+// ------------------------------------------------------------------------------------- preprocessing
+int vt_resize_u8(vt_ctx* c, const vt_resize_args* a) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr && a->src != nullptr && a->dst != nullptr, "null arguments");
+    VT_CHECK(a->filter == VT_FILTER_LANCZOS || a->filter == VT_FILTER_BILINEAR, "unknown resize filter");
+    VT_CHECK(a->src_w > 0 && a->src_h > 0 && a->dst_w > 0 && a->dst_h > 0, "image sizes must be positive");
+    VT_CHECK(a->crop_l >= 0 && a->crop_t >= 0 && a->crop_r <= a->src_w && a->crop_b <= a->src_h &&
+                 a->crop_l < a->crop_r && a->crop_t < a->crop_b,
+             "crop box must be a non-empty box inside the image");
+    VT_CHECK(a->src_stride >= 3LL * a->src_w && a->dst_stride >= 3LL * a->dst_w, "row stride smaller than a row");
+    if (!c->resize) c->resize = resize_cache_create();
+    return resize_u8(c->resize, *a, c->prof);
+}
+
+int vt_smart_crop_box(int src_w, int src_h, int dst_w, int dst_h, int32_t* box4) {
+    VT_CHECK(box4 != nullptr && src_w > 0 && src_h > 0 && dst_w > 0 && dst_h > 0, "bad crop box arguments");
+    int b[4];
+    smart_crop_box(src_w, src_h, dst_w, dst_h, b);
+    for (int i = 0; i < 4; ++i) box4[i] = b[i];
+    return 0;
+}
+
+int vt_resize_coefficients(int in_size, int out_size, int filter, int32_t* ksize, int32_t* bounds, int32_t* kk) {
+    VT_CHECK(in_size > 0 && out_size > 0 && ksize != nullptr, "bad coefficient arguments");
+    VT_CHECK(filter == VT_FILTER_LANCZOS || filter == VT_FILTER_BILINEAR, "unknown resize filter");
+    std::vector<int> b, k;
+    int ks = 0;
+    resize_coefficients(in_size, out_size, filter, &ks, b, k);
+    *ksize = ks;
+    if (bounds) std::copy(b.begin(), b.end(), bounds);
+    if (kk) std::copy(k.begin(), k.end(), kk);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------- e2e

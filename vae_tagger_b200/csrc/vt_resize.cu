@@ -1,0 +1,313 @@
+// GPU image preprocessing in front of conv_in: crop + resize of uint8 HWC images, bit-exact with what
+// the reference does on the host through Pillow.
+//
+// Replaces SmartResize.__call__ (modules.py:142-178: crop box, then img.resize((W,H), Image.LANCZOS)) and
+// transforms.Resize((res,res)) on a PIL image (modules.py:135: PIL BILINEAR).  The arithmetic is not in the
+// reference but in its dependency Pillow (requirements.txt: Pillow>=9.0, unpinned; 12.2.0 in this image),
+// src/libImaging/Resample.c, restated here from its published algorithm:
+//   * per output pixel a window [xmin, xmin+n) of the input, n <= ksize = 2*ceil(support*max(scale,1))+1,
+//     filter taps evaluated in double precision at (x + xmin - center + 0.5)/max(scale,1), normalised to
+//     sum 1, then rounded to fixed point with 22 fractional bits (precompute_coeffs, normalize_coeffs_8bpc);
+//   * horizontal pass over the rows, then vertical pass, each  out = clip8((2^21 + sum k*in) >> 22)  in
+//     int32, with a uint8 intermediate image; a pass is skipped when that dimension does not change.
+// The coefficient tables are computed on the host (they depend only on (in size, out size, filter)) and
+// cached on the device; the two passes are byte-streaming kernels: HBM/L2 bound, no tensor cores.
+#include <math.h>
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "../../include/vae_tagger_b200.h"
+#include "vt_internal.h"
+#include "vt_resize.h"
+
+namespace vt {
+
+namespace {
+
+constexpr int kPrecisionBits = 32 - 8 - 2;
+constexpr int kHBlock = 128;  // output pixels per CTA of the horizontal pass
+
+double sinc(double x) {
+    if (x == 0.0) return 1.0;
+    x = x * M_PI;
+    return sin(x) / x;
+}
+double filter_value(int filter, double x) {
+    if (filter == VT_FILTER_LANCZOS) return (-3.0 <= x && x < 3.0) ? sinc(x) * sinc(x / 3) : 0.0;
+    if (x < 0.0) x = -x;
+    return x < 1.0 ? 1.0 - x : 0.0;
+}
+
+__device__ __forceinline__ unsigned char clip8(int acc) {
+    acc >>= kPrecisionBits;
+    return static_cast<unsigned char>(min(max(acc, 0), 255));
+}
+
+// Horizontal pass.  grid (ceil(out_w/128), ceil(rows/rows_per_cta)); a CTA stages the span of source
+// pixels its 128 output pixels need in shared memory (coalesced), one row at a time.
+//   src: rows of 3-byte pixels, already offset to the crop origin; dst: [rows][out_w][3], row pitch dst_pitch
+//   kk_t: [ksize][out_w] (transposed: coalesced across the threads of a CTA), bounds: [out_w] (xmin, n)
+__global__ void __launch_bounds__(kHBlock) resize_h_kernel(const unsigned char* __restrict__ src, long long src_pitch,
+                                                           unsigned char* __restrict__ dst, long long dst_pitch,
+                                                           const int* __restrict__ kk_t,
+                                                           const int2* __restrict__ bounds, int out_w, int rows,
+                                                           int rows_per_cta) {
+    extern __shared__ unsigned char span[];
+    const int x0 = blockIdx.x * kHBlock;
+    const int xx = x0 + threadIdx.x;
+    const bool live = xx < out_w;
+    const int2 b = live ? bounds[xx] : make_int2(0, 0);
+    const int first = bounds[x0].x;
+    const int xl = min(x0 + kHBlock, out_w) - 1;
+    const int last = bounds[xl].x + bounds[xl].y;  // windows start and end monotonically
+    const int nbytes = (last - first) * 3;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    for (int r = r0; r < r1; ++r) {
+        const unsigned char* row = src + r * src_pitch + 3LL * first;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbytes; i += kHBlock) span[i] = row[i];
+        __syncthreads();
+        if (live) {
+            int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+            const unsigned char* p = span + 3 * (b.x - first);
+            for (int k = 0; k < b.y; ++k) {
+                const int c = kk_t[1LL * k * out_w + xx];
+                a0 += c * p[3 * k];
+                a1 += c * p[3 * k + 1];
+                a2 += c * p[3 * k + 2];
+            }
+            unsigned char* o = dst + r * dst_pitch + 3LL * xx;
+            o[0] = clip8(a0);
+            o[1] = clip8(a1);
+            o[2] = clip8(a2);
+        }
+    }
+}
+
+// Vertical pass.  One thread per VEC bytes of an output row (a row is out_w*3 bytes: channels and pixels
+// are interchangeable here), grid (ceil(row_bytes/VEC/256), out_h).  kk: [out_h][ksize], bounds [out_h].
+template <int VEC>
+__global__ void __launch_bounds__(256) resize_v_kernel(const unsigned char* __restrict__ src, long long src_pitch,
+                                                       unsigned char* __restrict__ dst, long long dst_pitch,
+                                                       const int* __restrict__ kk, const int2* __restrict__ bounds,
+                                                       int ksize, int row_bytes) {
+    const int yy = blockIdx.y;
+    const int j = (blockIdx.x * 256 + threadIdx.x) * VEC;
+    if (j >= row_bytes) return;
+    const int2 b = bounds[yy];
+    const int* k = kk + 1LL * yy * ksize;
+    int acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 1 << (kPrecisionBits - 1);
+    const unsigned char* p = src + b.x * src_pitch + j;
+    for (int t = 0; t < b.y; ++t) {
+        const int c = k[t];
+        if (VEC == 4) {
+            const uchar4 u = *reinterpret_cast<const uchar4*>(p);
+            acc[0] += c * u.x;
+            acc[1 % VEC] += c * u.y;
+            acc[2 % VEC] += c * u.z;
+            acc[3 % VEC] += c * u.w;
+        } else {
+            acc[0] += c * p[0];
+        }
+        p += src_pitch;
+    }
+    unsigned char* o = dst + yy * dst_pitch + j;
+    if (VEC == 4) {
+        *reinterpret_cast<uchar4*>(o) = make_uchar4(clip8(acc[0]), clip8(acc[1 % VEC]), clip8(acc[2 % VEC]),
+                                                    clip8(acc[3 % VEC]));
+    } else {
+        o[0] = clip8(acc[0]);
+    }
+}
+
+// plain crop copy when neither dimension changes (Pillow returns a copy of the cropped image)
+__global__ void __launch_bounds__(256) copy_rows_kernel(const unsigned char* __restrict__ src, long long src_pitch,
+                                                        unsigned char* __restrict__ dst, long long dst_pitch,
+                                                        int row_bytes) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j < row_bytes) dst[blockIdx.y * dst_pitch + j] = src[blockIdx.y * src_pitch + j];
+}
+
+}  // namespace
+
+struct ResizeTable {
+    int ksize = 0, out_size = 0, max_span = 0;
+    int* kk = nullptr;      // [out][ksize]
+    int* kk_t = nullptr;    // [ksize][out]
+    int2* bounds = nullptr; // [out]
+    unsigned long long stamp = 0;
+};
+
+struct ResizeCache {
+    std::map<std::tuple<int, int, int>, ResizeTable> tables;
+    unsigned long long clock = 0;
+    void* tmp = nullptr;
+    size_t tmp_cap = 0;
+};
+
+ResizeCache* resize_cache_create() { return new ResizeCache(); }
+void resize_cache_destroy(ResizeCache* c) {
+    if (!c) return;
+    for (auto& kv : c->tables) {
+        cudaFree(kv.second.kk);
+        cudaFree(kv.second.kk_t);
+        cudaFree(kv.second.bounds);
+    }
+    if (c->tmp) cudaFree(c->tmp);
+    delete c;
+}
+
+// Resample.c precompute_coeffs + normalize_coeffs_8bpc for the box (0, in_size)
+void resize_coefficients(int in_size, int out_size, int filter, int* ksize_out, std::vector<int>& bounds,
+                         std::vector<int>& kk) {
+    const double fsupport = filter == VT_FILTER_LANCZOS ? 3.0 : 1.0;
+    double scale = static_cast<double>(in_size) / out_size;
+    double filterscale = scale;
+    if (filterscale < 1.0) filterscale = 1.0;
+    const double support = fsupport * filterscale;
+    const int ksize = static_cast<int>(ceil(support)) * 2 + 1;
+    bounds.assign(static_cast<size_t>(out_size) * 2, 0);
+    kk.assign(static_cast<size_t>(out_size) * ksize, 0);
+    std::vector<double> w(ksize);
+    const double ss = 1.0 / filterscale;
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = (xx + 0.5) * scale;
+        int xmin = static_cast<int>(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = static_cast<int>(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        double ww = 0.0;
+        for (int x = 0; x < xmax; ++x) {
+            w[x] = filter_value(filter, (x + xmin - center + 0.5) * ss);
+            ww += w[x];
+        }
+        for (int x = 0; x < xmax; ++x) {
+            const double v = ww != 0.0 ? w[x] / ww : w[x];
+            kk[static_cast<size_t>(xx) * ksize + x] = v < 0 ? static_cast<int>(-0.5 + v * (1 << kPrecisionBits))
+                                                            : static_cast<int>(0.5 + v * (1 << kPrecisionBits));
+        }
+        bounds[2 * xx] = xmin;
+        bounds[2 * xx + 1] = xmax;
+    }
+    *ksize_out = ksize;
+}
+
+static int get_table(ResizeCache* c, int in_size, int out_size, int filter, const ResizeTable** out) {
+    const auto key = std::make_tuple(in_size, out_size, filter);
+    auto it = c->tables.find(key);
+    if (it == c->tables.end()) {
+        if (c->tables.size() >= 256) {  // evict the least recently used table (cudaFree waits for its users)
+            auto old = c->tables.begin();
+            for (auto j = c->tables.begin(); j != c->tables.end(); ++j)
+                if (j->second.stamp < old->second.stamp) old = j;
+            cudaFree(old->second.kk);
+            cudaFree(old->second.kk_t);
+            cudaFree(old->second.bounds);
+            c->tables.erase(old);
+        }
+        ResizeTable t;
+        std::vector<int> bounds, kk;
+        resize_coefficients(in_size, out_size, filter, &t.ksize, bounds, kk);
+        t.out_size = out_size;
+        std::vector<int> kk_t(kk.size());
+        for (int xx = 0; xx < out_size; ++xx)
+            for (int k = 0; k < t.ksize; ++k)
+                kk_t[static_cast<size_t>(k) * out_size + xx] = kk[static_cast<size_t>(xx) * t.ksize + k];
+        for (int x0 = 0; x0 < out_size; x0 += kHBlock) {
+            const int xl = std::min(x0 + kHBlock, out_size) - 1;
+            t.max_span = std::max(t.max_span, bounds[2 * xl] + bounds[2 * xl + 1] - bounds[2 * x0]);
+        }
+        VT_CUDA(cudaMalloc(&t.kk, kk.size() * sizeof(int)));
+        VT_CUDA(cudaMalloc(&t.kk_t, kk.size() * sizeof(int)));
+        VT_CUDA(cudaMalloc(&t.bounds, bounds.size() * sizeof(int)));
+        VT_CUDA(cudaMemcpy(t.kk, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
+        VT_CUDA(cudaMemcpy(t.kk_t, kk_t.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
+        VT_CUDA(cudaMemcpy(t.bounds, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
+        it = c->tables.emplace(key, t).first;
+    }
+    it->second.stamp = ++c->clock;
+    *out = &it->second;
+    return 0;
+}
+
+void smart_crop_box(int ow, int oh, int tw, int th, int* box) {
+    // SmartResize, crop_mode 'center' (modules.py:149-172); Python float == C double
+    const double target = static_cast<double>(tw) / th;
+    const double ratio = static_cast<double>(ow) / oh;
+    box[0] = 0; box[1] = 0; box[2] = ow; box[3] = oh;
+    if (ratio > target) {
+        const int nw = static_cast<int>(oh * target);
+        const int left = (ow - nw) / 2;
+        box[0] = left; box[2] = left + nw;
+    } else if (ratio < target) {
+        const int nh = static_cast<int>(ow / target);
+        const int top = (oh - nh) / 2;
+        box[1] = top; box[3] = top + nh;
+    }
+}
+
+int resize_u8(ResizeCache* c, const vt_resize_args& a, Profiler* pf) {
+    cudaStream_t s = static_cast<cudaStream_t>(a.stream);
+    const int cw = a.crop_r - a.crop_l, ch = a.crop_b - a.crop_t;
+    const unsigned char* src = static_cast<const unsigned char*>(a.src) + a.crop_t * a.src_stride + 3LL * a.crop_l;
+    unsigned char* dst = static_cast<unsigned char*>(a.dst);
+    const bool need_h = cw != a.dst_w, need_v = ch != a.dst_h;
+    const double bytes = 3.0 * cw * ch + 3.0 * a.dst_w * a.dst_h + (need_h && need_v ? 6.0 * a.dst_w * ch : 0.0);
+    profiler_begin(pf, KC_MISC, s, 0, bytes);
+    const unsigned char* vin = src;
+    long long vin_pitch = a.src_stride;
+    if (need_h) {
+        const ResizeTable* t = nullptr;
+        VT_TRY(get_table(c, cw, a.dst_w, a.filter, &t));
+        unsigned char* hout = dst;
+        long long hpitch = a.dst_stride;
+        if (need_v) {  // uint8 intermediate image [ch][dst_w][3], rows padded to 16 bytes
+            hpitch = (3LL * a.dst_w + 15) / 16 * 16;
+            const size_t need = static_cast<size_t>(hpitch) * ch;
+            if (need > c->tmp_cap) {
+                if (c->tmp) cudaFree(c->tmp);
+                c->tmp = nullptr;
+                c->tmp_cap = 0;
+                VT_CUDA(cudaMalloc(&c->tmp, need));
+                c->tmp_cap = need;
+            }
+            hout = static_cast<unsigned char*>(c->tmp);
+        }
+        const size_t smem = static_cast<size_t>(t->max_span) * 3;
+        VT_CHECK(smem <= 200 * 1024, "horizontal scale factor too large for the staged resize kernel");
+        if (smem > 48 * 1024)
+            VT_CUDA(cudaFuncSetAttribute(resize_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        const int gx = (a.dst_w + kHBlock - 1) / kHBlock;
+        int rows_per_cta = 1;
+        while (rows_per_cta < 16 && 1LL * gx * ((ch + rows_per_cta - 1) / rows_per_cta) > 148 * 16) rows_per_cta *= 2;
+        resize_h_kernel<<<dim3(gx, (ch + rows_per_cta - 1) / rows_per_cta), kHBlock, smem, s>>>(
+            src, a.src_stride, hout, hpitch, t->kk_t, t->bounds, a.dst_w, ch, rows_per_cta);
+        vin = hout;
+        vin_pitch = hpitch;
+    }
+    if (need_v) {
+        const ResizeTable* t = nullptr;
+        VT_TRY(get_table(c, ch, a.dst_h, a.filter, &t));
+        const int row_bytes = 3 * a.dst_w;
+        const bool vec = row_bytes % 4 == 0 && vin_pitch % 4 == 0 && a.dst_stride % 4 == 0 &&
+                         reinterpret_cast<uintptr_t>(vin) % 4 == 0 && reinterpret_cast<uintptr_t>(dst) % 4 == 0;
+        if (vec)
+            resize_v_kernel<4><<<dim3((row_bytes / 4 + 255) / 256, a.dst_h), 256, 0, s>>>(
+                vin, vin_pitch, dst, a.dst_stride, t->kk, t->bounds, t->ksize, row_bytes);
+        else
+            resize_v_kernel<1><<<dim3((row_bytes + 255) / 256, a.dst_h), 256, 0, s>>>(
+                vin, vin_pitch, dst, a.dst_stride, t->kk, t->bounds, t->ksize, row_bytes);
+    }
+    if (!need_h && !need_v)
+        copy_rows_kernel<<<dim3((3 * cw + 255) / 256, ch), 256, 0, s>>>(src, a.src_stride, dst, a.dst_stride, 3 * cw);
+    profiler_end(pf, KC_MISC, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace vt
