@@ -59,6 +59,25 @@ def test_infer_full_cli_matches_oracle(tmp_path, golden, monkeypatch):
             assert abs(t["confidence"] - c) <= 2e-4
         assert abs(entry["max_confidence"] - want["max_confidence"]) <= 2e-4
         assert abs(entry["avg_confidence_top5"] - want["avg_confidence_top5"]) <= 2e-4
+    # --gpu_preprocess: same pixels (the resize kernels are bit-exact with PIL), hence the same JSON
+    base = ["--vae_checkpoint", str(tmp_path / "vae.safetensors"), "--vae_config_path", str(tmp_path / "vae.json"),
+            "--decoder_checkpoint", str(tmp_path / "decoder.bin"), "--image_path", str(img_dir), "--tags_csv_path",
+            str(tmp_path / "tags.csv"), "--resolution", str(res), "--batch_size", "2"]
+
+    def same(a, b):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert a[k]["total_tags_above_threshold"] == b[k]["total_tags_above_threshold"]
+            assert [t["tag"] for t in a[k]["predicted_tags"]] == [t["tag"] for t in b[k]["predicted_tags"]]
+            for ta, tb in zip(a[k]["predicted_tags"], b[k]["predicted_tags"]):
+                assert abs(ta["confidence"] - tb["confidence"]) <= 1e-4
+            assert abs(a[k]["max_confidence"] - b[k]["max_confidence"]) <= 1e-4
+
+    same(infer_full.main(base + ["--output_dir", str(tmp_path / "out_gpu"), "--gpu_preprocess"]), saved)
+    bucket = ["--use_bucketing", "--base_resolution", "64", "--max_resolution", "128", "--bucket_step", "32"]
+    host = infer_full.main(base + bucket + ["--output_dir", str(tmp_path / "out_b")])
+    assert len(host) == 5
+    same(infer_full.main(base + bucket + ["--output_dir", str(tmp_path / "out_bg"), "--gpu_preprocess"]), host)
     with pytest.raises(RuntimeError):
         infer_full.main(["--vae_checkpoint", str(tmp_path / "vae.safetensors"), "--decoder_checkpoint",
                          str(tmp_path / "missing.bin"), "--image_path", str(img_dir), "--tags_csv_path",

@@ -105,6 +105,28 @@ def infer_and_classify(args):
         groups.setdefault(shape, []).append(p)
     results, errors = {}, 0
     bs = max(1, getattr(args, "batch_size", 8))
+    if getattr(args, "gpu_preprocess", False):
+        # decode on the host, everything after that on the GPU: uint8 upload, crop + resize kernels
+        # (bit-exact with PIL), ToTensor + Normalize fused into conv_in
+        import numpy as np
+
+        from .preprocess import BucketBatcher
+
+        def decoded():
+            nonlocal errors
+            for p in image_paths:
+                try:
+                    yield str(p), np.asarray(Image.open(p).convert("RGB"))
+                except Exception as e:  # noqa: BLE001 - the reference skips unreadable images (:130-132)
+                    errors += 1
+                    print(f"skipping image {p}: {e}")
+
+        batcher = BucketBatcher(device, batch_size=bs, resolution=args.resolution, bucketing=bucketing)
+        for _, names, batch in batcher.batches(decoded()):
+            conf, idx, cnt = classify_batch(vae_model, decoder, batch, args.confidence_threshold)
+            for name, c, i, n in zip(names, conf, idx, cnt):
+                results[name] = format_result(c, i, n, tag_names)
+        groups = {}
     for (w, h), paths in groups.items():
         tf = get_image_transform(args.resolution, bucketing is not None, (w, h) if bucketing else None)
         for i0 in range(0, len(paths), bs):
@@ -155,6 +177,8 @@ def build_parser():
     p.add_argument("--base_resolution", type=int, default=512)
     p.add_argument("--max_resolution", type=int, default=1024)
     p.add_argument("--bucket_step", type=int, default=64)
+    p.add_argument("--gpu_preprocess", action="store_true",
+                   help="resize / crop / normalise on the GPU (bit-exact with the PIL transform) instead of the host")
     return p
 
 
