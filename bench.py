@@ -25,6 +25,9 @@ import sys
 import threading
 import time
 
+# NCCL prints its version banner on stdout when NCCL_DEBUG is set on the box; stdout carries the JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
