@@ -92,6 +92,23 @@ typedef struct vt_encode_args {
  * AutoencoderKL.encode(x).latent_dist.{mode,sample,mean,logvar} (:73-74, :79-80). */
 int vt_encode(vt_ctx* ctx, const vt_encode_args* args);
 
+/* ---------------------------------------------------------------- VAE decoder
+ * Replaces: AutoencoderKL.decode(z).sample as called by DiffusersVAEWrapper.decode / .forward
+ * (diffusers_vae_loader.py:72-76, :88-94).  Uses the configuration given to vt_encoder_configure.
+ * name = diffusers state-dict key below "decoder.", e.g. "up_blocks.0.resnets.0.conv1.weight". */
+int vt_decoder_set_param(vt_ctx* ctx, const char* name, const float* data, const int64_t* shape, int ndim);
+int vt_decoder_finalize(vt_ctx* ctx);
+typedef struct vt_decode_args {
+    const float* latent; /* device [B,LC,h,w] fp32 NCHW */
+    int batch, lat_h, lat_w;
+    int precision;         /* VT_PREC_BF16 / VT_PREC_FP32 */
+    int apply_scale_shift; /* 1: DiffusersVAEWrapper.decode semantics, (z - shift) / scale first (:88-93) */
+    float* image;          /* out, device [B,3,8h,8w] fp32 NCHW */
+    int micro_batch;       /* images per internal pass; 0 = library default */
+    void* stream;
+} vt_decode_args;
+int vt_decode(vt_ctx* ctx, const vt_decode_args* args);
+
 /* ---------------------------------------------------------------- tag head
  * Replaces: AttentionClassificationDecoder / ClassificationDecoder (modules.py:303-475). */
 #define VT_HEAD_ATTENTION 0 /* AttentionClassificationDecoder */

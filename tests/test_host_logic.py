@@ -45,9 +45,7 @@ def test_vae_state_dict_keys_match_oracle_and_load():
     assert sorted(vae.state_dict().keys()) == sorted(oracle.state_dict().keys())
     assert sum(p.numel() for p in vae.parameters()) == 34_274_208
     sd = dict(oracle.state_dict())
-    # a full FLUX checkpoint also carries decoder.* keys; legacy checkpoints name the attention
-    # projections query/key/value/proj_attn
-    sd["decoder.conv_in.weight"] = torch.zeros(1)
+    # legacy checkpoints name the attention projections query/key/value/proj_attn
     for old, new in (("query", "to_q"), ("key", "to_k"), ("value", "to_v"), ("proj_attn", "to_out.0")):
         for leaf in ("weight", "bias"):
             sd[f"encoder.mid_block.attentions.0.{old}.{leaf}"] = sd.pop(f"encoder.mid_block.attentions.0.{new}.{leaf}")
@@ -57,6 +55,20 @@ def test_vae_state_dict_keys_match_oracle_and_load():
                        oracle.state_dict()["encoder.mid_block.attentions.0.to_q.weight"])
     assert vae.config.scaling_factor == 0.3611 and vae.config.shift_factor == 0.1159
     assert hasattr(vae.config, "scaling_factor")
+    # a full FLUX checkpoint also carries decoder.* keys: they materialise the decoder half
+    from oracle.decoder import make_oracle_decoder
+
+    assert vae.decoder is None
+    dec = make_oracle_decoder(1)
+    full = dict(oracle.state_dict())
+    full.update({"decoder." + k: v for k, v in dec.state_dict().items()})
+    missing, unexpected = vae.load_state_dict(full, strict=False)
+    assert not missing and not unexpected
+    assert sorted(k for k in vae.state_dict() if k.startswith("decoder.")) == sorted("decoder." + k for k in dec.state_dict())
+    assert torch.equal(vae.state_dict()["decoder.up_blocks.2.resnets.0.conv_shortcut.weight"],
+                       dec.state_dict()["up_blocks.2.resnets.0.conv_shortcut.weight"])
+    assert sum(p.numel() for p in vae.decoder.parameters()) == 49_545_475
+    assert sum(p.numel() for p in vae.parameters()) == 83_819_683      # SURVEY.md 8c known answer 1
 
 
 def test_loader_file_roundtrip(tmp_path):
@@ -84,8 +96,10 @@ def test_no_cpu_fallback():
         dec(torch.zeros(1, 16, 8, 8))
     with pytest.raises(_native.NativeError):
         dec.get_confidence(torch.zeros(1, 16, 8, 8))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(_native.NativeError):      # the decoder half has no CPU path either
         wrap.vae.decode(torch.zeros(1, 16, 8, 8))
+    with pytest.raises(_native.NativeError):
+        wrap.decode(torch.zeros(1, 16, 8, 8))
 
 
 def test_train_mode_head_is_differentiable_and_matches_oracle(golden):

@@ -44,6 +44,13 @@ class EncodeArgs(C.Structure):
     ]
 
 
+class DecodeArgs(C.Structure):
+    _fields_ = [
+        ("latent", C.c_void_p), ("batch", C.c_int), ("lat_h", C.c_int), ("lat_w", C.c_int), ("precision", C.c_int),
+        ("apply_scale_shift", C.c_int), ("image", C.c_void_p), ("micro_batch", C.c_int), ("stream", C.c_void_p),
+    ]
+
+
 class HeadConfig(C.Structure):
     _fields_ = [
         ("kind", C.c_int), ("latent_channels", C.c_int), ("num_classes", C.c_int),
@@ -99,6 +106,9 @@ SYMBOLS = {
     "vt_encoder_set_param": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
     "vt_encoder_finalize": (C.c_int, [_P]),
     "vt_encode": (C.c_int, [_P, C.POINTER(EncodeArgs)]),
+    "vt_decoder_set_param": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "vt_decoder_finalize": (C.c_int, [_P]),
+    "vt_decode": (C.c_int, [_P, C.POINTER(DecodeArgs)]),
     "vt_head_configure": (C.c_int, [_P, C.POINTER(HeadConfig)]),
     "vt_head_set_param": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
     "vt_head_finalize": (C.c_int, [_P]),
@@ -293,6 +303,28 @@ class Context:
         if want_moments:
             return lat, mean, logvar
         return lat
+
+    # ------------------------------------------------------------------ VAE decoder
+    def load_decoder(self, state_dict: Dict[str, torch.Tensor]):
+        """state_dict keys relative to ``decoder.`` (diffusers naming); needs ``configure_encoder`` first."""
+        self._set_params(self.lib.vt_decoder_set_param, state_dict)
+        _check(self.lib.vt_decoder_finalize(self.h))
+
+    def decode(self, latent: torch.Tensor, precision=PREC_BF16, apply_scale_shift=False, micro_batch=0):
+        """latent [B,LC,h,w] -> image [B,3,8h,8w] fp32 (``vae.decode(z).sample``; with apply_scale_shift the
+        ``(z - shift) / scale`` of ``DiffusersVAEWrapper.decode`` first)."""
+        lat = _f32c(latent, self.device)
+        B, _, h, w = lat.shape
+        up = 1 << (self.num_blocks - 1)
+        img = torch.empty(B, 3, h * up, w * up, device=self.device, dtype=torch.float32)
+        a = DecodeArgs()
+        a.latent = lat.data_ptr(); a.batch = B; a.lat_h = h; a.lat_w = w; a.precision = precision
+        a.apply_scale_shift = int(bool(apply_scale_shift)); a.image = img.data_ptr()
+        a.micro_batch = int(micro_batch)
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_decode(self.h, C.byref(a)))
+        return img
 
     # ------------------------------------------------------------------ head
     def configure_head(self, kind: int, latent_channels: int, num_classes: int, use_spatial_attention=True,

@@ -4,9 +4,10 @@ backed by the sm_100a encoder kernels.
 Only what the encode+tag hot path touches is implemented:
 ``.config`` (attribute access, incl. ``scaling_factor`` / ``shift_factor``),
 ``.encode(x).latent_dist`` with ``.mode() / .sample() / .kl() / .mean / .logvar / .std / .var``,
-``.load_state_dict(sd, strict=False)`` (diffusers key names, Appendix B; ``decoder.*`` keys of a
-full FLUX VAE checkpoint are tolerated), ``.parameters()``, ``.to()``, ``.eval()``.
-``.decode`` (the VAE decoder) is outside the path and raises.
+``.load_state_dict(sd, strict=False)`` (diffusers key names, Appendix B), ``.parameters()``, ``.to()``,
+``.eval()``.  ``.decode(z).sample`` / ``.forward`` (the VAE decoder) run the same kernel
+family; the decoder's parameters are materialised on demand (a checkpoint with ``decoder.*`` keys,
+``decode()``, or ``enable_decoder()``) so that encode-only users do not pay for them.
 
 The module holds ordinary ``nn.Parameter``s under diffusers' names so checkpoints load with the
 stock ``nn.Module`` machinery; the parameters are mirrored into the native context (repacked to
@@ -85,6 +86,44 @@ def _encoder_params(cfg) -> nn.Module:
     return enc
 
 
+def _decoder_params(cfg) -> nn.Module:
+    """Parameter containers with diffusers' ``Decoder`` state-dict layout (never called)."""
+    chans = list(reversed(cfg.block_out_channels))
+    g = cfg.norm_num_groups
+    dec = nn.Module()
+    dec.conv_in = nn.Conv2d(cfg.latent_channels, chans[0], 3, 1, 1)
+    mid = nn.Module()
+    c = chans[0]
+    if cfg.mid_block_add_attention:
+        a = nn.Module()
+        a.group_norm = nn.GroupNorm(g, c, eps=1e-6, affine=True)
+        a.to_q = nn.Linear(c, c)
+        a.to_k = nn.Linear(c, c)
+        a.to_v = nn.Linear(c, c)
+        a.to_out = nn.ModuleList([nn.Linear(c, c), nn.Dropout(0.0)])
+        mid.attentions = nn.ModuleList([a])
+    mid.resnets = nn.ModuleList([_resnet(c, c, g), _resnet(c, c, g)])
+    dec.mid_block = mid
+    blocks, cin = [], chans[0]
+    for i, cout in enumerate(chans):
+        b = nn.Module()
+        b.resnets = nn.ModuleList([_resnet(cin if j == 0 else cout, cout, g) for j in range(cfg.layers_per_block + 1)])
+        if i < len(chans) - 1:
+            u = nn.Module()
+            u.conv = nn.Conv2d(cout, cout, 3, 1, 1)
+            b.upsamplers = nn.ModuleList([u])
+        blocks.append(b)
+        cin = cout
+    dec.up_blocks = nn.ModuleList(blocks)
+    dec.conv_norm_out = nn.GroupNorm(g, chans[-1], eps=1e-6, affine=True)
+    dec.conv_out = nn.Conv2d(chans[-1], cfg.out_channels, 3, 1, 1)
+    return dec
+
+
+class DecoderOutput(SimpleNamespace):
+    pass
+
+
 class DiagonalGaussianDistribution:
     """Posterior returned by ``AutoencoderKL.encode(x).latent_dist``."""
 
@@ -144,6 +183,10 @@ class AutoencoderKL(nn.Module):
             use_post_quant_conv=use_post_quant_conv, force_upcast=force_upcast,
             mid_block_add_attention=mid_block_add_attention, latents_mean=latents_mean, latents_std=latents_std)
         self.encoder = _encoder_params(self.config)
+        # The decoder half (49.5 M parameters) is materialised on demand: by a checkpoint that carries
+        # ``decoder.*`` keys, by ``decode()`` / ``forward()``, or by ``enable_decoder()``.
+        self.decoder = None
+        self._native_dec_key = None
         # "bf16" (tcgen05 path) or "fp32" (verification mode); VT_B200_PRECISION overrides the default
         self.precision = os.environ.get("VT_B200_PRECISION", "bf16")
         self.micro_batch = 0
@@ -154,9 +197,11 @@ class AutoencoderKL(nn.Module):
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         sd = {}
         dropped = []
+        if any(k.startswith("decoder.") for k in state_dict):
+            self.enable_decoder()
         for k, v in state_dict.items():
-            if k.startswith(("decoder.", "quant_conv.", "post_quant_conv.")):
-                dropped.append(k)  # VAE decoder half: not on the encode path
+            if k.startswith(("quant_conv.", "post_quant_conv.")):
+                dropped.append(k)  # FLUX has no quant convs (use_quant_conv=False)
                 continue
             parts = k.split(".")
             if "attentions" in parts and len(parts) >= 2 and parts[-2] in _LEGACY_ATTN:
@@ -167,7 +212,17 @@ class AutoencoderKL(nn.Module):
             sd[k] = v
         result = super().load_state_dict(sd, strict=strict, assign=assign)
         self._native_key = None
+        self._native_dec_key = None
         return result
+
+    def enable_decoder(self):
+        """Materialise the decoder parameters (PyTorch default init) next to the encoder's."""
+        if self.decoder is None:
+            ref = next(self.encoder.parameters())
+            self.decoder = _decoder_params(self.config).to(device=ref.device, dtype=ref.dtype)
+            for p in self.decoder.parameters():
+                p.requires_grad_(ref.requires_grad)
+        return self
 
     # ------------------------------------------------------------------ native mirror
     def _sync_native(self, device) -> "_native.Context":
@@ -212,13 +267,34 @@ class AutoencoderKL(nn.Module):
         return ctx.encode(x, precision=self._precision(), sample=sample, apply_scale_shift=apply_scale_shift,
                           seed=seed, noise=noise, micro_batch=self.micro_batch, single_lane=self.single_lane)
 
-    def decode(self, z, return_dict: bool = True):
-        raise NotImplementedError(
-            "AutoencoderKL.decode (the VAE decoder) is outside the encode+tag hot path of vae_tagger_b200 "
-            "(SURVEY.md 8f item 3)")
+    def _sync_native_decoder(self, device) -> "_native.Context":
+        ctx = self._sync_native(device)  # the decoder shares the encoder's configuration
+        self.enable_decoder()
+        params = list(self.decoder.named_parameters())
+        key = (self._native_key, tuple((p.data_ptr(), p._version) for _, p in params))
+        if key != self._native_dec_key:
+            ctx.load_decoder({n: p for n, p in params})
+            self._native_dec_key = key
+        return ctx
 
-    def forward(self, x):
-        raise NotImplementedError("use .encode(); the reconstruction path needs the VAE decoder (out of scope)")
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, return_dict: bool = True, apply_scale_shift: bool = False):
+        """``vae.decode(z).sample`` (diffusers_vae_loader.py:75, :94); ``apply_scale_shift`` fuses the
+        ``(z - shift_factor) / scaling_factor`` of ``DiffusersVAEWrapper.decode`` (:88-93) into the first kernel."""
+        ctx = self._sync_native_decoder(self._device_of(z))
+        img = ctx.decode(z, precision=self._precision(), apply_scale_shift=apply_scale_shift,
+                         micro_batch=self.micro_batch)
+        if not return_dict:
+            return (img,)
+        return DecoderOutput(sample=img)
+
+    @torch.no_grad()
+    def forward(self, sample: torch.Tensor, sample_posterior: bool = False, return_dict: bool = True,
+                generator: Optional[torch.Generator] = None):
+        """diffusers ``AutoencoderKL.forward``: decode(posterior.sample() or .mode())."""
+        posterior = self.encode(sample).latent_dist
+        z = posterior.sample(generator=generator) if sample_posterior else posterior.mode()
+        return self.decode(z, return_dict=return_dict)
 
     @classmethod
     def from_pretrained(cls, path, subfolder=None, **kw):

@@ -93,6 +93,17 @@ struct vt_ctx {
     } lanes[2];
     cudaEvent_t ev_start = nullptr;
 
+    // ---- VAE decoder; shares ecfg with the encoder
+    bool dec_ready = false;
+    std::map<std::string, Param> dparams;
+    std::vector<void*> dpacked;
+    ConvW dconv_in, dconv_out;
+    std::vector<std::vector<ResnetW>> up;  // [block][layer], layers_per_block + 1 each
+    std::vector<ConvW> upsample;           // per block (Cout == 0: none)
+    ResnetW dmid0, dmid1;
+    AttnW dattn;
+    NormW dnorm_out;
+
     // ---- head
     vt_head_config hcfg{};
     bool hcfg_set = false, head_ready = false;
@@ -144,7 +155,8 @@ void free_params(std::map<std::string, Param>& m) {
 // offset k_off (the shortcut slab lands behind the taps).
 template <int OFMT>  // FMT_BF16 / FMT_F32 / FMT_F16
 __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restrict__ dstv, int Cout, int Cin, int ks,
-                                   int Ktot, int k_off) {
+                                   int Ktot, int k_off, int cin_pad = 0) {
+    const int CinP = cin_pad > 0 ? cin_pad : Cin;  // K index stride per tap (input channels zero-padded)
     const long long total = 1LL * Cout * Cin * ks * ks;
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
         // i indexes src = ((co*Cin + ci)*ks + kh)*ks + kw
@@ -153,7 +165,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restri
         const int kh = static_cast<int>(r % ks); r /= ks;
         const int ci = static_cast<int>(r % Cin);
         const int co = static_cast<int>(r / Cin);
-        const long long d = 1LL * co * Ktot + k_off + (kh * ks + kw) * Cin + ci;
+        const long long d = 1LL * co * Ktot + k_off + (kh * ks + kw) * CinP + ci;
         if constexpr (OFMT == FMT_BF16) static_cast<bf16*>(dstv)[d] = __float2bfloat16(src[i]);
         else if constexpr (OFMT == FMT_F16)
             static_cast<__half*>(dstv)[d] = __float2half_rn(fminf(fmaxf(src[i], -65504.f), 65504.f));
@@ -167,16 +179,19 @@ __global__ void add_vec_kernel(float* __restrict__ a, const float* __restrict__ 
 
 struct Packer {
     vt_ctx* c;
+    std::map<std::string, Param>* params;  // eparams (encoder) or dparams (decoder)
+    std::vector<void*>* packed;            // allocations owned by the packed representation
+    const char* what;
     int get(const std::string& name, std::initializer_list<int64_t> shape, const Param** out) {
-        auto it = c->eparams.find(name);
-        if (it == c->eparams.end()) {
-            set_error("encoder parameter missing: " + name);
+        auto it = params->find(name);
+        if (it == params->end()) {
+            set_error(std::string(what) + " parameter missing: " + name);
             return -4;
         }
         const Param& p = it->second;
         std::vector<int64_t> want(shape);
         if (p.shape != want) {
-            std::string m = "encoder parameter " + name + " has shape [";
+            std::string m = std::string(what) + " parameter " + name + " has shape [";
             for (auto d : p.shape) m += std::to_string(d) + ",";
             m += "] expected [";
             for (auto d : want) m += std::to_string(d) + ",";
@@ -191,7 +206,7 @@ struct Packer {
         void* q = nullptr;
         VT_CUDA(cudaMalloc(&q, n * sizeof(T)));
         VT_CUDA(cudaMemset(q, 0, n * sizeof(T)));
-        c->epacked.push_back(q);
+        packed->push_back(q);
         *p = static_cast<T*>(q);
         return 0;
     }
@@ -222,6 +237,24 @@ struct Packer {
             pack_weight_kernel<FMT_F32><<<grid, 256>>>(sw->dev, w->w32, Cout, Cs, 1, Ktot, ks * ks * Cin);
             add_vec_kernel<<<(Cout + 255) / 256, 256>>>(w->bias, sb->dev, Cout);
         }
+        VT_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // conv with the input channels zero-padded to CinP (one 64-wide K chunk) and the output channels to CoutP
+    // (a 32-column accumulator tile): the decoder's conv_in (16 -> 512) and conv_out (128 -> 3)
+    int conv_padded(const std::string& prefix, int Cin, int Cout, int ks, int CinP, int CoutP, ConvW* w, bool f16) {
+        const Param *pw, *pb;
+        VT_TRY(get(prefix + ".weight", {Cout, Cin, ks, ks}, &pw));
+        VT_TRY(get(prefix + ".bias", {Cout}, &pb));
+        const int Ktot = ks * ks * CinP;
+        w->Cin = CinP; w->Cout = CoutP; w->ksize = ks; w->Cs = 0; w->Ktot = Ktot; w->f16 = f16;
+        VT_TRY(alloc(&w->w16, static_cast<size_t>(CoutP) * Ktot));
+        VT_TRY(alloc(&w->w32, static_cast<size_t>(CoutP) * Ktot));
+        VT_TRY(alloc(&w->bias, static_cast<size_t>(CoutP)));
+        if (f16) pack_weight_kernel<FMT_F16><<<256, 256>>>(pw->dev, w->w16, Cout, Cin, ks, Ktot, 0, CinP);
+        else pack_weight_kernel<FMT_BF16><<<256, 256>>>(pw->dev, w->w16, Cout, Cin, ks, Ktot, 0, CinP);
+        pack_weight_kernel<FMT_F32><<<256, 256>>>(pw->dev, w->w32, Cout, Cin, ks, Ktot, 0, CinP);
+        VT_CUDA(cudaMemcpy(w->bias, pb->dev, Cout * sizeof(float), cudaMemcpyDeviceToDevice));
         VT_CUDA(cudaGetLastError());
         return 0;
     }
@@ -264,6 +297,14 @@ struct Packer {
         return 0;
     }
 };
+
+void free_packed_decoder(vt_ctx* c) {
+    for (void* p : c->dpacked) cudaFree(p);
+    c->dpacked.clear();
+    c->up.clear();
+    c->upsample.clear();
+    c->dec_ready = false;
+}
 
 void free_packed(vt_ctx* c) {
     for (void* p : c->epacked) cudaFree(p);
@@ -391,130 +432,74 @@ struct EncRun {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, int img0, int n, cudaStream_t s) {
-    const vt_encoder_config& cfg = c->ecfg;
-    const int H = a->height, Wd = a->width;
-    const int fp32 = a->precision == VT_PREC_FP32;
-    const size_t es = fp32 ? 4 : 2;
-    const int C0 = cfg.block_out_channels[0];
-    const int LC = cfg.latent_channels;
-    const int nb = cfg.num_blocks;
-    const int lh = H >> (nb - 1), lw = Wd >> (nb - 1);
-    const long long tokens = 1LL * lh * lw;
-    const int Cm = cfg.block_out_channels[nb - 1];
-
-    // ---- workspace layout.  One activation buffer holds the largest tensor of any level (level 0).
-    size_t act = static_cast<size_t>(n) * H * Wd * C0 * es;
-    act = align_up(act, 1024);
+struct AttnPlan {  // workspace of the mid-block attention (after the four activation buffers)
     size_t attn_bytes = 0;
     long long rows_per_chunk = 0;
     int ipc = 1;
     size_t qk_b = 0, vt_b = 0, s_b = 0, p_b = 0, o_b = 0, part_b = 0;
     int pv_splits = 1;
-    if (cfg.mid_block_add_attention) {
-        const size_t s_budget = 64ull << 20;  // score tile kept L2 resident
-        const long long max_rows = static_cast<long long>(s_budget / (tokens * 4));
-        if (max_rows >= tokens) {
-            rows_per_chunk = tokens;
-            ipc = static_cast<int>(std::min<long long>(n, std::max<long long>(1, max_rows / tokens)));
-        } else {
-            rows_per_chunk = std::max<long long>(128, max_rows / 128 * 128);
-            ipc = 1;
-        }
-        qk_b = align_up(static_cast<size_t>(n) * tokens * 2 * Cm * es, 1024);
-        vt_b = align_up(static_cast<size_t>(n) * tokens * Cm * es, 1024);
-        s_b = align_up(static_cast<size_t>(ipc) * rows_per_chunk * tokens * 4, 1024);
-        p_b = align_up(static_cast<size_t>(ipc) * rows_per_chunk * tokens * es, 1024);
-        o_b = vt_b;
-        // P.V of a row chunk has only ceil(rows/128) * C/256 output tiles: split K (= tokens) across
-        // CTAs when that leaves most of the machine idle, combine the fp32 partials afterwards
-        if (!fp32 && ipc == 1) {
-            const long long tiles = (rows_per_chunk + 127) / 128 * ((Cm + 255) / 256);
-            const long long kchunks = tokens / 64;
-            int want = static_cast<int>(std::min<long long>(16, 148 / std::max<long long>(1, tiles)));
-            while (want > 1 && kchunks % want != 0) --want;
-            pv_splits = std::max(1, want);
-            if (pv_splits > 1) part_b = align_up(static_cast<size_t>(pv_splits) * rows_per_chunk * Cm * 4, 1024);
-        }
-        attn_bytes = qk_b + vt_b + s_b + p_b + o_b + part_b;
-    }
-    VT_TRY(L.arena.ensure(4 * act + attn_bytes));
-    char* base = static_cast<char*>(L.arena.p);
-    void* Xp = base;           // residual stream
-    void* T = base + act;      // normalised operand
-    void* Hb = base + 2 * act; // conv1 output / conv_in gather
-    void* Yp = base + 3 * act; // block output
-    char* ab = base + 4 * act;
+};
 
-    const int groups = cfg.norm_num_groups;
-    const int max_slots = 64;
-    VT_TRY(L.stats.ensure(static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double)));
-    VT_CUDA(cudaMemsetAsync(L.stats.p, 0, static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double), s));
-    VT_TRY(L.mom.ensure(static_cast<size_t>(n) * tokens * 2 * LC * sizeof(float)));
-
-    EncRun R{c, s, fp32, n, static_cast<double*>(L.stats.p), 0, groups};
-    {
-        const char* e = getenv("VT_B200_NO_FUSED_GN");
-        R.use_fused = !(e && e[0] == '1');
-        const char* f = getenv("VT_B200_NO_FLASH");
-        R.use_flash = !(f && f[0] == '1');
-    }
-
-    // ---- conv_in: gather the 3x3x3 patches (K = 27 padded to 64) then one K chunk of contraction
-    const char* img = static_cast<const char*>(a->images);
-    const size_t img_stride = a->in_fmt == VT_IN_U8_NHWC ? static_cast<size_t>(H) * Wd * 3
-                                                         : static_cast<size_t>(H) * Wd * 3 * sizeof(float);
-    double* st_x = R.new_stats();
-    Act X{Xp, R.raw_fmt()};
-    const bool convin_direct = !fp32 && cfg.block_out_channels[0] == 128 && X.fmt == FMT_BF16 && c->conv_in.f16 &&
-                               !(getenv("VT_B200_NO_CONVIN") && getenv("VT_B200_NO_CONVIN")[0] == '1');
-    if (convin_direct) {
-        // operand rows built in shared memory from the image itself (vt_convin.cuh)
-        ConvInOp op;
-        op.img = img + img_stride * img0; op.in_fmt = a->in_fmt; op.N = n; op.H = H; op.W = Wd;
-        op.w = c->conv_in.w16; op.bias = c->conv_in.bias; op.out = X.p; op.stats = st_x;
-        VT_TRY(launch_conv_in(op, s, c->prof));
+AttnPlan plan_attention(bool enabled, int n, long long tokens, int Cm, size_t es, int fp32) {
+    AttnPlan pl;
+    if (!enabled) return pl;
+    const size_t s_budget = 64ull << 20;  // score tile kept L2 resident
+    const long long max_rows = static_cast<long long>(s_budget / (tokens * 4));
+    if (max_rows >= tokens) {
+        pl.rows_per_chunk = tokens;
+        pl.ipc = static_cast<int>(std::min<long long>(n, std::max<long long>(1, max_rows / tokens)));
     } else {
-        VT_TRY(launch_im2col3x3(img + img_stride * img0, a->in_fmt, Hb, R.opd_fmt(), n, H, Wd, s, c->prof));
-        ConvW w = c->conv_in;  // viewed as a 1x1 conv over the 64-wide gathered patches
-        w.Cin = 64; w.ksize = 1; w.Cs = 0;
-        VT_TRY(R.conv(Hb, H, Wd, w, 1, nullptr, nullptr, X, st_x));
+        pl.rows_per_chunk = std::max<long long>(128, max_rows / 128 * 128);
+        pl.ipc = 1;
     }
-    void* spare = Yp;
-    auto advance = [&](Act out) { spare = X.p; X = out; };
+    pl.qk_b = align_up(static_cast<size_t>(n) * tokens * 2 * Cm * es, 1024);
+    pl.vt_b = align_up(static_cast<size_t>(n) * tokens * Cm * es, 1024);
+    pl.s_b = align_up(static_cast<size_t>(pl.ipc) * pl.rows_per_chunk * tokens * 4, 1024);
+    pl.p_b = align_up(static_cast<size_t>(pl.ipc) * pl.rows_per_chunk * tokens * es, 1024);
+    pl.o_b = pl.vt_b;
+    // P.V of a row chunk has only ceil(rows/128) * C/256 output tiles: split K (= tokens) across
+    // CTAs when that leaves most of the machine idle, combine the fp32 partials afterwards
+    if (!fp32 && pl.ipc == 1) {
+        const long long tiles = (pl.rows_per_chunk + 127) / 128 * ((Cm + 255) / 256);
+        const long long kchunks = tokens / 64;
+        int want = static_cast<int>(std::min<long long>(16, 148 / std::max<long long>(1, tiles)));
+        while (want > 1 && kchunks % want != 0) --want;
+        pl.pv_splits = std::max(1, want);
+        if (pl.pv_splits > 1) pl.part_b = align_up(static_cast<size_t>(pl.pv_splits) * pl.rows_per_chunk * Cm * 4, 1024);
+    }
+    pl.attn_bytes = pl.qk_b + pl.vt_b + pl.s_b + pl.p_b + pl.o_b + pl.part_b;
+    return pl;
+}
 
-    int h = H, w_ = Wd;
-    for (int b = 0; b < nb; ++b) {
-        const int nl = static_cast<int>(c->down[b].size());
-        const bool has_down = c->downsample[b].Cout != 0;
-        for (int l = 0; l < nl; ++l) {
-            double* st_o = R.new_stats();
-            Act out{spare, R.raw_fmt()};
-            VT_TRY(R.resnet(c->down[b][l], X, st_x, h, w_, b, T, Hb, out, st_o));
-            advance(out);
-            st_x = st_o;
-        }
-        if (has_down) {
-            double* st_o = R.new_stats();
-            Act out{spare, R.raw_fmt()};
-            VT_CHECK(fp32 || X.fmt == FMT_BF16, "downsample operand must be bf16");
-            VT_TRY(R.conv(X.p, h, w_, c->downsample[b], 2, nullptr, nullptr, out, st_o));
-            advance(out);
-            st_x = st_o;
-            h /= 2; w_ /= 2;
-        }
-    }
-    const int lvl = nb - 1;
+struct MidW {
+    const ResnetW* mid0;
+    const AttnW* attn;
+    const ResnetW* mid1;
+    bool has_attn;
+};
+
+// UNetMidBlock2D (shared by the encoder and the decoder): resnet, single-head attention over all
+// tokens, resnet.  X / spare / st_x are the caller's ping-pong state.
+int run_mid_block(EncRun& R, const MidW& M, const AttnPlan& pl, char* ab, Act& X, void*& spare, double*& st_x, void* T,
+                  void* Hb, int n, int h, int w_, int fp32, size_t es) {
+    vt_ctx* c = R.c;
+    cudaStream_t s = R.s;
+    const long long tokens = 1LL * h * w_;
+    const long long rows_per_chunk = pl.rows_per_chunk;
+    const int ipc = pl.ipc, pv_splits = pl.pv_splits;
+    const size_t qk_b = pl.qk_b, vt_b = pl.vt_b, s_b = pl.s_b, p_b = pl.p_b, o_b = pl.o_b;
+    auto advance = [&](Act out) { spare = X.p; X = out; };
+    const int lvl = 0;
     // ---- mid block
     {
         double* st_o = R.new_stats();
         Act out{spare, R.raw_fmt()};
-        VT_TRY(R.resnet(c->mid0, X, st_x, h, w_, lvl, T, Hb, out, st_o));
+        VT_TRY(R.resnet((*M.mid0), X, st_x, h, w_, lvl, T, Hb, out, st_o));
         advance(out);
         st_x = st_o;
     }
-    if (cfg.mid_block_add_attention) {
-        const AttnW& A = c->attn;
+    if (M.has_attn) {
+        const AttnW& A = (*M.attn);
         const int C = A.C;
         char* QK = ab;
         char* Vt = QK + qk_b;
@@ -598,9 +583,99 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
     {
         double* st_o = R.new_stats();
         Act out{spare, R.raw_fmt()};
-        VT_TRY(R.resnet(c->mid1, X, st_x, h, w_, lvl, T, Hb, out, st_o));
+        VT_TRY(R.resnet((*M.mid1), X, st_x, h, w_, lvl, T, Hb, out, st_o));
         advance(out);
         st_x = st_o;
+    }
+    return 0;
+}
+
+int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, int img0, int n, cudaStream_t s) {
+    const vt_encoder_config& cfg = c->ecfg;
+    const int H = a->height, Wd = a->width;
+    const int fp32 = a->precision == VT_PREC_FP32;
+    const size_t es = fp32 ? 4 : 2;
+    const int C0 = cfg.block_out_channels[0];
+    const int LC = cfg.latent_channels;
+    const int nb = cfg.num_blocks;
+    const int lh = H >> (nb - 1), lw = Wd >> (nb - 1);
+    const long long tokens = 1LL * lh * lw;
+    const int Cm = cfg.block_out_channels[nb - 1];
+
+    // ---- workspace layout.  One activation buffer holds the largest tensor of any level (level 0).
+    size_t act = static_cast<size_t>(n) * H * Wd * C0 * es;
+    act = align_up(act, 1024);
+    const AttnPlan pl = plan_attention(cfg.mid_block_add_attention != 0, n, tokens, Cm, es, fp32);
+    const size_t attn_bytes = pl.attn_bytes;
+    VT_TRY(L.arena.ensure(4 * act + attn_bytes));
+    char* base = static_cast<char*>(L.arena.p);
+    void* Xp = base;           // residual stream
+    void* T = base + act;      // normalised operand
+    void* Hb = base + 2 * act; // conv1 output / conv_in gather
+    void* Yp = base + 3 * act; // block output
+    char* ab = base + 4 * act;
+
+    const int groups = cfg.norm_num_groups;
+    const int max_slots = 64;
+    VT_TRY(L.stats.ensure(static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double)));
+    VT_CUDA(cudaMemsetAsync(L.stats.p, 0, static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double), s));
+    VT_TRY(L.mom.ensure(static_cast<size_t>(n) * tokens * 2 * LC * sizeof(float)));
+
+    EncRun R{c, s, fp32, n, static_cast<double*>(L.stats.p), 0, groups};
+    {
+        const char* e = getenv("VT_B200_NO_FUSED_GN");
+        R.use_fused = !(e && e[0] == '1');
+        const char* f = getenv("VT_B200_NO_FLASH");
+        R.use_flash = !(f && f[0] == '1');
+    }
+
+    // ---- conv_in: gather the 3x3x3 patches (K = 27 padded to 64) then one K chunk of contraction
+    const char* img = static_cast<const char*>(a->images);
+    const size_t img_stride = a->in_fmt == VT_IN_U8_NHWC ? static_cast<size_t>(H) * Wd * 3
+                                                         : static_cast<size_t>(H) * Wd * 3 * sizeof(float);
+    double* st_x = R.new_stats();
+    Act X{Xp, R.raw_fmt()};
+    const bool convin_direct = !fp32 && cfg.block_out_channels[0] == 128 && X.fmt == FMT_BF16 && c->conv_in.f16 &&
+                               !(getenv("VT_B200_NO_CONVIN") && getenv("VT_B200_NO_CONVIN")[0] == '1');
+    if (convin_direct) {
+        // operand rows built in shared memory from the image itself (vt_convin.cuh)
+        ConvInOp op;
+        op.img = img + img_stride * img0; op.in_fmt = a->in_fmt; op.N = n; op.H = H; op.W = Wd;
+        op.w = c->conv_in.w16; op.bias = c->conv_in.bias; op.out = X.p; op.stats = st_x;
+        VT_TRY(launch_conv_in(op, s, c->prof));
+    } else {
+        VT_TRY(launch_im2col3x3(img + img_stride * img0, a->in_fmt, Hb, R.opd_fmt(), n, H, Wd, s, c->prof));
+        ConvW w = c->conv_in;  // viewed as a 1x1 conv over the 64-wide gathered patches
+        w.Cin = 64; w.ksize = 1; w.Cs = 0;
+        VT_TRY(R.conv(Hb, H, Wd, w, 1, nullptr, nullptr, X, st_x));
+    }
+    void* spare = Yp;
+    auto advance = [&](Act out) { spare = X.p; X = out; };
+
+    int h = H, w_ = Wd;
+    for (int b = 0; b < nb; ++b) {
+        const int nl = static_cast<int>(c->down[b].size());
+        const bool has_down = c->downsample[b].Cout != 0;
+        for (int l = 0; l < nl; ++l) {
+            double* st_o = R.new_stats();
+            Act out{spare, R.raw_fmt()};
+            VT_TRY(R.resnet(c->down[b][l], X, st_x, h, w_, b, T, Hb, out, st_o));
+            advance(out);
+            st_x = st_o;
+        }
+        if (has_down) {
+            double* st_o = R.new_stats();
+            Act out{spare, R.raw_fmt()};
+            VT_CHECK(fp32 || X.fmt == FMT_BF16, "downsample operand must be bf16");
+            VT_TRY(R.conv(X.p, h, w_, c->downsample[b], 2, nullptr, nullptr, out, st_o));
+            advance(out);
+            st_x = st_o;
+            h /= 2; w_ /= 2;
+        }
+    }
+    {   // ---- mid block
+        MidW M{&c->mid0, &c->attn, &c->mid1, cfg.mid_block_add_attention != 0};
+        VT_TRY(run_mid_block(R, M, pl, ab, X, spare, st_x, T, Hb, n, h, w_, fp32, es));
     }
     // ---- conv_norm_out + SiLU + conv_out -> moments (fp32 NHWC) -> DiagonalGaussian outputs
     VT_TRY(R.gn(X, T, st_x, c->norm_out, tokens, Cm, 1));
@@ -615,6 +690,102 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
                                     cfg.scaling_factor, cfg.shift_factor,
                                     a->apply_scale_shift && cfg.has_scaling_factor,
                                     a->apply_scale_shift && cfg.has_shift_factor, s, c->prof));
+    VT_CHECK(R.stats_used <= max_slots, "GroupNorm statistics slots exhausted");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The decoder schedule (diffusers Decoder.forward; reference call sites diffusers_vae_loader.py:72-76,
+// :88-94): conv_in, mid block, four UpDecoderBlock2D (layers_per_block + 1 resnets, nearest-2x upsample +
+// conv3x3 on all but the last), conv_norm_out + SiLU + conv_out.  Same kernels and formats as the encoder;
+// the nearest-neighbour upsample is an explicit HBM pass into the operand buffer of the following conv.
+int run_decoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_decode_args* a, int img0, int n, cudaStream_t s) {
+    const vt_encoder_config& cfg = c->ecfg;
+    const int fp32 = a->precision == VT_PREC_FP32;
+    const size_t es = fp32 ? 4 : 2;
+    const int nb = cfg.num_blocks;
+    const int LC = cfg.latent_channels;
+    const int lh = a->lat_h, lw = a->lat_w;
+    const int H = lh << (nb - 1), Wd = lw << (nb - 1);
+    const long long tokens = 1LL * lh * lw;
+    const int Cm = cfg.block_out_channels[nb - 1];
+    const int groups = cfg.norm_num_groups;
+
+    // ---- workspace: four ping-pong buffers sized for the largest tensor of the schedule
+    size_t elems = static_cast<size_t>(n) * tokens * std::max(Cm, 64);
+    {
+        int h = lh, w = lw;
+        for (int b = 0; b < nb; ++b) {
+            const int cout = cfg.block_out_channels[nb - 1 - b];
+            elems = std::max(elems, static_cast<size_t>(n) * h * w * std::max(cout, b ? cfg.block_out_channels[nb - b] : Cm));
+            if (b < nb - 1) {
+                h *= 2; w *= 2;
+                elems = std::max(elems, static_cast<size_t>(n) * h * w * cout);
+            }
+        }
+        elems = std::max(elems, static_cast<size_t>(n) * H * Wd * 32 * 4 / es);  // padded fp32 conv_out tile
+    }
+    const size_t act = align_up(elems * es, 1024);
+    const AttnPlan pl = plan_attention(cfg.mid_block_add_attention != 0, n, tokens, Cm, es, fp32);
+    VT_TRY(L.arena.ensure(4 * act + pl.attn_bytes));
+    char* base = static_cast<char*>(L.arena.p);
+    void* Xp = base;
+    void* T = base + act;
+    void* Hb = base + 2 * act;
+    void* Yp = base + 3 * act;
+    char* ab = base + 4 * act;
+    const int max_slots = 64;
+    VT_TRY(L.stats.ensure(static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double)));
+    VT_CUDA(cudaMemsetAsync(L.stats.p, 0, static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double), s));
+
+    EncRun R{c, s, fp32, n, static_cast<double*>(L.stats.p), 0, groups};
+    {
+        const char* e = getenv("VT_B200_NO_FUSED_GN");
+        R.use_fused = !(e && e[0] == '1');
+        const char* f = getenv("VT_B200_NO_FLASH");
+        R.use_flash = !(f && f[0] == '1');
+    }
+    // ---- (z - shift) / scale (diffusers_vae_loader.py:88-93), NCHW fp32 -> NHWC padded to one K chunk
+    const size_t lat_stride = static_cast<size_t>(LC) * tokens;
+    const float shift = (a->apply_scale_shift && cfg.has_shift_factor) ? cfg.shift_factor : 0.f;
+    const float inv_scale = (a->apply_scale_shift && cfg.has_scaling_factor) ? 1.0f / cfg.scaling_factor : 1.0f;
+    VT_TRY(launch_latent_to_nhwc(a->latent + lat_stride * img0, Hb, R.raw_fmt(), n, LC, c->dconv_in.Cin, tokens, shift,
+                                 inv_scale, s, c->prof));
+    double* st_x = R.new_stats();
+    Act X{Xp, R.raw_fmt()};
+    VT_TRY(R.conv(Hb, lh, lw, c->dconv_in, 1, nullptr, nullptr, X, st_x));
+    void* spare = Yp;
+    auto advance = [&](Act out) { spare = X.p; X = out; };
+    int h = lh, w_ = lw;
+    {
+        MidW M{&c->dmid0, &c->dattn, &c->dmid1, cfg.mid_block_add_attention != 0};
+        VT_TRY(run_mid_block(R, M, pl, ab, X, spare, st_x, T, Hb, n, h, w_, fp32, es));
+    }
+    for (int b = 0; b < nb; ++b) {
+        for (size_t l = 0; l < c->up[b].size(); ++l) {
+            double* st_o = R.new_stats();
+            Act out{spare, R.raw_fmt()};
+            VT_TRY(R.resnet(c->up[b][l], X, st_x, h, w_, b, T, Hb, out, st_o));
+            advance(out);
+            st_x = st_o;
+        }
+        if (c->upsample[b].Cout != 0) {
+            const int C = c->upsample[b].Cin;
+            VT_TRY(launch_upsample2x_nhwc(X.p, T, static_cast<int>(es), n, h, w_, C, s, c->prof));
+            h *= 2; w_ *= 2;
+            double* st_o = R.new_stats();
+            Act out{spare, R.raw_fmt()};
+            VT_TRY(R.conv(T, h, w_, c->upsample[b], 1, nullptr, nullptr, out, st_o));
+            advance(out);
+            st_x = st_o;
+        }
+    }
+    // ---- conv_norm_out + SiLU + conv_out (output channels padded to 32, fp32 NHWC) -> image NCHW fp32
+    const int C0 = cfg.block_out_channels[0];
+    VT_TRY(R.gn(X, T, st_x, c->dnorm_out, 1LL * h * w_, C0, 1));
+    VT_TRY(R.conv(T, h, w_, c->dconv_out, 1, nullptr, nullptr, Act{Hb, FMT_F32}, nullptr));
+    VT_TRY(launch_nhwc_to_image(static_cast<const float*>(Hb), a->image + static_cast<size_t>(3) * H * Wd * img0, n, 3,
+                                c->dconv_out.Cout, 1LL * H * Wd, s, c->prof));
     VT_CHECK(R.stats_used <= max_slots, "GroupNorm statistics slots exhausted");
     return 0;
 }
@@ -678,7 +849,9 @@ int vt_ctx_destroy(vt_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_packed(c);
+    free_packed_decoder(c);
     free_params(c->eparams);
+    free_params(c->dparams);
     free_params(c->hparams);
     for (auto& L : c->lanes) {
         L.arena.release(); L.stats.release(); L.mom.release();
@@ -724,7 +897,7 @@ int vt_encoder_finalize(vt_ctx* c) {
     VT_CHECK(c->ecfg_set, "vt_encoder_configure has not been called");
     free_packed(c);
     const vt_encoder_config& cfg = c->ecfg;
-    Packer P{c};
+    Packer P{c, &c->eparams, &c->epacked, "encoder"};
     const int C0 = cfg.block_out_channels[0];
     VT_TRY(P.conv("conv_in", 3, C0, 3, "", 0, 64, &c->conv_in));
     c->down.resize(cfg.num_blocks);
@@ -795,6 +968,76 @@ int vt_encode(vt_ctx* c, const vt_encode_args* a) {
         VT_CUDA(cudaEventRecord(L.done, L.stream));
         VT_CUDA(cudaStreamWaitEvent(s, L.done, 0));
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- VAE decoder
+int vt_decoder_set_param(vt_ctx* c, const char* name, const float* data, const int64_t* shape, int ndim) {
+    VT_TRY(set_device(c));
+    c->dec_ready = false;
+    return store_param(c->dparams, name, data, shape, ndim);
+}
+
+int vt_decoder_finalize(vt_ctx* c) {
+    VT_TRY(set_device(c));
+    VT_CHECK(c->ecfg_set, "vt_encoder_configure has not been called");
+    free_packed_decoder(c);
+    const vt_encoder_config& cfg = c->ecfg;
+    Packer P{c, &c->dparams, &c->dpacked, "decoder"};
+    const int nb = cfg.num_blocks;
+    const int Cm = cfg.block_out_channels[nb - 1];
+    VT_CHECK(cfg.latent_channels <= 64, "decoder: latent_channels must be at most 64");
+    // the latent is a raw (unbounded) activation: bf16 operand, bf16 weight columns
+    VT_TRY(P.conv_padded("conv_in", cfg.latent_channels, Cm, 3, 64, Cm, &c->dconv_in, /*f16=*/false));
+    VT_TRY(P.resnet("mid_block.resnets.0", Cm, Cm, &c->dmid0));
+    VT_TRY(P.resnet("mid_block.resnets.1", Cm, Cm, &c->dmid1));
+    if (cfg.mid_block_add_attention) {
+        const std::string a = "mid_block.attentions.0";
+        c->dattn.C = Cm;
+        VT_TRY(P.norm(a + ".group_norm", Cm, &c->dattn.gn));
+        VT_TRY(P.linear({a + ".to_q", a + ".to_k"}, Cm, Cm, true, &c->dattn.qk));
+        VT_TRY(P.linear({a + ".to_v"}, Cm, Cm, true, &c->dattn.v));
+        VT_TRY(P.linear({a + ".to_out.0"}, Cm, Cm, true, &c->dattn.out));
+    }
+    c->up.resize(nb);
+    c->upsample.resize(nb);
+    int cin = Cm;
+    for (int b = 0; b < nb; ++b) {
+        const int cout = cfg.block_out_channels[nb - 1 - b];
+        c->up[b].resize(cfg.layers_per_block + 1);
+        for (int l = 0; l <= cfg.layers_per_block; ++l)
+            VT_TRY(P.resnet("up_blocks." + std::to_string(b) + ".resnets." + std::to_string(l), l == 0 ? cin : cout,
+                            cout, &c->up[b][l]));
+        if (b < nb - 1)
+            VT_TRY(P.conv("up_blocks." + std::to_string(b) + ".upsamplers.0.conv", cout, cout, 3, "", 0, 0,
+                          &c->upsample[b], /*f16=*/false));
+        cin = cout;
+    }
+    const int C0 = cfg.block_out_channels[0];
+    VT_TRY(P.norm("conv_norm_out", C0, &c->dnorm_out));
+    VT_TRY(P.conv_padded("conv_out", C0, 3, 3, C0, 32, &c->dconv_out, /*f16=*/true));
+    VT_CUDA(cudaDeviceSynchronize());
+    c->dec_ready = true;
+    return 0;
+}
+
+int vt_decode(vt_ctx* c, const vt_decode_args* a) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr, "null arguments");
+    VT_CHECK(c->dec_ready, "decoder parameters not finalised (vt_decoder_finalize)");
+    VT_CHECK(a->latent != nullptr && a->image != nullptr, "null latent / image pointer");
+    VT_CHECK(a->batch > 0 && a->lat_h > 0 && a->lat_w > 0, "batch and latent size must be positive");
+    VT_CHECK(a->lat_h % 2 == 0 && a->lat_w % 2 == 0, "latent height and width must be even");
+    VT_CHECK(a->precision == VT_PREC_BF16 || a->precision == VT_PREC_FP32, "unknown precision");
+    cudaStream_t s = static_cast<cudaStream_t>(a->stream);
+    int mb = a->micro_batch;
+    if (mb <= 0) {
+        const int up = 1 << (c->ecfg.num_blocks - 1);
+        const double per_img = 4.0 * a->lat_h * up * a->lat_w * up * c->ecfg.block_out_channels[0];
+        mb = static_cast<int>(std::max(1.0, std::min(32.0, (2.2e9) / per_img)));
+    }
+    for (int i0 = 0; i0 < a->batch; i0 += mb)
+        VT_TRY(run_decoder_microbatch(c, c->lanes[0], a, i0, std::min(mb, a->batch - i0), s));
     return 0;
 }
 

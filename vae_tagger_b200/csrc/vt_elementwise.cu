@@ -513,6 +513,89 @@ int launch_nhwc_to_nchw(const void* in, int in_fmt, float* out, int N, int C, lo
     return 0;
 }
 
+// ---- VAE decoder I/O
+// latent NCHW fp32 [N][LC][HW] -> NHWC [N][HW][CP] (CP = LC padded to 64: one K chunk of the implicit GEMM),
+// with DiffusersVAEWrapper.decode's un-shift / un-scale (diffusers_vae_loader.py:88-93) fused in.
+template <int OFMT>
+__global__ void __launch_bounds__(256) latent_to_nhwc_kernel(const float* __restrict__ z, void* __restrict__ outv,
+                                                             int LC, int CP, long long HW, float shift,
+                                                             float inv_scale, long long total) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int c = static_cast<int>(i % CP);
+        const long long np = i / CP;
+        const long long n = np / HW, p = np - n * HW;
+        const float v = c < LC ? (z[(n * LC + c) * HW + p] - shift) * inv_scale : 0.f;
+        if constexpr (OFMT == FMT_BF16) static_cast<bf16*>(outv)[i] = __float2bfloat16(v);
+        else static_cast<float*>(outv)[i] = v;
+    }
+}
+int launch_latent_to_nhwc(const float* z, void* out, int out_fmt, int N, int LC, int CP, long long HW, float shift,
+                          float inv_scale, cudaStream_t s, Profiler* prof) {
+    const long long total = 1LL * N * HW * CP;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    profiler_begin(prof, KC_LATENT, s, 0, 4.0 * N * LC * HW + (out_fmt == FMT_F32 ? 4.0 : 2.0) * total);
+    if (out_fmt == FMT_F32) latent_to_nhwc_kernel<FMT_F32><<<grid, 256, 0, s>>>(z, out, LC, CP, HW, shift, inv_scale, total);
+    else latent_to_nhwc_kernel<FMT_BF16><<<grid, 256, 0, s>>>(z, out, LC, CP, HW, shift, inv_scale, total);
+    profiler_end(prof, KC_LATENT, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Upsample2D's F.interpolate(scale_factor=2, mode="nearest") on NHWC: out[n][2y+a][2x+b][:] = in[n][y][x][:].
+// One thread moves 16 bytes of a source pixel to its four destinations: reads once, writes coalesced.
+__global__ void __launch_bounds__(256) upsample2x_nhwc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                              int H, int W, int vec_per_px, long long total) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int v = static_cast<int>(i % vec_per_px);
+        const long long px = i / vec_per_px;
+        const int x = static_cast<int>(px % W);
+        const long long ny = px / W;
+        const int y = static_cast<int>(ny % H);
+        const long long n = ny / H;
+        const uint4 d = in[i];
+        const long long o = ((n * 2 * H + 2 * y) * 2 * W + 2 * x) * vec_per_px + v;
+        const long long row = 2LL * W * vec_per_px;
+        out[o] = d;
+        out[o + vec_per_px] = d;
+        out[o + row] = d;
+        out[o + row + vec_per_px] = d;
+    }
+}
+int launch_upsample2x_nhwc(const void* in, void* out, int elem_bytes, int N, int H, int W, int C, cudaStream_t s,
+                           Profiler* prof) {
+    VT_CHECK((1LL * C * elem_bytes) % 16 == 0, "upsample: a pixel must be a multiple of 16 bytes");
+    const int vpp = C * elem_bytes / 16;
+    const long long total = 1LL * N * H * W * vpp;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 32));
+    profiler_begin(prof, KC_MISC, s, 0, 5.0 * 16.0 * total);
+    upsample2x_nhwc_kernel<<<grid, 256, 0, s>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), H, W, vpp, total);
+    profiler_end(prof, KC_MISC, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// conv_out result fp32 NHWC [N][HW][CP] (CP = out_channels padded to 32) -> image NCHW fp32 [N][OC][HW]
+__global__ void __launch_bounds__(256) nhwc_to_image_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                            int OC, int CP, long long HW, long long total) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const long long p = i % HW;
+        const long long nc = i / HW;
+        const int c = static_cast<int>(nc % OC);
+        const long long n = nc / OC;
+        out[i] = in[(n * HW + p) * CP + c];
+    }
+}
+int launch_nhwc_to_image(const float* in, float* out, int N, int OC, int CP, long long HW, cudaStream_t s,
+                         Profiler* prof) {
+    const long long total = 1LL * N * OC * HW;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 32));
+    profiler_begin(prof, KC_LATENT, s, 0, 4.0 * N * HW * (CP + OC));
+    nhwc_to_image_kernel<<<grid, 256, 0, s>>>(in, out, OC, CP, HW, total);
+    profiler_end(prof, KC_LATENT, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // Split-K combine: out[r][c] = bias[c] + sum_s part[s][r][c]  (part fp32, out 16-bit; 4 columns / thread)
 template <int OFMT>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits,

@@ -169,6 +169,12 @@ int launch_moments_to_latent(const float* moments_nhwc, float* latent, float* me
                              float scale, float shift, int apply_scale, int apply_shift, cudaStream_t, Profiler*);
 int launch_nchw_to_nhwc(const float* in, void* out, int out_fmt, int N, int C, long long HW, cudaStream_t);
 int launch_nhwc_to_nchw(const void* in, int in_fmt, float* out, int N, int C, long long HW, cudaStream_t);
+// VAE decoder I/O
+int launch_latent_to_nhwc(const float* z, void* out, int out_fmt, int N, int LC, int CP, long long HW, float shift,
+                          float inv_scale, cudaStream_t, Profiler*);
+int launch_upsample2x_nhwc(const void* in, void* out, int elem_bytes, int N, int H, int W, int C, cudaStream_t,
+                           Profiler*);
+int launch_nhwc_to_image(const float* in, float* out, int N, int OC, int CP, long long HW, cudaStream_t, Profiler*);
 int launch_cast_f32_16(const float* in, void* out, int out_fmt, long long n, cudaStream_t);
 int launch_splitk_reduce(const float* part, int splits, long long split_stride, const float* bias, void* out,
                          int out_fmt, long long rows, int cols, long long ld_out, cudaStream_t, Profiler*);

@@ -83,7 +83,7 @@ class DiffusersVAEWrapper(torch.nn.Module):
         self.vae = vae_model
 
     def forward(self, x):
-        # (:72-76) needs the VAE decoder, which is outside the encode+tag path
+        # (:72-76) reconstruction through the native decoder
         posterior = self.vae.encode(x).latent_dist
         z = posterior.sample()
         reconstruction = self.vae.decode(z).sample
@@ -102,6 +102,9 @@ class DiffusersVAEWrapper(torch.nn.Module):
         return latent
 
     def decode(self, z):
+        if isinstance(self.vae, AutoencoderKL):
+            # un-shift / un-scale (:89-93) fused into the decoder's first kernel
+            return self.vae.decode(z, apply_scale_shift=True).sample
         if hasattr(self.vae.config, "shift_factor"):
             z = z - self.vae.config.shift_factor
         if hasattr(self.vae.config, "scaling_factor"):
