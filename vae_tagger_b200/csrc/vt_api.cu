@@ -933,7 +933,10 @@ int vt_encoder_finalize(vt_ctx* c) {
     return 0;
 }
 
-int vt_encode(vt_ctx* c, const vt_encode_args* a) {
+// host_src != nullptr: a->images is a device staging buffer that is filled from host_src (pinned) one
+// micro-batch at a time, on the stream that runs the micro-batch -- with two lanes the upload of micro-batch
+// k+1 overlaps the kernels of micro-batch k (vt_infer_host).
+static int encode_impl(vt_ctx* c, const vt_encode_args* a, const char* host_src) {
     VT_TRY(set_device(c));
     VT_CHECK(a != nullptr, "null arguments");
     VT_CHECK(c->enc_ready, "encoder parameters not finalised (vt_encoder_finalize)");
@@ -951,9 +954,19 @@ int vt_encode(vt_ctx* c, const vt_encode_args* a) {
         const double per_img = 1.0 * a->height * a->width * c->ecfg.block_out_channels[0] * 2;
         mb = static_cast<int>(std::max(1.0, std::min(32.0, (1.1e9) / per_img)));
     }
+    const size_t img_stride = static_cast<size_t>(a->height) * a->width * 3 * (a->in_fmt == VT_IN_U8_NHWC ? 1 : 4);
+    auto upload = [&](int i0, int n, cudaStream_t st) -> int {
+        if (host_src)
+            VT_CUDA(cudaMemcpyAsync(const_cast<char*>(static_cast<const char*>(a->images)) + img_stride * i0,
+                                    host_src + img_stride * i0, img_stride * n, cudaMemcpyHostToDevice, st));
+        return 0;
+    };
     if (mb >= a->batch || a->single_lane) {
-        for (int i0 = 0; i0 < a->batch; i0 += mb)
-            VT_TRY(run_encoder_microbatch(c, c->lanes[0], a, i0, std::min(mb, a->batch - i0), s));
+        for (int i0 = 0; i0 < a->batch; i0 += mb) {
+            const int n = std::min(mb, a->batch - i0);
+            VT_TRY(upload(i0, n, s));
+            VT_TRY(run_encoder_microbatch(c, c->lanes[0], a, i0, n, s));
+        }
         return 0;
     }
     // several micro-batches: alternate between the two lanes
@@ -962,7 +975,9 @@ int vt_encode(vt_ctx* c, const vt_encode_args* a) {
     int k = 0;
     for (int i0 = 0; i0 < a->batch; i0 += mb, ++k) {
         vt_ctx::Lane& L = c->lanes[k & 1];
-        VT_TRY(run_encoder_microbatch(c, L, a, i0, std::min(mb, a->batch - i0), L.stream));
+        const int n = std::min(mb, a->batch - i0);
+        VT_TRY(upload(i0, n, L.stream));
+        VT_TRY(run_encoder_microbatch(c, L, a, i0, n, L.stream));
     }
     for (auto& L : c->lanes) {
         VT_CUDA(cudaEventRecord(L.done, L.stream));
@@ -970,6 +985,8 @@ int vt_encode(vt_ctx* c, const vt_encode_args* a) {
     }
     return 0;
 }
+
+int vt_encode(vt_ctx* c, const vt_encode_args* a) { return encode_impl(c, a, nullptr); }
 
 // ------------------------------------------------------------------------------------- VAE decoder
 int vt_decoder_set_param(vt_ctx* c, const char* name, const float* data, const int64_t* shape, int ndim) {
@@ -1307,13 +1324,11 @@ int vt_infer_host(vt_ctx* c, const vt_infer_host_args* a) {
     float* d_conf = reinterpret_cast<float*>(d + img_b + lat_b);
     int64_t* d_idx = reinterpret_cast<int64_t*>(d + img_b + lat_b + conf_b);
     int32_t* d_cnt = reinterpret_cast<int32_t*>(d + img_b + lat_b + conf_b + idx_b);
-    VT_CUDA(cudaMemcpyAsync(d_img, a->images_host,
-                            static_cast<size_t>(B) * H * W * 3 * (a->in_fmt == VT_IN_U8_NHWC ? 1 : 4),
-                            cudaMemcpyHostToDevice, s));
+    // the upload is issued per micro-batch inside encode_impl, on the stream that consumes it
     vt_encode_args e{};
     e.images = d_img; e.in_fmt = a->in_fmt; e.batch = B; e.height = H; e.width = W; e.precision = a->precision;
     e.sample = 0; e.apply_scale_shift = 1; e.latent = d_lat; e.micro_batch = a->micro_batch; e.stream = a->stream;
-    VT_TRY(vt_encode(c, &e));
+    VT_TRY(encode_impl(c, &e, static_cast<const char*>(a->images_host)));
     vt_tag_args t{};
     t.latent = d_lat; t.batch = B; t.lat_h = lh; t.lat_w = lw; t.threshold = a->threshold;
     t.conf_sorted = d_conf; t.idx_sorted = d_idx; t.count = d_cnt; t.stream = a->stream;

@@ -268,8 +268,10 @@ __global__ void __launch_bounds__(64) head_adaptive_pool_kernel(const float* __r
     if (threadIdx.x == 0) out[1LL * n * C * OH * OW + idx] = (r[0] + r[1]) / static_cast<float>(wh * ww);
 }
 
-// ---- Linear: y[b][o] = bias[o] + sum_i W[o][i] x[b][i].  One warp per output neuron; the
-// neuron's weight row is read once (coalesced) and reused for every batch row.
+// ---- Linear: y[b][o] = bias[o] + sum_i W[o][i] x[b][i].  One warp per output neuron; the neuron's
+// weight row is read ONCE (coalesced, two loads in flight per lane) and applied to BT batch rows held in
+// registers; the activations (B x I floats) are L1/L2 resident and shared by every warp.
+template <int BT>
 __global__ void __launch_bounds__(256) head_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                           const float* __restrict__ bias, float* __restrict__ y,
                                                           int B, int I, int O) {
@@ -277,18 +279,38 @@ __global__ void __launch_bounds__(256) head_linear_kernel(const float* __restric
     const int lane = threadIdx.x & 31;
     if (o >= O) return;
     const float* wr = w + 1LL * o * I;
-    for (int b0 = 0; b0 < B; b0 += 8) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int i = lane; i < I; i += 32) {
-            const float wv = wr[i];
+    for (int b0 = 0; b0 < B; b0 += BT) {
+        float acc[BT];
 #pragma unroll
-            for (int bb = 0; bb < 8; ++bb)
-                if (b0 + bb < B) acc[bb] = fmaf(wv, x[1LL * (b0 + bb) * I + i], acc[bb]);
+        for (int bb = 0; bb < BT; ++bb) acc[bb] = 0.f;
+        const int nb = min(BT, B - b0);
+        if (nb == BT) {
+            int i = lane;
+            for (; i + 32 < I; i += 64) {
+                const float w0 = wr[i], w1 = wr[i + 32];
+#pragma unroll
+                for (int bb = 0; bb < BT; ++bb) {
+                    const float* xr = x + 1LL * (b0 + bb) * I + i;
+                    acc[bb] = fmaf(w1, xr[32], fmaf(w0, xr[0], acc[bb]));
+                }
+            }
+            for (; i < I; i += 32) {
+                const float w0 = wr[i];
+#pragma unroll
+                for (int bb = 0; bb < BT; ++bb) acc[bb] = fmaf(w0, x[1LL * (b0 + bb) * I + i], acc[bb]);
+            }
+        } else {
+            for (int i = lane; i < I; i += 32) {
+                const float w0 = wr[i];
+#pragma unroll
+                for (int bb = 0; bb < BT; ++bb)
+                    if (bb < nb) acc[bb] = fmaf(w0, x[1LL * (b0 + bb) * I + i], acc[bb]);
+            }
         }
 #pragma unroll
-        for (int bb = 0; bb < 8; ++bb) {
+        for (int bb = 0; bb < BT; ++bb) {
             const float t = h_warp_sum(acc[bb]);
-            if (lane == 0 && b0 + bb < B) y[1LL * (b0 + bb) * O + o] = t + (bias ? bias[o] : 0.f);
+            if (lane == 0 && bb < nb) y[1LL * (b0 + bb) * O + o] = t + (bias ? bias[o] : 0.f);
         }
     }
 }
@@ -451,7 +473,8 @@ int launch_head_adaptive_pool(const float* x, float* out, int N, int C, int H, i
 int launch_head_linear(const float* x, const float* w, const float* b, float* y, int B, int I, int O,
                        cudaStream_t s, Profiler* prof) {
     profiler_begin(prof, KC_HEAD, s, 2.0 * B * I * O, 4.0 * I * O);
-    head_linear_kernel<<<(O + 7) / 8, 256, 0, s>>>(x, w, b, y, B, I, O);
+    if (B >= 16) head_linear_kernel<32><<<(O + 7) / 8, 256, 0, s>>>(x, w, b, y, B, I, O);
+    else head_linear_kernel<8><<<(O + 7) / 8, 256, 0, s>>>(x, w, b, y, B, I, O);
     profiler_end(prof, KC_HEAD, s);
     VT_CUDA(cudaGetLastError());
     return 0;

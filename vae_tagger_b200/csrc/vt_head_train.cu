@@ -46,56 +46,76 @@ __device__ __forceinline__ double block_sum256_d(double v, double* red) {
     return t;
 }
 
+// Sums NV per-thread values over the 256 threads of a CTA with ONE shared-memory exchange (warp shuffles
+// first): thread k < NV returns the total of value k, other threads return 0.  sm: 8*NV floats.
+template <int NV>
+__device__ __forceinline__ float block_sum_many(float (&v)[NV], float* sm) {
+    static_assert(NV <= 256, "one result per thread");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = h_warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sm[warp * NV + k] = v[k];
+    }
+    __syncthreads();
+    float t = 0.f;
+    if (threadIdx.x < NV) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sm[w * NV + threadIdx.x];
+    }
+    return t;
+}
+
 // ------------------------------------------------------------------------------ feature_compress
-// conv3x3 C->Co (+bias) -> z[N][Co][HW], and per-CTA partial (sum, sumsq) of z per channel for the
-// batch statistics.  grid (ceil(HW/256), N); part[(n*gridDim.x+blockIdx.x)][Co][2] doubles.
+// conv3x3 C->CO (+bias) -> z[N][CO][HW], and per-CTA partial (sum, sumsq) of z per channel for the
+// batch statistics.  grid (ceil(HW/256), N); part[(n*gridDim.x+blockIdx.x)][CO][2] doubles.
+template <int CO>
 __global__ void __launch_bounds__(256) head_conv_train_kernel(const float* __restrict__ x,   // [N][C][H][W]
-                                                              const float* __restrict__ cw,  // [Co][C][3][3]
+                                                              const float* __restrict__ cw,  // [CO][C][3][3]
                                                               const float* __restrict__ cb, float* __restrict__ z,
-                                                              double* __restrict__ part, int C, int Co, int H,
-                                                              int W) {
-    extern __shared__ float sw[];  // Co*C*9 weights, then 8 floats scratch
-    float* red = sw + Co * C * 9;
+                                                              double* __restrict__ part, int C, int H, int W) {
+    extern __shared__ float sw[];  // CO*C*9 weights, then 8*2*CO floats scratch
+    float* red = sw + CO * C * 9;
     const int n = blockIdx.y, HW = H * W;
-    for (int i = threadIdx.x; i < Co * C * 9; i += 256) sw[i] = cw[i];
+    for (int i = threadIdx.x; i < CO * C * 9; i += 256) sw[i] = cw[i];
     __syncthreads();
     const int p = blockIdx.x * 256 + threadIdx.x;
     const bool live = p < HW;
-    float v[16];
+    float v[CO];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) v[o] = (o < Co) ? cb[o] : 0.f;
+    for (int o = 0; o < CO; ++o) v[o] = cb[o];
     if (live) {
         const int py = p / W, px = p - py * W;
         for (int c = 0; c < C; ++c) {
             const float* xp = x + (1LL * n * C + c) * HW;
+#pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
                 const int yy = py + ky - 1;
                 if (yy < 0 || yy >= H) continue;
+#pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const int xx = px + kx - 1;
                     if (xx < 0 || xx >= W) continue;
                     const float xv = xp[yy * W + xx];
 #pragma unroll
-                    for (int o = 0; o < 16; ++o)
-                        if (o < Co) v[o] = fmaf(sw[((o * C + c) * 3 + ky) * 3 + kx], xv, v[o]);
+                    for (int o = 0; o < CO; ++o) v[o] = fmaf(sw[((o * C + c) * 3 + ky) * 3 + kx], xv, v[o]);
                 }
             }
         }
     }
-    double* dst = part + (1LL * n * gridDim.x + blockIdx.x) * Co * 2;
+    float st[2 * CO];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) {
-        if (o < Co) {
-            const float t = live ? v[o] : 0.f;
-            if (live) z[(1LL * n * Co + o) * HW + p] = t;
-            const float s1 = block_sum256(t, red);
-            const float s2 = block_sum256(t * t, red);
-            if (threadIdx.x == 0) {
-                dst[2 * o] = static_cast<double>(s1);
-                dst[2 * o + 1] = static_cast<double>(s2);
-            }
-        }
+    for (int o = 0; o < CO; ++o) {
+        const float t = live ? v[o] : 0.f;
+        if (live) z[(1LL * n * CO + o) * HW + p] = t;
+        st[2 * o] = t;
+        st[2 * o + 1] = t * t;
     }
+    const float tot = block_sum_many<2 * CO>(st, red);
+    if (threadIdx.x < 2 * CO)
+        part[(1LL * n * gridDim.x + blockIdx.x) * CO * 2 + threadIdx.x] = static_cast<double>(tot);
 }
 
 // batch statistics from the partials (one CTA): stat[0..Co) = mean, stat[Co..2Co) = 1/sqrt(var+eps);
@@ -164,7 +184,7 @@ __global__ void __launch_bounds__(256) head_bn_bwd_stats_kernel(const float* __r
                                                                 const float* __restrict__ dpooled,  // [N][Co][64]
                                                                 float* __restrict__ dz, double* __restrict__ part,
                                                                 int Co, int H, int W) {
-    __shared__ float red[8];
+    __shared__ float red[8 * 32];
     const int n = blockIdx.y, HW = H * W;
     const int p = blockIdx.x * 256 + threadIdx.x;
     const bool live = p < HW;
@@ -188,25 +208,26 @@ __global__ void __launch_bounds__(256) head_bn_bwd_stats_kernel(const float* __r
             }
         }
     }
-    double* dst = part + (1LL * n * gridDim.x + blockIdx.x) * Co * 2;
-    for (int o = 0; o < Co; ++o) {
-        float dt = 0.f, xhat = 0.f;
-        if (live) {
+    float st[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) st[i] = 0.f;
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        if (o < Co && live) {
             const long long idx = (1LL * n * Co + o) * HW + p;
-            xhat = (z[idx] - stat[o]) * stat[Co + o];
+            const float xhat = (z[idx] - stat[o]) * stat[Co + o];
             const float t = xhat * bn_w[o] + bn_b[o];
             float dr = 0.f;
             for (int i = 0; i < ncell; ++i) dr += dpooled[(1LL * n * Co + o) * 64 + cells[i]] * inv_area[i];
-            dt = t > 0.f ? dr : 0.f;
+            const float dt = t > 0.f ? dr : 0.f;
             dz[idx] = dt;
-        }
-        const float s1 = block_sum256(dt, red);
-        const float s2 = block_sum256(dt * xhat, red);
-        if (threadIdx.x == 0) {
-            dst[2 * o] = static_cast<double>(s1);
-            dst[2 * o + 1] = static_cast<double>(s2);
+            st[2 * o] = dt;
+            st[2 * o + 1] = dt * xhat;
         }
     }
+    const float tot = block_sum_many<32>(st, red);
+    if (threadIdx.x < 2 * Co)
+        part[(1LL * n * gridDim.x + blockIdx.x) * Co * 2 + threadIdx.x] = static_cast<double>(tot);
 }
 
 // sums the partials (one CTA): sums[0..Co) = sum dt, sums[Co..2Co) = sum dt*xhat; BatchNorm affine grads
@@ -254,7 +275,7 @@ __global__ void __launch_bounds__(256) head_conv_bwd_w_kernel(const float* __res
                                                               const float* __restrict__ dz,  // [N][CO][H][W]
                                                               float* __restrict__ part_w, float* __restrict__ part_b,
                                                               int C, int H, int W) {
-    __shared__ float red[8];
+    __shared__ float red[8 * CO * 9];
     const int c = blockIdx.x, band = blockIdx.y, bands = gridDim.y, n = blockIdx.z;
     const int HW = H * W;
     const int r0 = (band * H) / bands, r1 = ((band + 1) * H) / bands;
@@ -287,20 +308,14 @@ __global__ void __launch_bounds__(256) head_conv_bwd_w_kernel(const float* __res
         }
     }
     const long long pidx = 1LL * n * bands + band;
-#pragma unroll
-    for (int o = 0; o < CO; ++o) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const float t = block_sum256(acc[o * 9 + k], red);
-            if (threadIdx.x == 0) part_w[(pidx * CO + o) * C * 9 + c * 9 + k] = t;
-        }
+    const float tw = block_sum_many<CO * 9>(acc, red);
+    if (threadIdx.x < CO * 9) {  // value index = o*9 + k
+        const int o = threadIdx.x / 9, k = threadIdx.x % 9;
+        part_w[(pidx * CO + o) * C * 9 + c * 9 + k] = tw;
     }
     if (c == 0) {
-#pragma unroll
-        for (int o = 0; o < CO; ++o) {
-            const float t = block_sum256(bacc[o], red);
-            if (threadIdx.x == 0) part_b[pidx * CO + o] = t;
-        }
+        const float tb = block_sum_many<CO>(bacc, red);
+        if (threadIdx.x < CO) part_b[pidx * CO + threadIdx.x] = tb;
     }
 }
 
@@ -383,7 +398,7 @@ __global__ void __launch_bounds__(256) head_sa_bwd_gate_sum_kernel(const float* 
                                                                    float* __restrict__ part_g, int C, int H, int W) {
     __shared__ float ws[98];
     __shared__ float g[64];
-    __shared__ float red[8];
+    __shared__ float red[8 * 32];
     const int n = blockIdx.y, HW = H * W;
     if (threadIdx.x < 98) ws[threadIdx.x] = w7[threadIdx.x];
     if (threadIdx.x < C) g[threadIdx.x] = cgate[1LL * n * C + threadIdx.x];
@@ -427,13 +442,8 @@ __global__ void __launch_bounds__(256) head_sa_bwd_gate_sum_kernel(const float* 
             }
         }
     }
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        if (c < C) {
-            const float t = block_sum256(acc[c], red);
-            if (threadIdx.x == 0) part_g[(1LL * n * gridDim.x + blockIdx.x) * C + c] = t;
-        }
-    }
+    const float tot = block_sum_many<32>(acc, red);
+    if (threadIdx.x < C) part_g[(1LL * n * gridDim.x + blockIdx.x) * C + threadIdx.x] = tot;
 }
 
 // Step C: 7x7 weight gradient dW7[ci][k] = sum_{n,p} dpre[p]*map2[ci][p+k].  grid (bands, N, 2):
@@ -441,7 +451,7 @@ __global__ void __launch_bounds__(256) head_sa_bwd_gate_sum_kernel(const float* 
 __global__ void __launch_bounds__(256) head_sa_bwd_w7_kernel(const float* __restrict__ map2,
                                                              const float* __restrict__ dpre,
                                                              float* __restrict__ part_w7, int H, int W) {
-    __shared__ float red[8];
+    __shared__ float red[8 * 49];
     const int n = blockIdx.y, ci = blockIdx.z, HW = H * W;
     const float* mp = map2 + (1LL * n * 2 + ci) * HW;
     const float* dp = dpre + 1LL * n * HW;
@@ -462,11 +472,8 @@ __global__ void __launch_bounds__(256) head_sa_bwd_w7_kernel(const float* __rest
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < 49; ++i) {
-        const float t = block_sum256(acc[i], red);
-        if (threadIdx.x == 0) part_w7[(1LL * n * gridDim.x + blockIdx.x) * 98 + ci * 49 + i] = t;
-    }
+    const float tot = block_sum_many<49>(acc, red);
+    if (threadIdx.x < 49) part_w7[(1LL * n * gridDim.x + blockIdx.x) * 98 + ci * 49 + threadIdx.x] = tot;
 }
 
 // Step D (one CTA): channel-gate MLP backward, summed over the batch in image order.
@@ -521,10 +528,11 @@ __global__ void __launch_bounds__(256) head_sa_bwd_mlp_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------ self-attention
-// MultiHeadSelfAttention in train mode (modules.py:66-91).  One CTA per image, one thread per token.
+// MultiHeadSelfAttention in train mode (modules.py:66-91), one thread per token.
 // prm = q.w q.b k.w k.b v.w v.b out.w out.b norm.w norm.b, contiguous (the flat parameter order).
-// BWD = false: feat[n][e*64+t].  BWD = true: recomputes the forward, then dpooled[n][e][t] and the
-// per-image parameter gradients partial[n][4(E*E+E)+2E] in the same order as prm.
+// The per-head part (scores, softmax, dropout, P.V and their backward) runs as one CTA per (head, image):
+// 8x the parallelism of a CTA per image; the cheap per-image parts (out_proj, projections / LayerNorm
+// backward, parameter-gradient sums) are separate one-CTA-per-image kernels.
 template <class F>
 __device__ __forceinline__ void token_reduce(float (*sm)[65], int t, int count, float* dst, F contrib) {
     for (int base = 0; base < count; base += 64) {
@@ -539,24 +547,10 @@ __device__ __forceinline__ void token_reduce(float (*sm)[65], int t, int count, 
     }
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(64) head_mhsa_train_kernel(const float* __restrict__ pooled,  // [N][E][64]
-                                                             const float* __restrict__ prm,
-                                                             float* __restrict__ feat,
-                                                             const float* __restrict__ dfeat,  // [N][E*64]
-                                                             float* __restrict__ dpooled,
-                                                             float* __restrict__ partial, int E, int heads,
-                                                             float drop_p, unsigned long long seed) {
-    __shared__ float sk[64][17];
-    __shared__ float sv[64][17];
-    __shared__ float sq[64][17];
-    __shared__ float sd[64][17];
-    __shared__ float sm[64][65];
-    const int n = blockIdx.x, t = threadIdx.x;
-    const int EE = E * E;
-    const float *wq = prm, *bq = wq + EE, *wk = bq + E, *bk = wk + EE, *wv = bk + E, *bv = wv + EE, *wo = bv + E,
-                *bo = wo + EE, *ln_w = bo + E, *ln_b = ln_w + E;
-    float xin[16], xhat[16], xn[16], q[16];
+// LayerNorm of token t of image n (eps 1e-5): raw input, normalised value, affine output
+__device__ __forceinline__ float mhsa_token_ln(const float* __restrict__ pooled, const float* __restrict__ ln_w,
+                                               const float* __restrict__ ln_b, int n, int E, int t, float* xin,
+                                               float* xhat, float* xn) {
     for (int e = 0; e < E; ++e) xin[e] = pooled[(1LL * n * E + e) * 64 + t];
     float mean = 0.f;
     for (int e = 0; e < E; ++e) mean += xin[e];
@@ -569,120 +563,178 @@ __global__ void __launch_bounds__(64) head_mhsa_train_kernel(const float* __rest
         xhat[e] = (xin[e] - mean) * rstd;
         xn[e] = xhat[e] * ln_w[e] + ln_b[e];
     }
-    for (int o = 0; o < E; ++o) {
+    return rstd;
+}
+
+// One head of one image: grid (heads, N), one thread per query token.
+//   BWD = false: ao[n][t][h*hd+d] = dropout(softmax(q k^T / sqrt(hd))) v           (attention output)
+//   BWD = true : recomputes the forward of this head, then dqkv[n][{q,k,v}][t][h*hd+d]
+template <bool BWD>
+__global__ void __launch_bounds__(64) head_mhsa_head_kernel(const float* __restrict__ pooled,  // [N][E][64]
+                                                            const float* __restrict__ prm,
+                                                            float* __restrict__ ao,            // [N][64][E]
+                                                            const float* __restrict__ dfeat,   // [N][E*64]
+                                                            float* __restrict__ dqkv,          // [N][3][64][E]
+                                                            int E, int heads, float drop_p,
+                                                            unsigned long long seed) {
+    __shared__ float sk[64][17];
+    __shared__ float sv[64][17];
+    __shared__ float sq[64][17];
+    __shared__ float sd[64][17];
+    __shared__ float sm[64][65];
+    const int h = blockIdx.x, n = blockIdx.y, t = threadIdx.x;
+    const int EE = E * E, hd = E / heads, c0 = h * hd;
+    const float *wq = prm, *bq = wq + EE, *wk = bq + E, *bk = wk + EE, *wv = bk + E, *bv = wv + EE, *wo = bv + E,
+                *ln_w = wo + EE + E, *ln_b = ln_w + E;
+    float xin[16], xhat[16], xn[16], q[16];
+    mhsa_token_ln(pooled, ln_w, ln_b, n, E, t, xin, xhat, xn);
+    for (int d = 0; d < hd; ++d) {
+        const int o = c0 + d;
         float a = bq[o], b = bk[o], c = bv[o];
         for (int e = 0; e < E; ++e) {
             a = fmaf(wq[o * E + e], xn[e], a);
             b = fmaf(wk[o * E + e], xn[e], b);
             c = fmaf(wv[o * E + e], xn[e], c);
         }
-        q[o] = a;
-        sk[t][o] = b;
-        sv[t][o] = c;
-        sq[t][o] = a;
+        q[d] = a;
+        sk[t][d] = b;
+        sv[t][d] = c;
+        sq[t][d] = a;
     }
-    float dout[16], dao[16], dq[16], dkk[16], dvv[16];
+    float dao[16];
     if (BWD) {
-        for (int o = 0; o < E; ++o) dout[o] = dfeat[1LL * n * E * 64 + o * 64 + t];
-        for (int e = 0; e < E; ++e) {
+        for (int d = 0; d < hd; ++d) {
             float a = 0.f;
-            for (int o = 0; o < E; ++o) a = fmaf(dout[o], wo[o * E + e], a);
-            dao[e] = a;
-            sd[t][e] = a;
+            for (int o = 0; o < E; ++o) a = fmaf(dfeat[1LL * n * E * 64 + o * 64 + t], wo[o * E + c0 + d], a);
+            dao[d] = a;
+            sd[t][d] = a;
         }
     }
     __syncthreads();
-    const int hd = E / heads;
     const float scale = 1.0f / sqrtf(static_cast<float>(hd));
     const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-    float ao[16];
-    for (int h = 0; h < heads; ++h) {
-        float P[64];
-        float m = -CUDART_INF_F;
+    float P[64];
+    float m = -CUDART_INF_F;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            float s = 0.f;
-            for (int d = 0; d < hd; ++d) s = fmaf(q[h * hd + d], sk[j][h * hd + d], s);
-            s *= scale;
-            P[j] = s;
-            m = fmaxf(m, s);
-        }
-        float sum = 0.f;
+    for (int j = 0; j < 64; ++j) {
+        float sc = 0.f;
+        for (int d = 0; d < hd; ++d) sc = fmaf(q[d], sk[j][d], sc);
+        sc *= scale;
+        P[j] = sc;
+        m = fmaxf(m, sc);
+    }
+    float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            P[j] = expf(P[j] - m);
-            sum += P[j];
-        }
-        const float inv = 1.0f / sum;
-        unsigned long long keep = ~0ULL;
-        if (drop_p > 0.f) {
-            keep = 0ULL;
-            const unsigned long long base = ((1ULL * n * heads + h) * 64 + t) * 64;
+    for (int j = 0; j < 64; ++j) {
+        P[j] = expf(P[j] - m);
+        sum += P[j];
+    }
+    const float inv = 1.0f / sum;
+    unsigned long long keep = ~0ULL;
+    if (drop_p > 0.f) {
+        keep = 0ULL;
+        const unsigned long long base = ((1ULL * n * heads + h) * 64 + t) * 64;
 #pragma unroll
-            for (int j = 0; j < 64; ++j)
-                if (h_dropout_keep(seed, 0u, base + j, drop_p)) keep |= 1ULL << j;
-        }
+        for (int j = 0; j < 64; ++j)
+            if (h_dropout_keep(seed, 0u, base + j, drop_p)) keep |= 1ULL << j;
+    }
 #pragma unroll
-        for (int j = 0; j < 64; ++j) P[j] *= inv;
+    for (int j = 0; j < 64; ++j) P[j] *= inv;
+    if (!BWD) {
         for (int d = 0; d < hd; ++d) {
             float o = 0.f;
 #pragma unroll
             for (int j = 0; j < 64; ++j)
-                if ((keep >> j) & 1ULL) o = fmaf(P[j] * inv_keep, sv[j][h * hd + d], o);
-            ao[h * hd + d] = o;
-        }
-        if (BWD) {
-            // dP_j = keep_j * inv_keep * sum_d dao[d]*v[j][d];  dS_j = P_j (dP_j - sum_j' dP_j' P_j') * scale
-            float rowdot = 0.f;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                if ((keep >> j) & 1ULL) {
-                    float dp = 0.f;
-                    for (int d = 0; d < hd; ++d) dp = fmaf(dao[h * hd + d], sv[j][h * hd + d], dp);
-                    rowdot = fmaf(dp * inv_keep, P[j], rowdot);
-                }
-            }
-            for (int d = 0; d < hd; ++d) dq[h * hd + d] = 0.f;
-            __syncthreads();  // previous head's column sums are done with sm
-#pragma unroll
-            for (int j = 0; j < 64; ++j) sm[t][j] = ((keep >> j) & 1ULL) ? P[j] * inv_keep : 0.f;
-            __syncthreads();
-            for (int d = 0; d < hd; ++d) {  // dv of token t as a key: column t of the dropped weights
-                float a = 0.f;
-                for (int r = 0; r < 64; ++r) a = fmaf(sm[r][t], sd[r][h * hd + d], a);
-                dvv[h * hd + d] = a;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                float dp = 0.f;
-                if ((keep >> j) & 1ULL) {
-                    for (int d = 0; d < hd; ++d) dp = fmaf(dao[h * hd + d], sv[j][h * hd + d], dp);
-                    dp *= inv_keep;
-                }
-                const float ds = P[j] * (dp - rowdot) * scale;
-                sm[t][j] = ds;
-                for (int d = 0; d < hd; ++d) dq[h * hd + d] = fmaf(ds, sk[j][h * hd + d], dq[h * hd + d]);
-            }
-            __syncthreads();
-            for (int d = 0; d < hd; ++d) {  // dk of token t as a key
-                float a = 0.f;
-                for (int r = 0; r < 64; ++r) a = fmaf(sm[r][t], sq[r][h * hd + d], a);
-                dkk[h * hd + d] = a;
-            }
-        }
-    }
-    if (!BWD) {
-        for (int o = 0; o < E; ++o) {
-            float a = bo[o];
-            for (int e = 0; e < E; ++e) a = fmaf(wo[o * E + e], ao[e], a);
-            feat[1LL * n * E * 64 + o * 64 + t] = a + xin[o];
+                if ((keep >> j) & 1ULL) o = fmaf(P[j] * inv_keep, sv[j][d], o);
+            ao[(1LL * n * 64 + t) * E + c0 + d] = o;
         }
         return;
     }
-    // gradient of the LayerNorm output: dxn = Wq^T dq + Wk^T dk + Wv^T dv
-    float dxn[16];
+    // dP_j = keep_j * inv_keep * sum_d dao[d]*v[j][d];  dS_j = P_j (dP_j - sum_j' dP_j' P_j') * scale
+    float rowdot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        if ((keep >> j) & 1ULL) {
+            float dp = 0.f;
+            for (int d = 0; d < hd; ++d) dp = fmaf(dao[d], sv[j][d], dp);
+            rowdot = fmaf(dp * inv_keep, P[j], rowdot);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 64; ++j) sm[t][j] = ((keep >> j) & 1ULL) ? P[j] * inv_keep : 0.f;
+    __syncthreads();
+    float* dq_out = dqkv + ((1LL * n * 3 + 0) * 64 + t) * E + c0;
+    float* dk_out = dqkv + ((1LL * n * 3 + 1) * 64 + t) * E + c0;
+    float* dv_out = dqkv + ((1LL * n * 3 + 2) * 64 + t) * E + c0;
+    for (int d = 0; d < hd; ++d) {  // dv of token t as a key: column t of the dropped weights
+        float a = 0.f;
+        for (int r = 0; r < 64; ++r) a = fmaf(sm[r][t], sd[r][d], a);
+        dv_out[d] = a;
+    }
+    __syncthreads();
+    float dq[16];
+    for (int d = 0; d < hd; ++d) dq[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        float dp = 0.f;
+        if ((keep >> j) & 1ULL) {
+            for (int d = 0; d < hd; ++d) dp = fmaf(dao[d], sv[j][d], dp);
+            dp *= inv_keep;
+        }
+        const float ds = P[j] * (dp - rowdot) * scale;
+        sm[t][j] = ds;
+        for (int d = 0; d < hd; ++d) dq[d] = fmaf(ds, sk[j][d], dq[d]);
+    }
+    __syncthreads();
+    for (int d = 0; d < hd; ++d) {  // dk of token t as a key
+        float a = 0.f;
+        for (int r = 0; r < 64; ++r) a = fmaf(sm[r][t], sq[r][d], a);
+        dk_out[d] = a;
+        dq_out[d] = dq[d];
+    }
+}
+
+// out_proj + residual (modules.py:86): feat[n][o*64+t] = bo[o] + sum_e Wo[o][e] ao[n][t][e] + x[n][o][t]
+__global__ void __launch_bounds__(64) head_mhsa_out_kernel(const float* __restrict__ pooled,
+                                                           const float* __restrict__ prm,
+                                                           const float* __restrict__ ao, float* __restrict__ feat,
+                                                           int E) {
+    const int n = blockIdx.x, t = threadIdx.x;
+    const int EE = E * E;
+    const float *wo = prm + 3 * (EE + E), *bo = wo + EE;
+    float a[16];
+    for (int e = 0; e < E; ++e) a[e] = ao[(1LL * n * 64 + t) * E + e];
+    for (int o = 0; o < E; ++o) {
+        float r = bo[o];
+        for (int e = 0; e < E; ++e) r = fmaf(wo[o * E + e], a[e], r);
+        feat[1LL * n * E * 64 + o * 64 + t] = r + pooled[(1LL * n * E + o) * 64 + t];
+    }
+}
+
+// The per-image tail of the backward: projections, LayerNorm and residual -> dpooled[n][e][t], and the
+// parameter gradients of this image (sums over its 64 tokens) -> partial[n][4(E*E+E)+2E], prm order.
+__global__ void __launch_bounds__(64) head_mhsa_bwd_tail_kernel(const float* __restrict__ pooled,
+                                                                const float* __restrict__ prm,
+                                                                const float* __restrict__ ao,
+                                                                const float* __restrict__ dqkv,
+                                                                const float* __restrict__ dfeat,
+                                                                float* __restrict__ dpooled,
+                                                                float* __restrict__ partial, int E) {
+    __shared__ float sm[64][65];
+    const int n = blockIdx.x, t = threadIdx.x;
+    const int EE = E * E;
+    const float *wq = prm, *wk = wq + EE + E, *wv = wk + EE + E, *wo = wv + EE + E, *ln_w = wo + EE + E,
+                *ln_b = ln_w + E;
+    float xin[16], xhat[16], xn[16], dq[16], dkk[16], dvv[16], dout[16], a_o[16], dxn[16];
+    const float rstd = mhsa_token_ln(pooled, ln_w, ln_b, n, E, t, xin, xhat, xn);
     for (int e = 0; e < E; ++e) {
+        dq[e] = dqkv[((1LL * n * 3 + 0) * 64 + t) * E + e];
+        dkk[e] = dqkv[((1LL * n * 3 + 1) * 64 + t) * E + e];
+        dvv[e] = dqkv[((1LL * n * 3 + 2) * 64 + t) * E + e];
+        dout[e] = dfeat[1LL * n * E * 64 + e * 64 + t];
+        a_o[e] = ao[(1LL * n * 64 + t) * E + e];
+    }
+    for (int e = 0; e < E; ++e) {  // gradient of the LayerNorm output: Wq^T dq + Wk^T dk + Wv^T dv
         float a = 0.f;
         for (int o = 0; o < E; ++o) {
             a = fmaf(dq[o], wq[o * E + e], a);
@@ -701,7 +753,6 @@ __global__ void __launch_bounds__(64) head_mhsa_train_kernel(const float* __rest
     m2 /= static_cast<float>(E);
     for (int e = 0; e < E; ++e)
         dpooled[(1LL * n * E + e) * 64 + t] = rstd * (dxn[e] * ln_w[e] - m1 - xhat[e] * m2) + dout[e];
-    // parameter gradients of this image: sums over the 64 tokens
     float* dst = partial + 1LL * n * (4 * (EE + E) + 2 * E);
     token_reduce(sm, t, EE, dst, [&](int i) { return dq[i / E] * xn[i % E]; });
     token_reduce(sm, t, E, dst + EE, [&](int i) { return dq[i]; });
@@ -709,7 +760,7 @@ __global__ void __launch_bounds__(64) head_mhsa_train_kernel(const float* __rest
     token_reduce(sm, t, E, dst + 2 * EE + E, [&](int i) { return dkk[i]; });
     token_reduce(sm, t, EE, dst + 2 * EE + 2 * E, [&](int i) { return dvv[i / E] * xn[i % E]; });
     token_reduce(sm, t, E, dst + 3 * EE + 2 * E, [&](int i) { return dvv[i]; });
-    token_reduce(sm, t, EE, dst + 3 * EE + 3 * E, [&](int i) { return dout[i / E] * ao[i % E]; });
+    token_reduce(sm, t, EE, dst + 3 * EE + 3 * E, [&](int i) { return dout[i / E] * a_o[i % E]; });
     token_reduce(sm, t, E, dst + 4 * EE + 3 * E, [&](int i) { return dout[i]; });
     token_reduce(sm, t, E, dst + 4 * EE + 4 * E, [&](int i) { return dxn[i] * xhat[i]; });
     token_reduce(sm, t, E, dst + 4 * EE + 5 * E, [&](int i) { return dxn[i]; });
@@ -816,35 +867,47 @@ __global__ void __launch_bounds__(256) head_linear_bwd_w_kernel(const float* __r
     if (i == 0) g_b[o] += bacc;
 }
 
-// Linear backward, input: dx[b][i] = sum_o dy[b][o]*W[o][i].  grid (ceil(I/256), ceil(B/8))
-__global__ void __launch_bounds__(256) head_linear_bwd_x_kernel(const float* __restrict__ dy,
+// Linear backward, input: dx[b][i] = sum_o dy[b][o]*W[o][i], split over o: grid (ceil(I/128), ceil(O/64)).
+// A CTA owns 64 rows of W (each read once, coalesced) and 128 columns; a thread keeps one column's sums
+// for 32 batch rows in registers.  part[ks][b][i]; the slices are added in a fixed order afterwards.
+__global__ void __launch_bounds__(128) head_linear_bwd_x_kernel(const float* __restrict__ dy,
                                                                 const float* __restrict__ w,
-                                                                float* __restrict__ dx, int B, int I, int O) {
-    __shared__ float sdy[8][256];
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const int b0 = blockIdx.y * 8;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int o0 = 0; o0 < O; o0 += 256) {
+                                                                float* __restrict__ part, int B, int I, int O) {
+    __shared__ float sdy[32][65];
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const int ks = blockIdx.y, o0 = ks * 64;
+    const int cnt = min(64, O - o0);
+    for (int b0 = 0; b0 < B; b0 += 32) {
         __syncthreads();
+        for (int e = threadIdx.x; e < 32 * 64; e += 128) {
+            const int bb = e >> 6, oo = e & 63;
+            sdy[bb][oo] = (b0 + bb < B && oo < cnt) ? dy[1LL * (b0 + bb) * O + o0 + oo] : 0.f;
+        }
+        __syncthreads();
+        float acc[32];
 #pragma unroll
-        for (int bb = 0; bb < 8; ++bb)
-            sdy[bb][threadIdx.x] =
-                (b0 + bb < B && o0 + threadIdx.x < O) ? dy[1LL * (b0 + bb) * O + o0 + threadIdx.x] : 0.f;
-        __syncthreads();
+        for (int bb = 0; bb < 32; ++bb) acc[bb] = 0.f;
         if (i < I) {
-            const int cnt = min(256, O - o0);
             for (int oo = 0; oo < cnt; ++oo) {
                 const float wv = w[1LL * (o0 + oo) * I + i];
 #pragma unroll
-                for (int bb = 0; bb < 8; ++bb) acc[bb] = fmaf(sdy[bb][oo], wv, acc[bb]);
+                for (int bb = 0; bb < 32; ++bb) acc[bb] = fmaf(sdy[bb][oo], wv, acc[bb]);
             }
+#pragma unroll
+            for (int bb = 0; bb < 32; ++bb)
+                if (b0 + bb < B) part[(1LL * ks * B + b0 + bb) * I + i] = acc[bb];
         }
     }
-    if (i < I) {
-#pragma unroll
-        for (int bb = 0; bb < 8; ++bb)
-            if (b0 + bb < B) dx[1LL * (b0 + bb) * I + i] = acc[bb];
-    }
+}
+
+// dst[i] = sum over parts of part[p][i]
+__global__ void __launch_bounds__(256) head_partial_assign_kernel(const float* __restrict__ part, int nparts,
+                                                                  long long P, float* __restrict__ dst) {
+    const long long i = blockIdx.x * 256LL + threadIdx.x;
+    if (i >= P) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part[1LL * p * P + i];
+    dst[i] = s;
 }
 
 __global__ void head_scale_add_kernel(const float* __restrict__ src, float scale, float* __restrict__ dst) {
@@ -986,10 +1049,11 @@ struct Arena {
 struct TrainWs {
     size_t pool, cgate, map2, x2, sgate, z, dz, dy, dpre, bnstat, bnsums, pooled, dpooled, feat, dfeat;
     size_t a[4], hbuf[4], stat[4], dtbuf, g0, g1, logits, dlogits, loss;
-    size_t part_bn, part_mhsa, part_cw, part_cb, part_g, part_w7, part_norm;
+    size_t part_dx, ao, dqkv, part_bn, part_mhsa, part_cw, part_cb, part_g, part_w7, part_norm;
     size_t total;
 };
-constexpr int kBands = 8;
+constexpr int kBands = 8;      // row bands / pixel chunks per image of the spatial-attention reductions
+constexpr int kConvBands = 2;  // row bands per image of the conv weight gradient (72 sums per CTA: keep CTAs fat)
 
 TrainWs plan(const vt_head_config& h, int B, int H, int W) {
     TrainWs w{};
@@ -1002,10 +1066,11 @@ TrainWs plan(const vt_head_config& h, int B, int H, int W) {
         w.x2 = A.take(B * C * HW); w.sgate = A.take(B * HW); w.z = A.take(B * E * HW); w.dz = A.take(B * E * HW);
         w.dy = A.take(B * C * HW); w.dpre = A.take(B * HW); w.bnstat = A.take(2 * E); w.bnsums = A.take(2 * E);
         w.pooled = A.take(B * E * 64); w.dpooled = A.take(B * E * 64);
+        w.ao = A.take(B * 64 * E); w.dqkv = A.take(B * 3 * 64 * E);
         w.part_bn = A.take(2 * (B * nblk * E * 2));  // doubles
         w.part_mhsa = A.take(B * (4 * (E * E + E) + 2 * E));
-        w.part_cw = A.take(static_cast<size_t>(B) * kBands * E * C * 9);
-        w.part_cb = A.take(static_cast<size_t>(B) * kBands * E);
+        w.part_cw = A.take(static_cast<size_t>(B) * kConvBands * E * C * 9);
+        w.part_cb = A.take(static_cast<size_t>(B) * kConvBands * E);
         w.part_g = A.take(static_cast<size_t>(B) * kBands * C);
         w.part_w7 = A.take(static_cast<size_t>(B) * kBands * 98);
     }
@@ -1018,6 +1083,12 @@ TrainWs plan(const vt_head_config& h, int B, int H, int W) {
         w.stat[i] = A.take(2 * static_cast<size_t>(B));
     }
     w.dtbuf = A.take(B * maxd); w.g0 = A.take(B * maxd); w.g1 = A.take(B * maxd);
+    {
+        size_t need = 0;
+        for (int i = 0; i < m.n; ++i)
+            need = std::max(need, static_cast<size_t>((m.dims[i + 1] + 63) / 64) * B * m.dims[i]);
+        w.part_dx = A.take(need);
+    }
     w.logits = A.take(B * T); w.dlogits = A.take(B * T); w.loss = A.take(1);
     w.total = A.off;
     return w;
@@ -1029,7 +1100,7 @@ size_t head_train_workspace_floats(const vt_head_config& h, int B, int H, int W)
 template <int CO>
 static void launch_conv_bwd(const float* x, const float* dz, const float* cw, float* part_w, float* part_b,
                             float* dy, int N, int H, int W, cudaStream_t s) {
-    head_conv_bwd_w_kernel<CO><<<dim3(2 * CO, kBands, N), 256, 0, s>>>(x, dz, part_w, part_b, 2 * CO, H, W);
+    head_conv_bwd_w_kernel<CO><<<dim3(2 * CO, kConvBands, N), 256, 0, s>>>(x, dz, part_w, part_b, 2 * CO, H, W);
     if (dy) head_conv_bwd_x_kernel<CO><<<dim3((H * W + 255) / 256, N), 256, 0, s>>>(dz, cw, dy, H, W);
 }
 
@@ -1072,9 +1143,17 @@ int head_train_step(const vt_head_config& h, const vt_head_train_args& a, float*
                                                  pf));
             y = ws + w.x2;
         }
-        const size_t smem = (static_cast<size_t>(E) * C * 9 + 8) * sizeof(float);
-        VT_KC(head_conv_train_kernel<<<dim3(nblk, B), 256, smem, s>>>(
-            y, P("feature_compress.0.weight"), P("feature_compress.0.bias"), ws + w.z, part_bn, C, E, H, W));
+        const size_t smem = (static_cast<size_t>(E) * C * 9 + 8 * 2 * E) * sizeof(float);
+        const float* cw = P("feature_compress.0.weight");
+        const float* cb = P("feature_compress.0.bias");
+        profiler_begin(pf, KC_HEAD, s, 2.0 * B * HW * E * C * 9, 4.0 * B * (C + E) * HW);
+        switch (E) {
+            case 4: head_conv_train_kernel<4><<<dim3(nblk, B), 256, smem, s>>>(y, cw, cb, ws + w.z, part_bn, C, H, W); break;
+            case 8: head_conv_train_kernel<8><<<dim3(nblk, B), 256, smem, s>>>(y, cw, cb, ws + w.z, part_bn, C, H, W); break;
+            case 12: head_conv_train_kernel<12><<<dim3(nblk, B), 256, smem, s>>>(y, cw, cb, ws + w.z, part_bn, C, H, W); break;
+            default: head_conv_train_kernel<16><<<dim3(nblk, B), 256, smem, s>>>(y, cw, cb, ws + w.z, part_bn, C, H, W); break;
+        }
+        profiler_end(pf, KC_HEAD, s);
         VT_KC(head_bn_finalize_kernel<<<1, 256, 0, s>>>(part_bn, B * nblk, E, static_cast<double>(B) * HW, 1e-5f,
                                                          a.bn_momentum, ws + w.bnstat, a.bn_running_mean,
                                                          a.bn_running_var,
@@ -1085,9 +1164,11 @@ int head_train_step(const vt_head_config& h, const vt_head_train_args& a, float*
                                                                      H, W));
         if (h.use_self_attention) {
             VT_CHECK(h.attention_heads >= 1 && E % h.attention_heads == 0, "embed_dim not divisible by heads");
-            VT_KC(head_mhsa_train_kernel<false><<<B, 64, 0, s>>>(
-                ws + w.pooled, P("self_attention_post.q_proj.weight"), ws + w.feat, nullptr, nullptr, nullptr, E,
+            VT_KC(head_mhsa_head_kernel<false><<<dim3(h.attention_heads, B), 64, 0, s>>>(
+                ws + w.pooled, P("self_attention_post.q_proj.weight"), ws + w.ao, nullptr, nullptr, E,
                 h.attention_heads, drop ? a.attention_dropout : 0.f, a.seed));
+            VT_KC(head_mhsa_out_kernel<<<B, 64, 0, s>>>(ws + w.pooled, P("self_attention_post.q_proj.weight"),
+                                                         ws + w.ao, ws + w.feat, E));
         }
     } else {
         VT_TRY(launch_head_adaptive_pool(a.latent, ws + w.feat, B, C, H, W, 4, 4, s, pf));
@@ -1132,8 +1213,10 @@ int head_train_step(const vt_head_config& h, const vt_head_train_args& a, float*
             gcur, xin, G(lin + ".weight"), G(lin + ".bias"), B, I, O));
         if (i == 0 && !att) break;  // the pooled latent needs no gradient
         float* gx = i == 0 ? ws + w.dfeat : gbuf[i & 1];
-        VT_KC(head_linear_bwd_x_kernel<<<dim3((I + 255) / 256, (B + 7) / 8), 256, 0, s>>>(gcur, P(lin + ".weight"),
-                                                                                           gx, B, I, O));
+        VT_KC(head_linear_bwd_x_kernel<<<dim3((I + 127) / 128, (O + 63) / 64), 128, 0, s>>>(
+            gcur, P(lin + ".weight"), ws + w.part_dx, B, I, O));
+        VT_KC(head_partial_assign_kernel<<<static_cast<int>((1LL * B * I + 255) / 256), 256, 0, s>>>(
+            ws + w.part_dx, (O + 63) / 64, 1LL * B * I, gx));
         gcur = gx;
         if (i > 0) {
             const std::string ln = "classifier." + std::to_string(4 * (i - 1) + 1);
@@ -1151,9 +1234,12 @@ int head_train_step(const vt_head_config& h, const vt_head_train_args& a, float*
         const float* dpooled = ws + w.dfeat;
         if (h.use_self_attention) {
             const int PM = 4 * (E * E + E) + 2 * E;
-            VT_KC(head_mhsa_train_kernel<true><<<B, 64, 0, s>>>(
-                ws + w.pooled, P("self_attention_post.q_proj.weight"), nullptr, ws + w.dfeat, ws + w.dpooled,
-                ws + w.part_mhsa, E, h.attention_heads, drop ? a.attention_dropout : 0.f, a.seed));
+            VT_KC(head_mhsa_head_kernel<true><<<dim3(h.attention_heads, B), 64, 0, s>>>(
+                ws + w.pooled, P("self_attention_post.q_proj.weight"), ws + w.ao, ws + w.dfeat, ws + w.dqkv, E,
+                h.attention_heads, drop ? a.attention_dropout : 0.f, a.seed));
+            VT_KC(head_mhsa_bwd_tail_kernel<<<B, 64, 0, s>>>(ws + w.pooled, P("self_attention_post.q_proj.weight"),
+                                                              ws + w.ao, ws + w.dqkv, ws + w.dfeat, ws + w.dpooled,
+                                                              ws + w.part_mhsa, E));
             VT_KC(head_partial_reduce_kernel<<<(PM + 255) / 256, 256, 0, s>>>(
                 ws + w.part_mhsa, B, PM, G("self_attention_post.q_proj.weight")));
             dpooled = ws + w.dpooled;
@@ -1181,8 +1267,8 @@ int head_train_step(const vt_head_config& h, const vt_head_train_args& a, float*
         }
         profiler_end(pf, KC_HEAD, s);
         VT_KC(head_partial_reduce_kernel<<<(E * C * 9 + 255) / 256, 256, 0, s>>>(
-            ws + w.part_cw, B * kBands, E * C * 9, G("feature_compress.0.weight")));
-        VT_KC(head_partial_reduce_kernel<<<1, 256, 0, s>>>(ws + w.part_cb, B * kBands, E,
+            ws + w.part_cw, B * kConvBands, E * C * 9, G("feature_compress.0.weight")));
+        VT_KC(head_partial_reduce_kernel<<<1, 256, 0, s>>>(ws + w.part_cb, B * kConvBands, E,
                                                             G("feature_compress.0.bias")));
         // -------------------------------------------------------------- spatial attention
         if (h.use_spatial_attention) {
