@@ -223,9 +223,10 @@ def run_ours(args):
     x = host.to(dev, non_blocking=True)
     ctx = _native.get_context(dev)
 
-    def step():
-        lat = wrap.encode(x)
-        return dec.tag(lat, threshold=0.5)
+    from vae_tagger_b200.infer_full import encode_and_tag
+
+    def step():  # the call infer_full.py makes per batch: encode + get_confidence + threshold count
+        return encode_and_tag(wrap, dec, x, threshold=0.5)
 
     def barrier():
         if world > 1:

@@ -158,6 +158,25 @@ typedef struct vt_infer_host_args {
 } vt_infer_host_args;
 int vt_infer_host(vt_ctx* ctx, const vt_infer_host_args* args);
 
+/* Same pipeline on DEVICE buffers (images already in HBM, results left in HBM): encode (mode, scale/shift) and,
+ * per internal micro-batch and right behind its encoder, the tag head -- what infer_full.py:95-118 does per
+ * image, for a batch, without host round trips.  No host synchronisation. */
+typedef struct vt_infer_args {
+    const void* images; /* device, format in_fmt */
+    int in_fmt;
+    int batch, height, width;
+    int precision;
+    float threshold;
+    float* conf_sorted;  /* out, device [B,T] */
+    int64_t* idx_sorted; /* out, device [B,T] */
+    int32_t* count;      /* out, device [B] */
+    float* latent;       /* out, device [B,LC,H/8,W/8] (required: the head reads it) */
+    int micro_batch;
+    int single_lane;     /* 1: micro-batches back to back on the caller's stream (per-kernel timing runs) */
+    void* stream;
+} vt_infer_args;
+int vt_infer(vt_ctx* ctx, const vt_infer_args* args);
+
 /* ---------------------------------------------------------------- focal loss (training step)
  * Replaces FocalLoss.forward (improved_losses.py:47-56) and its autograd backward:
  * loss_sum += sum(alpha*(1-pt)^gamma*bce); grad = grad_scale * d(sum)/d(logits). */

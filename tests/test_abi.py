@@ -43,8 +43,8 @@ def test_struct_sizes_match_header_layout():
     import subprocess
 
     got = [C.sizeof(t) for t in (_native.EncoderConfig, _native.HeadConfig, _native.EncodeArgs, _native.TagArgs,
-                                 _native.InferHostArgs, _native.HeadTrainArgs, _native.ResizeArgs, _native.DecodeArgs)]
-    assert got == [72, 24, 96, 72, 80, 128, 80, 56]
+                                 _native.InferHostArgs, _native.HeadTrainArgs, _native.ResizeArgs, _native.DecodeArgs, _native.InferArgs)]
+    assert got == [72, 24, 96, 72, 80, 128, 80, 56, 80]
     gcc = shutil.which("gcc")
     if gcc:  # compile the header as C and compare sizeof() of every struct
         import tempfile
@@ -52,9 +52,9 @@ def test_struct_sizes_match_header_layout():
         with tempfile.TemporaryDirectory() as d:
             src = os.path.join(d, "sz.c")
             open(src, "w").write(
-                '#include <stdio.h>\n#include "vae_tagger_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu",'
+                '#include <stdio.h>\n#include "vae_tagger_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu",'
                 "sizeof(vt_encoder_config),sizeof(vt_head_config),sizeof(vt_encode_args),sizeof(vt_tag_args),"
-                "sizeof(vt_infer_host_args),sizeof(vt_head_train_args),sizeof(vt_resize_args),sizeof(vt_decode_args));return 0;}\n")
+                "sizeof(vt_infer_host_args),sizeof(vt_head_train_args),sizeof(vt_resize_args),sizeof(vt_decode_args),sizeof(vt_infer_args));return 0;}\n")
             exe = os.path.join(d, "sz")
             subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
             out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()

@@ -142,3 +142,38 @@ def test_train_decoder_step_single_rank():
     with torch.enable_grad():
         graph = dec(lat)
     assert rel(native.cpu(), graph.detach().cpu()) < 2e-5
+
+
+def test_fused_infer_call_equals_encode_then_tag(golden):
+    """vt_infer (head per micro-batch behind its encoder) == DiffusersVAEWrapper.encode followed by decoder.tag,
+    on float and uint8 inputs, with and without internal micro-batching."""
+    from vae_tagger_b200.infer_full import encode_and_tag
+
+    torch.manual_seed(0)
+    wrap = L.DiffusersVAEWrapper(L.load_diffusers_vae_from_config(L.get_diffusers_vae_config())).cuda().eval()
+    sd = dict(golden["attention_head_base"]); sd.update(golden["attention_head"]["att_T11_64x64"]["state_dict"])
+    dec = M.create_attention_decoder(16, 8, 16, 11, attention_config={})
+    dec.load_state_dict(sd)
+    dec = dec.cuda().eval()
+    x = synthetic_images(5, 64, 128).cuda()
+    xu = ((x.permute(0, 2, 3, 1) * 0.5 + 0.5) * 255).round().clamp(0, 255).to(torch.uint8).contiguous()
+    wrap.vae.precision = "fp32"
+    for inp in (x, xu):
+        for mb in (0, 2):
+            wrap.vae.micro_batch = mb
+            lat = wrap.encode(inp)
+            want = dec.tag(lat, threshold=0.5)
+            got = encode_and_tag(wrap, dec, inp, threshold=0.5)
+            assert rel(got["latent"], lat) <= 1e-6
+            assert (got["conf"] - want["conf"]).abs().max().item() <= 1e-6
+            assert torch.equal(got["count"], want["count"])
+            gap = (want["conf"][:, :-1] - want["conf"][:, 1:]).abs().min().item()
+            if gap > 1e-5:
+                assert torch.equal(got["idx"], want["idx"])
+    wrap.vae.micro_batch = 0
+    wrap.vae.precision = "bf16"
+    host = x.cpu().pin_memory()
+    ctx = wrap.vae._sync_native(x.device)
+    out = ctx.infer_host(host, threshold=0.5)
+    want = encode_and_tag(wrap, dec, x, threshold=0.5)
+    assert (out["conf"] - want["conf"].cpu()).abs().max().item() <= 2e-2      # two bf16 runs (DESIGN.md 3)

@@ -75,6 +75,15 @@ class InferHostArgs(C.Structure):
     ]
 
 
+class InferArgs(C.Structure):
+    _fields_ = [
+        ("images", C.c_void_p), ("in_fmt", C.c_int), ("batch", C.c_int), ("height", C.c_int), ("width", C.c_int),
+        ("precision", C.c_int), ("threshold", C.c_float), ("conf_sorted", C.c_void_p), ("idx_sorted", C.c_void_p),
+        ("count", C.c_void_p), ("latent", C.c_void_p), ("micro_batch", C.c_int), ("single_lane", C.c_int),
+        ("stream", C.c_void_p),
+    ]
+
+
 class HeadTrainArgs(C.Structure):
     _fields_ = [
         ("latent", C.c_void_p), ("targets", C.c_void_p), ("batch", C.c_int), ("lat_h", C.c_int), ("lat_w", C.c_int),
@@ -114,6 +123,7 @@ SYMBOLS = {
     "vt_head_finalize": (C.c_int, [_P]),
     "vt_tag": (C.c_int, [_P, C.POINTER(TagArgs)]),
     "vt_infer_host": (C.c_int, [_P, C.POINTER(InferHostArgs)]),
+    "vt_infer": (C.c_int, [_P, C.POINTER(InferArgs)]),
     "vt_focal_loss": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, _P, _P, _P]),
     "vt_head_param_count": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "vt_head_param_layout": (C.c_int, [_P, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_int64),
@@ -363,6 +373,37 @@ class Context:
         a.stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             _check(self.lib.vt_tag(self.h, C.byref(a)))
+        return out
+
+    def infer(self, images: torch.Tensor, threshold=0.5, precision=PREC_BF16, micro_batch=0, single_lane=False):
+        """encode (mode, scale/shift) + tag on DEVICE tensors in one call: the head of each internal micro-batch
+        runs right behind its encoder.  images: float [B,3,H,W] or uint8 [B,H,W,3] on this device.  Returns a
+        dict of device tensors: conf, idx (sorted descending), count (conf >= threshold), latent."""
+        if images.dtype == torch.uint8:
+            fmt = IN_U8_NHWC
+            x = images.to(self.device).contiguous()
+            B, H, W = x.shape[0], x.shape[1], x.shape[2]
+        else:
+            fmt = IN_F32_NCHW
+            x = _f32c(images, self.device)
+            B, H, W = x.shape[0], x.shape[2], x.shape[3]
+        T = self.num_classes
+        down = 1 << (self.num_blocks - 1)
+        out = {
+            "conf": torch.empty(B, T, device=self.device, dtype=torch.float32),
+            "idx": torch.empty(B, T, device=self.device, dtype=torch.int64),
+            "count": torch.empty(B, device=self.device, dtype=torch.int32),
+            "latent": torch.empty(B, self.latent_channels, H // down, W // down, device=self.device),
+        }
+        a = InferArgs()
+        a.images = x.data_ptr(); a.in_fmt = fmt; a.batch = B; a.height = H; a.width = W
+        a.precision = precision; a.threshold = float(threshold)
+        a.conf_sorted = out["conf"].data_ptr(); a.idx_sorted = out["idx"].data_ptr()
+        a.count = out["count"].data_ptr(); a.latent = out["latent"].data_ptr()
+        a.micro_batch = int(micro_batch); a.single_lane = int(bool(single_lane))
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_infer(self.h, C.byref(a)))
         return out
 
     def infer_host(self, images_host: torch.Tensor, threshold=0.5, precision=PREC_BF16, want_latent=False,

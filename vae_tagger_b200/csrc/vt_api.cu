@@ -90,6 +90,7 @@ struct vt_ctx {
         DevBuf arena;  // activation workspace
         DevBuf stats;  // GroupNorm (sum, sumsq) slots
         DevBuf mom;    // conv_out moments fp32 NHWC
+        DevBuf hws;    // tag-head workspace when the head runs per micro-batch on this lane (vt_infer_host)
     } lanes[2];
     cudaEvent_t ev_start = nullptr;
 
@@ -854,7 +855,7 @@ int vt_ctx_destroy(vt_ctx* c) {
     free_params(c->dparams);
     free_params(c->hparams);
     for (auto& L : c->lanes) {
-        L.arena.release(); L.stats.release(); L.mom.release();
+        L.arena.release(); L.stats.release(); L.mom.release(); L.hws.release();
         if (L.stream) cudaStreamDestroy(L.stream);
         if (L.done) cudaEventDestroy(L.done);
     }
@@ -936,7 +937,15 @@ int vt_encoder_finalize(vt_ctx* c) {
 // host_src != nullptr: a->images is a device staging buffer that is filled from host_src (pinned) one
 // micro-batch at a time, on the stream that runs the micro-batch -- with two lanes the upload of micro-batch
 // k+1 overlaps the kernels of micro-batch k (vt_infer_host).
-static int encode_impl(vt_ctx* c, const vt_encode_args* a, const char* host_src) {
+struct TagTail {  // the tag head of a micro-batch, run right behind its encoder on the same stream
+    float threshold;
+    float* conf;
+    int64_t* idx;
+    int32_t* cnt;
+};
+static int tag_impl(vt_ctx* c, const vt_tag_args* a, DevBuf& hws);
+
+static int encode_impl(vt_ctx* c, const vt_encode_args* a, const char* host_src, const TagTail* tail = nullptr) {
     VT_TRY(set_device(c));
     VT_CHECK(a != nullptr, "null arguments");
     VT_CHECK(c->enc_ready, "encoder parameters not finalised (vt_encoder_finalize)");
@@ -961,11 +970,24 @@ static int encode_impl(vt_ctx* c, const vt_encode_args* a, const char* host_src)
                                     host_src + img_stride * i0, img_stride * n, cudaMemcpyHostToDevice, st));
         return 0;
     };
+    auto tag_tail = [&](vt_ctx::Lane& L, int i0, int n, cudaStream_t st) -> int {
+        if (!tail) return 0;
+        const int lh = a->height / down, lw = a->width / down, T = c->hcfg.num_classes;
+        vt_tag_args t{};
+        t.latent = a->latent + static_cast<size_t>(i0) * c->ecfg.latent_channels * lh * lw;
+        t.batch = n; t.lat_h = lh; t.lat_w = lw; t.threshold = tail->threshold;
+        t.conf_sorted = tail->conf + static_cast<size_t>(i0) * T;
+        t.idx_sorted = tail->idx + static_cast<size_t>(i0) * T;
+        t.count = tail->cnt + i0;
+        t.stream = st;
+        return tag_impl(c, &t, L.hws);
+    };
     if (mb >= a->batch || a->single_lane) {
         for (int i0 = 0; i0 < a->batch; i0 += mb) {
             const int n = std::min(mb, a->batch - i0);
             VT_TRY(upload(i0, n, s));
             VT_TRY(run_encoder_microbatch(c, c->lanes[0], a, i0, n, s));
+            VT_TRY(tag_tail(c->lanes[0], i0, n, s));
         }
         return 0;
     }
@@ -978,6 +1000,7 @@ static int encode_impl(vt_ctx* c, const vt_encode_args* a, const char* host_src)
         const int n = std::min(mb, a->batch - i0);
         VT_TRY(upload(i0, n, L.stream));
         VT_TRY(run_encoder_microbatch(c, L, a, i0, n, L.stream));
+        VT_TRY(tag_tail(L, i0, n, L.stream));
     }
     for (auto& L : c->lanes) {
         VT_CUDA(cudaEventRecord(L.done, L.stream));
@@ -1130,7 +1153,13 @@ int vt_head_finalize(vt_ctx* c) {
     return 0;
 }
 
+static int tag_impl(vt_ctx* c, const vt_tag_args* a, DevBuf& hws);
 int vt_tag(vt_ctx* c, const vt_tag_args* a) {
+    VT_CHECK(c != nullptr, "null context");
+    return tag_impl(c, a, c->hws);
+}
+
+static int tag_impl(vt_ctx* c, const vt_tag_args* a, DevBuf& hws) {
     VT_TRY(set_device(c));
     VT_CHECK(a != nullptr, "null arguments");
     VT_CHECK(c->head_ready, "head parameters not finalised (vt_head_finalize)");
@@ -1148,8 +1177,8 @@ int vt_tag(vt_ctx* c, const vt_tag_args* a) {
     const size_t o_pooled = take(static_cast<size_t>(B) * E * 64), o_feat = take(static_cast<size_t>(B) * 1024);
     const size_t o_a = take(static_cast<size_t>(B) * 1024), o_b = take(static_cast<size_t>(B) * 1024);
     const size_t o_logits = take(static_cast<size_t>(B) * T);
-    VT_TRY(c->hws.ensure(off * sizeof(float)));
-    float* ws = static_cast<float*>(c->hws.p);
+    VT_TRY(hws.ensure(off * sizeof(float)));
+    float* ws = static_cast<float*>(hws.p);
     float* logits = a->logits ? a->logits : ws + o_logits;
 
     if (h.kind == VT_HEAD_ATTENTION) {
@@ -1328,11 +1357,10 @@ int vt_infer_host(vt_ctx* c, const vt_infer_host_args* a) {
     vt_encode_args e{};
     e.images = d_img; e.in_fmt = a->in_fmt; e.batch = B; e.height = H; e.width = W; e.precision = a->precision;
     e.sample = 0; e.apply_scale_shift = 1; e.latent = d_lat; e.micro_batch = a->micro_batch; e.stream = a->stream;
-    VT_TRY(encode_impl(c, &e, static_cast<const char*>(a->images_host)));
-    vt_tag_args t{};
-    t.latent = d_lat; t.batch = B; t.lat_h = lh; t.lat_w = lw; t.threshold = a->threshold;
-    t.conf_sorted = d_conf; t.idx_sorted = d_idx; t.count = d_cnt; t.stream = a->stream;
-    VT_TRY(vt_tag(c, &t));
+    // the head of each micro-batch runs right behind its encoder on the same lane: it hides under the other
+    // lane's contractions instead of trailing the whole batch
+    const TagTail tail{a->threshold, d_conf, d_idx, d_cnt};
+    VT_TRY(encode_impl(c, &e, static_cast<const char*>(a->images_host), &tail));
     if (a->conf_sorted_host)
         VT_CUDA(cudaMemcpyAsync(a->conf_sorted_host, d_conf, static_cast<size_t>(B) * T * 4, cudaMemcpyDeviceToHost, s));
     if (a->idx_sorted_host)
@@ -1344,6 +1372,19 @@ int vt_infer_host(vt_ctx* c, const vt_infer_host_args* a) {
                                 cudaMemcpyDeviceToHost, s));
     VT_CUDA(cudaStreamSynchronize(s));
     return 0;
+}
+
+int vt_infer(vt_ctx* c, const vt_infer_args* a) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr && a->images != nullptr, "null arguments");
+    VT_CHECK(c->enc_ready && c->head_ready, "encoder and head must be finalised");
+    VT_CHECK(a->latent && a->conf_sorted && a->idx_sorted && a->count, "latent, conf_sorted, idx_sorted and count are required");
+    vt_encode_args e{};
+    e.images = a->images; e.in_fmt = a->in_fmt; e.batch = a->batch; e.height = a->height; e.width = a->width;
+    e.precision = a->precision; e.sample = 0; e.apply_scale_shift = 1; e.latent = a->latent;
+    e.micro_batch = a->micro_batch; e.single_lane = a->single_lane; e.stream = a->stream;
+    const TagTail tail{a->threshold, a->conf_sorted, a->idx_sorted, a->count};
+    return encode_impl(c, &e, nullptr, &tail);
 }
 
 int vt_focal_loss(vt_ctx* c, const float* logits, const float* targets, int64_t n, float alpha, float gamma,

@@ -73,10 +73,28 @@ def format_result(conf_row, idx_row, count, tag_names):
 
 
 @torch.no_grad()
+def encode_and_tag(vae_model, decoder, pixel_values, threshold=0.5):
+    """``decoder.get_confidence(vae_model.encode(x))`` + threshold count for a device batch (float [B,3,H,W] or
+    uint8 [B,H,W,3]) as ONE native call (``vt_infer``): the tag head of every internal micro-batch runs right
+    behind its encoder instead of trailing the whole batch.  Returns device tensors conf / idx / count / latent."""
+    from .autoencoder_kl import AutoencoderKL
+
+    vae = getattr(vae_model, "vae", vae_model)
+    if not isinstance(vae, AutoencoderKL) or not decoder._use_native():
+        latent = vae_model.encode(pixel_values)
+        out = decoder.tag(latent, threshold=threshold)
+        out["latent"] = latent
+        return out
+    ctx = vae._sync_native(vae._device_of(pixel_values))
+    decoder._native_ctx(pixel_values.device)
+    return ctx.infer(pixel_values, threshold=threshold, precision=vae._precision(), micro_batch=vae.micro_batch,
+                     single_lane=vae.single_lane)
+
+
+@torch.no_grad()
 def classify_batch(vae_model, decoder, pixel_values, threshold):
     """encode -> get_confidence -> threshold for a [B,3,H,W] device batch; returns host lists."""
-    latent = vae_model.encode(pixel_values)
-    out = decoder.tag(latent, threshold=threshold)
+    out = encode_and_tag(vae_model, decoder, pixel_values, threshold)
     conf = out["conf"].cpu()   # the only device->host traffic of the batch
     idx = out["idx"].cpu()
     cnt = out["count"].cpu()
