@@ -255,6 +255,9 @@ typedef struct vt_resize_args {
     void* stream;
 } vt_resize_args;
 int vt_resize_u8(vt_ctx* ctx, const vt_resize_args* args);
+/* n images in one call (one bucket batch: different sources, one destination shape each); items[i].stream is
+ * ignored, everything is enqueued on `stream` in order */
+int vt_resize_u8_batch(vt_ctx* ctx, const vt_resize_args* items, int n, void* stream);
 /* SmartResize's centre crop box for a src_w x src_h image and a dst_w x dst_h bucket (modules.py:149-172);
  * host-only helper, box4 = (left, top, right, bottom) */
 int vt_smart_crop_box(int src_w, int src_h, int dst_w, int dst_h, int32_t* box4);

@@ -10,8 +10,10 @@ The arithmetic itself lives in a third-party dependency that is not vendored in 
 ``src/libImaging/Resample.c``: ``precompute_coeffs`` (double-precision filter taps, normalised per output
 pixel), ``normalize_coeffs_8bpc`` (taps rounded to fixed point with 22 fractional bits),
 ``ImagingResampleHorizontal_8bpc`` then ``ImagingResampleVertical_8bpc`` (int32 accumulation started at
-2^21, arithmetic shift by 22, clip to [0,255]; the intermediate image is uint8), and the rule of
-``ImagingResampleInner`` that a pass is skipped when that dimension does not change.
+2^21, arithmetic shift by 22, clip to [0,255]; the intermediate image is uint8), the rule of
+``ImagingResampleInner`` that a pass is skipped when that dimension does not change, and the rule of
+``PIL/Image.py`` ``Image.resize`` (12.2) that an image more than 100 times taller than wide which shrinks
+vertically gets its vertical pass first.
 
 **Pinned**: ``tests/test_oracle_golden.py::test_resample_matches_pillow`` checks these functions bit for bit
 against Pillow itself (``Image.crop(...).resize(...)``) on seeded random images, in this container and
@@ -90,6 +92,13 @@ def _pass(img: np.ndarray, out_size: int, kind: int, axis: int) -> np.ndarray:
 def resize_u8(img: np.ndarray, out_w: int, out_h: int, kind: int = LANCZOS) -> np.ndarray:
     """``PIL.Image.fromarray(img).resize((out_w, out_h), kind)`` for an [h, w, c] uint8 array."""
     h, w = img.shape[:2]
+    if h > w * 100 and out_h < h:
+        # PIL/Image.py (Pillow 12.2) Image.resize: a tall thin image that shrinks vertically is resized in two
+        # calls, vertical pass first
+        img = _pass(img, out_h, kind, 0)
+        if w != out_w:
+            img = _pass(img, out_w, kind, 1)
+        return np.ascontiguousarray(img)
     if w != out_w:
         img = _pass(img, out_w, kind, 1)
     if h != out_h:

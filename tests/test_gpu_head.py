@@ -95,3 +95,26 @@ def test_focal_loss_native(ctx, golden):
         n = f["logits"].numel()
         assert abs(loss.item() / n - want["loss"].item()) < 1e-6 * max(1.0, abs(want["loss"].item()))
         assert rel(grad.cpu(), want["grad"]) < 1e-5
+
+
+def test_head_extremes(ctx, golden):
+    """Largest supported tag vocabulary (16 384: the sort's shared-memory limit), batch 1 and a batch that is
+    not a multiple of the linear kernel's 32-row pass; out-of-range vocabularies are refused."""
+    from vae_tagger_b200 import _native
+
+    torch.manual_seed(5)
+    for T, B in ((16384, 1), (16384, 3), (1000, 37)):
+        dec = M.create_attention_decoder(16, 16, 16, T, attention_config={}).eval()
+        sd = {k: v.clone() for k, v in dec.state_dict().items()}
+        lat = torch.randn(B, 16, 16, 16)
+        want = OH.attention_decoder_logits(sd, lat)
+        dec = dec.cuda()
+        out = dec.tag(lat.cuda(), threshold=0.5)
+        logits = dec(lat.cuda()).cpu()
+        assert rel(logits, want) < 2e-5
+        conf = out["conf"].cpu()
+        assert (conf[:, :-1] >= conf[:, 1:]).all()
+        assert torch.equal(out["idx"].cpu().sort(dim=1).values, torch.arange(T).expand(B, T))
+        assert torch.equal(out["count"].cpu(), (torch.sigmoid(logits) >= 0.5).sum(1).to(torch.int32))
+    with pytest.raises(_native.NativeError):
+        ctx.configure_head(_native.HEAD_ATTENTION, latent_channels=16, num_classes=16385)

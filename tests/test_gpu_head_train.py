@@ -271,3 +271,25 @@ def test_decoder_trainer_native_step_matches_autograd_step(golden):
             if d.mean().item() > 1e-4 or d.max().item() > 6.5e-3:
                 bad[k] = (d.mean().item(), d.max().item())
     assert not bad, bad
+
+
+def test_edge_shapes_and_errors(ctx, golden):
+    """Smallest batch / latent the train-mode BatchNorm allows, a ragged non-multiple-of-8 latent, and the
+    argument errors of the C-ABI."""
+    sd = full_sd(golden)
+    layout, flat = setup_head(ctx, sd)
+    g = torch.Generator().manual_seed(4)
+    for B, lh, lw in ((1, 8, 8), (2, 9, 13), (33, 8, 8)):
+        lat = torch.randn(B, 16, lh, lw, generator=g)
+        tgt = (torch.rand(B, 11, generator=g) < 0.3).float()
+        grads = torch.zeros_like(flat)
+        loss, logits = ctx.head_train_step(lat.cuda(), tgt.cuda(), flat, grads, dropout=False, want_logits=True)
+        want = OH.head_train_step(sd, lat, tgt, dtype=torch.float64)
+        assert rel(logits.cpu().double(), want["logits"]) < 2e-5
+        compare_grads(unflatten(layout, grads, sd),
+                      {k: v.float() for k, v in want["grads"].items()}, tol=2e-4)
+    with pytest.raises(_native.NativeError):
+        ctx.head_train_step(torch.zeros(1, 16, 1, 1).cuda(), torch.zeros(1, 11).cuda(), flat, torch.zeros_like(flat))
+    with pytest.raises(_native.NativeError):
+        ctx.head_train_step(torch.zeros(2, 16, 8, 8).cuda(), torch.zeros(2, 11).cuda(), flat, None,
+                            attention_dropout=1.0)

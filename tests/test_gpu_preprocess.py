@@ -66,6 +66,17 @@ def test_strided_source_and_batch_slot_output(ctx):
         ctx.resize_u8(view, (64, 64), None, 7)                 # unknown filter
 
 
+def test_batch_call_equals_single_calls(ctx):
+    rng = np.random.default_rng(4)
+    srcs = [torch.from_numpy(rnd_img(rng, w, h)).cuda() for w, h in ((640, 360), (500, 700), (300, 300))]
+    boxes = [_native.smart_crop_box(s.shape[1], s.shape[0], 192, 128) for s in srcs]
+    batch = ctx.resize_u8_batch(srcs, (192, 128), boxes)
+    for i, (s, b) in enumerate(zip(srcs, boxes)):
+        assert torch.equal(batch[i], ctx.resize_u8(s, (192, 128), b))
+        want = np.asarray(M.SmartResize(192, 128)(Image.fromarray(s.cpu().numpy())))
+        assert np.array_equal(batch[i].cpu().numpy(), want)
+
+
 def test_properties_at_full_size(ctx):
     """Size-independent properties at the bench resolution: a constant image stays constant, identity size is
     a copy, and the result does not depend on how the image is batched."""
@@ -114,3 +125,14 @@ def test_bucket_batcher_feeds_encoder_like_the_host_transform(ctx):
 
     want = np.asarray(transforms.Resize((192, 192))(Image.fromarray(images[0])))
     assert np.array_equal(sq, want)
+
+
+@pytest.mark.parametrize("src,dst", [((1, 1), (5, 7)), ((7, 5), (1, 1)), ((2, 300), (64, 3)), ((3, 3), (3, 3)),
+                                     ((2, 300), (3, 150)), ((2, 201), (2, 100)), ((3, 300), (64, 3)), ((4, 2000), (64, 640))])
+def test_degenerate_sizes(ctx, src, dst):
+    """1-pixel images, and Pillow's vertical-pass-first rule for images more than 100 times taller than wide."""
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (src[1], src[0], 3), dtype=np.uint8)
+    for kind, pil in ((R.LANCZOS, Image.LANCZOS), (R.BILINEAR, Image.BILINEAR)):
+        got = ctx.resize_u8(torch.from_numpy(img).cuda(), dst, None, kind).cpu().numpy()
+        assert np.array_equal(got, np.asarray(Image.fromarray(img).resize(dst, pil)))

@@ -152,7 +152,8 @@ def test_resample_matches_pillow():
 
     rng = np.random.default_rng(0)
     cases = [((97, 131), (64, 64)), ((300, 200), (128, 192)), ((64, 48), (128, 96)), ((200, 100), (200, 64)),
-             ((100, 200), (64, 200)), ((513, 767), (576, 832)), ((33, 47), (33, 47))]
+             ((100, 200), (64, 200)), ((513, 767), (576, 832)), ((33, 47), (33, 47)),
+             ((2, 300), (64, 3)), ((2, 300), (3, 150)), ((2, 201), (2, 100)), ((3, 300), (64, 3)), ((1, 1), (5, 7))]
     for (w, h), (tw, th) in cases:
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         for kind, pil in ((R.LANCZOS, Image.LANCZOS), (R.BILINEAR, Image.BILINEAR)):

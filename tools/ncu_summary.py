@@ -1,0 +1,21 @@
+"""Select the columns that matter from an `ncu --page raw --csv` export:
+    python tools/ncu_summary.py gpurun_out/<tag>_raw.csv profiles/<name>.csv"""
+import csv
+import sys
+
+COLS = ["ID", "Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum",
+        "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.per_cycle_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
+        "sm__cycles_elapsed.avg.per_second"]
+rows = list(csv.reader(open(sys.argv[1])))
+hdr = rows[0]
+keep = [hdr.index(c) for c in COLS if c in hdr]
+with open(sys.argv[2], "w", newline="") as f:
+    w = csv.writer(f)
+    for r in rows:
+        if len(r) == len(hdr):
+            w.writerow([r[i] for i in keep])
+print(len(rows) - 2, "kernels,", len(keep), "columns ->", sys.argv[2])

@@ -133,6 +133,7 @@ SYMBOLS = {
     "vt_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64] + [C.c_float] * 5 + [C.c_int64, C.c_float, C.c_float,
                                                                                   C.c_int, _P, _P]),
     "vt_resize_u8": (C.c_int, [_P, C.POINTER(ResizeArgs)]),
+    "vt_resize_u8_batch": (C.c_int, [_P, C.POINTER(ResizeArgs), C.c_int, _P]),
     "vt_smart_crop_box": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "vt_resize_coefficients": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32)]),
@@ -472,6 +473,28 @@ class Context:
         a.stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             _check(self.lib.vt_resize_u8(self.h, C.byref(a)))
+        return out
+
+    def resize_u8_batch(self, srcs, size, boxes=None, filter=FILTER_LANCZOS, out: torch.Tensor = None):
+        """``resize_u8`` for a list of source images into one ``[N, H, W, 3]`` uint8 batch (one native call)."""
+        W, H = int(size[0]), int(size[1])
+        n = len(srcs)
+        if out is None:
+            out = torch.empty(n, H, W, 3, dtype=torch.uint8, device=self.device)
+        assert out.dtype == torch.uint8 and tuple(out.shape) == (n, H, W, 3) and out.is_contiguous()
+        items = (ResizeArgs * n)()
+        for i, src in enumerate(srcs):
+            assert src.dtype == torch.uint8 and src.is_cuda and src.dim() == 3 and src.shape[2] == 3
+            assert src.stride(2) == 1 and src.stride(1) == 3, "pixels must be packed RGB"
+            h, w = src.shape[0], src.shape[1]
+            l, t, r, b = boxes[i] if boxes is not None and boxes[i] is not None else (0, 0, w, h)
+            a = items[i]
+            a.src = src.data_ptr(); a.src_w = w; a.src_h = h; a.src_stride = src.stride(0)
+            a.crop_l, a.crop_t, a.crop_r, a.crop_b = int(l), int(t), int(r), int(b)
+            a.dst = out[i].data_ptr(); a.dst_w = W; a.dst_h = H; a.dst_stride = out.stride(1)
+            a.filter = int(filter)
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_resize_u8_batch(self.h, items, n, _stream(self.device)))
         return out
 
     # ------------------------------------------------------------------ head training step

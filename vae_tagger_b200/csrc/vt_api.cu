@@ -1312,6 +1312,16 @@ int vt_resize_u8(vt_ctx* c, const vt_resize_args* a) {
     return resize_u8(c->resize, *a, c->prof);
 }
 
+int vt_resize_u8_batch(vt_ctx* c, const vt_resize_args* items, int n, void* stream) {
+    VT_CHECK(items != nullptr && n >= 0, "null arguments");
+    for (int i = 0; i < n; ++i) {
+        vt_resize_args a = items[i];
+        a.stream = stream;
+        VT_TRY(vt_resize_u8(c, &a));
+    }
+    return 0;
+}
+
 int vt_smart_crop_box(int src_w, int src_h, int dst_w, int dst_h, int32_t* box4) {
     VT_CHECK(box4 != nullptr && src_w > 0 && src_h > 0 && dst_w > 0 && dst_h > 0, "bad crop box arguments");
     int b[4];

@@ -9,7 +9,9 @@
 //     filter taps evaluated in double precision at (x + xmin - center + 0.5)/max(scale,1), normalised to
 //     sum 1, then rounded to fixed point with 22 fractional bits (precompute_coeffs, normalize_coeffs_8bpc);
 //   * horizontal pass over the rows, then vertical pass, each  out = clip8((2^21 + sum k*in) >> 22)  in
-//     int32, with a uint8 intermediate image; a pass is skipped when that dimension does not change.
+//     int32, with a uint8 intermediate image; a pass is skipped when that dimension does not change;
+//   * PIL/Image.py Image.resize (12.2): an image more than 100 times taller than wide that shrinks vertically
+//     gets its vertical pass first.
 // The coefficient tables are computed on the host (they depend only on (in size, out size, filter)) and
 // cached on the device; the two passes are byte-streaming kernels: HBM/L2 bound, no tensor cores.
 #include <math.h>
@@ -46,14 +48,16 @@ __device__ __forceinline__ unsigned char clip8(int acc) {
 }
 
 // Horizontal pass.  grid (ceil(out_w/128), ceil(rows/rows_per_cta)); a CTA stages the span of source
-// pixels its 128 output pixels need in shared memory (coalesced), one row at a time.
+// pixels its 128 output pixels need in shared memory (coalesced), R rows at a time: a thread loads each of its
+// taps once and applies it to R rows (R independent accumulation chains hide the load latency).
 //   src: rows of 3-byte pixels, already offset to the crop origin; dst: [rows][out_w][3], row pitch dst_pitch
 //   kk_t: [ksize][out_w] (transposed: coalesced across the threads of a CTA), bounds: [out_w] (xmin, n)
+template <int R>
 __global__ void __launch_bounds__(kHBlock) resize_h_kernel(const unsigned char* __restrict__ src, long long src_pitch,
                                                            unsigned char* __restrict__ dst, long long dst_pitch,
                                                            const int* __restrict__ kk_t,
                                                            const int2* __restrict__ bounds, int out_w, int rows,
-                                                           int rows_per_cta) {
+                                                           int rows_per_cta, int span_pitch) {
     extern __shared__ unsigned char span[];
     const int x0 = blockIdx.x * kHBlock;
     const int xx = x0 + threadIdx.x;
@@ -64,24 +68,39 @@ __global__ void __launch_bounds__(kHBlock) resize_h_kernel(const unsigned char* 
     const int last = bounds[xl].x + bounds[xl].y;  // windows start and end monotonically
     const int nbytes = (last - first) * 3;
     const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
-    for (int r = r0; r < r1; ++r) {
-        const unsigned char* row = src + r * src_pitch + 3LL * first;
+    for (int r = r0; r < r1; r += R) {
+        const int nr = min(R, r1 - r);
         __syncthreads();
-        for (int i = threadIdx.x; i < nbytes; i += kHBlock) span[i] = row[i];
+        for (int q = 0; q < nr; ++q) {
+            const unsigned char* row = src + (r + q) * src_pitch + 3LL * first;
+            for (int i = threadIdx.x; i < nbytes; i += kHBlock) span[q * span_pitch + i] = row[i];
+        }
         __syncthreads();
         if (live) {
-            int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+            int acc[R][3];
+#pragma unroll
+            for (int q = 0; q < R; ++q) acc[q][0] = acc[q][1] = acc[q][2] = 1 << (kPrecisionBits - 1);
             const unsigned char* p = span + 3 * (b.x - first);
             for (int k = 0; k < b.y; ++k) {
                 const int c = kk_t[1LL * k * out_w + xx];
-                a0 += c * p[3 * k];
-                a1 += c * p[3 * k + 1];
-                a2 += c * p[3 * k + 2];
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    if (q < nr) {
+                        acc[q][0] += c * p[q * span_pitch + 3 * k];
+                        acc[q][1] += c * p[q * span_pitch + 3 * k + 1];
+                        acc[q][2] += c * p[q * span_pitch + 3 * k + 2];
+                    }
+                }
             }
-            unsigned char* o = dst + r * dst_pitch + 3LL * xx;
-            o[0] = clip8(a0);
-            o[1] = clip8(a1);
-            o[2] = clip8(a2);
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                if (q < nr) {
+                    unsigned char* o = dst + (r + q) * dst_pitch + 3LL * xx;
+                    o[0] = clip8(acc[q][0]);
+                    o[1] = clip8(acc[q][1]);
+                    o[2] = clip8(acc[q][2]);
+                }
+            }
         }
     }
 }
@@ -257,54 +276,80 @@ int resize_u8(ResizeCache* c, const vt_resize_args& a, Profiler* pf) {
     const unsigned char* src = static_cast<const unsigned char*>(a.src) + a.crop_t * a.src_stride + 3LL * a.crop_l;
     unsigned char* dst = static_cast<unsigned char*>(a.dst);
     const bool need_h = cw != a.dst_w, need_v = ch != a.dst_h;
-    const double bytes = 3.0 * cw * ch + 3.0 * a.dst_w * a.dst_h + (need_h && need_v ? 6.0 * a.dst_w * ch : 0.0);
+    // PIL/Image.py Image.resize (Pillow 12.2): an image more than 100 times taller than wide that shrinks
+    // vertically is resized in two calls, vertical pass first
+    const bool v_first = ch > 100LL * cw && a.dst_h < ch;
+    const double bytes = 3.0 * cw * ch + 3.0 * a.dst_w * a.dst_h +
+                         (need_h && need_v ? 6.0 * (v_first ? 1.0 * cw * a.dst_h : 1.0 * a.dst_w * ch) : 0.0);
     profiler_begin(pf, KC_MISC, s, 0, bytes);
-    const unsigned char* vin = src;
-    long long vin_pitch = a.src_stride;
-    if (need_h) {
+    auto ensure_tmp = [&](size_t need) -> int {
+        if (need > c->tmp_cap) {
+            if (c->tmp) cudaFree(c->tmp);
+            c->tmp = nullptr;
+            c->tmp_cap = 0;
+            VT_CUDA(cudaMalloc(&c->tmp, need));
+            c->tmp_cap = need;
+        }
+        return 0;
+    };
+    auto pass_h = [&](const unsigned char* in, long long in_pitch, int rows, unsigned char* out,
+                      long long out_pitch) -> int {
         const ResizeTable* t = nullptr;
         VT_TRY(get_table(c, cw, a.dst_w, a.filter, &t));
-        unsigned char* hout = dst;
-        long long hpitch = a.dst_stride;
-        if (need_v) {  // uint8 intermediate image [ch][dst_w][3], rows padded to 16 bytes
-            hpitch = (3LL * a.dst_w + 15) / 16 * 16;
-            const size_t need = static_cast<size_t>(hpitch) * ch;
-            if (need > c->tmp_cap) {
-                if (c->tmp) cudaFree(c->tmp);
-                c->tmp = nullptr;
-                c->tmp_cap = 0;
-                VT_CUDA(cudaMalloc(&c->tmp, need));
-                c->tmp_cap = need;
-            }
-            hout = static_cast<unsigned char*>(c->tmp);
+        const int span_pitch = (t->max_span * 3 + 15) / 16 * 16;
+        VT_CHECK(span_pitch <= 200 * 1024, "horizontal scale factor too large for the staged resize kernel");
+        const int R = 4 * span_pitch <= 96 * 1024 && rows >= 4 ? 4 : 1;  // rows staged together
+        const size_t smem = static_cast<size_t>(span_pitch) * R;
+        if (smem > 48 * 1024) {
+            VT_CUDA(cudaFuncSetAttribute(resize_h_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            VT_CUDA(cudaFuncSetAttribute(resize_h_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         }
-        const size_t smem = static_cast<size_t>(t->max_span) * 3;
-        VT_CHECK(smem <= 200 * 1024, "horizontal scale factor too large for the staged resize kernel");
-        if (smem > 48 * 1024)
-            VT_CUDA(cudaFuncSetAttribute(resize_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         const int gx = (a.dst_w + kHBlock - 1) / kHBlock;
-        int rows_per_cta = 1;
-        while (rows_per_cta < 16 && 1LL * gx * ((ch + rows_per_cta - 1) / rows_per_cta) > 148 * 16) rows_per_cta *= 2;
-        resize_h_kernel<<<dim3(gx, (ch + rows_per_cta - 1) / rows_per_cta), kHBlock, smem, s>>>(
-            src, a.src_stride, hout, hpitch, t->kk_t, t->bounds, a.dst_w, ch, rows_per_cta);
-        vin = hout;
-        vin_pitch = hpitch;
-    }
-    if (need_v) {
+        int rows_per_cta = R;
+        while (rows_per_cta < 16 && 1LL * gx * ((rows + rows_per_cta - 1) / rows_per_cta) > 148 * 16) rows_per_cta *= 2;
+        const dim3 grid(gx, (rows + rows_per_cta - 1) / rows_per_cta);
+        if (R == 4)
+            resize_h_kernel<4><<<grid, kHBlock, smem, s>>>(in, in_pitch, out, out_pitch, t->kk_t, t->bounds, a.dst_w,
+                                                           rows, rows_per_cta, span_pitch);
+        else
+            resize_h_kernel<1><<<grid, kHBlock, smem, s>>>(in, in_pitch, out, out_pitch, t->kk_t, t->bounds, a.dst_w,
+                                                           rows, rows_per_cta, span_pitch);
+        return 0;
+    };
+    auto pass_v = [&](const unsigned char* in, long long in_pitch, int width, unsigned char* out,
+                      long long out_pitch) -> int {
         const ResizeTable* t = nullptr;
         VT_TRY(get_table(c, ch, a.dst_h, a.filter, &t));
-        const int row_bytes = 3 * a.dst_w;
-        const bool vec = row_bytes % 4 == 0 && vin_pitch % 4 == 0 && a.dst_stride % 4 == 0 &&
-                         reinterpret_cast<uintptr_t>(vin) % 4 == 0 && reinterpret_cast<uintptr_t>(dst) % 4 == 0;
+        const int row_bytes = 3 * width;
+        const bool vec = row_bytes % 4 == 0 && in_pitch % 4 == 0 && out_pitch % 4 == 0 &&
+                         reinterpret_cast<uintptr_t>(in) % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 4 == 0;
         if (vec)
             resize_v_kernel<4><<<dim3((row_bytes / 4 + 255) / 256, a.dst_h), 256, 0, s>>>(
-                vin, vin_pitch, dst, a.dst_stride, t->kk, t->bounds, t->ksize, row_bytes);
+                in, in_pitch, out, out_pitch, t->kk, t->bounds, t->ksize, row_bytes);
         else
             resize_v_kernel<1><<<dim3((row_bytes + 255) / 256, a.dst_h), 256, 0, s>>>(
-                vin, vin_pitch, dst, a.dst_stride, t->kk, t->bounds, t->ksize, row_bytes);
-    }
-    if (!need_h && !need_v)
+                in, in_pitch, out, out_pitch, t->kk, t->bounds, t->ksize, row_bytes);
+        return 0;
+    };
+    if (need_h && need_v) {  // uint8 intermediate image, rows padded to 16 bytes
+        const int mid_w = v_first ? cw : a.dst_w, mid_h = v_first ? a.dst_h : ch;
+        const long long mid_pitch = (3LL * mid_w + 15) / 16 * 16;
+        VT_TRY(ensure_tmp(static_cast<size_t>(mid_pitch) * mid_h));
+        unsigned char* mid = static_cast<unsigned char*>(c->tmp);
+        if (v_first) {
+            VT_TRY(pass_v(src, a.src_stride, cw, mid, mid_pitch));
+            VT_TRY(pass_h(mid, mid_pitch, a.dst_h, dst, a.dst_stride));
+        } else {
+            VT_TRY(pass_h(src, a.src_stride, ch, mid, mid_pitch));
+            VT_TRY(pass_v(mid, mid_pitch, a.dst_w, dst, a.dst_stride));
+        }
+    } else if (need_h) {
+        VT_TRY(pass_h(src, a.src_stride, ch, dst, a.dst_stride));
+    } else if (need_v) {
+        VT_TRY(pass_v(src, a.src_stride, cw, dst, a.dst_stride));
+    } else {
         copy_rows_kernel<<<dim3((3 * cw + 255) / 256, ch), 256, 0, s>>>(src, a.src_stride, dst, a.dst_stride, 3 * cw);
+    }
     profiler_end(pf, KC_MISC, s);
     VT_CUDA(cudaGetLastError());
     return 0;
