@@ -110,6 +110,11 @@ def test_decoder_fallback_kernels(trio, monkeypatch):
     z = latents(1, 16, 16)
     with torch.no_grad():
         ref = oracle_wrapper_decode(dec, z)
+    sub = wrap.decode(z.cuda()).cpu()                  # default: sub-pixel upsample convs
+    monkeypatch.setenv("VT_B200_NO_SUBPIXEL", "1")     # explicit nearest-2x pass + 3x3 conv
+    explicit = wrap.decode(z.cuda()).cpu()
+    assert rel(sub, ref) <= BF16_TOL and rel(explicit, ref) <= BF16_TOL, (rel(sub, ref), rel(explicit, ref))
+    assert rel(sub, explicit) <= BF16_TOL
     monkeypatch.setenv("VT_B200_NO_FUSED_GN", "1")
     monkeypatch.setenv("VT_B200_NO_FLASH", "1")
     got = wrap.decode(z.cuda()).cpu()

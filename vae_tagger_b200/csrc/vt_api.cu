@@ -101,6 +101,7 @@ struct vt_ctx {
     ConvW dconv_in, dconv_out;
     std::vector<std::vector<ResnetW>> up;  // [block][layer], layers_per_block + 1 each
     std::vector<ConvW> upsample;           // per block (Cout == 0: none)
+    std::vector<bf16*> upsample_sp;        // per block: sub-pixel weights [4][C][4C] (nullptr: none)
     ResnetW dmid0, dmid1;
     AttnW dattn;
     NormW dnorm_out;
@@ -171,6 +172,28 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restri
         else if constexpr (OFMT == FMT_F16)
             static_cast<__half*>(dstv)[d] = __float2half_rn(fminf(fmaxf(src[i], -65504.f), 65504.f));
         else static_cast<float*>(dstv)[d] = src[i];
+    }
+}
+// Sub-pixel weights of "nearest 2x upsample + conv3x3": for output parity (py,px) the 3x3 taps collapse onto
+// 2x2 source pixels.  Rows: py = 0 -> source rows {y-1: ky 0; y: ky 1+2}, py = 1 -> {y: ky 0+1; y+1: ky 2};
+// columns alike.  dst[par][co][(ty*2+tx)*C + ci], summed in fp32 then rounded to bf16 (raw operand).
+__global__ void pack_subpixel_kernel(const float* __restrict__ src /*[Co][C][3][3]*/, bf16* __restrict__ dst, int Co,
+                                     int C) {
+    const long long total = 4LL * Co * 4 * C;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        long long r = i;
+        const int ci = static_cast<int>(r % C); r /= C;
+        const int tap = static_cast<int>(r % 4); r /= 4;
+        const int co = static_cast<int>(r % Co);
+        const int par = static_cast<int>(r / Co);
+        const int py = par >> 1, px = par & 1, ty = tap >> 1, tx = tap & 1;
+        // kernel rows / columns that land on this source tap
+        const int ky0 = py == 0 ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = py == 0 ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+        const int kx0 = px == 0 ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = px == 0 ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+        float a = 0.f;
+        for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) a += src[((1LL * co * C + ci) * 3 + ky) * 3 + kx];
+        dst[i] = __float2bfloat16(a);
     }
 }
 __global__ void add_vec_kernel(float* __restrict__ a, const float* __restrict__ b, int n) {
@@ -259,6 +282,15 @@ struct Packer {
         VT_CUDA(cudaGetLastError());
         return 0;
     }
+    // the four sub-pixel weight sets of an upsample conv (bf16: the operand is a raw activation)
+    int conv_subpixel(const std::string& prefix, int C, bf16** w4) {
+        const Param* pw;
+        VT_TRY(get(prefix + ".weight", {C, C, 3, 3}, &pw));
+        VT_TRY(alloc(w4, static_cast<size_t>(4) * C * 4 * C));
+        pack_subpixel_kernel<<<1024, 256>>>(pw->dev, *w4, C, C);
+        VT_CUDA(cudaGetLastError());
+        return 0;
+    }
     // linear weights [out][in] stacked along the output dimension
     int linear(std::initializer_list<std::string> prefixes, int In, int OutEach, bool with_bias, ConvW* w) {
         const int n = static_cast<int>(prefixes.size());
@@ -304,6 +336,7 @@ void free_packed_decoder(vt_ctx* c) {
     c->dpacked.clear();
     c->up.clear();
     c->upsample.clear();
+    c->upsample_sp.clear();
     c->dec_ready = false;
 }
 
@@ -746,6 +779,7 @@ int run_decoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_decode_args* a, 
         const char* f = getenv("VT_B200_NO_FLASH");
         R.use_flash = !(f && f[0] == '1');
     }
+    const bool use_subpixel = !(getenv("VT_B200_NO_SUBPIXEL") && getenv("VT_B200_NO_SUBPIXEL")[0] == '1');
     // ---- (z - shift) / scale (diffusers_vae_loader.py:88-93), NCHW fp32 -> NHWC padded to one K chunk
     const size_t lat_stride = static_cast<size_t>(LC) * tokens;
     const float shift = (a->apply_scale_shift && cfg.has_shift_factor) ? cfg.shift_factor : 0.f;
@@ -771,12 +805,27 @@ int run_decoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_decode_args* a, 
             st_x = st_o;
         }
         if (c->upsample[b].Cout != 0) {
-            const int C = c->upsample[b].Cin;
-            VT_TRY(launch_upsample2x_nhwc(X.p, T, static_cast<int>(es), n, h, w_, C, s, c->prof));
-            h *= 2; w_ *= 2;
+            const ConvW& uw = c->upsample[b];
+            const int C = uw.Cin;
             double* st_o = R.new_stats();
             Act out{spare, R.raw_fmt()};
-            VT_TRY(R.conv(T, h, w_, c->upsample[b], 1, nullptr, nullptr, out, st_o));
+            if (!fp32 && use_subpixel && c->upsample_sp[b]) {
+                // Upsample2D without the upsampled tensor: four 2x2-tap convs of the source, one per output pixel
+                // parity, with pre-summed taps -- 16/36 of the FLOPs and no extra HBM pass
+                for (int par = 0; par < 4; ++par) {
+                    ConvOp op;
+                    op.in = X.p; op.N = n; op.Hin = h; op.Win = w_; op.Cin = C; op.ksize = 3; op.stride = 1;
+                    op.in_f16 = 0; op.w = c->upsample_sp[b] + static_cast<size_t>(par) * C * 4 * C; op.Cout = C;
+                    op.bias = uw.bias; op.out = out.p; op.out_fmt = out.fmt; op.stats = st_o;
+                    op.up2 = 1; op.up_py = par >> 1; op.up_px = par & 1;
+                    VT_TRY(launch_conv(op, s, c->prof));
+                }
+                h *= 2; w_ *= 2;
+            } else {
+                VT_TRY(launch_upsample2x_nhwc(X.p, T, static_cast<int>(es), n, h, w_, C, s, c->prof));
+                h *= 2; w_ *= 2;
+                VT_TRY(R.conv(T, h, w_, uw, 1, nullptr, nullptr, out, st_o));
+            }
             advance(out);
             st_x = st_o;
         }
@@ -1041,6 +1090,7 @@ int vt_decoder_finalize(vt_ctx* c) {
     }
     c->up.resize(nb);
     c->upsample.resize(nb);
+    c->upsample_sp.assign(nb, nullptr);
     int cin = Cm;
     for (int b = 0; b < nb; ++b) {
         const int cout = cfg.block_out_channels[nb - 1 - b];
@@ -1048,9 +1098,11 @@ int vt_decoder_finalize(vt_ctx* c) {
         for (int l = 0; l <= cfg.layers_per_block; ++l)
             VT_TRY(P.resnet("up_blocks." + std::to_string(b) + ".resnets." + std::to_string(l), l == 0 ? cin : cout,
                             cout, &c->up[b][l]));
-        if (b < nb - 1)
-            VT_TRY(P.conv("up_blocks." + std::to_string(b) + ".upsamplers.0.conv", cout, cout, 3, "", 0, 0,
-                          &c->upsample[b], /*f16=*/false));
+        if (b < nb - 1) {
+            const std::string up = "up_blocks." + std::to_string(b) + ".upsamplers.0.conv";
+            VT_TRY(P.conv(up, cout, cout, 3, "", 0, 0, &c->upsample[b], /*f16=*/false));
+            VT_TRY(P.conv_subpixel(up, cout, &c->upsample_sp[b]));
+        }
         cin = cout;
     }
     const int C0 = cfg.block_out_channels[0];

@@ -130,7 +130,9 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     VT_CHECK(op.sc_in == nullptr || op.stride == 1, "shortcut slab needs a stride-1 conv");
     const int Hout = op.stride == 1 ? op.Hin : op.Hin / 2;
     const int Wout = op.stride == 1 ? op.Win : op.Win / 2;
-    const int taps = op.ksize * op.ksize;
+    VT_CHECK(!op.up2 || (op.ksize == 3 && op.stride == 1 && op.sc_in == nullptr && op.residual == nullptr),
+             "sub-pixel upsample conv: 3x3, stride 1, no shortcut / residual");
+    const int taps = op.up2 ? 4 : op.ksize * op.ksize;
     const int Ktot = taps * op.Cin + (op.sc_in ? op.Cs : 0);
     const int block_n = pick_block_n(op.Cout);
 
@@ -154,8 +156,29 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     P.alpha = op.alpha;
     P.bias = op.bias; P.residual = op.residual; P.res_fp32 = op.residual_fp32; P.out = op.out; P.ld_out = op.Cout;
     P.out_bstride = 1LL * Hout * Wout * op.Cout; P.stats = op.stats;
+    if (op.up2) {  // strided view of the 2x-upsampled output: this launch writes one pixel parity
+        VT_CHECK(4LL * Hout * Wout * op.Cout < (1LL << 31), "upsampled conv output of one image exceeds 2^31 elements");
+        const size_t esz = op.out_fmt == FMT_F32 ? 4 : 2;
+        P.out = static_cast<char*>(op.out) + (static_cast<size_t>(op.up_py) * 2 * Wout + op.up_px) * op.Cout * esz;
+        P.out_row_pitch = 2 * (2 * Wout) * op.Cout;
+        P.out_px_stride = 2 * op.Cout;
+        P.out_bstride = 4LL * Hout * Wout * op.Cout;
+    }
 
     int ns = 0;
+    if (op.up2) {
+        for (int ty = 0; ty < 2; ++ty)
+            for (int tx = 0; tx < 2; ++tx) {
+                IgemmSlab& s = P.slabs[ns];
+                s.map = 0; s.c_base = 0; s.p = 0;
+                s.dy = op.up_py == 0 ? ty - 1 : ty;
+                s.dx = op.up_px == 0 ? tx - 1 : tx;
+                s.kb_base = ns * op.Cin;
+                s.nchunks = op.Cin / 64;
+                s.f16 = op.in_f16;
+                ++ns;
+            }
+    } else
     for (int kh = 0; kh < op.ksize; ++kh)
         for (int kw = 0; kw < op.ksize; ++kw) {
             IgemmSlab& s = P.slabs[ns];

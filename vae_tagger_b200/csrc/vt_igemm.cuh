@@ -60,6 +60,8 @@ struct IgemmParams {
     void* out;
     long long ld_out;      // elements between consecutive pixels of out / residual
     long long out_bstride;  // elements between consecutive images of out / residual
+    int out_row_pitch;      // elements between output rows (0: W * ld_out) -- a strided output view, e.g. one
+    int out_px_stride;      // parity of a 2x-upsampled image; elements between output pixels (0: ld_out)
     double* stats;     // [NB][n_total/group_size][2] running (sum, sum of squares): fp32 per-tile partials,
                        // fp64 atomics across tiles (keeps E[x^2]-E[x]^2 well conditioned)
     IgemmSlab slabs[IGEMM_MAX_SLABS];
@@ -158,6 +160,8 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
 
     // per-tile geometry: image, n-block, and for each sub-tile the element offset of this lane's first
     // row (i = 0) inside the image plus a 4-bit validity mask of its rows i = 0..3
+    const int out_pxs = P.out_px_stride ? P.out_px_stride : static_cast<int>(P.ld_out);
+    const int out_rowp = P.out_row_pitch ? P.out_row_pitch : P.W * static_cast<int>(P.ld_out);
     struct Geo {
         int nb, img;
         int off0[MT];
@@ -179,7 +183,7 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
             const int xs = (tx * (P.sub_dx ? MT : 1) + t * P.sub_dx) * P.tw;
             const int ys = (ty * (P.sub_dy ? MT : 1) + t * P.sub_dy) * P.th;
             const int px0 = xs + (r0 & (P.tw - 1)), py0 = ys + (r0 >> P.tw_log2);
-            g.off0[t] = (py0 * P.W + px0) * static_cast<int>(P.ld_out);
+            g.off0[t] = py0 * out_rowp + px0 * out_pxs;
             unsigned vm = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -190,8 +194,8 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
             g.vmask[t] = vm;
         }
     };
-    const int step1 = (P.ay1 * P.W + P.ax1) * static_cast<int>(P.ld_out);  // accumulator row r -> r + 8
-    const int step2 = (P.ay2 * P.W + P.ax2) * static_cast<int>(P.ld_out);  // accumulator row r -> r + 16
+    const int step1 = P.ay1 * out_rowp + P.ax1 * out_pxs;  // accumulator row r -> r + 8
+    const int step2 = P.ay2 * out_rowp + P.ax2 * out_pxs;  // accumulator row r -> r + 16
 
     // residual registers of one pass: 8 channels x 4 rows per lane
     struct ResRegs {

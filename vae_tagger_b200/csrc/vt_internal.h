@@ -79,6 +79,10 @@ struct ConvOp {
     int out_fmt = 0;                 // 0 bf16, 1 fp32, 2 fp16
     double* stats = nullptr;  // [N][32][2] GroupNorm (sum, sumsq) of the output (group = Cout/32 channels)
     float alpha = 1.f;
+    // Sub-pixel form of "nearest 2x upsample, then conv3x3" (tcgen05 path only): the output pixels of parity
+    // (up_py, up_px) of the 2Hin x 2Win result are a 2x2-tap conv of the SOURCE image whose taps are sums of the
+    // 3x3 taps; w = [Cout][4*Cin] (tap (ty,tx) at K offset (ty*2+tx)*Cin), out = the full upsampled tensor.
+    int up2 = 0, up_py = 0, up_px = 0;
 };
 int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof);
 
