@@ -177,3 +177,30 @@ def test_fused_infer_call_equals_encode_then_tag(golden):
     out = ctx.infer_host(host, threshold=0.5)
     want = encode_and_tag(wrap, dec, x, threshold=0.5)
     assert (out["conf"] - want["conf"].cpu()).abs().max().item() <= 2e-2      # two bf16 runs
+
+
+def test_config1_512_batch1_fp32(golden):
+    """BASELINE configs[0] -- the reference's own CPU-runnable case: FLUX VAE encoder (random init) + 8-head
+    attention tagger, 512x512, batch 1, fp32 -- through encode + tag, against the oracle run on the CPU:
+    latent rel-L2 <= 1e-4 (north star, fp32 mode), max |delta sigmoid| <= 1e-4, identical tags at 0.5."""
+    oracle = make_oracle_vae(0)
+    vae = L.load_diffusers_vae_from_config(L.get_diffusers_vae_config())
+    vae.load_state_dict(oracle.state_dict(), strict=False)
+    wrap = L.DiffusersVAEWrapper(vae).cuda().eval()
+    wrap.vae.precision = "fp32"
+    sd = dict(golden["attention_head_base"]); sd.update(golden["attention_head"]["att_T11_64x64"]["state_dict"])
+    dec = M.create_attention_decoder(16, 64, 64, 11, attention_config={})
+    dec.load_state_dict(sd)
+    dec = dec.cuda().eval()
+    x = synthetic_images(1, 512, 512)
+    with torch.no_grad():
+        ref_lat = oracle_wrapper_encode(oracle, x)
+        ref_p = torch.sigmoid(OH.attention_decoder_logits(sd, ref_lat))
+    lat = wrap.encode(x.cuda())
+    assert lat.shape == (1, 16, 64, 64) and rel(lat.cpu(), ref_lat) <= 1e-4, rel(lat.cpu(), ref_lat)
+    conf, idx = dec.get_confidence(lat)
+    p = torch.sigmoid(dec(lat)).cpu()
+    assert (p - ref_p).abs().max().item() <= 1e-4
+    assert torch.equal(p >= 0.5, ref_p >= 0.5)
+    assert torch.equal(idx.cpu()[0], torch.sort(ref_p[0], descending=True).indices) or \
+        (ref_p[0].sort(descending=True).values.diff().abs().min().item() < 1e-5)
