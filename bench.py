@@ -25,8 +25,6 @@ import sys
 import threading
 import time
 
-# NCCL prints its version banner on stdout when NCCL_DEBUG is set on the box; stdout carries the JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -350,10 +348,18 @@ def main():
     ap.add_argument("--resolution", type=int, default=RES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything native code prints there while the benchmark runs (NCCL's
+    # version banner under NCCL_DEBUG=VERSION is a plain printf) is sent to stderr at the file-descriptor level;
+    # print() inside run_* goes through sys.stdout, which is re-pointed at the real stdout
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
