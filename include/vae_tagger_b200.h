@@ -194,7 +194,8 @@ int vt_focal_loss(vt_ctx* ctx, const float* logits, const float* targets, int64_
  * fp32 device buffers laid out like the reference module's parameters() -- vt_head_param_layout
  * gives the offsets; the same flat gradient buffer is what the data-parallel step all-reduces
  * (train_decoder.py:39 accelerate/DDP).  BatchNorm2d runs on batch statistics and updates the
- * running buffers in place.  nn.BCEWithLogitsLoss is focal_alpha = 1, focal_gamma = 0. */
+ * running buffers in place.  nn.BCEWithLogitsLoss is focal_alpha = 1, focal_gamma = 0; ClassBalancedLoss
+ * (improved_losses.py:58-72, train_decoder.py:188-189) is that plus class_weights. */
 int vt_head_param_count(vt_ctx* ctx, int32_t* n_tensors, int64_t* n_floats);
 /* index in [0, n_tensors): state-dict key (copied into name, NUL-terminated), offset and size in floats */
 int vt_head_param_layout(vt_ctx* ctx, int32_t index, char* name, int32_t name_cap, int64_t* offset,
@@ -218,6 +219,8 @@ typedef struct vt_head_train_args {
     float* loss;   /* device scalar, += loss_scale * mean loss; may be NULL */
     float* logits; /* optional out, device [B,T] */
     void* stream;
+    const float* class_weights; /* optional device [T]: ClassBalancedLoss weights (improved_losses.py:66-69), each
+                                 * term of the loss is multiplied by its class weight; use focal_gamma = 0 */
 } vt_head_train_args;
 int vt_head_train_step(vt_ctx* ctx, const vt_head_train_args* args);
 

@@ -138,6 +138,19 @@ def focal_loss(logits: torch.Tensor, targets: torch.Tensor, alpha=1.0, gamma=2.0
     return fl
 
 
+def class_balanced_loss(logits: torch.Tensor, targets: torch.Tensor, samples_per_class, beta=0.9999):
+    """improved_losses.py:58-72 (ClassBalancedLoss.forward; gamma is unused there): effective-number class
+    weights in float64 numpy, cast to float32, times the elementwise BCE, mean."""
+    import numpy as np
+
+    effective_num = 1.0 - np.power(beta, np.asarray(samples_per_class))
+    weights = (1.0 - beta) / effective_num
+    weights = weights / weights.sum() * len(weights)
+    w = torch.tensor(weights, dtype=torch.float32)
+    bce = F.binary_cross_entropy_with_logits(logits, targets, reduction="none")
+    return (bce * w.to(bce.dtype).unsqueeze(0)).mean()
+
+
 def focal_loss_grad(logits: torch.Tensor, targets: torch.Tensor, alpha=1.0, gamma=2.0):
     """d mean(focal)/d logits via autograd on the restatement above (for the fused kernel)."""
     x = logits.detach().clone().requires_grad_(True)
@@ -216,7 +229,8 @@ def plain_decoder_train(sd: dict, latent: torch.Tensor, cls_masks=None) -> torch
 NON_TRAINABLE = ("running_mean", "running_var", "num_batches_tracked")
 
 
-def head_train_step(sd: dict, latent, targets, alpha=1.0, gamma=2.0, kind="attention", dtype=torch.float32, **kw):
+def head_train_step(sd: dict, latent, targets, alpha=1.0, gamma=2.0, kind="attention", dtype=torch.float32,
+                    samples_per_class=None, **kw):
     """One reference training step on the head (train_decoder.py:186-195 without the optimizer):
     train-mode forward, FocalLoss(alpha, gamma) mean, autograd backward.
     Returns dict(loss, logits, grads{key: tensor}, running_mean, running_var).
@@ -233,7 +247,10 @@ def head_train_step(sd: dict, latent, targets, alpha=1.0, gamma=2.0, kind="atten
         logits, rm, rv = attention_decoder_train(leaf, latent, **kw)
     else:
         logits, rm, rv = plain_decoder_train(leaf, latent, **kw), None, None
-    loss = focal_loss(logits, targets, alpha, gamma)
+    if samples_per_class is not None:     # train_decoder.py:188-189: ClassBalancedLoss instead of the focal loss
+        loss = class_balanced_loss(logits, targets, samples_per_class)
+    else:
+        loss = focal_loss(logits, targets, alpha, gamma)
     loss.backward()
     grads = {k: v.grad for k, v in leaf.items() if v.requires_grad and v.grad is not None}
     return {"loss": loss.detach(), "logits": logits.detach(), "grads": grads, "running_mean": rm, "running_var": rv}

@@ -21,6 +21,7 @@ import io
 import os
 import sys
 
+import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -114,6 +115,16 @@ def main():
     out["plain"] = {"latent": lat, "targets": tgt, "logits": logits.detach().clone(), "loss": loss.detach().clone(),
                     "grads": {k: digest(p.grad) for k, p in pdec.named_parameters()},
                     "param_order": [k for k, _ in pdec.named_parameters()]}
+
+    # ClassBalancedLoss (improved_losses.py:58-72) value and gradient
+    torch.manual_seed(15)
+    x = (torch.randn(6, 11) * 2).requires_grad_(True)
+    y = (torch.rand(6, 11) < 0.3).float()
+    spc = np.array([120.0, 3.0, 45.0, 1.0, 800.0, 17.0, 5.0, 260.0, 9.0, 33.0, 2.0])
+    cb = ref_losses.ClassBalancedLoss()(x, y, spc)
+    cb.backward()
+    out["class_balanced"] = {"logits": x.detach().clone(), "targets": y, "samples_per_class": spc,
+                             "loss": cb.detach().clone(), "grad": x.grad.clone()}
 
     # clip_grad_norm_ + AdamW on a flat tensor, three steps
     torch.manual_seed(14)

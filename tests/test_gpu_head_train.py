@@ -293,3 +293,40 @@ def test_edge_shapes_and_errors(ctx, golden):
     with pytest.raises(_native.NativeError):
         ctx.head_train_step(torch.zeros(2, 16, 8, 8).cuda(), torch.zeros(2, 11).cuda(), flat, None,
                             attention_dropout=1.0)
+
+
+def test_class_balanced_training_step(ctx, golden, train_golden):
+    """--use_class_balanced (train_decoder.py:188-189): the class weights go into the loss kernel; gradients
+    against the oracle's ClassBalancedLoss step, and DecoderTrainer picks the native step for it."""
+    from vae_tagger_b200.improved_losses import ClassBalancedCriterion, class_balanced_weights
+
+    sd = full_sd(golden)
+    layout, flat = setup_head(ctx, sd)
+    spc = train_golden["class_balanced"]["samples_per_class"]
+    g = torch.Generator().manual_seed(12)
+    lat = torch.randn(3, 16, 16, 24, generator=g)
+    tgt = (torch.rand(3, 11, generator=g) < 0.3).float()
+    w = torch.tensor(class_balanced_weights(spc), dtype=torch.float32).cuda()
+    grads = torch.zeros_like(flat)
+    loss, logits = ctx.head_train_step(lat.cuda(), tgt.cuda(), flat, grads, focal_alpha=1.0, focal_gamma=0.0,
+                                       dropout=False, class_weights=w, want_logits=True)
+    want = OH.head_train_step(sd, lat, tgt, samples_per_class=spc)
+    assert abs(loss.item() - want["loss"].item()) < 1e-6 * max(1.0, want["loss"].item())
+    compare_grads(unflatten(layout, grads, sd), want["grads"])
+
+    from vae_tagger_b200 import modules as M
+    from vae_tagger_b200.train_decoder import DecoderTrainer
+
+    class FrozenLatent(torch.nn.Module):
+        def encode(self, x):
+            return x
+
+    dec = M.create_attention_decoder(16, 16, 24, 11, attention_config={})
+    dec.load_state_dict(sd)
+    dec = dec.cuda()
+    opt = torch.optim.AdamW(dec.parameters(), lr=1e-3)
+    tr = DecoderTrainer(FrozenLatent(), dec, ClassBalancedCriterion(spc), opt, None, native_step=True)
+    assert tr.native and tr._gamma == 0.0 and tr._class_w is not None
+    l0 = tr.step(lat.cuda(), tgt.cuda()).item()
+    tr.flush()
+    assert l0 > 0 and torch.isfinite(torch.tensor(l0))

@@ -167,3 +167,19 @@ def test_resample_matches_pillow():
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         want = np.asarray(SmartResize(tw, th)(Image.fromarray(img)))
         assert np.array_equal(R.smart_resize_u8(img, tw, th), want), ((w, h), (tw, th))
+
+
+def test_class_balanced_loss_oracle_and_module(train_golden):
+    """ClassBalancedLoss (improved_losses.py:58-72): the oracle and the package's module (pure PyTorch on CPU)
+    against the reference's own value and gradient."""
+    from vae_tagger_b200.improved_losses import ClassBalancedCriterion, ClassBalancedLoss
+
+    g = train_golden["class_balanced"]
+    for fn in (lambda x: OH.class_balanced_loss(x, g["targets"], g["samples_per_class"]),
+               lambda x: ClassBalancedLoss()(x, g["targets"], g["samples_per_class"]),
+               lambda x: ClassBalancedCriterion(g["samples_per_class"])(x, g["targets"])):
+        x = g["logits"].clone().requires_grad_(True)
+        loss = fn(x)
+        loss.backward()
+        torch.testing.assert_close(loss.detach(), g["loss"], atol=1e-7, rtol=1e-6)
+        torch.testing.assert_close(x.grad, g["grad"], atol=1e-8, rtol=1e-6)

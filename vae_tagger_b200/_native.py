@@ -91,7 +91,7 @@ class HeadTrainArgs(C.Structure):
         ("bn_running_var", C.c_void_p), ("bn_num_batches_tracked", C.c_void_p), ("bn_momentum", C.c_float),
         ("focal_alpha", C.c_float), ("focal_gamma", C.c_float), ("loss_scale", C.c_float), ("dropout", C.c_int),
         ("attention_dropout", C.c_float), ("seed", C.c_uint64), ("loss", C.c_void_p), ("logits", C.c_void_p),
-        ("stream", C.c_void_p),
+        ("stream", C.c_void_p), ("class_weights", C.c_void_p),
     ]
 
 
@@ -515,7 +515,7 @@ class Context:
     def head_train_step(self, latent, targets, flat_params, flat_grads=None, bn_running_mean=None,
                         bn_running_var=None, bn_num_batches_tracked=None, bn_momentum=0.1, focal_alpha=1.0,
                         focal_gamma=2.0, loss_scale=1.0, dropout=True, attention_dropout=0.1, seed=0, loss=None,
-                        want_logits=False):
+                        want_logits=False, class_weights=None):
         """Train-mode forward + focal/BCE loss + backward of the configured head (``vt_head_train_step``).
         Gradients are accumulated into ``flat_grads``; returns (loss accumulator tensor, logits or None)."""
         lat = _f32c(latent, self.device)
@@ -538,6 +538,10 @@ class Context:
         a.loss_scale = float(loss_scale); a.dropout = int(bool(dropout))
         a.attention_dropout = float(attention_dropout); a.seed = int(seed) & (2 ** 64 - 1)
         a.loss = loss.data_ptr(); a.logits = logits.data_ptr() if logits is not None else None
+        if class_weights is not None:
+            assert class_weights.is_cuda and class_weights.dtype == torch.float32 and class_weights.is_contiguous()
+            assert class_weights.numel() == self.num_classes
+            a.class_weights = class_weights.data_ptr()
         a.stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             _check(self.lib.vt_head_train_step(self.h, C.byref(a)))

@@ -395,21 +395,23 @@ __global__ void __launch_bounds__(1024) head_confidence_kernel(const float* __re
 // loss_sum accumulates sum(fl) (one atomic per block); grad = grad_scale * dfl/dx.
 __global__ void __launch_bounds__(256) focal_loss_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                          float* __restrict__ loss_sum, float* __restrict__ grad,
-                                                         long long n, float alpha, float gamma, float grad_scale) {
+                                                         long long n, float alpha, float gamma, float grad_scale,
+                                                         const float* __restrict__ class_w, int T) {
     __shared__ float red[8];
     float local = 0.f;
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
         const float xv = x[i], yv = y[i];
+        const float cw = class_w ? class_w[i % T] : 1.0f;  // ClassBalancedLoss: per-class weight (improved_losses.py:66-72)
         const float bce = fmaxf(xv, 0.f) - xv * yv + log1pf(expf(-fabsf(xv)));
         const float pt = expf(-bce);
         const float om = 1.0f - pt;
         const float mod = (gamma == 0.f) ? 1.0f : powf(om, gamma);
-        local += alpha * mod * bce;
+        local += cw * alpha * mod * bce;
         if (grad) {
             const float dbce = sigmoidf_(xv) - yv;
             float dmod = 0.f;
             if (gamma != 0.f && om > 0.f) dmod = gamma * powf(om, gamma - 1.0f) * pt;
-            grad[i] = grad_scale * alpha * dbce * (mod + dmod * bce);
+            grad[i] = grad_scale * cw * alpha * dbce * (mod + dmod * bce);
         }
     }
     const float t = block_sum256(local, red);
@@ -509,10 +511,11 @@ int launch_head_confidence(const float* logits, float* conf_sorted, long long* i
 }
 
 int launch_focal_loss(const float* logits, const float* targets, float* loss_sum, float* grad, long long n,
-                      float alpha, float gamma, float grad_scale, cudaStream_t s, Profiler* prof) {
+                      float alpha, float gamma, float grad_scale, cudaStream_t s, Profiler* prof, const float* class_w,
+                      int T) {
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 8)));
     profiler_begin(prof, KC_HEAD, s, 0, 12.0 * n);
-    focal_loss_kernel<<<grid, 256, 0, s>>>(logits, targets, loss_sum, grad, n, alpha, gamma, grad_scale);
+    focal_loss_kernel<<<grid, 256, 0, s>>>(logits, targets, loss_sum, grad, n, alpha, gamma, grad_scale, class_w, T);
     profiler_end(prof, KC_HEAD, s);
     VT_CUDA(cudaGetLastError());
     return 0;

@@ -1195,7 +1195,7 @@ int head_train_step(const vt_head_config& h, const vt_head_train_args& a, float*
     const long long nl = 1LL * B * T;
     VT_CUDA(cudaMemsetAsync(ws + w.loss, 0, sizeof(float), s));
     VT_TRY(launch_focal_loss(logits, a.targets, ws + w.loss, ws + w.dlogits, nl, a.focal_alpha, a.focal_gamma,
-                             a.loss_scale / static_cast<float>(nl), s, pf));
+                             a.loss_scale / static_cast<float>(nl), s, pf, a.class_weights, T));
     if (a.loss)
         head_scale_add_kernel<<<1, 32, 0, s>>>(ws + w.loss, a.loss_scale / static_cast<float>(nl), a.loss);
     if (!a.grads) {

@@ -204,6 +204,7 @@ int launch_head_ln_act(float* x, const float* w, const float* b, int B, int D, i
 int launch_head_confidence(const float* logits, float* conf_sorted, long long* idx_sorted, int* count, float* probs,
                            int B, int T, float thr, cudaStream_t, Profiler*);
 int launch_focal_loss(const float* logits, const float* targets, float* loss_sum, float* grad, long long n,
-                      float alpha, float gamma, float grad_scale, cudaStream_t, Profiler*);
+                      float alpha, float gamma, float grad_scale, cudaStream_t, Profiler*,
+                      const float* class_w = nullptr /*[T] per-class weights*/, int T = 1);
 
 }  // namespace vt

@@ -2,8 +2,8 @@
 
 On CUDA tensors the loss value and ``d loss / d logits`` come from one kernel
 (``vt_focal_loss``: ``bce = BCEWithLogits``, ``pt = exp(-bce)``, ``alpha (1-pt)^gamma bce`` and the
-analytic gradient); autograd only sees a custom ``Function``.  ``ClassBalancedLoss`` (:58-72)
-composes the same kernel with per-class weights.  The triplet / contrastive / combined losses of
+analytic gradient); autograd only sees a custom ``Function``.  ``ClassBalancedLoss`` (:58-72) is the
+reference's weighted BCE; the native training step applies its weights inside the same kernel.  The triplet / contrastive / combined losses of
 the reference serve VAE fine-tuning (``train_full.py`` / ``train_vae.py``) and are out of scope.
 """
 from __future__ import annotations
@@ -46,22 +46,46 @@ class FocalLoss(nn.Module):
         return total / inputs.numel() if self.reduction == "mean" else total
 
 
+def class_balanced_weights(samples_per_class, beta=0.9999):
+    """Effective-number class weights exactly as the reference forms them (improved_losses.py:66-69): float64
+    numpy, ``(1-beta)/(1-beta^n)`` normalised to sum to the number of classes."""
+    spc = np.asarray(samples_per_class)
+    effective_num = 1.0 - np.power(beta, spc)
+    weights = (1.0 - beta) / effective_num
+    return weights / weights.sum() * len(weights)
+
+
 class ClassBalancedLoss(nn.Module):
-    """Effective-number class weights on top of the focal term (reference :58-72)."""
+    """Effective-number class weights on the binary cross entropy (reference :58-72; like the reference,
+    ``gamma`` is accepted and unused).  On CUDA tensors the weighted loss and its gradient come from the fused
+    kernel (``vt_focal_loss`` arithmetic with gamma = 0 and per-class weights)."""
 
     def __init__(self, beta=0.9999, gamma=2.0):
         super().__init__()
         self.beta, self.gamma = beta, gamma
 
-    def forward(self, logits, labels, samples_per_class):
-        n = torch.as_tensor(np.asarray(samples_per_class, dtype=np.float64), device=logits.device)
-        eff = 1.0 - torch.pow(torch.as_tensor(self.beta, dtype=torch.float64, device=logits.device), n)
-        w = (1.0 - self.beta) / (eff + 1e-8)
-        w = (w / w.sum() * len(samples_per_class)).to(logits.dtype)
-        # per-class weights commute with the elementwise focal term: weight the logits' gradient path
-        bce = torch.nn.functional.binary_cross_entropy_with_logits(logits, labels, reduction="none")
-        pt = torch.exp(-bce)
-        return (w.unsqueeze(0) * (1 - pt) ** self.gamma * bce).mean()
+    def forward(self, inputs, targets, samples_per_class):
+        weights = torch.tensor(class_balanced_weights(samples_per_class, self.beta), dtype=torch.float32,
+                               device=inputs.device)
+        bce = torch.nn.functional.binary_cross_entropy_with_logits(inputs, targets, reduction="none")
+        return (bce * weights.unsqueeze(0)).mean()
+
+
+class ClassBalancedCriterion(nn.Module):
+    """``loss_fn(logits, labels)`` form of ``ClassBalancedLoss()(logits, labels, class_distribution)``
+    (train_decoder.py:188-189) -- a module instead of a closure so that ``DecoderTrainer`` can hand the class
+    weights to the native training step."""
+
+    def __init__(self, class_distribution, beta=0.9999, gamma=2.0):
+        super().__init__()
+        self.loss = ClassBalancedLoss(beta, gamma)
+        self.class_distribution = np.asarray(class_distribution)
+
+    def weights(self):
+        return class_balanced_weights(self.class_distribution, self.loss.beta)
+
+    def forward(self, logits, labels):
+        return self.loss(logits, labels, self.class_distribution)
 
 
 def compute_class_distribution(dataset):

@@ -11,8 +11,8 @@ Differences in *how* (not what):
   * the decoder's train-mode forward, the focal / BCE loss, the backward, gradient clipping and AdamW run
     as native kernels on flat parameter / gradient buffers (``vt_head_train_step``, ``vt_adamw_step``);
     the module's parameters are views into the flat buffer, so checkpoints and ``state_dict`` are
-    unchanged.  Configurations without a kernel (``--use_cross_attention``, ``--use_class_balanced``, a
-    non-AdamW optimizer) keep the PyTorch autograd graph for the head only.
+    unchanged (``--use_class_balanced``: the class weights go into the loss kernel).  Configurations without a
+    kernel (``--use_cross_attention``, a non-AdamW optimizer) keep the PyTorch autograd graph for the head only.
 
 Launch:  torchrun --nproc-per-node N -m vae_tagger_b200.train_decoder --vae_checkpoint ... (same flags as
 the reference; ``--mixed_precision`` is accepted and ignored: the encoder runs bf16 tensor-core
@@ -99,7 +99,7 @@ class DecoderTrainer:
     # -- native training step -----------------------------------------------------------------
     def _native_plan(self):
         """None when the step can run as native kernels, else the reason it cannot."""
-        from .improved_losses import FocalLoss
+        from .improved_losses import ClassBalancedCriterion, FocalLoss
 
         dec, dev = self.decoder, self.params[0].device
         if dev.type != "cuda":
@@ -125,13 +125,17 @@ class DecoderTrainer:
         else:
             return f"classifier dropout rates {ps} differ from the reference's {want_p}"
         self._attn_p = float(attn_p)
-        if isinstance(self.loss_fn, FocalLoss) and self.loss_fn.reduction == "mean":
+        self._class_w = None
+        if isinstance(self.loss_fn, ClassBalancedCriterion):
+            self._alpha, self._gamma = 1.0, 0.0
+            self._class_w = torch.tensor(self.loss_fn.weights(), dtype=torch.float32, device=dev)
+        elif isinstance(self.loss_fn, FocalLoss) and self.loss_fn.reduction == "mean":
             self._alpha, self._gamma = float(self.loss_fn.alpha), float(self.loss_fn.gamma)
         elif (isinstance(self.loss_fn, nn.BCEWithLogitsLoss) and self.loss_fn.reduction == "mean"
               and self.loss_fn.weight is None and self.loss_fn.pos_weight is None):
             self._alpha, self._gamma = 1.0, 0.0
         else:
-            return "loss is neither FocalLoss(mean) nor BCEWithLogitsLoss(mean)"
+            return "loss is none of FocalLoss(mean), BCEWithLogitsLoss(mean), ClassBalancedCriterion"
         o = self.opt
         if type(o) is not torch.optim.AdamW or len(o.param_groups) != 1:
             return "optimizer is not a single-group torch.optim.AdamW"
@@ -175,7 +179,7 @@ class DecoderTrainer:
             bn.num_batches_tracked if bn is not None else None,
             bn_momentum=bn.momentum if bn is not None else 0.1, focal_alpha=self._alpha, focal_gamma=self._gamma,
             loss_scale=1.0 / self.accum, dropout=self._dropout, attention_dropout=self._attn_p,
-            seed=self._seed_base + self._micro * self.world + self.rank)
+            seed=self._seed_base + self._micro * self.world + self.rank, class_weights=self._class_w)
         return loss[0]
 
     # -- gradient exchange ------------------------------------------------------------------
@@ -248,7 +252,7 @@ def train_decoder(args):
     from torch.utils.data import DataLoader
     from torch.utils.data.distributed import DistributedSampler
 
-    from .improved_losses import ClassBalancedLoss, FocalLoss, compute_class_distribution
+    from .improved_losses import ClassBalancedCriterion, FocalLoss, compute_class_distribution
 
     if not torch.cuda.is_available():
         raise RuntimeError("vae_tagger_b200 needs CUDA devices (B200)")
@@ -308,11 +312,8 @@ def train_decoder(args):
     val_dl = DataLoader(val_ds, batch_size=args.train_batch_size, shuffle=False, pin_memory=True, num_workers=0)
 
     loss_fn = FocalLoss(alpha=args.focal_alpha, gamma=args.focal_gamma) if args.use_focal_loss else nn.BCEWithLogitsLoss()
-    cb = ClassBalancedLoss() if args.use_class_balanced else None
-    if cb is not None:
-        base_fn = lambda logits, labels: cb(logits, labels, class_distribution)  # noqa: E731
-    else:
-        base_fn = loss_fn
+    # train_decoder.py:188-189: with --use_class_balanced the class-balanced loss replaces the focal / BCE one
+    base_fn = ClassBalancedCriterion(class_distribution) if args.use_class_balanced else loss_fn
     optimizer = torch.optim.AdamW(decoder.parameters(), lr=args.learning_rate, weight_decay=args.weight_decay)
     scheduler = get_scheduler(args.lr_scheduler_type, optimizer, args.lr_warmup_steps, args.num_epochs * len(train_dl))
     trainer = DecoderTrainer(vae_model, decoder, base_fn, optimizer, scheduler, args.max_grad_norm,
