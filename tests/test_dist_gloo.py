@@ -90,3 +90,72 @@ def test_two_rank_gradient_exchange(tmp_path):
             continue
         assert torch.allclose(r0["end"][k], r1["end"][k], atol=1e-7), k
     assert not torch.equal(r0["end"]["feature_compress.1.running_mean"], r1["end"]["feature_compress.1.running_mean"])
+
+
+def _accum_data(rank, k):
+    g = torch.Generator().manual_seed(50 + 10 * k + rank)
+    return torch.randn(3, 16, 16, 16, generator=g) * 3, (torch.rand(3, 5, generator=g) < 0.3).float()
+
+
+def _worker_accum(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(200 + rank)
+    dec = M.create_attention_decoder(16, 16, 16, 5, attention_config={})
+    for m in dec.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0
+    opt = torch.optim.SGD(dec.parameters(), lr=0.1)
+    tr = DecoderTrainer(_IdentityVAE(), dec, nn.BCEWithLogitsLoss(), opt, None, max_grad_norm=0.02,
+                        gradient_accumulation_steps=2)
+    start = {k: v.clone() for k, v in dec.state_dict().items()}
+    for k in range(4):
+        tr.step(*_accum_data(rank, k))
+    tr.flush()
+    torch.save({"start": start, "end": dec.state_dict()}, os.path.join(out_dir, f"a{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_accumulation_matches_the_reference_loop(tmp_path):
+    """gradient_accumulation_steps = 2 on two ranks against a one-process emulation of the reference under DDP
+    (train_decoder.py:186-203): every backward is averaged over the ranks, the accumulated gradient is clipped
+    after every micro-step, the optimizer steps on every second one; BatchNorm statistics stay per rank."""
+    world, port = 2, _free_port()
+    mp.spawn(_worker_accum, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "a0.pt"), torch.load(tmp_path / "a1.pt")
+    dec = M.create_attention_decoder(16, 16, 16, 5, attention_config={})
+    for m in dec.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0
+    dec.load_state_dict(r0["start"])
+    dec.train()
+    opt = torch.optim.SGD(dec.parameters(), lr=0.1)
+    params = list(dec.parameters())
+    acc = [torch.zeros_like(p) for p in params]
+    loss_fn = nn.BCEWithLogitsLoss()
+    for k in range(4):
+        mean = [torch.zeros_like(p) for p in params]
+        for rank in range(world):
+            x, y = _accum_data(rank, k)
+            grads = torch.autograd.grad(loss_fn(dec(x), y) / 2, params)
+            for m_, g_ in zip(mean, grads):
+                m_ += g_ / world
+        for a_, m_ in zip(acc, mean):
+            a_ += m_
+        norm = torch.linalg.vector_norm(torch.stack([a_.norm() for a_ in acc]))
+        coef = torch.clamp(0.02 / (norm + 1e-6), max=1.0)
+        for a_ in acc:
+            a_ *= coef
+        if (k + 1) % 2 == 0:
+            for p, a_ in zip(params, acc):
+                p.grad = a_.clone()
+            opt.step()
+            for a_ in acc:
+                a_.zero_()
+    want = dec.state_dict()
+    for k in want:
+        if "running_" in k or "num_batches" in k:
+            continue
+        assert torch.allclose(r0["end"][k], r1["end"][k], atol=1e-7), k
+        assert torch.allclose(r0["end"][k], want[k], atol=2e-6), (k, (r0["end"][k] - want[k]).abs().max())

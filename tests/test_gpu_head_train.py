@@ -330,3 +330,58 @@ def test_class_balanced_training_step(ctx, golden, train_golden):
     l0 = tr.step(lat.cuda(), tgt.cuda()).item()
     tr.flush()
     assert l0 > 0 and torch.isfinite(torch.tensor(l0))
+
+
+def test_gradient_accumulation_follows_the_reference_loop(golden):
+    """gradient_accumulation_steps = 2: the reference (train_decoder.py:186-203) scales the loss by 1/2, clips the
+    accumulated gradient after EVERY backward and steps on every second one.  DecoderTrainer (native step) against
+    a literal transcription of that loop on the PyTorch graph of the same module."""
+    from vae_tagger_b200 import modules as M
+    from vae_tagger_b200.improved_losses import FocalLoss
+    from vae_tagger_b200.train_decoder import DecoderTrainer
+
+    class FrozenLatent(torch.nn.Module):
+        def encode(self, x):
+            return x
+
+    sd = full_sd(golden)
+    g = torch.Generator().manual_seed(31)
+    lat = [torch.randn(2, 16, 16, 16, generator=g).cuda() * 3 for _ in range(4)]     # large: the clip is active
+    tgt = [(torch.rand(2, 11, generator=g) < 0.3).float().cuda() for _ in range(4)]
+
+    def fresh():
+        dec = M.create_attention_decoder(16, 16, 16, 11, attention_config={"attention_dropout": 0.0})
+        dec.load_state_dict(sd)
+        dec = dec.cuda()
+        for mod in dec.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        return dec, torch.optim.AdamW(dec.parameters(), lr=1e-3, weight_decay=1e-2)
+
+    max_norm = 0.05
+    dec_n, opt_n = fresh()
+    tr = DecoderTrainer(FrozenLatent(), dec_n, FocalLoss(1.0, 2.0), opt_n, None, max_grad_norm=max_norm,
+                        gradient_accumulation_steps=2, native_step=True)
+    for x, y in zip(lat, tgt):
+        tr.step(x, y)
+    tr.flush()
+
+    dec_r, opt_r = fresh()
+    loss_fn = FocalLoss(1.0, 2.0)
+    dec_r.train()
+    for step, (x, y) in enumerate(zip(lat, tgt)):
+        with torch.enable_grad():
+            loss = loss_fn(dec_r(x), y) / 2
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(dec_r.parameters(), max_norm)
+        if (step + 1) % 2 == 0:
+            opt_r.step()
+            opt_r.zero_grad()
+    bad = {}
+    for (k, a), (_, b) in zip(dec_n.state_dict().items(), dec_r.state_dict().items()):
+        if k in ZERO_BY_CONSTRUCTION or k.endswith("num_batches_tracked"):
+            continue
+        d = (a - b).abs()
+        if d.mean().item() > 1e-4 or d.max().item() > 4.5e-3:
+            bad[k] = (d.mean().item(), d.max().item())
+    assert not bad, bad

@@ -274,7 +274,9 @@ def get_vae_config(resolution, use_quant_conv, use_post_quant_conv):
 def get_image_paths(path):
     """Image files under a directory (recursive, de-duplicated) or a single image file."""
     if os.path.isdir(path):
-        found = {p.resolve() for p in Path(path).rglob("*") if p.is_file() and p.suffix.lower() in IMAGE_EXTENSIONS}
+        # the reference globs "*<ext>" and "*<EXT>" (modules.py:263-268): all-lower or all-upper extensions only
+        both = IMAGE_EXTENSIONS + tuple(e.upper() for e in IMAGE_EXTENSIONS)
+        found = {p.resolve() for p in Path(path).rglob("*") if p.is_file() and p.name.endswith(both)}
         return list(found)
     if os.path.isfile(path):
         if path.lower().endswith(IMAGE_EXTENSIONS):

@@ -85,6 +85,7 @@ class DecoderTrainer:
             off += p.numel()
         self.buffers = [b for b in decoder.buffers() if b.is_floating_point()]
         self._pending = None
+        self._averaged = False
         self._micro = 0
         if self.world > 1:  # initial parameter broadcast (DDP does the same at wrap time)
             for t in list(decoder.parameters()) + list(decoder.buffers()):
@@ -193,7 +194,8 @@ class DecoderTrainer:
         """Wait for the in-flight all-reduce (if any), average, clip, step the optimizer."""
         if self._pending is None:
             return
-        if self.world > 1:
+        averaged, self._averaged = self._averaged, False
+        if self.world > 1 and not averaged:
             self._pending.wait()
             if not self.native:
                 self.flat_grad.div_(self.world)
@@ -203,7 +205,7 @@ class DecoderTrainer:
             self._t += 1
             self.ctx.adamw_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr=g["lr"],
                                 betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], step=self._t,
-                                grad_scale=1.0 / self.world, max_norm=float(self.max_grad_norm or 0.0), zero_grad=True)
+                                grad_scale=1.0 if averaged else 1.0 / self.world, max_norm=float(self.max_grad_norm or 0.0), zero_grad=True)
             self.decoder._native_key = None
             self.opt._opt_called = True                      # the scheduler only checks that a step happened
             if self.sched is not None:
@@ -225,6 +227,12 @@ class DecoderTrainer:
             for b in self.buffers:
                 dist.broadcast(b, src=0, group=self.pg)
         self.decoder.train()
+        # gradient_accumulation_steps > 1, reference semantics (train_decoder.py:193-203): DDP averages every
+        # backward, and the ACCUMULATED gradient is clipped after every micro-step, not only before the update
+        exact_accum = self.accum > 1
+        if exact_accum:
+            prev = self.flat_grad.clone()
+            self.flat_grad.zero_()
         if self.native:
             loss = self._native_forward_backward(latent, labels)
         else:
@@ -232,7 +240,18 @@ class DecoderTrainer:
             loss = self.loss_fn(logits, labels) / self.accum
             loss.backward()                              # accumulates into the flat bucket views
         self._micro += 1
-        if self._micro % self.accum == 0:
+        boundary = self._micro % self.accum == 0
+        if exact_accum:
+            if self.world > 1:
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+                self.flat_grad.div_(self.world)
+            self.flat_grad.add_(prev)
+            if boundary:
+                self._pending, self._averaged = True, True   # clipped (once more) and applied by finish_update
+            elif self.max_grad_norm and self.max_grad_norm > 0:
+                norm = torch.linalg.vector_norm(self.flat_grad)
+                self.flat_grad.mul_(torch.clamp(self.max_grad_norm / (norm + 1e-6), max=1.0))
+        elif boundary:
             self._launch_allreduce()
         return loss.detach()
 
