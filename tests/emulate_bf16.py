@@ -1,7 +1,7 @@
 """CPU emulation of the bf16 pipeline's rounding points on top of the fp32 oracle modules
 (development aid: predicts the GPU path's error vs the oracle and its sensitivity).
 
-    python tools/emulate_bf16.py [resolution]
+    python tests/emulate_bf16.py [resolution]
 """
 import math
 import os

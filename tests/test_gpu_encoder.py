@@ -63,7 +63,7 @@ def test_encoder_bf16_mode(pair, B, H, W):
 def test_micro_batching(pair):
     """Splitting a batch into micro-batches changes only the order of the fp64 statistics atomics.  In
     fp32 mode that is invisible (<= 1e-6).  In bf16 mode a last-bit change flips bf16 roundings, and
-    every flip re-draws the rounding noise downstream (tools/emulate_bf16.py: a 1e-7 input perturbation
+    every flip re-draws the rounding noise downstream (tests/emulate_bf16.py: a 1e-7 input perturbation
     moves the bf16 result by ~9e-3), so two bf16 runs agree only to the bf16 noise level -- both must
     still meet the bar against the oracle."""
     oracle, wrap = pair

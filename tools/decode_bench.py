@@ -1,6 +1,6 @@
 """Throughput of the native VAE decoder: images/s for ``DiffusersVAEWrapper.decode`` at
---res (latent res/8), batch B, bf16 tensor-core mode, with the algorithmic FLOP roofline and the bf16 error
-against the fp32 oracle at a small size.
+--res (latent res/8), batch B, bf16 tensor-core mode, with the algorithmic FLOP roofline (parity against the
+oracle is the tests' job: tests/test_gpu_decoder.py).
 
     python tools/decode_bench.py [--res 1024] [--batch 8] [--steps 5]
 """
@@ -70,16 +70,6 @@ def main():
     peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                         "MEASURED_PEAKS.json")))
     peak = float(peaks["bf16_tflops_sustained"])
-    # bf16 error against the fp32 oracle (CPU), small size
-    from oracle.decoder import make_oracle_decoder, oracle_wrapper_decode
-
-    dec = make_oracle_decoder(1)
-    wrap.vae.load_state_dict({"decoder." + k: v for k, v in dec.state_dict().items()}, strict=False)
-    zs = torch.randn(2, 16, 32, 32, generator=torch.Generator().manual_seed(3)) * 0.36 + 0.12
-    with torch.no_grad():
-        ref = oracle_wrapper_decode(dec, zs)
-    got = wrap.decode(zs.cuda()).cpu()
-    err = ((got - ref).norm() / ref.norm()).item()
     print(json.dumps({
         "metric": "images/s VAE decode bf16", "workload": f"latent {h}x{h} -> {a.res}x{a.res}, batch {a.batch}",
         "value": round(a.batch / ms * 1e3, 2), "ms_per_step": round(ms, 3),
@@ -87,7 +77,6 @@ def main():
         "roofline": {"bound": "tensor", "achieved": round(flops / ms / 1e9, 1), "peak": peak, "unit": "TFLOP/s",
                      "frac": round(flops / ms / 1e9 / peak, 4), "algorithmic_flop_per_image": flops / a.batch,
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
-        "bf16_rel_l2_vs_fp32_oracle_256px": err,
     }))
 
 

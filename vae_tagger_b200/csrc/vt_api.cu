@@ -358,7 +358,7 @@ void free_packed(vt_ctx* c) {
 //   * every *bounded* MMA operand -- GroupNorm+SiLU outputs, the normalised image patches, q/k/v, softmax
 //     probabilities, the attention output, and all weights that multiply them -- is fp16 (11-bit
 //     mantissa): the operand rounding that dominates the pipeline's error shrinks 8x.  Measured with
-//     tools/emulate_bf16.py against the fp32 oracle: all-bf16 operands 1.06e-2 latent rel-L2 (over the
+//     tests/emulate_bf16.py against the fp32 oracle: all-bf16 operands 1.06e-2 latent rel-L2 (over the
 //     1e-2 bar), fp16 bounded operands + bf16 storage 0.80e-2.  The reference itself infers under
 //     fp16 autocast (infer_full.py:100);
 //   * operands that ARE raw activations (downsample conv input, 1x1 shortcut input) stay bf16, with

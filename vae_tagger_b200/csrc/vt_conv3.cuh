@@ -550,7 +550,7 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int c = 0; c < nchunks; ++c) {
                 // SiLU(t) = t*sigmoid(t) = h + h*tanh(h) with h = t/2: the halving is folded into the per-channel
                 // scale/shift, h is rounded to fp16 and tanh / fma run on half2 (one MUFU per two elements);
-                // tools/emulate_bf16.py: no measurable change of the latent error vs the exp/rcp form
+                // tests/emulate_bf16.py: no measurable change of the latent error vs the exp/rcp form
                 float sc[8], sh[8];
                 {
                     const float half_if_silu = P.gn_silu ? 0.5f : 1.0f;
