@@ -84,16 +84,40 @@ def classifier(sd: dict, f: torch.Tensor, prefix="classifier.") -> torch.Tensor:
     return F.linear(f, sd[prefix + "12.weight"], sd[prefix + "12.bias"])
 
 
-def attention_decoder_logits(sd: dict, latent: torch.Tensor, heads: int = 8,
-                             use_spatial_attention=True, use_self_attention=True) -> torch.Tensor:
-    """AttentionClassificationDecoder.forward (modules.py:424-468), cross-attention off."""
+def cross_attention(sd: dict, query: torch.Tensor, key_value: torch.Tensor, heads: int = 8,
+                    prefix="cross_attention.") -> torch.Tensor:
+    """CrossAttention.forward (modules.py:105-122): one query per image over the spatial tokens, + residual."""
+    b = query.shape[0]
+    emb = sd[prefix + "q_proj.weight"].shape[0]
+    hd = emb // heads
+
+    def proj(name, t):
+        return F.linear(t, sd[prefix + name + ".weight"], sd[prefix + name + ".bias"])
+
+    q = proj("q_proj", query).unsqueeze(1).reshape(b, 1, heads, hd).transpose(1, 2)
+    k = proj("k_proj", key_value).reshape(b, -1, heads, hd).transpose(1, 2)
+    v = proj("v_proj", key_value).reshape(b, -1, heads, hd).transpose(1, 2)
+    p = torch.softmax(torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(hd), dim=-1)
+    o = torch.matmul(p, v).transpose(1, 2).reshape(b, emb)
+    return proj("out_proj", o) + query
+
+
+def attention_decoder_logits(sd: dict, latent: torch.Tensor, heads: int = 8, use_spatial_attention=True,
+                             use_self_attention=True, use_cross_attention=False) -> torch.Tensor:
+    """AttentionClassificationDecoder.forward (modules.py:424-468)."""
     x = latent
     if use_spatial_attention:
         x = spatial_attention(sd, x)
     x = feature_compress(sd, x)
     if use_self_attention:
         x = self_attention(sd, x, heads)
-    return classifier(sd, x.reshape(x.shape[0], -1))
+    flat = x.reshape(x.shape[0], -1)
+    if use_cross_attention:   # modules.py:450-459
+        query = F.linear(flat, sd["query_generator.weight"], sd["query_generator.bias"])
+        tokens = x.reshape(x.shape[0], x.shape[1], -1).transpose(1, 2)
+        attended = cross_attention(sd, query, tokens, heads)
+        flat = flat + attended.mean(dim=1, keepdim=True).expand_as(flat)
+    return classifier(sd, flat)
 
 
 def plain_decoder_logits(sd: dict, latent: torch.Tensor) -> torch.Tensor:

@@ -116,6 +116,22 @@ def main():
                     "grads": {k: digest(p.grad) for k, p in pdec.named_parameters()},
                     "param_order": [k for k, _ in pdec.named_parameters()]}
 
+    # --use_cross_attention head (modules.py:388-395, :450-459), eval mode: the shared parameters are those of
+    # head_golden.pt, the cross-attention / query_generator parameters are stored here
+    torch.manual_seed(16)
+    with quiet:
+        xdec = ref_modules.create_attention_decoder(16, 24, 40, 11, attention_config={"use_cross_attention": True})
+    xdec.load_state_dict(sd, strict=False)
+    xdec.eval()
+    lat = torch.randn(3, 16, 24, 40) * 0.5 + 0.1
+    with torch.no_grad(), quiet:
+        xl = xdec(lat)
+    out["cross_attention_head"] = {
+        "extra_state_dict": {k: v.clone() for k, v in xdec.state_dict().items()
+                             if k.startswith(("cross_attention.", "query_generator."))},
+        "latent": lat, "logits": xl,
+    }
+
     # ClassBalancedLoss (improved_losses.py:58-72) value and gradient
     torch.manual_seed(15)
     x = (torch.randn(6, 11) * 2).requires_grad_(True)

@@ -118,3 +118,37 @@ def test_head_extremes(ctx, golden):
         assert torch.equal(out["count"].cpu(), (torch.sigmoid(logits) >= 0.5).sum(1).to(torch.int32))
     with pytest.raises(_native.NativeError):
         ctx.configure_head(_native.HEAD_ATTENTION, latent_channels=16, num_classes=16385)
+
+
+def test_cross_attention_head_native(golden, train_golden):
+    """--use_cross_attention (modules.py:388-395, :450-459) runs as native kernels in inference: against the
+    reference module's own logits; training with it keeps the PyTorch graph and says so."""
+    from vae_tagger_b200 import _native
+    from vae_tagger_b200.train_decoder import DecoderTrainer
+
+    c = train_golden["cross_attention_head"]
+    sd = full_sd(golden, "att_T11_64x64")
+    sd.update(c["extra_state_dict"])
+    dec = M.create_attention_decoder(16, 24, 40, 11, attention_config={"use_cross_attention": True})
+    assert sorted(dec.state_dict().keys()) == sorted(sd.keys())
+    dec.load_state_dict(sd)
+    dec = dec.cuda().eval()
+    assert dec._use_native()
+    logits = dec(c["latent"].cuda()).cpu()
+    assert rel(logits, c["logits"]) < 2e-5, rel(logits, c["logits"])
+    conf, idx = dec.get_confidence(c["latent"].cuda())
+    assert (conf.cpu() - torch.sigmoid(c["logits"]).sort(descending=True).values).abs().max().item() < 1e-6
+    opt = torch.optim.AdamW(dec.parameters(), lr=1e-3)
+
+    class FrozenLatent(torch.nn.Module):
+        def encode(self, x):
+            return x
+
+    with pytest.raises(_native.NativeError):
+        DecoderTrainer(FrozenLatent(), dec, torch.nn.BCEWithLogitsLoss(), opt, None, native_step=True)
+    tr = DecoderTrainer(FrozenLatent(), dec, torch.nn.BCEWithLogitsLoss(), opt, None)
+    assert not tr.native
+    y = (torch.rand(3, 11) < 0.3).float().cuda()
+    l0 = tr.step(c["latent"].cuda(), y).item()
+    tr.flush()
+    assert l0 > 0

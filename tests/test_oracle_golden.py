@@ -183,3 +183,13 @@ def test_class_balanced_loss_oracle_and_module(train_golden):
         loss.backward()
         torch.testing.assert_close(loss.detach(), g["loss"], atol=1e-7, rtol=1e-6)
         torch.testing.assert_close(x.grad, g["grad"], atol=1e-8, rtol=1e-6)
+
+
+def test_cross_attention_head_oracle(golden, train_golden):
+    """--use_cross_attention (modules.py:388-395, :450-459) against the reference module's own logits."""
+    c = train_golden["cross_attention_head"]
+    sd = full_sd(golden, "att_T11_64x64")
+    sd.update(c["extra_state_dict"])
+    logits = OH.attention_decoder_logits(sd, c["latent"], use_cross_attention=True)
+    torch.testing.assert_close(logits, c["logits"], atol=1e-5, rtol=1e-5)
+    assert not torch.allclose(OH.attention_decoder_logits(sd, c["latent"]), c["logits"], atol=1e-3)   # the branch matters

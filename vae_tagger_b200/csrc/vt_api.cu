@@ -1141,6 +1141,8 @@ int vt_head_configure(vt_ctx* c, const vt_head_config* cfg) {
     VT_CHECK(cfg->latent_channels >= 8 && cfg->latent_channels <= 32 && cfg->latent_channels % 8 == 0,
              "latent_channels must be 8, 16, 24 or 32");
     VT_CHECK(cfg->num_classes >= 1 && cfg->num_classes <= 16384, "num_classes must be in 1..16384");
+    if (cfg->kind == VT_HEAD_ATTENTION && cfg->use_cross_attention)
+        VT_CHECK(cfg->attention_heads == 8, "the cross-attention branch needs attention_heads = 8 (embed 256, head_dim 32)");
     if (cfg->kind == VT_HEAD_ATTENTION && cfg->use_self_attention)
         VT_CHECK(cfg->attention_heads >= 1 && (cfg->latent_channels / 2) % cfg->attention_heads == 0,
                  "embed_dim must be divisible by num_heads (modules.py:56)");
@@ -1178,6 +1180,18 @@ int vt_head_finalize(vt_ctx* c) {
             }
             VT_TRY(hcheck(c, "self_attention_post.norm.weight", {E}));
             VT_TRY(hcheck(c, "self_attention_post.norm.bias", {E}));
+        }
+        if (h.use_cross_attention) {
+            VT_TRY(hcheck(c, "query_generator.weight", {512, E * 64}));
+            VT_TRY(hcheck(c, "query_generator.bias", {512}));
+            VT_TRY(hcheck(c, "cross_attention.q_proj.weight", {256, 512}));
+            VT_TRY(hcheck(c, "cross_attention.q_proj.bias", {256}));
+            for (const char* k : {"k_proj", "v_proj"}) {
+                VT_TRY(hcheck(c, std::string("cross_attention.") + k + ".weight", {256, E}));
+                VT_TRY(hcheck(c, std::string("cross_attention.") + k + ".bias", {256}));
+            }
+            VT_TRY(hcheck(c, "cross_attention.out_proj.weight", {512, 256}));
+            VT_TRY(hcheck(c, "cross_attention.out_proj.bias", {512}));
         }
         const int dims[5] = {E * 64, 1024, 512, 256, T};
         const int lin[4] = {0, 4, 8, 12}, ln[3] = {1, 5, 9};
@@ -1229,6 +1243,7 @@ static int tag_impl(vt_ctx* c, const vt_tag_args* a, DevBuf& hws) {
     const size_t o_pooled = take(static_cast<size_t>(B) * E * 64), o_feat = take(static_cast<size_t>(B) * 1024);
     const size_t o_a = take(static_cast<size_t>(B) * 1024), o_b = take(static_cast<size_t>(B) * 1024);
     const size_t o_logits = take(static_cast<size_t>(B) * T);
+    const size_t o_x1 = take(static_cast<size_t>(B) * (512 + 256 + 256 + 512)), o_feat2 = take(static_cast<size_t>(B) * 1024);
     VT_TRY(hws.ensure(off * sizeof(float)));
     float* ws = static_cast<float*>(hws.p);
     float* logits = a->logits ? a->logits : ws + o_logits;
@@ -1258,6 +1273,25 @@ static int tag_impl(vt_ctx* c, const vt_tag_args* a, DevBuf& hws) {
         const int lin[4] = {0, 4, 8, 12}, ln[3] = {1, 5, 9};
         const float* cur = ws + o_feat;
         float* bufs[2] = {ws + o_a, ws + o_b};
+        if (h.use_cross_attention) {
+            // modules.py:450-459: query = query_generator(flat); attended = CrossAttention(query, tokens);
+            // flat += mean(attended) -- the Linear layers are the batched warp-per-neuron kernel
+            float* query = ws + o_x1;
+            float* qp = query + static_cast<size_t>(B) * 512;
+            float* att = qp + static_cast<size_t>(B) * 256;
+            float* outp = att + static_cast<size_t>(B) * 256;
+            VT_TRY(launch_head_linear(cur, hp(c, "query_generator.weight"), hp(c, "query_generator.bias"), query, B,
+                                      E * 64, 512, s, pf));
+            VT_TRY(launch_head_linear(query, hp(c, "cross_attention.q_proj.weight"), hp(c, "cross_attention.q_proj.bias"),
+                                      qp, B, 512, 256, s, pf));
+            VT_TRY(launch_head_cross_attention(cur, qp, hp(c, "cross_attention.k_proj.weight"),
+                                               hp(c, "cross_attention.k_proj.bias"), hp(c, "cross_attention.v_proj.weight"),
+                                               hp(c, "cross_attention.v_proj.bias"), att, B, E, h.attention_heads, s, pf));
+            VT_TRY(launch_head_linear(att, hp(c, "cross_attention.out_proj.weight"),
+                                      hp(c, "cross_attention.out_proj.bias"), outp, B, 256, 512, s, pf));
+            VT_TRY(launch_head_cross_add(outp, query, cur, ws + o_feat2, B, 512, E * 64, s, pf));
+            cur = ws + o_feat2;
+        }
         for (int i = 0; i < 4; ++i) {
             float* out = i == 3 ? logits : bufs[i & 1];
             VT_TRY(launch_head_linear(cur, hp(c, "classifier." + std::to_string(lin[i]) + ".weight"),
@@ -1324,6 +1358,7 @@ int vt_head_train_step(vt_ctx* c, const vt_head_train_args* a) {
     VT_CHECK(a->latent && a->targets && a->params, "latent, targets and params are required");
     VT_CHECK(a->batch > 0 && a->lat_h > 0 && a->lat_w > 0, "bad latent arguments");
     VT_CHECK(a->attention_dropout >= 0.f && a->attention_dropout < 1.f, "attention_dropout must be in [0,1)");
+    VT_CHECK(!c->hcfg.use_cross_attention, "the cross-attention branch has no training kernels");
     if (c->hcfg.kind == VT_HEAD_ATTENTION)
         VT_CHECK(1LL * a->batch * a->lat_h * a->lat_w > 1, "BatchNorm in train mode needs more than one value per channel");
     VT_TRY(c->hws.ensure(head_train_workspace_floats(c->hcfg, a->batch, a->lat_h, a->lat_w) * sizeof(float)));

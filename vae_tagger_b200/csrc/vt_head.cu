@@ -247,6 +247,65 @@ __global__ void __launch_bounds__(64) head_mhsa_kernel(const float* __restrict__
     }
 }
 
+// ---- CrossAttention (modules.py:93-122), the optional --use_cross_attention branch (modules.py:450-459):
+// one query vector per image (q = q_proj(query_generator(flat)), computed by the Linear kernel) attends over
+// the 64 tokens of the 8x8 feature grid.  One CTA per image, thread d = one of the 256 embedding dims:
+// k/v projections of the tokens (E -> 256), per-head scores (head_dim 32, warp = head), softmax over the
+// 64 keys, weighted sum of the values.  feat: [N][E*64] (channel-major tokens), out: [N][256].
+__global__ void __launch_bounds__(256) head_cross_attn_kernel(const float* __restrict__ feat,
+                                                              const float* __restrict__ q,   // [N][256]
+                                                              const float* __restrict__ wk, const float* __restrict__ bk,
+                                                              const float* __restrict__ wv, const float* __restrict__ bv,
+                                                              float* __restrict__ out, int E, int heads) {
+    __shared__ float tok[16][64];
+    __shared__ float sc[8][64];
+    const int n = blockIdx.x, d = threadIdx.x;
+    const int hd = 256 / heads, h = d / hd;
+    for (int i = d; i < E * 64; i += 256) tok[i / 64][i % 64] = feat[1LL * n * E * 64 + i];
+    __syncthreads();
+    float kw[16], vw[16];
+    for (int e = 0; e < E; ++e) {
+        kw[e] = wk[d * E + e];
+        vw[e] = wv[d * E + e];
+    }
+    const float qd = q[1LL * n * 256 + d] / sqrtf(static_cast<float>(hd));
+    // scores[h][j] = sum over the head's dims of q[d] * k[j][d]: each thread adds its dim (shared-memory atomics
+    // would be order dependent: reduce inside the warp instead; hd = 32 -> one warp per head)
+    const int lane = d & 31;
+    for (int j = 0; j < 64; ++j) {
+        float kj = bk[d];
+        for (int e = 0; e < E; ++e) kj = fmaf(kw[e], tok[e][j], kj);
+        float part = qd * kj;
+        for (int o = hd / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o, 32);
+        if (lane % hd == 0) sc[h][j] = part;
+    }
+    __syncthreads();
+    float m = -CUDART_INF_F;
+    for (int j = 0; j < 64; ++j) m = fmaxf(m, sc[h][j]);
+    float sum = 0.f, acc = 0.f;
+    for (int j = 0; j < 64; ++j) {
+        const float p = expf(sc[h][j] - m);
+        float vj = bv[d];
+        for (int e = 0; e < E; ++e) vj = fmaf(vw[e], tok[e][j], vj);
+        sum += p;
+        acc = fmaf(p, vj, acc);
+    }
+    out[1LL * n * 256 + d] = acc / sum;
+}
+
+// flat[n][:] += mean_i(attended[n][i] + query[n][i])   (modules.py:118,459: out_proj output + residual query,
+// its mean over the 512 dims broadcast onto every feature).  One CTA per image.
+__global__ void __launch_bounds__(256) head_cross_add_kernel(const float* __restrict__ attended,
+                                                             const float* __restrict__ query, const float* __restrict__ in,
+                                                             float* __restrict__ out, int Q, int F) {
+    __shared__ float red[8];
+    const int n = blockIdx.x;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < Q; i += 256) s += attended[1LL * n * Q + i] + query[1LL * n * Q + i];
+    const float mean = block_sum256(s, red) / static_cast<float>(Q);
+    for (int i = threadIdx.x; i < F; i += 256) out[1LL * n * F + i] = in[1LL * n * F + i] + mean;
+}
+
 // ---- AdaptiveAvgPool2d((OH,OW)) for the plain ClassificationDecoder (modules.py:313, :339-340):
 // out[n][c*OH*OW + cell]
 __global__ void __launch_bounds__(64) head_adaptive_pool_kernel(const float* __restrict__ x, float* __restrict__ out,
@@ -458,6 +517,27 @@ int launch_head_mhsa(const float* pooled, const float* const* p /*10 pointers*/,
     profiler_begin(prof, KC_HEAD, s, 0, 8.0 * N * E * 64);
     head_mhsa_kernel<<<N, 64, 0, s>>>(pooled, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], feat, E,
                                       heads, enabled);
+    profiler_end(prof, KC_HEAD, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_head_cross_attention(const float* feat, const float* q, const float* wk, const float* bk, const float* wv,
+                                const float* bv, float* out, int N, int E, int heads, cudaStream_t s,
+                                Profiler* prof) {
+    VT_CHECK(E <= 16 && heads >= 1 && 256 % heads == 0 && (256 / heads == 32),
+             "cross-attention kernel: embed 256 with 8 heads of 32 (modules.py:396-398)");
+    profiler_begin(prof, KC_HEAD, s, 0, 4.0 * N * (E * 64 + 512));
+    head_cross_attn_kernel<<<N, 256, 0, s>>>(feat, q, wk, bk, wv, bv, out, E, heads);
+    profiler_end(prof, KC_HEAD, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_head_cross_add(const float* attended, const float* query, const float* in, float* out, int N, int Q, int F,
+                          cudaStream_t s, Profiler* prof) {
+    profiler_begin(prof, KC_HEAD, s, 0, 4.0 * N * (2 * Q + 2 * F));
+    head_cross_add_kernel<<<N, 256, 0, s>>>(attended, query, in, out, Q, F);
     profiler_end(prof, KC_HEAD, s);
     VT_CUDA(cudaGetLastError());
     return 0;

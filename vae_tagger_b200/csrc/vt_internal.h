@@ -196,6 +196,10 @@ int launch_head_compress(const float* x, const float* cw, const float* cb, const
                          int W, cudaStream_t, Profiler*);
 int launch_head_mhsa(const float* pooled, const float* const* params10, float* feat, int N, int E, int heads,
                      int enabled, cudaStream_t, Profiler*);
+int launch_head_cross_attention(const float* feat, const float* q, const float* wk, const float* bk, const float* wv,
+                                const float* bv, float* out, int N, int E, int heads, cudaStream_t, Profiler*);
+int launch_head_cross_add(const float* attended, const float* query, const float* in, float* out, int N, int Q, int F,
+                          cudaStream_t, Profiler*);
 int launch_head_adaptive_pool(const float* x, float* out, int N, int C, int H, int W, int OH, int OW, cudaStream_t,
                               Profiler*);
 int launch_head_linear(const float* x, const float* w, const float* b, float* y, int B, int I, int O, cudaStream_t,

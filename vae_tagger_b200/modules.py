@@ -216,11 +216,7 @@ class AttentionClassificationDecoder(_NativeHeadMixin, nn.Module):
         return _native.HEAD_ATTENTION, dict(
             latent_channels=self.latent_channels, num_classes=self.num_classes,
             use_spatial_attention=self.use_spatial_attention, use_self_attention=self.use_self_attention,
-            attention_heads=self.attention_heads)
-
-    def _use_native(self) -> bool:
-        # the optional cross-attention branch has no kernel yet: keep it on the differentiable graph
-        return super()._use_native() and not self.use_cross_attention
+            attention_heads=self.attention_heads, use_cross_attention=self.use_cross_attention)
 
     def forward(self, latent_vectors):
         if self._use_native():
