@@ -33,7 +33,8 @@ def pair():
     return make_pair()
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 128, 192), (1, 256, 256)])
+# (1, 1024, 1024): BASELINE configs[1] resolution, one image through the CPU oracle (a few seconds)
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 128, 192), (1, 256, 256), (1, 1024, 1024)])
 def test_encoder_fp32_mode(pair, B, H, W):
     oracle, wrap = pair
     x = synthetic_images(B, H, W)
@@ -47,7 +48,8 @@ def test_encoder_fp32_mode(pair, B, H, W):
 
 # (1, 576, 832): a reachable AspectRatioBucketing bucket (modules.py:188-222): 72x104 latent = ragged 8x16 / 8x32
 # tiles at every level, 7488 tokens = 58.5 query tiles (ragged key tile + an unpaired query tile in the attention)
-@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (3, 128, 192), (2, 256, 256), (1, 512, 512), (1, 576, 832)])
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (3, 128, 192), (2, 256, 256), (1, 512, 512), (1, 576, 832),
+                                   (1, 1024, 1024)])
 def test_encoder_bf16_mode(pair, B, H, W):
     oracle, wrap = pair
     x = synthetic_images(B, H, W)

@@ -204,3 +204,34 @@ def test_config1_512_batch1_fp32(golden):
     assert torch.equal(p >= 0.5, ref_p >= 0.5)
     assert torch.equal(idx.cpu()[0], torch.sort(ref_p[0], descending=True).indices) or \
         (ref_p[0].sort(descending=True).values.diff().abs().min().item() < 1e-5)
+
+
+def test_infer_vae_cli_matches_oracle(tmp_path, monkeypatch):
+    """infer_vae.py (reference :31-81): latent_vectors.json = flattened mode()*scale+shift per image, against the
+    oracle on the same host-transformed pixels (fp32 mode, rel-L2 <= 1e-4)."""
+    from PIL import Image
+    from safetensors.torch import save_file
+
+    from vae_tagger_b200 import infer_vae
+
+    oracle = make_oracle_vae(0)
+    save_file({k: v.contiguous() for k, v in oracle.state_dict().items()}, str(tmp_path / "vae.safetensors"))
+    (tmp_path / "vae.json").write_text(json.dumps(L.get_diffusers_vae_config()))
+    img_dir = tmp_path / "imgs"
+    img_dir.mkdir()
+    g = torch.Generator().manual_seed(2)
+    for i in range(3):
+        arr = torch.randint(0, 256, (40 + 16 * i, 72, 3), generator=g, dtype=torch.uint8).numpy()
+        Image.fromarray(arr).save(img_dir / f"im{i}.png")
+    monkeypatch.setenv("VT_B200_PRECISION", "fp32")
+    out = infer_vae.main(["--vae_checkpoint", str(tmp_path / "vae.safetensors"), "--vae_config_path",
+                          str(tmp_path / "vae.json"), "--image_path", str(img_dir), "--output_dir",
+                          str(tmp_path / "out"), "--resolution", "64", "--batch_size", "2"])
+    saved = json.loads((tmp_path / "out" / "latent_vectors.json").read_text())
+    assert saved.keys() == out.keys() and len(saved) == 3
+    tf = M.get_image_transform(64)
+    for path, vec in saved.items():
+        with torch.no_grad():
+            want = oracle_wrapper_encode(oracle, tf(Image.open(path).convert("RGB")).unsqueeze(0)).reshape(-1)
+        got = torch.tensor(vec)
+        assert got.numel() == 16 * 8 * 8 and rel(got, want) <= 1e-4
