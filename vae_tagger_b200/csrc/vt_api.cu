@@ -1244,6 +1244,7 @@ static int tag_impl(vt_ctx* c, const vt_tag_args* a, DevBuf& hws) {
     const size_t o_a = take(static_cast<size_t>(B) * 1024), o_b = take(static_cast<size_t>(B) * 1024);
     const size_t o_logits = take(static_cast<size_t>(B) * T);
     const size_t o_x1 = take(static_cast<size_t>(B) * (512 + 256 + 256 + 512)), o_feat2 = take(static_cast<size_t>(B) * 1024);
+    const size_t o_ao = take(static_cast<size_t>(B) * 64 * E);
     VT_TRY(hws.ensure(off * sizeof(float)));
     float* ws = static_cast<float*>(hws.p);
     float* logits = a->logits ? a->logits : ws + o_logits;
@@ -1267,7 +1268,7 @@ static int tag_impl(vt_ctx* c, const vt_tag_args* a, DevBuf& hws) {
                                hp(c, sp + "k_proj.weight"), hp(c, sp + "k_proj.bias"),
                                hp(c, sp + "v_proj.weight"), hp(c, sp + "v_proj.bias"),
                                hp(c, sp + "out_proj.weight"), hp(c, sp + "out_proj.bias")};
-        VT_TRY(launch_head_mhsa(ws + o_pooled, mp, ws + o_feat, B, E, h.use_self_attention ? h.attention_heads : 1,
+        VT_TRY(launch_head_mhsa(ws + o_pooled, mp, ws + o_feat, ws + o_ao, B, E, h.use_self_attention ? h.attention_heads : 1,
                                 h.use_self_attention, s, pf));
         const int dims[5] = {E * 64, 1024, 512, 256, T};
         const int lin[4] = {0, 4, 8, 12}, ln[3] = {1, 5, 9};

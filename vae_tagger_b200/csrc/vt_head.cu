@@ -172,25 +172,15 @@ __global__ void __launch_bounds__(256) head_compress_kernel(const float* __restr
 }
 
 // ---- MultiHeadSelfAttention on the 8x8 grid (modules.py:66-91): tokens [64][E], LN(E), q/k/v
-// E->E, heads x head_dim, softmax over 64 keys, out_proj + residual.  One CTA (64 threads, one per
-// token) per image; writes the flattened NCHW feature f[n][e*64 + token] (modules.py:448).
-// E <= 16.
-__global__ void __launch_bounds__(64) head_mhsa_kernel(const float* __restrict__ pooled,  // [N][E][64]
-                                                       const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                                                       const float* __restrict__ wq, const float* __restrict__ bq,
-                                                       const float* __restrict__ wk, const float* __restrict__ bk,
-                                                       const float* __restrict__ wv, const float* __restrict__ bv,
-                                                       const float* __restrict__ wo, const float* __restrict__ bo,
-                                                       float* __restrict__ feat, int E, int heads, int enabled) {
-    __shared__ float sk[64][17];
-    __shared__ float sv[64][17];
-    const int n = blockIdx.x, t = threadIdx.x;
+// E->E, heads x head_dim, softmax over 64 keys, out_proj + residual; E <= 16.
+// Two kernels: (1) one CTA per (head, image), one thread per query token: LayerNorm, this head's q/k/v,
+// softmax(q k^T / sqrt(hd)) v -> ao[n][t][e]  (8x the parallelism of a CTA per image -- the per-thread work is a
+// serial chain of 64 exponentials per head); (2) one CTA per image: out_proj + residual, written as the
+// flattened NCHW feature f[n][e*64 + token] (modules.py:448).
+__device__ __forceinline__ void mhsa_ln_token(const float* __restrict__ pooled, const float* __restrict__ ln_w,
+                                              const float* __restrict__ ln_b, int n, int E, int t, float* xn) {
     float xin[16];
     for (int e = 0; e < E; ++e) xin[e] = pooled[(1LL * n * E + e) * 64 + t];
-    if (!enabled) {
-        for (int e = 0; e < E; ++e) feat[1LL * n * E * 64 + e * 64 + t] = xin[e];
-        return;
-    }
     float mean = 0.f;
     for (int e = 0; e < E; ++e) mean += xin[e];
     mean /= static_cast<float>(E);
@@ -198,52 +188,76 @@ __global__ void __launch_bounds__(64) head_mhsa_kernel(const float* __restrict__
     for (int e = 0; e < E; ++e) var += (xin[e] - mean) * (xin[e] - mean);
     var /= static_cast<float>(E);
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
-    float xn[16], q[16];
     for (int e = 0; e < E; ++e) xn[e] = (xin[e] - mean) * rstd * ln_w[e] + ln_b[e];
-    for (int o = 0; o < E; ++o) {
+}
+
+__global__ void __launch_bounds__(64) head_mhsa_heads_kernel(const float* __restrict__ pooled,  // [N][E][64]
+                                                             const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                             const float* __restrict__ wq, const float* __restrict__ bq,
+                                                             const float* __restrict__ wk, const float* __restrict__ bk,
+                                                             const float* __restrict__ wv, const float* __restrict__ bv,
+                                                             float* __restrict__ ao,  // [N][64][E]
+                                                             int E, int heads) {
+    __shared__ float sk[64][17];
+    __shared__ float sv[64][17];
+    const int h = blockIdx.x, n = blockIdx.y, t = threadIdx.x;
+    const int hd = E / heads, c0 = h * hd;
+    float xn[16], q[16];
+    mhsa_ln_token(pooled, ln_w, ln_b, n, E, t, xn);
+    for (int d = 0; d < hd; ++d) {
+        const int o = c0 + d;
         float a = bq[o], b = bk[o], c = bv[o];
         for (int e = 0; e < E; ++e) {
             a = fmaf(wq[o * E + e], xn[e], a);
             b = fmaf(wk[o * E + e], xn[e], b);
             c = fmaf(wv[o * E + e], xn[e], c);
         }
-        q[o] = a;
-        sk[t][o] = b;
-        sv[t][o] = c;
+        q[d] = a;
+        sk[t][d] = b;
+        sv[t][d] = c;
     }
     __syncthreads();
-    const int hd = E / heads;
     const float scale = 1.0f / sqrtf(static_cast<float>(hd));
-    float ao[16];
-    for (int h = 0; h < heads; ++h) {
-        float sc[64];
-        float m = -CUDART_INF_F;
+    float sc[64];
+    float m = -CUDART_INF_F;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            float s = 0.f;
-            for (int d = 0; d < hd; ++d) s = fmaf(q[h * hd + d], sk[j][h * hd + d], s);
-            s *= scale;
-            sc[j] = s;
-            m = fmaxf(m, s);
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            sc[j] = expf(sc[j] - m);
-            sum += sc[j];
-        }
-        const float inv = 1.0f / sum;
-        for (int d = 0; d < hd; ++d) {
-            float o = 0.f;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) o = fmaf(sc[j] * inv, sv[j][h * hd + d], o);
-            ao[h * hd + d] = o;
-        }
+    for (int j = 0; j < 64; ++j) {
+        float s = 0.f;
+        for (int d = 0; d < hd; ++d) s = fmaf(q[d], sk[j][d], s);
+        s *= scale;
+        sc[j] = s;
+        m = fmaxf(m, s);
     }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        sc[j] = expf(sc[j] - m);
+        sum += sc[j];
+    }
+    const float inv = 1.0f / sum;
+    for (int d = 0; d < hd; ++d) {
+        float o = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) o = fmaf(sc[j] * inv, sv[j][d], o);
+        ao[(1LL * n * 64 + t) * E + c0 + d] = o;
+    }
+}
+
+__global__ void __launch_bounds__(64) head_mhsa_out_kernel_eval(const float* __restrict__ pooled,
+                                                                const float* __restrict__ ao,
+                                                                const float* __restrict__ wo, const float* __restrict__ bo,
+                                                                float* __restrict__ feat, int E, int enabled) {
+    const int n = blockIdx.x, t = threadIdx.x;
+    if (!enabled) {
+        for (int e = 0; e < E; ++e) feat[1LL * n * E * 64 + e * 64 + t] = pooled[(1LL * n * E + e) * 64 + t];
+        return;
+    }
+    float a[16];
+    for (int e = 0; e < E; ++e) a[e] = ao[(1LL * n * 64 + t) * E + e];
     for (int o = 0; o < E; ++o) {
-        float a = bo[o];
-        for (int e = 0; e < E; ++e) a = fmaf(wo[o * E + e], ao[e], a);
-        feat[1LL * n * E * 64 + o * 64 + t] = a + xin[o];
+        float r = bo[o];
+        for (int e = 0; e < E; ++e) r = fmaf(wo[o * E + e], a[e], r);
+        feat[1LL * n * E * 64 + o * 64 + t] = r + pooled[(1LL * n * E + o) * 64 + t];
     }
 }
 
@@ -511,12 +525,14 @@ int launch_head_compress(const float* x, const float* cw, const float* cb, const
     return 0;
 }
 
-int launch_head_mhsa(const float* pooled, const float* const* p /*10 pointers*/, float* feat, int N, int E,
-                     int heads, int enabled, cudaStream_t s, Profiler* prof) {
+int launch_head_mhsa(const float* pooled, const float* const* p /*10 pointers*/, float* feat, float* ao /*[N][64][E]*/,
+                     int N, int E, int heads, int enabled, cudaStream_t s, Profiler* prof) {
     VT_CHECK(E <= 16 && heads >= 1 && E % heads == 0, "self-attention embed dim must be <= 16 and divisible by heads");
     profiler_begin(prof, KC_HEAD, s, 0, 8.0 * N * E * 64);
-    head_mhsa_kernel<<<N, 64, 0, s>>>(pooled, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], feat, E,
-                                      heads, enabled);
+    if (enabled)
+        head_mhsa_heads_kernel<<<dim3(heads, N), 64, 0, s>>>(pooled, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], ao, E,
+                                                             heads);
+    head_mhsa_out_kernel_eval<<<N, 64, 0, s>>>(pooled, ao, p[8], p[9], feat, E, enabled);
     profiler_end(prof, KC_HEAD, s);
     VT_CUDA(cudaGetLastError());
     return 0;

@@ -194,8 +194,8 @@ int launch_head_spatial_attention(const float* latent, const float* w1, const fl
 int launch_head_compress(const float* x, const float* cw, const float* cb, const float* bn_w, const float* bn_b,
                          const float* bn_rm, const float* bn_rv, float bn_eps, float* pooled, int N, int C, int H,
                          int W, cudaStream_t, Profiler*);
-int launch_head_mhsa(const float* pooled, const float* const* params10, float* feat, int N, int E, int heads,
-                     int enabled, cudaStream_t, Profiler*);
+int launch_head_mhsa(const float* pooled, const float* const* params10, float* feat, float* ao /*[N][64][E] scratch*/,
+                     int N, int E, int heads, int enabled, cudaStream_t, Profiler*);
 int launch_head_cross_attention(const float* feat, const float* q, const float* wk, const float* bk, const float* wv,
                                 const float* bv, float* out, int N, int E, int heads, cudaStream_t, Profiler*);
 int launch_head_cross_add(const float* attended, const float* query, const float* in, float* out, int N, int Q, int F,
