@@ -13,7 +13,8 @@
 //   * PIL/Image.py Image.resize (12.2): an image more than 100 times taller than wide that shrinks vertically
 //     gets its vertical pass first.
 // The coefficient tables are computed on the host (they depend only on (in size, out size, filter)) and
-// cached on the device; the two passes are byte-streaming kernels: HBM/L2 bound, no tensor cores.
+// cached on the device; the two passes are byte-streaming kernels (no tensor cores).  The horizontal pass runs
+// on dp4a over three signed base-256 digits of the taps (VT_B200_RESIZE_SCALAR=1: the IMAD form).
 #include <math.h>
 
 #include <map>
@@ -105,6 +106,91 @@ __global__ void __launch_bounds__(kHBlock) resize_h_kernel(const unsigned char* 
     }
 }
 
+__device__ __forceinline__ int dp4a_u8s8(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// Horizontal pass on dp4a.  Same tiling as resize_h_kernel, but the staged span is de-interleaved into three byte
+// planes and the taps come as three signed base-256 digit words per group of four taps:
+//   sum_k c_k p_k = 65536 * dp4a(p, c2) + 256 * dp4a(p, c1) + dp4a(p, c0)      (exact: int32 wrap-around arithmetic)
+// A thread's window starts at an arbitrary pixel, so its four-pixel words are cut out of two aligned shared-memory
+// words with a funnel shift.  Per four taps, channel and row: 1 LDS.32 + 1 SHF + 3 DP4A instead of 4 LDS.U8 + 4 IMAD.
+template <int R>
+__global__ void __launch_bounds__(kHBlock) resize_h_dp4a_kernel(const unsigned char* __restrict__ src, long long src_pitch,
+                                                                unsigned char* __restrict__ dst, long long dst_pitch,
+                                                                const unsigned* __restrict__ kd,
+                                                                const int2* __restrict__ bounds, int out_w, int rows,
+                                                                int rows_per_cta, int plane_pitch) {
+    extern __shared__ __align__(16) unsigned char planes[];  // [R][3][plane_pitch]
+    const int x0 = blockIdx.x * kHBlock;
+    const int xx = x0 + threadIdx.x;
+    const bool live = xx < out_w;
+    const int2 b = live ? bounds[xx] : make_int2(0, 0);
+    const int first = bounds[x0].x;
+    const int xl = min(x0 + kHBlock, out_w) - 1;
+    const int npx = bounds[xl].x + bounds[xl].y - first;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    const int rel = b.x - first;
+    const int sh = (rel & 3) * 8;
+    const int ng = (b.y + 3) >> 2;
+    for (int r = r0; r < r1; r += R) {
+        const int nr = min(R, r1 - r);
+        __syncthreads();
+        for (int q = 0; q < nr; ++q) {
+            const unsigned char* row = src + (r + q) * src_pitch + 3LL * first;
+            unsigned char* pl = planes + q * 3 * plane_pitch;
+            for (int i = threadIdx.x; i < npx; i += kHBlock) {
+                pl[i] = row[3 * i];
+                pl[plane_pitch + i] = row[3 * i + 1];
+                pl[2 * plane_pitch + i] = row[3 * i + 2];
+            }
+        }
+        __syncthreads();
+        if (live) {
+            int S[R][3][3];
+            unsigned w0[R][3];
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    S[q][c][0] = S[q][c][1] = S[q][c][2] = 0;
+                    w0[q][c] = *reinterpret_cast<const unsigned*>(planes + (q * 3 + c) * plane_pitch + (rel & ~3));
+                }
+            for (int g = 0; g < ng; ++g) {
+                const unsigned k0 = kd[(1LL * g * 3 + 0) * out_w + xx];
+                const unsigned k1 = kd[(1LL * g * 3 + 1) * out_w + xx];
+                const unsigned k2 = kd[(1LL * g * 3 + 2) * out_w + xx];
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    if (q < nr) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const unsigned w1 = *reinterpret_cast<const unsigned*>(planes + (q * 3 + c) * plane_pitch +
+                                                                                   (rel & ~3) + 4 * (g + 1));
+                            const unsigned px = __funnelshift_r(w0[q][c], w1, sh);
+                            w0[q][c] = w1;
+                            S[q][c][0] = dp4a_u8s8(px, k0, S[q][c][0]);
+                            S[q][c][1] = dp4a_u8s8(px, k1, S[q][c][1]);
+                            S[q][c][2] = dp4a_u8s8(px, k2, S[q][c][2]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                if (q < nr) {
+                    unsigned char* o = dst + (r + q) * dst_pitch + 3LL * xx;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        o[c] = clip8((1 << (kPrecisionBits - 1)) + S[q][c][2] * 65536 + S[q][c][1] * 256 + S[q][c][0]);
+                }
+            }
+        }
+    }
+}
+
 // Vertical pass.  One thread per VEC bytes of an output row (a row is out_w*3 bytes: channels and pixels
 // are interchangeable here), grid (ceil(row_bytes/VEC/256), out_h).  kk: [out_h][ksize], bounds [out_h].
 template <int VEC>
@@ -157,6 +243,8 @@ struct ResizeTable {
     int ksize = 0, out_size = 0, max_span = 0;
     int* kk = nullptr;      // [out][ksize]
     int* kk_t = nullptr;    // [ksize][out]
+    unsigned* kd = nullptr; // [groups][3][out]: taps 4g..4g+3 as signed base-256 digits (digit d of four taps per word)
+    int groups = 0;         // ceil(ksize / 4)
     int2* bounds = nullptr; // [out]
     unsigned long long stamp = 0;
 };
@@ -174,6 +262,7 @@ void resize_cache_destroy(ResizeCache* c) {
     for (auto& kv : c->tables) {
         cudaFree(kv.second.kk);
         cudaFree(kv.second.kk_t);
+        cudaFree(kv.second.kd);
         cudaFree(kv.second.bounds);
     }
     if (c->tmp) cudaFree(c->tmp);
@@ -226,6 +315,7 @@ static int get_table(ResizeCache* c, int in_size, int out_size, int filter, cons
                 if (j->second.stamp < old->second.stamp) old = j;
             cudaFree(old->second.kk);
             cudaFree(old->second.kk_t);
+            cudaFree(old->second.kd);
             cudaFree(old->second.bounds);
             c->tables.erase(old);
         }
@@ -241,6 +331,22 @@ static int get_table(ResizeCache* c, int in_size, int out_size, int filter, cons
             const int xl = std::min(x0 + kHBlock, out_size) - 1;
             t.max_span = std::max(t.max_span, bounds[2 * xl] + bounds[2 * xl + 1] - bounds[2 * x0]);
         }
+        // signed base-256 digits of the 22-bit taps: c = c2*65536 + c1*256 + c0 with c0, c1 in [-128, 127]; the
+        // horizontal pass then runs on dp4a (u8 pixels x s8 digits, exact in int32)
+        t.groups = (t.ksize + 3) / 4;
+        std::vector<unsigned> kd(static_cast<size_t>(t.groups) * 3 * out_size, 0u);
+        for (int xx = 0; xx < out_size; ++xx)
+            for (int k = 0; k < t.ksize; ++k) {
+                int cc = kk[static_cast<size_t>(xx) * t.ksize + k];
+                for (int d = 0; d < 3; ++d) {
+                    const int dig = d < 2 ? ((cc + 128) & 255) - 128 : cc;
+                    cc = (cc - dig) >> 8;
+                    kd[(static_cast<size_t>(k / 4) * 3 + d) * out_size + xx] |=
+                        static_cast<unsigned>(dig & 255) << (8 * (k & 3));
+                }
+            }
+        VT_CUDA(cudaMalloc(&t.kd, kd.size() * sizeof(unsigned)));
+        VT_CUDA(cudaMemcpy(t.kd, kd.data(), kd.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
         VT_CUDA(cudaMalloc(&t.kk, kk.size() * sizeof(int)));
         VT_CUDA(cudaMalloc(&t.kk_t, kk.size() * sizeof(int)));
         VT_CUDA(cudaMalloc(&t.bounds, bounds.size() * sizeof(int)));
@@ -296,6 +402,29 @@ int resize_u8(ResizeCache* c, const vt_resize_args& a, Profiler* pf) {
                       long long out_pitch) -> int {
         const ResizeTable* t = nullptr;
         VT_TRY(get_table(c, cw, a.dst_w, a.filter, &t));
+        static const bool scalar = [] { const char* e = getenv("VT_B200_RESIZE_SCALAR"); return e && e[0] == '1'; }();
+        const int gx = (a.dst_w + kHBlock - 1) / kHBlock;
+        if (!scalar) {
+            // plane of one channel of one row: the span, the word the last window may run into, alignment slack
+            const int plane_pitch = (t->max_span + 8 + 15) / 16 * 16;
+            VT_CHECK(3 * plane_pitch <= 200 * 1024, "horizontal scale factor too large for the staged resize kernel");
+            const int R = 12 * plane_pitch <= 96 * 1024 && rows >= 4 ? 4 : 1;
+            const size_t smem = static_cast<size_t>(3) * plane_pitch * R;
+            if (smem > 48 * 1024) {
+                VT_CUDA(cudaFuncSetAttribute(resize_h_dp4a_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                VT_CUDA(cudaFuncSetAttribute(resize_h_dp4a_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            }
+            int rows_per_cta = R;
+            while (rows_per_cta < 16 && 1LL * gx * ((rows + rows_per_cta - 1) / rows_per_cta) > 148 * 16) rows_per_cta *= 2;
+            const dim3 grid(gx, (rows + rows_per_cta - 1) / rows_per_cta);
+            if (R == 4)
+                resize_h_dp4a_kernel<4><<<grid, kHBlock, smem, s>>>(in, in_pitch, out, out_pitch, t->kd, t->bounds, a.dst_w,
+                                                                    rows, rows_per_cta, plane_pitch);
+            else
+                resize_h_dp4a_kernel<1><<<grid, kHBlock, smem, s>>>(in, in_pitch, out, out_pitch, t->kd, t->bounds, a.dst_w,
+                                                                    rows, rows_per_cta, plane_pitch);
+            return 0;
+        }
         const int span_pitch = (t->max_span * 3 + 15) / 16 * 16;
         VT_CHECK(span_pitch <= 200 * 1024, "horizontal scale factor too large for the staged resize kernel");
         const int R = 4 * span_pitch <= 96 * 1024 && rows >= 4 ? 4 : 1;  // rows staged together
@@ -304,7 +433,6 @@ int resize_u8(ResizeCache* c, const vt_resize_args& a, Profiler* pf) {
             VT_CUDA(cudaFuncSetAttribute(resize_h_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             VT_CUDA(cudaFuncSetAttribute(resize_h_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         }
-        const int gx = (a.dst_w + kHBlock - 1) / kHBlock;
         int rows_per_cta = R;
         while (rows_per_cta < 16 && 1LL * gx * ((rows + rows_per_cta - 1) / rows_per_cta) > 148 * 16) rows_per_cta *= 2;
         const dim3 grid(gx, (rows + rows_per_cta - 1) / rows_per_cta);
