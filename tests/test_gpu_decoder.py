@@ -39,7 +39,7 @@ def latents(B, h, w, seed=3):
     return torch.randn(B, 16, h, w, generator=g) * 0.36 + 0.12      # the scale of wrapper latents
 
 
-@pytest.mark.parametrize("B,h,w", [(2, 8, 8), (1, 16, 24), (1, 32, 32)])
+@pytest.mark.parametrize("B,h,w", [(2, 8, 8), (1, 16, 24), (1, 32, 32), (2, 9, 11), (1, 1, 1)])
 def test_decoder_fp32_mode(trio, B, h, w):
     _, dec, wrap = trio
     z = latents(B, h, w)
@@ -53,7 +53,7 @@ def test_decoder_fp32_mode(trio, B, h, w):
 
 
 # 72x104 latent: the (832, 576) aspect-ratio bucket -- ragged tiles at every level of the up path
-@pytest.mark.parametrize("B,h,w", [(2, 8, 8), (3, 16, 24), (2, 32, 32), (1, 64, 64), (1, 72, 104)])
+@pytest.mark.parametrize("B,h,w", [(2, 8, 8), (3, 16, 24), (2, 32, 32), (1, 64, 64), (1, 72, 104), (2, 9, 11), (1, 33, 5)])
 def test_decoder_bf16_mode(trio, B, h, w):
     _, dec, wrap = trio
     z = latents(B, h, w)

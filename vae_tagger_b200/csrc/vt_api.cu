@@ -486,16 +486,19 @@ AttnPlan plan_attention(bool enabled, int n, long long tokens, int Cm, size_t es
         pl.rows_per_chunk = std::max<long long>(128, max_rows / 128 * 128);
         pl.ipc = 1;
     }
+    // rows of V^T, of the score matrix and of the probabilities are pitched to a multiple of 64 tokens (TMA row
+    // alignment, K chunks of the P.V contraction); the padding holds zeros
+    const long long tp = (tokens + 63) / 64 * 64;
     pl.qk_b = align_up(static_cast<size_t>(n) * tokens * 2 * Cm * es, 1024);
-    pl.vt_b = align_up(static_cast<size_t>(n) * tokens * Cm * es, 1024);
-    pl.s_b = align_up(static_cast<size_t>(pl.ipc) * pl.rows_per_chunk * tokens * 4, 1024);
-    pl.p_b = align_up(static_cast<size_t>(pl.ipc) * pl.rows_per_chunk * tokens * es, 1024);
+    pl.vt_b = align_up(static_cast<size_t>(n) * tp * Cm * es, 1024);
+    pl.s_b = align_up(static_cast<size_t>(pl.ipc) * pl.rows_per_chunk * tp * 4, 1024);
+    pl.p_b = align_up(static_cast<size_t>(pl.ipc) * pl.rows_per_chunk * tp * es, 1024);
     pl.o_b = pl.vt_b;
     // P.V of a row chunk has only ceil(rows/128) * C/256 output tiles: split K (= tokens) across
     // CTAs when that leaves most of the machine idle, combine the fp32 partials afterwards
     if (!fp32 && pl.ipc == 1) {
         const long long tiles = (pl.rows_per_chunk + 127) / 128 * ((Cm + 255) / 256);
-        const long long kchunks = tokens / 64;
+        const long long kchunks = tp / 64;
         int want = static_cast<int>(std::min<long long>(16, 148 / std::max<long long>(1, tiles)));
         while (want > 1 && kchunks % want != 0) --want;
         pl.pv_splits = std::max(1, want);
@@ -519,6 +522,7 @@ int run_mid_block(EncRun& R, const MidW& M, const AttnPlan& pl, char* ab, Act& X
     vt_ctx* c = R.c;
     cudaStream_t s = R.s;
     const long long tokens = 1LL * h * w_;
+    const long long tp = (tokens + 63) / 64 * 64;   // row pitch of V^T / scores / probabilities (plan_attention)
     const long long rows_per_chunk = pl.rows_per_chunk;
     const int ipc = pl.ipc, pv_splits = pl.pv_splits;
     const size_t qk_b = pl.qk_b, vt_b = pl.vt_b, s_b = pl.s_b, p_b = pl.p_b, o_b = pl.o_b;
@@ -550,7 +554,8 @@ int run_mid_block(EncRun& R, const MidW& M, const AttnPlan& pl, char* ab, Act& X
         }
         {   // V^T = Wv t^T : [n][C][tokens]  (bias b_v is added after P.V: softmax rows sum to one)
             GemmOp g;
-            g.A = R.W(A.v); g.B = T; g.batch = n; g.M = C; g.N = static_cast<int>(tokens); g.K = C;
+            g.A = R.W(A.v); g.B = T; g.batch = n; g.M = C; g.N = static_cast<int>(tp); g.b_rows = static_cast<int>(tokens);
+            g.K = C;
             g.a_batched = 0; g.b_batched = 1; g.out = Vt; g.ab_f16 = 1; g.out_fmt = R.opd_fmt();
             VT_TRY(R.gemm(g, 0));
         }
@@ -559,7 +564,7 @@ int run_mid_block(EncRun& R, const MidW& M, const AttnPlan& pl, char* ab, Act& X
             // fused attention (vt_flash.cu): scores and probabilities never leave the SM
             FlashOp f;
             f.qk = QK; f.vt = Vt; f.bias_v = A.v.bias; f.out = O; f.n = n; f.tokens = static_cast<int>(tokens);
-            f.C = C; f.scale = scale;
+            f.ld_vt = tp; f.C = C; f.scale = scale;
             VT_TRY(launch_flash_attention(f, s, c->prof));
         } else
         for (int i0 = 0; i0 < n; i0 += ipc) {
@@ -572,18 +577,18 @@ int run_mid_block(EncRun& R, const MidW& M, const AttnPlan& pl, char* ab, Act& X
                     g.lda = 2 * C; g.a_bstride = tokens * 2 * C;
                     g.B = QK + (static_cast<size_t>(i0) * tokens * 2 * C + C) * es;
                     g.ldb = 2 * C; g.b_bstride = tokens * 2 * C;
-                    g.batch = nb_img; g.M = rows; g.N = static_cast<int>(tokens); g.K = C;
+                    g.batch = nb_img; g.M = rows; g.N = static_cast<int>(tp); g.b_rows = static_cast<int>(tokens); g.K = C;
                     g.alpha = scale; g.out = S; g.out_fmt = FMT_F32; g.ab_f16 = 1;
                     VT_TRY(R.gemm(g, 0));
                 }
                 VT_TRY(launch_softmax_rows(reinterpret_cast<const float*>(S), P, R.opd_fmt(), 1LL * nb_img * rows,
-                                           static_cast<int>(tokens), tokens, tokens, s, c->prof));
+                                           static_cast<int>(tokens), tp, tp, s, c->prof));
                 if (pv_splits > 1) {
                     // O = P V + b_v with K split: batch index = K slice, fp32 partials, then combine
-                    const long long ks = tokens / pv_splits;
+                    const long long ks = tp / pv_splits;
                     GemmOp g;
-                    g.A = P; g.lda = tokens; g.a_bstride = ks;
-                    g.B = Vt + static_cast<size_t>(i0) * C * tokens * es; g.ldb = tokens; g.b_bstride = ks;
+                    g.A = P; g.lda = tp; g.a_bstride = ks;
+                    g.B = Vt + static_cast<size_t>(i0) * C * tp * es; g.ldb = tp; g.b_bstride = ks;
                     g.batch = pv_splits; g.M = rows; g.N = C; g.K = static_cast<int>(ks);
                     g.out = PART; g.out_fmt = FMT_F32; g.ab_f16 = 1; g.ld_out = C; g.out_bstride = 1LL * rows * C;
                     VT_TRY(R.gemm(g, 0));
@@ -592,9 +597,9 @@ int run_mid_block(EncRun& R, const MidW& M, const AttnPlan& pl, char* ab, Act& X
                                                 s, c->prof));
                 } else {   // O = P V + b_v
                     GemmOp g;
-                    g.A = P; g.lda = tokens; g.a_bstride = 1LL * rows * tokens;
-                    g.B = Vt + static_cast<size_t>(i0) * C * tokens * es; g.ldb = tokens; g.b_bstride = 1LL * C * tokens;
-                    g.batch = nb_img; g.M = rows; g.N = C; g.K = static_cast<int>(tokens);
+                    g.A = P; g.lda = tp; g.a_bstride = 1LL * rows * tp;
+                    g.B = Vt + static_cast<size_t>(i0) * C * tp * es; g.ldb = tp; g.b_bstride = 1LL * C * tp;
+                    g.batch = nb_img; g.M = rows; g.N = C; g.K = static_cast<int>(tp);
                     g.bias = A.v.bias; g.ab_f16 = 1; g.out_fmt = R.opd_fmt();
                     g.out = O + (static_cast<size_t>(i0) * tokens + r0) * C * es;
                     g.ld_out = C; g.out_bstride = tokens * C;
@@ -1119,7 +1124,6 @@ int vt_decode(vt_ctx* c, const vt_decode_args* a) {
     VT_CHECK(c->dec_ready, "decoder parameters not finalised (vt_decoder_finalize)");
     VT_CHECK(a->latent != nullptr && a->image != nullptr, "null latent / image pointer");
     VT_CHECK(a->batch > 0 && a->lat_h > 0 && a->lat_w > 0, "batch and latent size must be positive");
-    VT_CHECK(a->lat_h % 2 == 0 && a->lat_w % 2 == 0, "latent height and width must be even");
     VT_CHECK(a->precision == VT_PREC_BF16 || a->precision == VT_PREC_FP32, "unknown precision");
     cudaStream_t s = static_cast<cudaStream_t>(a->stream);
     int mb = a->micro_batch;

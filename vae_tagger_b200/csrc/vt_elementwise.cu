@@ -270,7 +270,7 @@ __device__ __forceinline__ void store_prob(TO* p, float v) {
 
 template <typename TO, int PER>  // PER values per thread, cols <= 256*PER
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, TO* __restrict__ p,
-                                                           int cols, long long ld_s, long long ld_p) {
+                                                           int cols, long long ld_s, long long ld_p, int cols_pad) {
     __shared__ float red[8];
     __shared__ float bcast;
     const long long row = blockIdx.x;
@@ -315,12 +315,14 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     for (int i = 0; i < PER; ++i) {
         const int c = i * 256 + threadIdx.x;
         if (c < cols) store_prob(pr + c, v[i] * inv);
+        else if (c < cols_pad) store_prob(pr + c, 0.f);  // K padding of the following P.V contraction
     }
 }
 
 template <typename TO>
 __global__ void __launch_bounds__(256) softmax_rows_wide_kernel(const float* __restrict__ s, TO* __restrict__ p,
-                                                                int cols, long long ld_s, long long ld_p) {
+                                                                int cols, long long ld_s, long long ld_p,
+                                                                int cols_pad) {
     __shared__ float red[8];
     __shared__ float bcast;
     const long long row = blockIdx.x;
@@ -352,16 +354,19 @@ __global__ void __launch_bounds__(256) softmax_rows_wide_kernel(const float* __r
     __syncthreads();
     const float inv = 1.0f / bcast;
     for (int c = threadIdx.x; c < cols; c += 256) store_prob(pr + c, expf(sr[c] - m) * inv);
+    for (int c = cols + threadIdx.x; c < cols_pad; c += 256) store_prob(pr + c, 0.f);
 }
 
 template <typename TO>
 static void softmax_dispatch(const float* s, TO* p, long long rows, int cols, long long ld_s, long long ld_p,
                              cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>(rows);
-    if (cols <= 256 * 4) softmax_rows_kernel<TO, 4><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p);
-    else if (cols <= 256 * 16) softmax_rows_kernel<TO, 16><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p);
-    else if (cols <= 256 * 64) softmax_rows_kernel<TO, 64><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p);
-    else softmax_rows_wide_kernel<TO><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p);
+    // probabilities beyond `cols` up to the next multiple of 64 (within the row pitch) are written as zeros
+    const int cp = static_cast<int>(std::min<long long>((cols + 63) / 64 * 64, ld_p));
+    if (cols <= 256 * 4) softmax_rows_kernel<TO, 4><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p, cp);
+    else if (cols <= 256 * 16) softmax_rows_kernel<TO, 16><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p, cp);
+    else if (cols <= 256 * 64) softmax_rows_kernel<TO, 64><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p, cp);
+    else softmax_rows_wide_kernel<TO><<<grid, 256, 0, st>>>(s, p, cols, ld_s, ld_p, cp);
 }
 
 int launch_softmax_rows(const float* s, void* p, int p_fmt, long long rows, int cols, long long ld_s,

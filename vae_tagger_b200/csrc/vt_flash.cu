@@ -318,7 +318,9 @@ flash_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
 int launch_flash_attention(const FlashOp& op, cudaStream_t stream, Profiler* prof) {
     VT_CHECK(op.C == FD, "fused attention is specialised for head_dim 512");
-    VT_CHECK(op.tokens > 0 && op.tokens % 8 == 0 && op.n > 0, "fused attention: token count must be a positive multiple of 8");
+    const long long ldv = op.ld_vt ? op.ld_vt : op.tokens;
+    VT_CHECK(op.tokens > 0 && op.n > 0 && ldv >= op.tokens && ldv % 8 == 0,
+             "fused attention: the row pitch of V^T must be a multiple of 8 elements and at least the token count");
     CUtensorMap tq, tk, tv;
     {
         uint64_t dims[3] = {static_cast<uint64_t>(2 * FD), static_cast<uint64_t>(op.tokens), static_cast<uint64_t>(op.n)};
@@ -330,7 +332,7 @@ int launch_flash_attention(const FlashOp& op, cudaStream_t stream, Profiler* pro
     }
     {
         uint64_t dims[3] = {static_cast<uint64_t>(op.tokens), static_cast<uint64_t>(FD), static_cast<uint64_t>(op.n)};
-        uint64_t str[2] = {2ull * op.tokens, 2ull * op.tokens * FD};
+        uint64_t str[2] = {2ull * ldv, 2ull * ldv * FD};
         uint32_t box[3] = {64, 64, 1};      // 64 keys x one CTA's 64 of the 128 d_v rows
         VT_TRY(make_tmap(&tv, op.vt, 3, dims, str, box));
     }

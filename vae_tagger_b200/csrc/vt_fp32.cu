@@ -21,6 +21,7 @@ struct F32Problem {
     long long ldb, b_bs;
     int M;  // rows per batch (Hout*Wout for convs)
     int N, K, batch;
+    int b_rows;  // rows of B that exist (rows b_rows..N-1 read as zero)
     const float* bias;
     const float* residual;
     float* out;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) f32_contract_kernel(const F32Problem P) {
         // ---- B tile
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         const int bn = n0 + lrow;
-        if (bn < P.N && k < P.K) bv = *reinterpret_cast<const float4*>(P.B + b * P.b_bs + 1LL * bn * P.ldb + k);
+        if (bn < P.b_rows && k < P.K) bv = *reinterpret_cast<const float4*>(P.B + b * P.b_bs + 1LL * bn * P.ldb + k);
         Bs[lk + 0][lrow] = bv.x; Bs[lk + 1][lrow] = bv.y; Bs[lk + 2][lrow] = bv.z; Bs[lk + 3][lrow] = bv.w;
         __syncthreads();
 #pragma unroll
@@ -126,7 +127,7 @@ int launch_conv_fp32(const ConvOp& op, cudaStream_t s, Profiler* prof) {
     P.Cs = op.sc_in ? op.Cs : 0;
     P.K = op.ksize * op.ksize * op.Cin + P.Cs;
     P.B = reinterpret_cast<const float*>(op.w); P.ldb = P.K; P.b_bs = 0;
-    P.M = P.Hout * P.Wout; P.N = op.Cout; P.batch = op.N;
+    P.M = P.Hout * P.Wout; P.N = op.Cout; P.b_rows = op.Cout; P.batch = op.N;
     P.bias = op.bias;
     P.residual = reinterpret_cast<const float*>(op.residual);
     P.out = static_cast<float*>(op.out); P.ld_out = op.Cout;
@@ -142,7 +143,8 @@ int launch_gemm_fp32(const GemmOp& op, cudaStream_t s, Profiler* prof) {
     P.a_bs = op.a_batched ? (op.a_bstride ? op.a_bstride : P.lda * op.M) : 0;
     P.B = reinterpret_cast<const float*>(op.B);
     P.ldb = op.ldb ? op.ldb : op.K;
-    P.b_bs = op.b_batched ? (op.b_bstride ? op.b_bstride : P.ldb * op.N) : 0;
+    P.b_rows = op.b_rows > 0 ? op.b_rows : op.N;
+    P.b_bs = op.b_batched ? (op.b_bstride ? op.b_bstride : P.ldb * P.b_rows) : 0;
     P.M = op.M; P.N = op.N; P.K = op.K; P.batch = op.batch;
     P.bias = op.bias;
     P.residual = reinterpret_cast<const float*>(op.residual);

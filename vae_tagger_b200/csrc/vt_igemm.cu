@@ -394,9 +394,10 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
         VT_TRY(make_tmap(&a, op.A, 5, dims, str, box));
     }
     {
-        uint64_t dims[3] = {static_cast<uint64_t>(op.K), static_cast<uint64_t>(op.N),
+        const int brows = op.b_rows > 0 ? op.b_rows : op.N;  // rows beyond brows: TMA out-of-bounds zero fill
+        uint64_t dims[3] = {static_cast<uint64_t>(op.K), static_cast<uint64_t>(brows),
                             static_cast<uint64_t>(op.b_batched ? op.batch : 1)};
-        uint64_t str[2] = {2ull * ldb, 2ull * (op.b_bstride ? op.b_bstride : ldb * op.N)};
+        uint64_t str[2] = {2ull * ldb, 2ull * (op.b_bstride ? op.b_bstride : ldb * brows)};
         uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
         VT_TRY(make_tmap(&b, op.B, 3, dims, str, box));
     }

@@ -105,6 +105,7 @@ struct GemmOp {
     const void* A = nullptr;
     const void* B = nullptr;
     int batch = 1, M = 0, N = 0, K = 0;
+    int b_rows = 0;  // rows of B that exist (default N); rows b_rows..N-1 read as zero (N padded to the tile size)
     int a_batched = 1, b_batched = 1;
     long long lda = 0, ldb = 0;              // row strides in elements (default K)
     long long a_bstride = 0, b_bstride = 0;  // batch strides in elements (default rows * ld)
@@ -133,6 +134,7 @@ struct FlashOp {
     const float* bias_v = nullptr;
     void* out = nullptr;
     int n = 0, tokens = 0, C = 512;
+    long long ld_vt = 0;  // elements between rows of vt (default tokens; a multiple of 8)
     float scale = 1.f;
 };
 int launch_flash_attention(const FlashOp& op, cudaStream_t stream, Profiler* prof);
