@@ -1,0 +1,72 @@
+"""BASELINE config 3 end to end: decoded uint8 photos of mixed sizes / aspect ratios in host memory -> upload ->
+GPU SmartResize into the aspect-ratio bucket (bit-exact with PIL) -> per-bucket batches -> encode + tag
+(`infer_full.py --use_bucketing --gpu_preprocess` without the file decoding).  One JSON line.
+
+    python tools/pipeline_bench.py [--images 512] [--batch 16]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vae_tagger_b200 import diffusers_vae_loader as L  # noqa: E402
+from vae_tagger_b200 import modules as M  # noqa: E402
+from vae_tagger_b200.infer_full import encode_and_tag  # noqa: E402
+from vae_tagger_b200.preprocess import BucketBatcher  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--tags", type=int, default=1000)
+    a = ap.parse_args()
+    torch.manual_seed(0)
+    wrap = L.DiffusersVAEWrapper(L.load_diffusers_vae_from_config(L.get_diffusers_vae_config())).cuda().eval()
+    arb = M.AspectRatioBucketing()
+    rng = np.random.default_rng(0)
+    # a pool of distinct source photos (1.5-6 Mpx, aspect ratios 0.5-2), cycled to the requested stream length
+    pool = []
+    for _ in range(24):
+        ratio = float(np.exp(rng.uniform(np.log(0.5), np.log(2.0))))
+        mpx = float(rng.uniform(1.5, 6.0))
+        h = int(round((mpx * 1e6 / ratio) ** 0.5))
+        w = int(round(h * ratio))
+        pool.append(torch.from_numpy(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).pin_memory())
+    decs = {}
+
+    def decoder_for(shape):
+        if shape not in decs:
+            decs[shape] = M.create_attention_decoder(16, shape[1] // 8, shape[0] // 8, a.tags, attention_config={}).cuda().eval()
+        return decs[shape]
+
+    def run(n):
+        bb = BucketBatcher("cuda", batch_size=a.batch, bucketing=arb)
+        done, mpx_out = 0, 0.0
+        for shape, keys, batch in bb.batches((i, pool[i % len(pool)]) for i in range(n)):
+            out = encode_and_tag(wrap, decoder_for(shape), batch, threshold=0.5)
+            out["count"].cpu()
+            done += len(keys)
+            mpx_out += len(keys) * shape[0] * shape[1] / 1e6
+        return done, mpx_out
+
+    run(3 * len(pool))  # warm-up: every bucket's workspace, coefficient tables, head parameters
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    done, mpx_out = run(a.images)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    src_mpx = sum(p.shape[0] * p.shape[1] for p in pool) / len(pool) / 1e6
+    print(json.dumps({"metric": "images/s mixed-bucket pipeline (uint8 host photos -> GPU SmartResize -> encode+tag)",
+                      "images": done, "batch": a.batch, "buckets_used": len(decs), "value": round(done / dt, 1),
+                      "seconds": round(dt, 3), "mean_source_mpx": round(src_mpx, 2),
+                      "mean_bucket_mpx": round(mpx_out / done, 3), "h2d_bytes_per_image": int(src_mpx * 3e6)}))
+
+
+if __name__ == "__main__":
+    main()
