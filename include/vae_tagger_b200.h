@@ -74,8 +74,8 @@ int vt_encoder_finalize(vt_ctx* ctx);
 typedef struct vt_encode_args {
     const void* images; /* device pointer, format in_fmt */
     int in_fmt;
-    int batch, height, width; /* any positive multiples of 8 (multiples of 64 -- the bucket sizes -- tile without
-                               * ragged edges at every level) */
+    int batch, height, width; /* any size >= 8: every Downsample2D halves with floor, the latent is floor(size/8);
+                               * multiples of 64 -- the bucket sizes -- tile without ragged edges at every level */
     int precision;            /* VT_PREC_* */
     int sample;               /* 0: latent_dist.mode() (diffusers_vae_loader.py:80); 1: .sample() (:74) */
     int apply_scale_shift;    /* 1: DiffusersVAEWrapper.encode semantics (mode*scale+shift, :80-84) */

@@ -35,9 +35,10 @@ def pair():
 
 # (1, 1024, 1024): BASELINE configs[1] resolution, one image through the CPU oracle (a few seconds)
 # (2, 72, 88) / (1, 520, 776) / (1, 8, 8): multiples of 8 only -- odd latent sizes (9x11, 65x97, 1x1), token counts
-# that are not multiples of the attention tiles (any --resolution the reference accepts)
+# that are not multiples of the attention tiles; (1, 500, 500) / (2, 100, 60) / (1, 9, 15): not even multiples of 8 --
+# every Downsample2D floors (any --resolution the reference accepts)
 @pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 128, 192), (1, 256, 256), (1, 1024, 1024), (2, 72, 88),
-                                   (1, 520, 776), (1, 8, 8)])
+                                   (1, 520, 776), (1, 8, 8), (1, 500, 500), (2, 100, 60), (1, 9, 15)])
 def test_encoder_fp32_mode(pair, B, H, W):
     oracle, wrap = pair
     x = synthetic_images(B, H, W)
@@ -52,7 +53,8 @@ def test_encoder_fp32_mode(pair, B, H, W):
 # (1, 576, 832): a reachable AspectRatioBucketing bucket (modules.py:188-222): 72x104 latent = ragged 8x16 / 8x32
 # tiles at every level, 7488 tokens = 58.5 query tiles (ragged key tile + an unpaired query tile in the attention)
 @pytest.mark.parametrize("B,H,W", [(2, 64, 64), (3, 128, 192), (2, 256, 256), (1, 512, 512), (1, 576, 832),
-                                   (1, 1024, 1024), (2, 72, 88), (1, 520, 776), (1, 8, 8), (3, 40, 8), (1, 264, 1000)])
+                                   (1, 1024, 1024), (2, 72, 88), (1, 520, 776), (1, 8, 8), (3, 40, 8), (1, 264, 1000),
+                                   (1, 500, 500), (2, 100, 60), (1, 9, 15), (1, 301, 203)])
 def test_encoder_bf16_mode(pair, B, H, W):
     oracle, wrap = pair
     x = synthetic_images(B, H, W)

@@ -1006,8 +1006,8 @@ static int encode_impl(vt_ctx* c, const vt_encode_args* a, const char* host_src,
     VT_CHECK(a->images != nullptr, "null image pointer");
     VT_CHECK(a->batch > 0, "batch must be positive");
     const int down = 1 << (c->ecfg.num_blocks - 1);
-    VT_CHECK(a->height > 0 && a->width > 0 && a->height % down == 0 && a->width % down == 0,
-             "image height and width must be positive multiples of 2^(num_blocks-1)");
+    // any size from 2^(num_blocks-1) up: every Downsample2D halves with floor, like the reference's
+    VT_CHECK(a->height >= down && a->width >= down, "image height and width must be at least 2^(num_blocks-1)");
     VT_CHECK(a->in_fmt == VT_IN_F32_NCHW || a->in_fmt == VT_IN_U8_NHWC, "unknown image format");
     VT_CHECK(a->precision == VT_PREC_BF16 || a->precision == VT_PREC_FP32, "unknown precision");
     cudaStream_t s = static_cast<cudaStream_t>(a->stream);
@@ -1443,7 +1443,7 @@ int vt_infer_host(vt_ctx* c, const vt_infer_host_args* a) {
     const int B = a->batch, H = a->height, W = a->width;
     const int LC = c->ecfg.latent_channels, T = c->hcfg.num_classes;
     const int down = 1 << (c->ecfg.num_blocks - 1);
-    VT_CHECK(B > 0 && H > 0 && W > 0 && H % down == 0 && W % down == 0, "bad image shape");
+    VT_CHECK(B > 0 && H >= down && W >= down, "bad image shape");
     const int lh = H / down, lw = W / down;
     const size_t img_b = align_up(static_cast<size_t>(B) * H * W * 3 * (a->in_fmt == VT_IN_U8_NHWC ? 1 : 4), 256);
     const size_t lat_b = align_up(static_cast<size_t>(B) * LC * lh * lw * 4, 256);

@@ -111,8 +111,10 @@ static int make_act_map(CUtensorMap* tm, const void* base, int N, int H, int W, 
         str[2] = 2ull * C * W;
         str[3] = 2ull * C * W * H;
     } else {
-        VT_CHECK(H % 2 == 0 && W % 2 == 0, "stride-2 conv needs even input size");
-        dims[0] = 2ull * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
+        // Odd sizes: the last pixel / row pair is partial.  Its missing half would be the next row's (image's) first
+        // pixel, but only taps of output pixels beyond floor(W/2) x floor(H/2) reach it, and those are never stored
+        // (diffusers' pad-right/bottom + stride-2 conv yields floor(size/2) outputs and never reads the pad then).
+        dims[0] = 2ull * C; dims[1] = (W + 1) / 2; dims[2] = 2; dims[3] = (H + 1) / 2; dims[4] = N;
         str[0] = 2ull * 2 * C;
         str[1] = 2ull * C * W;
         str[2] = 2ull * C * W * 2;
