@@ -235,3 +235,14 @@ def test_infer_vae_cli_matches_oracle(tmp_path, monkeypatch):
             want = oracle_wrapper_encode(oracle, tf(Image.open(path).convert("RGB")).unsqueeze(0)).reshape(-1)
         got = torch.tensor(vec)
         assert got.numel() == 16 * 8 * 8 and rel(got, want) <= 1e-4
+
+
+def test_empty_batch_is_an_empty_result(golden):
+    wrap = L.DiffusersVAEWrapper(L.load_diffusers_vae_from_config(L.get_diffusers_vae_config())).cuda().eval()
+    dec = M.create_attention_decoder(16, 8, 8, 11, attention_config={}).cuda().eval()
+    lat = wrap.encode(torch.empty(0, 3, 64, 64, device="cuda"))
+    assert lat.shape == (0, 16, 8, 8)
+    conf, idx = dec.get_confidence(lat)
+    assert conf.shape == (0, 11) and idx.shape == (0, 11) and idx.dtype == torch.int64
+    assert dec(lat).shape == (0, 11)
+    assert wrap.decode(lat).shape == (0, 3, 64, 64)

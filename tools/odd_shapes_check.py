@@ -18,7 +18,7 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-for (B, H, W) in [(2, 72, 88), (1, 8, 8), (3, 40, 8), (1, 264, 1000), (37, 64, 64)]:
+for (B, H, W) in [(2, 72, 88), (1, 8, 8), (3, 40, 8), (1, 264, 1000), (37, 64, 64), (1, 9, 15), (2, 301, 203), (1, 500, 500)]:
     g = torch.Generator().manual_seed(H * W)
     xu = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
     xf = ((xu.float() / 255 - 0.5) / 0.5).permute(0, 3, 1, 2).contiguous()

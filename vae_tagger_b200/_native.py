@@ -299,6 +299,8 @@ class Context:
         mean = torch.empty_like(lat) if want_moments else None
         logvar = torch.empty_like(lat) if want_moments else None
         nz = _f32c(noise, self.device) if noise is not None else None
+        if B == 0:  # an empty batch is an empty result, as in PyTorch
+            return (lat, mean, logvar) if want_moments else lat
         a = EncodeArgs()
         a.images = x.data_ptr(); a.in_fmt = fmt; a.batch = B; a.height = H; a.width = W
         a.precision = precision; a.sample = int(bool(sample)); a.apply_scale_shift = int(bool(apply_scale_shift))
@@ -329,6 +331,8 @@ class Context:
         B, _, h, w = lat.shape
         up = 1 << (self.num_blocks - 1)
         img = torch.empty(B, 3, h * up, w * up, device=self.device, dtype=torch.float32)
+        if B == 0:
+            return img
         a = DecodeArgs()
         a.latent = lat.data_ptr(); a.batch = B; a.lat_h = h; a.lat_w = w; a.precision = precision
         a.apply_scale_shift = int(bool(apply_scale_shift)); a.image = img.data_ptr()
@@ -365,6 +369,8 @@ class Context:
             out["idx"] = torch.empty(B, T, device=self.device, dtype=torch.int64)
         if "count" in want:
             out["count"] = torch.empty(B, device=self.device, dtype=torch.int32)
+        if B == 0:
+            return out
         a = TagArgs()
         a.latent = lat.data_ptr(); a.batch = B; a.lat_h = h; a.lat_w = w; a.threshold = float(threshold)
         a.logits = out["logits"].data_ptr() if "logits" in out else None
@@ -397,6 +403,8 @@ class Context:
             "count": torch.empty(B, device=self.device, dtype=torch.int32),
             "latent": torch.empty(B, self.latent_channels, H // down, W // down, device=self.device),
         }
+        if B == 0:
+            return out
         a = InferArgs()
         a.images = x.data_ptr(); a.in_fmt = fmt; a.batch = B; a.height = H; a.width = W
         a.precision = precision; a.threshold = float(threshold)
