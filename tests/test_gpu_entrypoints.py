@@ -246,3 +246,48 @@ def test_empty_batch_is_an_empty_result(golden):
     assert conf.shape == (0, 11) and idx.shape == (0, 11) and idx.dtype == torch.int64
     assert dec(lat).shape == (0, 11)
     assert wrap.decode(lat).shape == (0, 3, 64, 64)
+
+
+@pytest.mark.parametrize("extra", [["--use_focal_loss"], ["--use_class_balanced", "--gradient_accumulation_steps", "2"],
+                                   ["--no_attention"]])
+def test_train_decoder_cli_end_to_end(tmp_path, extra):
+    """train_decoder.py's command line on a tiny dataset: JSON prompts + tags.csv + image files -> two epochs ->
+    best_pytorch_model.bin (reference state-dict keys) + training_history.json, through the native training step."""
+    from PIL import Image
+    from safetensors.torch import save_file
+
+    from vae_tagger_b200 import train_decoder
+
+    oracle = make_oracle_vae(0)
+    save_file({k: v.contiguous() for k, v in oracle.state_dict().items()}, str(tmp_path / "vae.safetensors"))
+    (tmp_path / "vae.json").write_text(json.dumps(L.get_diffusers_vae_config()))
+    names = ["red", "green", "blue", "dark"]
+    (tmp_path / "tags.csv").write_text("name\n" + "\n".join(names) + "\n")
+    g = torch.Generator().manual_seed(3)
+    data = {}
+    for i in range(20):
+        c = i % 3
+        arr = torch.randint(0, 60, (72, 80, 3), generator=g, dtype=torch.uint8)
+        arr[..., c] += 150                                   # the tag is the dominant colour channel
+        path = tmp_path / f"im{i}.png"
+        Image.fromarray(arr.numpy()).save(path)
+        data[str(path)] = f"{names[c]}:1.0, dark:0.5" if i % 5 == 0 else names[c]
+    (tmp_path / "data.json").write_text(json.dumps(data))
+    out_dir = tmp_path / "out"
+    hist = train_decoder.main(["--vae_checkpoint", str(tmp_path / "vae.safetensors"), "--vae_config_path",
+                               str(tmp_path / "vae.json"), "--json_path", str(tmp_path / "data.json"),
+                               "--tags_csv_path", str(tmp_path / "tags.csv"), "--output_dir", str(out_dir),
+                               "--resolution", "64", "--train_batch_size", "4", "--num_epochs", "3",
+                               "--num_workers", "0", "--lr_warmup_steps", "1", "--learning_rate", "3e-3",
+                               "--logging_steps", "2"] + extra)
+    assert len(hist["train_loss"]) == 3 and all(torch.isfinite(torch.tensor(hist["train_loss"] + hist["val_loss"])))
+    assert hist["train_loss"][-1] < hist["train_loss"][0]
+    saved = json.loads((out_dir / "training_history.json").read_text())
+    assert saved == hist
+    sd = torch.load(out_dir / "best_pytorch_model.bin", map_location="cpu")
+    if "--no_attention" in extra:
+        ref = M.ClassificationDecoder(16, 8, 8, 4)
+    else:
+        ref = M.create_attention_decoder(16, 8, 8, 4, attention_config={})
+    assert list(sd.keys()) == list(ref.state_dict().keys())
+    ref.load_state_dict(sd)
