@@ -121,8 +121,7 @@ typedef struct vt_head_config {
     int use_spatial_attention;
     int use_self_attention;
     int attention_heads; /* 8 */
-    int use_cross_attention; /* --use_cross_attention (modules.py:388-395, :450-459): query_generator + CrossAttention;
-                              * inference only -- vt_head_train_step refuses it */
+    int use_cross_attention; /* --use_cross_attention (modules.py:388-395, :450-459): query_generator + CrossAttention */
 } vt_head_config;
 int vt_head_configure(vt_ctx* ctx, const vt_head_config* cfg);
 /* name = reference state-dict key, e.g. "classifier.12.weight" */

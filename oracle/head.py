@@ -222,7 +222,7 @@ def self_attention_train(sd: dict, x: torch.Tensor, heads: int = 8, attn_mask=No
 
 def attention_decoder_train(sd: dict, latent: torch.Tensor, heads: int = 8, use_spatial_attention=True,
                             use_self_attention=True, attn_mask=None, attention_dropout=0.1, cls_masks=None,
-                            momentum=0.1):
+                            momentum=0.1, use_cross_attention=False):
     """AttentionClassificationDecoder.forward (modules.py:424-468) under module.train().
     Returns (logits, new running_mean, new running_var)."""
     x = latent
@@ -232,6 +232,11 @@ def attention_decoder_train(sd: dict, latent: torch.Tensor, heads: int = 8, use_
     if use_self_attention:
         x = self_attention_train(sd, x, heads, attn_mask, attention_dropout)
     f = x.reshape(x.shape[0], -1)
+    if use_cross_attention:   # modules.py:450-459 (no dropout in this branch)
+        query = F.linear(f, sd["query_generator.weight"], sd["query_generator.bias"])
+        tokens = x.reshape(x.shape[0], x.shape[1], -1).transpose(1, 2)
+        attended = cross_attention(sd, query, tokens, heads)
+        f = f + attended.mean(dim=1, keepdim=True).expand_as(f)
     for i, (lin, ln) in enumerate(((0, 1), (4, 5), (8, 9))):
         f = F.linear(f, sd[f"classifier.{lin}.weight"], sd[f"classifier.{lin}.bias"])
         f = F.relu(F.layer_norm(f, (f.shape[-1],), sd[f"classifier.{ln}.weight"], sd[f"classifier.{ln}.bias"],

@@ -131,6 +131,21 @@ def main():
                              if k.startswith(("cross_attention.", "query_generator."))},
         "latent": lat, "logits": xl,
     }
+    # the same head in train mode (dropout off): gradients of the reference's own autograd graph
+    xdec.train()
+    for m_ in xdec.modules():
+        if isinstance(m_, torch.nn.Dropout):
+            m_.p = 0.0
+    tgt = (torch.rand(3, 11) < 0.3).float()
+    with quiet:
+        xlogits = xdec(lat)
+    xloss = ref_losses.FocalLoss(1.0, 2.0)(xlogits, tgt)
+    xloss.backward()
+    out["cross_attention_head"]["train"] = {
+        "targets": tgt, "logits": xlogits.detach().clone(), "loss": xloss.detach().clone(),
+        "grads": {k: digest(p.grad) for k, p in xdec.named_parameters()},
+        "param_order": [k for k, _ in xdec.named_parameters()],
+    }
 
     # ClassBalancedLoss (improved_losses.py:58-72) value and gradient
     torch.manual_seed(15)

@@ -122,7 +122,7 @@ def test_head_extremes(ctx, golden):
 
 def test_cross_attention_head_native(golden, train_golden):
     """--use_cross_attention (modules.py:388-395, :450-459) runs as native kernels in inference: against the
-    reference module's own logits; training with it keeps the PyTorch graph and says so."""
+    reference module's own logits; it also trains natively."""
     from vae_tagger_b200 import _native
     from vae_tagger_b200.train_decoder import DecoderTrainer
 
@@ -138,17 +138,22 @@ def test_cross_attention_head_native(golden, train_golden):
     assert rel(logits, c["logits"]) < 2e-5, rel(logits, c["logits"])
     conf, idx = dec.get_confidence(c["latent"].cuda())
     assert (conf.cpu() - torch.sigmoid(c["logits"]).sort(descending=True).values).abs().max().item() < 1e-6
-    opt = torch.optim.AdamW(dec.parameters(), lr=1e-3)
-
+    # training with the branch: native step (AdamW + BCE), and a non-AdamW optimizer keeps the PyTorch graph
     class FrozenLatent(torch.nn.Module):
         def encode(self, x):
             return x
 
-    with pytest.raises(_native.NativeError):
-        DecoderTrainer(FrozenLatent(), dec, torch.nn.BCEWithLogitsLoss(), opt, None, native_step=True)
-    tr = DecoderTrainer(FrozenLatent(), dec, torch.nn.BCEWithLogitsLoss(), opt, None)
-    assert not tr.native
     y = (torch.rand(3, 11) < 0.3).float().cuda()
-    l0 = tr.step(c["latent"].cuda(), y).item()
+    tr = DecoderTrainer(FrozenLatent(), dec, torch.nn.BCEWithLogitsLoss(), torch.optim.AdamW(dec.parameters(), lr=1e-3),
+                        None, native_step=True)
+    assert tr.native
+    losses = [tr.step(c["latent"].cuda(), y).item() for _ in range(6)]
     tr.flush()
-    assert l0 > 0
+    assert losses[-1] < losses[0]
+    with pytest.raises(_native.NativeError):
+        DecoderTrainer(FrozenLatent(), dec, torch.nn.BCEWithLogitsLoss(), torch.optim.SGD(dec.parameters(), lr=0.1), None,
+                       native_step=True)
+    tr2 = DecoderTrainer(FrozenLatent(), dec, torch.nn.BCEWithLogitsLoss(), torch.optim.SGD(dec.parameters(), lr=0.1), None)
+    assert not tr2.native
+    assert tr2.step(c["latent"].cuda(), y).item() > 0
+    tr2.flush()

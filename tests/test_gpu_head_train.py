@@ -385,3 +385,43 @@ def test_gradient_accumulation_follows_the_reference_loop(golden):
         if d.mean().item() > 1e-4 or d.max().item() > 4.5e-3:
             bad[k] = (d.mean().item(), d.max().item())
     assert not bad, bad
+
+
+def test_cross_attention_training_step(ctx, golden, train_golden):
+    """--use_cross_attention in training: logits, loss and every gradient (incl. cross_attention.* and
+    query_generator.*) against the reference module's own train-mode forward and autograd gradients."""
+    c = train_golden["cross_attention_head"]
+    t = c["train"]
+    sd = full_sd(golden)
+    sd.update(c["extra_state_dict"])
+    layout, flat = setup_head(ctx, sd, use_cross_attention=True)
+    assert [n for n, _, _ in layout] == t["param_order"]
+    grads = torch.zeros_like(flat)
+    loss, logits = ctx.head_train_step(c["latent"].cuda(), t["targets"].cuda(), flat, grads, dropout=False,
+                                       want_logits=True)
+    assert rel(logits.cpu(), t["logits"]) < 2e-5
+    assert abs(loss.item() - t["loss"].item()) < 1e-6
+    got = unflatten(layout, grads, sd)
+    zero = dict(ZERO_BY_CONSTRUCTION)
+    zero["cross_attention.k_proj.bias"] = "cross_attention.k_proj.weight"     # softmax shift invariance again
+    for k, want in t["grads"].items():
+        if k in zero:
+            assert got[k].abs().max().item() <= 1e-4 * got[zero[k]].abs().max().item(), k
+        else:
+            check_digest(got[k], want, key=k)
+    # and against the fp64 oracle with dropout on
+    attn_mask, cls_masks = ctx.head_dropout_masks(3, 0.1, 77)
+    grads.zero_()
+    ctx.head_train_step(c["latent"].cuda(), t["targets"].cuda(), flat, grads, dropout=True, seed=77)
+    want = OH.head_train_step(sd, c["latent"], t["targets"], use_cross_attention=True, attn_mask=attn_mask.cpu(),
+                              cls_masks=[m.cpu() for m in cls_masks], dtype=torch.float64)
+    wg = {k: v.float() for k, v in want["grads"].items()}
+    got = unflatten(layout, grads, sd)
+    bad = {}
+    for k in wg:
+        if k in zero:
+            continue
+        r = rel(got[k], wg[k])
+        if not r < 1e-4:
+            bad[k] = r
+    assert not bad, bad

@@ -1363,7 +1363,6 @@ int vt_head_train_step(vt_ctx* c, const vt_head_train_args* a) {
     VT_CHECK(a->latent && a->targets && a->params, "latent, targets and params are required");
     VT_CHECK(a->batch > 0 && a->lat_h > 0 && a->lat_w > 0, "bad latent arguments");
     VT_CHECK(a->attention_dropout >= 0.f && a->attention_dropout < 1.f, "attention_dropout must be in [0,1)");
-    VT_CHECK(!c->hcfg.use_cross_attention, "the cross-attention branch has no training kernels");
     if (c->hcfg.kind == VT_HEAD_ATTENTION)
         VT_CHECK(1LL * a->batch * a->lat_h * a->lat_w > 1, "BatchNorm in train mode needs more than one value per channel");
     VT_TRY(c->hws.ensure(head_train_workspace_floats(c->hcfg, a->batch, a->lat_h, a->lat_w) * sizeof(float)));

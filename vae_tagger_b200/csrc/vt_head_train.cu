@@ -766,6 +766,114 @@ __global__ void __launch_bounds__(64) head_mhsa_bwd_tail_kernel(const float* __r
     token_reduce(sm, t, E, dst + 4 * EE + 5 * E, [&](int i) { return dxn[i]; });
 }
 
+// ------------------------------------------------------------------------------ cross-attention (optional branch)
+// modules.py:450-459: flat += mean_i(CrossAttention(query, tokens)[i]); the mean is a scalar per image, so the gradient
+// w.r.t. every element of (out_proj output + residual query) is sum_i dflat[i] / Q.
+__global__ void __launch_bounds__(256) head_cross_mean_bwd_kernel(const float* __restrict__ dflat,
+                                                                  float* __restrict__ dq, int F, int Q) {
+    __shared__ float red[8];
+    const int n = blockIdx.x;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < F; i += 256) s += dflat[1LL * n * F + i];
+    const float g = block_sum256(s, red) / static_cast<float>(Q);
+    for (int i = threadIdx.x; i < Q; i += 256) dq[1LL * n * Q + i] = g;
+}
+
+// Backward of head_cross_attn_kernel (vt_head.cu).  One CTA per image, thread d = one of the 256 embedding dims
+// (warp = head, head_dim 32).  Recomputes k, v, the scores and the softmax; given datt[n][256] it writes
+//   dq[n][256], dtok[n][E*64] (gradient into the token features) and the per-image parameter gradients
+//   part[n] = { dWk[256][E], dbk[256], dWv[256][E], dbv[256] }   (the flat parameter order).
+__global__ void __launch_bounds__(256) head_cross_attn_bwd_kernel(const float* __restrict__ feat,
+                                                                  const float* __restrict__ q,
+                                                                  const float* __restrict__ wk, const float* __restrict__ bk,
+                                                                  const float* __restrict__ wv, const float* __restrict__ bv,
+                                                                  const float* __restrict__ datt, float* __restrict__ dq,
+                                                                  float* __restrict__ dtok, float* __restrict__ part,
+                                                                  int E, int heads) {
+    __shared__ float tok[16][64];
+    __shared__ float sc[8][64];
+    __shared__ float dp[8][64];
+    extern __shared__ float wpart[];  // [8][E*64]
+    const int n = blockIdx.x, d = threadIdx.x;
+    const int hd = 256 / heads, h = d / hd, lane = d & 31, warp = d >> 5;
+    for (int i = d; i < E * 64; i += 256) tok[i / 64][i % 64] = feat[1LL * n * E * 64 + i];
+    __syncthreads();
+    float kw[16], vw[16], gwk[16], gwv[16];
+    for (int e = 0; e < E; ++e) {
+        kw[e] = wk[d * E + e];
+        vw[e] = wv[d * E + e];
+        gwk[e] = 0.f;
+        gwv[e] = 0.f;
+    }
+    const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+    const float qd = q[1LL * n * 256 + d], da = datt[1LL * n * 256 + d];
+    for (int j = 0; j < 64; ++j) {
+        float kj = bk[d], vj = bv[d];
+        for (int e = 0; e < E; ++e) {
+            kj = fmaf(kw[e], tok[e][j], kj);
+            vj = fmaf(vw[e], tok[e][j], vj);
+        }
+        float ps = qd * scale * kj, pd = da * vj;
+        for (int o = hd / 2; o > 0; o >>= 1) {
+            ps += __shfl_xor_sync(0xFFFFFFFFu, ps, o, 32);
+            pd += __shfl_xor_sync(0xFFFFFFFFu, pd, o, 32);
+        }
+        if (lane % hd == 0) {
+            sc[h][j] = ps;
+            dp[h][j] = pd;
+        }
+    }
+    __syncthreads();
+    float m = -CUDART_INF_F;
+    for (int j = 0; j < 64; ++j) m = fmaxf(m, sc[h][j]);
+    float sum = 0.f;
+    for (int j = 0; j < 64; ++j) sum += expf(sc[h][j] - m);
+    const float inv = 1.0f / sum;
+    float rowdot = 0.f;
+    for (int j = 0; j < 64; ++j) rowdot = fmaf(expf(sc[h][j] - m) * inv, dp[h][j], rowdot);
+    float gq = 0.f, gbk = 0.f, gbv = 0.f;
+    for (int j = 0; j < 64; ++j) {
+        const float p = expf(sc[h][j] - m) * inv;
+        const float ds = p * (dp[h][j] - rowdot);
+        float kj = bk[d];
+        for (int e = 0; e < E; ++e) kj = fmaf(kw[e], tok[e][j], kj);
+        gq = fmaf(ds * scale, kj, gq);
+        const float dk = ds * scale * qd;  // d loss / d k[j][d]
+        const float dv = p * da;           // d loss / d v[j][d]
+        gbk += dk;
+        gbv += dv;
+        for (int e = 0; e < E; ++e) {
+            gwk[e] = fmaf(dk, tok[e][j], gwk[e]);
+            gwv[e] = fmaf(dv, tok[e][j], gwv[e]);
+            // gradient into token j, feature e: sum over the 256 dims -- inside the warp here, across warps below
+            float t = fmaf(dk, kw[e], dv * vw[e]);
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o, 32);
+            if (lane == 0) wpart[warp * E * 64 + e * 64 + j] = t;
+        }
+    }
+    dq[1LL * n * 256 + d] = gq;
+    float* pn = part + 1LL * n * (2 * (256 * E + 256));
+    for (int e = 0; e < E; ++e) {
+        pn[d * E + e] = gwk[e];
+        pn[256 * E + 256 + d * E + e] = gwv[e];
+    }
+    pn[256 * E + d] = gbk;
+    pn[2 * 256 * E + 256 + d] = gbv;
+    __syncthreads();
+    for (int i = d; i < E * 64; i += 256) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += wpart[w * E * 64 + i];
+        dtok[1LL * n * E * 64 + i] = t;
+    }
+}
+
+// dst[i] = a[i] + b[i] (+ c[i])
+__global__ void __launch_bounds__(256) head_add_kernel(const float* a, const float* b, const float* c, float* dst,
+                                                       long long n) {  // dst may alias a
+    const long long i = blockIdx.x * 256LL + threadIdx.x;
+    if (i < n) dst[i] = a[i] + b[i] + (c ? c[i] : 0.f);
+}
+
 // ------------------------------------------------------------------------------ classifier
 // LayerNorm (eps 1e-5) -> ReLU / LeakyReLU(0.2) -> Dropout(p), out of place; stat[b] = (mean, rstd).
 __global__ void __launch_bounds__(256) head_ln_act_drop_kernel(const float* __restrict__ a, float* __restrict__ h,
@@ -1021,6 +1129,16 @@ std::vector<HeadParamEntry> head_param_layout(const vt_head_config& h) {
             add("self_attention_post.norm.weight", {E});
             add("self_attention_post.norm.bias", {E});
         }
+        if (h.use_cross_attention) {  // CrossAttention(query_dim 512, key_dim E, embed_dim 256), modules.py:388-395
+            add("cross_attention.q_proj.weight", {256, 512});
+            add("cross_attention.q_proj.bias", {256});
+            add("cross_attention.k_proj.weight", {256, E});
+            add("cross_attention.k_proj.bias", {256});
+            add("cross_attention.v_proj.weight", {256, E});
+            add("cross_attention.v_proj.bias", {256});
+            add("cross_attention.out_proj.weight", {512, 256});
+            add("cross_attention.out_proj.bias", {512});
+        }
     }
     const Mlp m = mlp_of(h);
     for (int i = 0; i < m.n; ++i) {
@@ -1032,6 +1150,10 @@ std::vector<HeadParamEntry> head_param_layout(const vt_head_config& h) {
             add(ln + ".weight", {m.dims[i + 1]});
             add(ln + ".bias", {m.dims[i + 1]});
         }
+    }
+    if (h.kind == VT_HEAD_ATTENTION && h.use_cross_attention) {  // registered last in the reference (modules.py:421-422)
+        add("query_generator.weight", {512, E * 64});
+        add("query_generator.bias", {512});
     }
     (void)T;
     return L;
@@ -1049,7 +1171,7 @@ struct Arena {
 struct TrainWs {
     size_t pool, cgate, map2, x2, sgate, z, dz, dy, dpre, bnstat, bnsums, pooled, dpooled, feat, dfeat;
     size_t a[4], hbuf[4], stat[4], dtbuf, g0, g1, logits, dlogits, loss;
-    size_t part_dx, ao, dqkv, part_bn, part_mhsa, part_cw, part_cb, part_g, part_w7, part_norm;
+    size_t xq, xqp, xatt, xout, feat2, dxout, dxatt, dxqp, dxq, dfadd, dtok, part_x, part_dx, ao, dqkv, part_bn, part_mhsa, part_cw, part_cb, part_g, part_w7, part_norm;
     size_t total;
 };
 constexpr int kBands = 8;      // row bands / pixel chunks per image of the spatial-attention reductions
@@ -1082,11 +1204,20 @@ TrainWs plan(const vt_head_config& h, int B, int H, int W) {
         w.hbuf[i] = A.take(B * static_cast<size_t>(m.dims[i + 1]));
         w.stat[i] = A.take(2 * static_cast<size_t>(B));
     }
+    if (h.kind == VT_HEAD_ATTENTION && h.use_cross_attention) {
+        const size_t F = static_cast<size_t>(m.dims[0]);
+        w.xq = A.take(B * 512); w.xqp = A.take(B * 256); w.xatt = A.take(B * 256); w.xout = A.take(B * 512);
+        w.feat2 = A.take(B * F); w.dxout = A.take(B * 512); w.dxatt = A.take(B * 256); w.dxqp = A.take(B * 256);
+        w.dxq = A.take(B * 512); w.dfadd = A.take(B * F); w.dtok = A.take(B * F);
+        w.part_x = A.take(static_cast<size_t>(B) * 2 * (256 * E + 256));
+    }
     w.dtbuf = A.take(B * maxd); w.g0 = A.take(B * maxd); w.g1 = A.take(B * maxd);
     {
         size_t need = 0;
         for (int i = 0; i < m.n; ++i)
             need = std::max(need, static_cast<size_t>((m.dims[i + 1] + 63) / 64) * B * m.dims[i]);
+        if (h.kind == VT_HEAD_ATTENTION && h.use_cross_attention)
+            need = std::max(need, static_cast<size_t>(8) * B * std::max(512, m.dims[0]));
         w.part_dx = A.take(need);
     }
     w.logits = A.take(B * T); w.dlogits = A.take(B * T); w.loss = A.take(1);
@@ -1174,9 +1305,25 @@ int head_train_step(const vt_head_config& h, const vt_head_train_args& a, float*
         VT_TRY(launch_head_adaptive_pool(a.latent, ws + w.feat, B, C, H, W, 4, 4, s, pf));
     }
     const float* feat = (att && !h.use_self_attention) ? ws + w.pooled : ws + w.feat;
+    const bool cross = att && h.use_cross_attention;
+    const float* cls_in = feat;  // input of the classifier
+    if (cross) {
+        VT_CHECK(h.attention_heads == 8, "the cross-attention branch needs attention_heads = 8");
+        VT_TRY(launch_head_linear(feat, P("query_generator.weight"), P("query_generator.bias"), ws + w.xq, B, m.dims[0],
+                                  512, s, pf));
+        VT_TRY(launch_head_linear(ws + w.xq, P("cross_attention.q_proj.weight"), P("cross_attention.q_proj.bias"),
+                                  ws + w.xqp, B, 512, 256, s, pf));
+        VT_TRY(launch_head_cross_attention(feat, ws + w.xqp, P("cross_attention.k_proj.weight"),
+                                           P("cross_attention.k_proj.bias"), P("cross_attention.v_proj.weight"),
+                                           P("cross_attention.v_proj.bias"), ws + w.xatt, B, E, h.attention_heads, s, pf));
+        VT_TRY(launch_head_linear(ws + w.xatt, P("cross_attention.out_proj.weight"), P("cross_attention.out_proj.bias"),
+                                  ws + w.xout, B, 256, 512, s, pf));
+        VT_TRY(launch_head_cross_add(ws + w.xout, ws + w.xq, feat, ws + w.feat2, B, 512, m.dims[0], s, pf));
+        cls_in = ws + w.feat2;
+    }
     float* logits = a.logits ? a.logits : ws + w.logits;
     {
-        const float* cur = feat;
+        const float* cur = cls_in;
         for (int i = 0; i < m.n; ++i) {
             const std::string lin = "classifier." + std::to_string(4 * i);
             float* out = (i + 1 == m.n) ? logits : ws + w.a[i];
@@ -1207,7 +1354,7 @@ int head_train_step(const vt_head_config& h, const vt_head_train_args& a, float*
     float* gbuf[2] = {ws + w.g0, ws + w.g1};
     for (int i = m.n - 1; i >= 0; --i) {
         const std::string lin = "classifier." + std::to_string(4 * i);
-        const float* xin = i == 0 ? feat : ws + w.hbuf[i - 1];
+        const float* xin = i == 0 ? cls_in : ws + w.hbuf[i - 1];
         const int I = m.dims[i], O = m.dims[i + 1];
         VT_KC(head_linear_bwd_w_kernel<<<static_cast<int>((1LL * O * I + 255) / 256), 256, 0, s>>>(
             gcur, xin, G(lin + ".weight"), G(lin + ".bias"), B, I, O));
@@ -1228,6 +1375,38 @@ int head_train_step(const vt_head_config& h, const vt_head_train_args& a, float*
                                                                             ws + w.stat[i - 1], G(ln + ".weight"),
                                                                             G(ln + ".bias"), B, I));
         }
+    }
+    auto lin_bwd = [&](const float* dy, const float* x, const std::string& name, float* dx, int I, int O) -> int {
+        VT_KC(head_linear_bwd_w_kernel<<<static_cast<int>((1LL * O * I + 255) / 256), 256, 0, s>>>(
+            dy, x, G(name + ".weight"), G(name + ".bias"), B, I, O));
+        VT_KC(head_linear_bwd_x_kernel<<<dim3((I + 127) / 128, (O + 63) / 64), 128, 0, s>>>(dy, P(name + ".weight"),
+                                                                                           ws + w.part_dx, B, I, O));
+        VT_KC(head_partial_assign_kernel<<<static_cast<int>((1LL * B * I + 255) / 256), 256, 0, s>>>(
+            ws + w.part_dx, (O + 63) / 64, 1LL * B * I, dx));
+        return 0;
+    };
+    if (cross) {
+        // -------------------------------------------------------------- cross-attention branch (modules.py:450-459)
+        const int F = m.dims[0];
+        VT_KC(head_cross_mean_bwd_kernel<<<B, 256, 0, s>>>(ws + w.dfeat, ws + w.dxout, F, 512));
+        VT_TRY(lin_bwd(ws + w.dxout, ws + w.xatt, "cross_attention.out_proj", ws + w.dxatt, 256, 512));
+        const size_t smem_x = static_cast<size_t>(8) * E * 64 * sizeof(float);
+        VT_KC(head_cross_attn_bwd_kernel<<<B, 256, smem_x, s>>>(
+            feat, ws + w.xqp, P("cross_attention.k_proj.weight"), P("cross_attention.k_proj.bias"),
+            P("cross_attention.v_proj.weight"), P("cross_attention.v_proj.bias"), ws + w.dxatt, ws + w.dxqp, ws + w.dtok,
+            ws + w.part_x, E, h.attention_heads));
+        const int PX = 2 * (256 * E + 256);
+        VT_KC(head_partial_reduce_kernel<<<(PX + 255) / 256, 256, 0, s>>>(ws + w.part_x, B, PX,
+                                                                         G("cross_attention.k_proj.weight")));
+        VT_TRY(lin_bwd(ws + w.dxqp, ws + w.xq, "cross_attention.q_proj", ws + w.dxq, 512, 256));
+        // the query also feeds the residual of CrossAttention: d query = q_proj path + d(out + query)
+        VT_KC(head_add_kernel<<<static_cast<int>((1LL * B * 512 + 255) / 256), 256, 0, s>>>(ws + w.dxq, ws + w.dxout, nullptr,
+                                                                                           ws + w.dxq, 1LL * B * 512));
+        VT_TRY(lin_bwd(ws + w.dxq, feat, "query_generator", ws + w.dfadd, F, 512));
+        // d features = identity path of "flat + mean" + query_generator path + token path of k / v
+        VT_KC(head_add_kernel<<<static_cast<int>((1LL * B * F + 255) / 256), 256, 0, s>>>(ws + w.dfeat, ws + w.dfadd,
+                                                                                         ws + w.dtok, ws + w.dfeat,
+                                                                                         1LL * B * F));
     }
     if (att) {
         // -------------------------------------------------------------- self-attention

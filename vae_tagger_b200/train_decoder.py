@@ -11,8 +11,9 @@ Differences in *how* (not what):
   * the decoder's train-mode forward, the focal / BCE loss, the backward, gradient clipping and AdamW run
     as native kernels on flat parameter / gradient buffers (``vt_head_train_step``, ``vt_adamw_step``);
     the module's parameters are views into the flat buffer, so checkpoints and ``state_dict`` are
-    unchanged (``--use_class_balanced``: the class weights go into the loss kernel).  Configurations without a
-    kernel (``--use_cross_attention``, a non-AdamW optimizer) keep the PyTorch autograd graph for the head only.
+    unchanged (``--use_class_balanced``: the class weights go into the loss kernel; ``--use_cross_attention``: the
+    query_generator / CrossAttention branch has its own forward and backward kernels).  A non-AdamW optimizer or
+    a custom loss keeps the PyTorch autograd graph for the head only.
 
 Launch:  torchrun --nproc-per-node N -m vae_tagger_b200.train_decoder --vae_checkpoint ... (same flags as
 the reference; ``--mixed_precision`` is accepted and ignored: the encoder runs bf16 tensor-core
@@ -108,8 +109,6 @@ class DecoderTrainer:
         if len(self.params) != len(list(dec.parameters())):
             return "some decoder parameters are frozen"
         if isinstance(dec, AttentionClassificationDecoder):
-            if dec.use_cross_attention:
-                return "the cross-attention branch has no kernel"
             want_p = (0.3, 0.2, 0.1)
             attn_p = dec.self_attention_post.dropout.p if dec.use_self_attention else 0.0
         elif isinstance(dec, ClassificationDecoder):
