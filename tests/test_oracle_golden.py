@@ -193,3 +193,17 @@ def test_cross_attention_head_oracle(golden, train_golden):
     logits = OH.attention_decoder_logits(sd, c["latent"], use_cross_attention=True)
     torch.testing.assert_close(logits, c["logits"], atol=1e-5, rtol=1e-5)
     assert not torch.allclose(OH.attention_decoder_logits(sd, c["latent"]), c["logits"], atol=1e-3)   # the branch matters
+
+
+def test_cross_attention_head_train_oracle(golden, train_golden):
+    """The --use_cross_attention head in train mode: oracle gradients against the reference's own autograd graph."""
+    c = train_golden["cross_attention_head"]
+    t = c["train"]
+    sd = full_sd(golden, "att_T11_64x64")
+    sd.update(c["extra_state_dict"])
+    r = OH.head_train_step(sd, c["latent"], t["targets"], use_cross_attention=True)
+    torch.testing.assert_close(r["logits"], t["logits"], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(r["loss"], t["loss"], atol=1e-7, rtol=1e-5)
+    assert sorted(r["grads"]) == sorted(t["param_order"])
+    for k, want in t["grads"].items():
+        check_digest(r["grads"][k], want, atol=1e-7)
