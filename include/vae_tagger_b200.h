@@ -122,6 +122,8 @@ typedef struct vt_head_config {
     int use_self_attention;
     int attention_heads; /* 8 */
     int use_cross_attention; /* --use_cross_attention (modules.py:388-395, :450-459): query_generator + CrossAttention */
+    int plain_flat_dim;      /* VT_HEAD_PLAIN only: 0 = AdaptiveAvgPool(4,4) (use_adaptive_pooling=True, modules.py:312-314);
+                              * else LC*h*w: the latent is flattened as is (use_adaptive_pooling=False, :316-317) */
 } vt_head_config;
 int vt_head_configure(vt_ctx* ctx, const vt_head_config* cfg);
 /* name = reference state-dict key, e.g. "classifier.12.weight" */

@@ -120,9 +120,9 @@ def attention_decoder_logits(sd: dict, latent: torch.Tensor, heads: int = 8, use
     return classifier(sd, flat)
 
 
-def plain_decoder_logits(sd: dict, latent: torch.Tensor) -> torch.Tensor:
-    """ClassificationDecoder.forward (modules.py:335-349), use_adaptive_pooling=True."""
-    f = F.adaptive_avg_pool2d(latent, (4, 4)).reshape(latent.shape[0], -1)
+def plain_decoder_logits(sd: dict, latent: torch.Tensor, use_adaptive_pooling=True) -> torch.Tensor:
+    """ClassificationDecoder.forward (modules.py:335-349)."""
+    f = (F.adaptive_avg_pool2d(latent, (4, 4)) if use_adaptive_pooling else latent).reshape(latent.shape[0], -1)
     for lin, ln in ((0, 1), (4, 5)):
         f = F.linear(f, sd[f"classifier.{lin}.weight"], sd[f"classifier.{lin}.bias"])
         f = F.layer_norm(f, (f.shape[-1],), sd[f"classifier.{ln}.weight"], sd[f"classifier.{ln}.bias"], eps=1e-5)
@@ -245,9 +245,9 @@ def attention_decoder_train(sd: dict, latent: torch.Tensor, heads: int = 8, use_
     return F.linear(f, sd["classifier.12.weight"], sd["classifier.12.bias"]), rm, rv
 
 
-def plain_decoder_train(sd: dict, latent: torch.Tensor, cls_masks=None) -> torch.Tensor:
+def plain_decoder_train(sd: dict, latent: torch.Tensor, cls_masks=None, use_adaptive_pooling=True) -> torch.Tensor:
     """ClassificationDecoder.forward (modules.py:335-349) under module.train()."""
-    f = F.adaptive_avg_pool2d(latent, (4, 4)).reshape(latent.shape[0], -1)
+    f = (F.adaptive_avg_pool2d(latent, (4, 4)) if use_adaptive_pooling else latent).reshape(latent.shape[0], -1)
     for i, (lin, ln) in enumerate(((0, 1), (4, 5))):
         f = F.linear(f, sd[f"classifier.{lin}.weight"], sd[f"classifier.{lin}.bias"])
         f = F.layer_norm(f, (f.shape[-1],), sd[f"classifier.{ln}.weight"], sd[f"classifier.{ln}.bias"], eps=1e-5)

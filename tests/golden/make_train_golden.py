@@ -157,6 +157,29 @@ def main():
     out["class_balanced"] = {"logits": x.detach().clone(), "targets": y, "samples_per_class": spc,
                              "loss": cb.detach().clone(), "grad": x.grad.clone()}
 
+    # plain head without adaptive pooling (modules.py:316-317): a 16x4x4 latent flattens to the same 256 inputs, so
+    # the parameters are those of head_golden.pt's plain head
+    torch.manual_seed(17)
+    with quiet:
+        fdec = ref_modules.ClassificationDecoder(16, 4, 4, 11, use_adaptive_pooling=False)
+    fdec.load_state_dict(psd)
+    lat = torch.randn(5, 16, 4, 4)
+    tgt = (torch.rand(5, 11) < 0.3).float()
+    fdec.eval()
+    with torch.no_grad(), quiet:
+        flogits_eval = fdec(lat)
+    fdec.train()
+    for m_ in fdec.modules():
+        if isinstance(m_, torch.nn.Dropout):
+            m_.p = 0.0
+    with quiet:
+        flogits = fdec(lat)
+    floss = ref_losses.FocalLoss(1.0, 2.0)(flogits, tgt)
+    floss.backward()
+    out["plain_flat"] = {"latent": lat, "targets": tgt, "logits_eval": flogits_eval, "logits": flogits.detach().clone(),
+                         "loss": floss.detach().clone(),
+                         "grads": {k: digest(p.grad) for k, p in fdec.named_parameters()}}
+
     # clip_grad_norm_ + AdamW on a flat tensor, three steps
     torch.manual_seed(14)
     p = torch.nn.Parameter(torch.randn(1000))

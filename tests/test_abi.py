@@ -44,7 +44,7 @@ def test_struct_sizes_match_header_layout():
 
     got = [C.sizeof(t) for t in (_native.EncoderConfig, _native.HeadConfig, _native.EncodeArgs, _native.TagArgs,
                                  _native.InferHostArgs, _native.HeadTrainArgs, _native.ResizeArgs, _native.DecodeArgs, _native.InferArgs)]
-    assert got == [72, 28, 96, 72, 80, 136, 80, 56, 80]
+    assert got == [72, 32, 96, 72, 80, 136, 80, 56, 80]
     gcc = shutil.which("gcc")
     if gcc:  # compile the header as C and compare sizeof() of every struct
         import tempfile

@@ -425,3 +425,24 @@ def test_cross_attention_training_step(ctx, golden, train_golden):
         if not r < 1e-4:
             bad[k] = r
     assert not bad, bad
+
+
+def test_plain_head_without_pooling(ctx, golden, train_golden):
+    """ClassificationDecoder(use_adaptive_pooling=False): the flattened latent feeds the MLP directly -- module
+    inference and the native training step against the reference's own outputs / gradients."""
+    from vae_tagger_b200 import modules as M
+
+    c = train_golden["plain_flat"]
+    sd = golden["plain_head"]["state_dict"]
+    dec = M.ClassificationDecoder(16, 4, 4, 11, use_adaptive_pooling=False)
+    dec.load_state_dict(sd)
+    dec = dec.cuda().eval()
+    assert rel(dec(c["latent"].cuda()).cpu(), c["logits_eval"]) < 2e-5
+    with pytest.raises(_native.NativeError):
+        dec(torch.zeros(1, 16, 8, 8).cuda())                 # built for a 4x4 latent
+    layout, flat = setup_head(ctx, sd, kind=_native.HEAD_PLAIN, plain_flat_dim=256)
+    grads = torch.zeros_like(flat)
+    loss, logits = ctx.head_train_step(c["latent"].cuda(), c["targets"].cuda(), flat, grads, dropout=False,
+                                       want_logits=True)
+    assert rel(logits.cpu(), c["logits"]) < 2e-5 and abs(loss.item() - c["loss"].item()) < 1e-6
+    check_golden_grads(unflatten(layout, grads, sd), c["grads"])

@@ -207,3 +207,15 @@ def test_cross_attention_head_train_oracle(golden, train_golden):
     assert sorted(r["grads"]) == sorted(t["param_order"])
     for k, want in t["grads"].items():
         check_digest(r["grads"][k], want, atol=1e-7)
+
+
+def test_plain_head_without_pooling_oracle(golden, train_golden):
+    """ClassificationDecoder(use_adaptive_pooling=False) (modules.py:316-317): eval logits and train-mode gradients."""
+    c = train_golden["plain_flat"]
+    sd = golden["plain_head"]["state_dict"]
+    torch.testing.assert_close(OH.plain_decoder_logits(sd, c["latent"], use_adaptive_pooling=False), c["logits_eval"],
+                               atol=1e-5, rtol=1e-5)
+    r = OH.head_train_step(sd, c["latent"], c["targets"], kind="plain", use_adaptive_pooling=False)
+    torch.testing.assert_close(r["logits"], c["logits"], atol=1e-5, rtol=1e-5)
+    for k, want in c["grads"].items():
+        check_digest(r["grads"][k], want, atol=1e-7)

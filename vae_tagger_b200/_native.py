@@ -55,7 +55,7 @@ class HeadConfig(C.Structure):
     _fields_ = [
         ("kind", C.c_int), ("latent_channels", C.c_int), ("num_classes", C.c_int),
         ("use_spatial_attention", C.c_int), ("use_self_attention", C.c_int), ("attention_heads", C.c_int),
-        ("use_cross_attention", C.c_int),
+        ("use_cross_attention", C.c_int), ("plain_flat_dim", C.c_int),
     ]
 
 
@@ -344,9 +344,9 @@ class Context:
 
     # ------------------------------------------------------------------ head
     def configure_head(self, kind: int, latent_channels: int, num_classes: int, use_spatial_attention=True,
-                       use_self_attention=True, attention_heads=8, use_cross_attention=False):
+                       use_self_attention=True, attention_heads=8, use_cross_attention=False, plain_flat_dim=0):
         hc = HeadConfig(kind, latent_channels, num_classes, int(use_spatial_attention), int(use_self_attention),
-                        attention_heads, int(use_cross_attention))
+                        attention_heads, int(use_cross_attention), int(plain_flat_dim))
         _check(self.lib.vt_head_configure(self.h, C.byref(hc)))
         self.num_classes = num_classes
 

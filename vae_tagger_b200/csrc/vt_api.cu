@@ -1208,7 +1208,7 @@ int vt_head_finalize(vt_ctx* c) {
             }
         }
     } else {
-        const int dims[4] = {C * 16, 512, 256, T};
+        const int dims[4] = {h.plain_flat_dim > 0 ? h.plain_flat_dim : C * 16, 512, 256, T};
         const int lin[3] = {0, 4, 8}, ln[2] = {1, 5};
         for (int i = 0; i < 3; ++i) {
             VT_TRY(hcheck(c, "classifier." + std::to_string(lin[i]) + ".weight", {dims[i + 1], dims[i]}));
@@ -1309,10 +1309,15 @@ static int tag_impl(vt_ctx* c, const vt_tag_args* a, DevBuf& hws) {
             cur = out;
         }
     } else {
-        VT_TRY(launch_head_adaptive_pool(a->latent, ws + o_feat, B, C, H, W, 4, 4, s, pf));
-        const int dims[4] = {C * 16, 512, 256, T};
-        const int lin[3] = {0, 4, 8}, ln[2] = {1, 5};
         const float* cur = ws + o_feat;
+        if (h.plain_flat_dim > 0) {  // use_adaptive_pooling=False: latent.reshape(B, -1) is the NCHW buffer itself
+            VT_CHECK(h.plain_flat_dim == C * H * W, "latent size differs from the one the plain head was built for");
+            cur = a->latent;
+        } else {
+            VT_TRY(launch_head_adaptive_pool(a->latent, ws + o_feat, B, C, H, W, 4, 4, s, pf));
+        }
+        const int dims[4] = {h.plain_flat_dim > 0 ? h.plain_flat_dim : C * 16, 512, 256, T};
+        const int lin[3] = {0, 4, 8}, ln[2] = {1, 5};
         float* bufs[2] = {ws + o_a, ws + o_b};
         for (int i = 0; i < 3; ++i) {
             float* out = i == 2 ? logits : bufs[i & 1];

@@ -1090,7 +1090,7 @@ Mlp mlp_of(const vt_head_config& h) {
         m.drop[0] = 0.3f; m.drop[1] = 0.2f; m.drop[2] = 0.1f;
     } else {
         m.n = 3;
-        const int d[4] = {h.latent_channels * 16, 512, 256, h.num_classes};
+        const int d[4] = {h.plain_flat_dim > 0 ? h.plain_flat_dim : h.latent_channels * 16, 512, 256, h.num_classes};
         for (int i = 0; i < 4; ++i) m.dims[i] = d[i];
         m.act = 2;
         m.drop[0] = 0.3f; m.drop[1] = 0.2f;
@@ -1301,10 +1301,14 @@ int head_train_step(const vt_head_config& h, const vt_head_train_args& a, float*
             VT_KC(head_mhsa_out_kernel<<<B, 64, 0, s>>>(ws + w.pooled, P("self_attention_post.q_proj.weight"),
                                                          ws + w.ao, ws + w.feat, E));
         }
+    } else if (h.plain_flat_dim > 0) {
+        VT_CHECK(h.plain_flat_dim == C * H * W, "latent size differs from the one the plain head was built for");
     } else {
         VT_TRY(launch_head_adaptive_pool(a.latent, ws + w.feat, B, C, H, W, 4, 4, s, pf));
     }
-    const float* feat = (att && !h.use_self_attention) ? ws + w.pooled : ws + w.feat;
+    const float* feat = (att && !h.use_self_attention) ? ws + w.pooled
+                        : (!att && h.plain_flat_dim > 0)  ? a.latent
+                                                          : ws + w.feat;
     const bool cross = att && h.use_cross_attention;
     const float* cls_in = feat;  // input of the classifier
     if (cross) {

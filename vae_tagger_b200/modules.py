@@ -167,9 +167,9 @@ class ClassificationDecoder(_NativeHeadMixin, nn.Module):
             nn.Linear(256, num_classes))
 
     def _head_config(self):
-        if not self.use_adaptive_pooling:
-            raise NotImplementedError("native ClassificationDecoder needs use_adaptive_pooling=True")
-        return _native.HEAD_PLAIN, dict(latent_channels=self.latent_channels, num_classes=self.num_classes)
+        flat = 0 if self.use_adaptive_pooling else self.latent_channels * self.latent_height * self.latent_width
+        return _native.HEAD_PLAIN, dict(latent_channels=self.latent_channels, num_classes=self.num_classes,
+                                        plain_flat_dim=flat)
 
     def forward(self, latent_vectors):
         if self._use_native():

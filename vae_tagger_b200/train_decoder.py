@@ -112,8 +112,6 @@ class DecoderTrainer:
             want_p = (0.3, 0.2, 0.1)
             attn_p = dec.self_attention_post.dropout.p if dec.use_self_attention else 0.0
         elif isinstance(dec, ClassificationDecoder):
-            if not dec.use_adaptive_pooling:
-                return "ClassificationDecoder without adaptive pooling has no kernel"
             want_p, attn_p = (0.3, 0.2), 0.0
         else:
             return f"{type(dec).__name__} has no kernel"
