@@ -251,7 +251,11 @@ def test_empty_batch_is_an_empty_result(golden):
 @pytest.mark.parametrize("extra", [["--use_focal_loss"], ["--use_class_balanced", "--gradient_accumulation_steps", "2"],
                                    ["--no_attention"],
                                    ["--use_bucketing", "--base_resolution", "64", "--max_resolution", "128",
-                                    "--bucket_step", "32", "--train_batch_size", "1"]])
+                                    "--bucket_step", "32", "--train_batch_size", "1"],
+                                   ["--use_focal_loss", "--gpu_preprocess"],
+                                   ["--use_bucketing", "--base_resolution", "64", "--max_resolution", "128",
+                                    "--bucket_step", "32", "--train_batch_size", "1", "--gpu_preprocess",
+                                    "--num_workers", "2"]])
 def test_train_decoder_cli_end_to_end(tmp_path, extra):
     """train_decoder.py's command line on a tiny dataset: JSON prompts + tags.csv + image files -> two epochs ->
     best_pytorch_model.bin (reference state-dict keys) + training_history.json, through the native training step."""

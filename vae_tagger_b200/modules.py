@@ -396,8 +396,13 @@ class TaggedImageDataset(torch.utils.data.Dataset):
     triplet-mining outputs of the reference dataset serve ``train_full.py`` only and are not provided."""
 
     def __init__(self, json_path, tags_csv_path, transform=None, use_bucketing=False, base_resolution=512,
-                 max_resolution=1024, bucket_step=64):
+                 max_resolution=1024, bucket_step=64, raw_uint8=False):
         import json
+
+        # raw_uint8 (addition of this implementation): ``pixel_values`` is the decoded image as a uint8 [h,w,3]
+        # tensor plus its target (W, H) under ``target_size``; resize / crop / normalise then run on the GPU
+        # (vae_tagger_b200.preprocess), bit-exact with the PIL transform, instead of in the loader workers
+        self.raw_uint8 = raw_uint8
 
         import pandas as pd
 
@@ -442,6 +447,10 @@ class TaggedImageDataset(torch.utils.data.Dataset):
             side = 512 if self.use_bucketing else 224
             img = Image.new("RGB", (side, side), (0, 0, 0))
         bucket = self.bucketing.image_buckets.get(path) if self.bucketing else None
+        if self.raw_uint8:
+            import numpy as np
+
+            return torch.from_numpy(np.array(img)), bucket   # a writable copy of the decoded pixels
         if bucket:
             if bucket not in self._bucket_tf:
                 self._bucket_tf[bucket] = get_image_transform(0, True, bucket)
@@ -452,4 +461,7 @@ class TaggedImageDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, idx):
         path = self.image_paths[idx]
+        if self.raw_uint8:
+            img, bucket = self._load(path)
+            return {"pixel_values": img, "target_size": bucket, "labels": self.image_labels[path]}
         return {"pixel_values": self._load(path), "labels": self.image_labels[path]}

@@ -312,20 +312,49 @@ def train_decoder(args):
             print(f"decoder checkpoint could not be loaded, training from scratch: {e}")
     decoder.to(device)
 
-    transform = None if args.use_bucketing else get_image_transform(args.resolution)
+    gpu_pre = getattr(args, "gpu_preprocess", False)
+    transform = None if (args.use_bucketing or gpu_pre) else get_image_transform(args.resolution)
     dataset = TaggedImageDataset(args.json_path, args.tags_csv_path, transform=transform,
                                  use_bucketing=args.use_bucketing, base_resolution=args.base_resolution,
-                                 max_resolution=args.max_resolution, bucket_step=args.bucket_step)
+                                 max_resolution=args.max_resolution, bucket_step=args.bucket_step, raw_uint8=gpu_pre)
+
+    def collate_raw(items):  # decoded images differ in size: keep them as a list, stack the labels
+        return {"pixel_values": [it["pixel_values"] for it in items], "target_size": [it["target_size"] for it in items],
+                "labels": torch.stack([it["labels"] for it in items])}
+
+    def to_device_batch(batch):
+        """Device pixel batch of a loader batch: float [B,3,H,W] from the host transform, or -- with --gpu_preprocess --
+        uint8 [B,H,W,3] resized on the GPU (SmartResize into the bucket, else the square BILINEAR Resize)."""
+        if not gpu_pre:
+            return batch["pixel_values"].to(device, non_blocking=True)
+        from .preprocess import gpu_smart_resize, gpu_square_resize
+
+        sizes = {t if t is not None else (args.resolution, args.resolution) for t in batch["target_size"]}
+        if len(sizes) != 1:
+            raise ValueError("a batch mixes aspect-ratio buckets: use --train_batch_size 1 with --use_bucketing "
+                             "(images of different buckets cannot be stacked, as in the reference)")
+        (w, h), = sizes
+        out = torch.empty(len(batch["pixel_values"]), h, w, 3, dtype=torch.uint8, device=device)
+        for i, (img, t) in enumerate(zip(batch["pixel_values"], batch["target_size"])):
+            img = img.to(device, non_blocking=True)
+            if t is not None:
+                gpu_smart_resize(img, w, h, out=out[i])
+            else:
+                gpu_square_resize(img, args.resolution, out=out[i])
+        return out
+
     class_distribution = compute_class_distribution(dataset)
     val_size = max(1, int(len(dataset) * 0.1))
     train_ds, val_ds = torch.utils.data.random_split(dataset, [len(dataset) - val_size, val_size],
                                                      generator=torch.Generator().manual_seed(args.seed or 0))
     sampler = DistributedSampler(train_ds, world, rank, shuffle=True) if world > 1 else None
+    collate = collate_raw if gpu_pre else None
     train_dl = DataLoader(train_ds, batch_size=args.train_batch_size, shuffle=sampler is None, sampler=sampler,
-                          pin_memory=True, num_workers=args.num_workers,
+                          pin_memory=True, num_workers=args.num_workers, collate_fn=collate,
                           prefetch_factor=args.prefetch_factor if args.num_workers > 0 else None,
                           persistent_workers=args.num_workers > 0)
-    val_dl = DataLoader(val_ds, batch_size=args.train_batch_size, shuffle=False, pin_memory=True, num_workers=0)
+    val_dl = DataLoader(val_ds, batch_size=args.train_batch_size, shuffle=False, pin_memory=True, num_workers=0,
+                        collate_fn=collate)
 
     loss_fn = FocalLoss(alpha=args.focal_alpha, gamma=args.focal_gamma) if args.use_focal_loss else nn.BCEWithLogitsLoss()
     # train_decoder.py:188-189: with --use_class_balanced the class-balanced loss replaces the focal / BCE one
@@ -341,8 +370,7 @@ def train_decoder(args):
             sampler.set_epoch(epoch)
         total, steps = torch.zeros((), device=device), 0
         for step, batch in enumerate(train_dl):
-            loss = trainer.step(batch["pixel_values"].to(device, non_blocking=True),
-                                batch["labels"].to(device, non_blocking=True))
+            loss = trainer.step(to_device_batch(batch), batch["labels"].to(device, non_blocking=True))
             total += loss
             steps += 1
             if rank == 0 and step % args.logging_steps == 0:  # the only host sync of the loop
@@ -353,7 +381,7 @@ def train_decoder(args):
         vtotal, vsteps = torch.zeros((), device=device), 0
         with torch.no_grad():
             for batch in val_dl:
-                logits = decoder(vae_model.encode(batch["pixel_values"].to(device)))
+                logits = decoder(vae_model.encode(to_device_batch(batch)))
                 vtotal += base_fn(logits, batch["labels"].to(device))
                 vsteps += 1
         tl, vl = (total / max(1, steps)).item(), (vtotal / max(1, vsteps)).item()
@@ -418,6 +446,9 @@ def build_parser():
     p.add_argument("--seed", type=int, default=42)
     p.add_argument("--cudnn_benchmark", action="store_true")
     p.add_argument("--cudnn_deterministic", action="store_true")
+    # addition of this implementation (default keeps the reference's host-side PIL transform)
+    p.add_argument("--gpu_preprocess", action="store_true",
+                   help="loader workers only decode; resize / crop / normalise run on the GPU (bit-exact with PIL)")
     return p
 
 
