@@ -134,7 +134,7 @@ def infer_and_classify(args):
             nonlocal errors
             for p in image_paths:
                 try:
-                    yield str(p), np.asarray(Image.open(p).convert("RGB"))
+                    yield str(p), np.array(Image.open(p).convert("RGB"))   # writable copy
                 except Exception as e:  # noqa: BLE001 - the reference skips unreadable images (:130-132)
                     errors += 1
                     print(f"skipping image {p}: {e}")
