@@ -66,8 +66,8 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
+    def __init__(self, gpu_ident):   # nvidia-smi -i accepts an index or a "GPU-<uuid>"
+        self.gpu = gpu_ident
         self.rows = []
         self.proc = None
 
@@ -93,21 +93,27 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                clk, pw = float(f[1]), float(f[3])
+                mx.append(float(f[2]))
             except ValueError:
                 continue
+            rows.append((clk, pw))
             for nme, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        # "under load" = samples drawing at least 60 % of the highest power seen: the sampler also catches the idle
+        # moments around the timed region (barriers, its own start-up), where the clock sits at its maximum
+        pmax = max((pw for _, pw in rows), default=0.0)
+        load = [clk for clk, pw in rows if pw >= 0.6 * pmax]
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(load), "samples_total": len(rows), "power_w_max": pmax, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -249,7 +255,13 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         out = step()
     ctx.profile_read(reset=True)
-    sampler = ClockSampler(local)
+    # nvidia-smi numbers the GPUs by PCI bus, CUDA by its own order (and CUDA_VISIBLE_DEVICES): name the device by UUID
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        gpu_ident = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+    except Exception:  # noqa: BLE001 - older torch: fall back to the index
+        gpu_ident = str(local)
+    sampler = ClockSampler(gpu_ident)
     if rank == 0:
         sampler.start()
     ms = timed(step, args.steps)
