@@ -49,6 +49,21 @@ def make_config(B, R, world):
             "l2": "inputs larger than L2 (403 MB image batch, GB-scale activations)"}
 
 
+def kernel_source_sha():
+    """sha256 over the kernel / C-ABI sources (vae_tagger_b200/csrc/*, include/*.h, sorted by name): identifies the
+    BUILD a profile was taken on, independent of commits that do not touch a kernel."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for d in (os.path.join(ROOT, "vae_tagger_b200", "csrc"), os.path.join(ROOT, "include")):
+        for name in sorted(os.listdir(d)):
+            if name.endswith((".cu", ".cuh", ".h")):
+                h.update(name.encode())
+                with open(os.path.join(d, name), "rb") as f:
+                    h.update(f.read())
+    return h.hexdigest()
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -187,11 +202,18 @@ def run_reference(args):
         if time.perf_counter() - t_wall0 > 240 and vals:
             break
     v = statistics.mean(vals)
+    cfg = make_config(args.batch, args.resolution, max(1, args.gpus))
+    # what this arm actually times: ONE image per step on the host cores of rank 0 (a bounded sample of the
+    # workload above, scaled to 1024^2 when a smaller image had to be used); no GPU, one process at any N
+    cfg["global_batch"] = 1
+    cfg["parallelism"] = "1 CPU process (rank 0), all host threads"
+    cfg["workload"] = ("bounded sample of: " + cfg["workload"] + " -- timed here: batch 1 (one image per step) through "
+                       "the CPU restatement of the reference path (oracle/), fp32")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": warm, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": make_config(args.batch, args.resolution, max(1, args.gpus)),
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -304,29 +326,52 @@ def run_ours(args):
     prof_t = ctx.profile_read(reset=True)
     ctx.profile_enable(False)
     wrap.vae.single_lane = False
-    ig = prof_t["igemm_tcgen05"]
     peaks = load_peaks()
-    achieved = (FLOP_PER_IMAGE if R == 1024 else flops_per_image(R)) * B * 2 / (ig["ms"] * 1e-3) / 1e12 if ig["ms"] else 0.0
+    tensor_cls = [k for k in _native.TENSOR_KERNEL_CLASSES if prof_t[k]["launches"]]
+    t_ms = sum(prof_t[k]["ms"] for k in tensor_cls)
+    t_launches = sum(prof_t[k]["launches"] for k in tensor_cls)
+    alg_flop = FLOP_PER_IMAGE if R == 1024 else flops_per_image(R)
+    achieved = alg_flop * B * 2 / (t_ms * 1e-3) / 1e12 if t_ms else 0.0
+    # every tensor kernel family against its own roofline (its own algorithmic FLOPs / bytes as the launchers
+    # count them, CUDA events around each launch, inside a full step: sustained peak)
+    per_kernel = {}
+    for k in tensor_cls:
+        v = prof_t[k]
+        tf = v["flops"] / (v["ms"] * 1e-3) / 1e12
+        gbs = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+        hbm_bound = k == "conv_in"      # K = 27: 12 B read + 256 B written per pixel, 7 kFLOP -- write bound
+        per_kernel[k] = {"launches_per_step": v["launches"] / 2, "ms_per_step": v["ms"] / 2, "share_of_tensor_ms": v["ms"] / t_ms,
+                         "bound": "hbm" if hbm_bound else "tensor",
+                         "achieved": gbs if hbm_bound else tf, "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                         "frac": (gbs / peaks["hbm"]) if hbm_bound else (tf / peaks["sustained"])}
     roofline = {
-        "bound": "tensor", "kernel": "conv3_fused_kernel + igemm_kernel (tcgen05 implicit GEMM: every conv, projection, QK^T, PV)",
+        "bound": "tensor", "kernel": "all tcgen05 contraction kernels of the step (conv3_fused_kernel x3 variants, igemm_kernel, "
+                                     "flash_d512_kernel, conv_in_kernel); per family in per_kernel",
         "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"],
         "frac_of_burst_peak": achieved / peaks["burst"], "peak_source": peaks["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
-        "launches_per_step": ig["launches"] / 2, "avg_launch_ms": ig["ms"] / max(1.0, ig["launches"]),
-        "kernel_ms_per_step": ig["ms"] / 2, "algorithmic_flop_per_step": flops_per_image(R) * B,
-        "traffic": traffic_per_launch(R, B, ig["launches"] / 2),
+        "launches_per_step": t_launches / 2, "avg_launch_ms": t_ms / max(1.0, t_launches),
+        "kernel_ms_per_step": t_ms / 2, "algorithmic_flop_per_step": flops_per_image(R) * B,
+        "per_kernel": per_kernel,
         "per_class_ms_per_step": {k: v["ms"] / 2 for k, v in prof_t.items() if v["launches"]},
         "whole_step_frac_of_burst": (value / world) * flops_per_image(R) / 1e12 / peaks["burst"],
     }
+    roofline.update(traffic_per_launch(R, B, t_launches / 2))
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+        "dtype": "bf16 (storage of raw activations; fp16 bounded MMA operands and weights, fp32 accumulation in TMEM)",
+        "data": "synthetic",
         "config": make_config(B, R, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "vt_infer_host (C-ABI, pinned host buffers)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
+    # ---- auxiliary blocks beside the (unchanged) timed headline: configs[4] training step with the exposed
+    # all-reduce time, configs[3] bulk stream; default at N > 1 so that the scaling record carries them
+    if args.aux == "on" or (args.aux == "auto" and world > 1):
+        line["train_step"] = aux_train_step(world, rank, dev, wrap)
+        line["bulk_stream"] = aux_bulk_stream(world, rank, dev, ctx, images_per_gpu=args.bulk_images)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -338,16 +383,135 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def aux_train_step(world, rank, dev, wrap, steps=6, warmup=3, batch=8, res=RES):
+    """BASELINE configs[4] / SURVEY 8d-5 beside the headline (not part of the timed region): train_decoder step with
+    the frozen encoder -- encoder fwd (batch per GPU, 1024^2, 16-bit kernels) + head fwd/bwd (focal loss, native
+    kernels) + NCCL all-reduce of the flat fp32 gradient + clip + AdamW.  Device time (CUDA events), max over
+    ranks; the exposed time of a collective is the interval the compute stream waited for it."""
+    import torch
+    import torch.distributed as dist
+
+    from vae_tagger_b200 import modules as M
+    from vae_tagger_b200.improved_losses import FocalLoss
+    from vae_tagger_b200.train_decoder import DecoderTrainer
+
+    g = torch.Generator().manual_seed(7 + rank)
+    x = (torch.rand(batch, 3, res, res, generator=g) * 2 - 1).to(dev)
+    y = (torch.rand(batch, NUM_TAGS, generator=g) < 0.1).float().to(dev)
+
+    class Frozen(torch.nn.Module):
+        def __init__(self, lat):
+            super().__init__()
+            self.lat = lat
+
+        def encode(self, _):
+            return self.lat
+
+    def run(vae):
+        torch.manual_seed(1)
+        dec = M.create_attention_decoder(16, res // 8, res // 8, NUM_TAGS, attention_config={}).to(dev)
+        opt = torch.optim.AdamW(dec.parameters(), lr=1e-3, weight_decay=1e-6)
+        tr = DecoderTrainer(vae, dec, FocalLoss(1.0, 2.0), opt, None, max_grad_norm=1.0, native_step=True)
+        for _ in range(warmup):
+            tr.step(x, y)
+        tr.enable_timing(True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            tr.step(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        exposed = tr.timing_summary()
+        tr.flush()
+        t = torch.tensor([e0.elapsed_time(e1) / steps, exposed.get("allreduce_wait", 0.0),
+                          exposed.get("buffer_broadcast_wait", 0.0)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist(), sum(p.numel() for p in dec.parameters())
+
+    with torch.no_grad():
+        lat = wrap.encode(x)
+    (step_ms, ar_ms, bc_ms), nparam = run(wrap)
+    (head_ms, _, _), _ = run(Frozen(lat))
+    return {"workload": f"configs[4]: train_decoder step, frozen encoder, {res}x{res}, batch {batch} per GPU, {NUM_TAGS} tags, "
+                        "focal loss, AdamW, native head kernels", "n_gpus": world, "steps": steps,
+            "step_ms": step_ms, "head_fwd_bwd_adamw_ms": head_ms, "allreduce_exposed_ms": ar_ms,
+            "buffer_broadcast_exposed_ms": bc_ms, "allreduce_bytes": 4 * nparam,
+            "images_per_s": world * batch / step_ms * 1e3,
+            "how": "CUDA events on the compute stream, max over ranks; exposed = event interval around the wait for the "
+                   "async NCCL op (launched behind step k, waited after the encoder forward of step k+1)"}
+
+
+def aux_bulk_stream(world, rank, dev, ctx, images_per_gpu=8192, batch=BATCH, res=RES):
+    """BASELINE configs[3] / SURVEY 8d-4 beside the headline: batch-sharded bulk tagging of a synthetic uint8
+    image stream (3 MB per image, pinned host memory, double buffered) through vt_infer_host; rank r owns a
+    contiguous shard, no collective on the data path.  Wall clock, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    g = torch.Generator().manual_seed(1000 + rank)
+    pool = [torch.randint(0, 256, (batch, res, res, 3), generator=g, dtype=torch.uint8) for _ in range(2)]
+    bufs = [torch.empty(batch, res, res, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    outs = [None, None]
+    nb = max(1, images_per_gpu // batch)
+    tags = 0
+
+    def fill(slot, k):   # stands in for decode + collate of the next batch
+        bufs[slot].copy_(pool[k & 1])
+
+    fill(0, 0)
+    ctx.infer_host(bufs[0], threshold=0.5)   # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(nb):
+        slot = k & 1
+        th = None
+        if k + 1 < nb:
+            th = threading.Thread(target=fill, args=(slot ^ 1, k + 1))
+            th.start()
+        outs[slot] = ctx.infer_host(bufs[slot], threshold=0.5, out=outs[slot])
+        tags += int(outs[slot]["count"].sum())
+        if th is not None:
+            th.join()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n = nb * batch
+    return {"workload": f"configs[3]: bulk tagging of a uint8 host stream, {res}x{res}, {n} images per GPU "
+                        f"({n * world} total), contiguous shard per rank", "n_gpus": world, "images": n * world,
+            "images_per_s": n * world / t.item(), "seconds": t.item(), "h2d_bytes_per_image": res * res * 3,
+            "collectives_on_data_path": 0, "mean_tags_above_threshold": tags / n}
+
+
 def traffic_per_launch(R, B, launches_per_step):
-    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per tensor-kernel launch, from the committed
-    ``ncu --set full`` capture of one 1024^2 image (profiles/r01_dram_traffic_v20.json) scaled to this step's
-    images per launch; None for other resolutions or when the capture is absent."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_dram_traffic_v20.json")
+    """``roofline.traffic``: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per tensor-kernel launch, from
+    the committed ``ncu --set full`` capture of one 1024^2 image (profiles/r02_dram_traffic.json, written by
+    tools/make_traffic_json.py on the GPU box) scaled to this step's images per launch.  The capture carries the
+    sha256 of the kernel sources it was taken on; when that differs from the sources of THIS build the number is
+    not printed (null) -- a traffic figure of another build is not evidence for this one."""
+    path = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+    out = {"traffic": None, "traffic_source": None}
     if R != 1024 or not os.path.exists(path) or not launches_per_step:
-        return None
+        return out
     with open(path, "r", encoding="utf-8") as f:
-        t = json.load(f)["per_image_all_tensor_kernels"]
-    return (t["dram_read_MB"] + t["dram_write_MB"]) * 1e6 * B / launches_per_step
+        d = json.load(f)
+    sha = kernel_source_sha()
+    if d.get("kernel_source_sha256") != sha:
+        out["traffic_source"] = (f"profiles/r02_dram_traffic.json was captured on kernel sources {str(d.get('kernel_source_sha256'))[:12]}, "
+                                 f"this build is {sha[:12]}: not reported")
+        return out
+    t = d["per_image_all_tensor_kernels"]
+    out["traffic"] = (t["dram_read_MB"] + t["dram_write_MB"]) * 1e6 * B / launches_per_step
+    out["traffic_source"] = f"profiles/r02_dram_traffic.json (kernel sources {sha[:12]}, same as this build)"
+    out["traffic_per_image_by_kernel_MB"] = {k: round(v["dram_read_MB"] + v["dram_write_MB"], 1)
+                                             for k, v in d["per_image_by_kernel"].items()}
+    return out
 
 
 def main():
@@ -359,6 +523,9 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--resolution", type=int, default=RES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--aux", default="auto", choices=["auto", "on", "off"],
+                    help="train_step / bulk_stream blocks in the JSON line (auto: only under torchrun, N > 1)")
+    ap.add_argument("--bulk-images", type=int, default=8192, help="images per GPU of the bulk_stream block")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything native code prints there while the benchmark runs (NCCL's
     # version banner under NCCL_DEBUG=VERSION is a plain printf) is sent to stderr at the file-descriptor level;

@@ -273,9 +273,11 @@ int vt_smart_crop_box(int src_w, int src_h, int dst_w, int dst_h, int32_t* box4)
 int vt_resize_coefficients(int in_size, int out_size, int filter, int32_t* ksize, int32_t* bounds, int32_t* kk);
 
 /* ---------------------------------------------------------------- accounting
- * Kernel classes: 0 implicit GEMM (tcgen05), 1 GroupNorm, 2 conv_in gather, 3 softmax,
- * 4 latent, 5 head, 6 fp32-mode contraction, 7 misc. */
-#define VT_NUM_KERNEL_CLASSES 8
+ * Kernel classes: 0 implicit GEMM (tcgen05; stride-2 / 1x1 / projections / conv_out), 1 GroupNorm, 2 conv_in
+ * gather (fallback), 3 softmax, 4 latent, 5 head, 6 fp32-mode contraction, 7 misc, 8 fused GroupNorm+SiLU+3x3
+ * conv for 128 channels (transposed), 9 the same for 256 / 512 channels (CTA pairs), 10 fused attention,
+ * 11 conv_in, 12 backward-pass contractions. */
+#define VT_NUM_KERNEL_CLASSES 13
 int vt_profile_enable(vt_ctx* ctx, int timing);
 /* out[class][4] = {launches, milliseconds (timing mode only), flops, bytes}; synchronises the device */
 int vt_profile_read(vt_ctx* ctx, double* out, int reset);

@@ -219,3 +219,27 @@ def synthetic_images(n: int, h: int, w: int, seed: int = 1234) -> torch.Tensor:
         g = torch.Generator().manual_seed(seed + i)
         out[i] = torch.rand(3, h, w, generator=g) * 2.0 - 1.0
     return out
+
+
+def structured_images(n: int, h: int, w: int, seed: int = 4321, return_params: bool = False):
+    """Varied synthetic "photo-like" images in [-1,1] (fp32 NCHW): a smooth random colour field (bicubic
+    up-sampling of a small random grid) times a random contrast, plus a random colour offset, plus fine noise
+    of a random amplitude.  Uniform-noise images (``synthetic_images``) all give nearly the same latent
+    statistics, so the tag head sees nearly the same input for every image; these spread the latents, and with
+    them the logits, so that a per-image tag-set comparison is a comparison of different cases.
+    ``return_params``: also the generating parameters per image [n, 6] = (cells/8, contrast, offset r, g, b,
+    noise amplitude) -- what ``make_tagset_golden.py`` derives its synthetic training labels from."""
+    out = torch.empty(n, 3, h, w)
+    params = torch.empty(n, 6)
+    for i in range(n):
+        g = torch.Generator().manual_seed(seed + i)
+        cells = int(torch.randint(2, 9, (1,), generator=g))
+        grid = torch.rand(1, 3, cells, cells, generator=g) * 2.0 - 1.0
+        field = F.interpolate(grid, size=(h, w), mode="bicubic", align_corners=False)[0]
+        contrast = 0.2 + 0.8 * float(torch.rand(1, generator=g))
+        offset = (torch.rand(3, 1, 1, generator=g) * 2.0 - 1.0) * 0.5
+        noise_amp = 0.02 + 0.4 * float(torch.rand(1, generator=g)) ** 2
+        noise = (torch.rand(3, h, w, generator=g) * 2.0 - 1.0) * noise_amp
+        out[i] = (field * contrast + offset + noise).clamp_(-1.0, 1.0)
+        params[i] = torch.tensor([cells / 8.0, contrast, *offset.flatten().tolist(), noise_amp])
+    return (out, params) if return_params else out

@@ -68,6 +68,7 @@ def _worker(rank, world, port, out_dir):
     tr._pending = dist.all_reduce(torch.zeros(1), async_op=True)  # dummy handle so finish_update proceeds
     tr.flat_grad.copy_(summed)
     tr.finish_update()
+    tr.flush()                                    # also lands the BatchNorm-buffer broadcast sent behind the step
     torch.save({"start": start, "end": dec.state_dict(), "summed": summed, "local": local_grad},
                os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
@@ -84,12 +85,15 @@ def test_two_rank_gradient_exchange(tmp_path):
         assert torch.equal(r0["start"][k], r1["start"][k]), k
     # the all-reduce sums the per-rank gradients identically on both ranks
     assert torch.allclose(r0["summed"], r1["summed"])
-    # parameters stay in lock-step after the optimizer step; BatchNorm running stats are per rank
+    # parameters stay in lock-step after the optimizer step; BatchNorm batch statistics are per rank (no SyncBN)
+    # and the running buffers follow DDP's broadcast_buffers: every rank continues from rank 0's, sent right
+    # behind the step that produced them
     for k in r0["end"]:
         if "running_" in k or "num_batches" in k:
             continue
         assert torch.allclose(r0["end"][k], r1["end"][k], atol=1e-7), k
-    assert not torch.equal(r0["end"]["feature_compress.1.running_mean"], r1["end"]["feature_compress.1.running_mean"])
+    assert torch.equal(r0["end"]["feature_compress.1.running_mean"], r1["end"]["feature_compress.1.running_mean"])
+    assert not torch.equal(r0["end"]["feature_compress.1.running_mean"], r0["start"]["feature_compress.1.running_mean"])
 
 
 def _accum_data(rank, k):
@@ -159,3 +163,53 @@ def test_two_rank_gradient_accumulation_matches_the_reference_loop(tmp_path):
             continue
         assert torch.allclose(r0["end"][k], r1["end"][k], atol=1e-7), k
         assert torch.allclose(r0["end"][k], want[k], atol=2e-6), (k, (r0["end"][k] - want[k]).abs().max())
+
+
+# ----------------------------------------------------------------------------- sharded CLI (host logic)
+def test_cost_balanced_shards_tile_the_work_list():
+    from vae_tagger_b200.sharding import image_cost, shard_by_cost
+
+    g = torch.Generator().manual_seed(0)
+    shapes = [(512, 512), (1024, 1024), (832, 576), (640, 896)]
+    for n in (0, 1, 3, 257):
+        costs = [image_cost(*shapes[int(i)]) for i in torch.randint(0, 4, (n,), generator=g)]
+        for world in (1, 2, 4, 8):
+            spans = [shard_by_cost(costs, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            if n == 257:
+                loads = [sum(costs[a:b]) for a, b in spans]
+                assert max(loads) - min(loads) <= 2 * max(costs)       # within one item of the ideal on each side
+    # 1024^2: 4.8826 TFLOP per image, attention quadratic in the pixel count
+    assert abs(image_cost(1024, 1024) - 4.88266) < 1e-4 and abs(image_cost(512, 512) - 1.1176) < 1e-3
+
+
+def _worker_shard_gather(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from vae_tagger_b200.infer_full import merge_rank_results
+    from vae_tagger_b200.sharding import dist_env, gather_to_rank0, image_cost, init_host_group, shard_by_cost
+
+    assert dist_env() == (rank, world, rank)
+    own = init_host_group(world)
+    assert own and dist.is_initialized()
+    work = [((512 + 64 * (i % 5), 512), f"img{i:03d}.png") for i in range(23)]
+    lo, hi = shard_by_cost([image_cost(w, h) for (w, h), _ in work], rank, world)
+    results = {name: {"total_tags_above_threshold": int(name[3:6])} for _, name in work[lo:hi]}
+    merged, errors = merge_rank_results(gather_to_rank0((results, rank), rank, world), [n for _, n in work])
+    torch.save({"merged": merged, "errors": errors, "span": (lo, hi)}, os.path.join(out_dir, f"s{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_cli_gather(tmp_path):
+    """infer_full under torchrun (reference call site infer_full.py:94-139, sharded per SURVEY 8e): every image is
+    tagged by exactly one rank and rank 0 ends up with ONE result dict in the single-process order."""
+    world, port = 2, _free_port()
+    mp.spawn(_worker_shard_gather, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "s0.pt"), torch.load(tmp_path / "s1.pt")
+    assert r0["span"][0] == 0 and r0["span"][1] == r1["span"][0] and r1["span"][1] == 23
+    assert list(r0["merged"].keys()) == [f"img{i:03d}.png" for i in range(23)]
+    assert all(v["total_tags_above_threshold"] == int(k[3:6]) for k, v in r0["merged"].items())
+    assert r0["errors"] == 1 and r1["merged"] == {} and r1["errors"] == 0

@@ -297,3 +297,56 @@ def test_train_decoder_cli_end_to_end(tmp_path, extra):
         ref = M.create_attention_decoder(16, 8, 8, 4, attention_config={})
     assert list(sd.keys()) == list(ref.state_dict().keys())
     ref.load_state_dict(sd)
+
+
+def test_infer_full_sharded_under_torchrun(tmp_path, golden):
+    """``torchrun --nproc-per-node 2 -m vae_tagger_b200.infer_full`` (north star: the image batch is sharded
+    data-parallel, no collective on the inference path): one classification_results.json on rank 0, equal to
+    the single-process run entry by entry and in the same order.  With fewer GPUs than ranks the ranks share
+    cuda:0 -- the sharding / gather logic is the same.  Same for infer_vae's latent_vectors.json."""
+    import socket
+    import subprocess
+    import sys
+
+    from PIL import Image
+    from safetensors.torch import save_file
+
+    from vae_tagger_b200 import infer_full, infer_vae
+
+    oracle = make_oracle_vae(0)
+    save_file({k: v.contiguous() for k, v in oracle.state_dict().items()}, str(tmp_path / "vae.safetensors"))
+    (tmp_path / "vae.json").write_text(json.dumps(L.get_diffusers_vae_config()))
+    sd = dict(golden["attention_head_base"]); sd.update(golden["attention_head"]["att_T11_64x64"]["state_dict"])
+    torch.save(sd, tmp_path / "decoder.bin")
+    (tmp_path / "tags.csv").write_text("name\n" + "\n".join(f"tag{i}" for i in range(11)) + "\n")
+    img_dir = tmp_path / "imgs"
+    img_dir.mkdir()
+    g = torch.Generator().manual_seed(1)
+    for i in range(7):
+        arr = torch.randint(0, 256, (64 + 16 * (i % 3), 96, 3), generator=g, dtype=torch.uint8).numpy()
+        Image.fromarray(arr).save(img_dir / f"im{i}.png")
+    (img_dir / "broken.png").write_bytes(b"not an image")
+    base = ["--vae_checkpoint", str(tmp_path / "vae.safetensors"), "--vae_config_path", str(tmp_path / "vae.json"),
+            "--image_path", str(img_dir), "--resolution", "64", "--batch_size", "2"]
+    tag_args = ["--decoder_checkpoint", str(tmp_path / "decoder.bin"), "--tags_csv_path", str(tmp_path / "tags.csv"),
+                "--use_bucketing", "--base_resolution", "64", "--max_resolution", "128", "--bucket_step", "32"]
+    single = infer_full.main(base + tag_args + ["--output_dir", str(tmp_path / "one")])
+    single_lat = infer_vae.main(base + ["--output_dir", str(tmp_path / "one")])
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    run = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), "-m"]
+    logs = []
+    for mod, extra in (("vae_tagger_b200.infer_full", tag_args), ("vae_tagger_b200.infer_vae", [])):
+        out = subprocess.run(run + [mod] + base + extra + ["--output_dir", str(tmp_path / "two")], env=env, cwd=root,
+                             capture_output=True, text=True, timeout=900)
+        logs.append(out.stdout[-3000:] + out.stderr[-3000:])
+        assert out.returncode == 0, logs[-1]
+    sharded = json.loads((tmp_path / "two" / "classification_results.json").read_text())
+    assert list(sharded.keys()) == list(single.keys()) and len(sharded) == 7, (list(sharded.keys()), logs[0])
+    assert sharded == single       # bf16 mode is batch-invariant: bit-identical probabilities, hence identical JSON
+    sharded_lat = json.loads((tmp_path / "two" / "latent_vectors.json").read_text())
+    assert list(sharded_lat.keys()) == list(single_lat.keys()) and sharded_lat == single_lat

@@ -18,8 +18,10 @@ PREC_BF16, PREC_FP32, PREC_F16 = 0, 1, 2
 IN_F32_NCHW, IN_U8_NHWC = 0, 1
 HEAD_ATTENTION, HEAD_PLAIN = 0, 1
 FILTER_LANCZOS, FILTER_BILINEAR = 1, 2   # PIL.Image.LANCZOS / BILINEAR
-NUM_KERNEL_CLASSES = 8
-KERNEL_CLASS_NAMES = ["igemm_tcgen05", "group_norm", "conv_in_gather", "softmax", "latent", "head", "fp32_contract", "misc"]
+NUM_KERNEL_CLASSES = 13
+KERNEL_CLASS_NAMES = ["igemm_tcgen05", "group_norm", "conv_in_gather", "softmax", "latent", "head", "fp32_contract", "misc",
+                      "conv3_fused_128t", "conv3_fused_256", "flash_d512", "conv_in", "backward_contract"]
+TENSOR_KERNEL_CLASSES = ("igemm_tcgen05", "conv3_fused_128t", "conv3_fused_256", "flash_d512", "conv_in")
 
 
 class NativeError(RuntimeError):

@@ -169,8 +169,9 @@ class AutoencoderKL(nn.Module):
         nblk = len(block_out_channels)
         if act_fn != "silu":
             raise ValueError("only act_fn='silu' is implemented (FLUX VAE)")
-        if use_quant_conv:
-            raise ValueError("use_quant_conv=True is not implemented (FLUX VAE has no quant convs)")
+        if use_quant_conv or use_post_quant_conv:
+            raise ValueError("use_quant_conv / use_post_quant_conv = True are not implemented "
+                             "(the FLUX VAE of diffusers_vae_loader.py:102-134 has neither)")
         if down_block_types is not None and any(t != "DownEncoderBlock2D" for t in down_block_types):
             raise ValueError("only DownEncoderBlock2D encoder blocks are implemented")
         self.config = _Config(
@@ -213,6 +214,12 @@ class AutoencoderKL(nn.Module):
         result = super().load_state_dict(sd, strict=strict, assign=assign)
         self._native_key = None
         self._native_dec_key = None
+        # quant_conv.* / post_quant_conv.* tensors have no home in this architecture: report them as the
+        # reference's diffusers model would (diffusers_vae_loader.py:44-48 prints the unexpected keys)
+        if dropped:
+            if strict:
+                raise RuntimeError(f"Unexpected key(s) in state_dict: {dropped}")
+            result.unexpected_keys.extend(dropped)
         return result
 
     def enable_decoder(self):
@@ -229,10 +236,14 @@ class AutoencoderKL(nn.Module):
         ctx = _native.get_context(device)
         params = list(self.encoder.named_parameters())
         key = (id(ctx), tuple((p.data_ptr(), p._version) for _, p in params))
-        if key != self._native_key:
+        # the native context is process-wide per device and holds ONE encoder weight set: re-upload when these
+        # parameters changed OR when another AutoencoderKL instance loaded its weights into the context since
+        if key != self._native_key or getattr(ctx, "_enc_owner", None) is not self:
             ctx.configure_encoder(vars(self.config))
             ctx.load_encoder({n: p for n, p in params})
             self._native_key = key
+            ctx._enc_owner = self
+            ctx._dec_owner = None   # configure_encoder resets the shared configuration the decoder was built on
         return ctx
 
     def _precision(self) -> int:
@@ -272,9 +283,10 @@ class AutoencoderKL(nn.Module):
         self.enable_decoder()
         params = list(self.decoder.named_parameters())
         key = (self._native_key, tuple((p.data_ptr(), p._version) for _, p in params))
-        if key != self._native_dec_key:
+        if key != self._native_dec_key or getattr(ctx, "_dec_owner", None) is not self:
             ctx.load_decoder({n: p for n, p in params})
             self._native_dec_key = key
+            ctx._dec_owner = self
         return ctx
 
     @torch.no_grad()

@@ -89,6 +89,7 @@ struct vt_ctx {
         cudaEvent_t done = nullptr;
         DevBuf arena;  // activation workspace
         DevBuf stats;  // GroupNorm (sum, sumsq) slots
+        DevBuf statpart;  // per-tile partials of the layer in flight (two-stage statistics, vt_internal.h)
         DevBuf mom;    // conv_out moments fp32 NHWC
         DevBuf hws;    // tag-head workspace when the head runs per micro-batch on this lane (vt_infer_host)
     } lanes[2];
@@ -376,6 +377,7 @@ struct EncRun {
     double* stats_base;
     int stats_used = 0;
     int groups;
+    StatsScratch ws{};  // this lane's partial buffer for the epilogue statistics
     int use_fused = 1;  // GroupNorm+SiLU fused into the 3x3 convs (VT_B200_NO_FUSED_GN=1 disables)
     int use_flash = 1;  // fused attention kernel (VT_B200_NO_FLASH=1: score-matrix path)
 
@@ -404,7 +406,7 @@ struct EncRun {
             }
             return 0;
         }
-        op.stats = st;
+        op.stats = st; op.stats_ws = ws;
         return launch_conv(op, s, c->prof);
     }
     int gemm(GemmOp& op, long long rows_for_stats) {
@@ -416,6 +418,7 @@ struct EncRun {
             if (st) VT_TRY(launch_gn_stats(op.out, 1, st, op.batch, rows_for_stats, op.N, groups, s, c->prof));
             return 0;
         }
+        op.stats_ws = ws;
         return launch_gemm(op, s, c->prof);
     }
     // normalised operand: fp16 in 16-bit mode (it feeds TMA), fp32 in verification mode
@@ -430,7 +433,7 @@ struct EncRun {
         op.in = x.p; op.N = n; op.H = H; op.W = Wd; op.Cin = w.Cin; op.Cout = w.Cout; op.gn_stats = st_x;
         op.gamma = nw.gamma; op.beta = nw.beta; op.w = w.w16; op.bias = w.bias;
         if (residual) { op.residual = residual->p; op.residual_fp32 = residual->fmt == FMT_F32; }
-        op.out = out.p; op.out_fmt = out.fmt; op.stats = st;
+        op.out = out.p; op.out_fmt = out.fmt; op.stats = st; op.stats_ws = ws;
         return launch_conv3_fused(op, s, c->prof);
     }
     // ResnetBlock2D: out = x (+shortcut) + conv2(silu(norm2(conv1(silu(norm1(x))))))
@@ -657,10 +660,11 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
     const int groups = cfg.norm_num_groups;
     const int max_slots = 64;
     VT_TRY(L.stats.ensure(static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double)));
-    VT_CUDA(cudaMemsetAsync(L.stats.p, 0, static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double), s));
+    VT_TRY(L.statpart.ensure(stats_scratch_bytes(n, H, Wd)));
     VT_TRY(L.mom.ensure(static_cast<size_t>(n) * tokens * 2 * LC * sizeof(float)));
 
     EncRun R{c, s, fp32, n, static_cast<double*>(L.stats.p), 0, groups};
+    R.ws.part = static_cast<float*>(L.statpart.p); R.ws.bytes = L.statpart.cap;
     {
         const char* e = getenv("VT_B200_NO_FUSED_GN");
         R.use_fused = !(e && e[0] == '1');
@@ -680,7 +684,7 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
         // operand rows built in shared memory from the image itself (vt_convin.cuh)
         ConvInOp op;
         op.img = img + img_stride * img0; op.in_fmt = a->in_fmt; op.N = n; op.H = H; op.W = Wd;
-        op.w = c->conv_in.w16; op.bias = c->conv_in.bias; op.out = X.p; op.stats = st_x;
+        op.w = c->conv_in.w16; op.bias = c->conv_in.bias; op.out = X.p; op.stats = st_x; op.stats_ws = R.ws;
         VT_TRY(launch_conv_in(op, s, c->prof));
     } else {
         VT_TRY(launch_im2col3x3(img + img_stride * img0, a->in_fmt, Hb, R.opd_fmt(), n, H, Wd, s, c->prof));
@@ -775,9 +779,10 @@ int run_decoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_decode_args* a, 
     char* ab = base + 4 * act;
     const int max_slots = 64;
     VT_TRY(L.stats.ensure(static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double)));
-    VT_CUDA(cudaMemsetAsync(L.stats.p, 0, static_cast<size_t>(max_slots) * n * groups * 2 * sizeof(double), s));
+    VT_TRY(L.statpart.ensure(stats_scratch_bytes(n, H, Wd)));
 
     EncRun R{c, s, fp32, n, static_cast<double*>(L.stats.p), 0, groups};
+    R.ws.part = static_cast<float*>(L.statpart.p); R.ws.bytes = L.statpart.cap;
     {
         const char* e = getenv("VT_B200_NO_FUSED_GN");
         R.use_fused = !(e && e[0] == '1');
@@ -822,6 +827,7 @@ int run_decoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_decode_args* a, 
                     op.in = X.p; op.N = n; op.Hin = h; op.Win = w_; op.Cin = C; op.ksize = 3; op.stride = 1;
                     op.in_f16 = 0; op.w = c->upsample_sp[b] + static_cast<size_t>(par) * C * 4 * C; op.Cout = C;
                     op.bias = uw.bias; op.out = out.p; op.out_fmt = out.fmt; op.stats = st_o;
+                    op.stats_ws = R.ws; op.stats_ws.parts = 4; op.stats_ws.part_index = par;   // one tensor, four launches
                     op.up2 = 1; op.up_py = par >> 1; op.up_px = par & 1;
                     VT_TRY(launch_conv(op, s, c->prof));
                 }
@@ -909,7 +915,7 @@ int vt_ctx_destroy(vt_ctx* c) {
     free_params(c->dparams);
     free_params(c->hparams);
     for (auto& L : c->lanes) {
-        L.arena.release(); L.stats.release(); L.mom.release(); L.hws.release();
+        L.arena.release(); L.stats.release(); L.statpart.release(); L.mom.release(); L.hws.release();
         if (L.stream) cudaStreamDestroy(L.stream);
         if (L.done) cudaEventDestroy(L.done);
     }
@@ -1538,10 +1544,13 @@ int vt_op_conv2d(vt_ctx* c, const float* x, const float* w, const float* bias, c
     const size_t b_r = align_up(static_cast<size_t>(N) * Ho * Wo * Cout * es, 256);
     const size_t b_s = align_up(static_cast<size_t>(N) * Ho * Wo * std::max(Cs, 1) * es, 256);
     const size_t b_w = align_up(static_cast<size_t>(Cout) * Ktot * es, 256);
-    VT_TRY(c->opws.ensure(b_x + b_o + b_r + b_s + b_w));
+    const size_t b_st = align_up(stats_scratch_bytes(N, Ho, Wo), 256);
+    VT_TRY(c->opws.ensure(b_x + b_o + b_r + b_s + b_w + b_st));
     char* p = static_cast<char*>(c->opws.p);
     void* dx = p; void* dout = p + b_x; void* dres = p + b_x + b_o; void* dsc = p + b_x + b_o + b_r;
     void* dw = p + b_x + b_o + b_r + b_s;
+    StatsScratch ws;
+    ws.part = reinterpret_cast<float*>(p + b_x + b_o + b_r + b_s + b_w); ws.bytes = b_st;
     VT_TRY(launch_nchw_to_nhwc(x, dx, fmt, N, Cin, 1LL * H * W, s));
     if (residual) VT_TRY(launch_nchw_to_nhwc(residual, dres, raw, N, Cout, 1LL * Ho * Wo, s));
     if (sc_x) VT_TRY(launch_nchw_to_nhwc(sc_x, dsc, raw, N, Cs, 1LL * Ho * Wo, s));
@@ -1560,12 +1569,11 @@ int vt_op_conv2d(vt_ctx* c, const float* x, const float* w, const float* bias, c
     op.stride = stride; op.w = dw;
     op.Cout = Cout; op.sc_in = sc_x ? dsc : nullptr; op.Cs = Cs; op.bias = bias; op.residual = residual ? dres : nullptr;
     op.out = dout; op.out_fmt = FMT_F32;
-    if (stats) VT_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * N * 64, s));
     if (fp32) {
         VT_TRY(launch_conv_fp32(op, s, c->prof));
         if (stats) VT_TRY(launch_gn_stats(dout, 1, stats, N, 1LL * Ho * Wo, Cout, 32, s, c->prof));
     } else {
-        op.stats = stats;
+        op.stats = stats; op.stats_ws = ws;
         VT_TRY(launch_conv(op, s, c->prof));
     }
     return launch_nhwc_to_nchw(dout, FMT_F32, out, N, Cout, 1LL * Ho * Wo, s);
@@ -1587,7 +1595,8 @@ int vt_op_conv3_fused(vt_ctx* c, const float* x, const float* gamma, const float
     const size_t b_w = align_up(static_cast<size_t>(Cout) * Ktot * 2, 1024);
     const size_t b_s = 1024 + static_cast<size_t>(N) * 64 * sizeof(double);
     const size_t b_c = align_up(static_cast<size_t>(N) * HW * std::max(Cs, 1) * 2, 1024);
-    VT_TRY(c->opws.ensure(b_x + b_o + b_r + b_w + b_s + b_c));
+    const size_t b_st = align_up(stats_scratch_bytes(N, H, W), 1024);
+    VT_TRY(c->opws.ensure(b_x + b_o + b_r + b_w + b_s + b_c + b_st));
     char* p = static_cast<char*>(c->opws.p);
     void* dx = p; void* dout = p + b_x; void* dres = p + b_x + b_o; void* dw = p + b_x + b_o + b_r;
     double* st_in = reinterpret_cast<double*>(p + b_x + b_o + b_r + b_w);
@@ -1598,13 +1607,12 @@ int vt_op_conv3_fused(vt_ctx* c, const float* x, const float* gamma, const float
     pack_weight_kernel<FMT_F16><<<256, 256, 0, s>>>(w, dw, Cout, Cin, 3, Ktot, 0);
     if (sc_w) pack_weight_kernel<FMT_BF16><<<256, 256, 0, s>>>(sc_w, dw, Cout, Cs, 1, Ktot, 9 * Cin);
     VT_CUDA(cudaGetLastError());
-    VT_CUDA(cudaMemsetAsync(st_in, 0, static_cast<size_t>(N) * 64 * sizeof(double), s));
     VT_TRY(launch_gn_stats(dx, 0, st_in, N, HW, Cin, 32, s, c->prof));
-    if (stats) VT_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * N * 64, s));
     Conv3FusedOp op;
     op.in = dx; op.N = N; op.H = H; op.W = W; op.Cin = Cin; op.Cout = Cout; op.gn_stats = st_in; op.gamma = gamma;
     op.beta = beta; op.eps = eps; op.silu = silu; op.w = dw; op.bias = bias; op.residual = residual ? dres : nullptr;
     op.out = dout; op.out_fmt = FMT_F32; op.stats = stats; op.sc_in = sc_x ? dsc : nullptr; op.Cs = Cs;
+    op.stats_ws.part = reinterpret_cast<float*>(p + b_x + b_o + b_r + b_w + b_s + b_c); op.stats_ws.bytes = b_st;
     VT_TRY(launch_conv3_fused(op, s, c->prof));
     return launch_nhwc_to_nchw(dout, FMT_F32, out, N, Cout, HW, s);
 }

@@ -89,24 +89,12 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
     constexpr int NPASS = Cfg::PASSES_PER_SUB;             // 32-pixel passes per warp
     const int pc0 = (ew >> 2) * NPASS;                     // first pass of this warp (two warps per quadrant)
 
-    double* s_run = reinterpret_cast<double*>(ctrl + 256);
     float* s_part = reinterpret_cast<float*>(ctrl + 256 + 1024);  // [2][EPI_WARPS][8 slots][2]
     if (STATS) {
-        if (et < 128) s_run[et] = 0.0;
         for (int i = et; i < Cfg::PART_FLOATS; i += 32 * EPI_WARPS) s_part[i] = 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
     }
-    int run_img = -1, run_nb = -1;
-    auto flush_stats = [&]() {
-        const int nvals = 2 * 128 / P.group_size;
-        if (run_img >= 0 && et < nvals) {
-            const int g_total = P.n_total / P.group_size;
-            const int grp = run_nb * (128 / P.group_size) + (et >> 1);
-            if (grp < g_total)
-                atomicAdd(P.stats + (static_cast<long long>(run_img) * g_total + grp) * 2 + (et & 1), s_run[et]);
-            s_run[et] = 0.0;
-        }
-    };
+    int ptile = 0;   // pixel tile index inside the image (row of the statistics partial buffer)
     auto decode = [&](uint32_t tile, int& nb, int& x0, int& y0, int& img) {
         nb = static_cast<int>(tile % static_cast<uint32_t>(P.n_blocks));
         uint32_t m = tile / static_cast<uint32_t>(P.n_blocks);
@@ -114,6 +102,7 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
         m /= static_cast<uint32_t>(P.tiles_x);
         const int ty = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
         img = static_cast<int>(m / static_cast<uint32_t>(P.tiles_y));
+        ptile = ty * P.tiles_x + tx;
         x0 = tx * Cfg::PX_W;
         y0 = ty * Cfg::PX_H;
     };
@@ -126,10 +115,7 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
         const bool ch_ok = ch0 < P.n_total;
         const uint32_t acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        if (STATS && (img != run_img || nb != run_nb)) {
-            flush_stats();
-            run_img = img; run_nb = nb;
-        }
+        const int tile_row = ptile;   // decode() of the NEXT tile (residual prefetch below) overwrites ptile
         float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
         if (P.bias != nullptr && ch_ok) {
             b0 = __ldg(reinterpret_cast<const float4*>(P.bias + ch0));
@@ -262,7 +248,8 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
             if (lane < 4) *reinterpret_cast<float4*>(part + lane * 4) = make_float4(s_lo, q_lo, s_hi, q_hi);
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
             const int nvals = 2 * 128 / P.group_size;
-            if (et < nvals) {
+            const int g_total = P.n_total / P.group_size;
+            if (et < nvals && nb * (128 / P.group_size) + (et >> 1) < g_total) {
                 // value et = (group g, sum|sumsq): 4-channel slots g*gs/4 .. ; slot s lives in warp q' = s/8
                 const int g = et >> 1, which = et & 1;
                 const int spg = P.group_size / 4;
@@ -274,11 +261,12 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
                     for (int h = 0; h < EPI_WARPS / 4; ++h)
                         tot += s_part[(acc * EPI_WARPS + wsel + 4 * h) * 16 + (sidx & 7) * 2 + which];
                 }
-                s_run[et] += static_cast<double>(tot);
+                // this tile's own row of the partial buffer: no atomics, gn_finalize_kernel adds the rows in order
+                const long long row = static_cast<long long>(img) * P.stats_rows + P.stats_row0 + tile_row;
+                P.stats_part[(row * g_total + nb * (128 / P.group_size) + g) * 2 + which] = tot;
             }
         }
     }
-    if (STATS) flush_stats();
 }
 
 template <int BLOCK_N, int MT, bool TR, bool PAIR>

@@ -99,61 +99,98 @@ int launch_im2col3x3(const void* in, int fmt, void* out, int out_fmt, int N, int
 }
 
 // ------------------------------------------------------------------------------------------
-// GroupNorm statistics (used by the fp32 verification path and by tests; the bf16 path gets
-// its statistics from the producing conv's epilogue).  x: [N][HW][C] ; stats: [N][G][2] double,
-// ACCUMULATED into (caller zeroes).  grid = (chunks, N); each block reduces a pixel range.
+// GroupNorm statistics (used by the fp32 verification path, the unfused fallbacks and tests; the 16-bit
+// path gets its statistics from the producing contraction's epilogue + gn_finalize_kernel).
+// x: [N][HW][C] ; stats: [N][G][2] double (sum, sum of squares), WRITTEN.  One block per (image, group),
+// fixed pixel -> thread assignment and a fixed-order tree: the result depends on the image only, not on the
+// batch it is part of (no atomics).
 template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ stats,
                                                        long long HW, int C, int G) {
-    __shared__ double sh[2 * 32];
-    const int n = blockIdx.y;
-    const int cpg = C / G;
-    for (int i = threadIdx.x; i < 2 * G; i += 256) sh[i] = 0.0;
-    __syncthreads();
-    // thread -> fixed channel quad (4 channels); C/4 divides 256 for C in {128,256,512}; general C
-    // handled by looping the quad index.
-    const int quads = C / 4;
-    const long long chunk = (HW + gridDim.x - 1) / gridDim.x;
-    const long long p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
-    for (int qd = threadIdx.x % min(quads, 256); qd < quads; qd += 256) {
-        const int ppb = max(1, 256 / quads);  // pixels per block step
-        const int psub = threadIdx.x / quads;
-        double s = 0.0, ss = 0.0;
-        if (psub < ppb) {
-            float fs = 0.f, fss = 0.f;
-            int cnt = 0;
-            for (long long p = p0 + psub; p < p1; p += ppb) {
-                const T* px = x + (1LL * n * HW + p) * C + qd * 4;
-                float a, b, c, d;
-                if constexpr (sizeof(T) == 2) {
-                    const uint2 u = *reinterpret_cast<const uint2*>(px);
-                    a = bf16_lo(u.x); b = bf16_hi(u.x); c = bf16_lo(u.y); d = bf16_hi(u.y);
-                } else {
-                    const float4 f = *reinterpret_cast<const float4*>(px);
-                    a = f.x; b = f.y; c = f.z; d = f.w;
-                }
-                fs += (a + b) + (c + d);
-                fss += (a * a + b * b) + (c * c + d * d);
-                if (++cnt == 64) { s += fs; ss += fss; fs = fss = 0.f; cnt = 0; }
+    __shared__ double sh[2][256];
+    const int g = blockIdx.x, n = blockIdx.y;
+    const int cpg = C / G;              // a multiple of 4
+    const int quads = cpg / 4;          // 16-byte (fp32) / 8-byte (bf16) pieces of one pixel's group slice
+    const int qd = threadIdx.x % quads;
+    const int lanes = 256 / quads;      // pixel lanes
+    const int pl = threadIdx.x / quads;
+    double s = 0.0, ss = 0.0;
+    if (pl < lanes) {
+        float fs = 0.f, fss = 0.f;
+        int cnt = 0;
+        for (long long p = pl; p < HW; p += lanes) {
+            const T* px = x + (1LL * n * HW + p) * C + g * cpg + qd * 4;
+            float a, b, c, d;
+            if constexpr (sizeof(T) == 2) {
+                const uint2 u = *reinterpret_cast<const uint2*>(px);
+                a = bf16_lo(u.x); b = bf16_hi(u.x); c = bf16_lo(u.y); d = bf16_hi(u.y);
+            } else {
+                const float4 f = *reinterpret_cast<const float4*>(px);
+                a = f.x; b = f.y; c = f.z; d = f.w;
             }
-            s += fs; ss += fss;
+            fs += (a + b) + (c + d);
+            fss += (a * a + b * b) + (c * c + d * d);
+            if (++cnt == 64) { s += fs; ss += fss; fs = fss = 0.f; cnt = 0; }
         }
-        const int g = (qd * 4) / cpg;  // cpg is a multiple of 4
-        atomicAdd(&sh[2 * g], s);
-        atomicAdd(&sh[2 * g + 1], ss);
+        s += fs; ss += fss;
     }
+    sh[0][threadIdx.x] = s;
+    sh[1][threadIdx.x] = ss;
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += 256) atomicAdd(&stats[1LL * n * 2 * G + i], sh[i]);
+    for (int w = 128; w >= 1; w >>= 1) {
+        if (threadIdx.x < w) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + w];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 2) stats[(1LL * n * G + g) * 2 + threadIdx.x] = sh[threadIdx.x][0];
 }
 
 int launch_gn_stats(const void* x, int is_fp32, double* stats, int N, long long HW, int C, int G, cudaStream_t s,
                     Profiler* prof) {
-    VT_CHECK(G == 32 && C % (4 * G) == 0, "GroupNorm statistics need 32 groups of a multiple of 4 channels");
-    const int chunks = static_cast<int>(std::min<long long>((HW + 63) / 64, std::max(1, sm_count() * 8 / N)));
-    dim3 grid(chunks, N);
+    VT_CHECK(G == 32 && C % (4 * G) == 0 && C / (4 * G) <= 256, "GroupNorm statistics need 32 groups of a multiple of 4 channels");
+    dim3 grid(G, N);
     profiler_begin(prof, KC_GN_APPLY, s, 0, 1.0 * N * HW * C * (is_fp32 ? 4 : 2));
     if (is_fp32) gn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), stats, HW, C, G);
     else gn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), stats, HW, C, G);
+    profiler_end(prof, KC_GN_APPLY, s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Second stage of the epilogue statistics (vt_igemm.cuh / vt_conv3.cuh): part[img][tile][G][2] fp32 per-tile
+// (sum, sumsq) -> stats[img][G][2] fp64.  One block per (image, group): thread (lane = t/2, which = t%2) adds
+// tiles lane, lane+64, ... in fp64, then a fixed-order tree over the 64 lanes.  The order depends on the tile
+// count only, so an image's statistics are the same bits in any batch.
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ part, double* __restrict__ stats,
+                                                          int tiles, int G) {
+    __shared__ double sh[128];
+    const int g = blockIdx.x, n = blockIdx.y;
+    const int which = threadIdx.x & 1, lane = threadIdx.x >> 1;
+    const float* p = part + (1LL * n * tiles * G + g) * 2 + which;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // four chains in flight; combined in a fixed order
+    int t = lane;
+    for (; t + 192 < tiles; t += 256) {
+        a0 += static_cast<double>(__ldg(p + 1LL * t * G * 2));
+        a1 += static_cast<double>(__ldg(p + 1LL * (t + 64) * G * 2));
+        a2 += static_cast<double>(__ldg(p + 1LL * (t + 128) * G * 2));
+        a3 += static_cast<double>(__ldg(p + 1LL * (t + 192) * G * 2));
+    }
+    for (; t < tiles; t += 64) a0 += static_cast<double>(__ldg(p + 1LL * t * G * 2));
+    sh[threadIdx.x] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    for (int w = 32; w >= 1; w >>= 1) {
+        if (lane < w) sh[threadIdx.x] += sh[threadIdx.x + 2 * w];
+        __syncthreads();
+    }
+    if (threadIdx.x < 2) stats[(1LL * n * G + g) * 2 + threadIdx.x] = sh[threadIdx.x];
+}
+
+int launch_gn_finalize(const float* part, double* stats, int N, int tiles, int G, cudaStream_t s, Profiler* prof) {
+    VT_CHECK(part && stats && N > 0 && tiles > 0 && G > 0, "GroupNorm finalize: bad arguments");
+    profiler_begin(prof, KC_GN_APPLY, s, 0, 8.0 * N * tiles * G);
+    gn_finalize_kernel<<<dim3(G, N), 128, 0, s>>>(part, stats, tiles, G);
     profiler_end(prof, KC_GN_APPLY, s);
     VT_CUDA(cudaGetLastError());
     return 0;

@@ -336,22 +336,19 @@ int launch_flash_attention(const FlashOp& op, cudaStream_t stream, Profiler* pro
         uint32_t box[3] = {64, 64, 1};      // 64 keys x one CTA's 64 of the 128 d_v rows
         VT_TRY(make_tmap(&tv, op.vt, 3, dims, str, box));
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        VT_CUDA(cudaFuncSetAttribute(flash_d512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLASH_SMEM));
-        attr_set = true;
-    }
+    static SmemAttrOnce once;
+    VT_TRY(ensure_dyn_smem(once, flash_d512_kernel, FLASH_SMEM));
     const int q_tiles = (op.tokens + FQ - 1) / FQ;
     const int q_pairs = (q_tiles + 1) / 2;
     const int grid = op.n * q_pairs * 4;   // pair x d_v half
     const double key_t = (op.tokens + FK - 1) / FK * FK;
     // algorithmic work: QK^T and PV once each (the second QK^T of the d_v split is overhead, not counted)
     const double flops = 2.0 * op.n * q_tiles * FQ * key_t * FD * 2.0;
-    profiler_begin(prof, KC_IGEMM, stream, flops, 2.0 * op.n * op.tokens * FD * 4.0);
+    profiler_begin(prof, KC_FLASH, stream, flops, 2.0 * op.n * op.tokens * FD * 4.0);
     flash_d512_kernel<<<grid, FLASH_THREADS, FLASH_SMEM, stream>>>(tq, tk, tv, static_cast<__half*>(op.out), op.bias_v,
                                                                    op.tokens, q_pairs,
                                                                    op.scale * 1.4426950408889634f);
-    profiler_end(prof, KC_IGEMM, stream);
+    profiler_end(prof, KC_FLASH, stream);
     VT_CUDA(cudaGetLastError());
     return 0;
 }

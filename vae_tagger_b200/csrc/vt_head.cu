@@ -593,11 +593,8 @@ int launch_head_confidence(const float* logits, float* conf_sorted, long long* i
     while (p2 < T) p2 <<= 1;
     VT_CHECK(p2 <= 16384, "confidence sort supports up to 16384 tags");
     const size_t smem = static_cast<size_t>(p2) * 8;
-    static bool attr = false;
-    if (!attr) {
-        VT_CUDA(cudaFuncSetAttribute(head_confidence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-        attr = true;
-    }
+    static SmemAttrOnce once;
+    VT_TRY(ensure_dyn_smem(once, head_confidence_kernel, 16384 * 8));
     const int threads = std::max(32, std::min(1024, p2 / 2));
     profiler_begin(prof, KC_HEAD, s, 0, 16.0 * B * T);
     head_confidence_kernel<<<B, threads, smem, s>>>(logits, conf_sorted, idx_sorted, count, probs, T, p2, thr);

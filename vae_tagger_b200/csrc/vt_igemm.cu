@@ -47,6 +47,24 @@ int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
     return 0;
 }
 
+// two-stage GroupNorm statistics: point the kernel at the partial buffer (before the launch) ...
+static int bind_stats(IgemmParams& P, const StatsScratch& ws) {
+    if (P.stats == nullptr) return 0;
+    VT_CHECK(ws.parts >= 1 && ws.part_index >= 0 && ws.part_index < ws.parts, "bad statistics part index");
+    const int tiles = P.tiles_x * P.tiles_y;
+    const size_t need = static_cast<size_t>(P.NB) * ws.parts * tiles * (P.n_total / P.group_size) * 2 * sizeof(float);
+    VT_CHECK(ws.part != nullptr && ws.bytes >= need, "fused GroupNorm statistics need a stats_ws scratch buffer");
+    P.stats_part = ws.part;
+    P.stats_rows = ws.parts * tiles;
+    P.stats_row0 = ws.part_index * tiles;
+    return 0;
+}
+// ... and reduce the per-tile rows in a fixed order right behind it on the same stream
+static int finish_stats(const IgemmParams& P, cudaStream_t stream, Profiler* prof) {
+    if (P.stats == nullptr || P.stats_row0 + P.tiles_x * P.tiles_y != P.stats_rows) return 0;   // not the last part
+    return launch_gn_finalize(P.stats_part, P.stats, P.NB, P.stats_rows, P.n_total / P.group_size, stream, prof);
+}
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -62,12 +80,8 @@ template <int BLOCK_N, int MT>
 static int launch_variant(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const IgemmParams& P,
                           cudaStream_t stream) {
     using Cfg = IgemmCfg<BLOCK_N, MT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VT_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    static SmemAttrOnce once;
+    VT_TRY(ensure_dyn_smem(once, igemm_kernel<BLOCK_N, MT>, Cfg::SMEM_BYTES));
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y * P.n_blocks;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     igemm_kernel<BLOCK_N, MT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, P);
@@ -214,10 +228,12 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     }
     const double flops = 2.0 * op.N * Hout * Wout * static_cast<double>(op.Cout) * Ktot;
     const double bytes = 2.0 * op.N * (1.0 * op.Hin * op.Win * op.Cin + 1.0 * Hout * Wout * op.Cout);
+    VT_TRY(bind_stats(P, op.stats_ws));
     profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
     int rc = dispatch(block_n, a0, a1, b, P, stream);
     profiler_end(prof, KC_IGEMM, stream);
-    return rc;
+    VT_TRY(rc);
+    return finish_stats(P, stream, prof);
 }
 
 int launch_conv_in(const ConvInOp& op, cudaStream_t stream, Profiler* prof) {
@@ -244,32 +260,26 @@ int launch_conv_in(const ConvInOp& op, cudaStream_t stream, Profiler* prof) {
         VT_TRY(make_tmap(&b, op.w, 3, dims, str, box));
     }
     ConvInParams Q{op.img, op.in_fmt};
-    static bool attr_set = false;
-    if (!attr_set) {
-        VT_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvInCfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    static SmemAttrOnce once;
+    VT_TRY(ensure_dyn_smem(once, conv_in_kernel, ConvInCfg::SMEM_BYTES));
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     const double flops = 2.0 * op.N * op.H * op.W * 128.0 * 27.0;
     const double bytes = 1.0 * op.N * op.H * op.W * ((op.in_fmt ? 3.0 : 12.0) + 256.0);
-    profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
+    VT_TRY(bind_stats(P, op.stats_ws));
+    profiler_begin(prof, KC_CONVIN, stream, flops, bytes);
     conv_in_kernel<<<grid, ConvInCfg::THREADS, ConvInCfg::SMEM_BYTES, stream>>>(b, P, Q);
-    profiler_end(prof, KC_IGEMM, stream);
+    profiler_end(prof, KC_CONVIN, stream);
     VT_CUDA(cudaGetLastError());
-    return 0;
+    return finish_stats(P, stream, prof);
 }
 
 template <int BLOCK_N, int MT, bool TR, bool PAIR>
 static int launch_conv3_variant(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sc, const IgemmParams& P,
                                 cudaStream_t stream) {
     using Cfg = Conv3Cfg<BLOCK_N, MT, TR, PAIR>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VT_CUDA(cudaFuncSetAttribute(conv3_fused_kernel<BLOCK_N, MT, TR, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    static SmemAttrOnce once;
+    VT_TRY(ensure_dyn_smem(once, conv3_fused_kernel<BLOCK_N, MT, TR, PAIR>, Cfg::SMEM_BYTES));
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y * P.n_blocks;
     int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     if (!PAIR) {
@@ -348,12 +358,15 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
     }
     const double flops = 2.0 * op.N * H * W * static_cast<double>(op.Cout) * (9 * op.Cin + (op.sc_in ? op.Cs : 0));
     const double bytes = 2.0 * op.N * H * W * (1.0 * op.Cin + op.Cout);
-    profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
+    VT_TRY(bind_stats(P, op.stats_ws));
+    const KernelClass kc = tr ? KC_CONV3_T : KC_CONV3;
+    profiler_begin(prof, kc, stream, flops, bytes);
     int rc = tr ? launch_conv3_variant<128, 1, true, false>(a, b, sc, P, stream)
                 : pair ? launch_conv3_variant<256, 1, false, true>(a, b, sc, P, stream)
                        : launch_conv3_variant<256, 1, false, false>(a, b, sc, P, stream);
-    profiler_end(prof, KC_IGEMM, stream);
-    return rc;
+    profiler_end(prof, kc, stream);
+    VT_TRY(rc);
+    return finish_stats(P, stream, prof);
 }
 
 int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
@@ -407,10 +420,12 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     const double flops = 2.0 * op.batch * static_cast<double>(op.M) * op.N * op.K;
     const double bytes = 2.0 * op.batch * (1.0 * op.M * op.K + 1.0 * op.N * op.K) +
                          (op.out_fmt == 1 ? 4.0 : 2.0) * op.batch * op.M * op.N;
+    VT_TRY(bind_stats(P, op.stats_ws));
     profiler_begin(prof, KC_IGEMM, stream, flops, bytes);
     int rc = dispatch(block_n, a, a, b, P, stream);
     profiler_end(prof, KC_IGEMM, stream);
-    return rc;
+    VT_TRY(rc);
+    return finish_stats(P, stream, prof);
 }
 
 }  // namespace vt

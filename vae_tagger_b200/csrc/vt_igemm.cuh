@@ -62,8 +62,13 @@ struct IgemmParams {
     long long out_bstride;  // elements between consecutive images of out / residual
     int out_row_pitch;      // elements between output rows (0: W * ld_out) -- a strided output view, e.g. one
     int out_px_stride;      // parity of a 2x-upsampled image; elements between output pixels (0: ld_out)
-    double* stats;     // [NB][n_total/group_size][2] running (sum, sum of squares): fp32 per-tile partials,
-                       // fp64 atomics across tiles (keeps E[x^2]-E[x]^2 well conditioned)
+    // GroupNorm statistics of the output, two stages, no atomics (results do not depend on the batch composition
+    // or on which CTA processed which tile): every CTA tile stores its fp32 (sum, sum of squares) per group to
+    // stats_part[img][pixel tile][group][2]; gn_finalize_kernel adds the tiles of an image in index order in fp64
+    // (keeps E[x^2]-E[x]^2 well conditioned) into stats[img][group][2]
+    float* stats_part;
+    int stats_rows, stats_row0;   // rows per image in stats_part (>= pixel tiles per image) / first row of this launch
+    double* stats;
     IgemmSlab slabs[IGEMM_MAX_SLABS];
     // ---- fused GroupNorm+SiLU 3x3 convolution only (vt_conv3.cuh)
     const double* gn_stats;  // [NB][32][2] (sum, sumsq) of the INPUT tensor
@@ -139,31 +144,18 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
     const int rlane = lane >> 2;        // phase B: row slot 0..7
     const int j8 = (lane & 3) * 8;      // phase B: 8-column offset inside the 32-column pass
 
-    double* s_run = reinterpret_cast<double*>(ctrl + 256);                 // [128] fp64 running sums, slot et
     float* s_part = reinterpret_cast<float*>(ctrl + 256 + 1024);          // [2][EPI_WARPS][SLOTS][2]
     if (STATS) {
-        if (et < 128) s_run[et] = 0.0;
         for (int i = et; i < Cfg::PART_FLOATS; i += 32 * EPI_WARPS) s_part[i] = 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
     }
-    int run_img = -1, run_nb = -1;
-    auto flush_stats = [&]() {
-        const int nvals = 2 * BLOCK_N / P.group_size;
-        if (run_img >= 0 && et < nvals) {
-            const int g_total = P.n_total / P.group_size;
-            const int grp = run_nb * (BLOCK_N / P.group_size) + (et >> 1);
-            if (grp < g_total)
-                atomicAdd(P.stats + (static_cast<long long>(run_img) * g_total + grp) * 2 + (et & 1), s_run[et]);
-            s_run[et] = 0.0;
-        }
-    };
 
     // per-tile geometry: image, n-block, and for each sub-tile the element offset of this lane's first
     // row (i = 0) inside the image plus a 4-bit validity mask of its rows i = 0..3
     const int out_pxs = P.out_px_stride ? P.out_px_stride : static_cast<int>(P.ld_out);
     const int out_rowp = P.out_row_pitch ? P.out_row_pitch : P.W * static_cast<int>(P.ld_out);
     struct Geo {
-        int nb, img;
+        int nb, img, ptile;
         int off0[MT];
         unsigned vmask[MT];
     };
@@ -177,6 +169,7 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
         m /= static_cast<uint32_t>(P.tiles_x);
         const int ty = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
         g.img = static_cast<int>(m / static_cast<uint32_t>(P.tiles_y));
+        g.ptile = ty * P.tiles_x + tx;
         const int r0 = q * 32 + rlane;
 #pragma unroll
         for (int t = 0; t < MT; ++t) {
@@ -236,10 +229,6 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
         const uint32_t acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         float* part = s_part + (acc * EPI_WARPS + ew) * SLOTS * 2;
-        if (STATS && (geo.img != run_img || geo.nb != run_nb)) {
-            flush_stats();
-            run_img = geo.img; run_nb = geo.nb;
-        }
         const uint32_t next_tile = tile + gridDim.x;
         if (next_tile < total_tiles) {
             geometry(next_tile, ngeo);
@@ -377,10 +366,12 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
             }
         }
         if (STATS) {
-            // all epilogue warps have written their slots -> fold into the CTA's running fp64 sums
+            // all epilogue warps have written their slots -> this tile's (sum, sumsq) per group, added in a fixed
+            // order, stored to the tile's own row of the partial buffer
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
             const int nvals = 2 * BLOCK_N / P.group_size;  // (sum, sumsq) per group of this n-block
-            if (et < nvals) {
+            const int g_total = P.n_total / P.group_size;
+            if (et < nvals && geo.nb * (BLOCK_N / P.group_size) + (et >> 1) < g_total) {
                 const int g = et >> 1, which = et & 1;
                 const int slots_per_group = P.group_size / 4;
                 float tot = 0.f;
@@ -393,13 +384,13 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
                         *pv = 0.f;
                     }
                 }
-                s_run[et] += static_cast<double>(tot);
+                const long long row = static_cast<long long>(geo.img) * P.stats_rows + P.stats_row0 + geo.ptile;
+                P.stats_part[(row * g_total + geo.nb * (BLOCK_N / P.group_size) + g) * 2 + which] = tot;
             }
         }
         tile = next_tile;
         geo = ngeo;
     }
-    if (STATS) flush_stats();
 }
 
 template <int BLOCK_N, int MT>

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <algorithm>
+#include <atomic>
 #include <string>
 
 namespace vt {
@@ -37,6 +38,22 @@ const char* last_error();
         if (_r != 0) return _r;   \
     } while (0)
 
+// ---- cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: set it once per
+// (kernel, device), not once per process (one context per device may live in the same process)
+struct SmemAttrOnce {
+    std::atomic<unsigned long long> done{0};   // bit d: set on device d (devices >= 64 set it on every call)
+};
+template <typename F>
+int ensure_dyn_smem(SmemAttrOnce& once, F func, int bytes) {
+    int dev = 0;
+    VT_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = dev < 64 ? (1ull << dev) : 0ull;
+    if (bit && (once.done.load(std::memory_order_acquire) & bit)) return 0;
+    VT_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    once.done.fetch_or(bit, std::memory_order_release);
+    return 0;
+}
+
 // ---- kernel-class accounting (launch counts + optional CUDA-event timing per class)
 enum KernelClass {
     KC_IGEMM = 0,      // tcgen05 implicit-GEMM (convs, projections, QK^T, PV)
@@ -47,7 +64,15 @@ enum KernelClass {
     KC_HEAD = 5,       // tag head kernels
     KC_FP32 = 6,       // fp32 verification-mode kernels
     KC_MISC = 7,
-    KC_COUNT = 8
+    // the tensor kernels that carry the step, each under its own class so that bench.py can put every one of
+    // them against the roofline (KC_IGEMM keeps the remaining implicit-GEMM launches: stride-2 downsamples,
+    // projections, conv_out, the decoder's sub-pixel convs, the fallbacks)
+    KC_CONV3_T = 8,    // conv3_fused_kernel<128,1,true>: 128-channel layers, transposed accumulator
+    KC_CONV3 = 9,      // conv3_fused_kernel<256,...>: 256/512-channel layers (CTA pairs)
+    KC_FLASH = 10,     // flash_d512_kernel
+    KC_CONVIN = 11,    // conv_in_kernel
+    KC_BWD = 12,       // backward-pass contractions (dgrad / wgrad)
+    KC_COUNT = 13
 };
 struct Profiler;
 Profiler* profiler_create();
@@ -57,6 +82,24 @@ void profiler_begin(Profiler*, KernelClass, cudaStream_t, double flops, double b
 void profiler_end(Profiler*, KernelClass, cudaStream_t);
 // out: [KC_COUNT][4] = launches, milliseconds, flops, bytes ; resets when reset != 0
 int profiler_read(Profiler*, double* out, int reset);
+
+// Scratch for the two-stage GroupNorm statistics of a contraction's output: the kernel's epilogue stores one
+// fp32 (sum, sumsq) row of 32 groups per CTA tile, gn_finalize_kernel reduces the rows of an image in a fixed
+// order.  One buffer per stream (the finalize runs right behind the producer on the same stream).
+struct StatsScratch {
+    float* part = nullptr;
+    size_t bytes = 0;
+    // several launches that together produce ONE tensor (the four parities of a sub-pixel upsample conv): launch k
+    // of `parts` writes rows [k * tiles, (k+1) * tiles) of every image and only the last one reduces
+    int parts = 1, part_index = 0;
+};
+// enough rows for every tiling the launchers use on an H x W output (>= 64-pixel 2-D patches; conv_in: row tiles
+// of 256 pixels; GEMMs: 128 rows of M = H*W)
+inline size_t stats_scratch_bytes(int n, int H, int W) {
+    const size_t patches = ((static_cast<size_t>(H) + 7) / 8) * ((static_cast<size_t>(W) + 7) / 8);
+    const size_t row_tiles = static_cast<size_t>(H) * ((static_cast<size_t>(W) + 255) / 256);
+    return static_cast<size_t>(n) * std::max(patches, row_tiles) * 64 * sizeof(float) + 4096;
+}
 
 // ---- tcgen05 implicit GEMM (vt_igemm.cu)
 struct ConvOp {
@@ -78,6 +121,7 @@ struct ConvOp {
     void* out = nullptr;             // [N][Hout][Wout][Cout]
     int out_fmt = 0;                 // 0 bf16, 1 fp32, 2 fp16
     double* stats = nullptr;  // [N][32][2] GroupNorm (sum, sumsq) of the output (group = Cout/32 channels)
+    StatsScratch stats_ws;    // per-tile partials of the statistics (needed when stats != nullptr)
     float alpha = 1.f;
     // Sub-pixel form of "nearest 2x upsample, then conv3x3" (tcgen05 path only): the output pixels of parity
     // (up_py, up_px) of the 2Hin x 2Win result are a 2x2-tap conv of the SOURCE image whose taps are sums of the
@@ -96,6 +140,7 @@ struct ConvInOp {
     const float* bias = nullptr;
     void* out = nullptr;        // [N][H][W][128] bf16
     double* stats = nullptr;    // [N][32][2] or null
+    StatsScratch stats_ws;
 };
 int launch_conv_in(const ConvInOp& op, cudaStream_t stream, Profiler* prof);
 
@@ -118,6 +163,7 @@ struct GemmOp {
     long long ld_out = 0;       // default N
     long long out_bstride = 0;  // default M * ld_out (also used for residual)
     double* stats = nullptr;    // [batch][32][2] over (m, group of N/32 columns)
+    StatsScratch stats_ws;
     float alpha = 1.f;
 };
 int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof);
@@ -157,6 +203,7 @@ struct Conv3FusedOp {
     void* out = nullptr;
     int out_fmt = 0;
     double* stats = nullptr;           // (sum, sumsq) of the output
+    StatsScratch stats_ws;
 };
 int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* prof);
 
@@ -165,6 +212,8 @@ int launch_im2col3x3(const void* in, int fmt, void* out, int out_fmt, int N, int
                      Profiler*);
 int launch_gn_stats(const void* x, int is_fp32, double* stats, int N, long long HW, int C, int G, cudaStream_t,
                     Profiler*);
+// second stage of the epilogue statistics: part[N][tiles][G][2] fp32 -> stats[N][G][2] fp64, fixed order
+int launch_gn_finalize(const float* part, double* stats, int N, int tiles, int G, cudaStream_t, Profiler*);
 int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fmt, const double* stats, const float* gamma,
                     const float* beta, int N, long long HW, int C, int G, float eps, int silu, cudaStream_t,
                     Profiler*);

@@ -41,7 +41,10 @@ class FocalLoss(nn.Module):
         if inputs.device.type != "cuda":
             raise _native.NativeError("FocalLoss needs CUDA tensors on a B200 (no CPU fallback)")
         if self.reduction not in ("mean", "sum"):
-            raise NotImplementedError("the fused focal loss kernel provides reduction 'mean' and 'sum'")
+            # any other reduction: the per-element focal tensor, as the reference returns it (:52-56)
+            bce = torch.nn.functional.binary_cross_entropy_with_logits(inputs, targets.to(inputs.dtype),
+                                                                       reduction="none")
+            return self.alpha * (1 - torch.exp(-bce)) ** self.gamma * bce
         total = _FocalFn.apply(inputs, targets.to(inputs.dtype), float(self.alpha), float(self.gamma))
         return total / inputs.numel() if self.reduction == "mean" else total
 

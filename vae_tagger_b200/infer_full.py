@@ -102,11 +102,22 @@ def classify_batch(vae_model, decoder, pixel_values, threshold):
 
 
 def infer_and_classify(args):
+    """The reference's ``infer_and_classify`` (infer_full.py:73-139).  Under ``torchrun`` (WORLD_SIZE > 1) the image
+    list is sharded data-parallel over the GPUs of the box -- rank r takes a contiguous, cost-balanced span of the
+    (bucket-grouped) list, nothing crosses NVLink -- the per-image results are gathered on rank 0's host and rank 0
+    writes ONE ``classification_results.json`` identical to the single-GPU run."""
     from PIL import Image
+
+    from .sharding import dist_env, gather_to_rank0, image_cost, init_host_group, shard_by_cost
 
     if not torch.cuda.is_available():
         raise RuntimeError("vae_tagger_b200 needs a CUDA device (B200); there is no CPU path")
-    device = "cuda"
+    rank, world, local_rank = dist_env()
+    if world > 1:
+        local_rank %= torch.cuda.device_count()     # more ranks than GPUs (a test box): ranks share a device
+        torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}" if world > 1 else "cuda"
+    own_group = init_host_group(world)
     vae_model, decoder, tag_names = load_models(args, device)
     if not os.path.exists(args.image_path):
         raise FileNotFoundError(f"image path not found: {args.image_path}")
@@ -121,6 +132,12 @@ def infer_and_classify(args):
     for p in image_paths:
         shape = bucketing.assign_bucket(str(p)) if bucketing else (args.resolution, args.resolution)
         groups.setdefault(shape, []).append(p)
+    # the work list in processing order (group by group), and this rank's span of it
+    work = [(shape, p) for shape, paths in groups.items() for p in paths]
+    lo, hi = shard_by_cost([image_cost(w, h) for (w, h), _ in work], rank, world)
+    my_groups = {}
+    for shape, p in work[lo:hi]:
+        my_groups.setdefault(shape, []).append(p)
     results, errors = {}, 0
     bs = max(1, getattr(args, "batch_size", 8))
     if getattr(args, "gpu_preprocess", False):
@@ -132,7 +149,7 @@ def infer_and_classify(args):
 
         def decoded():
             nonlocal errors
-            for p in image_paths:
+            for _, p in work[lo:hi]:
                 try:
                     yield str(p), np.array(Image.open(p).convert("RGB"))   # writable copy
                 except Exception as e:  # noqa: BLE001 - the reference skips unreadable images (:130-132)
@@ -144,8 +161,8 @@ def infer_and_classify(args):
             conf, idx, cnt = classify_batch(vae_model, decoder, batch, args.confidence_threshold)
             for name, c, i, n in zip(names, conf, idx, cnt):
                 results[name] = format_result(c, i, n, tag_names)
-        groups = {}
-    for (w, h), paths in groups.items():
+        my_groups = {}
+    for (w, h), paths in my_groups.items():
         tf = get_image_transform(args.resolution, bucketing is not None, (w, h) if bucketing else None)
         for i0 in range(0, len(paths), bs):
             tensors, names = [], []
@@ -162,6 +179,13 @@ def infer_and_classify(args):
             conf, idx, cnt = classify_batch(vae_model, decoder, batch, args.confidence_threshold)
             for name, c, i, n in zip(names, conf, idx, cnt):
                 results[name] = format_result(c, i, n, tag_names)
+    results, errors = merge_rank_results(gather_to_rank0((results, errors), rank, world), [str(p) for _, p in work])
+    if own_group:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    if rank != 0:
+        return results
     print(f"done: {len(results)} ok, {errors} failed, {len(image_paths)} total")
     out_path = Path(args.output_dir) / "classification_results.json"
     out_path.parent.mkdir(parents=True, exist_ok=True)
@@ -169,6 +193,18 @@ def infer_and_classify(args):
         json.dump(results, f, indent=4, ensure_ascii=False)
     print(f"results saved to {out_path}")
     return results
+
+
+def merge_rank_results(gathered, order):
+    """Rank 0: merge the per-rank ``(results, errors)`` pairs into one dict in the processing order of the
+    single-GPU run (``order`` = every image name, group by group); other ranks (``gathered is None``) get ({}, 0)."""
+    if gathered is None:
+        return {}, 0
+    merged, errors = {}, 0
+    for res, err in gathered:
+        merged.update(res)
+        errors += err
+    return {name: merged[name] for name in order if name in merged}, errors
 
 
 def build_parser():

@@ -33,9 +33,19 @@ def load_vae(args, device="cuda"):
 def infer_and_save_latents(args):
     from PIL import Image
 
+    from .sharding import dist_env, gather_to_rank0, init_host_group, shard_range
+
     if not torch.cuda.is_available():
         raise RuntimeError("vae_tagger_b200 needs a CUDA device (B200); there is no CPU path")
-    vae_model = load_vae(args, "cuda")
+    # under torchrun: rank r encodes a contiguous shard of the image list on its own GPU (no collective), the
+    # latents are gathered on rank 0's host and rank 0 writes ONE latent_vectors.json
+    rank, world, local_rank = dist_env()
+    if world > 1:
+        local_rank %= torch.cuda.device_count()     # more ranks than GPUs (a test box): ranks share a device
+        torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}" if world > 1 else "cuda"
+    own_group = init_host_group(world)
+    vae_model = load_vae(args, device)
     transform = get_image_transform(args.resolution)
     if not os.path.exists(args.image_path):
         raise FileNotFoundError(f"image path not found: {args.image_path}")
@@ -45,9 +55,10 @@ def infer_and_save_latents(args):
         return {}
     latent_data, errors = {}, 0
     bs = max(1, getattr(args, "batch_size", 8))
-    for i0 in range(0, len(image_paths), bs):
+    lo, hi = shard_range(len(image_paths), rank, world)
+    for i0 in range(lo, hi, bs):
         tensors, names = [], []
-        for p in image_paths[i0:i0 + bs]:
+        for p in image_paths[i0:min(i0 + bs, hi)]:
             try:
                 tensors.append(transform(Image.open(p).convert("RGB")))
                 names.append(str(p))
@@ -56,10 +67,21 @@ def infer_and_save_latents(args):
                 print(f"skipping image {p}: {e}")
         if not tensors:
             continue
-        latent = vae_model.encode(torch.stack(tensors).pin_memory().to("cuda", non_blocking=True))
+        latent = vae_model.encode(torch.stack(tensors).pin_memory().to(device, non_blocking=True))
         flat = latent.reshape(latent.size(0), -1).cpu()
         for name, row in zip(names, flat):
             latent_data[name] = row.tolist()
+    gathered = gather_to_rank0((latent_data, errors), rank, world)
+    if own_group:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    if rank != 0:
+        return latent_data
+    latent_data, errors = {}, 0
+    for part, err in gathered:      # rank order = image-list order
+        latent_data.update(part)
+        errors += err
     print(f"done: {len(latent_data)} ok, {errors} failed, {len(image_paths)} total")
     out_path = Path(args.output_dir) / "latent_vectors.json"
     out_path.parent.mkdir(parents=True, exist_ok=True)

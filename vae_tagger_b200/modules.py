@@ -127,12 +127,18 @@ class _NativeHeadMixin:
             self._native_key = key
         return ctx
 
-    def _use_native(self) -> bool:
-        return not (self.training and torch.is_grad_enabled())
+    def _use_native(self, x=None) -> bool:
+        """Eval mode runs the CUDA head.  ``train()`` mode keeps the module's own graph (batch-statistics BatchNorm
+        and Dropout, as the reference -- also under ``no_grad``, e.g. ``get_confidence`` on a training-mode
+        decoder), and so does an eval-mode call whose input needs a gradient (the kernels build no autograd graph).
+        The native TRAINING step does not come through here: ``DecoderTrainer`` calls ``vt_head_train_step``."""
+        if self.training:
+            return False
+        return not (x is not None and torch.is_grad_enabled() and x.requires_grad)
 
     def get_confidence(self, latent_vectors):
         """sigmoid(logits) sorted descending with the tag indices (reference ``get_confidence``)."""
-        if self._use_native():
+        if self._use_native(latent_vectors):
             out = self._native_ctx(latent_vectors.device).tag(latent_vectors, want=("conf", "idx"))
             return out["conf"], out["idx"]
         with torch.no_grad():
@@ -172,7 +178,7 @@ class ClassificationDecoder(_NativeHeadMixin, nn.Module):
                                         plain_flat_dim=flat)
 
     def forward(self, latent_vectors):
-        if self._use_native():
+        if self._use_native(latent_vectors):
             return self._native_ctx(latent_vectors.device).tag(latent_vectors, want=("logits",))["logits"]
         x = self.adaptive_pool(latent_vectors) if self.use_adaptive_pooling else latent_vectors
         return self.classifier(x.reshape(latent_vectors.size(0), -1))
@@ -219,7 +225,7 @@ class AttentionClassificationDecoder(_NativeHeadMixin, nn.Module):
             attention_heads=self.attention_heads, use_cross_attention=self.use_cross_attention)
 
     def forward(self, latent_vectors):
-        if self._use_native():
+        if self._use_native(latent_vectors):
             return self._native_ctx(latent_vectors.device).tag(latent_vectors, want=("logits",))["logits"]
         x = latent_vectors
         if self.use_spatial_attention:

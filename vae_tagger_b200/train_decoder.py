@@ -85,6 +85,8 @@ class DecoderTrainer:
             p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.buffers = [b for b in decoder.buffers() if b.is_floating_point()]
+        self._buf_pending = []          # in-flight broadcasts of rank 0's BatchNorm buffers
+        self._events = None             # enable_timing(): CUDA-event pairs around the collective waits
         self._pending = None
         self._averaged = False
         self._micro = 0
@@ -180,7 +182,42 @@ class DecoderTrainer:
             seed=self._seed_base + self._micro * self.world + self.rank, class_weights=self._class_w)
         return loss[0]
 
+    # -- exposed time of the collectives ------------------------------------------------------
+    def enable_timing(self, on=True):
+        """Record CUDA-event pairs on the compute stream around every wait for a collective: the interval is the
+        time the compute stream was held up by it (0 when the exchange finished under the encoder forward)."""
+        self._events = {"allreduce_wait": [], "buffer_broadcast_wait": []} if on else None
+
+    def _timed_wait(self, key, waits):
+        if self._events is None:
+            for w in waits:
+                w.wait()
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for w in waits:
+            w.wait()
+        e1.record()
+        self._events[key].append((e0, e1))
+
+    def timing_summary(self, reset=True):
+        """Mean exposed milliseconds per wait, per kind (device time; synchronises)."""
+        if self._events is None:
+            return {}
+        torch.cuda.synchronize()
+        out = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v) if v else 0.0) for k, v in self._events.items()}
+        if reset:
+            self.enable_timing(True)
+        return out
+
     # -- gradient exchange ------------------------------------------------------------------
+    def _launch_buffer_broadcast(self):
+        """DDP ``broadcast_buffers`` semantics (every forward starts from rank 0's BatchNorm buffers,
+        train_decoder.py:194 under accelerate's DDP wrap), issued asynchronously right behind the step that
+        produced them: they travel under the next batch's encoder forward instead of in front of the head."""
+        if self.world > 1:
+            self._buf_pending = [dist.broadcast(b, src=0, group=self.pg, async_op=True) for b in self.buffers]
+
     def _launch_allreduce(self):
         if self.world > 1:
             self._pending = dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
@@ -193,7 +230,7 @@ class DecoderTrainer:
             return
         averaged, self._averaged = self._averaged, False
         if self.world > 1 and not averaged:
-            self._pending.wait()
+            self._timed_wait("allreduce_wait", [self._pending])
             if not self.native:
                 self.flat_grad.div_(self.world)
         self._pending = None
@@ -220,9 +257,9 @@ class DecoderTrainer:
         with torch.no_grad():
             latent = self.vae.encode(pixel_values)       # frozen encoder; overlaps the pending all-reduce
         self.finish_update()                             # parameters of step k-1 are now final
-        if self.world > 1:                               # DDP broadcast_buffers semantics
-            for b in self.buffers:
-                dist.broadcast(b, src=0, group=self.pg)
+        if self._buf_pending:                            # rank 0's buffers of step k-1 (sent behind that step)
+            self._timed_wait("buffer_broadcast_wait", self._buf_pending)
+            self._buf_pending = []
         self.decoder.train()
         # gradient_accumulation_steps > 1, reference semantics (train_decoder.py:193-203): DDP averages every
         # backward, and the ACCUMULATED gradient is clipped after every micro-step, not only before the update
@@ -250,10 +287,14 @@ class DecoderTrainer:
                 self.flat_grad.mul_(torch.clamp(self.max_grad_norm / (norm + 1e-6), max=1.0))
         elif boundary:
             self._launch_allreduce()
+        self._launch_buffer_broadcast()
         return loss.detach()
 
     def flush(self):
         self.finish_update()
+        for w in self._buf_pending:
+            w.wait()
+        self._buf_pending = []
 
 
 def _ddp_env():
