@@ -360,7 +360,12 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 (storage of raw activations; fp16 bounded MMA operands and weights, fp32 accumulation in TMEM)",
+        "dtype": ("16-bit tensor-core mode: bf16 storage of raw activations (VT_B200_RAW_BF16=1), fp16 bounded MMA "
+                  "operands and weights, fp32 accumulation in TMEM"
+                  if os.environ.get("VT_B200_RAW_BF16", "0")[:1] == "1" else
+                  "16-bit tensor-core mode ('bf16 mode' of the north star): fp16 storage and MMA operands -- the "
+                  "reference's own autocast dtype (infer_full.py:100), same tensor peak as bf16 -- fp32 accumulation "
+                  "in TMEM; VT_B200_RAW_BF16=1 stores raw activations as bf16 instead (same speed, 5x the error)"),
         "data": "synthetic",
         "config": make_config(B, R, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -5,6 +5,8 @@
 Tolerances (relative L2 of the image), the same bars as the encoder's: fp32 verification mode <= 1e-4;
 16-bit tensor-core mode <= 2e-2 (the decoder is ~2.5x deeper than the encoder -- 28 convs + attention between
 the latent and the image -- and its output is not squashed by a sigmoid)."""
+import sys
+
 import pytest
 import torch
 
@@ -66,8 +68,8 @@ def test_decoder_bf16_mode(trio, B, h, w):
 
 
 def test_raw_decode_and_micro_batching(trio):
-    """vae.decode(z).sample without the wrapper's un-shift / un-scale; micro-batching changes nothing in
-    fp32 mode beyond the order of the statistics atomics."""
+    """vae.decode(z).sample without the wrapper's un-shift / un-scale; micro-batching changes nothing at all
+    (statistics are reduced per image in a fixed order)."""
     _, dec, wrap = trio
     z = latents(5, 8, 16)
     with torch.no_grad():
@@ -78,7 +80,7 @@ def test_raw_decode_and_micro_batching(trio):
     b = wrap.vae.decode(z.cuda()).sample
     wrap.vae.micro_batch = 0
     wrap.vae.precision = "bf16"
-    assert rel(a.cpu(), ref) <= FP32_TOL and rel(b, a) <= 1e-6
+    assert rel(a.cpu(), ref) <= FP32_TOL and torch.equal(b, a)
 
 
 def test_wrapper_forward_reconstruction(trio):
@@ -121,17 +123,23 @@ def test_decoder_fallback_kernels(trio, monkeypatch):
     assert rel(got, ref) <= BF16_TOL, rel(got, ref)
 
 
-def test_decoder_full_size_bf16_vs_fp32_mode(trio):
-    """1024^2 (latent 128x128): the 16-bit tensor-core path against the fp32 verification mode of the same
-    schedule -- itself pinned to the oracle at the sizes the CPU oracle finishes in seconds -- and batch
-    composition invariance of the fp32 mode."""
-    _, _, wrap = trio
-    z = latents(2, 128, 128).cuda()
+def test_decoder_full_size_against_the_oracle(trio):
+    """1024^2 (latent 128x128): BOTH modes against the CPU oracle itself (10.5 TFLOP, a few seconds on the box's
+    host cores), plus batch-composition invariance (bit-exact: statistics are reduced per image in a fixed order)."""
+    _, dec, wrap = trio
+    z = latents(2, 128, 128)
+    with torch.no_grad():
+        ref = oracle_wrapper_decode(dec, z[1:])
+    zc = z.cuda()
     wrap.vae.precision = "fp32"
-    ref = wrap.decode(z)
-    one = wrap.decode(z[1:])
+    got32 = wrap.decode(zc)
+    one32 = wrap.decode(zc[1:])
     wrap.vae.precision = "bf16"
-    got = wrap.decode(z)
+    got = wrap.decode(zc)
+    one = wrap.decode(zc[1:])
     assert got.shape == (2, 3, 1024, 1024) and torch.isfinite(got).all()
-    assert rel(one, ref[1:]) <= 1e-5      # statistics atomics and tile order depend on the batch; 44 layers deep
-    assert rel(got, ref) <= BF16_TOL, rel(got, ref)
+    assert torch.equal(one32, got32[1:]) and torch.equal(one, got[1:])
+    e32, e16 = rel(got32[1:].cpu(), ref), rel(got[1:].cpu(), ref)
+    print(f"decoder 1024^2 vs oracle: fp32 mode {e32:.3e}, 16-bit mode {e16:.3e}", file=sys.stderr)
+    assert e32 <= FP32_TOL, e32
+    assert e16 <= BF16_TOL, e16

@@ -176,7 +176,8 @@ def test_fused_infer_call_equals_encode_then_tag(golden):
     ctx = wrap.vae._sync_native(x.device)
     out = ctx.infer_host(host, threshold=0.5)
     want = encode_and_tag(wrap, dec, x, threshold=0.5)
-    assert (out["conf"] - want["conf"].cpu()).abs().max().item() <= 2e-2      # two bf16 runs
+    assert torch.equal(out["conf"], want["conf"].cpu())      # two 16-bit runs: bit-identical
+    assert torch.equal(out["idx"], want["idx"].cpu())
 
 
 def test_config1_512_batch1_fp32(golden):

@@ -5,6 +5,8 @@ bf16 mode: operands are rounded to bf16, accumulation is fp32 in TMEM -> the ref
 from bf16-rounded operands in fp32, leaving only accumulation-order error (<= 2e-3 relative to the
 output scale is a loose bound; observed ~1e-6).
 """
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -24,6 +26,15 @@ def r16(t):
 
 def rh(t):
     return t.to(torch.float16).to(torch.float32)
+
+
+# storage format of RAW activations (residual stream, shortcut operand, GroupNorm input) in the 16-bit modes:
+# fp16 by default, bf16 with VT_B200_RAW_BF16=1 (vt_ctx::raw_f16)
+RAW_F16 = os.environ.get("VT_B200_RAW_BF16", "0")[:1] != "1"
+
+
+def raw(t):
+    return rh(t) if RAW_F16 else r16(t)
 
 
 def opd_round(prec):
@@ -102,10 +113,10 @@ def test_conv(ctx, case, prec):
     out, stats = (r if want_stats else (r, None))
     out = out.cpu()
     if prec != N.PREC_FP32:
-        # main operand + weights in the mode's format; residual / shortcut operands are raw bf16 tensors
+        # main operand + weights in the mode's format; residual / shortcut operands are raw 16-bit tensors
         rr = opd_round(prec)
-        ref = conv_ref(rr(x), rr(w), b, r16(res) if use_res else None, r16(scx) if cs else None,
-                       r16(scw) if cs else None, stride)
+        ref = conv_ref(rr(x), rr(w), b, raw(res) if use_res else None, raw(scx) if cs else None,
+                       raw(scw) if cs else None, stride)
         tol = 3e-5
     else:
         ref = conv_ref(x, w, b, res, scx, scw, stride)
@@ -128,7 +139,8 @@ def test_group_norm(ctx, shape, silu, prec):
     gamma = torch.randn(shape[1], generator=g)
     beta = torch.randn(shape[1], generator=g)
     out = ctx.op_group_norm(x, gamma, beta, silu=silu, precision=prec).cpu()
-    xin = x if prec == N.PREC_FP32 else r16(x)   # raw activations are stored bf16 in both 16-bit modes
+    # raw input storage: the context's raw format in fp16 mode, bf16 in bf16 mode
+    xin = x if prec == N.PREC_FP32 else (raw(x) if prec == N.PREC_F16 else r16(x))
     ref = F.group_norm(xin, 32, gamma, beta, eps=1e-6)
     if silu:
         ref = F.silu(ref)
@@ -160,8 +172,8 @@ def test_conv3_fused_with_shortcut_slab(ctx):
         scx = torch.randn(n, cs, h, w_, generator=g)
         scw = torch.randn(cout, cs, 1, 1, generator=g) / cs ** 0.5
         out = ctx.op_conv3_fused(x, gamma, beta, w, b, None, sc_x=scx, sc_w=scw).cpu()
-        t = F.silu(F.group_norm(r16(x), 32, gamma, beta, eps=1e-6))
-        ref = F.conv2d(rh(t), rh(w), b, padding=1) + F.conv2d(r16(scx), r16(scw))
+        t = F.silu(F.group_norm(raw(x), 32, gamma, beta, eps=1e-6))
+        ref = F.conv2d(rh(t), rh(w), b, padding=1) + F.conv2d(raw(scx), raw(scw))
         assert rel(out, ref) < 1e-3, (cin, rel(out, ref))
 
 
@@ -180,8 +192,8 @@ FUSED_CASES = [
 @pytest.mark.parametrize("case", FUSED_CASES)
 def test_conv3_fused_groupnorm_silu(ctx, case):
     """conv3x3(silu(GroupNorm32(x))) with the normalisation fused into the operand path (halo tile, nine
-    shifted descriptor views).  Reference: x rounded to bf16 (raw storage), GroupNorm+SiLU in fp32, result
-    rounded to fp16 (operand), fp16 weights, fp32 accumulation, bf16 residual."""
+    shifted descriptor views).  Reference: x rounded to the raw storage format, GroupNorm+SiLU in fp32, result
+    rounded to fp16 (operand), fp16 weights, fp32 accumulation, residual in the raw storage format."""
     n, cin, h, w_, cout, use_res = case
     g = torch.Generator().manual_seed(sum(case[:5]))
     x = torch.randn(n, cin, h, w_, generator=g) * 1.7 + 0.4
@@ -192,10 +204,10 @@ def test_conv3_fused_groupnorm_silu(ctx, case):
     res = torch.randn(n, cout, h, w_, generator=g) if use_res else None
     out, stats = ctx.op_conv3_fused(x, gamma, beta, w, b, res, want_stats=True)
     out = out.cpu()
-    t = F.silu(F.group_norm(r16(x), 32, gamma, beta, eps=1e-6))
+    t = F.silu(F.group_norm(raw(x), 32, gamma, beta, eps=1e-6))
     ref = F.conv2d(rh(t), rh(w), b, padding=1)
     if use_res:
-        ref = ref + r16(res)
+        ref = ref + raw(res)
     # the kernel evaluates SiLU as h + h*tanh.approx(h) on half2 (h = t/2 in fp16): operand values differ from
     # the fp32 reference rounded to fp16 by up to ~2 fp16 ulps (2^-10 relative)
     assert rel(out, ref) < 1e-3, (rel(out, ref), (out - ref).abs().max().item())

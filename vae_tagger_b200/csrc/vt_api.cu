@@ -69,6 +69,12 @@ struct DevBuf {
 struct vt_ctx {
     int device = 0;
     Profiler* prof = nullptr;
+    // 16-bit mode: storage format of RAW activations (residual stream, conv outputs) and of the weight columns
+    // that multiply them.  fp16 (default): the format the reference's own fp16 autocast stores them in
+    // (infer_full.py:100) -- 11-bit mantissa, latent error ~5e-3; bf16 (VT_B200_RAW_BF16=1 when the context is
+    // created): 8-bit mantissa, unbounded range, latent error 0.8-1.2e-2.  Fixed per context: the packed weights
+    // depend on it.
+    bool raw_f16 = true;
 
     // ---- encoder
     vt_encoder_config ecfg{};
@@ -178,6 +184,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restri
 // Sub-pixel weights of "nearest 2x upsample + conv3x3": for output parity (py,px) the 3x3 taps collapse onto
 // 2x2 source pixels.  Rows: py = 0 -> source rows {y-1: ky 0; y: ky 1+2}, py = 1 -> {y: ky 0+1; y+1: ky 2};
 // columns alike.  dst[par][co][(ty*2+tx)*C + ci], summed in fp32 then rounded to bf16 (raw operand).
+template <int OFMT>   // raw 16-bit format of the operand these weights multiply
 __global__ void pack_subpixel_kernel(const float* __restrict__ src /*[Co][C][3][3]*/, bf16* __restrict__ dst, int Co,
                                      int C) {
     const long long total = 4LL * Co * 4 * C;
@@ -194,7 +201,8 @@ __global__ void pack_subpixel_kernel(const float* __restrict__ src /*[Co][C][3][
         float a = 0.f;
         for (int ky = ky0; ky <= ky1; ++ky)
             for (int kx = kx0; kx <= kx1; ++kx) a += src[((1LL * co * C + ci) * 3 + ky) * 3 + kx];
-        dst[i] = __float2bfloat16(a);
+        if constexpr (OFMT == FMT_F16) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f));
+        else dst[i] = __float2bfloat16(a);
     }
 }
 __global__ void add_vec_kernel(float* __restrict__ a, const float* __restrict__ b, int n) {
@@ -236,10 +244,11 @@ struct Packer {
         return 0;
     }
     // conv weight `prefix`.weight [Cout][Cin][ks][ks] (+ optional shortcut [Cout][Cs][1][1]); Kpad pads K.
-    // f16: the main operand of this conv is a normalised (bounded) tensor -> fp16 weight columns; the
-    // shortcut columns always multiply a raw bf16 activation and stay bf16.
+    // f16: the main operand of this conv is a normalised (bounded) tensor -> fp16 weight columns; otherwise it is a
+    // raw activation and the columns take the context's raw format, like the shortcut columns always do.
     int conv(const std::string& prefix, int Cin, int Cout, int ks, const std::string& sc_prefix, int Cs, int Kpad,
              ConvW* w, bool f16 = true) {
+        f16 = f16 || c->raw_f16;
         const Param *pw, *pb;
         VT_TRY(get(prefix + ".weight", {Cout, Cin, ks, ks}, &pw));
         VT_TRY(get(prefix + ".bias", {Cout}, &pb));
@@ -258,7 +267,8 @@ struct Packer {
             const Param *sw, *sb;
             VT_TRY(get(sc_prefix + ".weight", {Cout, Cs, 1, 1}, &sw));
             VT_TRY(get(sc_prefix + ".bias", {Cout}, &sb));
-            pack_weight_kernel<FMT_BF16><<<grid, 256>>>(sw->dev, w->w16, Cout, Cs, 1, Ktot, ks * ks * Cin);
+            if (c->raw_f16) pack_weight_kernel<FMT_F16><<<grid, 256>>>(sw->dev, w->w16, Cout, Cs, 1, Ktot, ks * ks * Cin);
+            else pack_weight_kernel<FMT_BF16><<<grid, 256>>>(sw->dev, w->w16, Cout, Cs, 1, Ktot, ks * ks * Cin);
             pack_weight_kernel<FMT_F32><<<grid, 256>>>(sw->dev, w->w32, Cout, Cs, 1, Ktot, ks * ks * Cin);
             add_vec_kernel<<<(Cout + 255) / 256, 256>>>(w->bias, sb->dev, Cout);
         }
@@ -272,6 +282,7 @@ struct Packer {
         VT_TRY(get(prefix + ".weight", {Cout, Cin, ks, ks}, &pw));
         VT_TRY(get(prefix + ".bias", {Cout}, &pb));
         const int Ktot = ks * ks * CinP;
+        f16 = f16 || c->raw_f16;
         w->Cin = CinP; w->Cout = CoutP; w->ksize = ks; w->Cs = 0; w->Ktot = Ktot; w->f16 = f16;
         VT_TRY(alloc(&w->w16, static_cast<size_t>(CoutP) * Ktot));
         VT_TRY(alloc(&w->w32, static_cast<size_t>(CoutP) * Ktot));
@@ -283,12 +294,13 @@ struct Packer {
         VT_CUDA(cudaGetLastError());
         return 0;
     }
-    // the four sub-pixel weight sets of an upsample conv (bf16: the operand is a raw activation)
+    // the four sub-pixel weight sets of an upsample conv (the operand is a raw activation: the context's raw format)
     int conv_subpixel(const std::string& prefix, int C, bf16** w4) {
         const Param* pw;
         VT_TRY(get(prefix + ".weight", {C, C, 3, 3}, &pw));
         VT_TRY(alloc(w4, static_cast<size_t>(4) * C * 4 * C));
-        pack_subpixel_kernel<<<1024, 256>>>(pw->dev, *w4, C, C);
+        if (c->raw_f16) pack_subpixel_kernel<FMT_F16><<<1024, 256>>>(pw->dev, *w4, C, C);
+        else pack_subpixel_kernel<FMT_BF16><<<1024, 256>>>(pw->dev, *w4, C, C);
         VT_CUDA(cudaGetLastError());
         return 0;
     }
@@ -387,14 +399,15 @@ struct EncRun {
         return p;
     }
     const void* W(const ConvW& w) const { return fp32 ? static_cast<const void*>(w.w32) : static_cast<const void*>(w.w16); }
-    int raw_fmt() const { return fp32 ? FMT_F32 : FMT_BF16; }   // residual stream / conv1 outputs
+    int raw_fmt() const { return fp32 ? FMT_F32 : (c->raw_f16 ? FMT_F16 : FMT_BF16); }   // residual stream / conv1 outputs
+    int raw16() const { return !fp32 && c->raw_f16; }
     int opd_fmt() const { return fp32 ? FMT_F32 : FMT_F16; }    // bounded MMA operands
 
     int conv(const void* in, int H, int Wd, const ConvW& w, int stride, const void* sc_in, const Act* residual,
              Act out, double* st) {
         ConvOp op;
         op.in = in; op.N = n; op.Hin = H; op.Win = Wd; op.Cin = w.Cin; op.ksize = w.ksize; op.stride = stride;
-        op.in_f16 = w.f16;
+        op.in_f16 = w.f16; op.raw_f16 = raw16();
         op.w = W(w); op.Cout = w.Cout; op.sc_in = sc_in; op.Cs = w.Cs; op.bias = w.bias;
         if (residual) { op.residual = residual->p; op.residual_fp32 = residual->fmt == FMT_F32; }
         op.out = out.p; op.out_fmt = out.fmt;
@@ -418,12 +431,12 @@ struct EncRun {
             if (st) VT_TRY(launch_gn_stats(op.out, 1, st, op.batch, rows_for_stats, op.N, groups, s, c->prof));
             return 0;
         }
-        op.stats_ws = ws;
+        op.stats_ws = ws; op.raw_f16 = raw16();
         return launch_gemm(op, s, c->prof);
     }
     // normalised operand: fp16 in 16-bit mode (it feeds TMA), fp32 in verification mode
     int gn(Act x, void* y, const double* st, const NormW& nw, long long HW, int C, int silu) {
-        return launch_gn_apply(x.p, x.fmt == FMT_F32, y, opd_fmt(), st, nw.gamma, nw.beta, n, HW, C, groups, 1e-6f, silu,
+        return launch_gn_apply(x.p, x.fmt, y, opd_fmt(), st, nw.gamma, nw.beta, n, HW, C, groups, 1e-6f, silu,
                                s, c->prof);
     }
     int conv_fused(Act x, const double* st_x, const NormW& nw, int H, int Wd, const ConvW& w, const Act* residual,
@@ -433,7 +446,7 @@ struct EncRun {
         op.in = x.p; op.N = n; op.H = H; op.W = Wd; op.Cin = w.Cin; op.Cout = w.Cout; op.gn_stats = st_x;
         op.gamma = nw.gamma; op.beta = nw.beta; op.w = w.w16; op.bias = w.bias;
         if (residual) { op.residual = residual->p; op.residual_fp32 = residual->fmt == FMT_F32; }
-        op.out = out.p; op.out_fmt = out.fmt; op.stats = st; op.stats_ws = ws;
+        op.out = out.p; op.out_fmt = out.fmt; op.stats = st; op.stats_ws = ws; op.raw_f16 = raw16();
         return launch_conv3_fused(op, s, c->prof);
     }
     // ResnetBlock2D: out = x (+shortcut) + conv2(silu(norm2(conv1(silu(norm1(x))))))
@@ -450,7 +463,7 @@ struct EncRun {
             if (r.cin == r.cout) return conv_fused(h, st_h, r.norm2, H, Wd, r.conv2, &x, out, st_out);
             if (r.cout >= 256) {
                 // channel-changing block: the 1x1 shortcut of the block input is an extra K slab of conv2
-                VT_CHECK(x.fmt == FMT_BF16, "shortcut operand must be bf16");
+                VT_CHECK(x.fmt == raw_fmt(), "shortcut operand must be in the raw 16-bit format");
                 return conv_fused(h, st_h, r.norm2, H, Wd, r.conv2, nullptr, out, st_out, x.p);
             }
             VT_TRY(gn(h, T, st_h, r.norm2, HW, r.cout, 1));
@@ -460,7 +473,7 @@ struct EncRun {
         VT_TRY(conv(T, H, Wd, r.conv1, 1, nullptr, nullptr, h, st_h));
         VT_TRY(gn(h, T, st_h, r.norm2, HW, r.cout, 1));
         if (r.cin != r.cout) {
-            VT_CHECK(fp32 || x.fmt == FMT_BF16, "shortcut operand must be bf16");
+            VT_CHECK(fp32 || x.fmt == raw_fmt(), "shortcut operand must be in the raw 16-bit format");
             return conv(T, H, Wd, r.conv2, 1, x.p, nullptr, out, st_out);
         }
         return conv(T, H, Wd, r.conv2, 1, nullptr, &x, out, st_out);
@@ -678,13 +691,14 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
                                                          : static_cast<size_t>(H) * Wd * 3 * sizeof(float);
     double* st_x = R.new_stats();
     Act X{Xp, R.raw_fmt()};
-    const bool convin_direct = !fp32 && cfg.block_out_channels[0] == 128 && X.fmt == FMT_BF16 && c->conv_in.f16 &&
+    const bool convin_direct = !fp32 && cfg.block_out_channels[0] == 128 && c->conv_in.f16 &&
                                !(getenv("VT_B200_NO_CONVIN") && getenv("VT_B200_NO_CONVIN")[0] == '1');
     if (convin_direct) {
         // operand rows built in shared memory from the image itself (vt_convin.cuh)
         ConvInOp op;
         op.img = img + img_stride * img0; op.in_fmt = a->in_fmt; op.N = n; op.H = H; op.W = Wd;
         op.w = c->conv_in.w16; op.bias = c->conv_in.bias; op.out = X.p; op.stats = st_x; op.stats_ws = R.ws;
+        op.out_f16 = R.raw16();
         VT_TRY(launch_conv_in(op, s, c->prof));
     } else {
         VT_TRY(launch_im2col3x3(img + img_stride * img0, a->in_fmt, Hb, R.opd_fmt(), n, H, Wd, s, c->prof));
@@ -709,7 +723,7 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
         if (has_down) {
             double* st_o = R.new_stats();
             Act out{spare, R.raw_fmt()};
-            VT_CHECK(fp32 || X.fmt == FMT_BF16, "downsample operand must be bf16");
+            VT_CHECK(fp32 || X.fmt == R.raw_fmt(), "downsample operand must be in the raw 16-bit format");
             VT_TRY(R.conv(X.p, h, w_, c->downsample[b], 2, nullptr, nullptr, out, st_o));
             advance(out);
             st_x = st_o;
@@ -825,7 +839,8 @@ int run_decoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_decode_args* a, 
                 for (int par = 0; par < 4; ++par) {
                     ConvOp op;
                     op.in = X.p; op.N = n; op.Hin = h; op.Win = w_; op.Cin = C; op.ksize = 3; op.stride = 1;
-                    op.in_f16 = 0; op.w = c->upsample_sp[b] + static_cast<size_t>(par) * C * 4 * C; op.Cout = C;
+                    op.in_f16 = R.raw16(); op.raw_f16 = R.raw16();
+                    op.w = c->upsample_sp[b] + static_cast<size_t>(par) * C * 4 * C; op.Cout = C;
                     op.bias = uw.bias; op.out = out.p; op.out_fmt = out.fmt; op.stats = st_o;
                     op.stats_ws = R.ws; op.stats_ws.parts = 4; op.stats_ws.part_index = par;   // one tensor, four launches
                     op.up2 = 1; op.up_py = par >> 1; op.up_px = par & 1;
@@ -895,6 +910,10 @@ int vt_ctx_create(int device, vt_ctx** out) {
     }
     vt_ctx* c = new vt_ctx();
     c->device = device;
+    {
+        const char* e = getenv("VT_B200_RAW_BF16");
+        c->raw_f16 = !(e && e[0] == '1');
+    }
     c->prof = profiler_create();
     for (auto& L : c->lanes) {
         VT_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
@@ -1534,7 +1553,7 @@ int vt_op_conv2d(vt_ctx* c, const float* x, const float* w, const float* bias, c
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int fp32 = precision == VT_PREC_FP32;
     const int fmt = op_fmt(precision);
-    const int raw = fp32 ? FMT_F32 : FMT_BF16;
+    const int raw = fp32 ? FMT_F32 : (c->raw_f16 ? FMT_F16 : FMT_BF16);   // residual / shortcut operand storage
     const size_t es = fp32 ? 4 : 2;
     const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
     if (!sc_x) Cs = 0;
@@ -1561,10 +1580,14 @@ int vt_op_conv2d(vt_ctx* c, const float* x, const float* w, const float* bias, c
     } else {
         if (fmt == FMT_F16) pack_weight_kernel<FMT_F16><<<256, 256, 0, s>>>(w, dw, Cout, Cin, ksize, Ktot, 0);
         else pack_weight_kernel<FMT_BF16><<<256, 256, 0, s>>>(w, dw, Cout, Cin, ksize, Ktot, 0);
-        if (sc_w) pack_weight_kernel<FMT_BF16><<<256, 256, 0, s>>>(sc_w, dw, Cout, Cs, 1, Ktot, ksize * ksize * Cin);
+        if (sc_w) {
+            if (c->raw_f16) pack_weight_kernel<FMT_F16><<<256, 256, 0, s>>>(sc_w, dw, Cout, Cs, 1, Ktot, ksize * ksize * Cin);
+            else pack_weight_kernel<FMT_BF16><<<256, 256, 0, s>>>(sc_w, dw, Cout, Cs, 1, Ktot, ksize * ksize * Cin);
+        }
     }
     VT_CUDA(cudaGetLastError());
     ConvOp op;
+    op.raw_f16 = !fp32 && c->raw_f16;
     op.in = dx; op.in_f16 = fmt == FMT_F16; op.N = N; op.Hin = H; op.Win = W; op.Cin = Cin; op.ksize = ksize;
     op.stride = stride; op.w = dw;
     op.Cout = Cout; op.sc_in = sc_x ? dsc : nullptr; op.Cs = Cs; op.bias = bias; op.residual = residual ? dres : nullptr;
@@ -1601,15 +1624,20 @@ int vt_op_conv3_fused(vt_ctx* c, const float* x, const float* gamma, const float
     void* dx = p; void* dout = p + b_x; void* dres = p + b_x + b_o; void* dw = p + b_x + b_o + b_r;
     double* st_in = reinterpret_cast<double*>(p + b_x + b_o + b_r + b_w);
     void* dsc = p + b_x + b_o + b_r + b_w + b_s;
-    VT_TRY(launch_nchw_to_nhwc(x, dx, FMT_BF16, N, Cin, HW, s));
-    if (residual) VT_TRY(launch_nchw_to_nhwc(residual, dres, FMT_BF16, N, Cout, HW, s));
-    if (sc_x) VT_TRY(launch_nchw_to_nhwc(sc_x, dsc, FMT_BF16, N, Cs, HW, s));
+    const int raw = c->raw_f16 ? FMT_F16 : FMT_BF16;    // storage of the raw input, the residual and the shortcut operand
+    VT_TRY(launch_nchw_to_nhwc(x, dx, raw, N, Cin, HW, s));
+    if (residual) VT_TRY(launch_nchw_to_nhwc(residual, dres, raw, N, Cout, HW, s));
+    if (sc_x) VT_TRY(launch_nchw_to_nhwc(sc_x, dsc, raw, N, Cs, HW, s));
     pack_weight_kernel<FMT_F16><<<256, 256, 0, s>>>(w, dw, Cout, Cin, 3, Ktot, 0);
-    if (sc_w) pack_weight_kernel<FMT_BF16><<<256, 256, 0, s>>>(sc_w, dw, Cout, Cs, 1, Ktot, 9 * Cin);
+    if (sc_w) {
+        if (c->raw_f16) pack_weight_kernel<FMT_F16><<<256, 256, 0, s>>>(sc_w, dw, Cout, Cs, 1, Ktot, 9 * Cin);
+        else pack_weight_kernel<FMT_BF16><<<256, 256, 0, s>>>(sc_w, dw, Cout, Cs, 1, Ktot, 9 * Cin);
+    }
     VT_CUDA(cudaGetLastError());
-    VT_TRY(launch_gn_stats(dx, 0, st_in, N, HW, Cin, 32, s, c->prof));
+    VT_TRY(launch_gn_stats(dx, raw, st_in, N, HW, Cin, 32, s, c->prof));
     Conv3FusedOp op;
     op.in = dx; op.N = N; op.H = H; op.W = W; op.Cin = Cin; op.Cout = Cout; op.gn_stats = st_in; op.gamma = gamma;
+    op.raw_f16 = c->raw_f16;
     op.beta = beta; op.eps = eps; op.silu = silu; op.w = dw; op.bias = bias; op.residual = residual ? dres : nullptr;
     op.out = dout; op.out_fmt = FMT_F32; op.stats = stats; op.sc_in = sc_x ? dsc : nullptr; op.Cs = Cs;
     op.stats_ws.part = reinterpret_cast<float*>(p + b_x + b_o + b_r + b_w + b_s + b_c); op.stats_ws.bytes = b_st;
@@ -1666,7 +1694,7 @@ int vt_op_group_norm(vt_ctx* c, const float* x, const float* gamma, const float*
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int fp32 = precision == VT_PREC_FP32;
     const int ofmt = op_fmt(precision);          // output: bf16 / fp32 / fp16
-    const int ifmt = fp32 ? FMT_F32 : FMT_BF16;  // raw input storage
+    const int ifmt = fp32 ? FMT_F32 : ((ofmt == FMT_F16 && c->raw_f16) ? FMT_F16 : FMT_BF16);  // raw input storage
     const size_t es = fp32 ? 4 : 2;
     const long long HW = 1LL * H * W;
     const size_t b_x = align_up(static_cast<size_t>(N) * HW * C * es, 256);
@@ -1676,8 +1704,8 @@ int vt_op_group_norm(vt_ctx* c, const float* x, const float* gamma, const float*
     void* dx = p; void* dy = p + b_x; double* st = reinterpret_cast<double*>(p + 2 * b_x);
     VT_TRY(launch_nchw_to_nhwc(x, dx, ifmt, N, C, HW, s));
     VT_CUDA(cudaMemsetAsync(st, 0, b_s, s));
-    VT_TRY(launch_gn_stats(dx, fp32, st, N, HW, C, groups, s, c->prof));
-    VT_TRY(launch_gn_apply(dx, fp32, dy, ofmt, st, gamma, beta, N, HW, C, groups, eps, silu, s, c->prof));
+    VT_TRY(launch_gn_stats(dx, ifmt, st, N, HW, C, groups, s, c->prof));
+    VT_TRY(launch_gn_apply(dx, ifmt, dy, ofmt, st, gamma, beta, N, HW, C, groups, eps, silu, s, c->prof));
     return launch_nhwc_to_nchw(dy, ofmt, out, N, C, HW, s);
 }
 

@@ -72,7 +72,7 @@ struct Conv3Cfg {
 // staging tile so that 4 lanes hold 32 consecutive channels of one pixel (64 contiguous bytes) and a
 // warp store covers 8 pixels.  The lane's 8 channels are fixed for the whole kernel: bias lives in
 // registers and the GroupNorm partial sums are folded once per tile.
-template <typename Cfg, int OUT, int RES, bool STATS>
+template <typename Cfg, int OUT, int RES, bool STATS, int RAW = FMT_BF16>
 __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* staging_all, uint8_t* ctrl,
                                                 uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
                                                 uint32_t total_tiles, int warp, int lane) {
@@ -207,8 +207,8 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
                 v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
                 if (RES == 1) {
                     const uint4 u = rlo[i];
-                    v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
-                    v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
+                    v[0] += raw16_lo<RAW>(u.x); v[1] += raw16_hi<RAW>(u.x); v[2] += raw16_lo<RAW>(u.y); v[3] += raw16_hi<RAW>(u.y);
+                    v[4] += raw16_lo<RAW>(u.z); v[5] += raw16_hi<RAW>(u.z); v[6] += raw16_lo<RAW>(u.w); v[7] += raw16_hi<RAW>(u.w);
                 } else if (RES == 2) {
                     const uint4 a = rlo[i], b = rhi[i];
                     v[0] += __uint_as_float(a.x); v[1] += __uint_as_float(a.y); v[2] += __uint_as_float(a.z); v[3] += __uint_as_float(a.w);
@@ -269,7 +269,7 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
     }
 }
 
-template <int BLOCK_N, int MT, bool TR, bool PAIR>
+template <int BLOCK_N, int MT, bool TR, bool PAIR, int RAW = FMT_BF16>   // RAW: storage format of raw activations
 __global__ void __launch_bounds__(Conv3Cfg<BLOCK_N, MT, TR, PAIR>::THREADS, 1)
 conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmS, const __grid_constant__ IgemmParams P) {
@@ -461,7 +461,8 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (++hb == NHALO) { hb = 0; hphase ^= 1; }
                 }
                 if constexpr (!TR) {
-                    constexpr uint32_t idesc_sc = umma_idesc_16(PAIR ? 256 : IGEMM_BLOCK_M, BLOCK_N, false);   // bf16 x bf16
+                    // the shortcut operand is the raw block input: raw format x weight columns of the same format
+                    constexpr uint32_t idesc_sc = umma_idesc_16(PAIR ? 256 : IGEMM_BLOCK_M, BLOCK_N, RAW == FMT_F16);
                     const uint64_t dx_base = umma_desc_k_sw128(smem_u32(s_halo));                 // plain tile: 1024 B groups
                     for (int c = 0; c < sc_chunks; ++c) {
                         mbar_wait(&halo_ready[hb], hphase);
@@ -487,16 +488,17 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     } else if (warp < 2 + Cfg::EPI_WARPS) {
         // ------------------------------------------------------------ epilogue warps (2..5)
-        const int res = P.residual == nullptr ? 0 : (P.res_fp32 ? 2 : 1);
-        const int mode = P.out_fmt | (res << 2) | (P.group_size != 0 ? 16 : 0);
+        // output: fp32, or the raw 16-bit format of this instantiation; residual: none or raw 16-bit
+        const int res = P.residual == nullptr ? 0 : 1;
+        const int mode = (P.out_fmt == FMT_F32 ? 1 : 0) | (res << 2) | (P.group_size != 0 ? 16 : 0);
 #define VT_EPI_CASE(O, R, S)                                                                                  \
     case ((O) | ((R) << 2) | ((S) << 4)):                                                                     \
         if constexpr (TR)                                                                                     \
-            conv3t_epilogue<Cfg, (O), (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base,    \
-                                                      total_tiles, warp, lane);                               \
+            conv3t_epilogue<Cfg, (O) ? FMT_F32 : RAW, (R), (S) != 0, RAW>(P, staging_all, ctrl, tfull_bar,      \
+                                                      tempty_bar, tmem_base, total_tiles, warp, lane);        \
         else                                                                                                  \
-            igemm_epilogue<Cfg, (O), (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base,     \
-                                                     total_tiles, warp, lane);                                \
+            igemm_epilogue<Cfg, (O) ? FMT_F32 : RAW, (R), (S) != 0, RAW>(P, staging_all, ctrl, tfull_bar,       \
+                                                     tempty_bar, tmem_base, total_tiles, warp, lane);         \
         break;
         switch (mode) {
             VT_EPI_CASE(0, 0, 0) VT_EPI_CASE(1, 0, 0) VT_EPI_CASE(0, 1, 0) VT_EPI_CASE(1, 1, 0)
@@ -578,8 +580,8 @@ conv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     for (int r = 0; r < 4; ++r) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float lo = fmaf(bf16_lo(u[r][j]), sc[2 * j], sh[2 * j]);
-                            const float hi = fmaf(bf16_hi(u[r][j]), sc[2 * j + 1], sh[2 * j + 1]);
+                            const float lo = fmaf(raw16_lo<RAW>(u[r][j]), sc[2 * j], sh[2 * j]);
+                            const float hi = fmaf(raw16_hi<RAW>(u[r][j]), sc[2 * j + 1], sh[2 * j + 1]);
                             uint32_t h2 = pack_f16x2(lo, hi);
                             if (silu) {
                                 uint32_t th;

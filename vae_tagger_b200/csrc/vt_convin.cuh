@@ -117,7 +117,13 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         }
     } else if (warp < 2 + Epi::EPI_WARPS) {
         // ------------------------------------------------------------ epilogue warps
-        if (P.group_size != 0)
+        // output = raw activation: bf16, or fp16 (P.out_fmt)
+        if (P.out_fmt == FMT_F16) {
+            if (P.group_size != 0)
+                igemm_epilogue<Epi, FMT_F16, 0, true>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
+            else
+                igemm_epilogue<Epi, FMT_F16, 0, false>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
+        } else if (P.group_size != 0)
             igemm_epilogue<Epi, FMT_BF16, 0, true>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
         else
             igemm_epilogue<Epi, FMT_BF16, 0, false>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);

@@ -104,9 +104,11 @@ int launch_im2col3x3(const void* in, int fmt, void* out, int out_fmt, int N, int
 // x: [N][HW][C] ; stats: [N][G][2] double (sum, sum of squares), WRITTEN.  One block per (image, group),
 // fixed pixel -> thread assignment and a fixed-order tree: the result depends on the image only, not on the
 // batch it is part of (no atomics).
-template <typename T>
-__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ stats,
+template <int IFMT>   // element format of x: FMT_BF16 / FMT_F32 / FMT_F16
+__global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ xv, double* __restrict__ stats,
                                                        long long HW, int C, int G) {
+    typedef typename std::conditional<IFMT == FMT_F32, float, bf16>::type T;   // 16-bit formats share the pointer type
+    const T* x = static_cast<const T*>(xv);
     __shared__ double sh[2][256];
     const int g = blockIdx.x, n = blockIdx.y;
     const int cpg = C / G;              // a multiple of 4
@@ -121,9 +123,9 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
         for (long long p = pl; p < HW; p += lanes) {
             const T* px = x + (1LL * n * HW + p) * C + g * cpg + qd * 4;
             float a, b, c, d;
-            if constexpr (sizeof(T) == 2) {
+            if constexpr (IFMT != FMT_F32) {
                 const uint2 u = *reinterpret_cast<const uint2*>(px);
-                a = bf16_lo(u.x); b = bf16_hi(u.x); c = bf16_lo(u.y); d = bf16_hi(u.y);
+                a = raw16_lo<IFMT>(u.x); b = raw16_hi<IFMT>(u.x); c = raw16_lo<IFMT>(u.y); d = raw16_hi<IFMT>(u.y);
             } else {
                 const float4 f = *reinterpret_cast<const float4*>(px);
                 a = f.x; b = f.y; c = f.z; d = f.w;
@@ -147,13 +149,14 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
     if (threadIdx.x < 2) stats[(1LL * n * G + g) * 2 + threadIdx.x] = sh[threadIdx.x][0];
 }
 
-int launch_gn_stats(const void* x, int is_fp32, double* stats, int N, long long HW, int C, int G, cudaStream_t s,
+int launch_gn_stats(const void* x, int x_fmt, double* stats, int N, long long HW, int C, int G, cudaStream_t s,
                     Profiler* prof) {
     VT_CHECK(G == 32 && C % (4 * G) == 0 && C / (4 * G) <= 256, "GroupNorm statistics need 32 groups of a multiple of 4 channels");
     dim3 grid(G, N);
-    profiler_begin(prof, KC_GN_APPLY, s, 0, 1.0 * N * HW * C * (is_fp32 ? 4 : 2));
-    if (is_fp32) gn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), stats, HW, C, G);
-    else gn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), stats, HW, C, G);
+    profiler_begin(prof, KC_GN_APPLY, s, 0, 1.0 * N * HW * C * (x_fmt == FMT_F32 ? 4 : 2));
+    if (x_fmt == FMT_F32) gn_stats_kernel<FMT_F32><<<grid, 256, 0, s>>>(x, stats, HW, C, G);
+    else if (x_fmt == FMT_F16) gn_stats_kernel<FMT_F16><<<grid, 256, 0, s>>>(x, stats, HW, C, G);
+    else gn_stats_kernel<FMT_BF16><<<grid, 256, 0, s>>>(x, stats, HW, C, G);
     profiler_end(prof, KC_GN_APPLY, s);
     VT_CUDA(cudaGetLastError());
     return 0;
@@ -201,12 +204,14 @@ int launch_gn_finalize(const float* part, double* stats, int N, int tiles, int G
 // (sum, sumsq) doubles.  One thread owns 8 consecutive channels of a fixed channel block and
 // walks pixels, so scale/shift live in registers; every access is a 16-byte (bf16) or 2x16-byte
 // (fp32) vector and a warp touches 512 contiguous bytes.
-template <typename TI, int OFMT, bool FAST>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const TI* __restrict__ x, void* __restrict__ yv,
+template <int IFMT, int OFMT, bool FAST>   // IFMT: element format of x (FMT_BF16 / FMT_F32 / FMT_F16)
+__global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ xv, void* __restrict__ yv,
                                                        const double* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, long long HW, int C, int G,
                                                        float eps, int silu) {
+    typedef typename std::conditional<IFMT == FMT_F32, float, bf16>::type TI;
+    const TI* x = static_cast<const TI*>(xv);
     const int n = blockIdx.y;
     const int cb = C / 8;              // 8-channel blocks per pixel
     const int tpb = min(cb, 256);      // threads spanning the channel dimension
@@ -234,10 +239,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const TI* __restrict__ x,
         for (long long p = p0 + psub; p < p1; p += ppb) {
             const long long off = (1LL * n * HW + p) * C + c8 * 8;
             float v[8];
-            if constexpr (sizeof(TI) == 2) {
+            if constexpr (IFMT != FMT_F32) {
                 const uint4 u = *reinterpret_cast<const uint4*>(x + off);
-                v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
-                v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+                v[0] = raw16_lo<IFMT>(u.x); v[1] = raw16_hi<IFMT>(u.x); v[2] = raw16_lo<IFMT>(u.y); v[3] = raw16_hi<IFMT>(u.y);
+                v[4] = raw16_lo<IFMT>(u.z); v[5] = raw16_hi<IFMT>(u.z); v[6] = raw16_lo<IFMT>(u.w); v[7] = raw16_hi<IFMT>(u.w);
             } else {
                 const float4 a = *reinterpret_cast<const float4*>(x + off);
                 const float4 b = *reinterpret_cast<const float4*>(x + off + 4);
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const TI* __restrict__ x,
     }
 }
 
-int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fmt, const double* stats, const float* gamma,
+int launch_gn_apply(const void* x, int x_fmt, void* y, int y_fmt, const double* stats, const float* gamma,
                     const float* beta, int N, long long HW, int C, int G, float eps, int silu, cudaStream_t s,
                     Profiler* prof) {
     VT_CHECK(C % 8 == 0 && C % G == 0, "GroupNorm apply needs C % 8 == 0 and C % groups == 0");
@@ -275,16 +280,18 @@ int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fmt, const double*
     const long long cap = std::max(1, sm_count() * 16 / N);
     const int chunks = static_cast<int>(std::max<long long>(1, std::min(want, cap)));
     dim3 grid(chunks, N);
-    profiler_begin(prof, KC_GN_APPLY, s, 0, 1.0 * N * HW * C * ((x_fp32 ? 4 : 2) + (y_fmt == FMT_F32 ? 4 : 2)));
-#define VT_GN(TI, OF, FAST) \
-    gn_apply_kernel<TI, OF, FAST><<<grid, 256, 0, s>>>(static_cast<const TI*>(x), y, stats, gamma, beta, HW, C, G, eps, silu)
-    if (x_fp32 && y_fmt == FMT_F32) VT_GN(float, FMT_F32, false);
-    else if (x_fp32 && y_fmt == FMT_F16) VT_GN(float, FMT_F16, true);
-    else if (x_fp32 && y_fmt == FMT_BF16) VT_GN(float, FMT_BF16, true);
-    else if (!x_fp32 && y_fmt == FMT_F16) VT_GN(bf16, FMT_F16, true);
-    else if (!x_fp32 && y_fmt == FMT_BF16) VT_GN(bf16, FMT_BF16, true);
+    profiler_begin(prof, KC_GN_APPLY, s, 0, 1.0 * N * HW * C * ((x_fmt == FMT_F32 ? 4 : 2) + (y_fmt == FMT_F32 ? 4 : 2)));
+#define VT_GN(IF, OF, FAST) \
+    gn_apply_kernel<IF, OF, FAST><<<grid, 256, 0, s>>>(x, y, stats, gamma, beta, HW, C, G, eps, silu)
+    const bool x_fp32 = x_fmt == FMT_F32;
+    if (x_fp32 && y_fmt == FMT_F32) VT_GN(FMT_F32, FMT_F32, false);
+    else if (x_fp32 && y_fmt == FMT_F16) VT_GN(FMT_F32, FMT_F16, true);
+    else if (x_fp32 && y_fmt == FMT_BF16) VT_GN(FMT_F32, FMT_BF16, true);
+    else if (x_fmt == FMT_BF16 && y_fmt == FMT_F16) VT_GN(FMT_BF16, FMT_F16, true);
+    else if (x_fmt == FMT_BF16 && y_fmt == FMT_BF16) VT_GN(FMT_BF16, FMT_BF16, true);
+    else if (x_fmt == FMT_F16 && y_fmt == FMT_F16) VT_GN(FMT_F16, FMT_F16, true);
     else {
-        set_error("GroupNorm apply bf16 -> fp32 is not instantiated");
+        set_error("GroupNorm apply: this input / output format pair is not instantiated");
         return -2;
     }
 #undef VT_GN
@@ -568,6 +575,7 @@ __global__ void __launch_bounds__(256) latent_to_nhwc_kernel(const float* __rest
         const long long n = np / HW, p = np - n * HW;
         const float v = c < LC ? (z[(n * LC + c) * HW + p] - shift) * inv_scale : 0.f;
         if constexpr (OFMT == FMT_BF16) static_cast<bf16*>(outv)[i] = __float2bfloat16(v);
+        else if constexpr (OFMT == FMT_F16) static_cast<__half*>(outv)[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
         else static_cast<float*>(outv)[i] = v;
     }
 }
@@ -577,6 +585,7 @@ int launch_latent_to_nhwc(const float* z, void* out, int out_fmt, int N, int LC,
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
     profiler_begin(prof, KC_LATENT, s, 0, 4.0 * N * LC * HW + (out_fmt == FMT_F32 ? 4.0 : 2.0) * total);
     if (out_fmt == FMT_F32) latent_to_nhwc_kernel<FMT_F32><<<grid, 256, 0, s>>>(z, out, LC, CP, HW, shift, inv_scale, total);
+    else if (out_fmt == FMT_F16) latent_to_nhwc_kernel<FMT_F16><<<grid, 256, 0, s>>>(z, out, LC, CP, HW, shift, inv_scale, total);
     else latent_to_nhwc_kernel<FMT_BF16><<<grid, 256, 0, s>>>(z, out, LC, CP, HW, shift, inv_scale, total);
     profiler_end(prof, KC_LATENT, s);
     VT_CUDA(cudaGetLastError());

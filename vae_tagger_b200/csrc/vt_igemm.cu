@@ -166,10 +166,13 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     P.a_batched = 1; P.b_batched = 0;
     P.out_fmt = op.out_fmt;
     P.group_size = op.stats ? op.Cout / 32 : 0;
-    VT_CHECK(op.out_fmt != 2 || (op.residual == nullptr && op.stats == nullptr), "fp16 output has no residual / statistics epilogue");
+    VT_CHECK(op.out_fmt != 2 || op.residual == nullptr || (op.raw_f16 && !op.residual_fp32),
+             "fp16 output takes no residual other than an fp16 one");
+    VT_CHECK(op.out_fmt != 0 || op.residual == nullptr || op.residual_fp32 || !op.raw_f16,
+             "bf16 output takes no fp16 residual");
     VT_CHECK(op.stats == nullptr || (op.Cout % 32 == 0 && (P.group_size == 4 || P.group_size == 8 || P.group_size == 16)),
              "fused GroupNorm statistics need 4, 8 or 16 channels per group");
-    P.alpha = op.alpha;
+    P.alpha = op.alpha; P.raw_f16 = op.raw_f16;
     P.bias = op.bias; P.residual = op.residual; P.res_fp32 = op.residual_fp32; P.out = op.out; P.ld_out = op.Cout;
     P.out_bstride = 1LL * Hout * Wout * op.Cout; P.stats = op.stats;
     if (op.up2) {  // strided view of the 2x-upsampled output: this launch writes one pixel parity
@@ -211,7 +214,7 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
         IgemmSlab& s = P.slabs[ns];
         s.map = 1; s.c_base = 0; s.dx = 0; s.p = 0; s.dy = 0;
         s.kb_base = taps * op.Cin; s.nchunks = op.Cs / 64;
-        s.f16 = 0;  // the shortcut operand is a raw activation: bf16, and so are its weight columns
+        s.f16 = op.raw_f16;  // the shortcut operand is a raw activation: bf16 (fp16 when raw_f16), and so are its weight columns
         ++ns;
     }
     P.num_slabs = ns;
@@ -247,7 +250,7 @@ int launch_conv_in(const ConvInOp& op, cudaStream_t stream, Profiler* prof) {
     P.tiles_x = (op.W + 255) / 256;
     P.tiles_y = op.H;
     P.n_total = 128; P.n_blocks = 1;
-    P.out_fmt = FMT_BF16;
+    P.out_fmt = op.out_f16 ? FMT_F16 : FMT_BF16;
     P.group_size = op.stats ? 4 : 0;
     P.alpha = 1.f;
     P.bias = op.bias; P.out = op.out; P.ld_out = 128;
@@ -274,16 +277,16 @@ int launch_conv_in(const ConvInOp& op, cudaStream_t stream, Profiler* prof) {
     return finish_stats(P, stream, prof);
 }
 
-template <int BLOCK_N, int MT, bool TR, bool PAIR>
+template <int BLOCK_N, int MT, bool TR, bool PAIR, int RAW>
 static int launch_conv3_variant(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sc, const IgemmParams& P,
                                 cudaStream_t stream) {
     using Cfg = Conv3Cfg<BLOCK_N, MT, TR, PAIR>;
     static SmemAttrOnce once;
-    VT_TRY(ensure_dyn_smem(once, conv3_fused_kernel<BLOCK_N, MT, TR, PAIR>, Cfg::SMEM_BYTES));
+    VT_TRY(ensure_dyn_smem(once, conv3_fused_kernel<BLOCK_N, MT, TR, PAIR, RAW>, Cfg::SMEM_BYTES));
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y * P.n_blocks;
     int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     if (!PAIR) {
-        conv3_fused_kernel<BLOCK_N, MT, TR, PAIR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, b, sc, P);
+        conv3_fused_kernel<BLOCK_N, MT, TR, PAIR, RAW><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, b, sc, P);
     } else {
         grid &= ~1;   // whole clusters of two CTAs (tiles is even: the launcher checked)
         cudaLaunchConfig_t cfg{};
@@ -296,7 +299,7 @@ static int launch_conv3_variant(const CUtensorMap& a, const CUtensorMap& b, cons
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        VT_CUDA(cudaLaunchKernelEx(&cfg, conv3_fused_kernel<BLOCK_N, MT, TR, PAIR>, a, b, sc, P));
+        VT_CUDA(cudaLaunchKernelEx(&cfg, conv3_fused_kernel<BLOCK_N, MT, TR, PAIR, RAW>, a, b, sc, P));
     }
     VT_CUDA(cudaGetLastError());
     return 0;
@@ -308,7 +311,8 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
     VT_CHECK(op.Cout == 128 || (op.Cout >= 256 && op.Cout % 32 == 0), "fused conv: Cout must be 128 or >= 256");
     VT_CHECK(op.Cin % 32 == 0 && (op.Cin / 32) % 4 == 0, "fused conv: GroupNorm(32) groups must hold a multiple of 4 channels");
     VT_CHECK(op.gn_stats && op.gamma && op.beta, "fused conv needs the input statistics and affine parameters");
-    VT_CHECK(op.out_fmt != 2 && !op.residual_fp32, "fused conv: output must be bf16 or fp32 and the residual bf16");
+    VT_CHECK(!op.residual_fp32 && (op.out_fmt == FMT_F32 || op.out_fmt == (op.raw_f16 ? FMT_F16 : FMT_BF16)),
+             "fused conv: output must be fp32 or the raw 16-bit format, the residual the raw 16-bit format");
     // 128-channel layers: transposed variant (channels on the accumulator rows, an 8x32 pixel patch on the
     // columns); wider layers: 8x16 pixel patch x 256 channels
     const bool tr = op.Cout == 128;
@@ -328,6 +332,7 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
     P.a_batched = 1; P.b_batched = 0;
     P.out_fmt = op.out_fmt;
     P.res_fp32 = op.residual_fp32;
+    P.raw_f16 = op.raw_f16;
     P.group_size = op.stats ? op.Cout / 32 : 0;
     VT_CHECK(op.stats == nullptr || P.group_size == 4 || P.group_size == 8 || P.group_size == 16,
              "fused GroupNorm statistics need 4, 8 or 16 channels per group");
@@ -361,9 +366,15 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
     VT_TRY(bind_stats(P, op.stats_ws));
     const KernelClass kc = tr ? KC_CONV3_T : KC_CONV3;
     profiler_begin(prof, kc, stream, flops, bytes);
-    int rc = tr ? launch_conv3_variant<128, 1, true, false>(a, b, sc, P, stream)
-                : pair ? launch_conv3_variant<256, 1, false, true>(a, b, sc, P, stream)
-                       : launch_conv3_variant<256, 1, false, false>(a, b, sc, P, stream);
+    int rc;
+    if (op.raw_f16)
+        rc = tr ? launch_conv3_variant<128, 1, true, false, FMT_F16>(a, b, sc, P, stream)
+                : pair ? launch_conv3_variant<256, 1, false, true, FMT_F16>(a, b, sc, P, stream)
+                       : launch_conv3_variant<256, 1, false, false, FMT_F16>(a, b, sc, P, stream);
+    else
+        rc = tr ? launch_conv3_variant<128, 1, true, false, FMT_BF16>(a, b, sc, P, stream)
+                : pair ? launch_conv3_variant<256, 1, false, true, FMT_BF16>(a, b, sc, P, stream)
+                       : launch_conv3_variant<256, 1, false, false, FMT_BF16>(a, b, sc, P, stream);
     profiler_end(prof, kc, stream);
     VT_TRY(rc);
     return finish_stats(P, stream, prof);
@@ -390,10 +401,13 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     P.a_batched = op.a_batched; P.b_batched = op.b_batched;
     P.out_fmt = op.out_fmt;
     P.group_size = op.stats ? op.N / 32 : 0;
-    VT_CHECK(op.out_fmt != 2 || (op.residual == nullptr && op.stats == nullptr), "fp16 output has no residual / statistics epilogue");
+    VT_CHECK(op.out_fmt != 2 || op.residual == nullptr || (op.raw_f16 && !op.residual_fp32),
+             "fp16 output takes no residual other than an fp16 one");
+    VT_CHECK(op.out_fmt != 0 || op.residual == nullptr || op.residual_fp32 || !op.raw_f16,
+             "bf16 output takes no fp16 residual");
     VT_CHECK(op.stats == nullptr || (P.group_size == 4 || P.group_size == 8 || P.group_size == 16),
              "fused GroupNorm statistics need 4, 8 or 16 channels per group");
-    P.alpha = op.alpha;
+    P.alpha = op.alpha; P.raw_f16 = op.raw_f16;
     P.bias = op.bias; P.residual = op.residual; P.res_fp32 = op.residual_fp32; P.out = op.out; P.ld_out = ldo;
     P.out_bstride = op.out_bstride ? op.out_bstride : 1LL * op.M * ldo; P.stats = op.stats;
     P.num_slabs = 1;

@@ -51,7 +51,8 @@ struct IgemmParams {
     int a_batched;         // A coordinate 4 = image index (0: shared operand)
     int b_batched;         // B coordinate 2 = image index (0: shared operand)
     int out_fmt;           // output element type: FMT_BF16 / FMT_F32 / FMT_F16
-    int res_fp32;          // residual element type: 0 bf16, 1 fp32
+    int res_fp32;          // residual element type: 0 = 16-bit raw format (bf16, or fp16 when raw_f16), 1 = fp32
+    int raw_f16;           // raw activations (residual stream, conv outputs) are stored fp16 instead of bf16
     int group_size;        // channels per GroupNorm group for the fused statistics; 0 = off
     int ax1, ay1, ax2, ay2;  // pixel offset of accumulator row r+8 / r+16 relative to row r (patch shape dependent)
     float alpha;
@@ -124,7 +125,7 @@ struct IgemmCfg {
 // GroupNorm accumulators are per-warp slots (no shared-memory atomics): the first two versions of this
 // epilogue spent ~1000 issue slots per 32x32 chunk on branches, 64-bit address arithmetic and
 // compare-and-swap loops and were the limiter of every layer with few K chunks per tile.
-template <typename Cfg, int OUT, int RES, bool STATS>
+template <typename Cfg, int OUT, int RES, bool STATS, int RAW = FMT_BF16>   // RAW: format of a 16-bit residual (RES == 1)
 __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* staging_all, uint8_t* ctrl,
                                                uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
                                                uint32_t total_tiles, int warp, int lane) {
@@ -317,8 +318,8 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
                         v1.z = fmaf(v1.z, P.alpha, b1.z); v1.w = fmaf(v1.w, P.alpha, b1.w);
                         if (RES == 1) {
                             const uint4 u = rcur.lo[i];
-                            v0.x += bf16_lo(u.x); v0.y += bf16_hi(u.x); v0.z += bf16_lo(u.y); v0.w += bf16_hi(u.y);
-                            v1.x += bf16_lo(u.z); v1.y += bf16_hi(u.z); v1.z += bf16_lo(u.w); v1.w += bf16_hi(u.w);
+                            v0.x += raw16_lo<RAW>(u.x); v0.y += raw16_hi<RAW>(u.x); v0.z += raw16_lo<RAW>(u.y); v0.w += raw16_hi<RAW>(u.y);
+                            v1.x += raw16_lo<RAW>(u.z); v1.y += raw16_hi<RAW>(u.z); v1.z += raw16_lo<RAW>(u.w); v1.w += raw16_hi<RAW>(u.w);
                         } else if (RES == 2) {
                             const uint4 a = rcur.lo[i], b = rcur.hi[i];
                             v0.x += __uint_as_float(a.x); v0.y += __uint_as_float(a.y);
@@ -521,16 +522,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     } else {
         // ------------------------------------------------------------ epilogue warps
         const int res = P.residual == nullptr ? 0 : (P.res_fp32 ? 2 : 1);
-        const int mode = P.out_fmt | (res << 2) | (P.group_size != 0 ? 16 : 0);
-#define VT_EPI_CASE(O, R, S)                                                                                  \
-    case ((O) | ((R) << 2) | ((S) << 4)):                                                                     \
-        igemm_epilogue<Cfg, (O), (R), (S) != 0>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base,         \
+        const int mode = P.out_fmt | (res << 2) | (P.group_size != 0 ? 16 : 0) | (P.raw_f16 && res == 1 ? 32 : 0);
+#define VT_EPI_CASE(O, R, S, RAW)                                                                             \
+    case ((O) | ((R) << 2) | ((S) << 4) | ((RAW) == FMT_F16 && (R) == 1 ? 32 : 0)):                           \
+        igemm_epilogue<Cfg, (O), (R), (S) != 0, (RAW)>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base,  \
                                                          total_tiles, warp, lane);                            \
         break;
         switch (mode) {
-            VT_EPI_CASE(0, 0, 0) VT_EPI_CASE(1, 0, 0) VT_EPI_CASE(2, 0, 0) VT_EPI_CASE(0, 1, 0) VT_EPI_CASE(1, 1, 0)
-            VT_EPI_CASE(0, 2, 0) VT_EPI_CASE(1, 2, 0) VT_EPI_CASE(0, 0, 1) VT_EPI_CASE(1, 0, 1)
-            VT_EPI_CASE(0, 1, 1) VT_EPI_CASE(1, 1, 1) VT_EPI_CASE(0, 2, 1) VT_EPI_CASE(1, 2, 1)
+            // no residual (RAW irrelevant): bf16 / fp32 / fp16 outputs, with and without statistics
+            VT_EPI_CASE(0, 0, 0, FMT_BF16) VT_EPI_CASE(1, 0, 0, FMT_BF16) VT_EPI_CASE(2, 0, 0, FMT_BF16)
+            VT_EPI_CASE(0, 0, 1, FMT_BF16) VT_EPI_CASE(1, 0, 1, FMT_BF16) VT_EPI_CASE(2, 0, 1, FMT_BF16)
+            // fp32 residual
+            VT_EPI_CASE(0, 2, 0, FMT_BF16) VT_EPI_CASE(1, 2, 0, FMT_BF16) VT_EPI_CASE(0, 2, 1, FMT_BF16) VT_EPI_CASE(1, 2, 1, FMT_BF16)
+            // bf16 raw residual
+            VT_EPI_CASE(0, 1, 0, FMT_BF16) VT_EPI_CASE(1, 1, 0, FMT_BF16) VT_EPI_CASE(0, 1, 1, FMT_BF16) VT_EPI_CASE(1, 1, 1, FMT_BF16)
+            // fp16 raw residual
+            VT_EPI_CASE(2, 1, 0, FMT_F16) VT_EPI_CASE(1, 1, 0, FMT_F16) VT_EPI_CASE(2, 1, 1, FMT_F16) VT_EPI_CASE(1, 1, 1, FMT_F16)
             default: __trap();  // the host launcher rejects every other combination
         }
 #undef VT_EPI_CASE

@@ -106,6 +106,7 @@ struct ConvOp {
     // input activation, NHWC bf16
     const void* in = nullptr;  // 16-bit (tcgen05 path) or fp32 (launch_conv_fp32)
     int in_f16 = 0;            // tcgen05 path: main operand + its weight columns are fp16 (else bf16)
+    int raw_f16 = 0;           // tcgen05 path: 16-bit residual / shortcut operand (+ its weight columns) are fp16 (else bf16)
     int N = 0, Hin = 0, Win = 0, Cin = 0;
     int ksize = 3;   // 1 or 3
     int stride = 1;  // 1 (pad 1 for 3x3) or 2 (pad right/bottom by 1, diffusers Downsample2D)
@@ -138,7 +139,8 @@ struct ConvInOp {
     int N = 0, H = 0, W = 0;
     const void* w = nullptr;    // [128][64] fp16, k = (kh*3+kw)*3+c, k >= 27 zero
     const float* bias = nullptr;
-    void* out = nullptr;        // [N][H][W][128] bf16
+    void* out = nullptr;        // [N][H][W][128] bf16 (out_f16: fp16)
+    int out_f16 = 0;
     double* stats = nullptr;    // [N][32][2] or null
     StatsScratch stats_ws;
 };
@@ -160,6 +162,7 @@ struct GemmOp {
     void* out = nullptr;
     int out_fmt = 0;            // 0 bf16, 1 fp32, 2 fp16
     int ab_f16 = 0;             // tcgen05 path: A and B are fp16 (else bf16)
+    int raw_f16 = 0;            // tcgen05 path: a 16-bit residual is fp16 (else bf16)
     long long ld_out = 0;       // default N
     long long out_bstride = 0;  // default M * ld_out (also used for residual)
     double* stats = nullptr;    // [batch][32][2] over (m, group of N/32 columns)
@@ -187,7 +190,8 @@ int launch_flash_attention(const FlashOp& op, cudaStream_t stream, Profiler* pro
 
 // 3x3 stride-1 conv with GroupNorm(32)+SiLU of the INPUT fused into the operand path (vt_conv3.cuh)
 struct Conv3FusedOp {
-    const void* in = nullptr;   // raw activation, bf16 NHWC [N][H][W][Cin]
+    const void* in = nullptr;   // raw activation, 16-bit NHWC [N][H][W][Cin]: bf16, or fp16 when raw_f16
+    int raw_f16 = 0;            // raw activations (in, sc_in, residual, 16-bit out) and the shortcut weight columns are fp16
     int N = 0, H = 0, W = 0, Cin = 0, Cout = 0;
     const double* gn_stats = nullptr;  // [N][32][2] (sum, sumsq) of `in`
     const float* gamma = nullptr;      // [Cin]
@@ -210,11 +214,11 @@ int launch_conv3_fused(const Conv3FusedOp& op, cudaStream_t stream, Profiler* pr
 // ---- HBM-bound kernels (vt_elementwise.cu)
 int launch_im2col3x3(const void* in, int fmt, void* out, int out_fmt, int N, int H, int W, cudaStream_t,
                      Profiler*);
-int launch_gn_stats(const void* x, int is_fp32, double* stats, int N, long long HW, int C, int G, cudaStream_t,
+int launch_gn_stats(const void* x, int x_fmt /*FMT_BF16 | FMT_F32 | FMT_F16*/, double* stats, int N, long long HW, int C, int G, cudaStream_t,
                     Profiler*);
 // second stage of the epilogue statistics: part[N][tiles][G][2] fp32 -> stats[N][G][2] fp64, fixed order
 int launch_gn_finalize(const float* part, double* stats, int N, int tiles, int G, cudaStream_t, Profiler*);
-int launch_gn_apply(const void* x, int x_fp32, void* y, int y_fmt, const double* stats, const float* gamma,
+int launch_gn_apply(const void* x, int x_fmt /*FMT_BF16 | FMT_F32 | FMT_F16*/, void* y, int y_fmt, const double* stats, const float* gamma,
                     const float* beta, int N, long long HW, int C, int G, float eps, int silu, cudaStream_t,
                     Profiler*);
 int launch_softmax_rows(const float* s, void* p, int p_fmt, long long rows, int cols, long long ld_s,

@@ -293,5 +293,16 @@ __device__ __forceinline__ float f16_hi(uint32_t v) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+// low / high half of a packed pair of 16-bit values stored in format FMT (FMT_BF16 or FMT_F16)
+template <int FMT>
+__device__ __forceinline__ float raw16_lo(uint32_t v) {
+    if constexpr (FMT == FMT_F16) return f16_lo(v);
+    else return bf16_lo(v);
+}
+template <int FMT>
+__device__ __forceinline__ float raw16_hi(uint32_t v) {
+    if constexpr (FMT == FMT_F16) return f16_hi(v);
+    else return bf16_hi(v);
+}
 
 }  // namespace vt

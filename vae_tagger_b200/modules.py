@@ -274,12 +274,14 @@ def get_vae_config(resolution, use_quant_conv, use_post_quant_conv):
 
 
 def get_image_paths(path):
-    """Image files under a directory (recursive, de-duplicated) or a single image file."""
+    """Image files under a directory (recursive, de-duplicated) or a single image file.  The reference returns
+    ``list(set(...))`` (modules.py:270) -- an arbitrary, per-process order; here the list is sorted, so that every
+    rank of a sharded run sees the same order and the output is reproducible."""
     if os.path.isdir(path):
         # the reference globs "*<ext>" and "*<EXT>" (modules.py:263-268): all-lower or all-upper extensions only
         both = IMAGE_EXTENSIONS + tuple(e.upper() for e in IMAGE_EXTENSIONS)
         found = {p.resolve() for p in Path(path).rglob("*") if p.is_file() and p.name.endswith(both)}
-        return list(found)
+        return sorted(found)
     if os.path.isfile(path):
         if path.lower().endswith(IMAGE_EXTENSIONS):
             return [Path(path)]
