@@ -219,3 +219,106 @@ def test_plain_head_without_pooling_oracle(golden, train_golden):
     torch.testing.assert_close(r["logits"], c["logits"], atol=1e-5, rtol=1e-5)
     for k, want in c["grads"].items():
         check_digest(r["grads"][k], want, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Cross-check of the encoder / decoder restatements (diffusers is not installable, so no true pin exists): a
+# SECOND restatement, written independently as pure ``torch.nn.functional`` calls that walk the state dict by
+# its diffusers key names, with the attention going through
+# ``F.scaled_dot_product_attention`` -- the call diffusers' AttnProcessor2_0 makes -- instead of the oracle's
+# explicit matmul / softmax.  Both must agree to fp32 round-off.
+def _gn(sd, p, x):
+    import torch.nn.functional as F
+    return F.group_norm(x, 32, sd[p + ".weight"], sd[p + ".bias"], eps=1e-6)
+
+
+def _conv(sd, p, x, stride=1, padding=1):
+    import torch.nn.functional as F
+    return F.conv2d(x, sd[p + ".weight"], sd[p + ".bias"], stride=stride, padding=padding)
+
+
+def _resnet(sd, p, x):
+    import torch.nn.functional as F
+    h = _conv(sd, p + ".conv1", F.silu(_gn(sd, p + ".norm1", x)))
+    h = _conv(sd, p + ".conv2", F.silu(_gn(sd, p + ".norm2", h)))
+    if p + ".conv_shortcut.weight" in sd:
+        x = _conv(sd, p + ".conv_shortcut", x, padding=0)
+    return x + h
+
+
+def _attention(sd, p, x):
+    import torch.nn.functional as F
+    b, c, h, w = x.shape
+    t = _gn(sd, p + ".group_norm", x).flatten(2).transpose(1, 2)
+    q, k, v = (F.linear(t, sd[f"{p}.{n}.weight"], sd[f"{p}.{n}.bias"]).view(b, -1, 1, c).transpose(1, 2)
+               for n in ("to_q", "to_k", "to_v"))
+    o = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False)
+    o = o.transpose(1, 2).reshape(b, -1, c)
+    o = F.linear(o, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
+    return o.transpose(-1, -2).reshape(b, c, h, w) + x
+
+
+def _mid(sd, p, x):
+    x = _resnet(sd, p + ".resnets.0", x)
+    x = _attention(sd, p + ".attentions.0", x)
+    return _resnet(sd, p + ".resnets.1", x)
+
+
+def functional_encoder_moments(sd, x):
+    import torch.nn.functional as F
+    h = _conv(sd, "encoder.conv_in", x)
+    for i in range(4):
+        for j in range(2):
+            h = _resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", h)
+        if i < 3:
+            h = _conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", F.pad(h, (0, 1, 0, 1)), stride=2, padding=0)
+    h = _mid(sd, "encoder.mid_block", h)
+    return _conv(sd, "encoder.conv_out", F.silu(_gn(sd, "encoder.conv_norm_out", h)))
+
+
+def functional_decoder_image(sd, z):
+    import torch.nn.functional as F
+    h = _conv(sd, "conv_in", z)
+    h = _mid(sd, "mid_block", h)
+    for i in range(4):
+        for j in range(3):
+            h = _resnet(sd, f"up_blocks.{i}.resnets.{j}", h)
+        if i < 3:
+            h = _conv(sd, f"up_blocks.{i}.upsamplers.0.conv", F.interpolate(h, scale_factor=2.0, mode="nearest"))
+    return _conv(sd, "conv_out", F.silu(_gn(sd, "conv_norm_out", h)))
+
+
+@pytest.mark.parametrize("h,w", [(64, 64), (96, 160)])
+def test_encoder_oracle_agrees_with_independent_functional_restatement(h, w):
+    vae = OE.make_oracle_vae(seed=0)
+    sd = vae.state_dict()
+    x = torch.cat([OE.synthetic_images(1, h, w), OE.structured_images(1, h, w)])
+    with torch.no_grad():
+        want = functional_encoder_moments(sd, x)
+        got = vae.encoder(x)
+        lat = OE.oracle_wrapper_encode(vae, x)
+    assert got.shape == want.shape == (2, 32, h // 8, w // 8)
+    assert ((got - want).norm() / want.norm()).item() < 1e-6
+    # wrapper: mode() * 0.3611 + 0.1159 (diffusers_vae_loader.py:80-84) on the first 16 moment channels
+    assert torch.allclose(lat, want[:, :16] * 0.3611 + 0.1159, atol=1e-6)
+
+
+def test_oracle_attention_is_sdpa():
+    """``OracleAttention`` (explicit matmul / softmax) against the SDPA form on its own weights."""
+    torch.manual_seed(3)
+    att = OE.OracleAttention(64, 32)
+    sd = {"a." + k: v for k, v in att.state_dict().items()}
+    x = torch.randn(2, 64, 12, 20)
+    with torch.no_grad():
+        assert torch.allclose(att(x), _attention(sd, "a", x), atol=2e-6, rtol=1e-5)
+
+
+def test_decoder_oracle_agrees_with_independent_functional_restatement():
+    from oracle import decoder as OD
+    dec = OD.make_oracle_decoder(seed=0)
+    z = torch.randn(1, 16, 8, 12, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        want = functional_decoder_image(dec.state_dict(), z)
+        got = dec(z)
+    assert got.shape == want.shape == (1, 3, 64, 96)
+    assert ((got - want).norm() / want.norm()).item() < 5e-6      # fp32 round-off through 44 layers (measured 1.8e-6)
