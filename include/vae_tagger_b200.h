@@ -309,6 +309,32 @@ int vt_op_group_norm(vt_ctx* ctx, const float* x /*[N,C,H,W]*/, const float* gam
 int vt_op_softmax_rows(vt_ctx* ctx, const float* s, int64_t rows, int cols, int precision, float* out,
                        void* stream);
 
+/* ---- backward building blocks of the encoder (the reference fine-tunes the VAE through autograd,
+ * train_vae.py:124-186 / train_full.py:201-256; diffusers' ResnetBlock2D / Conv2d / GroupNorm).  NCHW fp32 device
+ * tensors in and out like the other vt_op_* entry points; precision VT_PREC_FP32 = FFMA verification mode, anything
+ * else = the 16-bit tensor-core mode (activations in the context's raw format, bf16 gradients, fp32 accumulation
+ * and fp32 parameter gradients).  Null gradient pointers are skipped. */
+/* y = conv2d(x, w) + b, 3x3 pad 1 or 1x1, stride 1: grad_x = d/dx, grad_w [Cout,Cin,k,k], grad_b [Cout] */
+int vt_op_conv2d_backward(vt_ctx* ctx, const float* x /*[N,Cin,H,W]*/, const float* w /*[Cout,Cin,k,k]*/,
+                          const float* grad_out /*[N,Cout,H,W]*/, int N, int Cin, int H, int W, int Cout, int ksize,
+                          int precision, float* grad_x, float* grad_w, float* grad_b, void* stream);
+/* y = act(GroupNorm32(x) * gamma + beta), act = SiLU when silu != 0 */
+int vt_op_group_norm_backward(vt_ctx* ctx, const float* x /*[N,C,H,W]*/, const float* gamma, const float* beta,
+                              const float* grad_y, int N, int C, int H, int W, float eps, int silu, int precision,
+                              float* grad_x, float* grad_gamma, float* grad_beta, void* stream);
+/* diffusers ResnetBlock2D (temb none): out = shortcut(x) + conv2(silu(norm2(conv1(silu(norm1(x)))))); shortcut =
+ * identity (Cin == Cout, sc_* null) or a 1x1 conv.  Runs the block's first half forward (to rebuild conv1's output)
+ * and the whole backward on the device in NHWC. */
+typedef struct vt_resnet_block_params {
+    const float *norm1_w, *norm1_b, *conv1_w, *conv1_b, *norm2_w, *norm2_b, *conv2_w, *conv2_b, *sc_w, *sc_b;
+} vt_resnet_block_params;
+typedef struct vt_resnet_block_grads {
+    float *x, *norm1_w, *norm1_b, *conv1_w, *conv1_b, *norm2_w, *norm2_b, *conv2_w, *conv2_b, *sc_w, *sc_b;
+} vt_resnet_block_grads;
+int vt_op_resnet_block_backward(vt_ctx* ctx, const float* x /*[N,Cin,H,W]*/, const vt_resnet_block_params* params,
+                                const float* grad_out /*[N,Cout,H,W]*/, int N, int Cin, int Cout, int H, int W,
+                                int precision, const vt_resnet_block_grads* grads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,96 @@
+"""Encoder backward building blocks (the reference fine-tunes the VAE through autograd in
+train_vae.py:124-186 / train_full.py:201-256): data / weight / bias gradients of the convs (tcgen05 implicit GEMMs:
+the data gradient is the forward kernel on flipped weights, the weight gradient a split-K GEMM over the pixels),
+GroupNorm+SiLU backward, and a whole ResnetBlock2D, against ``torch.autograd`` on the oracle's own modules (CPU fp32).
+
+Tolerances (relative L2 of each gradient tensor): fp32 verification mode <= 1e-4; 16-bit mode <= 2e-2 -- gradients
+and the re-laid-out operands are bf16 (8-bit mantissa: the range of a gradient is unbounded and the reference has no
+loss scaling), accumulation fp32."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.encoder import OracleResnetBlock2D
+from vae_tagger_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+B16_TOL = 2e-2
+
+
+def rel(a, b):
+    return ((a.cpu() - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def tol(prec):
+    return FP32_TOL if prec == N.PREC_FP32 else B16_TOL
+
+
+@pytest.mark.parametrize("prec", [N.PREC_FP32, N.PREC_F16])
+@pytest.mark.parametrize("n,cin,cout,h,w,k", [
+    (1, 128, 128, 16, 16, 3), (2, 128, 256, 24, 40, 3), (1, 256, 256, 33, 17, 3), (2, 512, 512, 8, 8, 3),
+    (1, 256, 128, 20, 12, 3), (2, 128, 256, 16, 24, 1), (1, 512, 512, 64, 64, 3),
+])
+def test_conv2d_backward(ctx, prec, n, cin, cout, h, w, k):
+    g = torch.Generator().manual_seed(n + cin + cout + h + w + k)
+    x = torch.randn(n, cin, h, w, generator=g, requires_grad=True)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).requires_grad_()
+    b = torch.randn(cout, generator=g, requires_grad=True)
+    go = torch.randn(n, cout, h, w, generator=g)
+    F.conv2d(x, wt, b, padding=k // 2).backward(go)
+    gx, gw, gb = ctx.op_conv2d_backward(x, wt, go, precision=prec)
+    assert rel(gx, x.grad) < tol(prec), ("grad_x", rel(gx, x.grad))
+    assert rel(gw, wt.grad) < tol(prec), ("grad_w", rel(gw, wt.grad))
+    assert rel(gb, b.grad) < tol(prec), ("grad_b", rel(gb, b.grad))
+
+
+def test_conv2d_backward_is_bit_reproducible(ctx):
+    """Split-K partial tiles are added in index order (no atomics): two runs give identical bits."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 128, 48, 40, generator=g)
+    wt = torch.randn(256, 128, 3, 3, generator=g) / 34.0
+    go = torch.randn(2, 256, 48, 40, generator=g)
+    a = ctx.op_conv2d_backward(x, wt, go)
+    b = ctx.op_conv2d_backward(x, wt, go)
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+
+@pytest.mark.parametrize("prec", [N.PREC_FP32, N.PREC_F16])
+@pytest.mark.parametrize("silu", [False, True])
+@pytest.mark.parametrize("shape", [(2, 128, 16, 24), (1, 256, 9, 7), (3, 512, 12, 4), (1, 128, 96, 96)])
+def test_group_norm_backward(ctx, prec, silu, shape):
+    g = torch.Generator().manual_seed(shape[1] + shape[2])
+    x = (torch.randn(*shape, generator=g) * 1.5 + 0.3).requires_grad_()
+    gamma = (torch.randn(shape[1], generator=g) * 0.5 + 1.0).requires_grad_()
+    beta = (torch.randn(shape[1], generator=g) * 0.3).requires_grad_()
+    gy = torch.randn(*shape, generator=g)
+    y = F.group_norm(x, 32, gamma, beta, eps=1e-6)
+    (F.silu(y) if silu else y).backward(gy)
+    gx, gg, gb = ctx.op_group_norm_backward(x, gamma, beta, gy, silu=silu, precision=prec)
+    assert rel(gx, x.grad) < tol(prec), ("grad_x", rel(gx, x.grad))
+    assert rel(gg, gamma.grad) < tol(prec), ("grad_gamma", rel(gg, gamma.grad))
+    assert rel(gb, beta.grad) < tol(prec), ("grad_beta", rel(gb, beta.grad))
+
+
+@pytest.mark.parametrize("prec", [N.PREC_FP32, N.PREC_F16])
+@pytest.mark.parametrize("n,cin,cout,h,w", [(2, 128, 128, 32, 32), (1, 128, 256, 24, 40), (1, 256, 512, 16, 16),
+                                            (2, 512, 512, 16, 8), (1, 128, 128, 64, 64)])
+def test_resnet_block_backward(ctx, prec, n, cin, cout, h, w):
+    """One ResnetBlock2D of the encoder: d out / d x and every parameter gradient vs autograd on the oracle block."""
+    torch.manual_seed(cin + cout + h)
+    blk = OracleResnetBlock2D(cin, cout, 32)
+    with torch.no_grad():   # non-trivial affine parameters
+        for m in (blk.norm1, blk.norm2):
+            m.weight.add_(torch.randn_like(m.weight) * 0.3)
+            m.bias.add_(torch.randn_like(m.bias) * 0.3)
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(n, cin, h, w, generator=g) * 1.2 + 0.2).requires_grad_()
+    go = torch.randn(n, cout, h, w, generator=g)
+    blk(x).backward(go)
+    gx, grads = ctx.op_resnet_block_backward(x, blk.state_dict(), go, precision=prec)
+    errs = {"x": rel(gx, x.grad)}
+    for k, p in blk.named_parameters():
+        errs[k] = rel(grads[k], p.grad)
+    assert set(grads) == {k for k, _ in blk.named_parameters()}
+    assert max(errs.values()) < tol(prec), errs

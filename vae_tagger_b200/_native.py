@@ -107,6 +107,16 @@ class ResizeArgs(C.Structure):
     ]
 
 
+class ResnetBlockPtrs(C.Structure):
+    """vt_resnet_block_params (const float*) and, with one more leading field, vt_resnet_block_grads."""
+    _fields_ = [(n, C.c_void_p) for n in ("norm1_w", "norm1_b", "conv1_w", "conv1_b", "norm2_w", "norm2_b", "conv2_w",
+                                          "conv2_b", "sc_w", "sc_b")]
+
+
+class ResnetBlockGrads(C.Structure):
+    _fields_ = [("x", C.c_void_p)] + ResnetBlockPtrs._fields_
+
+
 # every symbol include/vae_tagger_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -148,6 +158,10 @@ SYMBOLS = {
     "vt_op_gemm_nt": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, _P, _P]),
     "vt_op_group_norm": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_int, _P, _P]),
     "vt_op_softmax_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "vt_op_conv2d_backward": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 7 + [_P, _P, _P, _P]),
+    "vt_op_group_norm_backward": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "vt_op_resnet_block_backward": (C.c_int, [_P, _P, C.POINTER(ResnetBlockPtrs), _P] + [C.c_int] * 6 +
+                                    [C.POINTER(ResnetBlockGrads), _P]),
 }
 
 _lib = None
@@ -672,6 +686,57 @@ class Context:
         with torch.cuda.device(self.device):
             _check(self.lib.vt_op_softmax_rows(self.h, _ptr(s), rows, cols, precision, _ptr(out), _stream(self.device)))
         return out
+
+
+    # ---- backward building blocks of the encoder
+    def op_conv2d_backward(self, x, w, grad_out, precision=PREC_F16, want=(True, True, True)):
+        """(grad_x, grad_w, grad_b) of ``conv2d(x, w, b, padding=k//2)`` (stride 1, k = 1 or 3)."""
+        x = _f32c(x, self.device); w = _f32c(w, self.device); go = _f32c(grad_out, self.device)
+        N, Cin, H, W = x.shape
+        Cout, k = w.shape[0], w.shape[-1]
+        gx = torch.empty_like(x) if want[0] else None
+        gw = torch.empty_like(w) if want[1] else None
+        gb = torch.empty(Cout, device=self.device) if want[2] else None
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_op_conv2d_backward(self.h, _ptr(x), _ptr(w), _ptr(go), N, Cin, H, W, Cout, k, precision,
+                                                  _ptr(gx), _ptr(gw), _ptr(gb), _stream(self.device)))
+        return gx, gw, gb
+
+    def op_group_norm_backward(self, x, gamma, beta, grad_y, eps=1e-6, silu=True, precision=PREC_F16):
+        """(grad_x, grad_gamma, grad_beta) of ``act(group_norm(x, 32, gamma, beta))``."""
+        x = _f32c(x, self.device); gamma = _f32c(gamma, self.device); beta = _f32c(beta, self.device)
+        gy = _f32c(grad_y, self.device)
+        N, Cc, H, W = x.shape
+        gx, gg, gb = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(beta)
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_op_group_norm_backward(self.h, _ptr(x), _ptr(gamma), _ptr(beta), _ptr(gy), N, Cc, H, W,
+                                                      float(eps), int(silu), precision, _ptr(gx), _ptr(gg), _ptr(gb),
+                                                      _stream(self.device)))
+        return gx, gg, gb
+
+    def op_resnet_block_backward(self, x, params, grad_out, precision=PREC_F16):
+        """Backward of diffusers' ResnetBlock2D.  ``params``: dict with the block's state-dict keys (``norm1.weight``,
+        ``conv1.weight``, ..., optional ``conv_shortcut.weight/bias``).  Returns ``(grad_x, {key: grad})``."""
+        x = _f32c(x, self.device); go = _f32c(grad_out, self.device)
+        keys = {"norm1_w": "norm1.weight", "norm1_b": "norm1.bias", "conv1_w": "conv1.weight", "conv1_b": "conv1.bias",
+                "norm2_w": "norm2.weight", "norm2_b": "norm2.bias", "conv2_w": "conv2.weight", "conv2_b": "conv2.bias",
+                "sc_w": "conv_shortcut.weight", "sc_b": "conv_shortcut.bias"}
+        N, Cin, H, W = x.shape
+        Cout = params["conv1.weight"].shape[0]
+        pp, gp, held, grads = ResnetBlockPtrs(), ResnetBlockGrads(), [], {}
+        for f, k in keys.items():
+            if k in params:
+                t = _f32c(params[k], self.device)
+                g = torch.empty_like(t)
+                held.append(t)
+                grads[k] = g
+                setattr(pp, f, t.data_ptr()); setattr(gp, f, g.data_ptr())
+        gx = torch.empty_like(x)
+        gp.x = gx.data_ptr()
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_op_resnet_block_backward(self.h, _ptr(x), C.byref(pp), _ptr(go), N, Cin, Cout, H, W,
+                                                        precision, C.byref(gp), _stream(self.device)))
+        return gx, grads
 
 
 _contexts: Dict[int, Context] = {}

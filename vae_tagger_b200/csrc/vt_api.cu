@@ -8,6 +8,7 @@
 #include "../../include/vae_tagger_b200.h"
 #include "vt_head_train.h"
 #include "vt_internal.h"
+#include "vt_backward.h"
 #include "vt_resize.h"
 #include "vt_ptx.cuh"
 
@@ -1719,6 +1720,190 @@ int vt_op_softmax_rows(vt_ctx* c, const float* sc, int64_t rows, int cols, int p
     VT_TRY(launch_softmax_rows(sc, c->opws.p, fmt, rows, cols, cols, cols, s, c->prof));
     // widen to fp32 through the layout kernel with C = cols, HW = 1 per row
     return launch_nhwc_to_nchw(c->opws.p, fmt, out, static_cast<int>(rows), cols, 1, s);
+}
+
+// ------------------------------------------------------------------------------------- backward ops (8f-4)
+}  // extern "C"
+namespace {
+// carve buffers out of the single-op workspace: register (pointer, bytes) pairs, then bind them all at once
+struct Carver {
+    struct Item { void** p; size_t bytes; };
+    std::vector<Item> items;
+    template <typename T> void want(T** p, size_t bytes) { items.push_back({reinterpret_cast<void**>(p), align_up(bytes, 1024)}); }
+    int bind(DevBuf& ws) {
+        size_t total = 0;
+        for (auto& it : items) total += it.bytes;
+        VT_TRY(ws.ensure(total));
+        char* b = static_cast<char*>(ws.p);
+        for (auto& it : items) { *it.p = b; b += it.bytes; }
+        return 0;
+    }
+};
+BwdEnv bwd_env(vt_ctx* c, int precision, void* stream) {
+    BwdEnv e;
+    e.s = static_cast<cudaStream_t>(stream); e.prof = c->prof; e.fp32 = precision == VT_PREC_FP32;
+    e.raw_fmt = c->raw_f16 ? FMT_F16 : FMT_BF16;
+    return e;
+}
+}  // namespace
+extern "C" {
+
+int vt_op_conv2d_backward(vt_ctx* c, const float* x, const float* w, const float* grad_out, int N, int Cin, int H, int W,
+                          int Cout, int ksize, int precision, float* grad_x, float* grad_w, float* grad_b, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(x && w && grad_out, "null pointers");
+    VT_CHECK(ksize == 1 || ksize == 3, "kernel size 1 or 3");
+    VT_CHECK(Cin % 64 == 0 && Cout % 64 == 0, "channels must be multiples of 64");
+    const BwdEnv e = bwd_env(c, precision, stream);
+    const int gf = e.fp32 ? FMT_F32 : FMT_BF16, xf = e.fp32 ? FMT_F32 : e.raw_fmt;
+    const size_t es = e.fp32 ? 4 : 2;
+    const long long HW = 1LL * H * W;
+    const WgradPlan plan = bwd_wgrad_plan(e, N, H, W, Cout, Cin, ksize);
+    void *dX, *dG, *dDx, *wd, *pa, *pb, *cs;
+    float* part;
+    Carver cv;
+    cv.want(&dX, N * HW * Cin * es); cv.want(&dG, N * HW * Cout * es); cv.want(&dDx, N * HW * Cin * es);
+    cv.want(&wd, bwd_dgrad_weight_bytes(e, Cout, Cin, ksize));
+    cv.want(&pa, e.fp32 ? 0 : plan.a_bytes); cv.want(&pb, e.fp32 ? 0 : plan.b_bytes);
+    cv.want(&part, plan.part_bytes); cv.want(&cs, bwd_colsum_scratch_bytes(Cout));
+    VT_TRY(cv.bind(c->opws));
+    VT_TRY(launch_nchw_to_nhwc(x, dX, xf, N, Cin, HW, e.s));
+    VT_TRY(launch_nchw_to_nhwc(grad_out, dG, gf, N, Cout, HW, e.s));
+    if (grad_x) {
+        VT_TRY(bwd_pack_dgrad_weight(e, w, wd, Cout, Cin, ksize));
+        VT_TRY(bwd_conv_dgrad(e, dG, wd, dDx, nullptr, N, H, W, Cout, Cin, ksize));
+        VT_TRY(launch_nhwc_to_nchw(dDx, gf, grad_x, N, Cin, HW, e.s));
+    }
+    if (grad_w) {
+        if (e.fp32) {
+            VT_TRY(bwd_conv_wgrad(e, plan, dG, dX, part, grad_w, N, H, W, Cout, Cin, ksize, 0));
+        } else {
+            VT_TRY(bwd_pack_plane(e, plan, dG, FMT_BF16, pa, nullptr, nullptr, nullptr, N, H, W, Cout, 0.f, 0, 1));
+            VT_TRY(bwd_pack_plane(e, plan, dX, xf, pb, nullptr, nullptr, nullptr, N, H, W, Cin, 0.f, 0, ksize == 3 ? 3 : 1));
+            VT_TRY(bwd_conv_wgrad(e, plan, pa, pb, part, grad_w, N, H, W, Cout, Cin, ksize, 0));
+        }
+    }
+    if (grad_b) VT_TRY(bwd_bias_grad(e, dG, N * HW, Cout, grad_b, 0, cs));
+    return 0;
+}
+
+int vt_op_group_norm_backward(vt_ctx* c, const float* x, const float* gamma, const float* beta, const float* grad_y, int N,
+                              int C, int H, int W, float eps, int silu, int precision, float* grad_x, float* grad_gamma,
+                              float* grad_beta, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(x && gamma && beta && grad_y && grad_x && grad_gamma && grad_beta, "null pointers");
+    const BwdEnv e = bwd_env(c, precision, stream);
+    const int gf = e.fp32 ? FMT_F32 : FMT_BF16, xf = e.fp32 ? FMT_F32 : e.raw_fmt;
+    const size_t es = e.fp32 ? 4 : 2;
+    const long long HW = 1LL * H * W;
+    void *dX, *dG, *dDx, *sc;
+    double* st;
+    Carver cv;
+    cv.want(&dX, N * HW * C * es); cv.want(&dG, N * HW * C * es); cv.want(&dDx, N * HW * C * es);
+    cv.want(&st, static_cast<size_t>(N) * 64 * sizeof(double)); cv.want(&sc, bwd_gn_scratch_bytes(N, HW, C));
+    VT_TRY(cv.bind(c->opws));
+    VT_TRY(launch_nchw_to_nhwc(x, dX, xf, N, C, HW, e.s));
+    VT_TRY(launch_nchw_to_nhwc(grad_y, dG, gf, N, C, HW, e.s));
+    VT_TRY(launch_gn_stats(dX, xf, st, N, HW, C, 32, e.s, c->prof));
+    VT_TRY(bwd_group_norm(e, dX, dG, st, gamma, beta, nullptr, dDx, grad_gamma, grad_beta, N, HW, C, eps, silu, 0, sc));
+    return launch_nhwc_to_nchw(dDx, gf, grad_x, N, C, HW, e.s);
+}
+
+int vt_op_resnet_block_backward(vt_ctx* c, const float* x, const vt_resnet_block_params* pr, const float* grad_out, int N,
+                                int Cin, int Cout, int H, int W, int precision, const vt_resnet_block_grads* g, void* stream) {
+    VT_TRY(set_device(c));
+    VT_CHECK(x && pr && grad_out && g, "null pointers");
+    VT_CHECK(pr->norm1_w && pr->norm1_b && pr->conv1_w && pr->conv1_b && pr->norm2_w && pr->norm2_b && pr->conv2_w && pr->conv2_b,
+             "missing block parameters");
+    VT_CHECK(g->x && g->norm1_w && g->norm1_b && g->conv1_w && g->conv1_b && g->norm2_w && g->norm2_b && g->conv2_w && g->conv2_b,
+             "missing gradient outputs");
+    const bool sc = Cin != Cout;
+    VT_CHECK(!sc || (pr->sc_w && pr->sc_b && g->sc_w && g->sc_b), "a channel-changing block needs its 1x1 shortcut");
+    VT_CHECK(Cin % 128 == 0 && Cout % 128 == 0, "channels must be multiples of 128");
+    const BwdEnv e = bwd_env(c, precision, stream);
+    const int gf = e.fp32 ? FMT_F32 : FMT_BF16, xf = e.fp32 ? FMT_F32 : e.raw_fmt, of = e.fp32 ? FMT_F32 : FMT_F16;
+    const size_t es = e.fp32 ? 4 : 2;
+    const long long HW = 1LL * H * W;
+    const float eps = 1e-6f;
+    const int Cmax = std::max(Cin, Cout);
+    // one operand-plane geometry for the three weight gradients of the block (they share the planes of dOut / x)
+    WgradPlan plan = bwd_wgrad_plan(e, N, H, W, Cout, Cmax, 3);
+    plan.part_bytes = align_up(static_cast<size_t>(plan.batches) * Cout * 9 * Cmax * sizeof(float), 256);
+    void *X, *H1, *T, *dOut, *dA, *dH, *dX, *dSc, *w1, *wd1, *wd2, *wds, *pa, *pb, *gsc, *cs;
+    double *st_x, *st_h;
+    float* part;
+    Carver cv;
+    cv.want(&X, N * HW * Cin * es); cv.want(&H1, N * HW * Cout * es); cv.want(&T, N * HW * Cmax * es);
+    cv.want(&dOut, N * HW * Cout * es); cv.want(&dA, N * HW * Cmax * es); cv.want(&dH, N * HW * Cout * es);
+    cv.want(&dX, N * HW * Cin * es); cv.want(&dSc, sc ? N * HW * Cin * es : 0);
+    cv.want(&w1, static_cast<size_t>(Cout) * 9 * Cin * es);
+    cv.want(&wd1, bwd_dgrad_weight_bytes(e, Cout, Cin, 3)); cv.want(&wd2, bwd_dgrad_weight_bytes(e, Cout, Cout, 3));
+    cv.want(&wds, sc ? bwd_dgrad_weight_bytes(e, Cout, Cin, 1) : 0);
+    cv.want(&pa, e.fp32 ? 0 : align_up(static_cast<size_t>(Cout) * plan.rowlen * 2, 256));
+    cv.want(&pb, e.fp32 ? 0 : align_up(static_cast<size_t>(3) * Cmax * plan.rowlen * 2, 256));
+    cv.want(&part, plan.part_bytes);
+    cv.want(&gsc, bwd_gn_scratch_bytes(N, HW, Cmax)); cv.want(&cs, bwd_colsum_scratch_bytes(Cout));
+    cv.want(&st_x, static_cast<size_t>(N) * 64 * sizeof(double)); cv.want(&st_h, static_cast<size_t>(N) * 64 * sizeof(double));
+    VT_TRY(cv.bind(c->opws));
+
+    // ---- forward, first half: h = conv1(silu(norm1(x))) + b1 (stored in the raw format), statistics of x and h
+    VT_TRY(launch_nchw_to_nhwc(x, X, xf, N, Cin, HW, e.s));
+    VT_TRY(launch_nchw_to_nhwc(grad_out, dOut, gf, N, Cout, HW, e.s));
+    VT_TRY(launch_gn_stats(X, xf, st_x, N, HW, Cin, 32, e.s, c->prof));
+    VT_TRY(launch_gn_apply(X, xf, T, of, st_x, pr->norm1_w, pr->norm1_b, N, HW, Cin, 32, eps, 1, e.s, c->prof));
+    if (e.fp32) pack_weight_kernel<FMT_F32><<<256, 256, 0, e.s>>>(pr->conv1_w, w1, Cout, Cin, 3, 9 * Cin, 0);
+    else pack_weight_kernel<FMT_F16><<<256, 256, 0, e.s>>>(pr->conv1_w, w1, Cout, Cin, 3, 9 * Cin, 0);
+    VT_CUDA(cudaGetLastError());
+    {
+        ConvOp op;
+        op.in = T; op.in_f16 = 1; op.raw_f16 = c->raw_f16; op.N = N; op.Hin = H; op.Win = W; op.Cin = Cin; op.ksize = 3;
+        op.stride = 1; op.w = w1; op.Cout = Cout; op.bias = pr->conv1_b; op.out = H1; op.out_fmt = xf;
+        VT_TRY(e.fp32 ? launch_conv_fp32(op, e.s, c->prof) : launch_conv(op, e.s, c->prof));
+    }
+    VT_TRY(launch_gn_stats(H1, xf, st_h, N, HW, Cout, 32, e.s, c->prof));
+
+    // ---- conv2 (+ shortcut): weight / bias gradients, data gradient
+    VT_TRY(bwd_bias_grad(e, dOut, N * HW, Cout, g->conv2_b, 0, cs));
+    if (sc) VT_TRY(bwd_bias_grad(e, dOut, N * HW, Cout, g->sc_b, 0, cs));
+    WgradPlan p1 = plan; p1.taps = 1;
+    if (e.fp32) {
+        VT_TRY(launch_gn_apply(H1, xf, T, of, st_h, pr->norm2_w, pr->norm2_b, N, HW, Cout, 32, eps, 1, e.s, c->prof));
+        VT_TRY(bwd_conv_wgrad(e, plan, dOut, T, part, g->conv2_w, N, H, W, Cout, Cout, 3, 0));
+        if (sc) VT_TRY(bwd_conv_wgrad(e, p1, dOut, X, part, g->sc_w, N, H, W, Cout, Cin, 1, 0));
+    } else {
+        VT_TRY(bwd_pack_plane(e, plan, dOut, FMT_BF16, pa, nullptr, nullptr, nullptr, N, H, W, Cout, 0.f, 0, 1));
+        VT_TRY(bwd_pack_plane(e, plan, H1, xf, pb, st_h, pr->norm2_w, pr->norm2_b, N, H, W, Cout, eps, 1, 3));
+        VT_TRY(bwd_conv_wgrad(e, plan, pa, pb, part, g->conv2_w, N, H, W, Cout, Cout, 3, 0));
+        if (sc) {
+            VT_TRY(bwd_pack_plane(e, plan, X, xf, pb, nullptr, nullptr, nullptr, N, H, W, Cin, 0.f, 0, 1));
+            VT_TRY(bwd_conv_wgrad(e, p1, pa, pb, part, g->sc_w, N, H, W, Cout, Cin, 1, 0));
+        }
+    }
+    VT_TRY(bwd_pack_dgrad_weight(e, pr->conv2_w, wd2, Cout, Cout, 3));
+    VT_TRY(bwd_conv_dgrad(e, dOut, wd2, dA, nullptr, N, H, W, Cout, Cout, 3));
+    // ---- norm2 + SiLU
+    VT_TRY(bwd_group_norm(e, H1, dA, st_h, pr->norm2_w, pr->norm2_b, nullptr, dH, g->norm2_w, g->norm2_b, N, HW, Cout, eps, 1, 0, gsc));
+    // ---- conv1
+    VT_TRY(bwd_bias_grad(e, dH, N * HW, Cout, g->conv1_b, 0, cs));
+    if (e.fp32) {
+        VT_TRY(launch_gn_apply(X, xf, T, of, st_x, pr->norm1_w, pr->norm1_b, N, HW, Cin, 32, eps, 1, e.s, c->prof));
+        VT_TRY(bwd_conv_wgrad(e, plan, dH, T, part, g->conv1_w, N, H, W, Cout, Cin, 3, 0));
+    } else {
+        VT_TRY(bwd_pack_plane(e, plan, dH, FMT_BF16, pa, nullptr, nullptr, nullptr, N, H, W, Cout, 0.f, 0, 1));
+        VT_TRY(bwd_pack_plane(e, plan, X, xf, pb, st_x, pr->norm1_w, pr->norm1_b, N, H, W, Cin, eps, 1, 3));
+        VT_TRY(bwd_conv_wgrad(e, plan, pa, pb, part, g->conv1_w, N, H, W, Cout, Cin, 3, 0));
+    }
+    VT_TRY(bwd_pack_dgrad_weight(e, pr->conv1_w, wd1, Cout, Cin, 3));
+    VT_TRY(bwd_conv_dgrad(e, dH, wd1, dA, nullptr, N, H, W, Cout, Cin, 3));
+    // ---- shortcut branch gradient, added inside norm1's apply pass
+    const void* add = dOut;
+    if (sc) {
+        VT_TRY(bwd_pack_dgrad_weight(e, pr->sc_w, wds, Cout, Cin, 1));
+        VT_TRY(bwd_conv_dgrad(e, dOut, wds, dSc, nullptr, N, H, W, Cout, Cin, 1));
+        add = dSc;
+    }
+    VT_TRY(bwd_group_norm(e, X, dA, st_x, pr->norm1_w, pr->norm1_b, add, dX, g->norm1_w, g->norm1_b, N, HW, Cin, eps, 1, 0, gsc));
+    return launch_nhwc_to_nchw(dX, gf, g->x, N, Cin, HW, e.s);
 }
 
 }  // extern "C"

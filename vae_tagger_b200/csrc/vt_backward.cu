@@ -1,0 +1,570 @@
+// Backward pass of the encoder's building blocks (the reference fine-tunes the VAE through
+// autograd in train_vae.py:124-186 and train_full.py:201-256; the arithmetic restated here is the autograd of
+// diffusers' ResnetBlock2D = GroupNorm(32) -> SiLU -> conv3x3, twice, plus the identity / 1x1 shortcut).
+//
+//   * data gradient of a 3x3 / 1x1 stride-1 conv  = the forward implicit-GEMM tcgen05 kernel (vt_igemm.cuh) run on
+//     the output gradient with the weights flipped and transposed ([Cin][tap'][Cout], tap' = 8 - tap);
+//   * weight gradient = a tcgen05 GEMM whose K dimension is the PIXELS: dW[co][tap][ci] = sum_p dY[p][co] A[p+tap][ci].
+//     Both operands are re-laid out once per conv as channel-major rows over a zero-padded pixel plane
+//     ([C][guard | image 0: (H+2) x Wp | image 1 ... | guard], bf16), so that a tap is a constant flat offset
+//     (dy*Wp + dx) and the padding supplies the zeros of "pad 1"; the row of an image is cut into S equal K ranges
+//     (split-K: one GEMM "batch" per (image, range), fp32 partial tiles) and wgrad_reduce_kernel adds the partials
+//     in index order -- no atomics, bit-reproducible.  One launch of the forward GEMM kernel per tap, with a
+//     different K start coordinate for the B operand (GemmOp::b_k0; TMA coordinates need no alignment);
+//   * GroupNorm + SiLU backward: two HBM passes (per-channel sums of dt and dt*xhat with a fixed-order two-stage
+//     reduce, then the apply pass, with the residual-branch gradient added in the same pass);
+//   * bias gradients: fixed-order column sums.
+//
+// 16-bit mode: activations in the context's raw format, gradients and the re-laid-out operands bf16 (range of a
+// gradient is unbounded and no loss scaling exists in the reference), fp32 accumulation, fp32 parameter gradients.
+// fp32 mode (verification): everything fp32 on the FFMA pipe (f32_wgrad_kernel, launch_conv_fp32).
+#include <cstdlib>
+#include <type_traits>
+
+#include "vt_backward.h"
+#include "vt_ptx.cuh"
+
+namespace vt {
+
+namespace {
+
+inline size_t al(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+template <int F>
+__device__ __forceinline__ void load8(const void* base, long long off, float v[8]) {
+    if constexpr (F == FMT_F32) {
+        const float* p = static_cast<const float*>(base) + off;
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(base) + off);
+        v[0] = raw16_lo<F>(u.x); v[1] = raw16_hi<F>(u.x); v[2] = raw16_lo<F>(u.y); v[3] = raw16_hi<F>(u.y);
+        v[4] = raw16_lo<F>(u.z); v[5] = raw16_hi<F>(u.z); v[6] = raw16_lo<F>(u.w); v[7] = raw16_hi<F>(u.w);
+    }
+}
+template <int F>
+__device__ __forceinline__ void store8(void* base, long long off, const float v[8]) {
+    if constexpr (F == FMT_F32) {
+        float* p = static_cast<float*>(base) + off;
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        *reinterpret_cast<uint4*>(static_cast<bf16*>(base) + off) =
+            make_uint4(pack16x2<F>(v[0], v[1]), pack16x2<F>(v[2], v[3]), pack16x2<F>(v[4], v[5]), pack16x2<F>(v[6], v[7]));
+    }
+}
+
+// per-channel GroupNorm constants of the 8 channels a thread owns
+struct Gn8 {
+    float mean[8], rstd[8], ga[8], be[8];
+};
+__device__ __forceinline__ void gn8_load(Gn8& k, const double* stats, const float* gamma, const float* beta, int n,
+                                         int c0, int C, long long HW, float eps) {
+    const int cpg = C / 32;
+    const double cnt = static_cast<double>(HW) * cpg;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e, g = c / cpg;
+        const double su = stats[(1LL * n * 32 + g) * 2], sq = stats[(1LL * n * 32 + g) * 2 + 1];
+        const double mean = su / cnt;
+        double var = sq / cnt - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        k.mean[e] = static_cast<float>(mean);
+        k.rstd[e] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        k.ga[e] = gamma[c];
+        k.be[e] = beta[c];
+    }
+}
+// xhat and dt = dy * act'(t), t = gamma*xhat + beta
+__device__ __forceinline__ void gn_dt(float x, float dy, float mean, float rstd, float ga, float be, int silu, float& xhat,
+                                      float& dt) {
+    xhat = (x - mean) * rstd;
+    dt = dy;
+    if (silu) {
+        const float t = fmaf(ga, xhat, be);
+        const float sg = 1.0f / (1.0f + expf(-t));
+        dt = dy * sg * (1.0f + t * (1.0f - sg));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm(+SiLU) backward, pass 1: part[n][chunk][c] = (sum_p dt, sum_p dt*xhat) over the chunk's pixels.
+// Thread = 8 consecutive channels, walks pixels; the pixel sub-lanes of a block are folded in index order.
+template <int XF, int GF>
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restrict__ x, const void* __restrict__ dy,
+                                                            const double* __restrict__ stats,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ part,
+                                                            long long HW, int C, float eps, int silu) {
+    __shared__ float sh[256 * 16];
+    const int n = blockIdx.y;
+    const int tpb = C / 8;                 // threads across the channels (C <= 2048)
+    const int ppb = 256 / tpb;
+    const int c8 = threadIdx.x % tpb, psub = threadIdx.x / tpb;
+    const long long chunk = (HW + gridDim.x - 1) / gridDim.x;
+    const long long p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+    float a[8], b[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
+    if (psub < ppb) {
+        Gn8 k;
+        gn8_load(k, stats, gamma, beta, n, c8 * 8, C, HW, eps);
+        for (long long p = p0 + psub; p < p1; p += ppb) {
+            const long long off = (1LL * n * HW + p) * C + c8 * 8;
+            float xv[8], gv[8];
+            load8<XF>(x, off, xv);
+            load8<GF>(dy, off, gv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float xh, dt;
+                gn_dt(xv[e], gv[e], k.mean[e], k.rstd[e], k.ga[e], k.be[e], silu, xh, dt);
+                a[e] += dt;
+                b[e] = fmaf(dt, xh, b[e]);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        sh[threadIdx.x * 16 + e] = a[e];
+        sh[threadIdx.x * 16 + 8 + e] = b[e];
+    }
+    __syncthreads();
+    if (threadIdx.x < tpb) {
+        for (int e = 0; e < 16; ++e) {
+            float t = 0.f;
+            for (int q = 0; q < ppb; ++q) t += sh[(q * tpb + threadIdx.x) * 16 + e];
+            const int c = threadIdx.x * 8 + (e & 7);
+            part[((1LL * n * gridDim.x + blockIdx.x) * C + c) * 2 + (e >> 3)] = t;
+        }
+    }
+}
+
+// pass 1b (one block of C threads): chunks added in index order in fp64; per (image, group) the two sums the
+// apply pass needs, S1 = sum_c gamma_c A_c, S2 = sum_c gamma_c B_c; d gamma / d beta summed over the images in
+// index order.
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+                                       float* __restrict__ gsum /*[N][32][2]*/, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int N, int chunks, int C, int accumulate) {
+    __shared__ double sa[1024], sb[1024];
+    const int c = threadIdx.x;
+    const int cpg = C / 32;
+    double dg = 0.0, db = 0.0;
+    for (int n = 0; n < N; ++n) {
+        double A = 0.0, B = 0.0;
+        for (int k = 0; k < chunks; ++k) {
+            const float* p = part + ((1LL * n * chunks + k) * C + c) * 2;
+            A += p[0];
+            B += p[1];
+        }
+        db += A;
+        dg += B;
+        sa[c] = A * gamma[c];
+        sb[c] = B * gamma[c];
+        __syncthreads();
+        if (c < 32) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int e = 0; e < cpg; ++e) { s1 += sa[c * cpg + e]; s2 += sb[c * cpg + e]; }
+            gsum[(n * 32 + c) * 2] = static_cast<float>(s1);
+            gsum[(n * 32 + c) * 2 + 1] = static_cast<float>(s2);
+        }
+        __syncthreads();
+    }
+    if (accumulate) { dgamma[c] += static_cast<float>(dg); dbeta[c] += static_cast<float>(db); }
+    else { dgamma[c] = static_cast<float>(dg); dbeta[c] = static_cast<float>(db); }
+}
+
+// pass 2: dx = rstd * (gamma*dt - (S1 + xhat*S2)/m) (+ add)
+template <int XF, int GF>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restrict__ x, const void* __restrict__ dy,
+                                                           const double* __restrict__ stats,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta,
+                                                           const float* __restrict__ gsum,
+                                                           const void* __restrict__ add, void* __restrict__ dx,
+                                                           long long HW, int C, float eps, int silu) {
+    const int n = blockIdx.y;
+    const int tpb = C / 8;
+    const int ppb = 256 / tpb;
+    const int c8 = threadIdx.x % tpb, psub = threadIdx.x / tpb;
+    if (psub >= ppb) return;
+    const int cpg = C / 32;
+    const float inv_m = 1.0f / (static_cast<float>(HW) * cpg);
+    const long long chunk = (HW + gridDim.x - 1) / gridDim.x;
+    const long long p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+    Gn8 k;
+    gn8_load(k, stats, gamma, beta, n, c8 * 8, C, HW, eps);
+    float s1[8], s2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int g = (c8 * 8 + e) / cpg;
+        s1[e] = gsum[(n * 32 + g) * 2] * inv_m;
+        s2[e] = gsum[(n * 32 + g) * 2 + 1] * inv_m;
+    }
+    for (long long p = p0 + psub; p < p1; p += ppb) {
+        const long long off = (1LL * n * HW + p) * C + c8 * 8;
+        float xv[8], gv[8], av[8], o[8];
+        load8<XF>(x, off, xv);
+        load8<GF>(dy, off, gv);
+        if (add) load8<GF>(add, off, av);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float xh, dt;
+            gn_dt(xv[e], gv[e], k.mean[e], k.rstd[e], k.ga[e], k.be[e], silu, xh, dt);
+            o[e] = k.rstd[e] * (k.ga[e] * dt - (s1[e] + xh * s2[e]));
+            if (add) o[e] += av[e];
+        }
+        store8<GF>(dx, off, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bias gradient: column sums of g[rows][C], two fixed-order stages
+template <int GF>
+__global__ void __launch_bounds__(256) colsum_part_kernel(const void* __restrict__ g, float* __restrict__ part,
+                                                          long long rows, int C) {
+    __shared__ float sh[256 * 8];
+    const int tpb = C / 8, ppb = 256 / tpb;
+    const int c8 = threadIdx.x % tpb, psub = threadIdx.x / tpb;
+    const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
+    const long long p0 = blockIdx.x * chunk, p1 = min(rows, p0 + chunk);
+    float a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = 0.f;
+    if (psub < ppb)
+        for (long long p = p0 + psub; p < p1; p += ppb) {
+            float v[8];
+            load8<GF>(g, p * C + c8 * 8, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] += v[e];
+        }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sh[threadIdx.x * 8 + e] = a[e];
+    __syncthreads();
+    if (threadIdx.x < tpb)
+        for (int e = 0; e < 8; ++e) {
+            float t = 0.f;
+            for (int q = 0; q < ppb; ++q) t += sh[(q * tpb + threadIdx.x) * 8 + e];
+            part[1LL * blockIdx.x * C + threadIdx.x * 8 + e] = t;
+        }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int chunks, int C,
+                                    int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double t = 0.0;
+    for (int k = 0; k < chunks; ++k) t += part[1LL * k * C + c];
+    out[c] = (accumulate ? out[c] : 0.f) + static_cast<float>(t);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// flipped / transposed weights of the data-gradient conv: dst[ci][(ks*ks-1-tap)*Cout + co] = w[co][ci][tap]
+template <int OFMT>
+__global__ void pack_dgrad_weight_kernel(const float* __restrict__ w /*[Cout][Cin][ks][ks]*/, void* __restrict__ dst,
+                                         int Cout, int Cin, int ks) {
+    const long long total = 1LL * Cout * Cin * ks * ks;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int co = static_cast<int>(i % Cout);
+        long long r = i / Cout;
+        const int tp = static_cast<int>(r % (ks * ks));
+        const int ci = static_cast<int>(r / (ks * ks));
+        const float v = w[(1LL * co * Cin + ci) * ks * ks + (ks * ks - 1 - tp)];
+        if constexpr (OFMT == FMT_F32) static_cast<float*>(dst)[i] = v;
+        else static_cast<bf16*>(dst)[i] = __float2bfloat16(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NHWC [N][H][W][C] (format XF) -> channel-major rows over the zero-padded pixel plane, bf16:
+//   dst[c][G + n*Kimg + (y+1)*Wp + LP + x],  optionally through GroupNorm(+SiLU) of the source (the operand a
+//   conv actually saw).  64 pixels x 64 channels per block through shared memory; 16-byte stores (LP = 8, Wp % 8 == 0).
+constexpr int WG_LP = 8;
+template <int XF>
+__global__ void __launch_bounds__(256) pack_plane_kernel(const void* __restrict__ src, bf16* __restrict__ dst,
+                                                         const double* __restrict__ stats,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int H, int W, int C, int Wp,
+                                                         long long Kimg, long long G, long long rowlen, float eps,
+                                                         int silu, int copies) {
+    __shared__ bf16 tile[64][72];
+    const int xt = blockIdx.x % ((W + 63) / 64), y = blockIdx.x / ((W + 63) / 64);
+    const int c0 = blockIdx.y * 64, n = blockIdx.z;
+    const int x0 = xt * 64;
+    {
+        const int px = threadIdx.x >> 2, q = threadIdx.x & 3;   // pixel, 16-channel quarter
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = 0.f;
+        if (x0 + px < W) {
+            const long long off = ((1LL * n * H + y) * W + x0 + px) * C + c0 + q * 16;
+            load8<XF>(src, off, v);
+            load8<XF>(src, off + 8, v + 8);
+            if (stats) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    Gn8 k;
+                    gn8_load(k, stats, gamma, beta, n, c0 + q * 16 + h * 8, C, 1LL * H * W, eps);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float t = fmaf(k.ga[e] * k.rstd[e], v[h * 8 + e] - k.mean[e], k.be[e]);
+                        if (silu) t = t / (1.0f + expf(-t));
+                        v[h * 8 + e] = t;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) tile[q * 16 + e][px] = __float2bfloat16(v[e]);
+    }
+    __syncthreads();
+    {
+        const int c = threadIdx.x >> 2, q = threadIdx.x & 3;    // channel, 16-pixel quarter
+        bf16* row = dst + 1LL * (c0 + c) * rowlen + G + 1LL * n * Kimg + 1LL * (y + 1) * Wp + WG_LP + x0 + q * 16;
+        if (copies == 3) row += 1LL * C * rowlen;   // copies: [dx = -1 | dx = 0 | dx = +1], copy j holds plane[q + j - 1] at q
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int xs = x0 + q * 16 + h * 8;
+            if (xs + 8 <= W) {
+                *reinterpret_cast<uint4*>(row + h * 8) = *reinterpret_cast<const uint4*>(&tile[c][q * 16 + h * 8]);
+            } else {
+                for (int e = 0; e < 8 && xs + e < W; ++e) row[h * 8 + e] = tile[c][q * 16 + h * 8 + e];
+            }
+            if (copies == 3) {
+                // TMA needs 16-byte aligned start coordinates in the innermost dimension: a +-1 pixel tap cannot be a
+                // coordinate offset, so the two horizontally shifted planes are materialised (2-byte stores)
+                bf16* lo = row - 1LL * C * rowlen + 1;   // dx = -1: value of position q - 1 stored at q
+                bf16* hi = row + 1LL * C * rowlen - 1;   // dx = +1: value of position q + 1 stored at q
+                for (int e = 0; e < 8 && xs + e < W; ++e) {
+                    const bf16 v = tile[c][q * 16 + h * 8 + e];
+                    lo[h * 8 + e] = v;
+                    hi[h * 8 + e] = v;
+                }
+            }
+        }
+    }
+}
+
+// partial tiles part[b][co][taps*Cin] -> dW [Cout][Cin][ks][ks] (OIHW, what torch holds), batches in index order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int batches, int Cout,
+                                    int Cin, int taps, int accumulate) {
+    const long long total = 1LL * Cout * Cin * taps;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int ci = static_cast<int>(i % Cin);
+        long long r = i / Cin;
+        const int tp = static_cast<int>(r % taps);
+        const int co = static_cast<int>(r / taps);
+        double t = 0.0;
+        for (int b = 0; b < batches; ++b) t += part[(1LL * b * Cout + co) * taps * Cin + 1LL * tp * Cin + ci];
+        float* o = dw + (1LL * co * Cin + ci) * taps + tp;
+        *o = (accumulate ? *o : 0.f) + static_cast<float>(t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 verification mode: weight gradient straight from the NHWC tensors on the FFMA pipe ("TN" GEMM, K = pixels).
+// grid (Cout/64, taps * Cin/64, splits); part[split][co][taps*Cin]
+__global__ void __launch_bounds__(256) f32_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ a,
+                                                        float* __restrict__ part, int N, int H, int W, int Cout, int Cin,
+                                                        int ks) {
+    __shared__ float As[16][68], Bs[16][68];
+    const int taps = ks * ks;
+    const int cit = Cin / 64;
+    const int tap = blockIdx.y / cit, ci0 = (blockIdx.y % cit) * 64, co0 = blockIdx.x * 64;
+    const int dyo = ks == 3 ? tap / 3 - 1 : 0, dxo = ks == 3 ? tap % 3 - 1 : 0;
+    const long long P = 1LL * N * H * W;
+    const long long chunk = (P + gridDim.z - 1) / gridDim.z;
+    const long long p0 = blockIdx.z * chunk, p1 = min(P, p0 + chunk);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lk = threadIdx.x >> 4, lc = (threadIdx.x & 15) * 4;
+    float acc[4][4] = {};
+    for (long long pb = p0; pb < p1; pb += 16) {
+        const long long p = pb + lk;
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+        if (p < p1) {
+            av = *reinterpret_cast<const float4*>(dy + p * Cout + co0 + lc);
+            const int x = static_cast<int>(p % W);
+            const long long r = p / W;
+            const int y = static_cast<int>(r % H);
+            const int ys = y + dyo, xs = x + dxo;
+            if (ys >= 0 && ys < H && xs >= 0 && xs < W)
+                bv = *reinterpret_cast<const float4*>(a + (p + 1LL * dyo * W + dxo) * Cin + ci0 + lc);
+        }
+        *reinterpret_cast<float4*>(&As[lk][lc]) = av;
+        *reinterpret_cast<float4*>(&Bs[lk][lc]) = bv;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            part[(1LL * blockIdx.z * Cout + co0 + ty * 4 + i) * taps * Cin + 1LL * tap * Cin + ci0 + tx * 4 + j] = acc[i][j];
+}
+
+int grid_for(long long n) { return static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 8)); }
+
+}  // namespace
+
+// =========================================================================================================
+int bwd_gn_chunks(int N, long long HW) {
+    const long long want = (HW + 255) / 256;
+    return static_cast<int>(std::max<long long>(1, std::min<long long>(want, std::max(1, 148 * 4 / std::max(N, 1)))));
+}
+size_t bwd_gn_scratch_bytes(int N, long long HW, int C) {
+    return al(static_cast<size_t>(N) * bwd_gn_chunks(N, HW) * C * 2 * sizeof(float)) + al(static_cast<size_t>(N) * 64 * sizeof(float));
+}
+
+int bwd_group_norm(const BwdEnv& e, const void* x, const void* dy, const double* stats, const float* gamma,
+                   const float* beta, const void* add, void* dx, float* dgamma, float* dbeta, int N, long long HW, int C,
+                   float eps, int silu, int accumulate, void* scratch) {
+    VT_CHECK(C % 256 == 0 || C == 128, "GroupNorm backward: 128 channels or a multiple of 256");
+    VT_CHECK(C <= 1024, "GroupNorm backward: at most 1024 channels");
+    const int chunks = bwd_gn_chunks(N, HW);
+    float* part = static_cast<float*>(scratch);
+    float* gsum = reinterpret_cast<float*>(static_cast<char*>(scratch) + al(static_cast<size_t>(N) * chunks * C * 2 * sizeof(float)));
+    dim3 grid(chunks, N);
+    profiler_begin(e.prof, KC_GN_APPLY, e.s, 0, 2.0 * N * HW * C * (e.fp32 ? 8.0 : 4.0) + 1.0 * N * HW * C * (e.fp32 ? 4 : 2));
+    if (e.fp32) {
+        gn_bwd_reduce_kernel<FMT_F32, FMT_F32><<<grid, 256, 0, e.s>>>(x, dy, stats, gamma, beta, part, HW, C, eps, silu);
+    } else if (e.raw_fmt == FMT_F16) {
+        gn_bwd_reduce_kernel<FMT_F16, FMT_BF16><<<grid, 256, 0, e.s>>>(x, dy, stats, gamma, beta, part, HW, C, eps, silu);
+    } else {
+        gn_bwd_reduce_kernel<FMT_BF16, FMT_BF16><<<grid, 256, 0, e.s>>>(x, dy, stats, gamma, beta, part, HW, C, eps, silu);
+    }
+    gn_bwd_finalize_kernel<<<1, C, 0, e.s>>>(part, gamma, gsum, dgamma, dbeta, N, chunks, C, accumulate);
+    if (e.fp32) {
+        gn_bwd_apply_kernel<FMT_F32, FMT_F32><<<grid, 256, 0, e.s>>>(x, dy, stats, gamma, beta, gsum, add, dx, HW, C, eps, silu);
+    } else if (e.raw_fmt == FMT_F16) {
+        gn_bwd_apply_kernel<FMT_F16, FMT_BF16><<<grid, 256, 0, e.s>>>(x, dy, stats, gamma, beta, gsum, add, dx, HW, C, eps, silu);
+    } else {
+        gn_bwd_apply_kernel<FMT_BF16, FMT_BF16><<<grid, 256, 0, e.s>>>(x, dy, stats, gamma, beta, gsum, add, dx, HW, C, eps, silu);
+    }
+    profiler_end(e.prof, KC_GN_APPLY, e.s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+size_t bwd_colsum_scratch_bytes(int C) { return al(static_cast<size_t>(148 * 4) * C * sizeof(float)); }
+int bwd_bias_grad(const BwdEnv& e, const void* g, long long rows, int C, float* db, int accumulate, void* scratch) {
+    VT_CHECK(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bias gradient: channel count must divide 2048");
+    const int chunks = static_cast<int>(std::max<long long>(1, std::min<long long>((rows + 255) / 256, 148 * 4)));
+    float* part = static_cast<float*>(scratch);
+    if (e.fp32) colsum_part_kernel<FMT_F32><<<chunks, 256, 0, e.s>>>(g, part, rows, C);
+    else colsum_part_kernel<FMT_BF16><<<chunks, 256, 0, e.s>>>(g, part, rows, C);
+    colsum_final_kernel<<<(C + 127) / 128, 128, 0, e.s>>>(part, db, chunks, C, accumulate);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- data gradient
+size_t bwd_dgrad_weight_bytes(const BwdEnv& e, int Cout, int Cin, int ks) {
+    return al(static_cast<size_t>(Cout) * Cin * ks * ks * (e.fp32 ? 4 : 2));
+}
+int bwd_pack_dgrad_weight(const BwdEnv& e, const float* w, void* dst, int Cout, int Cin, int ks) {
+    const long long total = 1LL * Cout * Cin * ks * ks;
+    if (e.fp32) pack_dgrad_weight_kernel<FMT_F32><<<grid_for(total), 256, 0, e.s>>>(w, dst, Cout, Cin, ks);
+    else pack_dgrad_weight_kernel<FMT_BF16><<<grid_for(total), 256, 0, e.s>>>(w, dst, Cout, Cin, ks);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+int bwd_conv_dgrad(const BwdEnv& e, const void* dy, const void* wd, void* dx, const void* add, int N, int H, int W,
+                   int Cout, int Cin, int ks) {
+    // a stride-1 conv of the output gradient ([N][H][W][Cout]) with the flipped / transposed weights [Cin][ks*ks*Cout]
+    ConvOp op;
+    op.in = dy; op.in_f16 = 0; op.raw_f16 = 0; op.N = N; op.Hin = H; op.Win = W; op.Cin = Cout; op.ksize = ks; op.stride = 1;
+    op.w = wd; op.Cout = Cin; op.out = dx; op.out_fmt = e.fp32 ? FMT_F32 : FMT_BF16;
+    op.residual = add; op.residual_fp32 = e.fp32;
+    op.kclass = KC_BWD;
+    return e.fp32 ? launch_conv_fp32(op, e.s, e.prof) : launch_conv(op, e.s, e.prof);
+}
+
+// ---- weight gradient
+WgradPlan bwd_wgrad_plan(const BwdEnv& e, int N, int H, int W, int Cout, int Cin, int ks) {
+    WgradPlan p{};
+    p.taps = ks * ks;
+    if (e.fp32) {
+        const long long P = 1LL * N * H * W;
+        const int tiles = (Cout / 64) * (p.taps * Cin / 64);
+        p.splits = static_cast<int>(std::max<long long>(1, std::min<long long>((P + 1023) / 1024, std::max(1, 148 * 8 / tiles))));
+        p.batches = p.splits;
+        p.part_bytes = al(static_cast<size_t>(p.batches) * Cout * p.taps * Cin * sizeof(float));
+        return p;
+    }
+    p.Wp = (W + WG_LP + 1 + 7) / 8 * 8;
+    const long long plane = 1LL * (H + 2) * p.Wp;
+    const int mt = Cin >= 256 ? 1 : 2;                                  // launch_gemm's tile: 128 x 256 or 2x128 x 128
+    const int block_n = Cin >= 256 ? 256 : 128;
+    const int tiles = ((Cout + 128 * mt - 1) / (128 * mt)) * ((Cin + block_n - 1) / block_n);
+    long long S = std::max(1, (2 * 148 + N * tiles - 1) / (N * tiles));   // ~2 waves of CTAs per tap launch
+    S = std::min<long long>(S, std::max<long long>(1, plane / 512));       // at least 8 K chunks per tile
+    p.Ks = ((plane + S - 1) / S + 63) / 64 * 64;
+    p.splits = static_cast<int>(S);
+    p.Kimg = p.Ks * S;
+    p.G = (p.Wp + 1 + 7) / 8 * 8;
+    p.rowlen = (p.G + 1LL * N * p.Kimg + p.G + 64 + 7) / 8 * 8;
+    p.batches = N * p.splits;
+    p.a_bytes = al(static_cast<size_t>(Cout) * p.rowlen * 2);
+    p.b_bytes = al(static_cast<size_t>(ks == 3 ? 3 : 1) * Cin * p.rowlen * 2);
+    p.part_bytes = al(static_cast<size_t>(p.batches) * Cout * p.taps * Cin * sizeof(float));
+    return p;
+}
+
+int bwd_pack_plane(const BwdEnv& e, const WgradPlan& p, const void* src, int src_fmt, void* dst, const double* stats,
+                   const float* gamma, const float* beta, int N, int H, int W, int C, float eps, int silu, int copies) {
+    VT_CHECK(!e.fp32 && C % 64 == 0, "operand planes exist in the 16-bit mode only; channels a multiple of 64");
+    VT_CHECK(copies == 1 || copies == 3, "one plane, or the three horizontally shifted planes of a 3x3 conv input");
+    VT_CUDA(cudaMemsetAsync(dst, 0, static_cast<size_t>(copies) * C * p.rowlen * 2, e.s));
+    dim3 grid(((W + 63) / 64) * H, C / 64, N);
+    profiler_begin(e.prof, KC_MISC, e.s, 0, 4.0 * N * H * W * C);
+    if (src_fmt == FMT_F16)
+        pack_plane_kernel<FMT_F16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), stats, gamma, beta, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, eps, silu, copies);
+    else
+        pack_plane_kernel<FMT_BF16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), stats, gamma, beta, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, eps, silu, copies);
+    profiler_end(e.prof, KC_MISC, e.s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bwd_conv_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const void* a, float* part, float* dw, int N, int H,
+                   int W, int Cout, int Cin, int ks, int accumulate) {
+    if (e.fp32) {
+        VT_CHECK(Cout % 64 == 0 && Cin % 64 == 0, "fp32 weight gradient: channels must be multiples of 64");
+        dim3 grid(Cout / 64, p.taps * (Cin / 64), p.splits);
+        profiler_begin(e.prof, KC_FP32, e.s, 2.0 * N * H * W * Cout * Cin * p.taps, 0);
+        f32_wgrad_kernel<<<grid, 256, 0, e.s>>>(static_cast<const float*>(dy), static_cast<const float*>(a), part, N, H, W, Cout, Cin, ks);
+        profiler_end(e.prof, KC_FP32, e.s);
+    } else {
+        // dy, a: operand planes (bwd_pack_plane).  One GEMM launch per tap: M = Cout, N = Cin, K = Ks per (image, range)
+        const char* tm = getenv("VT_BWD_TAPMASK");    // debugging aid: run a subset of the taps
+        const int tapmask = tm ? atoi(tm) : 0x1FF;
+        for (int tap = 0; tap < p.taps; ++tap) {
+            if (!((tapmask >> tap) & 1)) continue;
+            const int dyo = ks == 3 ? tap / 3 - 1 : 0, dxo = ks == 3 ? tap % 3 - 1 : 0;
+            GemmOp g;
+            // a: three planes for a 3x3 conv (dx = -1, 0, +1), one for a 1x1 conv
+            g.A = dy; g.B = static_cast<const bf16*>(a) + (ks == 3 ? 1LL * (dxo + 1) * Cin * p.rowlen : 0); g.batch = p.batches; g.M = Cout; g.N = Cin; g.K = static_cast<int>(p.Ks);
+            g.lda = p.rowlen; g.ldb = p.rowlen; g.a_bstride = p.Ks; g.b_bstride = p.Ks;
+            g.a_kdim = p.rowlen; g.b_kdim = p.rowlen;
+            g.a_k0 = p.G; g.b_k0 = p.G + 1LL * dyo * p.Wp;     // k runs over plane positions, pads included
+            g.out = part + 1LL * tap * Cin; g.out_fmt = FMT_F32; g.ld_out = 1LL * p.taps * Cin;
+            g.out_bstride = 1LL * Cout * p.taps * Cin;
+            g.ab_f16 = 0; g.kclass = KC_BWD;
+            VT_TRY(launch_gemm(g, e.s, e.prof));
+        }
+    }
+    const long long total = 1LL * Cout * Cin * p.taps;
+    wgrad_reduce_kernel<<<grid_for(total), 256, 0, e.s>>>(part, dw, p.batches, Cout, Cin, p.taps, accumulate);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace vt

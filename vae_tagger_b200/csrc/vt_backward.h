@@ -1,0 +1,51 @@
+// Internal interface of the encoder backward building blocks (vt_backward.cu) used by the C-ABI layer.
+#pragma once
+#include "vt_internal.h"
+
+namespace vt {
+
+struct BwdEnv {
+    cudaStream_t s = nullptr;
+    Profiler* prof = nullptr;
+    int fp32 = 0;        // verification mode: every tensor fp32, FFMA kernels
+    int raw_fmt = 0;     // 16-bit mode: storage format of the forward activations (FMT_F16 / FMT_BF16); gradients are bf16
+};
+
+// GroupNorm(32)(+SiLU) backward over NHWC tensors.  x: forward input (raw format / fp32), dy: gradient of the output,
+// stats: (sum, sumsq) of x per (image, group), add: optional tensor added to dx (gradient format).
+int bwd_gn_chunks(int N, long long HW);
+size_t bwd_gn_scratch_bytes(int N, long long HW, int C);
+int bwd_group_norm(const BwdEnv& e, const void* x, const void* dy, const double* stats, const float* gamma,
+                   const float* beta, const void* add, void* dx, float* dgamma, float* dbeta, int N, long long HW, int C,
+                   float eps, int silu, int accumulate, void* scratch);
+
+// db[c] (+)= sum over rows of g[rows][C] (gradient format)
+size_t bwd_colsum_scratch_bytes(int C);
+int bwd_bias_grad(const BwdEnv& e, const void* g, long long rows, int C, float* db, int accumulate, void* scratch);
+
+// data gradient of a stride-1 conv: dx[N][H][W][Cin] = conv(dy[N][H][W][Cout], flipped / transposed weights) (+ add)
+size_t bwd_dgrad_weight_bytes(const BwdEnv& e, int Cout, int Cin, int ks);
+int bwd_pack_dgrad_weight(const BwdEnv& e, const float* w /*[Cout][Cin][ks][ks] fp32*/, void* dst, int Cout, int Cin, int ks);
+int bwd_conv_dgrad(const BwdEnv& e, const void* dy, const void* wd, void* dx, const void* add, int N, int H, int W,
+                   int Cout, int Cin, int ks);
+
+// weight gradient of a stride-1 conv
+struct WgradPlan {
+    int taps, splits, batches;
+    int Wp;                          // padded plane width (16-bit mode)
+    long long Ks, Kimg, G, rowlen;   // K range per GEMM batch, plane length per image, guard, row length (elements)
+    size_t a_bytes, b_bytes;         // operand planes of the output gradient / of the conv input
+    size_t part_bytes;               // fp32 split-K partial tiles
+};
+WgradPlan bwd_wgrad_plan(const BwdEnv& e, int N, int H, int W, int Cout, int Cin, int ks);
+// 16-bit mode: NHWC tensor -> bf16 operand plane (optionally through GroupNorm(+SiLU) given the tensor's statistics).
+// copies = 3: the input of a 3x3 conv -- three planes shifted by dx = -1, 0, +1 pixels ([3][C][rowlen]; TMA start
+// coordinates must be 16-byte aligned in the innermost dimension, so a one-pixel tap cannot be a coordinate offset)
+int bwd_pack_plane(const BwdEnv& e, const WgradPlan& p, const void* src, int src_fmt, void* dst, const double* stats,
+                   const float* gamma, const float* beta, int N, int H, int W, int C, float eps, int silu, int copies);
+// dw[Cout][Cin][ks][ks] (+)= sum_p dy[p][co] a[p + tap][ci].  16-bit mode: dy / a are operand planes; fp32 mode:
+// the NHWC fp32 tensors themselves (a = the conv's actual input).
+int bwd_conv_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const void* a, float* part, float* dw, int N, int H,
+                   int W, int Cout, int Cin, int ks, int accumulate);
+
+}  // namespace vt
