@@ -335,6 +335,30 @@ int vt_op_resnet_block_backward(vt_ctx* ctx, const float* x /*[N,Cin,H,W]*/, con
                                 const float* grad_out /*[N,Cout,H,W]*/, int N, int Cin, int Cout, int H, int W,
                                 int precision, const vt_resnet_block_grads* grads, void* stream);
 
+/* ---- VAE fine-tuning losses of the reference (improved_losses.py), value + analytic gradient in one call
+ * (SURVEY.md 8f-4).  Device pointers, fp32. */
+typedef struct vt_embed_loss_args {
+    const float *a, *p, *n;            /* [B][D] flattened latents: anchor / positive / negative (n null for kind 1);
+                                          kind 1: the two embeddings are a and p */
+    const float *labels_a, *labels_p;  /* [B][T] multi-hot labels: optional for kind 0, required for kind 1 */
+    int B;
+    int64_t D;
+    int T;
+    int kind;        /* 0: ImprovedTripletLoss (improved_losses.py:74-109), 1: ContrastiveLoss (:6-37) */
+    int similarity;  /* 0: cosine, 1: euclidean */
+    float margin;
+    float* loss;     /* [1]: mean over the batch */
+    float *grad_a, *grad_p, *grad_n;   /* d loss / d inputs [B][D], each may be null */
+    void* stream;
+} vt_embed_loss_args;
+int vt_embed_loss(vt_ctx* ctx, const vt_embed_loss_args* args);
+/* F.mse_loss(x, y) (mean) and d loss / d x */
+int vt_mse_loss(vt_ctx* ctx, const float* x, const float* y, int64_t n, float* loss, float* grad_x, void* stream);
+/* AdaptiveLossWeights (improved_losses.py:111-125): weights = softmax(log_w / temperature), total = sum w_i L_i;
+ * d total / d L_i = weights[i], grad_log_w[j] = d total / d log_w_j */
+int vt_adaptive_loss_weights(vt_ctx* ctx, const float* log_w, const float* losses, int n, float temperature,
+                             float* total, float* weights, float* grad_log_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

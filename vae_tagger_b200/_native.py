@@ -107,6 +107,15 @@ class ResizeArgs(C.Structure):
     ]
 
 
+class EmbedLossArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("p", C.c_void_p), ("n", C.c_void_p), ("labels_a", C.c_void_p), ("labels_p", C.c_void_p),
+        ("B", C.c_int), ("D", C.c_int64), ("T", C.c_int), ("kind", C.c_int), ("similarity", C.c_int),
+        ("margin", C.c_float), ("loss", C.c_void_p), ("grad_a", C.c_void_p), ("grad_p", C.c_void_p),
+        ("grad_n", C.c_void_p), ("stream", C.c_void_p),
+    ]
+
+
 class ResnetBlockPtrs(C.Structure):
     """vt_resnet_block_params (const float*) and, with one more leading field, vt_resnet_block_grads."""
     _fields_ = [(n, C.c_void_p) for n in ("norm1_w", "norm1_b", "conv1_w", "conv1_b", "norm2_w", "norm2_b", "conv2_w",
@@ -158,6 +167,9 @@ SYMBOLS = {
     "vt_op_gemm_nt": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, _P, _P]),
     "vt_op_group_norm": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_int, _P, _P]),
     "vt_op_softmax_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "vt_embed_loss": (C.c_int, [_P, C.POINTER(EmbedLossArgs)]),
+    "vt_mse_loss": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
+    "vt_adaptive_loss_weights": (C.c_int, [_P, _P, _P, C.c_int, C.c_float, _P, _P, _P, _P]),
     "vt_op_conv2d_backward": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 7 + [_P, _P, _P, _P]),
     "vt_op_group_norm_backward": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_int, _P, _P, _P, _P]),
     "vt_op_resnet_block_backward": (C.c_int, [_P, _P, C.POINTER(ResnetBlockPtrs), _P] + [C.c_int] * 6 +
@@ -687,6 +699,52 @@ class Context:
             _check(self.lib.vt_op_softmax_rows(self.h, _ptr(s), rows, cols, precision, _ptr(out), _stream(self.device)))
         return out
 
+
+    # ---- VAE fine-tuning losses (improved_losses.py): value + analytic gradients in one call
+    def embed_loss(self, kind, a, p, n=None, labels_a=None, labels_p=None, margin=1.0, similarity="cosine",
+                   want_grad=True):
+        """``kind`` 0: ImprovedTripletLoss(a, p, n, labels_a, labels_p); 1: ContrastiveLoss(a, p, labels_a, labels_p).
+        Returns ``(loss [1], (grad_a, grad_p, grad_n))`` with ``d loss / d input`` (``None`` when not wanted)."""
+        a = _f32c(a, self.device); p = _f32c(p, self.device)
+        n = None if n is None else _f32c(n, self.device)
+        la = None if labels_a is None else _f32c(labels_a, self.device)
+        lp = None if labels_p is None else _f32c(labels_p, self.device)
+        B, D = a.shape
+        args = EmbedLossArgs()
+        loss = torch.empty(1, device=self.device)
+        ga = torch.empty_like(a) if want_grad else None
+        gp = torch.empty_like(p) if want_grad else None
+        gn = torch.empty_like(n) if (want_grad and n is not None and kind == 0) else None
+        args.a, args.p, args.n = a.data_ptr(), p.data_ptr(), (n.data_ptr() if n is not None else None)
+        args.labels_a = la.data_ptr() if la is not None else None
+        args.labels_p = lp.data_ptr() if lp is not None else None
+        args.B, args.D, args.T = B, D, (la.shape[1] if la is not None else 0)
+        args.kind, args.similarity, args.margin = kind, (0 if similarity == "cosine" else 1), float(margin)
+        args.loss = loss.data_ptr()
+        args.grad_a = ga.data_ptr() if ga is not None else None
+        args.grad_p = gp.data_ptr() if gp is not None else None
+        args.grad_n = gn.data_ptr() if gn is not None else None
+        args.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_embed_loss(self.h, C.byref(args)))
+        return loss, (ga, gp, gn)
+
+    def mse_loss(self, x, y, want_grad=True):
+        x = _f32c(x, self.device); y = _f32c(y, self.device)
+        loss = torch.empty(1, device=self.device)
+        gx = torch.empty_like(x) if want_grad else None
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_mse_loss(self.h, _ptr(x), _ptr(y), x.numel(), _ptr(loss), _ptr(gx), _stream(self.device)))
+        return loss, gx
+
+    def adaptive_loss_weights(self, log_w, losses, temperature=1.0):
+        log_w = _f32c(log_w, self.device); losses = _f32c(losses, self.device)
+        total = torch.empty(1, device=self.device)
+        weights, glw = torch.empty_like(log_w), torch.empty_like(log_w)
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_adaptive_loss_weights(self.h, _ptr(log_w), _ptr(losses), log_w.numel(), float(temperature),
+                                                     _ptr(total), _ptr(weights), _ptr(glw), _stream(self.device)))
+        return total, weights, glw
 
     # ---- backward building blocks of the encoder (SURVEY.md 8f-4)
     def op_conv2d_backward(self, x, w, grad_out, precision=PREC_F16, want=(True, True, True)):

@@ -9,6 +9,7 @@
 #include "vt_head_train.h"
 #include "vt_internal.h"
 #include "vt_backward.h"
+#include "vt_losses.h"
 #include "vt_resize.h"
 #include "vt_ptx.cuh"
 
@@ -1904,6 +1905,24 @@ int vt_op_resnet_block_backward(vt_ctx* c, const float* x, const vt_resnet_block
     }
     VT_TRY(bwd_group_norm(e, X, dA, st_x, pr->norm1_w, pr->norm1_b, add, dX, g->norm1_w, g->norm1_b, N, HW, Cin, eps, 1, 0, gsc));
     return launch_nhwc_to_nchw(dX, gf, g->x, N, Cin, HW, e.s);
+}
+
+// ------------------------------------------------------------------------------------- fine-tuning losses (8f-4)
+int vt_embed_loss(vt_ctx* c, const vt_embed_loss_args* a) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr, "null arguments");
+    VT_TRY(c->optws.ensure(embed_loss_scratch_bytes(a->B, a->D)));
+    return launch_embed_loss(*a, c->optws.p, static_cast<cudaStream_t>(a->stream), c->prof);
+}
+int vt_mse_loss(vt_ctx* c, const float* x, const float* y, int64_t n, float* loss, float* grad_x, void* stream) {
+    VT_TRY(set_device(c));
+    VT_TRY(c->optws.ensure(148 * 8 * sizeof(float)));
+    return launch_mse_loss(x, y, n, loss, grad_x, c->optws.p, static_cast<cudaStream_t>(stream), c->prof);
+}
+int vt_adaptive_loss_weights(vt_ctx* c, const float* log_w, const float* losses, int n, float temperature, float* total,
+                             float* weights, float* grad_log_w, void* stream) {
+    VT_TRY(set_device(c));
+    return launch_adaptive_weights(log_w, losses, n, temperature, total, weights, grad_log_w, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
