@@ -359,6 +359,30 @@ int vt_mse_loss(vt_ctx* ctx, const float* x, const float* y, int64_t n, float* l
 int vt_adaptive_loss_weights(vt_ctx* ctx, const float* log_w, const float* losses, int n, float temperature,
                              float* total, float* weights, float* grad_log_w, void* stream);
 
+/* ---- encoder training (the reference back-propagates through vae.encode in train_full.py:201-256 and
+ * train_vae.py:124-186).  vt_encoder_train_forward = vt_encode on the caller's stream over the whole batch, keeping
+ * every activation the backward needs inside the context; vt_encoder_backward consumes them: given d loss / d mean and
+ * d loss / d logvar (NCHW fp32 [N][latent_channels][h][w], either may be null; logvar is the clamped value the forward
+ * returned -- mask saturated entries yourself) it writes (accumulate = 0) or adds (accumulate != 0) the gradient of
+ * EVERY encoder parameter into the fp32 device buffer bound to its name (diffusers key without the "encoder." prefix,
+ * e.g. "down_blocks.0.resnets.0.conv1.weight"; the buffer has the parameter's own shape).  Image sizes must be
+ * multiples of 8.  Results are bit-reproducible (no atomics). */
+#define VT_MAX_TAPES 8
+/* slot: which of the context's VT_MAX_TAPES tapes keeps this forward (the reference runs three forwards -- anchor,
+ * positive, negative -- before one backward, train_full.py:210-212); a slot is overwritten by its next forward */
+int vt_encoder_train_forward(vt_ctx* ctx, const vt_encode_args* args, int slot);
+int vt_encoder_grad_bind(vt_ctx* ctx, const char* name, float* grad);
+typedef struct vt_encoder_backward_args {
+    const float* grad_mean;
+    const float* grad_logvar;
+    int slot;
+    int accumulate;
+    void* stream;
+} vt_encoder_backward_args;
+int vt_encoder_backward(vt_ctx* ctx, const vt_encoder_backward_args* args);
+/* frees the activations a slot holds (they are otherwise kept for reuse by the next forward on that slot) */
+int vt_encoder_tape_release(vt_ctx* ctx, int slot);
+
 #ifdef __cplusplus
 }
 #endif

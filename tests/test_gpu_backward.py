@@ -94,3 +94,80 @@ def test_resnet_block_backward(ctx, prec, n, cin, cout, h, w):
         errs[k] = rel(grads[k], p.grad)
     assert set(grads) == {k for k, _ in blk.named_parameters()}
     assert max(errs.values()) < tol(prec), errs
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The whole encoder: training forward + backward (vt_encoder_train_forward / vt_encoder_backward) through the
+# reference-facing module (AutoencoderKL.encode in train() mode) against autograd on the oracle encoder.
+def _encoder_pair(seed=0):
+    from oracle.encoder import make_oracle_vae
+    from vae_tagger_b200 import diffusers_vae_loader as L
+    oracle = make_oracle_vae(seed=seed)
+    vae = L.load_diffusers_vae_from_config(L.get_diffusers_vae_config())
+    missing, unexpected = vae.load_state_dict(oracle.state_dict(), strict=False)
+    assert not missing and not unexpected
+    for m in (oracle, vae):
+        for q in m.parameters():
+            q.requires_grad_(True)
+    return oracle, vae.cuda()
+
+
+@pytest.mark.parametrize("prec,n,h,w", [("fp32", 2, 64, 64), ("bf16", 2, 64, 64), ("bf16", 1, 96, 160), ("fp32", 1, 32, 48)])
+def test_encoder_backward_matches_autograd(prec, n, h, w):
+    from oracle.encoder import structured_images, synthetic_images
+    oracle, vae = _encoder_pair()
+    x = torch.cat([synthetic_images(1, h, w), structured_images(n - 1, h, w)]) if n > 1 else structured_images(1, h, w)
+    g = torch.Generator().manual_seed(3)
+    gm = torch.randn(n, 16, h // 8, w // 8, generator=g)
+    gl = torch.randn(n, 16, h // 8, w // 8, generator=g) * 0.3
+    # oracle: autograd through the restated encoder
+    oracle.train()
+    for p in oracle.parameters():
+        p.grad = None
+    dist = oracle.encode(x).latent_dist
+    ((dist.mean * gm).sum() + (dist.logvar * gl).sum()).backward()
+    ref = {k: p.grad for k, p in oracle.encoder.named_parameters()}
+    # native
+    vae.train()
+    vae.precision = prec
+    post = vae.encode(x.cuda()).latent_dist
+    assert post.mean.requires_grad and post.logvar.requires_grad
+    assert rel(post.mean.detach(), dist.mean.detach()) < (1e-4 if prec == "fp32" else 1e-2)
+    ((post.mean * gm.cuda()).sum() + (post.logvar * gl.cuda()).sum()).backward()
+    got = {k: p.grad for k, p in vae.encoder.named_parameters()}
+    assert set(got) == set(ref) and len(ref) == 106
+    bar = FP32_TOL if prec == "fp32" else 3e-2
+    # d loss / d to_k.bias is analytically ZERO (q . b_k shifts every score of a query by the same amount and softmax
+    # ignores it): both sides hold round-off only -- compare against the scale of the sibling gradient instead
+    kb = "mid_block.attentions.0.to_k.bias"
+    scale = ref["mid_block.attentions.0.to_q.bias"].norm().item()
+    assert ref[kb].norm().item() < 1e-4 * scale and got[kb].cpu().norm().item() < (1e-4 if prec == "fp32" else 2e-2) * scale
+    errs = {k: rel(got[k], ref[k]) for k in ref if k != kb}
+    worst = max(errs, key=errs.get)
+    print(f"encoder backward {prec} {n}x{h}x{w}: worst {worst} {errs[worst]:.3e}, "
+          f"median {sorted(errs.values())[len(errs) // 2]:.3e}", file=__import__("sys").stderr)
+    assert errs[worst] < bar, {k: v for k, v in errs.items() if v >= bar}
+
+
+def test_three_forwards_then_one_backward():
+    """train_full.py:210-212 runs the VAE on anchor, positive and negative before ONE backward: every forward keeps its
+    own tape, gradients add up like autograd's, and an eval-mode / no-grad encode leaves no graph."""
+    from oracle.encoder import structured_images
+    oracle, vae = _encoder_pair()
+    vae.precision = "fp32"
+    xs = [structured_images(1, 32, 32, seed=s) for s in (1, 2, 3)]
+    oracle.train()
+    for p in oracle.parameters():
+        p.grad = None
+    sum(oracle.encode(x).latent_dist.mean.square().sum() for x in xs).backward()
+    vae.train()
+    sum(vae.encode(x.cuda()).latent_dist.mean.square().sum() for x in xs).backward()
+    for k, p in oracle.encoder.named_parameters():
+        if k == "mid_block.attentions.0.to_k.bias":   # analytically zero (see above)
+            continue
+        assert rel(dict(vae.encoder.named_parameters())[k].grad, p.grad) < FP32_TOL, k
+    vae.eval()
+    assert not vae.encode(xs[0].cuda()).latent_dist.mean.requires_grad
+    vae.train()
+    with torch.no_grad():
+        assert not vae.encode(xs[0].cuda()).latent_dist.mean.requires_grad

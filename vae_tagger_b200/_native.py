@@ -107,6 +107,14 @@ class ResizeArgs(C.Structure):
     ]
 
 
+class EncoderBackwardArgs(C.Structure):
+    _fields_ = [("grad_mean", C.c_void_p), ("grad_logvar", C.c_void_p), ("slot", C.c_int), ("accumulate", C.c_int),
+                ("stream", C.c_void_p)]
+
+
+MAX_TAPES = 8
+
+
 class EmbedLossArgs(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("p", C.c_void_p), ("n", C.c_void_p), ("labels_a", C.c_void_p), ("labels_p", C.c_void_p),
@@ -167,6 +175,10 @@ SYMBOLS = {
     "vt_op_gemm_nt": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, _P, _P]),
     "vt_op_group_norm": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_int, _P, _P]),
     "vt_op_softmax_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "vt_encoder_train_forward": (C.c_int, [_P, C.POINTER(EncodeArgs), C.c_int]),
+    "vt_encoder_grad_bind": (C.c_int, [_P, C.c_char_p, _P]),
+    "vt_encoder_backward": (C.c_int, [_P, C.POINTER(EncoderBackwardArgs)]),
+    "vt_encoder_tape_release": (C.c_int, [_P, C.c_int]),
     "vt_embed_loss": (C.c_int, [_P, C.POINTER(EmbedLossArgs)]),
     "vt_mse_loss": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     "vt_adaptive_loss_weights": (C.c_int, [_P, _P, _P, C.c_int, C.c_float, _P, _P, _P, _P]),
@@ -345,6 +357,52 @@ class Context:
         if want_moments:
             return lat, mean, logvar
         return lat
+
+    # ------------------------------------------------------------------ encoder training
+    def encode_train(self, images: torch.Tensor, precision=PREC_BF16, slot=0):
+        """Training forward: ``(mean, logvar)`` of the posterior, with every activation kept on tape ``slot`` for
+        ``encoder_backward``.  Image sizes must be multiples of 8."""
+        if images.dtype == torch.uint8:
+            fmt = IN_U8_NHWC
+            x = images.to(self.device).contiguous()
+            B, H, W = x.shape[0], x.shape[1], x.shape[2]
+        else:
+            fmt = IN_F32_NCHW
+            x = _f32c(images, self.device)
+            B, H, W = x.shape[0], x.shape[2], x.shape[3]
+        down = 1 << (self.num_blocks - 1)
+        mean = torch.empty(B, self.latent_channels, H // down, W // down, device=self.device, dtype=torch.float32)
+        logvar = torch.empty_like(mean)
+        a = EncodeArgs()
+        a.images = x.data_ptr(); a.in_fmt = fmt; a.batch = B; a.height = H; a.width = W
+        a.precision = precision; a.sample = 0; a.apply_scale_shift = 0
+        a.mean = mean.data_ptr(); a.logvar = logvar.data_ptr(); a.latent = None
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_encoder_train_forward(self.h, C.byref(a), int(slot)))
+        self._tape_inputs = getattr(self, "_tape_inputs", {})
+        self._tape_inputs[slot] = x      # the backward reads the image again (conv_in weight gradient)
+        return mean, logvar
+
+    def encoder_backward(self, grad_mean, grad_logvar, grads: Dict[str, torch.Tensor], slot=0, accumulate=False):
+        """Back-propagate through the forward kept on ``slot``.  ``grads``: fp32 device tensor per encoder parameter
+        name (diffusers key without the ``encoder.`` prefix), written -- or added to when ``accumulate``."""
+        gm = None if grad_mean is None else _f32c(grad_mean, self.device)
+        gl = None if grad_logvar is None else _f32c(grad_logvar, self.device)
+        for name, g in grads.items():
+            assert g.dtype == torch.float32 and g.is_contiguous() and g.device.index == self.device.index
+            _check(self.lib.vt_encoder_grad_bind(self.h, name.encode(), g.data_ptr()))
+        a = EncoderBackwardArgs()
+        a.grad_mean = gm.data_ptr() if gm is not None else None
+        a.grad_logvar = gl.data_ptr() if gl is not None else None
+        a.slot, a.accumulate = int(slot), int(bool(accumulate))
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_encoder_backward(self.h, C.byref(a)))
+
+    def release_tape(self, slot=0):
+        _check(self.lib.vt_encoder_tape_release(self.h, int(slot)))
+        getattr(self, "_tape_inputs", {}).pop(slot, None)
 
     # ------------------------------------------------------------------ VAE decoder
     def load_decoder(self, state_dict: Dict[str, torch.Tensor]):

@@ -153,6 +153,40 @@ class DiagonalGaussianDistribution:
         return 0.5 * torch.sum(self.mean.pow(2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
 
 
+class _EncodeTrainFn(torch.autograd.Function):
+    """``encoder(x) -> (mean, logvar)`` with the native training forward / backward (what autograd does
+    for the reference in train_full.py:201-256 / train_vae.py:124-186).  The activations stay inside the native context
+    on a tape slot until the backward has run; the backward returns one gradient per encoder parameter."""
+
+    @staticmethod
+    def forward(ctx, vae, x, *params):
+        nctx = vae._sync_native(x.device)
+        slot = vae._take_tape_slot()
+        mean, logvar = nctx.encode_train(x, precision=vae._precision(), slot=slot)
+        ctx.vae, ctx.nctx, ctx.slot = vae, nctx, slot
+        ctx.names = [n for n, _ in vae.encoder.named_parameters()]
+        ctx.save_for_backward(logvar)
+        ctx.mark_non_differentiable()
+        return mean, logvar
+
+    @staticmethod
+    def backward(ctx, g_mean, g_logvar):
+        (logvar,) = ctx.saved_tensors
+        if g_logvar is not None:
+            # the kernel returns logvar clamped to [-30, 20] (diffusers DiagonalGaussianDistribution): no gradient
+            # flows through a saturated entry
+            g_logvar = g_logvar * ((logvar > -30.0) & (logvar < 20.0))
+        params = dict(ctx.vae.encoder.named_parameters())
+        grads = {n: torch.empty_like(params[n], dtype=torch.float32) for n in ctx.names}
+        if g_mean is None and g_logvar is None:
+            for g in grads.values():
+                g.zero_()
+        else:
+            ctx.nctx.encoder_backward(g_mean, g_logvar, grads, slot=ctx.slot, accumulate=False)
+        ctx.vae._free_tape_slot(ctx.slot)
+        return (None, None) + tuple(grads[n].to(params[n].dtype) for n in ctx.names)
+
+
 class AutoencoderKLOutput(SimpleNamespace):
     pass
 
@@ -258,12 +292,32 @@ class AutoencoderKL(nn.Module):
         return x.device
 
     # ------------------------------------------------------------------ API
-    @torch.no_grad()
+    def _take_tape_slot(self) -> int:
+        used = self.__dict__.setdefault("_tape_slots", set())
+        for s in range(_native.MAX_TAPES):
+            if s not in used:
+                used.add(s)
+                return s
+        raise RuntimeError(f"more than {_native.MAX_TAPES} encoder forwards are waiting for their backward")
+
+    def _free_tape_slot(self, slot: int):
+        self.__dict__.setdefault("_tape_slots", set()).discard(slot)
+
     def encode(self, x: torch.Tensor, return_dict: bool = True):
-        """``vae.encode(x).latent_dist`` (diffusers_vae_loader.py:73, :79)."""
-        ctx = self._sync_native(self._device_of(x))
-        _, mean, logvar = ctx.encode(x, precision=self._precision(), sample=False, apply_scale_shift=False,
-                                     want_moments=True, micro_batch=self.micro_batch, single_lane=self.single_lane)
+        """``vae.encode(x).latent_dist`` (diffusers_vae_loader.py:73, :79).  In ``train()`` mode, with autograd enabled
+        and trainable encoder parameters, the posterior carries a graph: the native training forward keeps its activations and the
+        native backward produces every parameter gradient (the reference fine-tunes the VAE this way,
+        train_full.py:201-256)."""
+        self._device_of(x)
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder.parameters()):
+            params = [p for _, p in self.encoder.named_parameters()]
+            mean, logvar = _EncodeTrainFn.apply(self, x, *params)
+        else:
+            with torch.no_grad():
+                ctx = self._sync_native(x.device)
+                _, mean, logvar = ctx.encode(x, precision=self._precision(), sample=False, apply_scale_shift=False,
+                                             want_moments=True, micro_batch=self.micro_batch,
+                                             single_lane=self.single_lane)
         dist = DiagonalGaussianDistribution(mean, logvar)
         if not return_dict:
             return (dist,)

@@ -66,7 +66,23 @@ struct DevBuf {
     }
 };
 
+// carve buffers out of the single-op workspace: register (pointer, bytes) pairs, then bind them all at once
+struct Carver {
+    struct Item { void** p; size_t bytes; };
+    std::vector<Item> items;
+    template <typename T> void want(T** p, size_t bytes) { items.push_back({reinterpret_cast<void**>(p), (bytes + 1023) / 1024 * 1024}); }
+    int bind(DevBuf& ws) {
+        size_t total = 0;
+        for (auto& it : items) total += it.bytes;
+        VT_TRY(ws.ensure(total));
+        char* b = static_cast<char*>(ws.p);
+        for (auto& it : items) { *it.p = b; b += it.bytes; }
+        return 0;
+    }
+};
 }  // namespace
+
+struct EncTape;   // activations kept by the encoder's training forward (vt_train_encoder.cuh)
 
 struct vt_ctx {
     int device = 0;
@@ -102,6 +118,11 @@ struct vt_ctx {
         DevBuf hws;    // tag-head workspace when the head runs per micro-batch on this lane (vt_infer_host)
     } lanes[2];
     cudaEvent_t ev_start = nullptr;
+
+    // ---- encoder training: the tape of the last training forward, gradient buffers by parameter name
+    EncTape* tapes[VT_MAX_TAPES] = {};
+    std::map<std::string, float*> egrads;
+    DevBuf tbws, tlws, tg0;   // backward scratch: one helper call / one layer / the rotating gradient buffers
 
     // ---- VAE decoder; shares ecfg with the encoder
     bool dec_ready = false;
@@ -533,10 +554,10 @@ struct MidW {
     bool has_attn;
 };
 
-// UNetMidBlock2D (shared by the encoder and the decoder): resnet, single-head attention over all
-// tokens, resnet.  X / spare / st_x are the caller's ping-pong state.
-int run_mid_block(EncRun& R, const MidW& M, const AttnPlan& pl, char* ab, Act& X, void*& spare, double*& st_x, void* T,
-                  void* Hb, int n, int h, int w_, int fp32, size_t es) {
+// Single-head attention of the mid block over all tokens (diffusers Attention + AttnProcessor2_0):
+// out = to_out(softmax(q k^T / sqrt(C)) v) + x.  T receives the normalised tokens, ab the [q|k], V^T, (S, P,) O buffers.
+int run_attention(EncRun& R, const AttnW& A, const AttnPlan& pl, char* ab, Act X, const double* st_x, void* T, Act out,
+                  double* st_o, int n, int h, int w_, int fp32, size_t es) {
     vt_ctx* c = R.c;
     cudaStream_t s = R.s;
     const long long tokens = 1LL * h * w_;
@@ -544,18 +565,7 @@ int run_mid_block(EncRun& R, const MidW& M, const AttnPlan& pl, char* ab, Act& X
     const long long rows_per_chunk = pl.rows_per_chunk;
     const int ipc = pl.ipc, pv_splits = pl.pv_splits;
     const size_t qk_b = pl.qk_b, vt_b = pl.vt_b, s_b = pl.s_b, p_b = pl.p_b, o_b = pl.o_b;
-    auto advance = [&](Act out) { spare = X.p; X = out; };
-    const int lvl = 0;
-    // ---- mid block
     {
-        double* st_o = R.new_stats();
-        Act out{spare, R.raw_fmt()};
-        VT_TRY(R.resnet((*M.mid0), X, st_x, h, w_, lvl, T, Hb, out, st_o));
-        advance(out);
-        st_x = st_o;
-    }
-    if (M.has_attn) {
-        const AttnW& A = (*M.attn);
         const int C = A.C;
         char* QK = ab;
         char* Vt = QK + qk_b;
@@ -626,16 +636,43 @@ int run_mid_block(EncRun& R, const MidW& M, const AttnPlan& pl, char* ab, Act& X
             }
         }
         {   // out = O Wo^T + b_o + x
-            double* st_o = R.new_stats();
-            Act out{spare, R.raw_fmt()};
             GemmOp g;
             g.A = O; g.B = R.W(A.out); g.batch = n; g.M = static_cast<int>(tokens); g.N = C; g.K = C;
             g.a_batched = 1; g.b_batched = 0; g.bias = A.out.bias; g.residual = X.p; g.residual_fp32 = X.fmt == FMT_F32;
             g.out = out.p; g.out_fmt = out.fmt; g.ab_f16 = 1; g.stats = st_o;
             VT_TRY(R.gemm(g, tokens));
-            advance(out);
-            st_x = st_o;
         }
+    }
+    return 0;
+}
+
+// UNetMidBlock2D (shared by the encoder and the decoder): resnet, single-head attention over all
+// tokens, resnet.  X / spare / st_x are the caller's ping-pong state.
+int run_mid_block(EncRun& R, const MidW& M, const AttnPlan& pl, char* ab, Act& X, void*& spare, double*& st_x, void* T,
+                  void* Hb, int n, int h, int w_, int fp32, size_t es) {
+    vt_ctx* c = R.c;
+    cudaStream_t s = R.s;
+    const long long tokens = 1LL * h * w_;
+    const long long tp = (tokens + 63) / 64 * 64;   // row pitch of V^T / scores / probabilities (plan_attention)
+    const long long rows_per_chunk = pl.rows_per_chunk;
+    const int ipc = pl.ipc, pv_splits = pl.pv_splits;
+    const size_t qk_b = pl.qk_b, vt_b = pl.vt_b, s_b = pl.s_b, p_b = pl.p_b, o_b = pl.o_b;
+    auto advance = [&](Act out) { spare = X.p; X = out; };
+    const int lvl = 0;
+    // ---- mid block
+    {
+        double* st_o = R.new_stats();
+        Act out{spare, R.raw_fmt()};
+        VT_TRY(R.resnet((*M.mid0), X, st_x, h, w_, lvl, T, Hb, out, st_o));
+        advance(out);
+        st_x = st_o;
+    }
+    if (M.has_attn) {
+        double* st_o = R.new_stats();
+        Act out{spare, R.raw_fmt()};
+        VT_TRY(run_attention(R, *M.attn, pl, ab, X, st_x, T, out, st_o, n, h, w_, fp32, es));
+        advance(out);
+        st_x = st_o;
     }
     {
         double* st_o = R.new_stats();
@@ -752,6 +789,10 @@ int run_encoder_microbatch(vt_ctx* c, vt_ctx::Lane& L, const vt_encode_args* a, 
     VT_CHECK(R.stats_used <= max_slots, "GroupNorm statistics slots exhausted");
     return 0;
 }
+
+}  // namespace
+#include "vt_train_encoder.cuh"
+namespace {
 
 // ---------------------------------------------------------------------------------------------
 // The decoder schedule (diffusers Decoder.forward; reference call sites diffusers_vae_loader.py:72-76,
@@ -942,6 +983,9 @@ int vt_ctx_destroy(vt_ctx* c) {
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     c->hws.release(); c->e2e.release(); c->opws.release(); c->optws.release();
+    for (auto& t : c->tapes)
+        if (t) { t->release(); delete t; t = nullptr; }
+    c->tbws.release(); c->tlws.release(); c->tg0.release();
     resize_cache_destroy(c->resize);
     profiler_destroy(c->prof);
     delete c;
@@ -1726,20 +1770,6 @@ int vt_op_softmax_rows(vt_ctx* c, const float* sc, int64_t rows, int cols, int p
 // ------------------------------------------------------------------------------------- backward ops (8f-4)
 }  // extern "C"
 namespace {
-// carve buffers out of the single-op workspace: register (pointer, bytes) pairs, then bind them all at once
-struct Carver {
-    struct Item { void** p; size_t bytes; };
-    std::vector<Item> items;
-    template <typename T> void want(T** p, size_t bytes) { items.push_back({reinterpret_cast<void**>(p), align_up(bytes, 1024)}); }
-    int bind(DevBuf& ws) {
-        size_t total = 0;
-        for (auto& it : items) total += it.bytes;
-        VT_TRY(ws.ensure(total));
-        char* b = static_cast<char*>(ws.p);
-        for (auto& it : items) { *it.p = b; b += it.bytes; }
-        return 0;
-    }
-};
 BwdEnv bwd_env(vt_ctx* c, int precision, void* stream) {
     BwdEnv e;
     e.s = static_cast<cudaStream_t>(stream); e.prof = c->prof; e.fp32 = precision == VT_PREC_FP32;
@@ -1923,6 +1953,42 @@ int vt_adaptive_loss_weights(vt_ctx* c, const float* log_w, const float* losses,
                              float* weights, float* grad_log_w, void* stream) {
     VT_TRY(set_device(c));
     return launch_adaptive_weights(log_w, losses, n, temperature, total, weights, grad_log_w, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------- encoder training (8f-4)
+int vt_encoder_train_forward(vt_ctx* c, const vt_encode_args* a, int slot) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr, "null arguments");
+    VT_CHECK(slot >= 0 && slot < VT_MAX_TAPES, "tape slot out of range");
+    VT_CHECK(c->enc_ready, "encoder parameters not finalised (vt_encoder_finalize)");
+    VT_CHECK(a->images != nullptr, "null image pointer");
+    VT_CHECK(a->batch > 0 && a->height > 0 && a->width > 0, "batch and image size must be positive");
+    VT_CHECK(a->in_fmt == VT_IN_F32_NCHW || a->in_fmt == VT_IN_U8_NHWC, "unknown input format");
+    return run_encoder_train_forward(c, a, slot);
+}
+int vt_encoder_grad_bind(vt_ctx* c, const char* name, float* grad) {
+    VT_CHECK(c != nullptr && name != nullptr, "null arguments");
+    VT_CHECK(c->eparams.count(name) != 0, std::string("unknown encoder parameter ") + name);
+    if (grad) c->egrads[name] = grad;
+    else c->egrads.erase(name);
+    return 0;
+}
+int vt_encoder_tape_release(vt_ctx* c, int slot) {
+    VT_TRY(set_device(c));
+    VT_CHECK(slot >= 0 && slot < VT_MAX_TAPES, "tape slot out of range");
+    if (c->tapes[slot]) {
+        VT_CUDA(cudaDeviceSynchronize());
+        c->tapes[slot]->release();
+        delete c->tapes[slot];
+        c->tapes[slot] = nullptr;
+    }
+    return 0;
+}
+int vt_encoder_backward(vt_ctx* c, const vt_encoder_backward_args* a) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr, "null arguments");
+    VT_CHECK(a->grad_mean != nullptr || a->grad_logvar != nullptr, "no output gradient");
+    return run_encoder_backward(c, a);
 }
 
 }  // extern "C"

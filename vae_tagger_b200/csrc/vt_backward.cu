@@ -284,7 +284,9 @@ __global__ void __launch_bounds__(256) pack_plane_kernel(const void* __restrict_
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, int H, int W, int C, int Wp,
                                                          long long Kimg, long long G, long long rowlen, float eps,
-                                                         int silu, int copies) {
+                                                         int silu, int copies, int sstride, int spy, int spx, int Hs,
+                                                         int Ws) {
+    // plane pixel (y, x) <- source pixel (sstride*y + spy, sstride*x + spx) of the Hs x Ws source (zero outside)
     __shared__ bf16 tile[64][72];
     const int xt = blockIdx.x % ((W + 63) / 64), y = blockIdx.x / ((W + 63) / 64);
     const int c0 = blockIdx.y * 64, n = blockIdx.z;
@@ -294,15 +296,16 @@ __global__ void __launch_bounds__(256) pack_plane_kernel(const void* __restrict_
         float v[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] = 0.f;
-        if (x0 + px < W) {
-            const long long off = ((1LL * n * H + y) * W + x0 + px) * C + c0 + q * 16;
+        const int sy = sstride * y + spy, sx = sstride * (x0 + px) + spx;
+        if (x0 + px < W && sy < Hs && sx < Ws) {
+            const long long off = ((1LL * n * Hs + sy) * Ws + sx) * C + c0 + q * 16;
             load8<XF>(src, off, v);
             load8<XF>(src, off + 8, v + 8);
             if (stats) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     Gn8 k;
-                    gn8_load(k, stats, gamma, beta, n, c0 + q * 16 + h * 8, C, 1LL * H * W, eps);
+                    gn8_load(k, stats, gamma, beta, n, c0 + q * 16 + h * 8, C, 1LL * Hs * Ws, eps);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         float t = fmaf(k.ga[e] * k.rstd[e], v[h * 8 + e] - k.mean[e], k.be[e]);
@@ -362,14 +365,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
 // ---------------------------------------------------------------------------------------------------------
 // fp32 verification mode: weight gradient straight from the NHWC tensors on the FFMA pipe ("TN" GEMM, K = pixels).
 // grid (Cout/64, taps * Cin/64, splits); part[split][co][taps*Cin]
+// H x W: dimensions of dy (the conv output); the conv input a is (stride*H [+1]) x (stride*W [+1]) = Hi x Wi and the
+// tap (ky, kx) of output pixel (y, x) reads input pixel (stride*y + ky - pad, stride*x + kx - pad).
 __global__ void __launch_bounds__(256) f32_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ a,
                                                         float* __restrict__ part, int N, int H, int W, int Cout, int Cin,
-                                                        int ks) {
+                                                        int ks, int stride, int Hi, int Wi) {
     __shared__ float As[16][68], Bs[16][68];
     const int taps = ks * ks;
     const int cit = Cin / 64;
     const int tap = blockIdx.y / cit, ci0 = (blockIdx.y % cit) * 64, co0 = blockIdx.x * 64;
-    const int dyo = ks == 3 ? tap / 3 - 1 : 0, dxo = ks == 3 ? tap % 3 - 1 : 0;
+    const int pad = (ks == 3 && stride == 1) ? 1 : 0;
+    const int dyo = ks == 3 ? tap / 3 - pad : 0, dxo = ks == 3 ? tap % 3 - pad : 0;
     const long long P = 1LL * N * H * W;
     const long long chunk = (P + gridDim.z - 1) / gridDim.z;
     const long long p0 = blockIdx.z * chunk, p1 = min(P, p0 + chunk);
@@ -384,9 +390,10 @@ __global__ void __launch_bounds__(256) f32_wgrad_kernel(const float* __restrict_
             const int x = static_cast<int>(p % W);
             const long long r = p / W;
             const int y = static_cast<int>(r % H);
-            const int ys = y + dyo, xs = x + dxo;
-            if (ys >= 0 && ys < H && xs >= 0 && xs < W)
-                bv = *reinterpret_cast<const float4*>(a + (p + 1LL * dyo * W + dxo) * Cin + ci0 + lc);
+            const long long img = r / H;
+            const int ys = y * stride + dyo, xs = x * stride + dxo;
+            if (ys >= 0 && ys < Hi && xs >= 0 && xs < Wi)
+                bv = *reinterpret_cast<const float4*>(a + ((img * Hi + ys) * Wi + xs) * Cin + ci0 + lc);
         }
         *reinterpret_cast<float4*>(&As[lk][lc]) = av;
         *reinterpret_cast<float4*>(&Bs[lk][lc]) = bv;
@@ -520,15 +527,20 @@ WgradPlan bwd_wgrad_plan(const BwdEnv& e, int N, int H, int W, int Cout, int Cin
 
 int bwd_pack_plane(const BwdEnv& e, const WgradPlan& p, const void* src, int src_fmt, void* dst, const double* stats,
                    const float* gamma, const float* beta, int N, int H, int W, int C, float eps, int silu, int copies) {
+    return bwd_pack_plane_strided(e, p, src, src_fmt, dst, stats, gamma, beta, N, H, W, C, eps, silu, copies, 1, 0, 0, H, W);
+}
+int bwd_pack_plane_strided(const BwdEnv& e, const WgradPlan& p, const void* src, int src_fmt, void* dst, const double* stats,
+                           const float* gamma, const float* beta, int N, int H, int W, int C, float eps, int silu, int copies,
+                           int sstride, int spy, int spx, int Hs, int Ws) {
     VT_CHECK(!e.fp32 && C % 64 == 0, "operand planes exist in the 16-bit mode only; channels a multiple of 64");
     VT_CHECK(copies == 1 || copies == 3, "one plane, or the three horizontally shifted planes of a 3x3 conv input");
     VT_CUDA(cudaMemsetAsync(dst, 0, static_cast<size_t>(copies) * C * p.rowlen * 2, e.s));
     dim3 grid(((W + 63) / 64) * H, C / 64, N);
     profiler_begin(e.prof, KC_MISC, e.s, 0, 4.0 * N * H * W * C);
     if (src_fmt == FMT_F16)
-        pack_plane_kernel<FMT_F16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), stats, gamma, beta, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, eps, silu, copies);
+        pack_plane_kernel<FMT_F16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), stats, gamma, beta, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, eps, silu, copies, sstride, spy, spx, Hs, Ws);
     else
-        pack_plane_kernel<FMT_BF16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), stats, gamma, beta, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, eps, silu, copies);
+        pack_plane_kernel<FMT_BF16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), stats, gamma, beta, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, eps, silu, copies, sstride, spy, spx, Hs, Ws);
     profiler_end(e.prof, KC_MISC, e.s);
     VT_CUDA(cudaGetLastError());
     return 0;
@@ -540,7 +552,7 @@ int bwd_conv_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const vo
         VT_CHECK(Cout % 64 == 0 && Cin % 64 == 0, "fp32 weight gradient: channels must be multiples of 64");
         dim3 grid(Cout / 64, p.taps * (Cin / 64), p.splits);
         profiler_begin(e.prof, KC_FP32, e.s, 2.0 * N * H * W * Cout * Cin * p.taps, 0);
-        f32_wgrad_kernel<<<grid, 256, 0, e.s>>>(static_cast<const float*>(dy), static_cast<const float*>(a), part, N, H, W, Cout, Cin, ks);
+        f32_wgrad_kernel<<<grid, 256, 0, e.s>>>(static_cast<const float*>(dy), static_cast<const float*>(a), part, N, H, W, Cout, Cin, ks, 1, H, W);
         profiler_end(e.prof, KC_FP32, e.s);
     } else {
         // dy, a: operand planes (bwd_pack_plane).  One GEMM launch per tap: M = Cout, N = Cin, K = Ks per (image, range)
@@ -565,6 +577,300 @@ int bwd_conv_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const vo
     wgrad_reduce_kernel<<<grid_for(total), 256, 0, e.s>>>(part, dw, p.batches, Cout, Cin, p.taps, accumulate);
     VT_CUDA(cudaGetLastError());
     return 0;
+}
+
+
+// =========================================================================================================
+// Pieces of the whole-encoder backward (vt_train_encoder.cuh): stride-2 downsample convs, conv_in, attention.
+namespace {
+
+template <int F>
+__device__ __forceinline__ float ld1(const void* p, long long i) {
+    if constexpr (F == FMT_F32) return static_cast<const float*>(p)[i];
+    else if constexpr (F == FMT_F16) return __half2float(static_cast<const __half*>(p)[i]);
+    else return __bfloat162float(static_cast<const bf16*>(p)[i]);
+}
+template <int F>
+__device__ __forceinline__ void st1(void* p, long long i, float v) {
+    if constexpr (F == FMT_F32) static_cast<float*>(p)[i] = v;
+    else if constexpr (F == FMT_F16) static_cast<__half*>(p)[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    else static_cast<bf16*>(p)[i] = __float2bfloat16(v);
+}
+
+// out[b][c][r] = in[b][r][c] (r < rows, c < cols), 32x32 tiles; out columns rows..ld_out-1 are left untouched
+template <int FI, int FO>
+__global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__ in, void* __restrict__ out, int rows, int cols,
+                                                        long long ld_in, long long ld_out, long long in_bs, long long out_bs) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < rows && c < cols) ? ld1<FI>(in, b * in_bs + 1LL * r * ld_in + c) : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (c < cols && r < rows) st1<FO>(out, b * out_bs + 1LL * c * ld_out + r, tile[tx][i]);
+    }
+}
+
+// out[row] = sum_c a[row][c] * b[row][c]   (one warp per row)
+template <int FA, int FB>
+__global__ void __launch_bounds__(256) rowdot_kernel(const void* __restrict__ a, const void* __restrict__ b,
+                                                     float* __restrict__ out, long long rows, int cols) {
+    const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float t = 0.f;
+    for (int c = threadIdx.x & 31; c < cols; c += 32) t = fmaf(ld1<FA>(a, row * cols + c), ld1<FB>(b, row * cols + c), t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+    if ((threadIdx.x & 31) == 0) out[row] = t;
+}
+
+// dS[q][k] = P[q][k] * (dP[q][k] - D[q]) * scale for k < T, zero in the row padding
+template <int FP, int FO>
+__global__ void __launch_bounds__(256) attn_ds_kernel(const void* __restrict__ P, const float* __restrict__ dP,
+                                                      const float* __restrict__ D, void* __restrict__ out, long long rows,
+                                                      int T, long long tp, float scale) {
+    const long long total = rows * tp;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const long long q = i / tp;
+        const int k = static_cast<int>(i - q * tp);
+        st1<FO>(out, i, k < T ? ld1<FP>(P, i) * (dP[i] - D[q]) * scale : 0.f);
+    }
+}
+
+// ---- stride-2 conv (pad right / bottom): data-gradient weights in the sub-pixel form of launch_conv's up2 mode.
+// dX pixel (2y+py, 2x+px) = sum over the 2x2 source taps (ty, tx) of dY; row taps of parity 0: {y-1 <-> ky 2, y <-> ky 0},
+// parity 1: {y <-> ky 1, y+1 <-> none}; columns alike.  dst[par][ci][(ty*2+tx)*Cout + co]
+template <int OFMT>
+__global__ void pack_dgrad_s2_kernel(const float* __restrict__ w /*[Cout][Cin][3][3]*/, void* __restrict__ dst, int Cout,
+                                     int Cin) {
+    const long long total = 4LL * Cin * 4 * Cout;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int co = static_cast<int>(i % Cout);
+        long long r = i / Cout;
+        const int t = static_cast<int>(r % 4); r /= 4;
+        const int ci = static_cast<int>(r % Cin);
+        const int par = static_cast<int>(r / Cin);
+        const int py = par >> 1, px = par & 1, ty = t >> 1, tx = t & 1;
+        const int ky = py == 0 ? (ty == 0 ? 2 : 0) : (ty == 0 ? 1 : -1);
+        const int kx = px == 0 ? (tx == 0 ? 2 : 0) : (tx == 0 ? 1 : -1);
+        const float v = (ky >= 0 && kx >= 0) ? w[((1LL * co * Cin + ci) * 3 + ky) * 3 + kx] : 0.f;
+        st1<OFMT>(dst, i, v);
+    }
+}
+// fp32 verification mode: direct transposed conv.  dx[n][iy][ix][ci] = sum_{ky,kx,co} dy[n][(iy-ky)/2][(ix-kx)/2][co] w[co][ci][ky][kx]
+__global__ void __launch_bounds__(128) f32_dgrad_s2_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                           float* __restrict__ dx, int N, int Hi, int Wi, int Ho, int Wo,
+                                                           int Cout, int Cin) {
+    const long long pix = blockIdx.x;            // n*Hi*Wi + iy*Wi + ix
+    const int ix = static_cast<int>(pix % Wi);
+    const long long r = pix / Wi;
+    const int iy = static_cast<int>(r % Hi);
+    const long long n = r / Hi;
+    for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
+        float acc = 0.f;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ty = iy - ky;
+            if (ty < 0 || (ty & 1) || ty / 2 >= Ho) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int tx = ix - kx;
+                if (tx < 0 || (tx & 1) || tx / 2 >= Wo) continue;
+                const float* g = dy + ((n * Ho + ty / 2) * Wo + tx / 2) * Cout;
+                for (int co = 0; co < Cout; ++co) acc = fmaf(g[co], w[((1LL * co * Cin + ci) * 3 + ky) * 3 + kx], acc);
+            }
+        }
+        dx[pix * Cin + ci] = acc;
+    }
+}
+
+// ---- conv_in (3 -> Cout, 3x3 pad 1): weight gradient straight from the image.  One thread per output channel keeps the
+// 27 sums of its row; a block walks a range of pixels with the 27 patch values of each pixel broadcast from shared memory.
+template <int GF>
+__global__ void __launch_bounds__(128) convin_wgrad_kernel(const void* __restrict__ dy, const void* __restrict__ img, int in_u8,
+                                                           float* __restrict__ part, int N, int H, int W, int Cout) {
+    __shared__ float patch[32][28];
+    const long long P = 1LL * N * H * W;
+    const long long chunk = (P + gridDim.x - 1) / gridDim.x;
+    const long long p0 = blockIdx.x * chunk, p1 = min(P, p0 + chunk);
+    float acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+    for (long long pb = p0; pb < p1; pb += 32) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * 27; i += blockDim.x) {
+            const int j = i / 27, k = i - j * 27;
+            const long long p = pb + j;
+            float v = 0.f;
+            if (p < p1) {
+                const int x = static_cast<int>(p % W);
+                const long long r = p / W;
+                const int y = static_cast<int>(r % H);
+                const long long n = r / H;
+                const int tap = k / 3, c = k - tap * 3;
+                const int ys = y + tap / 3 - 1, xs = x + tap % 3 - 1;
+                if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
+                    if (in_u8) v = static_cast<const unsigned char*>(img)[((n * H + ys) * W + xs) * 3 + c] * (2.0f / 255.0f) - 1.0f;
+                    else v = static_cast<const float*>(img)[((n * 3 + c) * H + ys) * W + xs];
+                }
+            }
+            patch[j][k] = v;
+        }
+        __syncthreads();
+        for (int co = threadIdx.x; co < Cout; co += blockDim.x) {   // Cout == blockDim.x in practice
+            const int lim = static_cast<int>(min(32LL, p1 - pb));
+            for (int j = 0; j < lim; ++j) {
+                const float g = ld1<GF>(dy, (pb + j) * Cout + co);
+#pragma unroll
+                for (int k = 0; k < 27; ++k) acc[k] = fmaf(g, patch[j][k], acc[k]);
+            }
+        }
+    }
+    if (threadIdx.x < Cout)
+#pragma unroll
+        for (int k = 0; k < 27; ++k) part[(1LL * blockIdx.x * Cout + threadIdx.x) * 27 + k] = acc[k];
+}
+// part[chunk][co][tap*3 + c] -> dw[co][c][tap]
+__global__ void convin_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int chunks, int Cout,
+                                           int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cout * 27) return;
+    const int co = i / 27, k = i - co * 27, tap = k / 3, c = k - tap * 3;
+    double t = 0.0;
+    for (int b = 0; b < chunks; ++b) t += part[(1LL * b * Cout + co) * 27 + k];
+    float* o = dw + (co * 3 + c) * 9 + tap;
+    *o = (accumulate ? *o : 0.f) + static_cast<float>(t);
+}
+
+// channel padding: out[row][Cp] = (in[row][C] | 0), fp32 NHWC source -> gradient format
+template <int FO>
+__global__ void pad_channels_kernel(const float* __restrict__ in, void* __restrict__ out, long long rows, int C, int Cp) {
+    const long long total = rows * Cp;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const long long r = i / Cp;
+        const int c = static_cast<int>(i - r * Cp);
+        st1<FO>(out, i, c < C ? in[r * C + c] : 0.f);
+    }
+}
+
+}  // namespace
+
+int bwd_transpose(const BwdEnv& e, const void* in, int in_fmt, void* out, int out_fmt, int rows, int cols, long long ld_in,
+                  long long ld_out, int batch, long long in_bs, long long out_bs) {
+    dim3 grid((rows + 31) / 32, (cols + 31) / 32, batch);
+#define VT_TR(FI, FO) transpose_kernel<FI, FO><<<grid, 256, 0, e.s>>>(in, out, rows, cols, ld_in, ld_out, in_bs, out_bs)
+    if (in_fmt == FMT_F32 && out_fmt == FMT_F32) VT_TR(FMT_F32, FMT_F32);
+    else if (in_fmt == FMT_F16 && out_fmt == FMT_BF16) VT_TR(FMT_F16, FMT_BF16);
+    else if (in_fmt == FMT_BF16 && out_fmt == FMT_BF16) VT_TR(FMT_BF16, FMT_BF16);
+    else if (in_fmt == FMT_F16 && out_fmt == FMT_F16) VT_TR(FMT_F16, FMT_F16);
+    else { set_error("transpose: format pair not instantiated"); return -2; }
+#undef VT_TR
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bwd_rowdot(const BwdEnv& e, const void* a, int a_fmt, const void* b, int b_fmt, float* out, long long rows, int cols) {
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    if (a_fmt == FMT_F32 && b_fmt == FMT_F32) rowdot_kernel<FMT_F32, FMT_F32><<<grid, 256, 0, e.s>>>(a, b, out, rows, cols);
+    else if (a_fmt == FMT_BF16 && b_fmt == FMT_F16) rowdot_kernel<FMT_BF16, FMT_F16><<<grid, 256, 0, e.s>>>(a, b, out, rows, cols);
+    else { set_error("rowdot: format pair not instantiated"); return -2; }
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bwd_attn_ds(const BwdEnv& e, const void* P, int p_fmt, const float* dP, const float* D, void* out, long long rows, int T,
+                long long tp, float scale) {
+    const int grid = grid_for(rows * tp);
+    if (e.fp32) attn_ds_kernel<FMT_F32, FMT_F32><<<grid, 256, 0, e.s>>>(P, dP, D, out, rows, T, tp, scale);
+    else if (p_fmt == FMT_F16) attn_ds_kernel<FMT_F16, FMT_BF16><<<grid, 256, 0, e.s>>>(P, dP, D, out, rows, T, tp, scale);
+    else { set_error("attention dS: format not instantiated"); return -2; }
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bwd_pad_channels(const BwdEnv& e, const float* in, void* out, long long rows, int C, int Cp) {
+    if (e.fp32) pad_channels_kernel<FMT_F32><<<grid_for(rows * Cp), 256, 0, e.s>>>(in, out, rows, C, Cp);
+    else pad_channels_kernel<FMT_BF16><<<grid_for(rows * Cp), 256, 0, e.s>>>(in, out, rows, C, Cp);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- stride-2 downsample conv (Hi x Wi -> Ho x Wo = Hi/2 x Wi/2, even sizes)
+size_t bwd_dgrad_s2_weight_bytes(const BwdEnv& e, int Cout, int Cin) {
+    return e.fp32 ? 0 : al(static_cast<size_t>(4) * Cin * 4 * Cout * 2);
+}
+int bwd_conv_s2_dgrad(const BwdEnv& e, const void* dy, const float* w, void* wd_scratch, void* dx, int N, int Hi, int Wi,
+                      int Cout, int Cin) {
+    VT_CHECK(Hi % 2 == 0 && Wi % 2 == 0, "stride-2 conv backward needs even input sizes");
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    if (e.fp32) {
+        profiler_begin(e.prof, KC_FP32, e.s, 2.0 * N * Ho * Wo * 9.0 * Cout * Cin, 0);
+        f32_dgrad_s2_kernel<<<static_cast<unsigned>(1LL * N * Hi * Wi), 128, 0, e.s>>>(
+            static_cast<const float*>(dy), w, static_cast<float*>(dx), N, Hi, Wi, Ho, Wo, Cout, Cin);
+        profiler_end(e.prof, KC_FP32, e.s);
+        VT_CUDA(cudaGetLastError());
+        return 0;
+    }
+    pack_dgrad_s2_kernel<FMT_BF16><<<grid_for(16LL * Cin * Cout), 256, 0, e.s>>>(w, wd_scratch, Cout, Cin);
+    VT_CUDA(cudaGetLastError());
+    for (int par = 0; par < 4; ++par) {
+        ConvOp op;
+        op.in = dy; op.in_f16 = 0; op.raw_f16 = 0; op.N = N; op.Hin = Ho; op.Win = Wo; op.Cin = Cout; op.ksize = 3; op.stride = 1;
+        op.w = static_cast<const bf16*>(wd_scratch) + static_cast<size_t>(par) * Cin * 4 * Cout; op.Cout = Cin;
+        op.out = dx; op.out_fmt = FMT_BF16; op.up2 = 1; op.up_py = par >> 1; op.up_px = par & 1; op.kclass = KC_BWD;
+        VT_TRY(launch_conv(op, e.s, e.prof));
+    }
+    return 0;
+}
+// 16-bit mode: planes_x = the four parity planes of the conv input in the OUTPUT geometry, three shifted copies each
+// ([par][3][Cin][rowlen], bwd_pack_plane_strided), dy_plane = plane of the output gradient
+int bwd_conv_s2_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const void* x, float* part, float* dw, int N, int Hi,
+                      int Wi, int Cout, int Cin, int accumulate) {
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    if (e.fp32) {
+        dim3 grid(Cout / 64, 9 * (Cin / 64), p.splits);
+        profiler_begin(e.prof, KC_FP32, e.s, 2.0 * N * Ho * Wo * Cout * Cin * 9.0, 0);
+        f32_wgrad_kernel<<<grid, 256, 0, e.s>>>(static_cast<const float*>(dy), static_cast<const float*>(x), part, N, Ho, Wo, Cout,
+                                               Cin, 3, 2, Hi, Wi);
+        profiler_end(e.prof, KC_FP32, e.s);
+    } else {
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap % 3;
+            const int par = (ky & 1) * 2 + (kx & 1), dyo = ky >> 1, dxo = kx >> 1;
+            GemmOp g;
+            g.A = dy;
+            g.B = static_cast<const bf16*>(x) + (static_cast<long long>(par) * 3 + (dxo + 1)) * Cin * p.rowlen;
+            g.batch = p.batches; g.M = Cout; g.N = Cin; g.K = static_cast<int>(p.Ks);
+            g.lda = p.rowlen; g.ldb = p.rowlen; g.a_bstride = p.Ks; g.b_bstride = p.Ks;
+            g.a_kdim = p.rowlen; g.b_kdim = p.rowlen;
+            g.a_k0 = p.G; g.b_k0 = p.G + 1LL * dyo * p.Wp;
+            g.out = part + 1LL * tap * Cin; g.out_fmt = FMT_F32; g.ld_out = 9LL * Cin; g.out_bstride = 1LL * Cout * 9 * Cin;
+            g.ab_f16 = 0; g.kclass = KC_BWD;
+            VT_TRY(launch_gemm(g, e.s, e.prof));
+        }
+    }
+    wgrad_reduce_kernel<<<grid_for(9LL * Cout * Cin), 256, 0, e.s>>>(part, dw, p.batches, Cout, Cin, 9, accumulate);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bwd_convin_wgrad(const BwdEnv& e, const void* dy, const void* img, int in_u8, float* part, float* dw, int N, int H, int W,
+                     int Cout, int accumulate) {
+    VT_CHECK(Cout <= 128, "conv_in weight gradient: at most 128 output channels");
+    const int chunks = bwd_convin_chunks(N, H, W);
+    profiler_begin(e.prof, KC_MISC, e.s, 2.0 * N * H * W * 27.0 * Cout, 0);
+    if (e.fp32) convin_wgrad_kernel<FMT_F32><<<chunks, 128, 0, e.s>>>(dy, img, in_u8, part, N, H, W, Cout);
+    else convin_wgrad_kernel<FMT_BF16><<<chunks, 128, 0, e.s>>>(dy, img, in_u8, part, N, H, W, Cout);
+    convin_wgrad_reduce_kernel<<<(Cout * 27 + 127) / 128, 128, 0, e.s>>>(part, dw, chunks, Cout, accumulate);
+    profiler_end(e.prof, KC_MISC, e.s);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+int bwd_convin_chunks(int N, int H, int W) {
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((1LL * N * H * W + 255) / 256, 148 * 8)));
 }
 
 }  // namespace vt

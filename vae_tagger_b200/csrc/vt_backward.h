@@ -43,9 +43,30 @@ WgradPlan bwd_wgrad_plan(const BwdEnv& e, int N, int H, int W, int Cout, int Cin
 // coordinates must be 16-byte aligned in the innermost dimension, so a one-pixel tap cannot be a coordinate offset)
 int bwd_pack_plane(const BwdEnv& e, const WgradPlan& p, const void* src, int src_fmt, void* dst, const double* stats,
                    const float* gamma, const float* beta, int N, int H, int W, int C, float eps, int silu, int copies);
+int bwd_pack_plane_strided(const BwdEnv& e, const WgradPlan& p, const void* src, int src_fmt, void* dst, const double* stats,
+                           const float* gamma, const float* beta, int N, int H, int W, int C, float eps, int silu, int copies,
+                           int sstride, int spy, int spx, int Hs, int Ws);
 // dw[Cout][Cin][ks][ks] (+)= sum_p dy[p][co] a[p + tap][ci].  16-bit mode: dy / a are operand planes; fp32 mode:
 // the NHWC fp32 tensors themselves (a = the conv's actual input).
 int bwd_conv_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const void* a, float* part, float* dw, int N, int H,
                    int W, int Cout, int Cin, int ks, int accumulate);
+
+// ---- pieces of the whole-encoder backward
+int bwd_transpose(const BwdEnv& e, const void* in, int in_fmt, void* out, int out_fmt, int rows, int cols, long long ld_in,
+                  long long ld_out, int batch, long long in_bs, long long out_bs);
+int bwd_rowdot(const BwdEnv& e, const void* a, int a_fmt, const void* b, int b_fmt, float* out, long long rows, int cols);
+int bwd_attn_ds(const BwdEnv& e, const void* P, int p_fmt, const float* dP, const float* D, void* out, long long rows, int T,
+                long long tp, float scale);
+int bwd_pad_channels(const BwdEnv& e, const float* in, void* out, long long rows, int C, int Cp);
+// stride-2 downsample conv (diffusers Downsample2D: pad right / bottom, 3x3, stride 2), even input sizes
+size_t bwd_dgrad_s2_weight_bytes(const BwdEnv& e, int Cout, int Cin);
+int bwd_conv_s2_dgrad(const BwdEnv& e, const void* dy, const float* w /*OIHW fp32*/, void* wd_scratch, void* dx, int N, int Hi,
+                      int Wi, int Cout, int Cin);
+int bwd_conv_s2_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const void* x, float* part, float* dw, int N, int Hi,
+                      int Wi, int Cout, int Cin, int accumulate);
+// conv_in: dw[Cout][3][3][3] from the image itself (fp32 NCHW in [-1,1] or uint8 NHWC normalised to it)
+int bwd_convin_chunks(int N, int H, int W);
+int bwd_convin_wgrad(const BwdEnv& e, const void* dy, const void* img, int in_u8, float* part /*[chunks][Cout][27]*/, float* dw,
+                     int N, int H, int W, int Cout, int accumulate);
 
 }  // namespace vt
