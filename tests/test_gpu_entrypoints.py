@@ -351,3 +351,48 @@ def test_infer_full_sharded_under_torchrun(tmp_path, golden):
     assert sharded == single       # bf16 mode is batch-invariant: bit-identical probabilities, hence identical JSON
     sharded_lat = json.loads((tmp_path / "two" / "latent_vectors.json").read_text())
     assert list(sharded_lat.keys()) == list(single_lat.keys()) and sharded_lat == single_lat
+
+
+@pytest.mark.parametrize("extra", [["--use_focal_loss"], ["--use_full_loss", "--use_adaptive_weights", "--similarity_type", "euclidean"],
+                                   ["--mixed_precision", "no", "--gradient_accumulation_steps", "2"]])
+def test_train_full_cli_end_to_end(tmp_path, extra):
+    """train_full.py's command line (reference step train_full.py:201-256): three native encoder training
+    forwards per step, triplet + classification loss, native encoder backward, AdamW over the encoder AND the head.
+    Two epochs on a tiny dataset: losses finite and falling, the fine-tuned VAE is saved in the diffusers layout and
+    its encoder weights have moved."""
+    from PIL import Image
+    from safetensors.torch import load_file, save_file
+
+    from vae_tagger_b200 import train_full
+
+    oracle = make_oracle_vae(0)
+    save_file({k: v.contiguous() for k, v in oracle.state_dict().items()}, str(tmp_path / "vae.safetensors"))
+    (tmp_path / "vae.json").write_text(json.dumps(L.get_diffusers_vae_config()))
+    names = ["red", "green", "blue", "dark"]
+    (tmp_path / "tags.csv").write_text("name\n" + "\n".join(names) + "\n")
+    g = torch.Generator().manual_seed(3)
+    data = {}
+    for i in range(12):
+        c = i % 3
+        arr = torch.randint(0, 60, (72, 80, 3), generator=g, dtype=torch.uint8)
+        arr[..., c] += 150
+        path = tmp_path / f"im{i}.png"
+        Image.fromarray(arr.numpy()).save(path)
+        data[str(path)] = f"{names[c]}:1.0, dark:0.5" if i % 4 == 0 else names[c]
+    (tmp_path / "data.json").write_text(json.dumps(data))
+    out_dir = tmp_path / "out"
+    hist = train_full.main(["--vae_checkpoint", str(tmp_path / "vae.safetensors"), "--vae_config_path", str(tmp_path / "vae.json"),
+                            "--json_path", str(tmp_path / "data.json"), "--tags_csv_path", str(tmp_path / "tags.csv"),
+                            "--output_dir", str(out_dir), "--resolution", "64", "--train_batch_size", "2", "--num_epochs", "3",
+                            "--num_workers", "0", "--lr_warmup_steps", "1", "--learning_rate", "2e-4", "--logging_steps", "2",
+                            "--save_steps", "1"] + extra)
+    vals = torch.tensor(hist["train_loss"] + hist["val_loss"])
+    assert len(hist["train_loss"]) == 3 and torch.isfinite(vals).all()
+    assert json.loads((out_dir / "training_history.json").read_text()) == hist
+    tuned = load_file(str(out_dir / "vae" / "diffusion_pytorch_model.safetensors"))
+    ref = oracle.state_dict()
+    moved = [k for k in ref if k.startswith("encoder.") and not torch.equal(tuned[k], ref[k])]
+    assert len(moved) == 106, len(moved)       # every encoder tensor received a gradient and an AdamW update
+    assert (out_dir / "vae" / "config.json").exists() and (out_dir / "decoder" / "pytorch_model.bin").exists()
+    back = L.load_diffusers_vae_from_pretrained(str(out_dir / "vae"))
+    assert back is not None and torch.equal(back.state_dict()["encoder.conv_in.weight"], tuned["encoder.conv_in.weight"])

@@ -362,6 +362,21 @@ class AutoencoderKL(nn.Module):
         z = posterior.sample(generator=generator) if sample_posterior else posterior.mode()
         return self.decode(z, return_dict=return_dict)
 
+    def save_pretrained(self, path):
+        """``config.json`` + ``diffusion_pytorch_model.safetensors`` in the diffusers layout (what the reference's
+        training scripts call on the fine-tuned VAE, train_full.py:352); ``from_pretrained`` reads it back."""
+        import json
+
+        from safetensors.torch import save_file
+
+        os.makedirs(path, exist_ok=True)
+        cfg = {k: v for k, v in vars(self.config).items() if not k.startswith("_")}
+        cfg["_class_name"] = "AutoencoderKL"
+        with open(os.path.join(path, "config.json"), "w", encoding="utf-8") as f:
+            json.dump(cfg, f, indent=2)
+        save_file({k: v.detach().contiguous().cpu() for k, v in self.state_dict().items()},
+                  os.path.join(path, "diffusion_pytorch_model.safetensors"))
+
     @classmethod
     def from_pretrained(cls, path, subfolder=None, **kw):
         """Local directory with ``config.json`` + ``diffusion_pytorch_model.safetensors`` (no network)."""

@@ -400,12 +400,16 @@ class VAE(nn.Module):
 
 class TaggedImageDataset(torch.utils.data.Dataset):
     """``{image_path: "tag[:w], tag[:w], ..."}`` JSON + ``tags.csv`` (column ``name``) -> dicts with
-    ``pixel_values`` and multi-hot ``labels`` (the two keys ``train_decoder.py`` consumes).  The
-    triplet-mining outputs of the reference dataset serve ``train_full.py`` only and are not provided."""
+    ``pixel_values`` and multi-hot ``labels`` (the two keys ``train_decoder.py`` consumes).  With
+    ``triplets=True`` every item also carries ``anchor`` / ``positive`` / ``negative`` images and
+    ``positive_labels`` / ``negative_labels`` from the reference's online triplet mining (modules.py:600-685),
+    which ``train_full.py`` / ``train_vae.py`` consume."""
 
     def __init__(self, json_path, tags_csv_path, transform=None, use_bucketing=False, base_resolution=512,
-                 max_resolution=1024, bucket_step=64, raw_uint8=False):
+                 max_resolution=1024, bucket_step=64, raw_uint8=False, triplets=False):
         import json
+
+        self.triplets = triplets
 
         # raw_uint8 (addition of this implementation): ``pixel_values`` is the decoded image as a uint8 [h,w,3]
         # tensor plus its target (W, H) under ``target_size``; resize / crop / normalise then run on the GPU
@@ -467,9 +471,54 @@ class TaggedImageDataset(torch.utils.data.Dataset):
             return self.transform(img)
         return get_image_transform(512)(img) if self.use_bucketing else img
 
+    def _mine_triplet(self, idx, anchor_labels, max_candidates=100):
+        """Online triplet mining as the reference does it (modules.py:600-685): up to ``max_candidates`` random other
+        images split into positives (any shared tag) and negatives; a multi-tag anchor takes the positive with the
+        largest overlap 70 % of the time, otherwise a random one; without candidates the anchor stands in for the
+        positive and a random other image for the negative."""
+        import random
+
+        n = len(self.image_paths)
+        anchor = self.image_paths[idx]
+        k = min(max_candidates, max(0, n - 1))
+        picked = set()
+        while len(picked) < k:
+            j = random.randrange(0, n)
+            if j != idx:
+                picked.add(j)
+        pos, neg = [], []
+        for j in picked:
+            p = self.image_paths[j]
+            (pos if (self.image_labels[p] * anchor_labels).sum().item() > 0 else neg).append(p)
+        if pos:
+            if anchor_labels.sum().item() > 1 and len(pos) > 1 and random.random() < 0.7:
+                positive = max(pos, key=lambda p: (self.image_labels[p] * anchor_labels).sum().item())
+            else:
+                positive = random.choice(pos)
+        else:
+            positive = anchor
+        if neg:
+            negative = random.choice(neg)
+        elif n > 1:
+            j = idx
+            while j == idx:
+                j = random.randrange(0, n)
+            negative = self.image_paths[j]
+        else:
+            negative = anchor
+        return positive, negative
+
     def __getitem__(self, idx):
         path = self.image_paths[idx]
         if self.raw_uint8:
             img, bucket = self._load(path)
             return {"pixel_values": img, "target_size": bucket, "labels": self.image_labels[path]}
-        return {"pixel_values": self._load(path), "labels": self.image_labels[path]}
+        img = self._load(path)
+        item = {"pixel_values": img, "labels": self.image_labels[path]}
+        if self.triplets:
+            labels = self.image_labels[path]
+            pos, neg = self._mine_triplet(idx, labels)
+            item.update(anchor=img, positive=self._load(pos), negative=self._load(neg),
+                        positive_labels=self.image_labels.get(pos, labels),
+                        negative_labels=self.image_labels.get(neg, torch.zeros_like(labels)))
+        return item
