@@ -1871,7 +1871,7 @@ int vt_op_resnet_block_backward(vt_ctx* c, const float* x, const vt_resnet_block
     cv.want(&wd1, bwd_dgrad_weight_bytes(e, Cout, Cin, 3)); cv.want(&wd2, bwd_dgrad_weight_bytes(e, Cout, Cout, 3));
     cv.want(&wds, sc ? bwd_dgrad_weight_bytes(e, Cout, Cin, 1) : 0);
     cv.want(&pa, e.fp32 ? 0 : align_up(static_cast<size_t>(Cout) * plan.rowlen * 2, 256));
-    cv.want(&pb, e.fp32 ? 0 : align_up(static_cast<size_t>(3) * Cmax * plan.rowlen * 2, 256));
+    cv.want(&pb, e.fp32 ? 0 : align_up(static_cast<size_t>(3) * Cmax * plan.rowlen * 2, 256) + static_cast<size_t>(N) * Cmax * 8 + 256);
     cv.want(&part, plan.part_bytes);
     cv.want(&gsc, bwd_gn_scratch_bytes(N, HW, Cmax)); cv.want(&cs, bwd_colsum_scratch_bytes(Cout));
     cv.want(&st_x, static_cast<size_t>(N) * 64 * sizeof(double)); cv.want(&st_h, static_cast<size_t>(N) * 64 * sizeof(double));

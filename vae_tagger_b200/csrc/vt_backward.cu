@@ -75,14 +75,16 @@ __device__ __forceinline__ void gn8_load(Gn8& k, const double* stats, const floa
         k.be[e] = beta[c];
     }
 }
-// xhat and dt = dy * act'(t), t = gamma*xhat + beta
+// xhat and dt = dy * act'(t), t = gamma*xhat + beta.  FAST (16-bit mode): ex2 / rcp approximations -- their error is two
+// orders below the bf16 rounding of the gradient that is stored afterwards
+template <bool FAST>
 __device__ __forceinline__ void gn_dt(float x, float dy, float mean, float rstd, float ga, float be, int silu, float& xhat,
                                       float& dt) {
     xhat = (x - mean) * rstd;
     dt = dy;
     if (silu) {
         const float t = fmaf(ga, xhat, be);
-        const float sg = 1.0f / (1.0f + expf(-t));
+        const float sg = FAST ? __fdividef(1.0f, 1.0f + __expf(-t)) : 1.0f / (1.0f + expf(-t));
         dt = dy * sg * (1.0f + t * (1.0f - sg));
     }
 }
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 float xh, dt;
-                gn_dt(xv[e], gv[e], k.mean[e], k.rstd[e], k.ga[e], k.be[e], silu, xh, dt);
+                gn_dt<XF != FMT_F32>(xv[e], gv[e], k.mean[e], k.rstd[e], k.ga[e], k.be[e], silu, xh, dt);
                 a[e] += dt;
                 b[e] = fmaf(dt, xh, b[e]);
             }
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float xh, dt;
-            gn_dt(xv[e], gv[e], k.mean[e], k.rstd[e], k.ga[e], k.be[e], silu, xh, dt);
+            gn_dt<XF != FMT_F32>(xv[e], gv[e], k.mean[e], k.rstd[e], k.ga[e], k.be[e], silu, xh, dt);
             o[e] = k.rstd[e] * (k.ga[e] * dt - (s1[e] + xh * s2[e]));
             if (add) o[e] += av[e];
         }
@@ -276,72 +278,84 @@ __global__ void pack_dgrad_weight_kernel(const float* __restrict__ w /*[Cout][Ci
 // ---------------------------------------------------------------------------------------------------------
 // NHWC [N][H][W][C] (format XF) -> channel-major rows over the zero-padded pixel plane, bf16:
 //   dst[c][G + n*Kimg + (y+1)*Wp + LP + x],  optionally through GroupNorm(+SiLU) of the source (the operand a
-//   conv actually saw).  64 pixels x 64 channels per block through shared memory; 16-byte stores (LP = 8, Wp % 8 == 0).
+//   conv actually saw).  A block owns 64 consecutive positions of the ROW (guards, pad rows / columns and the K padding
+//   behind an image included: they are written as zeros, so the buffer needs no memset and may hold anything) x 64
+//   channels, staged through shared memory with one halo position on either side; every copy -- the plane itself and,
+//   for a 3x3 conv input, the planes shifted by one pixel left / right -- leaves as 16-byte stores.
 constexpr int WG_LP = 8;
+// per (image, channel) scale / shift of GroupNorm: t = x * sc + sh
+__global__ void gn_table_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float2* __restrict__ table, int N, int C, long long HW, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * C) return;
+    const int n = i / C, c = i - n * C, cpg = C / 32, g = c / cpg;
+    const double cnt = static_cast<double>(HW) * cpg;
+    const double mean = stats[(1LL * n * 32 + g) * 2] / cnt;
+    double var = stats[(1LL * n * 32 + g) * 2 + 1] / cnt - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    table[i] = make_float2(rstd * gamma[c], beta[c] - static_cast<float>(mean) * rstd * gamma[c]);
+}
 template <int XF>
 __global__ void __launch_bounds__(256) pack_plane_kernel(const void* __restrict__ src, bf16* __restrict__ dst,
-                                                         const double* __restrict__ stats,
-                                                         const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, int H, int W, int C, int Wp,
-                                                         long long Kimg, long long G, long long rowlen, float eps,
+                                                         const float2* __restrict__ table, int N, int H, int W, int C, int Wp,
+                                                         long long Kimg, long long G, long long rowlen,
                                                          int silu, int copies, int sstride, int spy, int spx, int Hs,
                                                          int Ws) {
     // plane pixel (y, x) <- source pixel (sstride*y + spy, sstride*x + spx) of the Hs x Ws source (zero outside)
-    __shared__ bf16 tile[64][72];
-    const int xt = blockIdx.x % ((W + 63) / 64), y = blockIdx.x / ((W + 63) / 64);
-    const int c0 = blockIdx.y * 64, n = blockIdx.z;
-    const int x0 = xt * 64;
-    {
-        const int px = threadIdx.x >> 2, q = threadIdx.x & 3;   // pixel, 16-channel quarter
+    __shared__ __align__(16) bf16 tile[64][80];    // [channel][1 halo + 64 positions + 1 halo (+ pad)]
+    const long long pos0 = 64LL * blockIdx.x;      // first row position of this block
+    const int c0 = blockIdx.y * 64;
+    // ---- load: thread = (position, 16-channel quarter); positions pos0-1 .. pos0+64 (66 of them)
+    for (int i = threadIdx.x; i < 66 * 4; i += 256) {
+        const int pi = i >> 2, q = i & 3;
+        const long long qpos = pos0 - 1 + pi - G;          // position relative to the first image's plane
         float v[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] = 0.f;
-        const int sy = sstride * y + spy, sx = sstride * (x0 + px) + spx;
-        if (x0 + px < W && sy < Hs && sx < Ws) {
-            const long long off = ((1LL * n * Hs + sy) * Ws + sx) * C + c0 + q * 16;
-            load8<XF>(src, off, v);
-            load8<XF>(src, off + 8, v + 8);
-            if (stats) {
+        if (qpos >= 0 && qpos < 1LL * N * Kimg) {
+            const int n = static_cast<int>(qpos / Kimg);
+            const long long r = qpos - 1LL * n * Kimg;
+            const int yp = static_cast<int>(r / Wp), j = static_cast<int>(r - 1LL * yp * Wp);
+            const int y = yp - 1, x = j - WG_LP;
+            if (y >= 0 && y < H && x >= 0 && x < W) {
+                const int sy = sstride * y + spy, sx = sstride * x + spx;
+                if (sy < Hs && sx < Ws) {
+                    const long long off = ((1LL * n * Hs + sy) * Ws + sx) * C + c0 + q * 16;
+                    load8<XF>(src, off, v);
+                    load8<XF>(src, off + 8, v + 8);
+                    if (table) {
+                        const float2* tb = table + 1LL * n * C + c0 + q * 16;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    Gn8 k;
-                    gn8_load(k, stats, gamma, beta, n, c0 + q * 16 + h * 8, C, 1LL * Hs * Ws, eps);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float t = fmaf(k.ga[e] * k.rstd[e], v[h * 8 + e] - k.mean[e], k.be[e]);
-                        if (silu) t = t / (1.0f + expf(-t));
-                        v[h * 8 + e] = t;
+                        for (int e = 0; e < 16; ++e) {
+                            const float2 k = tb[e];
+                            float t = fmaf(v[e], k.x, k.y);
+                            if (silu) t = __fdividef(t, 1.0f + __expf(-t));
+                            v[e] = t;
+                        }
                     }
                 }
             }
         }
 #pragma unroll
-        for (int e = 0; e < 16; ++e) tile[q * 16 + e][px] = __float2bfloat16(v[e]);
+        for (int e = 0; e < 16; ++e) tile[q * 16 + e][pi] = __float2bfloat16(v[e]);
     }
     __syncthreads();
-    {
-        const int c = threadIdx.x >> 2, q = threadIdx.x & 3;    // channel, 16-pixel quarter
-        bf16* row = dst + 1LL * (c0 + c) * rowlen + G + 1LL * n * Kimg + 1LL * (y + 1) * Wp + WG_LP + x0 + q * 16;
-        if (copies == 3) row += 1LL * C * rowlen;   // copies: [dx = -1 | dx = 0 | dx = +1], copy j holds plane[q + j - 1] at q
+    // ---- store: thread = (channel, 16-position quarter); tile column of row position pos0 + k is k + 1
+    const int c = threadIdx.x >> 2, q = threadIdx.x & 3;
+    for (int cp = 0; cp < copies; ++cp) {
+        // copies: [dx = -1 | dx = 0 | dx = +1]; copy j holds plane[pos + j - 1] at pos (one copy: the plane itself)
+        const int shift = copies == 3 ? cp - 1 : 0;
+        bf16* row = dst + (1LL * cp * C + c0 + c) * rowlen + pos0 + q * 16;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int xs = x0 + q * 16 + h * 8;
-            if (xs + 8 <= W) {
-                *reinterpret_cast<uint4*>(row + h * 8) = *reinterpret_cast<const uint4*>(&tile[c][q * 16 + h * 8]);
-            } else {
-                for (int e = 0; e < 8 && xs + e < W; ++e) row[h * 8 + e] = tile[c][q * 16 + h * 8 + e];
-            }
-            if (copies == 3) {
-                // TMA needs 16-byte aligned start coordinates in the innermost dimension: a +-1 pixel tap cannot be a
-                // coordinate offset, so the two horizontally shifted planes are materialised (2-byte stores)
-                bf16* lo = row - 1LL * C * rowlen + 1;   // dx = -1: value of position q - 1 stored at q
-                bf16* hi = row + 1LL * C * rowlen - 1;   // dx = +1: value of position q + 1 stored at q
-                for (int e = 0; e < 8 && xs + e < W; ++e) {
-                    const bf16 v = tile[c][q * 16 + h * 8 + e];
-                    lo[h * 8 + e] = v;
-                    hi[h * 8 + e] = v;
-                }
-            }
+            const long long pos = pos0 + q * 16 + h * 8;
+            if (pos >= rowlen) continue;     // rowlen is a multiple of 8: whole vectors only
+            const bf16* t = &tile[c][q * 16 + h * 8 + 1 + shift];
+            __align__(16) bf16 v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = t[e];
+            *reinterpret_cast<uint4*>(row + h * 8) = *reinterpret_cast<const uint4*>(v);
         }
     }
 }
@@ -519,8 +533,9 @@ WgradPlan bwd_wgrad_plan(const BwdEnv& e, int N, int H, int W, int Cout, int Cin
     p.G = (p.Wp + 1 + 7) / 8 * 8;
     p.rowlen = (p.G + 1LL * N * p.Kimg + p.G + 64 + 7) / 8 * 8;
     p.batches = N * p.splits;
-    p.a_bytes = al(static_cast<size_t>(Cout) * p.rowlen * 2);
-    p.b_bytes = al(static_cast<size_t>(ks == 3 ? 3 : 1) * Cin * p.rowlen * 2);
+    // + room for the GroupNorm scale / shift table of a transformed operand (bwd_pack_plane)
+    p.a_bytes = al(static_cast<size_t>(Cout) * p.rowlen * 2) + al(static_cast<size_t>(N) * Cout * 8);
+    p.b_bytes = al(static_cast<size_t>(ks == 3 ? 3 : 1) * Cin * p.rowlen * 2) + al(static_cast<size_t>(N) * Cin * 8);
     p.part_bytes = al(static_cast<size_t>(p.batches) * Cout * p.taps * Cin * sizeof(float));
     return p;
 }
@@ -534,13 +549,18 @@ int bwd_pack_plane_strided(const BwdEnv& e, const WgradPlan& p, const void* src,
                            int sstride, int spy, int spx, int Hs, int Ws) {
     VT_CHECK(!e.fp32 && C % 64 == 0, "operand planes exist in the 16-bit mode only; channels a multiple of 64");
     VT_CHECK(copies == 1 || copies == 3, "one plane, or the three horizontally shifted planes of a 3x3 conv input");
-    VT_CUDA(cudaMemsetAsync(dst, 0, static_cast<size_t>(copies) * C * p.rowlen * 2, e.s));
-    dim3 grid(((W + 63) / 64) * H, C / 64, N);
-    profiler_begin(e.prof, KC_MISC, e.s, 0, 4.0 * N * H * W * C);
+    dim3 grid(static_cast<unsigned>((p.rowlen + 63) / 64), C / 64);
+    // the (image, channel) scale / shift table sits behind the planes (bwd_wgrad_plan leaves room for it)
+    float2* table = nullptr;
+    if (stats) {
+        table = reinterpret_cast<float2*>(static_cast<char*>(dst) + al(static_cast<size_t>(copies) * C * p.rowlen * 2));
+        gn_table_kernel<<<(N * C + 255) / 256, 256, 0, e.s>>>(stats, gamma, beta, table, N, C, 1LL * Hs * Ws, eps);
+    }
+    profiler_begin(e.prof, KC_MISC, e.s, 0, 2.0 * N * H * W * C + 2.0 * copies * C * p.rowlen);
     if (src_fmt == FMT_F16)
-        pack_plane_kernel<FMT_F16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), stats, gamma, beta, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, eps, silu, copies, sstride, spy, spx, Hs, Ws);
+        pack_plane_kernel<FMT_F16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), table, N, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, silu, copies, sstride, spy, spx, Hs, Ws);
     else
-        pack_plane_kernel<FMT_BF16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), stats, gamma, beta, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, eps, silu, copies, sstride, spy, spx, Hs, Ws);
+        pack_plane_kernel<FMT_BF16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), table, N, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, silu, copies, sstride, spy, spx, Hs, Ws);
     profiler_end(e.prof, KC_MISC, e.s);
     VT_CUDA(cudaGetLastError());
     return 0;
