@@ -79,12 +79,17 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
     constexpr int EPI_WARPS = Cfg::EPI_WARPS;
     constexpr int RF = Cfg::STAGE_ROW_FLOATS;
     constexpr bool OUT_F32 = (OUT == FMT_F32);
+    // 16-bit outputs go through a 16-bit staging tile ([channel][32 pixels] = 64-byte rows, bias already added): half
+    // the shared-memory wavefronts of the fp32 tile (this kernel is bound by the shared-memory data pipe).  The value
+    // is rounded to the output format once more after the residual add; fp32 outputs keep the fp32 tile.
+    constexpr bool STG16 = !OUT_F32;
     typedef typename std::conditional<OUT_F32, float, __nv_bfloat16>::type OutT;
     const int ew = warp - 2;
     const int q = warp & 3;                   // TMEM lane quadrant = channels 32q .. 32q+31 of the n-block
     const uint32_t stg = smem_u32(staging_all + ew * 32 * RF);
     const int et = threadIdx.x - 64;
     const int cgrp = lane & 3;                // phase B: 8-channel group inside the warp's 32 channels
+    const uint32_t hsel = (cgrp & 1) ? 0x1032u : 0x3210u;   // STG16: PRMT selector that swaps the 16-bit halves on odd groups
     const int swz_a = 8 * ((lane >> 3) & 3);  // phase A: column swizzle of this thread's staging row
     constexpr int NPASS = Cfg::PASSES_PER_SUB;             // 32-pixel passes per warp
     const int pc0 = (ew >> 2) * NPASS;                     // first pass of this warp (two warps per quadrant)
@@ -117,9 +122,14 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
         const uint32_t acc_phase = (it >> 1) & 1;
         const int tile_row = ptile;   // decode() of the NEXT tile (residual prefetch below) overwrites ptile
         float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        float bias_a = 0.f;   // STG16: bias of the channel this thread holds in phase A (TMEM lane)
         if (P.bias != nullptr && ch_ok) {
-            b0 = __ldg(reinterpret_cast<const float4*>(P.bias + ch0));
-            b1 = __ldg(reinterpret_cast<const float4*>(P.bias + ch0 + 4));
+            if constexpr (STG16) {
+                bias_a = __ldg(P.bias + nb * 128 + q * 32 + lane);
+            } else {
+                b0 = __ldg(reinterpret_cast<const float4*>(P.bias + ch0));
+                b1 = __ldg(reinterpret_cast<const float4*>(P.bias + ch0 + 4));
+            }
         }
         const long long img_off = static_cast<long long>(img) * P.out_bstride + ch0;
         OutT* out_img = static_cast<OutT*>(P.out) + img_off;
@@ -180,17 +190,52 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 }
-                const uint32_t dst = stg + lane * RF * 4;
+                if constexpr (STG16) {
+                    // row = channel (64 bytes), 16-byte chunk k at (k ^ sw): conflict-free for the 8-lane store phases
+                    // here and for the 16-lane 8-byte reads of phase B
+                    const uint32_t dst = stg + lane * 64;
+                    const int sw = ((lane >> 1) & 3) ^ (((lane >> 4) & 1) << 1);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    sts128(dst + (((4 * k) ^ swz_a) << 2), __uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
-                           __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            w[j] = pack16x2<OUT>(__uint_as_float(r[8 * k + 2 * j]) + bias_a,
+                                                 __uint_as_float(r[8 * k + 2 * j + 1]) + bias_a);
+                        sts128(dst + ((k ^ sw) << 4), __uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]),
+                               __uint_as_float(w[3]));
+                    }
+                } else {
+                    const uint32_t dst = stg + lane * RF * 4;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        sts128(dst + (((4 * k) ^ swz_a) << 2), __uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
+                               __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+                }
             }
             __syncwarp();
             // ---- phase B: 4 pixels x 8 channels per lane; one 16-byte staging read per channel (the column
             // swizzle of phase A makes the eight lanes of a quarter-warp hit eight different bank groups)
             float vv[4][8];
-            {
+            if constexpr (STG16) {
+                // 4 pixels x 8 channels per lane: one 8-byte read per channel; lanes with an odd channel group walk
+                // their rows in the order e ^ 1 so that a 16-lane phase covers all 32 banks
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int ee = e ^ (cgrp & 1);
+                    const int R = cgrp * 8 + ee;
+                    const int sw = ((R >> 1) & 3) ^ (((R >> 4) & 1) << 1);
+                    uint32_t w0, w1;
+                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
+                                 : "=r"(w0), "=r"(w1)
+                                 : "r"(stg + R * 64 + (((pq >> 1) ^ sw) << 4) + ((pq & 1) << 3))
+                                 : "memory");
+                    // register slot e of an odd-group lane therefore holds channel e ^ 1: the residual and the packed
+                    // output words get their 16-bit halves swapped to match (one PRMT each), nothing is re-ordered
+                    vv[0][e] = raw16_lo<OUT>(w0); vv[1][e] = raw16_hi<OUT>(w0);
+                    vv[2][e] = raw16_lo<OUT>(w1); vv[3][e] = raw16_hi<OUT>(w1);
+                }
+            } else {
                 const uint32_t src = stg + ((cgrp * 8) * RF + ((4 * pq) ^ (8 * cgrp))) * 4;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -203,10 +248,16 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = vv[i][e];
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                if constexpr (!STG16) {
+                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
                 if (RES == 1) {
-                    const uint4 u = rlo[i];
+                    uint4 u = rlo[i];
+                    if constexpr (STG16) {
+                        u.x = __byte_perm(u.x, 0u, hsel); u.y = __byte_perm(u.y, 0u, hsel);
+                        u.z = __byte_perm(u.z, 0u, hsel); u.w = __byte_perm(u.w, 0u, hsel);
+                    }
                     v[0] += raw16_lo<RAW>(u.x); v[1] += raw16_hi<RAW>(u.x); v[2] += raw16_lo<RAW>(u.y); v[3] += raw16_hi<RAW>(u.y);
                     v[4] += raw16_lo<RAW>(u.z); v[5] += raw16_hi<RAW>(u.z); v[6] += raw16_lo<RAW>(u.w); v[7] += raw16_hi<RAW>(u.w);
                 } else if (RES == 2) {
@@ -228,8 +279,12 @@ __device__ __forceinline__ void conv3t_epilogue(const IgemmParams& P, float* sta
                         reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
                     }
                 } else {
-                    const uint4 pk = make_uint4(pack16x2<OUT>(v[0], v[1]), pack16x2<OUT>(v[2], v[3]),
-                                                pack16x2<OUT>(v[4], v[5]), pack16x2<OUT>(v[6], v[7]));
+                    uint4 pk = make_uint4(pack16x2<OUT>(v[0], v[1]), pack16x2<OUT>(v[2], v[3]),
+                                          pack16x2<OUT>(v[4], v[5]), pack16x2<OUT>(v[6], v[7]));
+                    if constexpr (STG16) {
+                        pk.x = __byte_perm(pk.x, 0u, hsel); pk.y = __byte_perm(pk.y, 0u, hsel);
+                        pk.z = __byte_perm(pk.z, 0u, hsel); pk.w = __byte_perm(pk.w, 0u, hsel);
+                    }
                     if (ok) *reinterpret_cast<uint4*>(o) = pk;
                 }
             }
