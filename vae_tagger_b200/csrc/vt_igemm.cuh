@@ -134,6 +134,10 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
     constexpr int RF = Cfg::STAGE_ROW_FLOATS;
     constexpr int SLOTS = Cfg::COLS_PER_WARP / 4;  // 4-column statistic slots per warp
     constexpr bool OUT_F32 = (OUT == FMT_F32);
+    // 16-bit outputs go through a 16-bit staging tile (64-byte rows, 16-byte chunks XOR-swizzled by the row pair):
+    // half the shared-memory wavefronts of the fp32 tile; the accumulator is rounded to the output format before
+    // alpha / bias / residual are applied and once more afterwards.  fp32 outputs keep the fp32 tile.
+    constexpr bool STG16 = !OUT_F32;
     typedef typename std::conditional<OUT_F32, float, __nv_bfloat16>::type OutT;  // 2-byte outputs share the pointer type
 
     const int ew = warp - 2;            // 0 .. EPI_WARPS-1
@@ -278,11 +282,25 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
                             else mbar_arrive(&tempty_bar[acc]);
                         }
                     }
-                    const uint32_t dst = stg + lane * RF * 4;
+                    if constexpr (STG16) {
+                        const uint32_t dst = stg + lane * 64;
+                        const int sw = (lane >> 1) & 3;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        sts128(dst + i * 16, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                        for (int k = 0; k < 4; ++k) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                w[j] = pack16x2<OUT>(__uint_as_float(r[8 * k + 2 * j]), __uint_as_float(r[8 * k + 2 * j + 1]));
+                            sts128(dst + ((k ^ sw) << 4), __uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]),
+                                   __uint_as_float(w[3]));
+                        }
+                    } else {
+                        const uint32_t dst = stg + lane * RF * 4;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            sts128(dst + i * 16, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                    }
                 }
                 __syncwarp();
                 // ---- phase B: staging -> global
@@ -304,9 +322,18 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
                     float4 sv0[4], sv1[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const uint32_t sp = stg + ((8 * i + rlane) * RF + j8) * 4;
-                        sv0[i] = lds128(sp);
-                        sv1[i] = lds128(sp + 16);
+                        if constexpr (STG16) {
+                            const int R = 8 * i + rlane;
+                            const float4 t = lds128(stg + R * 64 + (((lane & 3) ^ ((R >> 1) & 3)) << 4));
+                            const uint32_t w0 = __float_as_uint(t.x), w1 = __float_as_uint(t.y), w2 = __float_as_uint(t.z),
+                                           w3 = __float_as_uint(t.w);
+                            sv0[i] = make_float4(raw16_lo<OUT>(w0), raw16_hi<OUT>(w0), raw16_lo<OUT>(w1), raw16_hi<OUT>(w1));
+                            sv1[i] = make_float4(raw16_lo<OUT>(w2), raw16_hi<OUT>(w2), raw16_lo<OUT>(w3), raw16_hi<OUT>(w3));
+                        } else {
+                            const uint32_t sp = stg + ((8 * i + rlane) * RF + j8) * 4;
+                            sv0[i] = lds128(sp);
+                            sv1[i] = lds128(sp + 16);
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
