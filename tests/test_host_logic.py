@@ -179,3 +179,44 @@ def test_resize_coefficients_and_crop_box_match_the_oracle():
         assert box == R.smart_crop_box(ow, oh, tw, th)
         l, t, r, b = box
         assert 0 <= l < r <= ow and 0 <= t < b <= oh
+
+
+def test_triplet_dataset_mining(tmp_path):
+    """``TaggedImageDataset(triplets=True)`` yields the keys train_full.py consumes (reference modules.py:628-648) and
+    its mining follows the reference's rules: a positive shares a tag with the anchor whenever one exists among the
+    other images, a negative shares none."""
+    import json as _json
+    import random
+
+    from PIL import Image
+
+    from vae_tagger_b200 import modules as M
+    names = ["a", "b", "c"]
+    (tmp_path / "tags.csv").write_text("name\n" + "\n".join(names) + "\n")
+    data = {}
+    for i in range(9):
+        p = tmp_path / f"im{i}.png"
+        Image.new("RGB", (40, 32), (i * 20, 0, 0)).save(p)
+        data[str(p)] = ("a, b" if i % 3 == 0 else names[i % 3]) + (":0.5" if i == 4 else "")
+    (tmp_path / "d.json").write_text(_json.dumps(data))
+    ds = M.TaggedImageDataset(str(tmp_path / "d.json"), str(tmp_path / "tags.csv"), M.get_image_transform(32), triplets=True)
+    random.seed(0)
+    for idx in range(len(ds)):
+        it = ds[idx]
+        assert set(it) == {"pixel_values", "labels", "anchor", "positive", "negative", "positive_labels", "negative_labels"}
+        assert it["anchor"].shape == it["positive"].shape == it["negative"].shape == (3, 32, 32)
+        assert (it["positive_labels"] * it["labels"]).sum() > 0          # every tag has other carriers here
+        assert (it["negative_labels"] * it["labels"]).sum() == 0
+    plain = M.TaggedImageDataset(str(tmp_path / "d.json"), str(tmp_path / "tags.csv"), M.get_image_transform(32))
+    assert set(plain[0]) == {"pixel_values", "labels"}
+    assert plain.image_labels[str(tmp_path / "im4.png")][1].item() == 0.5
+
+
+def test_save_pretrained_round_trip(tmp_path):
+    from vae_tagger_b200 import diffusers_vae_loader as L
+    vae = L.load_diffusers_vae_from_config(L.get_diffusers_vae_config())
+    vae.save_pretrained(str(tmp_path / "v"))
+    back = L.load_diffusers_vae_from_pretrained(str(tmp_path / "v"))
+    assert back is not None and back.config.scaling_factor == 0.3611
+    a, b = vae.state_dict(), back.state_dict()
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
