@@ -377,6 +377,8 @@ def run_ours(args):
     if args.aux == "on" or (args.aux == "auto" and world > 1):
         line["train_step"] = aux_train_step(world, rank, dev, wrap)
         line["bulk_stream"] = aux_bulk_stream(world, rank, dev, ctx, images_per_gpu=args.bulk_images)
+    if args.aux != "off":
+        line["encoder_train"] = aux_encoder_train(world, rank, dev)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -448,6 +450,47 @@ def aux_train_step(world, rank, dev, wrap, steps=6, warmup=3, batch=8, res=RES):
             "images_per_s": world * batch / step_ms * 1e3,
             "how": "CUDA events on the compute stream, max over ranks; exposed = event interval around the wait for the "
                    "async NCCL op (launched behind step k, waited after the encoder forward of step k+1)"}
+
+
+def aux_encoder_train(world, rank, dev, batch=2, res=512, steps=3, warmup=2):
+    """SURVEY 8f-4 beside the headline (not part of the timed region): one VAE fine-tuning pass of the encoder --
+    native training forward (activations kept on a tape) + native backward (all 106 parameter gradients), the work
+    autograd does for the reference in train_full.py:201-256.  Device time (CUDA events), max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from vae_tagger_b200 import diffusers_vae_loader as L
+
+    torch.manual_seed(3)
+    vae = L.load_diffusers_vae_from_config(L.get_diffusers_vae_config()).to(dev).train()
+    x = (torch.rand(batch, 3, res, res, generator=torch.Generator().manual_seed(11 + rank)) * 2 - 1).to(dev)
+    nctx = vae._sync_native(dev)
+    grads = {n: torch.empty_like(p, dtype=torch.float32) for n, p in vae.encoder.named_parameters()}
+    gm = torch.randn(batch, 16, res // 8, res // 8, device=dev)
+
+    def step():
+        nctx.encode_train(x, precision=vae._precision(), slot=0)
+        nctx.encoder_backward(gm, None, grads, slot=0)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    nctx.release_tape(0)
+    ms = t.item()
+    flop = 3.0 * flops_per_image(res) * batch      # forward + data gradients + weight gradients
+    return {"workload": f"encoder fine-tuning pass (training forward + backward), {batch} x {res}x{res} per GPU, 16-bit mode",
+            "n_gpus": world, "steps": steps, "step_ms": ms, "images_per_s": world * batch / ms * 1e3,
+            "algorithmic_tflops": flop / ms / 1e9, "parameter_gradients": len(grads),
+            "how": "CUDA events around vt_encoder_train_forward + vt_encoder_backward, max over ranks"}
 
 
 def aux_bulk_stream(world, rank, dev, ctx, images_per_gpu=8192, batch=BATCH, res=RES):
