@@ -376,6 +376,10 @@ def run_ours(args):
     # all-reduce time, configs[3] bulk stream; default at N > 1 so that the scaling record carries them
     if args.aux == "on" or (args.aux == "auto" and world > 1):
         line["train_step"] = aux_train_step(world, rank, dev, wrap)
+        # the training block loaded its own head (and, below, the fine-tuning block its own encoder) into the
+        # device's context: hand the context back to the benched modules before the stream runs through it
+        wrap.vae._sync_native(dev)
+        dec._native_ctx(dev)
         line["bulk_stream"] = aux_bulk_stream(world, rank, dev, ctx, images_per_gpu=args.bulk_images)
     if args.aux != "off":
         line["encoder_train"] = aux_encoder_train(world, rank, dev)

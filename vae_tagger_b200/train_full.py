@@ -73,7 +73,7 @@ def train_full(args):
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl")
     random.seed(args.seed + rank)
-    torch.manual_seed(args.seed + rank)
+    torch.manual_seed(args.seed)     # every rank builds the SAME initial models (DDP's start-up broadcast)
     main_proc = rank == 0
     os.makedirs(args.output_dir, exist_ok=True)
 
@@ -106,6 +106,10 @@ def train_full(args):
     if args.decoder_checkpoint and os.path.exists(args.decoder_checkpoint):
         decoder.load_state_dict(torch.load(args.decoder_checkpoint, map_location="cpu"))
     decoder = decoder.to(device)
+    if world > 1:   # identical start on every rank, whatever the checkpoints did
+        for t in list(vae_model.vae.encoder.parameters()) + list(decoder.parameters()) + list(decoder.buffers()):
+            dist.broadcast(t.data, src=0)
+    torch.manual_seed(args.seed + 1000 + rank)   # from here on: per-rank randomness (posterior samples, dropout)
 
     n_val = max(1, int(0.1 * len(dataset))) if len(dataset) > 1 else 0
     g = torch.Generator().manual_seed(args.seed)
