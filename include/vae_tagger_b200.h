@@ -383,6 +383,25 @@ int vt_encoder_backward(vt_ctx* ctx, const vt_encoder_backward_args* args);
 /* frees the activations a slot holds (they are otherwise kept for reuse by the next forward on that slot) */
 int vt_encoder_tape_release(vt_ctx* ctx, int slot);
 
+/* ---- decoder training (the reference back-propagates the reconstruction MSE through vae.decode: train_vae.py:124-186,
+ * CombinedLoss improved_losses.py:278).  Same protocol as the encoder's: vt_decoder_train_forward = vt_decode on the
+ * caller's stream over the whole batch with the activations kept on tape `slot`; vt_decoder_backward takes
+ * d loss / d image (NCHW fp32 [N][3][H][W]), writes / adds the gradient of every decoder parameter into the buffer
+ * bound to its name (diffusers key without the "decoder." prefix) and, when grad_latent is non-null, writes
+ * d loss / d latent (NCHW fp32 [N][latent_channels][h][w], w.r.t. the latent the caller passed: the un-scale of
+ * apply_scale_shift is included). */
+int vt_decoder_train_forward(vt_ctx* ctx, const vt_decode_args* args, int slot);
+int vt_decoder_grad_bind(vt_ctx* ctx, const char* name, float* grad);
+typedef struct vt_decoder_backward_args {
+    const float* grad_image;
+    float* grad_latent;
+    int slot;
+    int accumulate;
+    void* stream;
+} vt_decoder_backward_args;
+int vt_decoder_backward(vt_ctx* ctx, const vt_decoder_backward_args* args);
+int vt_decoder_tape_release(vt_ctx* ctx, int slot);
+
 #ifdef __cplusplus
 }
 #endif

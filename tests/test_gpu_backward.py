@@ -171,3 +171,49 @@ def test_three_forwards_then_one_backward():
     vae.train()
     with torch.no_grad():
         assert not vae.encode(xs[0].cuda()).latent_dist.mean.requires_grad
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The decoder half: training forward + backward (vt_decoder_train_forward / vt_decoder_backward) behind
+# AutoencoderKL.decode in train() mode, against autograd on the oracle decoder -- every parameter gradient and
+# d loss / d latent (the path the reconstruction MSE takes back into the encoder, train_vae.py:124-186).
+@pytest.mark.parametrize("prec,n,lh,lw,scale_shift", [("fp32", 2, 8, 8, False), ("bf16", 2, 8, 8, True), ("bf16", 1, 12, 20, False),
+                                                      ("fp32", 1, 4, 6, True)])
+def test_decoder_backward_matches_autograd(prec, n, lh, lw, scale_shift):
+    from oracle.decoder import make_oracle_decoder, oracle_wrapper_decode
+    from vae_tagger_b200 import diffusers_vae_loader as L
+    dec = make_oracle_decoder(seed=0)
+    for q in dec.parameters():
+        q.requires_grad_(True)
+    vae = L.load_diffusers_vae_from_config(L.get_diffusers_vae_config())
+    vae.enable_decoder()
+    missing, unexpected = vae.load_state_dict({"decoder." + k: v for k, v in dec.state_dict().items()}, strict=False)
+    assert not unexpected and all(k.startswith("encoder.") for k in missing)
+    vae = vae.cuda().train()
+    for q in vae.decoder.parameters():
+        q.requires_grad_(True)
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(n, 16, lh, lw, generator=g)
+    gi = torch.randn(n, 3, 8 * lh, 8 * lw, generator=g)
+    zr = z.clone().requires_grad_()
+    img_ref = oracle_wrapper_decode(dec, zr) if scale_shift else dec(zr)
+    (img_ref * gi).sum().backward()
+    ref = {k: p.grad for k, p in dec.named_parameters()}
+    vae.precision = prec
+    zc = z.cuda().requires_grad_()
+    img = vae.decode(zc, apply_scale_shift=scale_shift).sample
+    assert img.requires_grad
+    assert rel(img.detach(), img_ref.detach()) < (1e-4 if prec == "fp32" else 2e-2)
+    (img * gi.cuda()).sum().backward()
+    got = {k: p.grad for k, p in vae.decoder.named_parameters()}
+    assert set(got) == set(ref) and len(ref) == 138
+    bar = FP32_TOL if prec == "fp32" else 3e-2
+    kb = "mid_block.attentions.0.to_k.bias"      # analytically zero gradient (see the encoder test)
+    scale = ref["mid_block.attentions.0.to_q.bias"].norm().item()
+    assert got[kb].cpu().norm().item() < (1e-4 if prec == "fp32" else 2e-2) * scale
+    errs = {k: rel(got[k], ref[k]) for k in ref if k != kb}
+    errs["latent"] = rel(zc.grad, zr.grad)
+    worst = max(errs, key=errs.get)
+    print(f"decoder backward {prec} {n}x{lh}x{lw}: worst {worst} {errs[worst]:.3e}, latent {errs['latent']:.3e}, "
+          f"median {sorted(errs.values())[len(errs) // 2]:.3e}", file=__import__("sys").stderr)
+    assert errs[worst] < bar, {k: v for k, v in errs.items() if v >= bar}

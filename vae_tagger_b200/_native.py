@@ -112,6 +112,11 @@ class EncoderBackwardArgs(C.Structure):
                 ("stream", C.c_void_p)]
 
 
+class DecoderBackwardArgs(C.Structure):
+    _fields_ = [("grad_image", C.c_void_p), ("grad_latent", C.c_void_p), ("slot", C.c_int), ("accumulate", C.c_int),
+                ("stream", C.c_void_p)]
+
+
 MAX_TAPES = 8
 
 
@@ -179,6 +184,10 @@ SYMBOLS = {
     "vt_encoder_grad_bind": (C.c_int, [_P, C.c_char_p, _P]),
     "vt_encoder_backward": (C.c_int, [_P, C.POINTER(EncoderBackwardArgs)]),
     "vt_encoder_tape_release": (C.c_int, [_P, C.c_int]),
+    "vt_decoder_train_forward": (C.c_int, [_P, C.POINTER(DecodeArgs), C.c_int]),
+    "vt_decoder_grad_bind": (C.c_int, [_P, C.c_char_p, _P]),
+    "vt_decoder_backward": (C.c_int, [_P, C.POINTER(DecoderBackwardArgs)]),
+    "vt_decoder_tape_release": (C.c_int, [_P, C.c_int]),
     "vt_embed_loss": (C.c_int, [_P, C.POINTER(EmbedLossArgs)]),
     "vt_mse_loss": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     "vt_adaptive_loss_weights": (C.c_int, [_P, _P, _P, C.c_int, C.c_float, _P, _P, _P, _P]),
@@ -427,6 +436,41 @@ class Context:
         with torch.cuda.device(self.device):
             _check(self.lib.vt_decode(self.h, C.byref(a)))
         return img
+
+    def decode_train(self, latent: torch.Tensor, precision=PREC_BF16, apply_scale_shift=False, slot=0):
+        """Training forward of the decoder: the image, with every activation kept on decoder tape ``slot``."""
+        lat = _f32c(latent, self.device)
+        B, _, h, w = lat.shape
+        up = 1 << (self.num_blocks - 1)
+        img = torch.empty(B, 3, h * up, w * up, device=self.device, dtype=torch.float32)
+        a = DecodeArgs()
+        a.latent = lat.data_ptr(); a.batch = B; a.lat_h = h; a.lat_w = w; a.precision = precision
+        a.apply_scale_shift = int(bool(apply_scale_shift)); a.image = img.data_ptr()
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_decoder_train_forward(self.h, C.byref(a), int(slot)))
+        return img
+
+    def decoder_backward(self, grad_image, grads: Dict[str, torch.Tensor], want_latent_grad=True, slot=0, accumulate=False):
+        """Back-propagate ``d loss / d image`` through the decoder forward kept on ``slot``: fills ``grads`` (fp32 tensor
+        per decoder parameter name, diffusers key without ``decoder.``) and returns ``d loss / d latent`` (or None)."""
+        gi = _f32c(grad_image, self.device)
+        for name, g in grads.items():
+            assert g.dtype == torch.float32 and g.is_contiguous() and g.device.index == self.device.index
+            _check(self.lib.vt_decoder_grad_bind(self.h, name.encode(), g.data_ptr()))
+        B, _, H, W = gi.shape
+        down = 1 << (self.num_blocks - 1)
+        gz = torch.empty(B, self.latent_channels, H // down, W // down, device=self.device) if want_latent_grad else None
+        a = DecoderBackwardArgs()
+        a.grad_image = gi.data_ptr(); a.grad_latent = gz.data_ptr() if gz is not None else None
+        a.slot, a.accumulate = int(slot), int(bool(accumulate))
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.vt_decoder_backward(self.h, C.byref(a)))
+        return gz
+
+    def release_decoder_tape(self, slot=0):
+        _check(self.lib.vt_decoder_tape_release(self.h, int(slot)))
 
     # ------------------------------------------------------------------ head
     def configure_head(self, kind: int, latent_channels: int, num_classes: int, use_spatial_attention=True,

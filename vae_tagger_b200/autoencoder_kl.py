@@ -187,6 +187,30 @@ class _EncodeTrainFn(torch.autograd.Function):
         return (None, None) + tuple(grads[n].to(params[n].dtype) for n in ctx.names)
 
 
+class _DecodeTrainFn(torch.autograd.Function):
+    """``decoder(z) -> image`` with the native training forward / backward (the reference back-propagates its
+    reconstruction MSE through ``vae.decode``: train_vae.py:124-186, improved_losses.py:278).  The backward returns
+    ``d loss / d z`` and one gradient per decoder parameter."""
+
+    @staticmethod
+    def forward(ctx, vae, apply_scale_shift, z, *params):
+        nctx = vae._sync_native_decoder(z.device)
+        slot = vae._take_tape_slot("_dtape_slots")
+        img = nctx.decode_train(z, precision=vae._precision(), apply_scale_shift=apply_scale_shift, slot=slot)
+        ctx.vae, ctx.nctx, ctx.slot = vae, nctx, slot
+        ctx.names = [n for n, _ in vae.decoder.named_parameters()]
+        ctx.z_dtype = z.dtype
+        return img
+
+    @staticmethod
+    def backward(ctx, g_img):
+        params = dict(ctx.vae.decoder.named_parameters())
+        grads = {n: torch.empty_like(params[n], dtype=torch.float32) for n in ctx.names}
+        gz = ctx.nctx.decoder_backward(g_img, grads, want_latent_grad=ctx.needs_input_grad[2], slot=ctx.slot)
+        ctx.vae._free_tape_slot(ctx.slot, "_dtape_slots")
+        return (None, None, None if gz is None else gz.to(ctx.z_dtype)) + tuple(grads[n].to(params[n].dtype) for n in ctx.names)
+
+
 class AutoencoderKLOutput(SimpleNamespace):
     pass
 
@@ -292,16 +316,16 @@ class AutoencoderKL(nn.Module):
         return x.device
 
     # ------------------------------------------------------------------ API
-    def _take_tape_slot(self) -> int:
-        used = self.__dict__.setdefault("_tape_slots", set())
+    def _take_tape_slot(self, pool="_tape_slots") -> int:
+        used = self.__dict__.setdefault(pool, set())
         for s in range(_native.MAX_TAPES):
             if s not in used:
                 used.add(s)
                 return s
         raise RuntimeError(f"more than {_native.MAX_TAPES} encoder forwards are waiting for their backward")
 
-    def _free_tape_slot(self, slot: int):
-        self.__dict__.setdefault("_tape_slots", set()).discard(slot)
+    def _free_tape_slot(self, slot: int, pool="_tape_slots"):
+        self.__dict__.setdefault(pool, set()).discard(slot)
 
     def encode(self, x: torch.Tensor, return_dict: bool = True):
         """``vae.encode(x).latent_dist`` (diffusers_vae_loader.py:73, :79).  In ``train()`` mode, with autograd enabled
@@ -343,18 +367,26 @@ class AutoencoderKL(nn.Module):
             ctx._dec_owner = self
         return ctx
 
-    @torch.no_grad()
     def decode(self, z: torch.Tensor, return_dict: bool = True, apply_scale_shift: bool = False):
         """``vae.decode(z).sample`` (diffusers_vae_loader.py:75, :94); ``apply_scale_shift`` fuses the
-        ``(z - shift_factor) / scaling_factor`` of ``DiffusersVAEWrapper.decode`` (:88-93) into the first kernel."""
-        ctx = self._sync_native_decoder(self._device_of(z))
-        img = ctx.decode(z, precision=self._precision(), apply_scale_shift=apply_scale_shift,
-                         micro_batch=self.micro_batch)
+        ``(z - shift_factor) / scaling_factor`` of ``DiffusersVAEWrapper.decode`` (:88-93) into the first kernel.
+        In ``train()`` mode with autograd enabled the image carries a graph: gradients flow into the decoder
+        parameters and back into ``z`` (train_vae.py:124-186)."""
+        self._device_of(z)
+        self.enable_decoder()
+        if self.training and torch.is_grad_enabled() and (
+                z.requires_grad or any(p.requires_grad for p in self.decoder.parameters())):
+            params = [p for _, p in self.decoder.named_parameters()]
+            img = _DecodeTrainFn.apply(self, bool(apply_scale_shift), z, *params)
+        else:
+            with torch.no_grad():
+                ctx = self._sync_native_decoder(z.device)
+                img = ctx.decode(z, precision=self._precision(), apply_scale_shift=apply_scale_shift,
+                                 micro_batch=self.micro_batch)
         if not return_dict:
             return (img,)
         return DecoderOutput(sample=img)
 
-    @torch.no_grad()
     def forward(self, sample: torch.Tensor, sample_posterior: bool = False, return_dict: bool = True,
                 generator: Optional[torch.Generator] = None):
         """diffusers ``AutoencoderKL.forward``: decode(posterior.sample() or .mode())."""

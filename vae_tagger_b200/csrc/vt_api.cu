@@ -121,7 +121,8 @@ struct vt_ctx {
 
     // ---- encoder training: the tape of the last training forward, gradient buffers by parameter name
     EncTape* tapes[VT_MAX_TAPES] = {};
-    std::map<std::string, float*> egrads;
+    EncTape* dtapes[VT_MAX_TAPES] = {};    // decoder training forwards
+    std::map<std::string, float*> egrads, dgrads;
     DevBuf tbws, tlws, tg0;   // backward scratch: one helper call / one layer / the rotating gradient buffers
 
     // ---- VAE decoder; shares ecfg with the encoder
@@ -984,6 +985,8 @@ int vt_ctx_destroy(vt_ctx* c) {
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     c->hws.release(); c->e2e.release(); c->opws.release(); c->optws.release();
     for (auto& t : c->tapes)
+        if (t) { t->release(); delete t; t = nullptr; }
+    for (auto& t : c->dtapes)
         if (t) { t->release(); delete t; t = nullptr; }
     c->tbws.release(); c->tlws.release(); c->tg0.release();
     resize_cache_destroy(c->resize);
@@ -1989,6 +1992,39 @@ int vt_encoder_backward(vt_ctx* c, const vt_encoder_backward_args* a) {
     VT_CHECK(a != nullptr, "null arguments");
     VT_CHECK(a->grad_mean != nullptr || a->grad_logvar != nullptr, "no output gradient");
     return run_encoder_backward(c, a);
+}
+
+int vt_decoder_train_forward(vt_ctx* c, const vt_decode_args* a, int slot) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr, "null arguments");
+    VT_CHECK(slot >= 0 && slot < VT_MAX_TAPES, "tape slot out of range");
+    VT_CHECK(c->dec_ready, "decoder parameters not finalised (vt_decoder_finalize)");
+    VT_CHECK(a->latent != nullptr && a->image != nullptr, "null latent / image pointer");
+    VT_CHECK(a->batch > 0 && a->lat_h > 0 && a->lat_w > 0, "batch and latent size must be positive");
+    return run_decoder_train_forward(c, a, slot);
+}
+int vt_decoder_grad_bind(vt_ctx* c, const char* name, float* grad) {
+    VT_CHECK(c != nullptr && name != nullptr, "null arguments");
+    VT_CHECK(c->dparams.count(name) != 0, std::string("unknown decoder parameter ") + name);
+    if (grad) c->dgrads[name] = grad;
+    else c->dgrads.erase(name);
+    return 0;
+}
+int vt_decoder_backward(vt_ctx* c, const vt_decoder_backward_args* a) {
+    VT_TRY(set_device(c));
+    VT_CHECK(a != nullptr && a->grad_image != nullptr, "null arguments");
+    return run_decoder_backward(c, a);
+}
+int vt_decoder_tape_release(vt_ctx* c, int slot) {
+    VT_TRY(set_device(c));
+    VT_CHECK(slot >= 0 && slot < VT_MAX_TAPES, "tape slot out of range");
+    if (c->dtapes[slot]) {
+        VT_CUDA(cudaDeviceSynchronize());
+        c->dtapes[slot]->release();
+        delete c->dtapes[slot];
+        c->dtapes[slot] = nullptr;
+    }
+    return 0;
 }
 
 }  // extern "C"
