@@ -13,11 +13,10 @@ What runs where:
   * ``accelerate`` is replaced by plain ``torch.distributed``: one process per GPU, the gradients of both models are
     flattened and all-reduced once per optimizer step.
 
-Deviation (stated, not hidden): the VAE *decoder* has no native backward.  With ``--use_simplified_loss`` (the
-reference's default and recommendation) nothing depends on it -- the reconstruction is not even computed.  With the
-full ``CombinedLoss`` the reconstruction comes from the native decoder forward and enters the loss VALUE, but no
-gradient flows through it (neither into the VAE decoder nor, via the reconstruction, into the encoder); the script
-says so at start-up.
+With ``--use_simplified_loss`` (the reference's default and recommendation) the loss never touches the reconstruction:
+it is not computed and only the encoder and the head train.  With the full ``CombinedLoss`` (``--use_full_loss``) the
+reconstruction comes from the native decoder TRAINING forward and its MSE is back-propagated natively through the
+decoder (parameter gradients) and on into the anchor's posterior sample, i.e. into the encoder.
 
 Launch:  [torchrun --nproc-per-node N] python -m vae_tagger_b200.train_full --json_path ... (the reference's flags).
 """
@@ -59,8 +58,7 @@ def encode_triplet(vae_model, anchor, positive, negative, want_reconstruction):
     zs = [p.sample() for p in posts]
     recon = None
     if want_reconstruction:
-        with torch.no_grad():   # no native decoder backward: a constant of the step (module docstring)
-            recon = vae_model.vae.decode(zs[0].detach()).sample
+        recon = vae_model.vae.decode(zs[0]).sample
     return recon, posts, zs
 
 
@@ -86,7 +84,10 @@ def train_full(args):
         vae_model = DiffusersVAEWrapper(load_diffusers_vae_from_config(cfg, args.vae_checkpoint))
     vae_model = vae_model.to(device)
     vae_model.vae.precision = "fp32" if args.mixed_precision == "no" else "bf16"
-    for p in vae_model.vae.encoder.parameters():
+    simplified = args.use_simplified_loss and not args.use_full_loss
+    if not simplified:
+        vae_model.vae.enable_decoder()    # the reconstruction term trains the VAE decoder too
+    for p in vae_model.vae.parameters():
         p.requires_grad_(True)
 
     tf = get_image_transform(args.resolution)
@@ -107,7 +108,7 @@ def train_full(args):
         decoder.load_state_dict(torch.load(args.decoder_checkpoint, map_location="cpu"))
     decoder = decoder.to(device)
     if world > 1:   # identical start on every rank, whatever the checkpoints did
-        for t in list(vae_model.vae.encoder.parameters()) + list(decoder.parameters()) + list(decoder.buffers()):
+        for t in list(vae_model.vae.parameters()) + list(decoder.parameters()) + list(decoder.buffers()):
             dist.broadcast(t.data, src=0)
     torch.manual_seed(args.seed + 1000 + rank)   # from here on: per-rank randomness (posterior samples, dropout)
 
@@ -123,7 +124,6 @@ def train_full(args):
     class_distribution = compute_class_distribution(dataset) if args.use_class_balanced else None
 
     # ---- loss (train_full.py:141-177)
-    simplified = args.use_simplified_loss and not args.use_full_loss
     if simplified:
         loss_fn = SimplifiedCombinedLoss(classification_weight=args.bce_weight, triplet_weight=args.triplet_weight,
                                          use_focal_loss=args.use_focal_loss, use_class_balanced=args.use_class_balanced,
@@ -136,10 +136,7 @@ def train_full(args):
                                use_adaptive_weights=args.use_adaptive_weights, focal_alpha=args.focal_alpha,
                                focal_gamma=args.focal_gamma, triplet_margin=args.triplet_margin,
                                similarity_type=args.similarity_type).to(device)
-        if main_proc:
-            print("note: the reconstruction term enters the loss value only -- the VAE decoder has no native backward "
-                  "(use --use_simplified_loss, the reference's default, to train without it)")
-    params = list(vae_model.vae.encoder.parameters()) + list(decoder.parameters())
+    params = list(vae_model.vae.parameters()) + list(decoder.parameters())
     if not simplified and args.use_adaptive_weights:
         params += list(loss_fn.adaptive_weights.parameters())
     optimizer = torch.optim.AdamW(params, lr=args.learning_rate, weight_decay=args.weight_decay)
