@@ -141,38 +141,52 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
     }
 }
 
-// pass 1b (one block of C threads): chunks added in index order in fp64; per (image, group) the two sums the
-// apply pass needs, S1 = sum_c gamma_c A_c, S2 = sum_c gamma_c B_c; d gamma / d beta summed over the images in
-// index order.
-__global__ void gn_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
-                                       float* __restrict__ gsum /*[N][32][2]*/, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int N, int chunks, int C, int accumulate) {
-    __shared__ double sa[1024], sb[1024];
-    const int c = threadIdx.x;
-    const int cpg = C / 32;
+// pass 1b: one warp per channel -- lanes stride over the chunks of an image, then a fixed shuffle tree (fp64): the order
+// of the additions depends on (chunks) only.  Writes the per-(image, channel) sums times gamma for the group stage
+// and d gamma / d beta summed over the images in index order.
+__global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+                                                              float* __restrict__ ab /*[N][C][2]*/, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, int N, int chunks, int C, int accumulate) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= C) return;
     double dg = 0.0, db = 0.0;
+    const float ga = gamma[c];
     for (int n = 0; n < N; ++n) {
         double A = 0.0, B = 0.0;
-        for (int k = 0; k < chunks; ++k) {
-            const float* p = part + ((1LL * n * chunks + k) * C + c) * 2;
-            A += p[0];
-            B += p[1];
+        for (int k = lane; k < chunks; k += 32) {
+            const float2 v = *reinterpret_cast<const float2*>(part + ((1LL * n * chunks + k) * C + c) * 2);
+            A += v.x;
+            B += v.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            A += __shfl_xor_sync(0xFFFFFFFFu, A, o);
+            B += __shfl_xor_sync(0xFFFFFFFFu, B, o);
         }
         db += A;
         dg += B;
-        sa[c] = A * gamma[c];
-        sb[c] = B * gamma[c];
-        __syncthreads();
-        if (c < 32) {
-            double s1 = 0.0, s2 = 0.0;
-            for (int e = 0; e < cpg; ++e) { s1 += sa[c * cpg + e]; s2 += sb[c * cpg + e]; }
-            gsum[(n * 32 + c) * 2] = static_cast<float>(s1);
-            gsum[(n * 32 + c) * 2 + 1] = static_cast<float>(s2);
+        if (lane == 0) {
+            ab[(1LL * n * C + c) * 2] = static_cast<float>(A * ga);
+            ab[(1LL * n * C + c) * 2 + 1] = static_cast<float>(B * ga);
         }
-        __syncthreads();
     }
-    if (accumulate) { dgamma[c] += static_cast<float>(dg); dbeta[c] += static_cast<float>(db); }
-    else { dgamma[c] = static_cast<float>(dg); dbeta[c] = static_cast<float>(db); }
+    if (lane == 0) {
+        dgamma[c] = (accumulate ? dgamma[c] : 0.f) + static_cast<float>(dg);
+        dbeta[c] = (accumulate ? dbeta[c] : 0.f) + static_cast<float>(db);
+    }
+}
+// pass 1c: per (image, group) S1 = sum_c gamma_c A_c, S2 = sum_c gamma_c B_c over the group's channels, in channel order
+__global__ void gn_bwd_groups_kernel(const float* __restrict__ ab, float* __restrict__ gsum /*[N][32][2]*/, int C) {
+    const int n = blockIdx.x, g = threadIdx.x;
+    const int cpg = C / 32;
+    double s1 = 0.0, s2 = 0.0;
+    for (int e = 0; e < cpg; ++e) {
+        s1 += ab[(1LL * n * C + g * cpg + e) * 2];
+        s2 += ab[(1LL * n * C + g * cpg + e) * 2 + 1];
+    }
+    gsum[(n * 32 + g) * 2] = static_cast<float>(s1);
+    gsum[(n * 32 + g) * 2 + 1] = static_cast<float>(s2);
 }
 
 // pass 2: dx = rstd * (gamma*dt - (S1 + xhat*S2)/m) (+ add)
@@ -314,9 +328,11 @@ __global__ void __launch_bounds__(256) pack_plane_kernel(const void* __restrict_
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] = 0.f;
         if (qpos >= 0 && qpos < 1LL * N * Kimg) {
-            const int n = static_cast<int>(qpos / Kimg);
-            const long long r = qpos - 1LL * n * Kimg;
-            const int yp = static_cast<int>(r / Wp), j = static_cast<int>(r - 1LL * yp * Wp);
+            // 32-bit arithmetic: the launcher checks that a row has fewer than 2^31 positions
+            const unsigned uq = static_cast<unsigned>(qpos), uk = static_cast<unsigned>(Kimg);
+            const int n = static_cast<int>(uq / uk);
+            const unsigned r = uq - static_cast<unsigned>(n) * uk;
+            const int yp = static_cast<int>(r / static_cast<unsigned>(Wp)), j = static_cast<int>(r - static_cast<unsigned>(yp) * Wp);
             const int y = yp - 1, x = j - WG_LP;
             if (y >= 0 && y < H && x >= 0 && x < W) {
                 const int sy = sstride * y + spy, sx = sstride * x + spx;
@@ -369,8 +385,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
         long long r = i / Cin;
         const int tp = static_cast<int>(r % taps);
         const int co = static_cast<int>(r / taps);
-        double t = 0.0;
-        for (int b = 0; b < batches; ++b) t += part[(1LL * b * Cout + co) * taps * Cin + 1LL * tp * Cin + ci];
+        // batches b = 4j + r go to partial sum r (four loads in flight), the four are combined in index order: the
+        // association is fixed by `batches` alone
+        const float* src = part + 1LL * co * taps * Cin + 1LL * tp * Cin + ci;
+        const long long bs = 1LL * Cout * taps * Cin;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        int b = 0;
+        for (; b + 4 <= batches; b += 4) {
+            t0 += src[(b + 0) * bs]; t1 += src[(b + 1) * bs]; t2 += src[(b + 2) * bs]; t3 += src[(b + 3) * bs];
+        }
+        for (; b < batches; ++b) t0 += src[b * bs];
+        const double t = (t0 + t1) + (t2 + t3);
         float* o = dw + (1LL * co * Cin + ci) * taps + tp;
         *o = (accumulate ? *o : 0.f) + static_cast<float>(t);
     }
@@ -441,7 +466,8 @@ int bwd_gn_chunks(int N, long long HW) {
     return static_cast<int>(std::max<long long>(1, std::min<long long>(want, std::max(1, 148 * 4 / std::max(N, 1)))));
 }
 size_t bwd_gn_scratch_bytes(int N, long long HW, int C) {
-    return al(static_cast<size_t>(N) * bwd_gn_chunks(N, HW) * C * 2 * sizeof(float)) + al(static_cast<size_t>(N) * 64 * sizeof(float));
+    return al(static_cast<size_t>(N) * bwd_gn_chunks(N, HW) * C * 2 * sizeof(float)) +
+           al(static_cast<size_t>(N) * 64 * sizeof(float) + static_cast<size_t>(N) * C * 2 * sizeof(float));
 }
 
 int bwd_group_norm(const BwdEnv& e, const void* x, const void* dy, const double* stats, const float* gamma,
@@ -461,7 +487,9 @@ int bwd_group_norm(const BwdEnv& e, const void* x, const void* dy, const double*
     } else {
         gn_bwd_reduce_kernel<FMT_BF16, FMT_BF16><<<grid, 256, 0, e.s>>>(x, dy, stats, gamma, beta, part, HW, C, eps, silu);
     }
-    gn_bwd_finalize_kernel<<<1, C, 0, e.s>>>(part, gamma, gsum, dgamma, dbeta, N, chunks, C, accumulate);
+    float* ab = gsum + static_cast<size_t>(N) * 64;
+    gn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, e.s>>>(part, gamma, ab, dgamma, dbeta, N, chunks, C, accumulate);
+    gn_bwd_groups_kernel<<<N, 32, 0, e.s>>>(ab, gsum, C);
     if (e.fp32) {
         gn_bwd_apply_kernel<FMT_F32, FMT_F32><<<grid, 256, 0, e.s>>>(x, dy, stats, gamma, beta, gsum, add, dx, HW, C, eps, silu);
     } else if (e.raw_fmt == FMT_F16) {
@@ -549,6 +577,7 @@ int bwd_pack_plane_strided(const BwdEnv& e, const WgradPlan& p, const void* src,
                            int sstride, int spy, int spx, int Hs, int Ws) {
     VT_CHECK(!e.fp32 && C % 64 == 0, "operand planes exist in the 16-bit mode only; channels a multiple of 64");
     VT_CHECK(copies == 1 || copies == 3, "one plane, or the three horizontally shifted planes of a 3x3 conv input");
+    VT_CHECK(p.rowlen < (1LL << 31), "operand plane rows are limited to 2^31 positions");
     dim3 grid(static_cast<unsigned>((p.rowlen + 63) / 64), C / 64);
     // the (image, channel) scale / shift table sits behind the planes (bwd_wgrad_plan leaves room for it)
     float2* table = nullptr;
