@@ -310,19 +310,24 @@ __global__ void gn_table_kernel(const double* __restrict__ stats, const float* _
     const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
     table[i] = make_float2(rstd * gamma[c], beta[c] - static_cast<float>(mean) * rstd * gamma[c]);
 }
-template <int XF>
+// PB positions x CB channels per block (PB * CB = 4096): a thread loads 16 channels of one position (32 bytes) and
+// stores 16 positions of one channel (32 bytes); PB = 128 gives 256-byte runs per channel row on the store side
+template <int XF, int PB>
 __global__ void __launch_bounds__(256) pack_plane_kernel(const void* __restrict__ src, bf16* __restrict__ dst,
                                                          const float2* __restrict__ table, int N, int H, int W, int C, int Wp,
                                                          long long Kimg, long long G, long long rowlen,
                                                          int silu, int copies, int sstride, int spy, int spx, int Hs,
                                                          int Ws) {
     // plane pixel (y, x) <- source pixel (sstride*y + spy, sstride*x + spx) of the Hs x Ws source (zero outside)
-    __shared__ __align__(16) bf16 tile[64][80];    // [channel][1 halo + 64 positions + 1 halo (+ pad)]
-    const long long pos0 = 64LL * blockIdx.x;      // first row position of this block
-    const int c0 = blockIdx.y * 64;
-    // ---- load: thread = (position, 16-channel quarter); positions pos0-1 .. pos0+64 (66 of them)
-    for (int i = threadIdx.x; i < 66 * 4; i += 256) {
-        const int pi = i >> 2, q = i & 3;
+    constexpr int CB = 4096 / PB;          // channels per block
+    constexpr int QN = CB / 16;            // 16-channel quarters per position
+    constexpr int TP = PB + 16;            // tile row pitch in elements (1 halo + PB + 1 halo, padded; 16-byte multiple)
+    __shared__ __align__(16) bf16 tile[CB][TP];
+    const long long pos0 = static_cast<long long>(PB) * blockIdx.x;      // first row position of this block
+    const int c0 = blockIdx.y * CB;
+    // ---- load: thread = (position, 16-channel quarter); positions pos0-1 .. pos0+PB (PB + 2 of them)
+    for (int i = threadIdx.x; i < (PB + 2) * QN; i += 256) {
+        const int pi = i / QN, q = i - pi * QN;
         const long long qpos = pos0 - 1 + pi - G;          // position relative to the first image's plane
         float v[16];
 #pragma unroll
@@ -357,21 +362,24 @@ __global__ void __launch_bounds__(256) pack_plane_kernel(const void* __restrict_
         for (int e = 0; e < 16; ++e) tile[q * 16 + e][pi] = __float2bfloat16(v[e]);
     }
     __syncthreads();
-    // ---- store: thread = (channel, 16-position quarter); tile column of row position pos0 + k is k + 1
-    const int c = threadIdx.x >> 2, q = threadIdx.x & 3;
-    for (int cp = 0; cp < copies; ++cp) {
-        // copies: [dx = -1 | dx = 0 | dx = +1]; copy j holds plane[pos + j - 1] at pos (one copy: the plane itself)
-        const int shift = copies == 3 ? cp - 1 : 0;
-        bf16* row = dst + (1LL * cp * C + c0 + c) * rowlen + pos0 + q * 16;
+    // ---- store: thread = (channel, 16-position segment); tile column of row position pos0 + k is k + 1
+    constexpr int SEG = PB / 16;           // segments per channel row
+    for (int i = threadIdx.x; i < CB * SEG; i += 256) {
+        const int c = i / SEG, q = i - c * SEG;
+        for (int cp = 0; cp < copies; ++cp) {
+            // copies: [dx = -1 | dx = 0 | dx = +1]; copy j holds plane[pos + j - 1] at pos (one copy: the plane itself)
+            const int shift = copies == 3 ? cp - 1 : 0;
+            bf16* row = dst + (1LL * cp * C + c0 + c) * rowlen + pos0 + q * 16;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const long long pos = pos0 + q * 16 + h * 8;
-            if (pos >= rowlen) continue;     // rowlen is a multiple of 8: whole vectors only
-            const bf16* t = &tile[c][q * 16 + h * 8 + 1 + shift];
-            __align__(16) bf16 v[8];
+            for (int h = 0; h < 2; ++h) {
+                const long long pos = pos0 + q * 16 + h * 8;
+                if (pos >= rowlen) continue;     // rowlen is a multiple of 8: whole vectors only
+                const bf16* t = &tile[c][q * 16 + h * 8 + 1 + shift];
+                __align__(16) bf16 v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = t[e];
-            *reinterpret_cast<uint4*>(row + h * 8) = *reinterpret_cast<const uint4*>(v);
+                for (int e = 0; e < 8; ++e) v[e] = t[e];
+                *reinterpret_cast<uint4*>(row + h * 8) = *reinterpret_cast<const uint4*>(v);
+            }
         }
     }
 }
@@ -554,7 +562,7 @@ WgradPlan bwd_wgrad_plan(const BwdEnv& e, int N, int H, int W, int Cout, int Cin
     const int block_n = Cin >= 256 ? 256 : 128;
     const int tiles = ((Cout + 128 * mt - 1) / (128 * mt)) * ((Cin + block_n - 1) / block_n);
     long long S = std::max(1, (2 * 148 + N * tiles - 1) / (N * tiles));   // ~2 waves of CTAs per tap launch
-    S = std::min<long long>(S, std::max<long long>(1, plane / 512));       // at least 8 K chunks per tile
+    S = std::min<long long>(S, std::max<long long>(1, plane / 2048));      // at least 32 K chunks per tile
     p.Ks = ((plane + S - 1) / S + 63) / 64 * 64;
     p.splits = static_cast<int>(S);
     p.Kimg = p.Ks * S;
@@ -578,7 +586,8 @@ int bwd_pack_plane_strided(const BwdEnv& e, const WgradPlan& p, const void* src,
     VT_CHECK(!e.fp32 && C % 64 == 0, "operand planes exist in the 16-bit mode only; channels a multiple of 64");
     VT_CHECK(copies == 1 || copies == 3, "one plane, or the three horizontally shifted planes of a 3x3 conv input");
     VT_CHECK(p.rowlen < (1LL << 31), "operand plane rows are limited to 2^31 positions");
-    dim3 grid(static_cast<unsigned>((p.rowlen + 63) / 64), C / 64);
+    constexpr int PB = 128;
+    dim3 grid(static_cast<unsigned>((p.rowlen + PB - 1) / PB), C / (4096 / PB));
     // the (image, channel) scale / shift table sits behind the planes (bwd_wgrad_plan leaves room for it)
     float2* table = nullptr;
     if (stats) {
@@ -587,9 +596,9 @@ int bwd_pack_plane_strided(const BwdEnv& e, const WgradPlan& p, const void* src,
     }
     profiler_begin(e.prof, KC_MISC, e.s, 0, 2.0 * N * H * W * C + 2.0 * copies * C * p.rowlen);
     if (src_fmt == FMT_F16)
-        pack_plane_kernel<FMT_F16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), table, N, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, silu, copies, sstride, spy, spx, Hs, Ws);
+        pack_plane_kernel<FMT_F16, PB><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), table, N, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, silu, copies, sstride, spy, spx, Hs, Ws);
     else
-        pack_plane_kernel<FMT_BF16><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), table, N, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, silu, copies, sstride, spy, spx, Hs, Ws);
+        pack_plane_kernel<FMT_BF16, PB><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), table, N, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, silu, copies, sstride, spy, spx, Hs, Ws);
     profiler_end(e.prof, KC_MISC, e.s);
     VT_CUDA(cudaGetLastError());
     return 0;

@@ -8,6 +8,11 @@
 // stay resident in shared memory; two K=16 MMAs per 128-pixel sub-tile; the epilogue (bias, GroupNorm
 // partial sums of the output, bf16 pack, stores) is the implicit-GEMM one.
 //
+// What bounds it (ncu source page, round 2): instruction issue in the epilogue -- ~480 warp instructions per 32x32
+// output chunk (alpha/bias FFMA, GroupNorm sum / sum-of-squares, 16-bit pack / unpack, predicates and address
+// arithmetic) against 27 MACs per output element on the tensor core; neither loading the image one tile ahead nor
+// sixteen epilogue warps instead of eight moved it (both tried and reverted).
+//
 // Tile = 256 consecutive pixels of one image row (two 128-row sub-tiles) x 128 output channels.
 // Algorithmic HBM traffic per image: 3*H*W*4 B read + H*W*128*2 B written (the 64-wide patch matrix the
 // first version materialised, 128 B per pixel written and read again, is gone).
@@ -135,19 +140,18 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         const long long plane = static_cast<long long>(P.H) * P.W;
         int stage = 0;
         uint32_t phase = 0, it = 0;
-        // The image values of a tile are loaded into registers ONE TILE AHEAD: the HBM / L2 round trip of tile i+1 runs
-        // under the strip and operand-row work of tile i (without it every tile exposed one global-memory latency and
-        // the kernel sat at a quarter of its store roofline).
-        float vf[27];          // fp32 NCHW input: [rowid = kh*3 + c][part]
-        unsigned char vu[21];  // u8 NHWC input:  [kh][part]
-        auto issue_loads = [&](uint32_t tile) {
+        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int tx = static_cast<int>(tile % static_cast<uint32_t>(P.tiles_x));
             const uint32_t m = tile / static_cast<uint32_t>(P.tiles_x);
             const int y = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
             const int img = static_cast<int>(m / static_cast<uint32_t>(P.tiles_y));
             const int x0 = tx * 256;
+            __half* strip = strips + (it & 1) * (Cfg::STRIP_ALLOC / 4);
+            // ---- image rows y-1 .. y+1, columns x0-1 .. x0+256, three channels -> fp16 strip [kh*3+c][x]
+            // (all loads of a tile are issued before the first is used: one L2 round trip per tile, not one per element)
             if (Q.in_fmt == 0) {
                 const float* src = static_cast<const float*>(Q.img) + 3LL * img * plane;
+                float v[27];
 #pragma unroll
                 for (int rowid = 0; rowid < 9; ++rowid) {
                     const int kh = rowid / 3, c = rowid - kh * 3;
@@ -159,11 +163,19 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                         const int xx = gt + NG * part, gx = x0 + xx - 1;
                         float t = 0.f;
                         if (y_ok && xx < 258 && gx >= 0 && gx < P.W) t = __ldg(rowp + xx);
-                        vf[rowid * 3 + part] = t;
+                        v[rowid * 3 + part] = t;
                     }
                 }
+#pragma unroll
+                for (int rowid = 0; rowid < 9; ++rowid)
+#pragma unroll
+                    for (int part = 0; part < 3; ++part) {
+                        const int xx = gt + NG * part;
+                        if (xx < 258) strip[rowid * SW + xx] = __float2half_rn(v[rowid * 3 + part]);
+                    }
             } else {
                 const unsigned char* src = static_cast<const unsigned char*>(Q.img) + 3LL * img * plane;
+                unsigned char u[21];
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                     const int gy = y + kh - 1;
@@ -174,28 +186,9 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                         const int b = gt + NG * part, xx = b / 3, gx = x0 + xx - 1;
                         unsigned char t = 0;
                         if (y_ok && b < 774 && gx >= 0 && gx < P.W) t = __ldg(rowp + b);
-                        vu[kh * 7 + part] = t;
+                        u[kh * 7 + part] = t;
                     }
                 }
-            }
-        };
-        if (blockIdx.x < total_tiles) issue_loads(blockIdx.x);
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int tx = static_cast<int>(tile % static_cast<uint32_t>(P.tiles_x));
-            const uint32_t m = tile / static_cast<uint32_t>(P.tiles_x);
-            const int y = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
-            const int x0 = tx * 256;
-            __half* strip = strips + (it & 1) * (Cfg::STRIP_ALLOC / 4);
-            // ---- image rows y-1 .. y+1, columns x0-1 .. x0+256, three channels -> fp16 strip [kh*3+c][x]
-            if (Q.in_fmt == 0) {
-#pragma unroll
-                for (int rowid = 0; rowid < 9; ++rowid)
-#pragma unroll
-                    for (int part = 0; part < 3; ++part) {
-                        const int xx = gt + NG * part;
-                        if (xx < 258) strip[rowid * SW + xx] = __float2half_rn(vf[rowid * 3 + part]);
-                    }
-            } else {
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                     const int gy = y + kh - 1;
@@ -204,13 +197,11 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                     for (int part = 0; part < 7; ++part) {
                         const int b = gt + NG * part, xx = b / 3, c = b - xx * 3, gx = x0 + xx - 1;
                         const bool ok = y_ok && gx >= 0 && gx < P.W;
-                        const float val = ok ? (static_cast<float>(vu[kh * 7 + part]) / 255.0f - 0.5f) / 0.5f : 0.f;
+                        const float val = ok ? (static_cast<float>(u[kh * 7 + part]) / 255.0f - 0.5f) / 0.5f : 0.f;
                         if (b < 774) strip[(kh * 3 + c) * SW + xx] = __float2half_rn(val);
                     }
                 }
             }
-            // the next tile's loads go out now; they land while this tile's operand rows are built
-            if (tile + gridDim.x < total_tiles) issue_loads(tile + gridDim.x);
             asm volatile("bar.sync 3, %0;" ::"n"(NG) : "memory");
             mbar_wait(&a_empty[stage], phase ^ 1);
             // ---- two pixels per thread: k = (kh*3 + kw)*3 + c  ->  strip[kh*3 + c][x + kw]
