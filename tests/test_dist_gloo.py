@@ -213,3 +213,32 @@ def test_two_rank_sharded_cli_gather(tmp_path):
     assert list(r0["merged"].keys()) == [f"img{i:03d}.png" for i in range(23)]
     assert all(v["total_tags_above_threshold"] == int(k[3:6]) for k, v in r0["merged"].items())
     assert r0["errors"] == 1 and r1["merged"] == {} and r1["errors"] == 0
+
+
+def _worker_flat_allreduce(rank, world, port, out_dir):
+    """train_full / train_vae: one flat all-reduce over every gradient of the step (mean over ranks), parameters
+    without a gradient are skipped (a frozen or unused tensor must not desynchronise the flat layout)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vae_tagger_b200.train_full import _allreduce_grads
+    torch.manual_seed(3)
+    params = [nn.Parameter(torch.zeros(4, 3)), nn.Parameter(torch.zeros(5)), nn.Parameter(torch.zeros(2, 2))]
+    g = torch.Generator().manual_seed(10 + rank)
+    params[0].grad = torch.randn(4, 3, generator=g)
+    params[2].grad = torch.randn(2, 2, generator=g)      # params[1] has no gradient on any rank
+    local = [None if p.grad is None else p.grad.clone() for p in params]
+    _allreduce_grads(params, world)
+    torch.save({"local": local, "reduced": [None if p.grad is None else p.grad.clone() for p in params]},
+               os.path.join(out_dir, f"f{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_flat_gradient_allreduce(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker_flat_allreduce, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "f0.pt"), torch.load(tmp_path / "f1.pt")
+    for i in (0, 2):
+        want = (r0["local"][i] + r1["local"][i]) / 2
+        assert torch.allclose(r0["reduced"][i], want) and torch.equal(r0["reduced"][i], r1["reduced"][i])
+    assert r0["reduced"][1] is None and r1["reduced"][1] is None
