@@ -225,3 +225,19 @@ def test_degenerate_images(pair, kind):
         assert torch.isfinite(got).all()
         assert rel(got, ref) <= tol, (kind, prec, rel(got, ref))
     wrap.vae.precision = "bf16"
+
+
+def test_batch_invariance_at_the_benched_size(pair):
+    """BASELINE configs[1] size (1024^2): a size-independent property instead of the oracle (which needs minutes
+    per image on the CPU): an image's latent is bit-identical whether it is encoded alone, inside a batch of 6
+    (two micro-batches, both lanes), or at another batch position -- in the 16-bit mode the bench runs."""
+    _, wrap = pair
+    wrap.vae.precision = "bf16"
+    x = torch.cat([synthetic_images(3, 1024, 1024, seed=77), structured_images(3, 1024, 1024, seed=78)]).cuda()
+    whole = wrap.encode(x)
+    assert torch.isfinite(whole).all() and whole.shape == (6, 16, 128, 128)
+    assert torch.equal(wrap.encode(x[4:5].contiguous()), whole[4:5])
+    perm = torch.tensor([5, 0, 3, 1, 4, 2], device=x.device)
+    back = torch.empty_like(whole)
+    back[perm] = wrap.encode(x[perm].contiguous())
+    assert torch.equal(back, whole)

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libvt_b200.so")
 OBJ_DIR = os.path.join(os.path.dirname(HERE), "build", "vt_b200")
 
 SOURCES = ["vt_common.cu", "vt_igemm.cu", "vt_flash.cu", "vt_elementwise.cu", "vt_fp32.cu", "vt_head.cu", "vt_head_train.cu", "vt_resize.cu",
-           "vt_backward.cu", "vt_losses.cu", "vt_api.cu"]
+           "vt_backward.cu", "vt_wgrad.cu", "vt_losses.cu", "vt_api.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 

@@ -1793,13 +1793,14 @@ int vt_op_conv2d_backward(vt_ctx* c, const float* x, const float* w, const float
     const size_t es = e.fp32 ? 4 : 2;
     const long long HW = 1LL * H * W;
     const WgradPlan plan = bwd_wgrad_plan(e, N, H, W, Cout, Cin, ksize);
-    void *dX, *dG, *dDx, *wd, *pa, *pb, *cs;
+    void *dX, *dG, *dDx, *wd, *cs, *a16;
     float* part;
     Carver cv;
     cv.want(&dX, N * HW * Cin * es); cv.want(&dG, N * HW * Cout * es); cv.want(&dDx, N * HW * Cin * es);
+    cv.want(&a16, e.fp32 ? 0 : bwd_wgrad16_a16_bytes(N, H, W, Cin, 1));
     cv.want(&wd, bwd_dgrad_weight_bytes(e, Cout, Cin, ksize));
-    cv.want(&pa, e.fp32 ? 0 : plan.a_bytes); cv.want(&pb, e.fp32 ? 0 : plan.b_bytes);
-    cv.want(&part, plan.part_bytes); cv.want(&cs, bwd_colsum_scratch_bytes(Cout));
+    cv.want(&part, e.fp32 ? plan.part_bytes : bwd_wgrad_mn_plan(N, H, W, Cout, Cin, ksize).part_bytes);
+    cv.want(&cs, bwd_colsum_scratch_bytes(Cout));
     VT_TRY(cv.bind(c->opws));
     VT_TRY(launch_nchw_to_nhwc(x, dX, xf, N, Cin, HW, e.s));
     VT_TRY(launch_nchw_to_nhwc(grad_out, dG, gf, N, Cout, HW, e.s));
@@ -1809,13 +1810,8 @@ int vt_op_conv2d_backward(vt_ctx* c, const float* x, const float* w, const float
         VT_TRY(launch_nhwc_to_nchw(dDx, gf, grad_x, N, Cin, HW, e.s));
     }
     if (grad_w) {
-        if (e.fp32) {
-            VT_TRY(bwd_conv_wgrad(e, plan, dG, dX, part, grad_w, N, H, W, Cout, Cin, ksize, 0));
-        } else {
-            VT_TRY(bwd_pack_plane(e, plan, dG, FMT_BF16, pa, nullptr, nullptr, nullptr, N, H, W, Cout, 0.f, 0, 1));
-            VT_TRY(bwd_pack_plane(e, plan, dX, xf, pb, nullptr, nullptr, nullptr, N, H, W, Cin, 0.f, 0, ksize == 3 ? 3 : 1));
-            VT_TRY(bwd_conv_wgrad(e, plan, pa, pb, part, grad_w, N, H, W, Cout, Cin, ksize, 0));
-        }
+        if (e.fp32) VT_TRY(bwd_conv_wgrad(e, plan, dG, dX, part, grad_w, N, H, W, Cout, Cin, ksize, 0));
+        else VT_TRY(bwd_conv_wgrad16(e, dG, dX, xf, nullptr, nullptr, nullptr, 0.f, 0, a16, part, grad_w, N, H, W, Cout, Cin, ksize, 1, 0));
     }
     if (grad_b) VT_TRY(bwd_bias_grad(e, dG, N * HW, Cout, grad_b, 0, cs));
     return 0;
@@ -1860,10 +1856,10 @@ int vt_op_resnet_block_backward(vt_ctx* c, const float* x, const vt_resnet_block
     const long long HW = 1LL * H * W;
     const float eps = 1e-6f;
     const int Cmax = std::max(Cin, Cout);
-    // one operand-plane geometry for the three weight gradients of the block (they share the planes of dOut / x)
-    WgradPlan plan = bwd_wgrad_plan(e, N, H, W, Cout, Cmax, 3);
+    WgradPlan plan = bwd_wgrad_plan(e, N, H, W, Cout, Cmax, 3);    // fp32 mode: FFMA split-K plan
     plan.part_bytes = align_up(static_cast<size_t>(plan.batches) * Cout * 9 * Cmax * sizeof(float), 256);
-    void *X, *H1, *T, *dOut, *dA, *dH, *dX, *dSc, *w1, *wd1, *wd2, *wds, *pa, *pb, *gsc, *cs;
+    if (!e.fp32) plan.part_bytes = bwd_wgrad_mn_plan(N, H, W, Cout, Cmax, 3).part_bytes;   // >= the 1x1 shortcut's and conv1's
+    void *X, *H1, *T, *dOut, *dA, *dH, *dX, *dSc, *w1, *wd1, *wd2, *wds, *a16, *gsc, *cs;
     double *st_x, *st_h;
     float* part;
     Carver cv;
@@ -1873,9 +1869,8 @@ int vt_op_resnet_block_backward(vt_ctx* c, const float* x, const vt_resnet_block
     cv.want(&w1, static_cast<size_t>(Cout) * 9 * Cin * es);
     cv.want(&wd1, bwd_dgrad_weight_bytes(e, Cout, Cin, 3)); cv.want(&wd2, bwd_dgrad_weight_bytes(e, Cout, Cout, 3));
     cv.want(&wds, sc ? bwd_dgrad_weight_bytes(e, Cout, Cin, 1) : 0);
-    cv.want(&pa, e.fp32 ? 0 : align_up(static_cast<size_t>(Cout) * plan.rowlen * 2, 256));
-    cv.want(&pb, e.fp32 ? 0 : align_up(static_cast<size_t>(3) * Cmax * plan.rowlen * 2, 256) + static_cast<size_t>(N) * Cmax * 8 + 256);
-    cv.want(&part, plan.part_bytes);
+    cv.want(&a16, e.fp32 ? 0 : bwd_wgrad16_a16_bytes(N, H, W, Cmax, 1));
+    cv.want(&part, std::max(plan.part_bytes, bwd_wgrad_mn_plan(N, H, W, Cout, Cin, 3).part_bytes));
     cv.want(&gsc, bwd_gn_scratch_bytes(N, HW, Cmax)); cv.want(&cs, bwd_colsum_scratch_bytes(Cout));
     cv.want(&st_x, static_cast<size_t>(N) * 64 * sizeof(double)); cv.want(&st_h, static_cast<size_t>(N) * 64 * sizeof(double));
     VT_TRY(cv.bind(c->opws));
@@ -1905,13 +1900,8 @@ int vt_op_resnet_block_backward(vt_ctx* c, const float* x, const vt_resnet_block
         VT_TRY(bwd_conv_wgrad(e, plan, dOut, T, part, g->conv2_w, N, H, W, Cout, Cout, 3, 0));
         if (sc) VT_TRY(bwd_conv_wgrad(e, p1, dOut, X, part, g->sc_w, N, H, W, Cout, Cin, 1, 0));
     } else {
-        VT_TRY(bwd_pack_plane(e, plan, dOut, FMT_BF16, pa, nullptr, nullptr, nullptr, N, H, W, Cout, 0.f, 0, 1));
-        VT_TRY(bwd_pack_plane(e, plan, H1, xf, pb, st_h, pr->norm2_w, pr->norm2_b, N, H, W, Cout, eps, 1, 3));
-        VT_TRY(bwd_conv_wgrad(e, plan, pa, pb, part, g->conv2_w, N, H, W, Cout, Cout, 3, 0));
-        if (sc) {
-            VT_TRY(bwd_pack_plane(e, plan, X, xf, pb, nullptr, nullptr, nullptr, N, H, W, Cin, 0.f, 0, 1));
-            VT_TRY(bwd_conv_wgrad(e, p1, pa, pb, part, g->sc_w, N, H, W, Cout, Cin, 1, 0));
-        }
+        VT_TRY(bwd_conv_wgrad16(e, dOut, H1, xf, st_h, pr->norm2_w, pr->norm2_b, eps, 1, a16, part, g->conv2_w, N, H, W, Cout, Cout, 3, 1, 0));
+        if (sc) VT_TRY(bwd_conv_wgrad16(e, dOut, X, xf, nullptr, nullptr, nullptr, 0.f, 0, a16, part, g->sc_w, N, H, W, Cout, Cin, 1, 1, 0));
     }
     VT_TRY(bwd_pack_dgrad_weight(e, pr->conv2_w, wd2, Cout, Cout, 3));
     VT_TRY(bwd_conv_dgrad(e, dOut, wd2, dA, nullptr, N, H, W, Cout, Cout, 3));
@@ -1923,9 +1913,7 @@ int vt_op_resnet_block_backward(vt_ctx* c, const float* x, const vt_resnet_block
         VT_TRY(launch_gn_apply(X, xf, T, of, st_x, pr->norm1_w, pr->norm1_b, N, HW, Cin, 32, eps, 1, e.s, c->prof));
         VT_TRY(bwd_conv_wgrad(e, plan, dH, T, part, g->conv1_w, N, H, W, Cout, Cin, 3, 0));
     } else {
-        VT_TRY(bwd_pack_plane(e, plan, dH, FMT_BF16, pa, nullptr, nullptr, nullptr, N, H, W, Cout, 0.f, 0, 1));
-        VT_TRY(bwd_pack_plane(e, plan, X, xf, pb, st_x, pr->norm1_w, pr->norm1_b, N, H, W, Cin, eps, 1, 3));
-        VT_TRY(bwd_conv_wgrad(e, plan, pa, pb, part, g->conv1_w, N, H, W, Cout, Cin, 3, 0));
+        VT_TRY(bwd_conv_wgrad16(e, dH, X, xf, st_x, pr->norm1_w, pr->norm1_b, eps, 1, a16, part, g->conv1_w, N, H, W, Cout, Cin, 3, 1, 0));
     }
     VT_TRY(bwd_pack_dgrad_weight(e, pr->conv1_w, wd1, Cout, Cin, 3));
     VT_TRY(bwd_conv_dgrad(e, dH, wd1, dA, nullptr, N, H, W, Cout, Cin, 3));

@@ -931,4 +931,44 @@ int bwd_convin_chunks(int N, int H, int W) {
     return static_cast<int>(std::max<long long>(1, std::min<long long>((1LL * N * H * W + 255) / 256, 148 * 8)));
 }
 
+
+// fp16 -> bf16 copy (8 elements per thread): tcgen05 kind::f16 wants both operands of an MMA in ONE 16-bit format (a
+// bf16 x fp16 pair traps -- tools/umma_mn_probe.cu), and the gradient side must be bf16 for its range
+__global__ void __launch_bounds__(256) f16_to_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long n8) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n8; i += 256LL * gridDim.x) {
+        const uint4 u = in[i];
+        out[i] = make_uint4(pack_bf16x2(f16_lo(u.x), f16_hi(u.x)), pack_bf16x2(f16_lo(u.y), f16_hi(u.y)),
+                            pack_bf16x2(f16_lo(u.z), f16_hi(u.z)), pack_bf16x2(f16_lo(u.w), f16_hi(u.w)));
+    }
+}
+
+// ---- 16-bit weight gradient through the MN-major kernel (vt_wgrad.cu)
+size_t bwd_wgrad16_a16_bytes(int N, int H, int W, int Cin, int stride) {
+    return al(static_cast<size_t>(N) * stride * H * stride * W * Cin * 2);
+}
+int bwd_conv_wgrad16(const BwdEnv& e, const void* dy, const void* a_src, int a_fmt, const double* stats, const float* gamma,
+                     const float* beta, float eps, int silu, void* a16, float* part, float* dw, int N, int H, int W, int Cout,
+                     int Cin, int ks, int stride, int accumulate) {
+    const void* a = a_src;
+    const long long elems = 1LL * N * stride * H * stride * W * Cin;
+    if (stats) {
+        VT_CHECK(a16 != nullptr, "the normalised operand needs a scratch buffer");
+        VT_TRY(launch_gn_apply(a_src, a_fmt, a16, FMT_BF16, stats, gamma, beta, N, 1LL * stride * H * stride * W, Cin, 32, eps, silu,
+                               e.s, e.prof));
+        a = a16;
+    } else if (a_fmt == FMT_F16) {
+        VT_CHECK(a16 != nullptr, "an fp16 operand needs a scratch buffer for its bf16 copy");
+        f16_to_bf16_kernel<<<grid_for(elems / 8), 256, 0, e.s>>>(static_cast<const uint4*>(a_src), static_cast<uint4*>(a16), elems / 8);
+        VT_CUDA(cudaGetLastError());
+        a = a16;
+    }
+    a_fmt = FMT_BF16;
+    const WgradMnPlan p = bwd_wgrad_mn_plan(N, H, W, Cout, Cin, ks);
+    VT_TRY(bwd_conv_wgrad_mn(e, p, dy, FMT_BF16, a, a_fmt, part, N, H, W, Cout, Cin, ks, stride));
+    const int taps = ks * ks;
+    wgrad_reduce_kernel<<<grid_for(1LL * Cout * Cin * taps), 256, 0, e.s>>>(part, dw, p.splits, Cout, Cin, taps, accumulate);
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace vt

@@ -51,6 +51,23 @@ int bwd_pack_plane_strided(const BwdEnv& e, const WgradPlan& p, const void* src,
 int bwd_conv_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const void* a, float* part, float* dw, int N, int H,
                    int W, int Cout, int Cin, int ks, int accumulate);
 
+// ---- weight gradient straight from the NHWC tensors (vt_wgrad.cu): MN-major tcgen05 operands, taps = shifted TMA boxes
+struct WgradMnPlan {
+    int tiles_x, tiles_y, col_groups, m_blocks, splits, per_split;
+    size_t part_bytes;      // fp32 split-K partial tiles [splits][Cout][taps*Cin]
+};
+WgradMnPlan bwd_wgrad_mn_plan(int N, int H, int W, int Cout, int Cin, int ks);
+int bwd_conv_wgrad_mn(const BwdEnv& e, const WgradMnPlan& p, const void* dy, int y_fmt, const void* a, int a_fmt, float* part,
+                      int N, int H, int W, int Cout, int Cin, int ks, int stride);
+// 16-bit mode, whole weight gradient of one conv: the conv input as a bf16 NHWC operand in `a16` -- through
+// GroupNorm(+SiLU) when stats != null, a plain fp16 -> bf16 copy otherwise (both MMA operands must share one format and
+// the gradient side is bf16); a bf16 input is used as stored -- then the MN-major GEMM and the fixed-order reduce into
+// dw[Cout][Cin][ks][ks].  H, W: size of dy (the conv OUTPUT); the input is (stride*H) x (stride*W).
+size_t bwd_wgrad16_a16_bytes(int N, int H, int W, int Cin, int stride);
+int bwd_conv_wgrad16(const BwdEnv& e, const void* dy, const void* a_src, int a_fmt, const double* stats, const float* gamma,
+                     const float* beta, float eps, int silu, void* a16, float* part, float* dw, int N, int H, int W, int Cout,
+                     int Cin, int ks, int stride, int accumulate);
+
 // ---- pieces of the whole-encoder backward
 int bwd_transpose(const BwdEnv& e, const void* in, int in_fmt, void* out, int out_fmt, int rows, int cols, long long ld_in,
                   long long ld_out, int batch, long long in_bs, long long out_bs);

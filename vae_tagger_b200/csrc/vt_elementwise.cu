@@ -290,6 +290,7 @@ int launch_gn_apply(const void* x, int x_fmt, void* y, int y_fmt, const double* 
     else if (x_fmt == FMT_BF16 && y_fmt == FMT_F16) VT_GN(FMT_BF16, FMT_F16, true);
     else if (x_fmt == FMT_BF16 && y_fmt == FMT_BF16) VT_GN(FMT_BF16, FMT_BF16, true);
     else if (x_fmt == FMT_F16 && y_fmt == FMT_F16) VT_GN(FMT_F16, FMT_F16, true);
+    else if (x_fmt == FMT_F16 && y_fmt == FMT_BF16) VT_GN(FMT_F16, FMT_BF16, true);   // backward operand (vt_wgrad.cu)
     else {
         set_error("GroupNorm apply: this input / output format pair is not instantiated");
         return -2;

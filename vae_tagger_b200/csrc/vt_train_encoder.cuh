@@ -209,18 +209,19 @@ struct EncBwd {
     //   fp32 mode:   a_src is the conv's actual fp32 input (the caller applies the normalisation)
     int conv_wgrad(const void* dy, const void* a_src, int a_fmt, const double* st, const float* gamma, const float* beta,
                    int silu, int H, int W, int Cout, int Cin, int ks, float* dw, float* db) {
-        const WgradPlan p = bwd_wgrad_plan(e, n, H, W, Cout, Cin, ks);
-        void *pa = nullptr, *pb = nullptr, *cs = nullptr;
+        void *a16 = nullptr, *cs = nullptr;
         float* part = nullptr;
-        cv.want(&pa, e.fp32 ? 0 : p.a_bytes); cv.want(&pb, e.fp32 ? 0 : p.b_bytes); cv.want(&part, p.part_bytes);
-        cv.want(&cs, bwd_colsum_scratch_bytes(Cout));
-        VT_TRY(bind());
         if (e.fp32) {
+            const WgradPlan p = bwd_wgrad_plan(e, n, H, W, Cout, Cin, ks);
+            cv.want(&part, p.part_bytes); cv.want(&cs, bwd_colsum_scratch_bytes(Cout));
+            VT_TRY(bind());
             VT_TRY(bwd_conv_wgrad(e, p, dy, a_src, part, dw, n, H, W, Cout, Cin, ks, acc));
         } else {
-            VT_TRY(bwd_pack_plane(e, p, dy, FMT_BF16, pa, nullptr, nullptr, nullptr, n, H, W, Cout, 0.f, 0, 1));
-            VT_TRY(bwd_pack_plane(e, p, a_src, a_fmt, pb, st, gamma, beta, n, H, W, Cin, 1e-6f, silu, ks == 3 ? 3 : 1));
-            VT_TRY(bwd_conv_wgrad(e, p, pa, pb, part, dw, n, H, W, Cout, Cin, ks, acc));
+            cv.want(&a16, bwd_wgrad16_a16_bytes(n, H, W, Cin, 1));
+            cv.want(&part, bwd_wgrad_mn_plan(n, H, W, Cout, Cin, ks).part_bytes);
+            cv.want(&cs, bwd_colsum_scratch_bytes(Cout));
+            VT_TRY(bind());
+            VT_TRY(bwd_conv_wgrad16(e, dy, a_src, a_fmt, st, gamma, beta, 1e-6f, silu, a16, part, dw, n, H, W, Cout, Cin, ks, 1, acc));
         }
         if (db) VT_TRY(bwd_bias_grad(e, dy, 1LL * n * H * W, Cout, db, acc, cs));
         return 0;
@@ -302,21 +303,18 @@ struct EncBwd {
         int err = 0;
         float *gw = G(p + ".weight", &err), *gb = G(p + ".bias", &err);
         if (err) return err;
-        const WgradPlan pl = bwd_wgrad_plan(e, n, Ho, Wo, C, C, 3);
-        void *pa = nullptr, *pb = nullptr, *cs = nullptr, *wd = nullptr;
+        void *cs = nullptr, *wd = nullptr, *a16 = nullptr;
         float* part = nullptr;
-        const size_t plane = static_cast<size_t>(C) * pl.rowlen * 2;
-        cv.want(&pa, e.fp32 ? 0 : plane); cv.want(&pb, e.fp32 ? 0 : 12 * plane); cv.want(&part, pl.part_bytes);
+        const WgradPlan pl = bwd_wgrad_plan(e, n, Ho, Wo, C, C, 3);
+        cv.want(&a16, e.fp32 ? 0 : bwd_wgrad16_a16_bytes(n, Ho, Wo, C, 2));
+        cv.want(&part, e.fp32 ? pl.part_bytes : bwd_wgrad_mn_plan(n, Ho, Wo, C, C, 3).part_bytes);
         cv.want(&cs, bwd_colsum_scratch_bytes(C)); cv.want(&wd, bwd_dgrad_s2_weight_bytes(e, C, C));
         VT_TRY(bind());
         if (e.fp32) {
             VT_TRY(bwd_conv_s2_wgrad(e, pl, dOut, op.x.p, part, gw, n, Hi, Wi, C, C, acc));
         } else {
-            VT_TRY(bwd_pack_plane(e, pl, dOut, FMT_BF16, pa, nullptr, nullptr, nullptr, n, Ho, Wo, C, 0.f, 0, 1));
-            for (int par = 0; par < 4; ++par)
-                VT_TRY(bwd_pack_plane_strided(e, pl, op.x.p, xf, static_cast<char*>(pb) + static_cast<size_t>(par) * 3 * plane, nullptr,
-                                              nullptr, nullptr, n, Ho, Wo, C, 0.f, 0, 3, 2, par >> 1, par & 1, Hi, Wi));
-            VT_TRY(bwd_conv_s2_wgrad(e, pl, pa, pb, part, gw, n, Hi, Wi, C, C, acc));
+            // the conv input as stored (a raw activation), read through the stride-2 parity view
+            VT_TRY(bwd_conv_wgrad16(e, dOut, op.x.p, xf, nullptr, nullptr, nullptr, 0.f, 0, a16, part, gw, n, Ho, Wo, C, C, 3, 2, acc));
         }
         VT_TRY(bwd_bias_grad(e, dOut, 1LL * n * Ho * Wo, C, gb, acc, cs));
         return bwd_conv_s2_dgrad(e, dOut, Wt(p + ".weight"), wd, dX, n, Hi, Wi, C, C);
