@@ -4,13 +4,11 @@
 //
 //   * data gradient of a 3x3 / 1x1 stride-1 conv  = the forward implicit-GEMM tcgen05 kernel (vt_igemm.cuh) run on
 //     the output gradient with the weights flipped and transposed ([Cin][tap'][Cout], tap' = 8 - tap);
-//   * weight gradient = a tcgen05 GEMM whose K dimension is the PIXELS: dW[co][tap][ci] = sum_p dY[p][co] A[p+tap][ci].
-//     Both operands are re-laid out once per conv as channel-major rows over a zero-padded pixel plane
-//     ([C][guard | image 0: (H+2) x Wp | image 1 ... | guard], bf16), so that a tap is a constant flat offset
-//     (dy*Wp + dx) and the padding supplies the zeros of "pad 1"; the row of an image is cut into S equal K ranges
-//     (split-K: one GEMM "batch" per (image, range), fp32 partial tiles) and wgrad_reduce_kernel adds the partials
-//     in index order -- no atomics, bit-reproducible.  One launch of the forward GEMM kernel per tap, with a
-//     different K start coordinate for the B operand (GemmOp::b_k0; TMA coordinates need no alignment);
+//   * weight gradient = a tcgen05 GEMM whose K dimension is the PIXELS: dW[co][tap][ci] = sum_p dY[p][co] A[p+tap][ci],
+//     with BOTH operands read straight from the NHWC tensors as MN-major tiles and every tap a shifted TMA box
+//     (vt_wgrad.cu); split-K over pixel patches, fp32 partial tiles, wgrad_reduce_kernel adds them in index order --
+//     no atomics, bit-reproducible.  The conv input is handed over as a bf16 NHWC operand: through GroupNorm+SiLU when
+//     the conv saw the normalised tensor, a plain fp16 -> bf16 copy otherwise (bwd_conv_wgrad16);
 //   * GroupNorm + SiLU backward: two HBM passes (per-channel sums of dt and dt*xhat with a fixed-order two-stage
 //     reduce, then the apply pass, with the residual-branch gradient added in the same pass);
 //   * bias gradients: fixed-order column sums.
@@ -289,101 +287,6 @@ __global__ void pack_dgrad_weight_kernel(const float* __restrict__ w /*[Cout][Ci
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// NHWC [N][H][W][C] (format XF) -> channel-major rows over the zero-padded pixel plane, bf16:
-//   dst[c][G + n*Kimg + (y+1)*Wp + LP + x],  optionally through GroupNorm(+SiLU) of the source (the operand a
-//   conv actually saw).  A block owns 64 consecutive positions of the ROW (guards, pad rows / columns and the K padding
-//   behind an image included: they are written as zeros, so the buffer needs no memset and may hold anything) x 64
-//   channels, staged through shared memory with one halo position on either side; every copy -- the plane itself and,
-//   for a 3x3 conv input, the planes shifted by one pixel left / right -- leaves as 16-byte stores.
-constexpr int WG_LP = 8;
-// per (image, channel) scale / shift of GroupNorm: t = x * sc + sh
-__global__ void gn_table_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float2* __restrict__ table, int N, int C, long long HW, float eps) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N * C) return;
-    const int n = i / C, c = i - n * C, cpg = C / 32, g = c / cpg;
-    const double cnt = static_cast<double>(HW) * cpg;
-    const double mean = stats[(1LL * n * 32 + g) * 2] / cnt;
-    double var = stats[(1LL * n * 32 + g) * 2 + 1] / cnt - mean * mean;
-    var = var > 0.0 ? var : 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    table[i] = make_float2(rstd * gamma[c], beta[c] - static_cast<float>(mean) * rstd * gamma[c]);
-}
-// PB positions x CB channels per block (PB * CB = 4096): a thread loads 16 channels of one position (32 bytes) and
-// stores 16 positions of one channel (32 bytes); PB = 128 gives 256-byte runs per channel row on the store side
-template <int XF, int PB>
-__global__ void __launch_bounds__(256) pack_plane_kernel(const void* __restrict__ src, bf16* __restrict__ dst,
-                                                         const float2* __restrict__ table, int N, int H, int W, int C, int Wp,
-                                                         long long Kimg, long long G, long long rowlen,
-                                                         int silu, int copies, int sstride, int spy, int spx, int Hs,
-                                                         int Ws) {
-    // plane pixel (y, x) <- source pixel (sstride*y + spy, sstride*x + spx) of the Hs x Ws source (zero outside)
-    constexpr int CB = 4096 / PB;          // channels per block
-    constexpr int QN = CB / 16;            // 16-channel quarters per position
-    constexpr int TP = PB + 16;            // tile row pitch in elements (1 halo + PB + 1 halo, padded; 16-byte multiple)
-    __shared__ __align__(16) bf16 tile[CB][TP];
-    const long long pos0 = static_cast<long long>(PB) * blockIdx.x;      // first row position of this block
-    const int c0 = blockIdx.y * CB;
-    // ---- load: thread = (position, 16-channel quarter); positions pos0-1 .. pos0+PB (PB + 2 of them)
-    for (int i = threadIdx.x; i < (PB + 2) * QN; i += 256) {
-        const int pi = i / QN, q = i - pi * QN;
-        const long long qpos = pos0 - 1 + pi - G;          // position relative to the first image's plane
-        float v[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = 0.f;
-        if (qpos >= 0 && qpos < 1LL * N * Kimg) {
-            // 32-bit arithmetic: the launcher checks that a row has fewer than 2^31 positions
-            const unsigned uq = static_cast<unsigned>(qpos), uk = static_cast<unsigned>(Kimg);
-            const int n = static_cast<int>(uq / uk);
-            const unsigned r = uq - static_cast<unsigned>(n) * uk;
-            const int yp = static_cast<int>(r / static_cast<unsigned>(Wp)), j = static_cast<int>(r - static_cast<unsigned>(yp) * Wp);
-            const int y = yp - 1, x = j - WG_LP;
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                const int sy = sstride * y + spy, sx = sstride * x + spx;
-                if (sy < Hs && sx < Ws) {
-                    const long long off = ((1LL * n * Hs + sy) * Ws + sx) * C + c0 + q * 16;
-                    load8<XF>(src, off, v);
-                    load8<XF>(src, off + 8, v + 8);
-                    if (table) {
-                        const float2* tb = table + 1LL * n * C + c0 + q * 16;
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const float2 k = tb[e];
-                            float t = fmaf(v[e], k.x, k.y);
-                            if (silu) t = __fdividef(t, 1.0f + __expf(-t));
-                            v[e] = t;
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) tile[q * 16 + e][pi] = __float2bfloat16(v[e]);
-    }
-    __syncthreads();
-    // ---- store: thread = (channel, 16-position segment); tile column of row position pos0 + k is k + 1
-    constexpr int SEG = PB / 16;           // segments per channel row
-    for (int i = threadIdx.x; i < CB * SEG; i += 256) {
-        const int c = i / SEG, q = i - c * SEG;
-        for (int cp = 0; cp < copies; ++cp) {
-            // copies: [dx = -1 | dx = 0 | dx = +1]; copy j holds plane[pos + j - 1] at pos (one copy: the plane itself)
-            const int shift = copies == 3 ? cp - 1 : 0;
-            bf16* row = dst + (1LL * cp * C + c0 + c) * rowlen + pos0 + q * 16;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const long long pos = pos0 + q * 16 + h * 8;
-                if (pos >= rowlen) continue;     // rowlen is a multiple of 8: whole vectors only
-                const bf16* t = &tile[c][q * 16 + h * 8 + 1 + shift];
-                __align__(16) bf16 v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = t[e];
-                *reinterpret_cast<uint4*>(row + h * 8) = *reinterpret_cast<const uint4*>(v);
-            }
-        }
-    }
-}
-
 // partial tiles part[b][co][taps*Cin] -> dW [Cout][Cin][ks][ks] (OIHW, what torch holds), batches in index order
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int batches, int Cout,
                                     int Cin, int taps, int accumulate) {
@@ -545,92 +448,27 @@ int bwd_conv_dgrad(const BwdEnv& e, const void* dy, const void* wd, void* dx, co
 }
 
 // ---- weight gradient
+// fp32 verification mode: split-K plan of the FFMA weight-gradient kernel
 WgradPlan bwd_wgrad_plan(const BwdEnv& e, int N, int H, int W, int Cout, int Cin, int ks) {
+    (void)e;
     WgradPlan p{};
     p.taps = ks * ks;
-    if (e.fp32) {
-        const long long P = 1LL * N * H * W;
-        const int tiles = (Cout / 64) * (p.taps * Cin / 64);
-        p.splits = static_cast<int>(std::max<long long>(1, std::min<long long>((P + 1023) / 1024, std::max(1, 148 * 8 / tiles))));
-        p.batches = p.splits;
-        p.part_bytes = al(static_cast<size_t>(p.batches) * Cout * p.taps * Cin * sizeof(float));
-        return p;
-    }
-    p.Wp = (W + WG_LP + 1 + 7) / 8 * 8;
-    const long long plane = 1LL * (H + 2) * p.Wp;
-    const int mt = Cin >= 256 ? 1 : 2;                                  // launch_gemm's tile: 128 x 256 or 2x128 x 128
-    const int block_n = Cin >= 256 ? 256 : 128;
-    const int tiles = ((Cout + 128 * mt - 1) / (128 * mt)) * ((Cin + block_n - 1) / block_n);
-    long long S = std::max(1, (2 * 148 + N * tiles - 1) / (N * tiles));   // ~2 waves of CTAs per tap launch
-    S = std::min<long long>(S, std::max<long long>(1, plane / 2048));      // at least 32 K chunks per tile
-    p.Ks = ((plane + S - 1) / S + 63) / 64 * 64;
-    p.splits = static_cast<int>(S);
-    p.Kimg = p.Ks * S;
-    p.G = (p.Wp + 1 + 7) / 8 * 8;
-    p.rowlen = (p.G + 1LL * N * p.Kimg + p.G + 64 + 7) / 8 * 8;
-    p.batches = N * p.splits;
-    // + room for the GroupNorm scale / shift table of a transformed operand (bwd_pack_plane)
-    p.a_bytes = al(static_cast<size_t>(Cout) * p.rowlen * 2) + al(static_cast<size_t>(N) * Cout * 8);
-    p.b_bytes = al(static_cast<size_t>(ks == 3 ? 3 : 1) * Cin * p.rowlen * 2) + al(static_cast<size_t>(N) * Cin * 8);
+    const long long P = 1LL * N * H * W;
+    const int tiles = std::max(1, (Cout / 64) * (p.taps * Cin / 64));
+    p.splits = static_cast<int>(std::max<long long>(1, std::min<long long>((P + 1023) / 1024, std::max(1, 148 * 8 / tiles))));
+    p.batches = p.splits;
     p.part_bytes = al(static_cast<size_t>(p.batches) * Cout * p.taps * Cin * sizeof(float));
     return p;
 }
 
-int bwd_pack_plane(const BwdEnv& e, const WgradPlan& p, const void* src, int src_fmt, void* dst, const double* stats,
-                   const float* gamma, const float* beta, int N, int H, int W, int C, float eps, int silu, int copies) {
-    return bwd_pack_plane_strided(e, p, src, src_fmt, dst, stats, gamma, beta, N, H, W, C, eps, silu, copies, 1, 0, 0, H, W);
-}
-int bwd_pack_plane_strided(const BwdEnv& e, const WgradPlan& p, const void* src, int src_fmt, void* dst, const double* stats,
-                           const float* gamma, const float* beta, int N, int H, int W, int C, float eps, int silu, int copies,
-                           int sstride, int spy, int spx, int Hs, int Ws) {
-    VT_CHECK(!e.fp32 && C % 64 == 0, "operand planes exist in the 16-bit mode only; channels a multiple of 64");
-    VT_CHECK(copies == 1 || copies == 3, "one plane, or the three horizontally shifted planes of a 3x3 conv input");
-    VT_CHECK(p.rowlen < (1LL << 31), "operand plane rows are limited to 2^31 positions");
-    constexpr int PB = 128;
-    dim3 grid(static_cast<unsigned>((p.rowlen + PB - 1) / PB), C / (4096 / PB));
-    // the (image, channel) scale / shift table sits behind the planes (bwd_wgrad_plan leaves room for it)
-    float2* table = nullptr;
-    if (stats) {
-        table = reinterpret_cast<float2*>(static_cast<char*>(dst) + al(static_cast<size_t>(copies) * C * p.rowlen * 2));
-        gn_table_kernel<<<(N * C + 255) / 256, 256, 0, e.s>>>(stats, gamma, beta, table, N, C, 1LL * Hs * Ws, eps);
-    }
-    profiler_begin(e.prof, KC_MISC, e.s, 0, 2.0 * N * H * W * C + 2.0 * copies * C * p.rowlen);
-    if (src_fmt == FMT_F16)
-        pack_plane_kernel<FMT_F16, PB><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), table, N, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, silu, copies, sstride, spy, spx, Hs, Ws);
-    else
-        pack_plane_kernel<FMT_BF16, PB><<<grid, 256, 0, e.s>>>(src, static_cast<bf16*>(dst), table, N, H, W, C, p.Wp, p.Kimg, p.G, p.rowlen, silu, copies, sstride, spy, spx, Hs, Ws);
-    profiler_end(e.prof, KC_MISC, e.s);
-    VT_CUDA(cudaGetLastError());
-    return 0;
-}
-
 int bwd_conv_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const void* a, float* part, float* dw, int N, int H,
                    int W, int Cout, int Cin, int ks, int accumulate) {
-    if (e.fp32) {
-        VT_CHECK(Cout % 64 == 0 && Cin % 64 == 0, "fp32 weight gradient: channels must be multiples of 64");
-        dim3 grid(Cout / 64, p.taps * (Cin / 64), p.splits);
-        profiler_begin(e.prof, KC_FP32, e.s, 2.0 * N * H * W * Cout * Cin * p.taps, 0);
-        f32_wgrad_kernel<<<grid, 256, 0, e.s>>>(static_cast<const float*>(dy), static_cast<const float*>(a), part, N, H, W, Cout, Cin, ks, 1, H, W);
-        profiler_end(e.prof, KC_FP32, e.s);
-    } else {
-        // dy, a: operand planes (bwd_pack_plane).  One GEMM launch per tap: M = Cout, N = Cin, K = Ks per (image, range)
-        const char* tm = getenv("VT_BWD_TAPMASK");    // debugging aid: run a subset of the taps
-        const int tapmask = tm ? atoi(tm) : 0x1FF;
-        for (int tap = 0; tap < p.taps; ++tap) {
-            if (!((tapmask >> tap) & 1)) continue;
-            const int dyo = ks == 3 ? tap / 3 - 1 : 0, dxo = ks == 3 ? tap % 3 - 1 : 0;
-            GemmOp g;
-            // a: three planes for a 3x3 conv (dx = -1, 0, +1), one for a 1x1 conv
-            g.A = dy; g.B = static_cast<const bf16*>(a) + (ks == 3 ? 1LL * (dxo + 1) * Cin * p.rowlen : 0); g.batch = p.batches; g.M = Cout; g.N = Cin; g.K = static_cast<int>(p.Ks);
-            g.lda = p.rowlen; g.ldb = p.rowlen; g.a_bstride = p.Ks; g.b_bstride = p.Ks;
-            g.a_kdim = p.rowlen; g.b_kdim = p.rowlen;
-            g.a_k0 = p.G; g.b_k0 = p.G + 1LL * dyo * p.Wp;     // k runs over plane positions, pads included
-            g.out = part + 1LL * tap * Cin; g.out_fmt = FMT_F32; g.ld_out = 1LL * p.taps * Cin;
-            g.out_bstride = 1LL * Cout * p.taps * Cin;
-            g.ab_f16 = 0; g.kclass = KC_BWD;
-            VT_TRY(launch_gemm(g, e.s, e.prof));
-        }
-    }
+    VT_CHECK(e.fp32, "bwd_conv_wgrad is the fp32 verification path (16-bit mode: bwd_conv_wgrad16)");
+    VT_CHECK(Cout % 64 == 0 && Cin % 64 == 0, "fp32 weight gradient: channels must be multiples of 64");
+    dim3 grid(Cout / 64, p.taps * (Cin / 64), p.splits);
+    profiler_begin(e.prof, KC_FP32, e.s, 2.0 * N * H * W * Cout * Cin * p.taps, 0);
+    f32_wgrad_kernel<<<grid, 256, 0, e.s>>>(static_cast<const float*>(dy), static_cast<const float*>(a), part, N, H, W, Cout, Cin, ks, 1, H, W);
+    profiler_end(e.prof, KC_FP32, e.s);
     const long long total = 1LL * Cout * Cin * p.taps;
     wgrad_reduce_kernel<<<grid_for(total), 256, 0, e.s>>>(part, dw, p.batches, Cout, Cin, p.taps, accumulate);
     VT_CUDA(cudaGetLastError());
@@ -883,33 +721,16 @@ int bwd_conv_s2_dgrad(const BwdEnv& e, const void* dy, const float* w, void* wd_
     }
     return 0;
 }
-// 16-bit mode: planes_x = the four parity planes of the conv input in the OUTPUT geometry, three shifted copies each
-// ([par][3][Cin][rowlen], bwd_pack_plane_strided), dy_plane = plane of the output gradient
+// fp32 verification mode (the 16-bit mode reads the stride-2 parity view straight from the input: bwd_conv_wgrad16)
 int bwd_conv_s2_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const void* x, float* part, float* dw, int N, int Hi,
                       int Wi, int Cout, int Cin, int accumulate) {
     const int Ho = Hi / 2, Wo = Wi / 2;
-    if (e.fp32) {
-        dim3 grid(Cout / 64, 9 * (Cin / 64), p.splits);
-        profiler_begin(e.prof, KC_FP32, e.s, 2.0 * N * Ho * Wo * Cout * Cin * 9.0, 0);
-        f32_wgrad_kernel<<<grid, 256, 0, e.s>>>(static_cast<const float*>(dy), static_cast<const float*>(x), part, N, Ho, Wo, Cout,
-                                               Cin, 3, 2, Hi, Wi);
-        profiler_end(e.prof, KC_FP32, e.s);
-    } else {
-        for (int tap = 0; tap < 9; ++tap) {
-            const int ky = tap / 3, kx = tap % 3;
-            const int par = (ky & 1) * 2 + (kx & 1), dyo = ky >> 1, dxo = kx >> 1;
-            GemmOp g;
-            g.A = dy;
-            g.B = static_cast<const bf16*>(x) + (static_cast<long long>(par) * 3 + (dxo + 1)) * Cin * p.rowlen;
-            g.batch = p.batches; g.M = Cout; g.N = Cin; g.K = static_cast<int>(p.Ks);
-            g.lda = p.rowlen; g.ldb = p.rowlen; g.a_bstride = p.Ks; g.b_bstride = p.Ks;
-            g.a_kdim = p.rowlen; g.b_kdim = p.rowlen;
-            g.a_k0 = p.G; g.b_k0 = p.G + 1LL * dyo * p.Wp;
-            g.out = part + 1LL * tap * Cin; g.out_fmt = FMT_F32; g.ld_out = 9LL * Cin; g.out_bstride = 1LL * Cout * 9 * Cin;
-            g.ab_f16 = 0; g.kclass = KC_BWD;
-            VT_TRY(launch_gemm(g, e.s, e.prof));
-        }
-    }
+    VT_CHECK(e.fp32, "bwd_conv_s2_wgrad is the fp32 verification path (16-bit mode: bwd_conv_wgrad16 with stride 2)");
+    dim3 grid(Cout / 64, 9 * (Cin / 64), p.splits);
+    profiler_begin(e.prof, KC_FP32, e.s, 2.0 * N * Ho * Wo * Cout * Cin * 9.0, 0);
+    f32_wgrad_kernel<<<grid, 256, 0, e.s>>>(static_cast<const float*>(dy), static_cast<const float*>(x), part, N, Ho, Wo, Cout,
+                                           Cin, 3, 2, Hi, Wi);
+    profiler_end(e.prof, KC_FP32, e.s);
     wgrad_reduce_kernel<<<grid_for(9LL * Cout * Cin), 256, 0, e.s>>>(part, dw, p.batches, Cout, Cin, 9, accumulate);
     VT_CUDA(cudaGetLastError());
     return 0;

@@ -29,25 +29,12 @@ int bwd_pack_dgrad_weight(const BwdEnv& e, const float* w /*[Cout][Cin][ks][ks] 
 int bwd_conv_dgrad(const BwdEnv& e, const void* dy, const void* wd, void* dx, const void* add, int N, int H, int W,
                    int Cout, int Cin, int ks);
 
-// weight gradient of a stride-1 conv
+// weight gradient, fp32 verification mode (FFMA, straight from the NHWC fp32 tensors; a = the conv's actual input)
 struct WgradPlan {
     int taps, splits, batches;
-    int Wp;                          // padded plane width (16-bit mode)
-    long long Ks, Kimg, G, rowlen;   // K range per GEMM batch, plane length per image, guard, row length (elements)
-    size_t a_bytes, b_bytes;         // operand planes of the output gradient / of the conv input
     size_t part_bytes;               // fp32 split-K partial tiles
 };
 WgradPlan bwd_wgrad_plan(const BwdEnv& e, int N, int H, int W, int Cout, int Cin, int ks);
-// 16-bit mode: NHWC tensor -> bf16 operand plane (optionally through GroupNorm(+SiLU) given the tensor's statistics).
-// copies = 3: the input of a 3x3 conv -- three planes shifted by dx = -1, 0, +1 pixels ([3][C][rowlen]; TMA start
-// coordinates must be 16-byte aligned in the innermost dimension, so a one-pixel tap cannot be a coordinate offset)
-int bwd_pack_plane(const BwdEnv& e, const WgradPlan& p, const void* src, int src_fmt, void* dst, const double* stats,
-                   const float* gamma, const float* beta, int N, int H, int W, int C, float eps, int silu, int copies);
-int bwd_pack_plane_strided(const BwdEnv& e, const WgradPlan& p, const void* src, int src_fmt, void* dst, const double* stats,
-                           const float* gamma, const float* beta, int N, int H, int W, int C, float eps, int silu, int copies,
-                           int sstride, int spy, int spx, int Hs, int Ws);
-// dw[Cout][Cin][ks][ks] (+)= sum_p dy[p][co] a[p + tap][ci].  16-bit mode: dy / a are operand planes; fp32 mode:
-// the NHWC fp32 tensors themselves (a = the conv's actual input).
 int bwd_conv_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const void* a, float* part, float* dw, int N, int H,
                    int W, int Cout, int Cin, int ks, int accumulate);
 

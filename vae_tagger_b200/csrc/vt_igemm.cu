@@ -412,13 +412,11 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     P.bias = op.bias; P.residual = op.residual; P.res_fp32 = op.residual_fp32; P.out = op.out; P.ld_out = ldo;
     P.out_bstride = op.out_bstride ? op.out_bstride : 1LL * op.M * ldo; P.stats = op.stats;
     P.num_slabs = 1;
-    VT_CHECK(op.a_k0 > -(1LL << 30) && op.a_k0 < (1LL << 30) && op.b_k0 > -(1LL << 30) && op.b_k0 < (1LL << 30),
-             "GEMM K offsets out of range");
-    P.slabs[0] = IgemmSlab{0, static_cast<int>(op.a_k0), 0, 0, 0, static_cast<int>(op.b_k0), op.K / 64, op.ab_f16};
+    P.slabs[0] = IgemmSlab{0, 0, 0, 0, 0, 0, op.K / 64, op.ab_f16};
 
     CUtensorMap a, b;
     {
-        uint64_t dims[5] = {static_cast<uint64_t>(op.a_kdim ? op.a_kdim : op.K), static_cast<uint64_t>(op.M), 1, 1,
+        uint64_t dims[5] = {static_cast<uint64_t>(op.K), static_cast<uint64_t>(op.M), 1, 1,
                             static_cast<uint64_t>(op.a_batched ? op.batch : 1)};
         const uint64_t abs_ = 2ull * (op.a_bstride ? op.a_bstride : lda * op.M);
         uint64_t str[4] = {2ull * lda, abs_, abs_, abs_};
@@ -427,7 +425,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     }
     {
         const int brows = op.b_rows > 0 ? op.b_rows : op.N;  // rows beyond brows: TMA out-of-bounds zero fill
-        uint64_t dims[3] = {static_cast<uint64_t>(op.b_kdim ? op.b_kdim : op.K), static_cast<uint64_t>(brows),
+        uint64_t dims[3] = {static_cast<uint64_t>(op.K), static_cast<uint64_t>(brows),
                             static_cast<uint64_t>(op.b_batched ? op.batch : 1)};
         uint64_t str[2] = {2ull * ldb, 2ull * (op.b_bstride ? op.b_bstride : ldb * brows)};
         uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};

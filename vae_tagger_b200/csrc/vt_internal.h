@@ -157,10 +157,6 @@ struct GemmOp {
     int a_batched = 1, b_batched = 1;
     long long lda = 0, ldb = 0;              // row strides in elements (default K)
     long long a_bstride = 0, b_bstride = 0;  // batch strides in elements (default rows * ld)
-    // tcgen05 path: the K range of a batch starts at element a_k0 / b_k0 of its rows (any integer: TMA coordinates need
-    // no alignment) and rows are a_kdim / b_kdim elements long (default K) -- a weight-gradient GEMM reads an
-    // activation row shifted by a tap offset relative to the gradient row (vt_backward.cu)
-    long long a_k0 = 0, b_k0 = 0, a_kdim = 0, b_kdim = 0;
     int kclass = -1;   // profiler class of the launch (default KC_IGEMM)
     const float* bias = nullptr;
     const void* residual = nullptr;
