@@ -112,7 +112,8 @@ def _encoder_pair(seed=0):
     return oracle, vae.cuda()
 
 
-@pytest.mark.parametrize("prec,n,h,w", [("fp32", 2, 64, 64), ("bf16", 2, 64, 64), ("bf16", 1, 96, 160), ("fp32", 1, 32, 48)])
+@pytest.mark.parametrize("prec,n,h,w", [("fp32", 2, 64, 64), ("bf16", 2, 64, 64), ("bf16", 1, 96, 160), ("fp32", 1, 32, 48),
+                                        ("bf16", 2, 256, 256)])   # 256^2: many pixel patches per CTA, several K splits
 def test_encoder_backward_matches_autograd(prec, n, h, w):
     from oracle.encoder import structured_images, synthetic_images
     oracle, vae = _encoder_pair()
@@ -178,7 +179,7 @@ def test_three_forwards_then_one_backward():
 # AutoencoderKL.decode in train() mode, against autograd on the oracle decoder -- every parameter gradient and
 # d loss / d latent (the path the reconstruction MSE takes back into the encoder, train_vae.py:124-186).
 @pytest.mark.parametrize("prec,n,lh,lw,scale_shift", [("fp32", 2, 8, 8, False), ("bf16", 2, 8, 8, True), ("bf16", 1, 12, 20, False),
-                                                      ("fp32", 1, 4, 6, True)])
+                                                      ("fp32", 1, 4, 6, True), ("bf16", 1, 32, 32, True)])
 def test_decoder_backward_matches_autograd(prec, n, lh, lw, scale_shift):
     from oracle.decoder import make_oracle_decoder, oracle_wrapper_decode
     from vae_tagger_b200 import diffusers_vae_loader as L
@@ -217,3 +218,25 @@ def test_decoder_backward_matches_autograd(prec, n, lh, lw, scale_shift):
     print(f"decoder backward {prec} {n}x{lh}x{lw}: worst {worst} {errs[worst]:.3e}, latent {errs['latent']:.3e}, "
           f"median {sorted(errs.values())[len(errs) // 2]:.3e}", file=__import__("sys").stderr)
     assert errs[worst] < bar, {k: v for k, v in errs.items() if v >= bar}
+
+
+def test_forwards_without_backward_do_not_leak_tape_slots():
+    """A train()-mode forward whose graph is dropped (a loss that is only logged) gives its tape slot back: more such
+    forwards than the context has slots must keep working, and a later forward + backward is still correct."""
+    from oracle.encoder import structured_images
+    from vae_tagger_b200 import _native as NV
+    oracle, vae = _encoder_pair()
+    vae.precision = "fp32"
+    vae.train()
+    x = structured_images(1, 32, 32, seed=9).cuda()
+    for _ in range(NV.MAX_TAPES + 3):
+        post = vae.encode(x).latent_dist
+        assert post.mean.requires_grad
+        del post
+    for p in oracle.parameters():
+        p.grad = None
+    oracle.train()
+    oracle.encode(x.cpu()).latent_dist.mean.square().sum().backward()
+    vae.encode(x).latent_dist.mean.square().sum().backward()
+    k = "down_blocks.0.resnets.0.conv1.weight"
+    assert rel(dict(vae.encoder.named_parameters())[k].grad, dict(oracle.encoder.named_parameters())[k].grad) < FP32_TOL

@@ -153,6 +153,24 @@ class DiagonalGaussianDistribution:
         return 0.5 * torch.sum(self.mean.pow(2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
 
 
+class _TapeSlot:
+    """Owns one tape slot of the native context for the lifetime of an autograd graph node: the slot goes back to the
+    pool when the backward has consumed it OR when the graph is dropped without a backward (a forward in ``train()``
+    mode whose loss is never back-propagated must not leak one of the context's ``MAX_TAPES`` slots)."""
+
+    def __init__(self, vae, pool):
+        self.vae, self.pool = vae, pool
+        self.slot = vae._take_tape_slot(pool)
+
+    def release(self):
+        if self.slot is not None:
+            self.vae._free_tape_slot(self.slot, self.pool)
+            self.slot = None
+
+    def __del__(self):
+        self.release()
+
+
 class _EncodeTrainFn(torch.autograd.Function):
     """``encoder(x) -> (mean, logvar)`` with the native training forward / backward (what autograd does
     for the reference in train_full.py:201-256 / train_vae.py:124-186).  The activations stay inside the native context
@@ -161,7 +179,8 @@ class _EncodeTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vae, x, *params):
         nctx = vae._sync_native(x.device)
-        slot = vae._take_tape_slot()
+        ctx.tape = _TapeSlot(vae, "_tape_slots")
+        slot = ctx.tape.slot
         mean, logvar = nctx.encode_train(x, precision=vae._precision(), slot=slot)
         ctx.vae, ctx.nctx, ctx.slot = vae, nctx, slot
         ctx.names = [n for n, _ in vae.encoder.named_parameters()]
@@ -183,7 +202,7 @@ class _EncodeTrainFn(torch.autograd.Function):
                 g.zero_()
         else:
             ctx.nctx.encoder_backward(g_mean, g_logvar, grads, slot=ctx.slot, accumulate=False)
-        ctx.vae._free_tape_slot(ctx.slot)
+        ctx.tape.release()
         return (None, None) + tuple(grads[n].to(params[n].dtype) for n in ctx.names)
 
 
@@ -195,7 +214,8 @@ class _DecodeTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vae, apply_scale_shift, z, *params):
         nctx = vae._sync_native_decoder(z.device)
-        slot = vae._take_tape_slot("_dtape_slots")
+        ctx.tape = _TapeSlot(vae, "_dtape_slots")
+        slot = ctx.tape.slot
         img = nctx.decode_train(z, precision=vae._precision(), apply_scale_shift=apply_scale_shift, slot=slot)
         ctx.vae, ctx.nctx, ctx.slot = vae, nctx, slot
         ctx.names = [n for n, _ in vae.decoder.named_parameters()]
@@ -207,7 +227,7 @@ class _DecodeTrainFn(torch.autograd.Function):
         params = dict(ctx.vae.decoder.named_parameters())
         grads = {n: torch.empty_like(params[n], dtype=torch.float32) for n in ctx.names}
         gz = ctx.nctx.decoder_backward(g_img, grads, want_latent_grad=ctx.needs_input_grad[2], slot=ctx.slot)
-        ctx.vae._free_tape_slot(ctx.slot, "_dtape_slots")
+        ctx.tape.release()
         return (None, None, None if gz is None else gz.to(ctx.z_dtype)) + tuple(grads[n].to(params[n].dtype) for n in ctx.names)
 
 
