@@ -2,6 +2,7 @@
 // table for each conv / GEMM and launches igemm_kernel<BLOCK_N>.
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "vt_conv3.cuh"
@@ -76,15 +77,30 @@ static int num_sms() {
     return n;
 }
 
-template <int BLOCK_N, int MT>
+template <int BLOCK_N, int MT, bool PAIR>
 static int launch_variant(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const IgemmParams& P,
                           cudaStream_t stream) {
-    using Cfg = IgemmCfg<BLOCK_N, MT>;
+    using Cfg = IgemmCfg<BLOCK_N, MT, PAIR>;
     static SmemAttrOnce once;
-    VT_TRY(ensure_dyn_smem(once, igemm_kernel<BLOCK_N, MT>, Cfg::SMEM_BYTES));
+    VT_TRY(ensure_dyn_smem(once, igemm_kernel<BLOCK_N, MT, PAIR>, Cfg::SMEM_BYTES));
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y * P.n_blocks;
-    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    igemm_kernel<BLOCK_N, MT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, P);
+    int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    if (!PAIR) {
+        igemm_kernel<BLOCK_N, MT, PAIR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, P);
+    } else {
+        grid &= ~1;   // whole clusters of two CTAs (the tile count is even: dispatch() checked)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(Cfg::THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        VT_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<BLOCK_N, MT, PAIR>, a0, a1, b, P));
+    }
     VT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -99,12 +115,29 @@ static int pick_block_n(int n_total) {
 // every weight chunk: same bytes per flop as the 128x256 tile), 128 x 32 for conv_out.
 static int pick_mt(int block_n) { return block_n == 128 ? 2 : 1; }
 
+static bool pairing_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VT_B200_NO_PAIR");
+        v = !(e && e[0] == '1');
+    }
+    return v != 0;
+}
+
+// CTA pairs (cta_group::2) whenever the pixel tiles of an image pair up: two neighbouring tiles of the same image and
+// n-block share every weight chunk, each CTA streaming half of it
+static bool igemm_pair_ok(int block_n, const IgemmParams& P) {
+    return pairing_enabled() && block_n != 32 && ((P.tiles_x * P.tiles_y) % 2 == 0);
+}
+// `pair`: the caller built the B tensor map with a box of block_n / 2 rows (each CTA loads its half)
 static int dispatch(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                    const IgemmParams& P, cudaStream_t stream) {
+                    const IgemmParams& P0, cudaStream_t stream, bool pair) {
+    IgemmParams P = P0;
+    P.pair = pair ? 1 : 0;
     switch (block_n) {
-        case 256: return launch_variant<256, 1>(a0, a1, b, P, stream);
-        case 128: return launch_variant<128, 2>(a0, a1, b, P, stream);
-        case 32: return launch_variant<32, 1>(a0, a1, b, P, stream);
+        case 256: return pair ? launch_variant<256, 1, true>(a0, a1, b, P, stream) : launch_variant<256, 1, false>(a0, a1, b, P, stream);
+        case 128: return pair ? launch_variant<128, 2, true>(a0, a1, b, P, stream) : launch_variant<128, 2, false>(a0, a1, b, P, stream);
+        case 32: return launch_variant<32, 1, false>(a0, a1, b, P, stream);
     }
     set_error("unsupported BLOCK_N");
     return -2;
@@ -219,6 +252,7 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     }
     P.num_slabs = ns;
 
+    const bool pair = igemm_pair_ok(block_n, P);
     CUtensorMap a0, a1, b;
     VT_TRY(make_act_map(&a0, op.in, op.N, op.Hin, op.Win, op.Cin, op.stride, P.tw, P.th * mt));
     if (op.sc_in) VT_TRY(make_act_map(&a1, op.sc_in, op.N, Hout, Wout, op.Cs, 1, P.tw, P.th * mt));
@@ -226,7 +260,7 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     {
         uint64_t dims[3] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(op.Cout), 1};
         uint64_t str[2] = {2ull * Ktot, 2ull * Ktot * op.Cout};
-        uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
+        uint32_t box[3] = {64, static_cast<uint32_t>(pair ? block_n / 2 : block_n), 1};
         VT_TRY(make_tmap(&b, op.w, 3, dims, str, box));
     }
     const double flops = 2.0 * op.N * Hout * Wout * static_cast<double>(op.Cout) * Ktot;
@@ -234,7 +268,7 @@ int launch_conv(const ConvOp& op, cudaStream_t stream, Profiler* prof) {
     VT_TRY(bind_stats(P, op.stats_ws));
     const KernelClass kc = op.kclass >= 0 ? static_cast<KernelClass>(op.kclass) : KC_IGEMM;
     profiler_begin(prof, kc, stream, flops, bytes);
-    int rc = dispatch(block_n, a0, a1, b, P, stream);
+    int rc = dispatch(block_n, a0, a1, b, P, stream, pair);
     profiler_end(prof, kc, stream);
     VT_TRY(rc);
     return finish_stats(P, stream, prof);
@@ -414,6 +448,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     P.num_slabs = 1;
     P.slabs[0] = IgemmSlab{0, 0, 0, 0, 0, 0, op.K / 64, op.ab_f16};
 
+    const bool pair = igemm_pair_ok(block_n, P);
     CUtensorMap a, b;
     {
         uint64_t dims[5] = {static_cast<uint64_t>(op.K), static_cast<uint64_t>(op.M), 1, 1,
@@ -428,7 +463,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
         uint64_t dims[3] = {static_cast<uint64_t>(op.K), static_cast<uint64_t>(brows),
                             static_cast<uint64_t>(op.b_batched ? op.batch : 1)};
         uint64_t str[2] = {2ull * ldb, 2ull * (op.b_bstride ? op.b_bstride : ldb * brows)};
-        uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
+        uint32_t box[3] = {64, static_cast<uint32_t>(pair ? block_n / 2 : block_n), 1};
         VT_TRY(make_tmap(&b, op.B, 3, dims, str, box));
     }
     // the epilogue addresses out as ((img*H + y)*W + x)*ld_out: batch stride is M*ld_out
@@ -438,7 +473,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, Profiler* prof) {
     VT_TRY(bind_stats(P, op.stats_ws));
     const KernelClass kc = op.kclass >= 0 ? static_cast<KernelClass>(op.kclass) : KC_IGEMM;
     profiler_begin(prof, kc, stream, flops, bytes);
-    int rc = dispatch(block_n, a, a, b, P, stream);
+    int rc = dispatch(block_n, a, a, b, P, stream, pair);
     profiler_end(prof, kc, stream);
     VT_TRY(rc);
     return finish_stats(P, stream, prof);

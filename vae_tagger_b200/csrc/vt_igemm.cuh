@@ -83,11 +83,17 @@ struct IgemmParams {
     int pair;                // CTA-pair kernel: tile index = ((pixel-pair * n_blocks + n-block) * 2 + cluster rank)
 };
 
-template <int BLOCK_N, int MT>  // MT = 128-row sub-tiles per CTA tile (2: two pixel tiles share every weight chunk)
+// MT = 128-row sub-tiles per CTA tile (2: two pixel tiles share every weight chunk).
+// PAIR: two CTAs with neighbouring pixel tiles form a cluster and run every MMA as one tcgen05.mma.cta_group::2
+// (M = 256: 128 rows per CTA); the B tile is split across the pair, so each CTA streams and reads only half of it
+// (shared-memory data pipe: 12 -> 8 KB per 128x256x16 MMA, 8 -> 6 KB per 128x128x16).
+template <int BLOCK_N, int MT, bool PAIR = false>
 struct IgemmCfg {
     static constexpr int kBlockN = BLOCK_N, kMT = MT;
+    static constexpr bool kPair = PAIR;
     static constexpr int A_BYTES = MT * IGEMM_A_BYTES;
-    static constexpr int B_BYTES = BLOCK_N * IGEMM_BLOCK_K * 2;
+    static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;
+    static constexpr int B_BYTES = B_ROWS * IGEMM_BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, splitting the columns)
     // 128-column tiles have few K chunks per tile (level 0, conv_in): their epilogue is on the critical
@@ -101,7 +107,10 @@ struct IgemmCfg {
     static constexpr int EPI_STAGING_BYTES = EPI_WARPS * 32 * STAGE_ROW_FLOATS * 4;
     // the epilogue is latency bound (one dependent chain per warp): two warps per scheduler are worth more
     // than a fourth operand stage, which is what their staging tiles cost
-    static constexpr int STAGES = (STAGE_BYTES >= 48 * 1024) ? (EPI_WARPS == 8 ? 3 : 4) : (STAGE_BYTES >= 32 * 1024 ? 5 : 8);
+    static constexpr int STAGES_SOLO = (STAGE_BYTES >= 48 * 1024) ? (EPI_WARPS == 8 ? 3 : 4) : (STAGE_BYTES >= 32 * 1024 ? 5 : 8);
+    // pair kernels have smaller stages (half a B tile): as many as fit next to the epilogue staging, at most six
+    static constexpr int STAGES_FIT = (227 * 1024 - EPI_STAGING_BYTES - 4096 - 1024) / STAGE_BYTES;
+    static constexpr int STAGES = PAIR ? (STAGES_FIT < 6 ? STAGES_FIT : 6) : STAGES_SOLO;
     static constexpr int ACC_COLS = MT * BLOCK_N;  // TMEM columns of one accumulator set
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
                                      : (2 * ACC_COLS <= 256) ? 256 : 512;
@@ -421,11 +430,11 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, float* stag
     }
 }
 
-template <int BLOCK_N, int MT>
-__global__ void __launch_bounds__(IgemmCfg<BLOCK_N, MT>::THREADS, 1)
+template <int BLOCK_N, int MT, bool PAIR = false>
+__global__ void __launch_bounds__(IgemmCfg<BLOCK_N, MT, PAIR>::THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ IgemmParams P) {
-    using Cfg = IgemmCfg<BLOCK_N, MT>;
+    using Cfg = IgemmCfg<BLOCK_N, MT, PAIR>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int EPI_WARPS = Cfg::EPI_WARPS;
 
@@ -441,6 +450,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // pair kernels: rank 0 (leader) issues every MMA
 
     const uint32_t tiles_per_img = static_cast<uint32_t>(P.tiles_x * P.tiles_y);
     const uint32_t total_tiles = static_cast<uint32_t>(P.NB) * tiles_per_img * static_cast<uint32_t>(P.n_blocks);
@@ -455,16 +465,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], EPI_WARPS);
+            mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * EPI_WARPS);   // pair: both CTAs' epilogue warps, on the leader
         }
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (PAIR) { tmem_alloc_pair(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // the peer's barriers exist before any remote arrive / TMA signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -474,8 +485,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             int stage = 0;
             uint32_t phase = 0;
             for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nb = static_cast<int>(tile % static_cast<uint32_t>(P.n_blocks));
-                uint32_t m = tile / static_cast<uint32_t>(P.n_blocks);
+                // pair kernels number the tiles ((pixel-pair * n_blocks + n-block) * 2 + rank): blockIdx.x + k * gridDim.x
+                // (gridDim.x even) keeps the rank, and the two CTAs of a cluster walk the same (pixel-pair, n-block) sequence
+                const uint32_t tq = PAIR ? (tile >> 1) : tile;
+                const int nb = static_cast<int>(tq % static_cast<uint32_t>(P.n_blocks));
+                uint32_t m = tq / static_cast<uint32_t>(P.n_blocks);
+                if (PAIR) m = 2u * m + (tile & 1u);
                 const int tx = static_cast<int>(m % static_cast<uint32_t>(P.tiles_x));
                 m /= static_cast<uint32_t>(P.tiles_x);
                 const int ty = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
@@ -488,11 +503,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                         uint8_t* sb = sa + Cfg::A_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                        tma_load_5d(sa, mapA, &full_bar[stage], sl.c_base + cc * IGEMM_BLOCK_K, x0 + sl.dx, sl.p,
-                                    y0 + sl.dy, P.a_batched ? img : 0);
-                        tma_load_3d(sb, &tmB, &full_bar[stage], sl.kb_base + cc * IGEMM_BLOCK_K, n0,
-                                    P.b_batched ? img : 0);
+                        if constexpr (PAIR) {
+                            // both CTAs' A tiles and B halves are counted on the leader's barrier
+                            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                            tma_load_5d_pair(sa, mapA, &full_bar[stage], sl.c_base + cc * IGEMM_BLOCK_K, x0 + sl.dx, sl.p,
+                                             y0 + sl.dy, P.a_batched ? img : 0);
+                            tma_load_3d_pair(sb, &tmB, &full_bar[stage], sl.kb_base + cc * IGEMM_BLOCK_K,
+                                             n0 + static_cast<int>(rank) * Cfg::B_ROWS, P.b_batched ? img : 0);
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                            tma_load_5d(sa, mapA, &full_bar[stage], sl.c_base + cc * IGEMM_BLOCK_K, x0 + sl.dx, sl.p,
+                                        y0 + sl.dy, P.a_batched ? img : 0);
+                            tma_load_3d(sb, &tmB, &full_bar[stage], sl.kb_base + cc * IGEMM_BLOCK_K, n0,
+                                        P.b_batched ? img : 0);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -503,9 +527,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         // ------------------------------------------------------------ MMA issuer
         // The whole warp walks the loops (warp-uniform control flow keeps the descriptors in uniform
         // registers); one elected lane issues the MMAs and commits.
-        {
-            constexpr uint32_t idesc_bf16 = umma_idesc_16(IGEMM_BLOCK_M, BLOCK_N, false);
-            constexpr uint32_t idesc_f16 = umma_idesc_16(IGEMM_BLOCK_M, BLOCK_N, true);
+        if (rank == 0) {
+            constexpr uint32_t idesc_bf16 = umma_idesc_16(PAIR ? 256 : IGEMM_BLOCK_M, BLOCK_N, false);
+            constexpr uint32_t idesc_f16 = umma_idesc_16(PAIR ? 256 : IGEMM_BLOCK_M, BLOCK_N, true);
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accum) {
+                if constexpr (PAIR) umma_f16_ss_pair(d, a, b, id, accum);
+                else umma_bf16_ss(d, a, b, id, accum);
+            };
+            auto commit = [&](uint64_t* bar) {
+                if constexpr (PAIR) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
             const uint64_t da_base = umma_desc_k_sw128(smem_u32(smem));                  // stage 0, sub-tile 0
             const uint64_t db_base = umma_desc_k_sw128(smem_u32(smem) + Cfg::A_BYTES);   // stage 0
             int stage = 0;
@@ -531,18 +563,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 #pragma unroll
                                 for (int t = 0; t < MT; ++t) {
                                     // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
-                                    umma_bf16_ss(tmem_d + t * BLOCK_N, da_base + so + (t * (IGEMM_A_BYTES >> 4) + 2 * k),
-                                                 db_base + so + 2 * k, idesc, first | k);
+                                    mma(tmem_d + t * BLOCK_N, da_base + so + (t * (IGEMM_A_BYTES >> 4) + 2 * k),
+                                        db_base + so + 2 * k, idesc, first | k);
                                 }
                             }
-                            umma_commit(&empty_bar[stage]);
+                            commit(&empty_bar[stage]);
                         }
                         __syncwarp();
                         first = 1;
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
-                if (elect_one()) umma_commit(&tfull_bar[acc]);
+                if (elect_one()) commit(&tfull_bar[acc]);
                 __syncwarp();
             }
         }
@@ -572,9 +604,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // neither CTA leaves while the pair still signals / computes
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
