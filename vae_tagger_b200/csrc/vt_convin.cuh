@@ -5,13 +5,18 @@
 // So the A operand is BUILT in shared memory: four gather warps stage the three image rows a tile
 // touches as fp16, then every thread writes the 32-value patch of two pixels straight into the
 // 128-byte-swizzled operand rows the tensor core reads.  The weights ([128][64] fp16, k >= 27 zero)
-// stay resident in shared memory; two K=16 MMAs per 128-pixel sub-tile; the epilogue (bias, GroupNorm
-// partial sums of the output, bf16 pack, stores) is the implicit-GEMM one.
+// stay resident in shared memory; two K=16 MMAs per 128-pixel sub-tile.
 //
-// What bounds it (ncu source page, round 2): instruction issue in the epilogue -- ~480 warp instructions per 32x32
-// output chunk (alpha/bias FFMA, GroupNorm sum / sum-of-squares, 16-bit pack / unpack, predicates and address
-// arithmetic) against 27 MACs per output element on the tensor core; neither loading the image one tile ahead nor
-// sixteen epilogue warps instead of eight moved it (both tried and reverted).
+// Round 1/2 used the shared implicit-GEMM epilogue here and ncu showed the kernel bound by instruction issue in it
+// (~480 warp instructions per 32x32 output chunk: staging round trip, alpha / bias FFMA, 16-bit pack / unpack, address
+// arithmetic and predicates of the general output geometry).  The epilogue below is specific to this kernel:
+//   * the bias rides on the tensor core: k = 27 and 28 of every operand row are 1.0 and the weight rows carry
+//     fp16(bias) and fp16(bias - fp16(bias)) there (patched into the resident weight tile), so the accumulator
+//     already holds conv + bias to ~2^-22;
+//   * one lane owns one pixel x 64 channels straight out of TMEM: GroupNorm partial sums are accumulated in registers
+//     over the tile and folded across lanes once per tile by a 31-shuffle transposing reduction;
+//   * the 16-bit tile leaves through a swizzled 4 KB staging buffer and ONE TMA store per 32 pixels x 64 channels
+//     (cp.async.bulk.tensor, S2G): no staging read-back, no store instructions, ragged widths clipped by the map.
 //
 // Tile = 256 consecutive pixels of one image row (two 128-row sub-tiles) x 128 output channels.
 // Algorithmic HBM traffic per image: 3*H*W*4 B read + H*W*128*2 B written (the 64-wide patch matrix the
@@ -29,20 +34,116 @@ struct ConvInCfg {
     static constexpr int A_STAGE = 2 * IGEMM_A_BYTES;  // two sub-tiles of 128 rows x 128 B
     static constexpr int STAGES = 3;
     static constexpr int B_BYTES = 128 * 128;          // 128 output channels x 64 k (fp16)
-    static constexpr int STRIP_W = 264;                // 258 columns used: x0-1 .. x0+256
+    static constexpr int STRIP_W = 264;                // columns x0-1 .. x0+256 at index 3 .. 260 (x0 at 4: 8-byte aligned)
     static constexpr int STRIP_BYTES = 9 * STRIP_W * 2;  // [kh][c][x] fp16
     static constexpr int STRIP_ALLOC = 2 * ((STRIP_BYTES + 127) / 128 * 128);
-    static constexpr int SMEM_BYTES = STAGES * A_STAGE + B_BYTES + Epi::EPI_STAGING_BYTES + STRIP_ALLOC + Epi::BAR_BYTES + 1024;
+    static constexpr int OUT_STAGING = Epi::EPI_WARPS * 2 * 4096;   // per epilogue warp: two 32 px x 64 ch 16-bit boxes
+    static constexpr int SMEM_BYTES = STAGES * A_STAGE + B_BYTES + OUT_STAGING + STRIP_ALLOC + Epi::BAR_BYTES + 1024;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct ConvInParams {
     const void* img;   // [N][3][H][W] fp32 in [-1,1]  or  [N][H][W][3] u8
     int in_fmt;        // 0 fp32 NCHW, 1 u8 NHWC (normalised (u/255 - 0.5)/0.5 on the fly)
+    int vec;           // fp32 rows may be read as aligned float4 (W % 4 == 0, 16-byte aligned base)
 };
 
+// Epilogue of one warp: accumulator rows 32q .. 32q+31 (pixels) x columns 64cg .. 64cg+63 (channels) of both sub-tiles.
+template <int OUT, bool STATS>
+__device__ __forceinline__ void convin_epilogue(const CUtensorMap* tmO, const IgemmParams& P, uint8_t* staging_all,
+                                                float* s_part, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                uint32_t tmem_base, uint32_t total_tiles, int warp, int lane) {
+    using Epi = ConvInCfg::Epi;
+    const int ew = warp - 2;
+    const int q = warp & 3;    // TMEM lane quadrant this warp may access
+    const int cg = ew >> 2;    // channel half
+    const int et = threadIdx.x - 64;
+    const uint32_t stg = smem_u32(staging_all + ew * 8192);
+    const int sw = lane & 7;   // 128-byte swizzle: 16-byte chunk index ^ (row & 7)
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int tx = static_cast<int>(tile % static_cast<uint32_t>(P.tiles_x));
+        const uint32_t m = tile / static_cast<uint32_t>(P.tiles_x);
+        const int y = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
+        const int img = static_cast<int>(m / static_cast<uint32_t>(P.tiles_y));
+        const uint32_t acc = it & 1;
+        mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * Epi::ACC_COLS + cg * 64 + (static_cast<uint32_t>(q * 32) << 16);
+        float st[32];          // [16 groups of 4 channels][sum, sum of squares] of this lane's two pixels
+#pragma unroll
+        for (int i = 0; i < 32; ++i) st[i] = 0.f;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+            uint32_t r[64];
+            tmem_ld_32x32(taddr + sub * 128, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+            tmem_ld_32x32(taddr + sub * 128 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+            tmem_ld_wait();
+            if (sub == 1) {    // this warp's part of the accumulator set is in registers: hand the TMEM buffer back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
+            const int x = tx * 256 + sub * 128 + q * 32;     // first pixel of this warp's 32
+            if (STATS && x + lane < P.W) {
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    const float a = __uint_as_float(r[4 * g]), b = __uint_as_float(r[4 * g + 1]);
+                    const float c = __uint_as_float(r[4 * g + 2]), d = __uint_as_float(r[4 * g + 3]);
+                    st[2 * g] += (a + b) + (c + d);
+                    st[2 * g + 1] = fmaf(a, a, fmaf(b, b, fmaf(c, c, fmaf(d, d, st[2 * g + 1]))));
+                }
+            }
+            // the store that last read this buffer (two stores ago) must have drained it
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            const uint32_t dst = stg + sub * 4096 + lane * 128;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    w[j] = pack16x2<OUT>(__uint_as_float(r[8 * k + 2 * j]), __uint_as_float(r[8 * k + 2 * j + 1]));
+                sts128(dst + ((k ^ sw) << 4), __uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]),
+                       __uint_as_float(w[3]));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (x < P.W) tma_store_3d(tmO, stg + sub * 4096, cg * 64, x, img * P.H + y);
+                bulk_commit();
+            }
+        }
+        if (STATS) {
+            // transposing reduction over the 32 lanes: after the five halving steps lane L holds entry L of st[]
+            // summed over all lanes (a fixed tree: the result does not depend on anything but the tile's values)
+#pragma unroll
+            for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    const float send = up ? st[i] : st[i + n];
+                    const float keep = up ? st[i + n] : st[i];
+                    st[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, off);
+                }
+            }
+            s_part[(acc * Epi::EPI_WARPS + ew) * 32 + lane] = st[0];
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * Epi::EPI_WARPS) : "memory");
+            if (et < 64) {     // 32 groups x (sum, sumsq): the four pixel quadrants added in a fixed order
+                const int g = et >> 1, which = et & 1;
+                const float* pv = s_part + (acc * Epi::EPI_WARPS + (g >> 4) * 4) * 32 + (g & 15) * 2 + which;
+                const float tot = ((pv[0] + pv[32]) + pv[64]) + pv[96];
+                const long long row = static_cast<long long>(img) * P.stats_rows + P.stats_row0 + (y * P.tiles_x + tx);
+                P.stats_part[(row * 32 + g) * 2 + which] = tot;
+            }
+        }
+    }
+    if (lane == 0) bulk_wait_all();   // the staging buffers must outlive the stores that read them
+}
+
 __global__ void __launch_bounds__(ConvInCfg::THREADS, 1)
-conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ IgemmParams P, const ConvInParams Q) {
+conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+               const __grid_constant__ IgemmParams P, const ConvInParams Q) {
     using Cfg = ConvInCfg;
     using Epi = ConvInCfg::Epi;
     constexpr int STAGES = Cfg::STAGES;
@@ -50,15 +151,17 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_b = smem + STAGES * Cfg::A_STAGE;
-    float* staging_all = reinterpret_cast<float*>(s_b + Cfg::B_BYTES);
-    __half* strips = reinterpret_cast<__half*>(s_b + Cfg::B_BYTES + Epi::EPI_STAGING_BYTES);
-    uint8_t* ctrl = s_b + Cfg::B_BYTES + Epi::EPI_STAGING_BYTES + Cfg::STRIP_ALLOC;
+    uint8_t* staging_all = s_b + Cfg::B_BYTES;            // 1024-byte aligned: the swizzle pattern follows the address
+    __half* strips = reinterpret_cast<__half*>(s_b + Cfg::B_BYTES + Cfg::OUT_STAGING);
+    uint8_t* ctrl = s_b + Cfg::B_BYTES + Cfg::OUT_STAGING + Cfg::STRIP_ALLOC;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);   // [STAGES]  128 gather threads arrive
     uint64_t* a_empty = a_full + STAGES;                    // [STAGES]  tcgen05.commit
     uint64_t* tfull_bar = a_empty + STAGES;                 // [2]
     uint64_t* tempty_bar = tfull_bar + 2;                   // [2]
-    uint64_t* b_full = tempty_bar + 2;                      // [1]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
+    uint64_t* b_full = tempty_bar + 2;                      // [1]  weight TMA landed
+    uint64_t* b_ready = b_full + 1;                         // [1]  bias columns patched in
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_ready + 1);
+    float* s_part = reinterpret_cast<float*>(ctrl + 256 + 1024);   // [2][EPI_WARPS][32] statistic partials
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -66,6 +169,7 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&a_full[i], 32 * Cfg::GATHER_WARPS);
             mbar_init(&a_empty[i], 1);
@@ -75,6 +179,7 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             mbar_init(&tempty_bar[i], Epi::EPI_WARPS);
         }
         mbar_init(b_full, 1);
+        mbar_init(b_ready, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -93,12 +198,28 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             tma_load_3d(s_b, &tmB, b_full, 0, 0, 0);
         }
         __syncwarp();
+        // bias as two more contraction terms: weight row n gets fp16(bias) at k = 27 and the fp16 remainder at k = 28
+        // (the gather warps put 1.0 there); element (n, k) of the swizzled tile = n*128 + ((k/8) ^ (n%8))*16 + (k%8)*2
+        mbar_wait(b_full, 0);
+        if (P.bias != nullptr) {
+            for (int n = lane; n < 128; n += 32) {
+                const float bv = __ldg(P.bias + n);
+                const __half hi = __float2half_rn(bv);
+                const __half lo = __float2half_rn(bv - __half2float(hi));
+                __half* rowp = reinterpret_cast<__half*>(s_b + n * 128 + ((3 ^ (n & 7)) << 4));
+                rowp[3] = hi;
+                rowp[4] = lo;
+            }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_ready);
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (warp-uniform loop)
         constexpr uint32_t idesc = umma_idesc_16(IGEMM_BLOCK_M, 128, true);
         const uint64_t da_base = umma_desc_k_sw128(smem_u32(smem));
         const uint64_t db = umma_desc_k_sw128(smem_u32(s_b));
-        mbar_wait(b_full, 0);
+        mbar_wait(b_ready, 0);
         int stage = 0;
         uint32_t phase = 0, it = 0;
         for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -125,13 +246,13 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         // output = raw activation: bf16, or fp16 (P.out_fmt)
         if (P.out_fmt == FMT_F16) {
             if (P.group_size != 0)
-                igemm_epilogue<Epi, FMT_F16, 0, true>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
+                convin_epilogue<FMT_F16, true>(&tmO, P, staging_all, s_part, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
             else
-                igemm_epilogue<Epi, FMT_F16, 0, false>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
+                convin_epilogue<FMT_F16, false>(&tmO, P, staging_all, s_part, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
         } else if (P.group_size != 0)
-            igemm_epilogue<Epi, FMT_BF16, 0, true>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
+            convin_epilogue<FMT_BF16, true>(&tmO, P, staging_all, s_part, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
         else
-            igemm_epilogue<Epi, FMT_BF16, 0, false>(P, staging_all, ctrl, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
+            convin_epilogue<FMT_BF16, false>(&tmO, P, staging_all, s_part, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
     } else {
         // ------------------------------------------------------------ gather warps: build the operand rows
         const int gt = threadIdx.x - (64 + 32 * Epi::EPI_WARPS);   // 0..127
@@ -140,18 +261,46 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         const long long plane = static_cast<long long>(P.H) * P.W;
         int stage = 0;
         uint32_t phase = 0, it = 0;
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        // image rows y-1 .. y+1, columns x0-1 .. x0+256, three channels of a tile: loaded into registers one tile
+        // AHEAD (the loads of tile t+1 are in flight while tile t's operand rows are built), then written to the
+        // fp16 strip [kh*3+c][x] of the tile
+        float v[27];
+        float4 vq[5];
+        unsigned char u[21];
+        const int c4 = gt & 63, rsel = gt >> 6;   // float4 path: column quad / row parity of this thread's units
+        auto coords = [&](uint32_t tile, int& x0, int& y, int& img) {
             const int tx = static_cast<int>(tile % static_cast<uint32_t>(P.tiles_x));
             const uint32_t m = tile / static_cast<uint32_t>(P.tiles_x);
-            const int y = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
-            const int img = static_cast<int>(m / static_cast<uint32_t>(P.tiles_y));
-            const int x0 = tx * 256;
-            __half* strip = strips + (it & 1) * (Cfg::STRIP_ALLOC / 4);
-            // ---- image rows y-1 .. y+1, columns x0-1 .. x0+256, three channels -> fp16 strip [kh*3+c][x]
-            // (all loads of a tile are issued before the first is used: one L2 round trip per tile, not one per element)
-            if (Q.in_fmt == 0) {
+            y = static_cast<int>(m % static_cast<uint32_t>(P.tiles_y));
+            img = static_cast<int>(m / static_cast<uint32_t>(P.tiles_y));
+            x0 = tx * 256;
+        };
+        auto load_tile = [&](uint32_t tile) {
+            int x0, y, img;
+            coords(tile, x0, y, img);
+            if (Q.in_fmt == 0 && Q.vec) {
+                // 9 rows x 64 aligned float4 (columns x0 .. x0+255) = 4.5 loads per thread, + the two edge columns
                 const float* src = static_cast<const float*>(Q.img) + 3LL * img * plane;
-                float v[27];
+                const int iplane = static_cast<int>(plane);
+                const bool xok = x0 + 4 * c4 < P.W;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int rowid = 2 * j + rsel;
+                    const int kh = (rowid * 11) >> 5, c = rowid - kh * 3;
+                    const int gy = y + kh - 1;
+                    const bool ok = xok && gy >= 0 && gy < P.H && (j < 4 || rsel == 0);
+                    vq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) vq[j] = __ldg(reinterpret_cast<const float4*>(src + (c * iplane + gy * P.W + x0 + 4 * c4)));
+                }
+                v[0] = 0.f;
+                if (gt >= 64 && gt < 82) {
+                    const int e = gt - 64, rowid = e >> 1;
+                    const int kh = (rowid * 11) >> 5, c = rowid - kh * 3;
+                    const int gy = y + kh - 1, gx = (e & 1) ? x0 + 256 : x0 - 1;
+                    if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) v[0] = __ldg(src + (c * iplane + gy * P.W + gx));
+                }
+            } else if (Q.in_fmt == 0) {
+                const float* src = static_cast<const float*>(Q.img) + 3LL * img * plane;
 #pragma unroll
                 for (int rowid = 0; rowid < 9; ++rowid) {
                     const int kh = rowid / 3, c = rowid - kh * 3;
@@ -166,16 +315,8 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                         v[rowid * 3 + part] = t;
                     }
                 }
-#pragma unroll
-                for (int rowid = 0; rowid < 9; ++rowid)
-#pragma unroll
-                    for (int part = 0; part < 3; ++part) {
-                        const int xx = gt + NG * part;
-                        if (xx < 258) strip[rowid * SW + xx] = __float2half_rn(v[rowid * 3 + part]);
-                    }
             } else {
                 const unsigned char* src = static_cast<const unsigned char*>(Q.img) + 3LL * img * plane;
-                unsigned char u[21];
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                     const int gy = y + kh - 1;
@@ -189,6 +330,34 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                         u[kh * 7 + part] = t;
                     }
                 }
+            }
+        };
+        auto store_strip = [&](uint32_t tile, __half* strip) {
+            if (Q.in_fmt == 0 && Q.vec) {
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    if (j == 4 && rsel != 0) break;
+                    const __half2 lo = __floats2half2_rn(vq[j].x, vq[j].y), hi = __floats2half2_rn(vq[j].z, vq[j].w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(strip + (2 * j + rsel) * SW + 4 + 4 * c4) = pk;
+                }
+                if (gt >= 64 && gt < 82) {
+                    const int e = gt - 64;
+                    strip[(e >> 1) * SW + ((e & 1) ? 260 : 3)] = __float2half_rn(v[0]);
+                }
+            } else if (Q.in_fmt == 0) {
+#pragma unroll
+                for (int rowid = 0; rowid < 9; ++rowid)
+#pragma unroll
+                    for (int part = 0; part < 3; ++part) {
+                        const int xx = gt + NG * part;
+                        if (xx < 258) strip[rowid * SW + xx + 3] = __float2half_rn(v[rowid * 3 + part]);
+                    }
+            } else {
+                int x0, y, img;
+                coords(tile, x0, y, img);
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                     const int gy = y + kh - 1;
@@ -198,10 +367,16 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                         const int b = gt + NG * part, xx = b / 3, c = b - xx * 3, gx = x0 + xx - 1;
                         const bool ok = y_ok && gx >= 0 && gx < P.W;
                         const float val = ok ? (static_cast<float>(u[kh * 7 + part]) / 255.0f - 0.5f) / 0.5f : 0.f;
-                        if (b < 774) strip[(kh * 3 + c) * SW + xx] = __float2half_rn(val);
+                        if (b < 774) strip[(kh * 3 + c) * SW + xx + 3] = __float2half_rn(val);
                     }
                 }
             }
+        };
+        if (blockIdx.x < total_tiles) load_tile(blockIdx.x);
+        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            __half* strip = strips + (it & 1) * (Cfg::STRIP_ALLOC / 4);
+            store_strip(tile, strip);
+            if (tile + gridDim.x < total_tiles) load_tile(tile + gridDim.x);
             asm volatile("bar.sync 3, %0;" ::"n"(NG) : "memory");
             mbar_wait(&a_empty[stage], phase ^ 1);
             // ---- two pixels per thread: k = (kh*3 + kw)*3 + c  ->  strip[kh*3 + c][x + kw]
@@ -215,8 +390,10 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                 for (int kp = 0; kp < 16; ++kp) {
                     uint32_t lo = 0, hi = 0;
                     const int k = 2 * kp;
-                    if (k < 27) lo = sp[((k / 9) * 3 + (k % 3)) * SW + px + (k / 3) % 3];
-                    if (k + 1 < 27) hi = sp[(((k + 1) / 9) * 3 + ((k + 1) % 3)) * SW + px + ((k + 1) / 3) % 3];
+                    if (k < 27) lo = sp[((k / 9) * 3 + (k % 3)) * SW + px + 3 + (k / 3) % 3];
+                    else if (k == 28) lo = 0x3C00u;          // 1.0: the bias terms (k = 27, 28)
+                    if (k + 1 < 27) hi = sp[(((k + 1) / 9) * 3 + ((k + 1) % 3)) * SW + px + 3 + ((k + 1) / 3) % 3];
+                    else if (k + 1 == 27) hi = 0x3C00u;
                     w[kp] = lo | (hi << 16);
                 }
                 const uint32_t row = sa + t * IGEMM_A_BYTES + gt * 128;

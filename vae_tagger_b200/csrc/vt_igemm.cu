@@ -297,7 +297,16 @@ int launch_conv_in(const ConvInOp& op, cudaStream_t stream, Profiler* prof) {
         uint32_t box[3] = {64, 128, 1};
         VT_TRY(make_tmap(&b, op.w, 3, dims, str, box));
     }
-    ConvInParams Q{op.img, op.in_fmt};
+    CUtensorMap o;   // output viewed as (channel, x, image row): the store clips pixels beyond the row end
+    {
+        uint64_t dims[3] = {128, static_cast<uint64_t>(op.W), static_cast<uint64_t>(op.N) * op.H};
+        uint64_t str[2] = {256, 256ull * op.W};
+        uint32_t box[3] = {64, 32, 1};
+        VT_TRY(make_tmap(&o, op.out, 3, dims, str, box));
+    }
+    VT_CHECK(3LL * op.H * op.W < (1LL << 31), "conv_in image exceeds 2^31 elements");
+    ConvInParams Q{op.img, op.in_fmt,
+                   (op.in_fmt == 0 && op.W % 4 == 0 && reinterpret_cast<uintptr_t>(op.img) % 16 == 0) ? 1 : 0};
     static SmemAttrOnce once;
     VT_TRY(ensure_dyn_smem(once, conv_in_kernel, ConvInCfg::SMEM_BYTES));
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y;
@@ -306,7 +315,7 @@ int launch_conv_in(const ConvInOp& op, cudaStream_t stream, Profiler* prof) {
     const double bytes = 1.0 * op.N * op.H * op.W * ((op.in_fmt ? 3.0 : 12.0) + 256.0);
     VT_TRY(bind_stats(P, op.stats_ws));
     profiler_begin(prof, KC_CONVIN, stream, flops, bytes);
-    conv_in_kernel<<<grid, ConvInCfg::THREADS, ConvInCfg::SMEM_BYTES, stream>>>(b, P, Q);
+    conv_in_kernel<<<grid, ConvInCfg::THREADS, ConvInCfg::SMEM_BYTES, stream>>>(b, o, P, Q);
     profiler_end(prof, KC_CONVIN, stream);
     VT_CUDA(cudaGetLastError());
     return finish_stats(P, stream, prof);
