@@ -3,8 +3,8 @@
 (oracle/decoder.py) on identical random-init weights.
 
 Tolerances (relative L2 of the image), the same bars as the encoder's: fp32 verification mode <= 1e-4;
-16-bit tensor-core mode <= 2e-2 (the decoder is ~2.5x deeper than the encoder -- 28 convs + attention between
-the latent and the image -- and its output is not squashed by a sigmoid)."""
+16-bit tensor-core mode <= 1e-2 (round 1, with bf16 raw activations, needed 2e-2 here -- the decoder is ~2.5x deeper than
+the encoder; with fp16 raw activations it meets the north-star bar itself)."""
 import sys
 
 import pytest
@@ -17,7 +17,7 @@ from vae_tagger_b200 import diffusers_vae_loader as L
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-4
-BF16_TOL = 2e-2
+BF16_TOL = 1e-2
 
 
 def rel(a, b):
