@@ -163,37 +163,61 @@ int launch_gn_stats(const void* x, int x_fmt, double* stats, int N, long long HW
 }
 
 // Second stage of the epilogue statistics (vt_igemm.cuh / vt_conv3.cuh): part[img][tile][G][2] fp32 per-tile
-// (sum, sumsq) -> stats[img][G][2] fp64.  One block per (image, group): thread (lane = t/2, which = t%2) adds
-// tiles lane, lane+64, ... in fp64, then a fixed-order tree over the 64 lanes.  The order depends on the tile
-// count only, so an image's statistics are the same bits in any batch.
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ part, double* __restrict__ stats,
-                                                          int tiles, int G) {
-    __shared__ double sh[128];
-    const int g = blockIdx.x, n = blockIdx.y;
-    const int which = threadIdx.x & 1, lane = threadIdx.x >> 1;
-    const float* p = part + (1LL * n * tiles * G + g) * 2 + which;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // four chains in flight; combined in a fixed order
-    int t = lane;
-    for (; t + 192 < tiles; t += 256) {
-        a0 += static_cast<double>(__ldg(p + 1LL * t * G * 2));
-        a1 += static_cast<double>(__ldg(p + 1LL * (t + 64) * G * 2));
-        a2 += static_cast<double>(__ldg(p + 1LL * (t + 128) * G * 2));
-        a3 += static_cast<double>(__ldg(p + 1LL * (t + 192) * G * 2));
+// (sum, sumsq) -> stats[img][G][2] fp64.  A tile row is 2G consecutive floats; a block of 1024 threads owns four
+// 16-byte column quads of one image x 256 row lanes: thread (quad, lane) adds rows lane, lane+256, ... in fp64 (all of
+// an 8-row batch of loads in flight at once; a warp reads 8 rows x 64 contiguous bytes), then a fixed-order tree over
+// the 256 lanes.  The order depends on the tile count only, so an image's statistics are the same bits in any batch.
+// (Round 2 first had one block per (image, group) with 4-byte loads 2G floats apart and four loads in flight: 32 us per
+// launch at 4096 tiles, 2-3 % of the whole encoder step.)
+constexpr int GNF_QUADS = 4, GNF_LANES = 256;
+__global__ void __launch_bounds__(GNF_QUADS * GNF_LANES) gn_finalize_kernel(const float* __restrict__ part,
+                                                                            double* __restrict__ stats, int tiles, int G) {
+    __shared__ double sh[GNF_LANES][GNF_QUADS][4];
+    const int n = blockIdx.y;
+    const int ql = threadIdx.x & (GNF_QUADS - 1), lane = threadIdx.x >> 2;
+    const int quad = blockIdx.x * GNF_QUADS + ql;          // 16-byte column group of the 2G-float row
+    const int row_f4 = G / 2;                              // float4 per row
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    if (quad < row_f4) {
+        const float4* p = reinterpret_cast<const float4*>(part) + (1LL * n * tiles) * row_f4 + quad;
+        int t = lane;
+        for (; t + 7 * GNF_LANES < tiles; t += 8 * GNF_LANES) {
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(p + 1LL * (t + i * GNF_LANES) * row_f4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[0] += static_cast<double>(v[i].x); a[1] += static_cast<double>(v[i].y);
+                a[2] += static_cast<double>(v[i].z); a[3] += static_cast<double>(v[i].w);
+            }
+        }
+        for (; t < tiles; t += GNF_LANES) {
+            const float4 v = __ldg(p + 1LL * t * row_f4);
+            a[0] += static_cast<double>(v.x); a[1] += static_cast<double>(v.y);
+            a[2] += static_cast<double>(v.z); a[3] += static_cast<double>(v.w);
+        }
     }
-    for (; t < tiles; t += 64) a0 += static_cast<double>(__ldg(p + 1LL * t * G * 2));
-    sh[threadIdx.x] = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sh[lane][ql][j] = a[j];
     __syncthreads();
-    for (int w = 32; w >= 1; w >>= 1) {
-        if (lane < w) sh[threadIdx.x] += sh[threadIdx.x + 2 * w];
+    for (int w = GNF_LANES / 2; w >= 1; w >>= 1) {
+        if (lane < w) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sh[lane][ql][j] += sh[lane + w][ql][j];
+        }
         __syncthreads();
     }
-    if (threadIdx.x < 2) stats[(1LL * n * G + g) * 2 + threadIdx.x] = sh[threadIdx.x];
+    if (lane == 0 && quad < row_f4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) stats[1LL * n * G * 2 + quad * 4 + j] = sh[0][ql][j];
+    }
 }
 
 int launch_gn_finalize(const float* part, double* stats, int N, int tiles, int G, cudaStream_t s, Profiler* prof) {
     VT_CHECK(part && stats && N > 0 && tiles > 0 && G > 0, "GroupNorm finalize: bad arguments");
     profiler_begin(prof, KC_GN_APPLY, s, 0, 8.0 * N * tiles * G);
-    gn_finalize_kernel<<<dim3(G, N), 128, 0, s>>>(part, stats, tiles, G);
+    VT_CHECK(G % 2 == 0, "GroupNorm finalize: odd group count");
+    gn_finalize_kernel<<<dim3((G / 2 + GNF_QUADS - 1) / GNF_QUADS, N), GNF_QUADS * GNF_LANES, 0, s>>>(part, stats, tiles, G);
     profiler_end(prof, KC_GN_APPLY, s);
     VT_CUDA(cudaGetLastError());
     return 0;
