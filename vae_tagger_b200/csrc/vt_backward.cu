@@ -73,8 +73,8 @@ __device__ __forceinline__ void gn8_load(Gn8& k, const double* stats, const floa
         k.be[e] = beta[c];
     }
 }
-// xhat and dt = dy * act'(t), t = gamma*xhat + beta.  FAST (16-bit mode): ex2 / rcp approximations -- their error is two
-// orders below the bf16 rounding of the gradient that is stored afterwards
+// xhat and dt = dy * act'(t), t = gamma*xhat + beta.  FAST (16-bit mode): tanh.approx (2^-11 relative) -- below the bf16
+// rounding (2^-9) of the gradient that is stored afterwards
 template <bool FAST>
 __device__ __forceinline__ void gn_dt(float x, float dy, float mean, float rstd, float ga, float be, int silu, float& xhat,
                                       float& dt) {
@@ -82,7 +82,14 @@ __device__ __forceinline__ void gn_dt(float x, float dy, float mean, float rstd,
     dt = dy;
     if (silu) {
         const float t = fmaf(ga, xhat, be);
-        const float sg = FAST ? __fdividef(1.0f, 1.0f + __expf(-t)) : 1.0f / (1.0f + expf(-t));
+        float sg;
+        if (FAST) {   // one MUFU: sigmoid(t) = 0.5 + 0.5 tanh(t/2)
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * t));
+            sg = fmaf(0.5f, th, 0.5f);
+        } else {
+            sg = 1.0f / (1.0f + expf(-t));
+        }
         dt = dy * sg * (1.0f + t * (1.0f - sg));
     }
 }
@@ -109,17 +116,32 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
     if (psub < ppb) {
         Gn8 k;
         gn8_load(k, stats, gamma, beta, n, c8 * 8, C, HW, eps);
-        for (long long p = p0 + psub; p < p1; p += ppb) {
+        // two pixels per trip: all four loads are issued before the first is used (same summation order as one
+        // pixel per trip)
+        for (long long p = p0 + psub; p < p1; p += 2 * ppb) {
             const long long off = (1LL * n * HW + p) * C + c8 * 8;
-            float xv[8], gv[8];
+            const bool two = p + ppb < p1;
+            const long long off2 = two ? off + 1LL * ppb * C : off;
+            float xv[8], gv[8], xw[8], gw[8];
             load8<XF>(x, off, xv);
             load8<GF>(dy, off, gv);
+            load8<XF>(x, off2, xw);
+            load8<GF>(dy, off2, gw);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 float xh, dt;
                 gn_dt<XF != FMT_F32>(xv[e], gv[e], k.mean[e], k.rstd[e], k.ga[e], k.be[e], silu, xh, dt);
                 a[e] += dt;
                 b[e] = fmaf(dt, xh, b[e]);
+            }
+            if (two) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float xh, dt;
+                    gn_dt<XF != FMT_F32>(xw[e], gw[e], k.mean[e], k.rstd[e], k.ga[e], k.be[e], silu, xh, dt);
+                    a[e] += dt;
+                    b[e] = fmaf(dt, xh, b[e]);
+                }
             }
         }
     }
@@ -214,12 +236,17 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
         s1[e] = gsum[(n * 32 + g) * 2] * inv_m;
         s2[e] = gsum[(n * 32 + g) * 2 + 1] * inv_m;
     }
-    for (long long p = p0 + psub; p < p1; p += ppb) {
+    for (long long p = p0 + psub; p < p1; p += 2 * ppb) {   // two pixels per trip, loads first
         const long long off = (1LL * n * HW + p) * C + c8 * 8;
-        float xv[8], gv[8], av[8], o[8];
+        const bool two = p + ppb < p1;
+        const long long off2 = two ? off + 1LL * ppb * C : off;
+        float xv[8], gv[8], av[8], xw[8], gw[8], aw[8], o[8];
         load8<XF>(x, off, xv);
         load8<GF>(dy, off, gv);
         if (add) load8<GF>(add, off, av);
+        load8<XF>(x, off2, xw);
+        load8<GF>(dy, off2, gw);
+        if (add) load8<GF>(add, off2, aw);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float xh, dt;
@@ -228,6 +255,16 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
             if (add) o[e] += av[e];
         }
         store8<GF>(dx, off, o);
+        if (two) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float xh, dt;
+                gn_dt<XF != FMT_F32>(xw[e], gw[e], k.mean[e], k.rstd[e], k.ga[e], k.be[e], silu, xh, dt);
+                o[e] = k.rstd[e] * (k.ga[e] * dt - (s1[e] + xh * s2[e]));
+                if (add) o[e] += aw[e];
+            }
+            store8<GF>(dx, off2, o);
+        }
     }
 }
 
