@@ -822,9 +822,10 @@ int bwd_conv_wgrad16(const BwdEnv& e, const void* dy, const void* a_src, int a_f
     }
     a_fmt = FMT_BF16;
     const WgradMnPlan p = bwd_wgrad_mn_plan(N, H, W, Cout, Cin, ks);
-    VT_TRY(bwd_conv_wgrad_mn(e, p, dy, FMT_BF16, a, a_fmt, part, N, H, W, Cout, Cin, ks, stride));
+    int splits = 0;
+    VT_TRY(bwd_conv_wgrad_mn(e, p, dy, FMT_BF16, a, a_fmt, part, N, H, W, Cout, Cin, ks, stride, &splits));
     const int taps = ks * ks;
-    wgrad_reduce_kernel<<<grid_for(1LL * Cout * Cin * taps), 256, 0, e.s>>>(part, dw, p.splits, Cout, Cin, taps, accumulate);
+    wgrad_reduce_kernel<<<grid_for(1LL * Cout * Cin * taps), 256, 0, e.s>>>(part, dw, splits, Cout, Cin, taps, accumulate);
     VT_CUDA(cudaGetLastError());
     return 0;
 }

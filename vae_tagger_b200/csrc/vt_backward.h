@@ -41,11 +41,12 @@ int bwd_conv_wgrad(const BwdEnv& e, const WgradPlan& p, const void* dy, const vo
 // ---- weight gradient straight from the NHWC tensors (vt_wgrad.cu): MN-major tcgen05 operands, taps = shifted TMA boxes
 struct WgradMnPlan {
     int tiles_x, tiles_y, col_groups, m_blocks, splits, per_split;
-    size_t part_bytes;      // fp32 split-K partial tiles [splits][Cout][taps*Cin]
+    int h_tiles_x, h_tiles_y, h_groups, h_splits, h_per_split;   // halo variant (3x3 stride 1)
+    size_t part_bytes;      // fp32 split-K partial tiles [splits][Cout][taps*Cin] (the larger of the two variants)
 };
 WgradMnPlan bwd_wgrad_mn_plan(int N, int H, int W, int Cout, int Cin, int ks);
 int bwd_conv_wgrad_mn(const BwdEnv& e, const WgradMnPlan& p, const void* dy, int y_fmt, const void* a, int a_fmt, float* part,
-                      int N, int H, int W, int Cout, int Cin, int ks, int stride);
+                      int N, int H, int W, int Cout, int Cin, int ks, int stride, int* splits_used);
 // 16-bit mode, whole weight gradient of one conv: the conv input as a bf16 NHWC operand in `a16` -- through
 // GroupNorm(+SiLU) when stats != null, a plain fp16 -> bf16 copy otherwise (both MMA operands must share one format and
 // the gradient side is bf16); a bf16 input is used as stored -- then the MN-major GEMM and the fixed-order reduce into
