@@ -549,6 +549,39 @@ __global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__
     }
 }
 
+// the same for 16-bit -> 16-bit (optionally fp16 -> bf16): 64x64 tiles moved as 32-bit pairs, so a warp reads and
+// writes 128 contiguous bytes per row (the 32x32 element-wise form above ran the T x T transposes of the attention
+// backward at 1.9 TB/s).  ld_in, ld_out even, 4-byte aligned bases.
+template <int FI, int FO>
+__global__ void __launch_bounds__(256) transpose16_kernel(const unsigned short* __restrict__ in, unsigned short* __restrict__ out,
+                                                          int rows, int cols, long long ld_in, long long ld_out, long long in_bs,
+                                                          long long out_bs) {
+    __shared__ uint32_t tile[64][33];
+    in += blockIdx.z * in_bs;
+    out += blockIdx.z * out_bs;
+    const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 64; i += 8) {
+        const int r = r0 + i, c = c0 + 2 * tx;
+        uint32_t v = 0;
+        if (r < rows) {
+            if (c + 1 < cols) v = *reinterpret_cast<const uint32_t*>(in + 1LL * r * ld_in + c);
+            else if (c < cols) v = in[1LL * r * ld_in + c];
+        }
+        if (FI == FMT_F16 && FO == FMT_BF16) v = pack_bf16x2(f16_lo(v), f16_hi(v));
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 64; i += 8) {
+        const int c = c0 + i, r = r0 + 2 * tx;
+        if (c >= cols || r >= rows) continue;
+        const uint32_t w0 = tile[2 * tx][i >> 1], w1 = tile[2 * tx + 1][i >> 1];
+        const uint32_t lo = (i & 1) ? (w0 >> 16) : (w0 & 0xFFFFu), hi = (i & 1) ? (w1 >> 16) : (w1 & 0xFFFFu);
+        if (r + 1 < rows) *reinterpret_cast<uint32_t*>(out + 1LL * c * ld_out + r) = lo | (hi << 16);
+        else out[1LL * c * ld_out + r] = static_cast<unsigned short>(lo);
+    }
+}
+
 // out[row] = sum_c a[row][c] * b[row][c]   (one warp per row)
 template <int FA, int FB>
 __global__ void __launch_bounds__(256) rowdot_kernel(const void* __restrict__ a, const void* __restrict__ b,
@@ -572,6 +605,55 @@ __global__ void __launch_bounds__(256) attn_ds_kernel(const void* __restrict__ P
         const long long q = i / tp;
         const int k = static_cast<int>(i - q * tp);
         st1<FO>(out, i, k < T ? ld1<FP>(P, i) * (dP[i] - D[q]) * scale : 0.f);
+    }
+}
+
+// 16-bit mode: the same in 64x64 tiles, sixteen elements per thread, writing dS AND its transpose (the operand of dK) in
+// one pass over P and dP.  tp % 64 == 0; rows / columns >= T of both outputs are zero (dS rows >= T are not written).
+__global__ void __launch_bounds__(256) attn_ds_t_kernel(const __half* __restrict__ P, const float* __restrict__ dP,
+                                                        const float* __restrict__ D, bf16* __restrict__ dS,
+                                                        bf16* __restrict__ dST, int T, long long tp, float scale) {
+    __shared__ uint32_t tile[64][33];
+    const int q0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+    const int row = threadIdx.x >> 2, seg = threadIdx.x & 3;
+    const int q = q0 + row, kb = k0 + seg * 16;
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = 0u;
+    if (q < T) {
+        const long long off = 1LL * q * tp + kb;
+        const uint4 p0 = *reinterpret_cast<const uint4*>(P + off), p1 = *reinterpret_cast<const uint4*>(P + off + 8);
+        float4 g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] = *reinterpret_cast<const float4*>(dP + off + 4 * j);
+        const float d = D[q];
+        const uint32_t pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        const float gv[16] = {g[0].x, g[0].y, g[0].z, g[0].w, g[1].x, g[1].y, g[1].z, g[1].w,
+                              g[2].x, g[2].y, g[2].z, g[2].w, g[3].x, g[3].y, g[3].z, g[3].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a = kb + 2 * j < T ? f16_lo(pw[j]) * (gv[2 * j] - d) * scale : 0.f;
+            const float b = kb + 2 * j + 1 < T ? f16_hi(pw[j]) * (gv[2 * j + 1] - d) * scale : 0.f;
+            w[j] = pack_bf16x2(a, b);
+        }
+        *reinterpret_cast<uint4*>(dS + off) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dS + off + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tile[row][seg * 8 + j] = w[j];
+    __syncthreads();
+    // thread (kk, seg): output row k0 + kk, columns q0 + 16 seg .. + 15 = tile rows 16 seg .. + 15, column kk
+    const int kk = threadIdx.x >> 2;
+    if (k0 + kk < T) {
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t a = tile[seg * 16 + 2 * j][kk >> 1], b = tile[seg * 16 + 2 * j + 1][kk >> 1];
+            o[j] = (kk & 1) ? ((a >> 16) | (b & 0xFFFF0000u)) : ((a & 0xFFFFu) | (b << 16));
+        }
+        bf16* dst = dST + 1LL * (k0 + kk) * tp + q0 + seg * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
     }
 }
 
@@ -693,6 +775,17 @@ __global__ void pad_channels_kernel(const float* __restrict__ in, void* __restri
 
 int bwd_transpose(const BwdEnv& e, const void* in, int in_fmt, void* out, int out_fmt, int rows, int cols, long long ld_in,
                   long long ld_out, int batch, long long in_bs, long long out_bs) {
+    if (in_fmt != FMT_F32 && out_fmt != FMT_F32 && ld_in % 2 == 0 && ld_out % 2 == 0 && in_bs % 2 == 0 && out_bs % 2 == 0 &&
+        reinterpret_cast<uintptr_t>(in) % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 4 == 0 &&
+        (in_fmt == out_fmt || (in_fmt == FMT_F16 && out_fmt == FMT_BF16))) {
+        dim3 g16((rows + 63) / 64, (cols + 63) / 64, batch);
+        const unsigned short* i16 = static_cast<const unsigned short*>(in);
+        unsigned short* o16 = static_cast<unsigned short*>(out);
+        if (in_fmt == out_fmt) transpose16_kernel<FMT_BF16, FMT_BF16><<<g16, 256, 0, e.s>>>(i16, o16, rows, cols, ld_in, ld_out, in_bs, out_bs);
+        else transpose16_kernel<FMT_F16, FMT_BF16><<<g16, 256, 0, e.s>>>(i16, o16, rows, cols, ld_in, ld_out, in_bs, out_bs);
+        VT_CUDA(cudaGetLastError());
+        return 0;
+    }
     dim3 grid((rows + 31) / 32, (cols + 31) / 32, batch);
 #define VT_TR(FI, FO) transpose_kernel<FI, FO><<<grid, 256, 0, e.s>>>(in, out, rows, cols, ld_in, ld_out, in_bs, out_bs)
     if (in_fmt == FMT_F32 && out_fmt == FMT_F32) VT_TR(FMT_F32, FMT_F32);
@@ -720,6 +813,17 @@ int bwd_attn_ds(const BwdEnv& e, const void* P, int p_fmt, const float* dP, cons
     if (e.fp32) attn_ds_kernel<FMT_F32, FMT_F32><<<grid, 256, 0, e.s>>>(P, dP, D, out, rows, T, tp, scale);
     else if (p_fmt == FMT_F16) attn_ds_kernel<FMT_F16, FMT_BF16><<<grid, 256, 0, e.s>>>(P, dP, D, out, rows, T, tp, scale);
     else { set_error("attention dS: format not instantiated"); return -2; }
+    VT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// 16-bit mode: dS and dS^T ([tp][tp] each, bf16) in one pass; P fp16, dP fp32
+int bwd_attn_ds_t(const BwdEnv& e, const void* P, int p_fmt, const float* dP, const float* D, void* dS, void* dST, int T, long long tp,
+                  float scale) {
+    VT_CHECK(!e.fp32 && p_fmt == FMT_F16 && tp % 64 == 0, "fused dS / dS^T pass: 16-bit mode, fp16 probabilities, padded to 64");
+    dim3 grid(static_cast<unsigned>(tp / 64), static_cast<unsigned>((T + 63) / 64));
+    attn_ds_t_kernel<<<grid, 256, 0, e.s>>>(static_cast<const __half*>(P), dP, D, static_cast<bf16*>(dS), static_cast<bf16*>(dST), T, tp,
+                                            scale);
     VT_CUDA(cudaGetLastError());
     return 0;
 }

@@ -62,6 +62,8 @@ int bwd_transpose(const BwdEnv& e, const void* in, int in_fmt, void* out, int ou
 int bwd_rowdot(const BwdEnv& e, const void* a, int a_fmt, const void* b, int b_fmt, float* out, long long rows, int cols);
 int bwd_attn_ds(const BwdEnv& e, const void* P, int p_fmt, const float* dP, const float* D, void* out, long long rows, int T,
                 long long tp, float scale);
+int bwd_attn_ds_t(const BwdEnv& e, const void* P, int p_fmt, const float* dP, const float* D, void* dS, void* dST, int T, long long tp,
+                  float scale);
 int bwd_pad_channels(const BwdEnv& e, const float* in, void* out, long long rows, int C, int Cp);
 // stride-2 downsample conv (diffusers Downsample2D: pad right / bottom, 3x3, stride 2), even input sizes
 size_t bwd_dgrad_s2_weight_bytes(const BwdEnv& e, int Cout, int Cin);

@@ -415,10 +415,14 @@ struct EncBwd {
                 g.K = C; g.out = S; g.out_fmt = FMT_F32; g.ab_f16 = 0;
                 VT_TRY(gemm(g));
             }
-            VT_TRY(bwd_attn_ds(e, P, of, static_cast<const float*>(S), D + 1LL * i * T, dS, T, static_cast<int>(T), tp, scale));
-            // transposes (square, zero padded) and the [C][tokens] views of q, k, dO
+            // dS, and the transposes (square, zero padded) and [C][tokens] views of q, k, dO
+            if (!e.fp32 && of == FMT_F16) {
+                VT_TRY(bwd_attn_ds_t(e, P, of, static_cast<const float*>(S), D + 1LL * i * T, dS, dST, static_cast<int>(T), tp, scale));
+            } else {
+                VT_TRY(bwd_attn_ds(e, P, of, static_cast<const float*>(S), D + 1LL * i * T, dS, T, static_cast<int>(T), tp, scale));
+                VT_TRY(bwd_transpose(e, dS, bfmt, dST, bfmt, static_cast<int>(T), static_cast<int>(T), tp, tp, 1, 0, 0));
+            }
             VT_TRY(bwd_transpose(e, P, of, PT, bfmt, static_cast<int>(T), static_cast<int>(T), tp, tp, 1, 0, 0));
-            VT_TRY(bwd_transpose(e, dS, bfmt, dST, bfmt, static_cast<int>(T), static_cast<int>(T), tp, tp, 1, 0, 0));
             VT_TRY(bwd_transpose(e, q_i, of, QT, bfmt, static_cast<int>(T), C, 2 * C, tp, 1, 0, 0));
             VT_TRY(bwd_transpose(e, q_i + static_cast<size_t>(C) * es, of, KT, bfmt, static_cast<int>(T), C, 2 * C, tp, 1, 0, 0));
             VT_TRY(bwd_transpose(e, dO_i, bfmt, dOT, bfmt, static_cast<int>(T), C, C, tp, 1, 0, 0));
