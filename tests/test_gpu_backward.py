@@ -240,3 +240,19 @@ def test_forwards_without_backward_do_not_leak_tape_slots():
     vae.encode(x).latent_dist.mean.square().sum().backward()
     k = "down_blocks.0.resnets.0.conv1.weight"
     assert rel(dict(vae.encoder.named_parameters())[k].grad, dict(oracle.encoder.named_parameters())[k].grad) < FP32_TOL
+
+
+def test_weight_gradient_box_form_agrees():
+    """VT_B200_NO_WGRAD_HALO=1 sends the 3x3 stride-1 weight gradients through the shifted-box kernel (the one the
+    stride-2 and 1x1 convs always use) instead of the halo-tile kernel; both must meet the same bars.  The switch is
+    read once per process, so the conv / ResnetBlock cases run again in a fresh interpreter."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e["VT_B200_NO_WGRAD_HALO"] = "1"
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_backward.py"), "-q", "-m", "gpu", "-x",
+                          "-k", "test_conv2d_backward or test_resnet_block_backward"], env=e, cwd=root, capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
