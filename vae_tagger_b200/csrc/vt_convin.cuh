@@ -45,7 +45,7 @@ struct ConvInCfg {
 struct ConvInParams {
     const void* img;   // [N][3][H][W] fp32 in [-1,1]  or  [N][H][W][3] u8
     int in_fmt;        // 0 fp32 NCHW, 1 u8 NHWC (normalised (u/255 - 0.5)/0.5 on the fly)
-    int vec;           // fp32 rows may be read as aligned float4 (W % 4 == 0, 16-byte aligned base)
+    int vec;           // rows may be read as aligned 16-byte vectors (fp32: W % 4 == 0, u8: W % 16 == 0; aligned base)
 };
 
 // Epilogue of one warp: accumulator rows 32q .. 32q+31 (pixels) x columns 64cg .. 64cg+63 (channels) of both sub-tiles.
@@ -259,14 +259,18 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         constexpr int NG = 32 * Cfg::GATHER_WARPS;
         constexpr int SW = Cfg::STRIP_W;
         const long long plane = static_cast<long long>(P.H) * P.W;
-        int stage = 0;
-        uint32_t phase = 0, it = 0;
         // image rows y-1 .. y+1, columns x0-1 .. x0+256, three channels of a tile: loaded into registers one tile
         // AHEAD (the loads of tile t+1 are in flight while tile t's operand rows are built), then written to the
-        // fp16 strip [kh*3+c][x] of the tile
+        // fp16 strip [kh*3+c][x] of the tile.  The loop is specialised per input mode (0 fp32 float4, 1 fp32 scalar,
+        // 2 u8 16-byte units, 3 u8 scalar) so that only one mode's staging registers are live across it.
+        auto gather = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        int stage = 0;
+        uint32_t phase = 0, it = 0;
         float v[27];
         float4 vq[5];
         unsigned char u[21];
+        uint4 uq[2];          // u8 vector path: 16 consecutive bytes of a row (5 1/3 pixels) per unit, 144 units per tile
         const int c4 = gt & 63, rsel = gt >> 6;   // float4 path: column quad / row parity of this thread's units
         auto coords = [&](uint32_t tile, int& x0, int& y, int& img) {
             const int tx = static_cast<int>(tile % static_cast<uint32_t>(P.tiles_x));
@@ -278,7 +282,7 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         auto load_tile = [&](uint32_t tile) {
             int x0, y, img;
             coords(tile, x0, y, img);
-            if (Q.in_fmt == 0 && Q.vec) {
+            if constexpr (MODE == 0) {
                 // 9 rows x 64 aligned float4 (columns x0 .. x0+255) = 4.5 loads per thread, + the two edge columns
                 const float* src = static_cast<const float*>(Q.img) + 3LL * img * plane;
                 const int iplane = static_cast<int>(plane);
@@ -299,7 +303,7 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                     const int gy = y + kh - 1, gx = (e & 1) ? x0 + 256 : x0 - 1;
                     if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) v[0] = __ldg(src + (c * iplane + gy * P.W + gx));
                 }
-            } else if (Q.in_fmt == 0) {
+            } else if constexpr (MODE == 1) {
                 const float* src = static_cast<const float*>(Q.img) + 3LL * img * plane;
 #pragma unroll
                 for (int rowid = 0; rowid < 9; ++rowid) {
@@ -314,6 +318,24 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                         if (y_ok && xx < 258 && gx >= 0 && gx < P.W) t = __ldg(rowp + xx);
                         v[rowid * 3 + part] = t;
                     }
+                }
+            } else if constexpr (MODE == 2) {
+                // u8 NHWC, W % 16 == 0: the 768 bytes of pixels x0 .. x0+255 of a row are 48 aligned 16-byte units
+                const unsigned char* src = static_cast<const unsigned char*>(Q.img) + 3LL * img * plane;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int unit = gt + NG * k;             // < 144: rows kh = unit / 48
+                    const int kh = unit / 48, j = unit - 48 * kh;
+                    const int gy = y + kh - 1;
+                    uq[k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (unit < 144 && gy >= 0 && gy < P.H && x0 * 3 + 16 * j < P.W * 3)
+                        uq[k] = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<long long>(gy) * P.W + x0) * 3 + 16 * j));
+                }
+                u[0] = 0;
+                if (gt >= 32 && gt < 50) {                    // the two edge pixels of the three rows
+                    const int e = gt - 32, kh = e / 6, side = (e / 3) & 1, c = e - 3 * (e / 3);
+                    const int gy = y + kh - 1, gx = side ? x0 + 256 : x0 - 1;
+                    if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) u[0] = __ldg(src + (static_cast<long long>(gy) * P.W + gx) * 3 + c);
                 }
             } else {
                 const unsigned char* src = static_cast<const unsigned char*>(Q.img) + 3LL * img * plane;
@@ -333,7 +355,7 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             }
         };
         auto store_strip = [&](uint32_t tile, __half* strip) {
-            if (Q.in_fmt == 0 && Q.vec) {
+            if constexpr (MODE == 0) {
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
                     if (j == 4 && rsel != 0) break;
@@ -347,7 +369,7 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                     const int e = gt - 64;
                     strip[(e >> 1) * SW + ((e & 1) ? 260 : 3)] = __float2half_rn(v[0]);
                 }
-            } else if (Q.in_fmt == 0) {
+            } else if constexpr (MODE == 1) {
 #pragma unroll
                 for (int rowid = 0; rowid < 9; ++rowid)
 #pragma unroll
@@ -355,6 +377,32 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                         const int xx = gt + NG * part;
                         if (xx < 258) strip[rowid * SW + xx + 3] = __float2half_rn(v[rowid * 3 + part]);
                     }
+            } else if constexpr (MODE == 2) {
+                int x0, y, img;
+                coords(tile, x0, y, img);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int unit = gt + NG * k;
+                    if (unit >= 144) break;
+                    const int kh = unit / 48, j = unit - 48 * kh;
+                    const int gy = y + kh - 1;
+                    const bool ok = gy >= 0 && gy < P.H && x0 * 3 + 16 * j < P.W * 3;
+                    const uint32_t w4[4] = {uq[k].x, uq[k].y, uq[k].z, uq[k].w};
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int b = 16 * j + i, px = b / 3, c = b - 3 * px;
+                        const float uv = static_cast<float>((w4[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+                        const float val = ok ? (uv / 255.0f - 0.5f) / 0.5f : 0.f;
+                        strip[(kh * 3 + c) * SW + 4 + px] = __float2half_rn(val);
+                    }
+                }
+                if (gt >= 32 && gt < 50) {
+                    const int e = gt - 32, kh = e / 6, side = (e / 3) & 1, c = e - 3 * (e / 3);
+                    const int gy = y + kh - 1, gx = side ? x0 + 256 : x0 - 1;
+                    const bool ok = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+                    const float val = ok ? (static_cast<float>(u[0]) / 255.0f - 0.5f) / 0.5f : 0.f;
+                    strip[(kh * 3 + c) * SW + (side ? 260 : 3)] = __float2half_rn(val);
+                }
             } else {
                 int x0, y, img;
                 coords(tile, x0, y, img);
@@ -405,6 +453,14 @@ conv_in_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             fence_proxy_async_smem();
             mbar_arrive(&a_full[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        };
+        if (Q.in_fmt == 0) {
+            if (Q.vec) gather(std::integral_constant<int, 0>{});
+            else gather(std::integral_constant<int, 1>{});
+        } else {
+            if (Q.vec) gather(std::integral_constant<int, 2>{});
+            else gather(std::integral_constant<int, 3>{});
         }
     }
 

@@ -306,7 +306,7 @@ int launch_conv_in(const ConvInOp& op, cudaStream_t stream, Profiler* prof) {
     }
     VT_CHECK(3LL * op.H * op.W < (1LL << 31), "conv_in image exceeds 2^31 elements");
     ConvInParams Q{op.img, op.in_fmt,
-                   (op.in_fmt == 0 && op.W % 4 == 0 && reinterpret_cast<uintptr_t>(op.img) % 16 == 0) ? 1 : 0};
+                   (op.W % (op.in_fmt == 0 ? 4 : 16) == 0 && reinterpret_cast<uintptr_t>(op.img) % 16 == 0) ? 1 : 0};
     static SmemAttrOnce once;
     VT_TRY(ensure_dyn_smem(once, conv_in_kernel, ConvInCfg::SMEM_BYTES));
     const long long tiles = 1LL * P.NB * P.tiles_x * P.tiles_y;

@@ -3,10 +3,10 @@
 // VAE (train_full.py:201-256: triplet / contrastive loss on posterior samples; train_vae.py:124-186).  Included by
 // vt_api.cu behind the encoder schedule (EncRun, run_attention, AttnPlan).  Same kernels and formats as inference for
 // the forward; the backward is built from vt_backward.cu:
-//   conv 3x3 / 1x1 stride 1 ... bwd_conv_dgrad (forward tcgen05 kernel on flipped weights) + bwd_conv_wgrad (split-K GEMM
-//                               over pixel planes)
+//   conv 3x3 / 1x1 stride 1 ... bwd_conv_dgrad (forward tcgen05 kernel on flipped weights) + bwd_conv_wgrad16 (vt_wgrad.cu:
+//                               MN-major tcgen05 GEMM over the pixels, split-K with a fixed-order reduce)
 //   Downsample2D (stride 2) ... bwd_conv_s2_dgrad (sub-pixel form: four 2x2-tap convs of the output gradient) +
-//                               bwd_conv_s2_wgrad (parity planes of the input)
+//                               bwd_conv_wgrad16 on the (2C, W/2, 2, H/2, N) parity view of the input
 //   GroupNorm(+SiLU) .......... bwd_group_norm (the residual / shortcut gradient is added in its apply pass)
 //   attention ................. scores and probabilities are rebuilt per image (S = q k^T, P = softmax), then
 //                               dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(dO o O)) / sqrt(C), dQ = dS K, dK = dS^T Q
