@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--images", type=int, default=512)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--tags", type=int, default=1000)
+    ap.add_argument("--repeat", type=int, default=5)
     a = ap.parse_args()
     torch.manual_seed(0)
     wrap = L.DiffusersVAEWrapper(L.load_diffusers_vae_from_config(L.get_diffusers_vae_config())).cuda().eval()
@@ -56,15 +57,19 @@ def main():
         return done, mpx_out
 
     run(3 * len(pool))  # warm-up: every bucket's workspace, coefficient tables, head parameters
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    done, mpx_out = run(a.images)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    run(a.images)       # and once more with the timed stream itself (full batches: the largest workspaces)
+    times = []
+    for _ in range(a.repeat):   # wall clock of a 1-3 s host-driven loop is noisy on a shared box: report the median
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        done, mpx_out = run(a.images)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    dt = sorted(times)[len(times) // 2]
     src_mpx = sum(p.shape[0] * p.shape[1] for p in pool) / len(pool) / 1e6
     print(json.dumps({"metric": "images/s mixed-bucket pipeline (uint8 host photos -> GPU SmartResize -> encode+tag)",
                       "images": done, "batch": a.batch, "buckets_used": len(decs), "value": round(done / dt, 1),
-                      "seconds": round(dt, 3), "mean_source_mpx": round(src_mpx, 2),
+                      "seconds": round(dt, 3), "seconds_all": [round(t, 3) for t in times], "mean_source_mpx": round(src_mpx, 2),
                       "mean_bucket_mpx": round(mpx_out / done, 3), "h2d_bytes_per_image": int(src_mpx * 3e6)}))
 
 
